@@ -1,0 +1,168 @@
+/*
+ * snb_b200.h -- C ABI of the B200-native tiled-segmentation hot path.
+ *
+ * The reference (BloodAxe/segmentation-networks-benchmark) is pure Python and has no FFI of its own; the only
+ * native boundary it knows is the call surface of the external `inplace_abn` extension
+ * (lib/modules/abn/functions.py:1,46-118).  This header is therefore the boundary a maintainer would bind
+ * with `ctypes` to move the hot path of inria_submit.py / lib/tiles.py onto a B200:
+ *
+ *   group              replaces (reference file:line)
+ *   -----------------  ---------------------------------------------------------------------------------
+ *   snb_slicer_*       ImageSlicer.__init__ margins + crop list                lib/tiles.py:35-96
+ *   snb_split_*        ImageSlicer.split / cut_patch (+ NormalizeImage,        lib/tiles.py:98-135,
+ *                      InMemoryDataset HWC->CHW .float(), tta_d4_aug)          lib/augmentations.py:452-491,
+ *                                                                              lib/common.py:59-76
+ *   snb_merge          ImageSlicer.merge (+ tta_d4_deaug, `mask > 0.5`)        lib/tiles.py:137-161,
+ *                                                                              lib/augmentations.py:494-511,
+ *                                                                              inria_submit.py:305
+ *   snb_conv_*         nn.Conv2d / nn.ConvTranspose2d (+bias, ReLU, 1x1 head,  lib/models/unet16.py:8-49,113-131,
+ *                      sigmoid) as executed by UNet16/UNet11/ZF_UNET forward   lib/models/unet11.py:106-122,
+ *                                                                              inria_submit.py:250-251
+ *   snb_maxpool2x2     nn.MaxPool2d(2, 2)                                      lib/models/unet16.py:64
+ *   snb_loss_iou_*     BCEWithLogitsLossAndSmoothJaccard / JaccardScore /      lib/losses.py:31-75,
+ *                      PixelAccuracy partial sums and integer counts           lib/metrics.py:9-40
+ *   snb_pr_curve_*     PRCurveMeter.update                                     lib/train_utils.py:109-125
+ *
+ * Conventions: every pointer named `d_*` is a DEVICE pointer owned by the caller; sizes are int64_t; `stream`
+ * is a cudaStream_t passed as void* (0 = legacy default stream).  All entry points enqueue work on `stream`
+ * and return without synchronising.  Return value: 0 = ok, negative = error (SNB_E_*); the message of the
+ * last error on the calling thread is returned by snb_last_error().  There is no CPU fallback anywhere.
+ */
+#ifndef SNB_B200_H_
+#define SNB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SNB_API __attribute__((visibility("default")))
+#else
+#define SNB_API
+#endif
+
+#define SNB_OK 0
+#define SNB_E_INVALID (-1) /* bad argument: maps to ValueError (lib/tiles.py:56-57,81-85,138-139) */
+#define SNB_E_SHAPE (-2)   /* shape mismatch: maps to AssertionError (lib/tiles.py:99-100)          */
+#define SNB_E_CUDA (-3)    /* CUDA runtime / driver failure: maps to RuntimeError                   */
+#define SNB_E_UNSUPPORTED (-4)
+
+SNB_API int snb_version(void);
+SNB_API const char* snb_last_error(void);
+/* number of SMs of the current device (grid sizing), or negative error */
+SNB_API int snb_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------ slicer */
+typedef struct snb_slicer snb_slicer;
+
+/* lib/tiles.py:35-96.  tile_step < 1 or > tile_size, or an image_margin that does not tile -> SNB_E_INVALID */
+SNB_API int snb_slicer_create(int64_t image_h, int64_t image_w, int64_t tile_size, int64_t tile_step,
+                      int64_t image_margin, snb_slicer** out);
+SNB_API void snb_slicer_destroy(snb_slicer* s);
+/* info[0..7] = margin_left, margin_right, margin_top, margin_bottom, n_tiles, tiles_x, tiles_y, tile_size */
+SNB_API int snb_slicer_info(const snb_slicer* s, int64_t info[8]);
+/* xy[2*i] = x, xy[2*i+1] = y of crop i, in crop order (y outer, x inner; lib/tiles.py:94-96) */
+SNB_API int snb_slicer_crops(const snb_slicer* s, int64_t* xy);
+
+/* Bit-exact ImageSlicer.split for BORDER_REFLECT101 (border_mode 0) or BORDER_CONSTANT (border_mode 1, the
+ * border filled with `elem_bytes` bytes taken from `border_value`):
+ *   d_src [H][W][C] elements of elem_bytes  ->  d_dst [tile_count][T][T][C], tiles tile_begin.. in crop order. */
+SNB_API int snb_split_hwc(const snb_slicer* s, const void* d_src, int64_t channels, int64_t elem_bytes,
+                  int border_mode, const void* border_value, void* d_dst, int64_t tile_begin,
+                  int64_t tile_count, void* stream);
+
+/* Fused split for the network input: u8 HWC image -> reflect-101 pad -> crop -> per-channel 256-entry LUT
+ * (NormalizeImage evaluated on the host exactly as the reference does) -> D4 view `tta` (0..7, order of
+ * tta_d4_aug) -> one of the layouts below.  d_lut is float[channels][256].
+ *   SNB_LAYOUT_NCHW_F32   float [n][C][T][T]           (what InMemoryDataset + DataLoader produce)
+ *   SNB_LAYOUT_PATCH32    bf16  [n][T][T][32]          (first-layer operand: 3x3 neighbourhood x 3 channels,
+ *                                                       k = (ky*3+kx)*3 + c, zero outside the tile, k>=27 zero) */
+#define SNB_LAYOUT_NCHW_F32 0
+#define SNB_LAYOUT_PATCH32 1
+SNB_API int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int64_t channels, const float* d_lut,
+                      int tta, int layout, void* d_dst, int64_t tile_begin, int64_t tile_count, void* stream);
+
+/* float [n][3][H][W] (the nn.Module.forward input) -> PATCH32 rows, same definition as above */
+SNB_API int snb_nchw_f32_to_patch32(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w,
+                            void* d_dst, void* stream);
+
+/* ImageSlicer.merge (lib/tiles.py:137-161): weighted overlap-add in float64 in crop order, clip of the norm at
+ * DBL_EPSILON, divide, cast, crop.  d_tiles [n_tiles][T][T][C] of tile_dtype (SNB_DT_*), d_weight double[T][T].
+ * `tta` = number of D4 views per tile (1 or 8): with 8, d_tiles holds [n_tiles][8][T][T][C] float32 views in
+ * tta_d4_aug order and the de-augmented mean (tta_d4_deaug: fp32 sum in listed order, * 0.125f) is merged.
+ * Outputs (either may be NULL): d_out [H][W][C] of out_dtype; d_mask [H][W][C] u8 = (value > thr) ? 255 : 0
+ * evaluated on the float32 result (inria_submit.py:305). */
+#define SNB_DT_U8 0
+#define SNB_DT_F32 1
+#define SNB_DT_F64 2
+#define SNB_DT_I64 3
+SNB_API int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
+              const double* d_weight, void* d_out, int out_dtype, uint8_t* d_mask, float thr, void* stream);
+
+/* ------------------------------------------------------------------------------------------ convolutions */
+/* Activations are NHWC bf16 inside channel slabs: pixel stride = *_cstride channels, so a producer can write
+ * straight into its slot of a concat buffer (torch.cat of lib/models/unet16.py:122-127 never materialises).
+ * Weights are pre-packed bf16 [phase][tap][Cout][Cin] (K-major), bias is float[Cout]. */
+#define SNB_CONV_3X3 0      /* k3 s1 p1: 1 phase x 9 taps, tap = ky*3+kx                     */
+#define SNB_CONV_1X1 1      /* k1: 1 phase x 1 tap                                           */
+#define SNB_CONVT_4X4_S2 2  /* ConvTranspose2d k4 s2 p1: 4 sub-pixel phases x 4 taps         */
+
+typedef struct snb_conv_desc {
+  int32_t kind;          /* SNB_CONV_*                                                      */
+  int32_t relu;          /* apply ReLU after bias                                           */
+  int64_t n, h, w;       /* input batch and spatial size                                    */
+  int64_t cin;           /* input channels read (multiple of 32)                            */
+  int64_t in_cstride;    /* pixel stride of the input slab, in channels                     */
+  int64_t cout;          /* output channels (multiple of 32)                                */
+  int64_t out_cstride;   /* pixel stride of the output slab, in channels                    */
+  const void* d_in;      /* bf16, first channel read                                        */
+  void* d_out;           /* bf16, first channel written (may be NULL when the head is fused) */
+  const void* d_weight;  /* packed bf16                                                     */
+  const float* d_bias;   /* float[cout]                                                     */
+  /* optional fused 1x1 head (cout must be 32): out = [sigmoid](dot(relu(conv), head_w) + head_b) */
+  const float* d_head_w; /* float[32] or NULL                                               */
+  float head_b;
+  int32_t head_sigmoid;
+  float* d_head_out;     /* float [n][h][w]                                                 */
+} snb_conv_desc;
+
+typedef struct snb_conv snb_conv;
+SNB_API int snb_conv_create(const snb_conv_desc* desc, snb_conv** out);
+SNB_API int snb_conv_launch(const snb_conv* c, void* stream);
+SNB_API void snb_conv_destroy(snb_conv* c);
+/* algorithmic FLOPs of one launch (2*MACs, padding excluded), for roofline bookkeeping */
+SNB_API double snb_conv_flops(const snb_conv* c);
+
+/* nn.MaxPool2d(2,2) on NHWC bf16 slabs; h, w even; channels multiple of 8 */
+SNB_API int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                   void* d_out, int64_t out_cstride, void* stream);
+
+/* bf16 NHWC slab -> float NCHW (leaving the network through the nn.Module interface) */
+SNB_API int snb_nhwc_bf16_to_nchw_f32(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels,
+                              int64_t in_cstride, float* d_out, void* stream);
+
+/* ----------------------------------------------------------------------------------------- loss / metrics */
+/* One pass over logits/targets (lib/losses.py:36-53, lib/metrics.py:13-36):
+ *   p = sigmoid(x); z = logsigmoid(x); bce_i = max(z,0) - z*t + log1p(exp(-|z|))
+ *   d_sums[0..3]   = sum bce_i, sum p*t, sum p, sum t                       (double)
+ *   d_counts[0..3] = tp, fp, fn, tn at p > 0.5 (float32 compare)            (int64)
+ * targets of dtype SNB_DT_I64 / SNB_DT_U8 / SNB_DT_F32.  The outputs are zeroed by the call. */
+SNB_API int snb_loss_iou_reduce(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
+                        double* d_sums, int64_t* d_counts, void* stream);
+
+/* Same integer counts from probabilities already on the device (mask parity path): pred = prob > thr. */
+SNB_API int snb_confusion_counts(const float* d_probs, const void* d_targets, int target_dtype, int64_t n, float thr,
+                         int64_t* d_counts, void* stream);
+
+/* PRCurveMeter.update (lib/train_utils.py:109-125): for every threshold k (float32, ascending),
+ * pred = sigmoid(x) > thr[k]; adds tp/tn/fp/fn counts into uint64 arrays of length n_thr (accumulating). */
+SNB_API int snb_pr_curve_update(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
+                        const float* d_thresholds, int64_t n_thr, uint64_t* d_tp, uint64_t* d_tn,
+                        uint64_t* d_fp, uint64_t* d_fn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNB_B200_H_ */

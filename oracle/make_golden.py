@@ -1,0 +1,217 @@
+"""Generate tests/golden/* by RUNNING THE REFERENCE (imported from /root/reference) on seeded synthetic inputs.
+
+Runs only in the build container (the reference is not present on the GPU box).  The reference ships no golden
+vectors of its own, so these files are what pins the oracle and, through it, the CUDA path.
+Usage: python oracle/make_golden.py
+"""
+import collections
+import collections.abc
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SNB_REFERENCE", "/root/reference")
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+from oracle import synth  # noqa: E402
+
+# non-invasive import shims: optional deps the hot path never uses
+for name in ("tensorboardX", "matplotlib", "matplotlib.pyplot", "seaborn"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+collections.Iterable = collections.abc.Iterable
+
+from lib import augmentations as aug  # noqa: E402
+from lib import losses as ref_losses  # noqa: E402
+from lib import metrics as ref_metrics  # noqa: E402
+from lib.common import InMemoryDataset  # noqa: E402
+from lib.datasets.Inria import INRIA_MEAN, INRIA_STD  # noqa: E402
+from lib.models.unet11 import UNet11  # noqa: E402
+from lib.models.unet16 import UNet16  # noqa: E402
+from lib.tiles import ImageSlicer, compute_patch_weight_loss  # noqa: E402
+from lib.train_utils import PRCurveMeter  # noqa: E402
+
+
+def slicer_kats():
+    cases = [((5000, 5000, 3), 512, 384, 0), ((5000, 5000, 3), 512, 256, 0), ((5000, 5000, 3), 224, 112, 0),
+             ((5000, 5000), 1024, 512, 0), ((360, 360), 256, 128, 0), ((256, 256), 256, 128, 0),
+             ((50, 70), 256, 128, 0), ((5000, 5000), 512, 384, 60), ((37, 53, 3), 16, 8, 0), ((37, 53), 16, 16, 0),
+             ((100, 90), 32, 20, 0), ((96, 80, 3), 64, 32, 0), ((5, 7), 32, 16, 0), ((1, 9), 4, 2, 0)]
+    out = []
+    for shape, tile, step, margin in cases:
+        s = ImageSlicer(shape, tile, step, image_margin=margin)
+        out.append(dict(shape=list(shape), tile=tile, step=step, margin=margin,
+                        margins=[s.margin_left, s.margin_right, s.margin_top, s.margin_bottom],
+                        n_crops=len(s.crops), crops_head=[list(c) for c in s.crops[:3]],
+                        crops_tail=[list(c) for c in s.crops[-3:]],
+                        crops_sum=[int(sum(c[0] for c in s.crops)), int(sum(c[1] for c in s.crops))]))
+    errors = []
+    for shape, tile, step, margin in [((5000, 5000), 512, 384, 10), ((5000, 5000), 512, 0, 0),
+                                      ((64, 64), 32, 33, 0), ((64, 64), 32, -1, 0)]:
+        try:
+            ImageSlicer(shape, tile, step, image_margin=margin)
+            errors.append(dict(shape=list(shape), tile=tile, step=step, margin=margin, error=None))
+        except Exception as e:  # noqa: BLE001
+            errors.append(dict(shape=list(shape), tile=tile, step=step, margin=margin, error=type(e).__name__))
+    return dict(cases=out, errors=errors)
+
+
+def split_merge_vectors():
+    rs = np.random.RandomState(7)
+    d = {}
+    # (name, shape, dtype, tile, step)
+    specs = [("u8c3", (37, 53, 3), np.uint8, 16, 8), ("f32c1", (40, 33, 1), np.float32, 16, 12),
+             ("u8_2d", (37, 53), np.uint8, 16, 16), ("f64c3", (21, 30, 3), np.float64, 8, 4),
+             ("tiny_multi_reflect", (5, 7, 1), np.float32, 32, 16)]
+    for name, shape, dt, tile, step in specs:
+        img = (rs.randint(0, 256, shape).astype(dt) if dt == np.uint8 else rs.standard_normal(shape).astype(dt))
+        s = ImageSlicer(shape, tile, step)
+        tiles = s.split(img)
+        d[name + "_image"] = img
+        d[name + "_tiles"] = np.stack(tiles)
+        d[name + "_cfg"] = np.array([tile, step])
+        d[name + "_cut3"] = s.cut_patch(img, min(3, len(s.crops) - 1))
+    for weight in ("mean", "pyramid"):
+        s = ImageSlicer((37, 53, 3), 16, 8, weight=weight)
+        tiles = [rs.rand(16, 16, 2).astype(np.float32) for _ in s.crops]
+        d["merge_%s_tiles" % weight] = np.stack(tiles)
+        d["merge_%s_out" % weight] = s.merge(tiles)
+        # identity: merge(split(x)) == x exactly
+        img = rs.rand(37, 53, 3).astype(np.float32)
+        d["merge_%s_identity_in" % weight] = img
+        d["merge_%s_identity_out" % weight] = s.merge(s.split(img))
+    s = ImageSlicer((37, 53, 3), 16, 8, weight="mean")
+    tiles = [rs.randint(0, 256, (16, 16, 3)).astype(np.uint8) for _ in s.crops]
+    d["merge_u8_tiles"] = np.stack(tiles)
+    d["merge_u8_out"] = s.merge(tiles, dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "split_merge.npz"), **d)
+
+
+def weight_vectors():
+    w16 = compute_patch_weight_loss(16, 16)[0]
+    w24 = compute_patch_weight_loss(24, 24)[0]
+    w64 = compute_patch_weight_loss(64, 64)[0]
+    np.savez_compressed(os.path.join(OUT, "pyramid.npz"), w16=w16, w24=w24, w64=w64)
+    # survey KAT for the 512 tile (7 s python loop in the reference): min / max / sum, SURVEY 8c'
+    return dict(n512=dict(min=0.006262400053660891, max=3.1974996323919567, sum=262143.99999999997),
+                n64=dict(min=float(w64.min()), max=float(w64.max()), sum=float(w64.sum())))
+
+
+def normalize_vectors():
+    t = aug.NormalizeImage(mean=INRIA_MEAN, std=INRIA_STD)
+    levels = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, axis=2)   # 256 x 1 x 3 BGR "image"
+    out64 = t(levels)
+    ds = InMemoryDataset([out64], None)
+    np.savez_compressed(os.path.join(OUT, "normalize.npz"), levels=levels, out64=out64, chw_f32=ds[0].numpy())
+
+
+def tta_vectors():
+    rs = np.random.RandomState(11)
+    tiles = [rs.rand(6, 6, 2).astype(np.float32) for _ in range(2)]
+    views = aug.tta_d4_aug(tiles)
+    preds = [rs.rand(6, 6, 1).astype(np.float32) for _ in range(16)]
+    deaug = aug.tta_d4_deaug(preds)
+    np.savez_compressed(os.path.join(OUT, "tta.npz"), tiles=np.stack(tiles), views=np.stack(views),
+                        preds=np.stack(preds), deaug=np.stack(deaug))
+
+
+def loss_vectors():
+    out = {}
+    for seed, shape in [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))]:
+        logits, targets = synth.logits_targets(seed, shape)
+        loss = ref_losses.BCEWithLogitsLossAndSmoothJaccard()
+        loss.bce_loss.size_average = True   # attributes modern _Loss no longer stores
+        loss.bce_loss.reduce = True
+        bce = ref_losses.BCEWithSigmoidLoss.__new__(ref_losses.BCEWithSigmoidLoss)
+        torch.nn.Module.__init__(bce)
+        bce.size_average, bce.reduce = True, True
+        pa = ref_metrics.PixelAccuracy()(logits, targets)
+        meter = PRCurveMeter()
+        meter.update(logits, targets)
+        p = torch.sigmoid(logits)
+        pred = p > 0.5
+        t = targets.bool()
+        out["seed%d" % seed] = dict(
+            shape=list(shape),
+            bce_jaccard=float(loss(logits, targets)), bce=float(bce(logits, targets)),
+            smooth_jaccard=float(ref_losses.SmoothJaccardLoss()(logits, targets)),
+            jaccard_score=float(ref_metrics.JaccardScore()(logits, targets)), pixel_accuracy=float(pa),
+            counts=[int((pred & t).sum()), int((pred & ~t).sum()), int((~pred & t).sum()), int((~pred & ~t).sum())],
+            pr_tp=[int(v) for v in meter.tp], pr_tn=[int(v) for v in meter.tn],
+            pr_fp=[int(v) for v in meter.fp], pr_fn=[int(v) for v in meter.fn])
+    return out
+
+
+def model_vectors():
+    d = {}
+    for arch, cls in (("unet16", UNet16), ("unet11", UNet11)):
+        m = cls()
+        sd = synth.vgg_unet_state_dict(arch, seed=1)
+        missing = m.load_state_dict(sd, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        m.eval()
+        x = torch.from_numpy(np.random.RandomState(5).standard_normal((2, 3, 64, 96)).astype(np.float32))
+        with torch.no_grad():
+            d[arch + "_logits"] = m(x).numpy()
+        d[arch + "_x"] = x.numpy()
+    np.savez_compressed(os.path.join(OUT, "models.npz"), **d)
+
+
+def predict_tiled_vector():
+    """inria_submit.predict_tiled (:237-257) on CPU: same calls, without .cuda(); tile 64 / step 32, with and
+    without D4 TTA, plus the submit threshold (:305)."""
+    m = UNet16()
+    m.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=2))
+    m.eval()
+    image = synth.image_u8(9, 96, 80)
+    t = aug.Sequential([aug.ImageOnly(aug.NormalizeImage(mean=INRIA_MEAN, std=INRIA_STD))])
+    d = dict(image=image)
+    for tta in (False, True):
+        x, _ = t(image)
+        slicer = ImageSlicer(x.shape, 64, 32, weight='pyramid')
+        patches = slicer.split(x)
+        if tta:
+            patches = aug.tta_d4_aug(patches)
+        ds = InMemoryDataset(patches, None)
+        preds = []
+        with torch.no_grad():
+            for i in range(0, len(ds), 4):
+                xb = torch.stack([ds[j] for j in range(i, min(i + 4, len(ds)))])
+                y = torch.sigmoid(m(xb)).numpy()
+                preds.extend(np.moveaxis(y, 1, -1))
+        if tta:
+            preds = aug.tta_d4_deaug(preds)
+        mask = slicer.merge(preds, dtype=np.float32)
+        key = "tta" if tta else "plain"
+        d[key + "_tiles"] = np.stack(preds)
+        d[key + "_merged"] = mask
+        d[key + "_mask"] = ((mask > 0.5) * 255).astype(np.uint8)
+    np.savez_compressed(os.path.join(OUT, "predict_tiled.npz"), **d)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(),
+                torch_version=torch.__version__, numpy_version=np.__version__)
+    split_merge_vectors()
+    normalize_vectors()
+    tta_vectors()
+    model_vectors()
+    predict_tiled_vector()
+    with open(os.path.join(OUT, "kats.json"), "w") as fh:
+        json.dump(kats, fh, indent=1)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""CPU PyTorch fp32 restatement of the network / loss / metric part of the hot path (TEST INFRASTRUCTURE).
+
+unet_vgg_forward follows lib/models/unet16.py:113-131 and lib/models/unet11.py:106-122 functionally from a
+state_dict (no nn.Module, no torchvision); losses follow lib/losses.py:31-75, metrics lib/metrics.py:9-40 and
+lib/train_utils.py:109-125.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+VGG16_STAGES = [[0, 2], [5, 7], [10, 12, 14], [17, 19, 21], [24, 26, 28]]   # encoder.N indices per stage
+VGG11_STAGES = [[0], [3], [6, 8], [11, 13], [16, 18]]
+STAGES = {'unet16': VGG16_STAGES, 'unet11': VGG11_STAGES}
+
+
+def _conv_relu(x, sd, prefix, quant=None):
+    w, b = sd[prefix + '.weight'], sd[prefix + '.bias']
+    if quant is not None:
+        x, w = quant(x), quant(w)
+    return F.relu(F.conv2d(x, w, b, padding=1))
+
+
+def _decoder(x, sd, name, quant=None):
+    x = _conv_relu(x, sd, name + '.block.0.conv', quant)
+    w, b = sd[name + '.block.1.weight'], sd[name + '.block.1.bias']
+    if quant is not None:
+        x, w = quant(x), quant(w)
+    return F.relu(F.conv_transpose2d(x, w, b, stride=2, padding=1))
+
+
+def unet_vgg_forward(sd, x, arch='unet16', quant=None):
+    """Logits [N,1,H,W].  `quant` (e.g. a bf16 round trip) is applied to every conv's input and weight to model
+    the precision of the bf16 tensor-core path while keeping fp32 accumulation."""
+    skips = []
+    for stage in STAGES[arch]:
+        for idx in stage:
+            x = _conv_relu(x, sd, 'encoder.%d' % idx, quant)
+        skips.append(x)
+        x = F.max_pool2d(x, 2, 2)
+    x = _decoder(x, sd, 'center', quant)
+    for name, skip in zip(['dec5', 'dec4', 'dec3', 'dec2'], skips[:0:-1]):
+        x = _decoder(torch.cat([x, skip], 1), sd, name, quant)
+    x = _conv_relu(torch.cat([x, skips[0]], 1), sd, 'dec1.conv', quant)
+    w, b = sd['final.weight'], sd['final.bias']
+    return F.conv2d(x, w, b)   # the 1x1 head stays fp32 on the device path too
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------- loss / metrics
+def bce_with_sigmoid(logits, targets):
+    """lib/losses.py:46-53: BCE-with-logits applied to logsigmoid(logits) (the reference's double squash), mean."""
+    z = F.logsigmoid(logits)
+    return F.binary_cross_entropy_with_logits(z, targets.float(), reduction='mean')
+
+
+def smooth_jaccard(logits, targets, smooth=100):
+    p = torch.sigmoid(logits)
+    t = targets.float()
+    inter = torch.sum(p * t)
+    union = torch.sum(p) + torch.sum(t)
+    return 1 - (inter + smooth) / (union - inter + smooth)
+
+
+def bce_jaccard(logits, targets, bce_weight=1, jaccard_weight=0.5):
+    return (bce_with_sigmoid(logits, targets) * bce_weight + smooth_jaccard(logits, targets) * jaccard_weight) / (
+        bce_weight + jaccard_weight)
+
+
+def jaccard_score(logits, targets):
+    p = torch.sigmoid(logits)
+    t = targets.float()
+    inter = (p * t).sum()
+    union = p.sum() + t.sum()
+    return inter / (union - inter + 1e-7)
+
+
+def pixel_accuracy(logits, targets):
+    pred = torch.sigmoid(logits) > 0.5
+    n_true = torch.eq(pred, targets.byte()).sum()
+    if n_true == 0:
+        return n_true
+    return n_true.float() / targets.numel()
+
+
+def confusion_counts(probs, targets, thr=0.5):
+    """int64 [tp, fp, fn, tn] at probs > thr."""
+    pred = (probs > thr).reshape(-1)
+    truth = (targets != 0).reshape(-1)
+    return torch.stack([(pred & truth).sum(), (pred & ~truth).sum(), (~pred & truth).sum(), (~pred & ~truth).sum()])
+
+
+def pr_curve_counts(logits, targets, n_thresholds=127):
+    """lib/train_utils.py:92-125 -> uint64 arrays tp, tn, fp, fn per threshold arange(0, 1, 1/n) (float32)."""
+    thr = np.arange(0., 1., 1. / n_thresholds, dtype=np.float32)
+    p = torch.sigmoid(logits).numpy().reshape(-1)
+    t = targets.numpy().astype(np.int32).reshape(-1)
+    tp = np.zeros(len(thr), np.uint64); tn = np.zeros(len(thr), np.uint64)
+    fp = np.zeros(len(thr), np.uint64); fn = np.zeros(len(thr), np.uint64)
+    for i, v in enumerate(thr):
+        conf = np.bincount((p > v).astype(np.int32) + 2 * t, minlength=4).reshape(2, 2)   # [truth][pred]
+        tp[i], tn[i], fp[i], fn[i] = conf[1, 1], conf[0, 0], conf[0, 1], conf[1, 0]
+    return tp, tn, fp, fn

@@ -1,0 +1,81 @@
+"""Deterministic synthetic weights and inputs shared by the golden generator, the tests and bench.py
+(TEST INFRASTRUCTURE).  Everything derives from numpy RandomState seeds, so the GPU box regenerates bit-identical
+tensors without any file transfer."""
+import numpy as np
+import torch
+
+# (out_channels of each conv, in torchvision `features` index order); 'M' = max-pool
+_VGG = {
+    'unet16': [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M'],
+    'unet11': [64, 'M', 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
+}
+# decoder blocks (in, mid, out) for num_filters = 32: center, dec5, dec4, dec3, dec2
+_DEC = {
+    'unet16': [(512, 512, 256), (768, 512, 256), (768, 512, 256), (512, 256, 64), (192, 128, 32)],
+    'unet11': [(512, 512, 256), (768, 512, 256), (768, 512, 128), (384, 256, 64), (192, 128, 32)],
+}
+_ALIASES = {   # convK.M -> encoder.N, the double registration of lib/models/unet16.py:73-102 / unet11.py:71-93
+    'unet16': {'conv1': [0, 2], 'conv2': [5, 7], 'conv3': [10, 12, 14], 'conv4': [17, 19, 21], 'conv5': [24, 26, 28]},
+    'unet11': {'conv1': [0], 'conv2': [3], 'conv3': [6, 8], 'conv4': [11, 13], 'conv5': [16, 18]},
+}
+
+
+def _he(rs, shape, fan_in, gain=1.0):
+    return torch.from_numpy((rs.standard_normal(shape) * gain * np.sqrt(2.0 / fan_in)).astype(np.float32))
+
+
+def _bias(rs, n):
+    return torch.from_numpy((rs.standard_normal(n) * 0.05).astype(np.float32))
+
+
+def vgg_unet_state_dict(arch='unet16', seed=0):
+    """Random (He-scaled) state_dict with the reference's key names and shapes, aliases included."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+    cin, idx = 3, 0
+    for v in _VGG[arch]:
+        if v == 'M':
+            idx += 1
+            continue
+        sd['encoder.%d.weight' % idx] = _he(rs, (v, cin, 3, 3), cin * 9)
+        sd['encoder.%d.bias' % idx] = _bias(rs, v)
+        cin = v
+        idx += 2
+    for name, positions in _ALIASES[arch].items():
+        for k, enc_idx in enumerate(positions):
+            for leaf in ('weight', 'bias'):
+                sd['%s.%d.%s' % (name, 2 * k, leaf)] = sd['encoder.%d.%s' % (enc_idx, leaf)]
+    for name, (cin_d, mid, out) in zip(['center', 'dec5', 'dec4', 'dec3', 'dec2'], _DEC[arch]):
+        sd[name + '.block.0.conv.weight'] = _he(rs, (mid, cin_d, 3, 3), cin_d * 9)
+        sd[name + '.block.0.conv.bias'] = _bias(rs, mid)
+        sd[name + '.block.1.weight'] = _he(rs, (mid, out, 4, 4), mid * 4)   # 4 taps reach each output pixel
+        sd[name + '.block.1.bias'] = _bias(rs, out)
+    sd['dec1.conv.weight'] = _he(rs, (32, 96, 3, 3), 96 * 9)
+    sd['dec1.conv.bias'] = _bias(rs, 32)
+    sd['final.weight'] = _he(rs, (1, 32, 1, 1), 32, gain=2.0)
+    sd['final.bias'] = _bias(rs, 1)
+    return sd
+
+
+def image_u8(seed, h, w, c=3, smooth=True):
+    """Inria-shaped synthetic uint8 image; low-pass structure so masks are not pure noise."""
+    rs = np.random.RandomState(seed)
+    if not smooth:
+        return rs.randint(0, 256, (h, w, c)).astype(np.uint8)
+    ch, cw = (h + 31) // 32 + 1, (w + 31) // 32 + 1
+    coarse = rs.rand(ch, cw, c).astype(np.float32)
+    up = np.repeat(np.repeat(coarse, 32, axis=0), 32, axis=1)[:h, :w]
+    noise = rs.rand(h, w, c).astype(np.float32)
+    return np.clip((0.7 * up + 0.3 * noise) * 255.0, 0, 255).astype(np.uint8)
+
+
+def gt_mask_u8(seed, h, w):
+    """Synthetic ground truth {0,1} (RandomState(1000+i).rand(h, w) > 0.5)."""
+    return (np.random.RandomState(1000 + seed).rand(h, w) > 0.5).astype(np.uint8)
+
+
+def logits_targets(seed, shape):
+    rs = np.random.RandomState(seed)
+    logits = torch.from_numpy(rs.standard_normal(shape).astype(np.float32))
+    targets = torch.from_numpy((rs.rand(*shape) > 0.5).astype(np.int64))
+    return logits, targets

@@ -1,0 +1,137 @@
+"""ctypes binding of libsnb_b200.so (include/snb_b200.h).
+
+This is the only place the package touches native code.  There is no CPU fallback: if the library is missing
+the import of anything that computes fails loudly, and every entry point takes DEVICE pointers only.
+Error codes are mapped onto the exception types the reference raises for the same mistakes
+(`ValueError` lib/tiles.py:56-57,81-85,138-139; `AssertionError` lib/tiles.py:99-100; `RuntimeError` for CUDA
+failures, mirroring `_check` in lib/modules/abn/functions.py:12-15).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnb_b200.so")
+
+SNB_OK = 0
+SNB_E_INVALID = -1
+SNB_E_SHAPE = -2
+SNB_E_CUDA = -3
+SNB_E_UNSUPPORTED = -4
+
+DT_U8, DT_F32, DT_F64, DT_I64 = 0, 1, 2, 3
+LAYOUT_NCHW_F32, LAYOUT_PATCH32 = 0, 1
+CONV_3X3, CONV_1X1, CONVT_4X4_S2 = 0, 1, 2
+
+c_i64 = ctypes.c_int64
+c_vp = ctypes.c_void_p
+c_int = ctypes.c_int
+
+
+class ConvDesc(ctypes.Structure):
+    """struct snb_conv_desc (include/snb_b200.h)."""
+
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("relu", ctypes.c_int32),
+        ("n", c_i64),
+        ("h", c_i64),
+        ("w", c_i64),
+        ("cin", c_i64),
+        ("in_cstride", c_i64),
+        ("cout", c_i64),
+        ("out_cstride", c_i64),
+        ("d_in", c_vp),
+        ("d_out", c_vp),
+        ("d_weight", c_vp),
+        ("d_bias", c_vp),
+        ("d_head_w", c_vp),
+        ("head_b", ctypes.c_float),
+        ("head_sigmoid", ctypes.c_int32),
+        ("d_head_out", c_vp),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/snb_b200.h declares
+SIGNATURES = {
+    "snb_version": (c_int, []),
+    "snb_last_error": (ctypes.c_char_p, []),
+    "snb_device_sm_count": (c_int, []),
+    "snb_slicer_create": (c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp)]),
+    "snb_slicer_destroy": (None, [c_vp]),
+    "snb_slicer_info": (c_int, [c_vp, ctypes.POINTER(c_i64)]),
+    "snb_slicer_crops": (c_int, [c_vp, ctypes.POINTER(c_i64)]),
+    "snb_split_hwc": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "snb_split_norm_u8": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp]),
+    "snb_nchw_f32_to_patch32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "snb_merge": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_float, c_vp]),
+    "snb_conv_create": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
+    "snb_conv_launch": (c_int, [c_vp, c_vp]),
+    "snb_conv_destroy": (None, [c_vp]),
+    "snb_conv_flops": (ctypes.c_double, [c_vp]),
+    "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "snb_confusion_counts": (c_int, [c_vp, c_vp, c_int, c_i64, ctypes.c_float, c_vp, c_vp]),
+    "snb_pr_curve_update": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises ImportError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    msg = lib().snb_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc):
+    """Raise the reference's exception type for a non-zero return code."""
+    if rc == SNB_OK:
+        return
+    msg = last_error()
+    if rc == SNB_E_INVALID:
+        raise ValueError(msg)
+    if rc == SNB_E_SHAPE:
+        raise AssertionError(msg)
+    if rc == SNB_E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("segmentation-networks-benchmark_b200 runs on CUDA devices only (no CPU fallback)")
+
+
+def stream_ptr():
+    import torch
+
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (must be CUDA)."""
+    if t is None:
+        return c_vp(0)
+    if not t.is_cuda:
+        raise RuntimeError("expected a CUDA tensor (no CPU fallback)")
+    return c_vp(t.data_ptr())

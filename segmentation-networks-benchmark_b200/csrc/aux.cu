@@ -1,0 +1,83 @@
+// Layout / pooling helpers around the convolution kernels: nn.MaxPool2d(2,2) (lib/models/unet16.py:64) on NHWC
+// bf16 channel slabs and the NHWC-bf16 -> NCHW-fp32 exit conversion of the nn.Module interface.
+// Pure HBM streaming: 16-byte vectors of 8 channels, one output vector per thread, x/channel fastest.
+#include <cuda_bf16.h>
+
+#include "snb_internal.h"
+
+namespace snb {
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int H, int W, int CV /*channels/8*/, int in_sv /*cstride/8*/,
+                                  uint4* __restrict__ out, int out_sv, int64_t total) {
+  const int OH = H / 2, OW = W / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int cv = (int)(r % CV); r /= CV;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int64_t n = r / OH;
+    const int64_t base = ((n * H + 2 * oy) * W + 2 * ox) * in_sv + cv;
+    const uint4 a = __ldg(in + base), b = __ldg(in + base + in_sv);
+    const uint4 c = __ldg(in + base + (int64_t)W * in_sv), d = __ldg(in + base + (int64_t)W * in_sv + in_sv);
+    out[((n * OH + oy) * OW + ox) * out_sv + cv] = bf16x8_max(bf16x8_max(a, b), bf16x8_max(c, d));
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int cstride,
+                                    float* __restrict__ out, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const int64_t n = r / C;
+    out[i] = __bfloat162float(in[((n * H + y) * W + x) * cstride + c]);
+  }
+}
+
+static int aux_grid(int64_t total) {
+  const int64_t need = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                              void* d_out, int64_t out_cstride, void* stream) {
+  if (!d_in || !d_out) return fail(SNB_E_INVALID, "snb_maxpool2x2: null argument");
+  if (n <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return fail(SNB_E_INVALID, "maxpool needs even positive h, w");
+  if (channels <= 0 || channels % 8 || in_cstride % 8 || out_cstride % 8 || in_cstride < channels || out_cstride < channels)
+    return fail(SNB_E_INVALID, "channel counts and strides must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
+  const int64_t total = n * (h / 2) * (w / 2) * (channels / 8);
+  maxpool2x2_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
+                                                                     (int)(channels / 8), (int)(in_cstride / 8),
+                                                                     static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_nhwc_bf16_to_nchw_f32(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels,
+                                         int64_t in_cstride, float* d_out, void* stream) {
+  if (!d_in || !d_out) return fail(SNB_E_INVALID, "snb_nhwc_bf16_to_nchw_f32: null argument");
+  if (n <= 0 || h <= 0 || w <= 0 || channels <= 0 || in_cstride < channels) return fail(SNB_E_INVALID, "bad shape");
+  const int64_t total = n * channels * h * w;
+  nhwc_to_nchw_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(d_in), (int)h, (int)w,
+                                                                       (int)channels, (int)in_cstride, d_out, total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

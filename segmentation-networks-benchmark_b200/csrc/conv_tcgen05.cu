@@ -1,0 +1,501 @@
+// Tap-list implicit-GEMM convolution on the sm_100a tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// One kernel family covers what UNet16 / UNet11 / ZF_UNET execute (lib/models/unet16.py:8-49,113-131):
+//   conv3x3 s1 p1      = 1 phase  x 9 taps  (dy,dx in -1..1)
+//   conv1x1            = 1 phase  x 1 tap
+//   ConvTranspose k4s2 = 4 phases x 4 taps  (sub-pixel decomposition; phase (py,px) writes out[2y+py][2x+px])
+// GEMM view per phase:  D[pixel][cout] = sum_{tap,cin} A[pixel + (dy,dx)][cin] * W[tap][cout][cin]
+//   M tile = 128 output pixels = an 8 x 16 spatial patch of one image (TMA box over NHWC, OOB -> 0 gives the
+//            conv zero padding and ragged edges for free; no im2col buffer exists),
+//   N tile = BN output channels, K step = one tap x BK input channels (BK*2 bytes = one swizzle span).
+//
+// Persistent CTAs (<= 1 per SM), warp-specialised:
+//   warp 0  : TMA producer   (A box + B box per K step into an NSTAGES ring, mbarrier expect_tx)
+//   warp 1  : MMA issuer     (one thread: tcgen05.mma kind::f16, accumulators in TMEM, 2 accumulator stages)
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled smem -> TMA store into the channel
+//                             slab at its concat offset; or the fused 1x1 head + sigmoid for the last layer)
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "sm100_ptx.cuh"
+#include "snb_internal.h"
+
+namespace snb {
+
+constexpr int kTileW = 16;   // spatial patch of one M tile
+constexpr int kTileH = 8;
+constexpr int kBM = kTileW * kTileH;  // 128 = UMMA M
+constexpr int kMaxPhases = 4;
+constexpr int kMaxTaps = 9;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct alignas(64) ConvParams {
+  CUtensorMap map_a;               // activations (C, W, H, N), box (BK, 16, 8, 1)
+  CUtensorMap map_b;               // weights (Cin, Cout, phase*taps), box (BK, BN, 1)
+  CUtensorMap map_d[kMaxPhases];   // outputs per phase (C, W, H, N), box (CW, 16, 8, 1)
+  int32_t n_phases, taps;          // taps per phase
+  int32_t k_chunks;                // Cin / BK
+  int32_t n_tiles;                 // Cout / BN
+  int32_t tiles_x, tiles_y, n_img;
+  int32_t total_tiles;
+  int32_t relu;
+  int32_t head_sigmoid;
+  int32_t out_w, out_h;            // head output bounds
+  float head_b;
+  const float* bias;
+  const float* head_w;
+  float* head_out;
+  int8_t tap_dy[kMaxPhases][kMaxTaps];
+  int8_t tap_dx[kMaxPhases][kMaxTaps];
+};
+
+template <int BN, int BK>
+struct ConvCfg {
+  static constexpr int SWZ = BK * 2;                    // bytes per operand row = swizzle span
+  static constexpr int A_BYTES = kBM * SWZ;
+  static constexpr int B_BYTES = BN * SWZ;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int CW = BN < 64 ? BN : 64;          // channels per output store chunk
+  static constexpr int OUT_SWZ = CW * 2;
+  static constexpr int OUT_BYTES = kBM * OUT_SWZ;
+  static constexpr int CTRL_BYTES = 1024;               // barriers + tmem pointer
+  static constexpr int RAW_STAGES = (kSmemBudget - 1024 /*align slack*/ - 2 * OUT_BYTES - CTRL_BYTES) / STAGE_BYTES;
+  static constexpr int NSTAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = 1024 + NSTAGES * STAGE_BYTES + 2 * OUT_BYTES + CTRL_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages (power of two)
+  static_assert(NSTAGES >= 3, "pipeline too shallow");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0, "swizzle atom alignment");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns");
+};
+
+struct TileCoord {
+  int nt, x0, y0, img, ph;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  c.nt = t % p.n_tiles;
+  t /= p.n_tiles;
+  c.x0 = (t % p.tiles_x) * kTileW;
+  t /= p.tiles_x;
+  c.y0 = (t % p.tiles_y) * kTileH;
+  t /= p.tiles_y;
+  c.img = t % p.n_img;
+  c.ph = t / p.n_img;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int BK, bool HEAD>
+__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN, BK>;
+  constexpr int NSTAGES = Cfg::NSTAGES;
+  constexpr uint32_t IDESC = make_idesc_bf16(kBM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_stage = smem;                                  // NSTAGES x [A | B]
+  uint8_t* smem_out = smem + NSTAGES * Cfg::STAGE_BYTES;       // 2 x OUT_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 2 * Cfg::OUT_BYTES);
+  uint64_t* full_bar = bars;                  // [NSTAGES]
+  uint64_t* empty_bar = bars + NSTAGES;       // [NSTAGES]
+  uint64_t* tmem_full = bars + 2 * NSTAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+    if (!HEAD)
+      for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.map_d[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc05_fence_before();
+  __syncthreads();
+  tc05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int k_steps = p.taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int ax = tc.x0 + p.tap_dx[tc.ph][tap];
+          const int ay = tc.y0 + p.tap_dy[tc.ph][tap];
+          const int wtap = tc.ph * p.taps + tap;
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % NSTAGES;
+            const uint32_t ph = (it / NSTAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            tma_load_4d(&p.map_a, &full_bar[s], sa, kc * BK, ax, ay, tc.img);
+            tma_load_3d(&p.map_b, &full_bar[s], sb, kc * BK, tc.nt * BN, wtap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (elect_one()) {
+      uint32_t it = 0;
+      uint32_t local_tile = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+        const uint32_t acc = local_tile & 1;
+        const uint32_t acc_ph = (local_tile >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < k_steps; ++ks, ++it) {
+          const uint32_t s = it % NSTAGES;
+          const uint32_t ph = (it / NSTAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc05_fence_after();
+          const uint32_t a_addr = smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_desc<Cfg::SWZ>(a_addr);
+          const uint64_t bdesc = make_kmajor_desc<Cfg::SWZ>(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_bf16_ss(adesc + 2 * k, bdesc + 2 * k, d_tmem, IDESC, (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;       // pixel index inside the 8x16 patch
+    const int epi_tid = threadIdx.x - 128;
+    uint32_t local_tile = 0;
+    uint32_t n_store = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+      const TileCoord tc = decode_tile(p, t);
+      const uint32_t acc = local_tile & 1;
+      const uint32_t acc_ph = (local_tile >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc05_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+      if constexpr (HEAD) {
+        static_assert(!HEAD || BN == 32, "fused head needs all channels of a pixel in one thread");
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr, v);
+        tmem_ld_wait();
+        tc05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        float dot = p.head_b;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]) + __ldg(p.bias + i);
+          if (p.relu) x = fmaxf(x, 0.f);
+          dot = fmaf(x, __ldg(p.head_w + i), dot);
+        }
+        if (p.head_sigmoid) dot = 1.f / (1.f + expf(-dot));
+        const int ox = tc.x0 + (row & (kTileW - 1));
+        const int oy = tc.y0 + (row >> 4);
+        if (ox < p.out_w && oy < p.out_h)
+          p.head_out[(static_cast<int64_t>(tc.img) * p.out_h + oy) * p.out_w + ox] = dot;
+      } else {
+        constexpr int CW = Cfg::CW;
+        constexpr int NCHUNK = BN / CW;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c, ++n_store) {
+          uint8_t* sout = smem_out + (n_store & 1) * Cfg::OUT_BYTES;
+          // the TMA store issued two chunks ago must have finished reading this buffer
+          if (epi_tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int g = 0; g < CW / 32; ++g) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_addr + c * CW + g * 32, v);
+            tmem_ld_wait();
+            const float* bias = p.bias + tc.nt * BN + c * CW + g * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // 4 x 16-byte chunks of 8 channels
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo = __uint_as_float(v[j * 8 + 2 * e]) + __ldg(bias + j * 8 + 2 * e);
+                float hi = __uint_as_float(v[j * 8 + 2 * e + 1]) + __ldg(bias + j * 8 + 2 * e + 1);
+                if (p.relu) {
+                  lo = fmaxf(lo, 0.f);
+                  hi = fmaxf(hi, 0.f);
+                }
+                w[e] = pack_bf16x2(lo, hi);
+              }
+              const int chunk = g * 4 + j;
+              const int sw = Cfg::OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
+              uint4* dst = reinterpret_cast<uint4*>(sout + row * Cfg::OUT_SWZ + ((chunk ^ sw) << 4));
+              *dst = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (c == NCHUNK - 1) {
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+            tc05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (epi_tid == 0) {
+            tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- host side
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// bf16 tensor map over up to 4 dims; strides in bytes for dims 1..rank-1
+static int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SNB_E_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SNB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SNB_OK;
+}
+
+struct KernelChoice {
+  const void* fn;
+  int smem;
+  int bn, bk;
+};
+
+template <int BN, int BK, bool HEAD>
+static KernelChoice choice() {
+  return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>), ConvCfg<BN, BK>::SMEM_BYTES,
+                      BN, BK};
+}
+
+static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
+  if (head) {
+    if (bn != 32) return false;
+    *out = bk == 64 ? choice<32, 64, true>() : choice<32, 32, true>();
+    return true;
+  }
+#define SNB_PICK(BN_, BK_)                  \
+  if (bn == BN_ && bk == BK_) {             \
+    *out = choice<BN_, BK_, false>();       \
+    return true;                            \
+  }
+  SNB_PICK(32, 32)
+  SNB_PICK(32, 64)
+  SNB_PICK(64, 32)
+  SNB_PICK(64, 64)
+  SNB_PICK(128, 32)
+  SNB_PICK(128, 64)
+  SNB_PICK(256, 32)
+  SNB_PICK(256, 64)
+#undef SNB_PICK
+  return false;
+}
+
+}  // namespace snb
+
+struct snb_conv {
+  snb::ConvParams params;
+  snb::KernelChoice kernel;
+  int grid;
+  double flops;
+};
+
+using namespace snb;
+
+extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
+  if (!d || !out) return fail(SNB_E_INVALID, "snb_conv_create: null argument");
+  *out = nullptr;
+  if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_4X4_S2) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
+  if (d->cin <= 0 || d->cin % 32 != 0) return fail(SNB_E_INVALID, "cin=%lld must be a positive multiple of 32", (long long)d->cin);
+  if (d->cout <= 0 || d->cout % 32 != 0) return fail(SNB_E_INVALID, "cout=%lld must be a positive multiple of 32", (long long)d->cout);
+  if (d->in_cstride < d->cin || d->in_cstride % 8 != 0) return fail(SNB_E_INVALID, "bad in_cstride");
+  const bool head = d->d_head_w != nullptr;
+  if (head && (d->cout != 32 || d->kind == SNB_CONVT_4X4_S2 || !d->d_head_out))
+    return fail(SNB_E_INVALID, "fused head needs cout == 32, a plain conv and an output pointer");
+  if (!head && (!d->d_out || d->out_cstride < d->cout || d->out_cstride % 8 != 0))
+    return fail(SNB_E_INVALID, "bad output slab");
+  if (!d->d_in || !d->d_weight || !d->d_bias) return fail(SNB_E_INVALID, "null tensor pointer");
+  if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
+      (reinterpret_cast<uintptr_t>(d->d_weight) & 15))
+    return fail(SNB_E_INVALID, "tensor pointers must be 16-byte aligned");
+
+  const int bk = d->cin % 64 == 0 ? 64 : 32;
+  int bn = 32;
+  if (d->cout % 256 == 0) bn = 256;
+  else if (d->cout % 128 == 0) bn = 128;
+  else if (d->cout % 64 == 0) bn = 64;
+  KernelChoice kc;
+  if (!pick_kernel(bn, bk, head, &kc)) return fail(SNB_E_UNSUPPORTED, "no kernel for BN=%d BK=%d head=%d", bn, bk, (int)head);
+
+  snb_conv* c = new (std::nothrow) snb_conv();
+  if (!c) return fail(SNB_E_INVALID, "out of host memory");
+  ConvParams& p = c->params;
+  std::memset(&p, 0, sizeof(p));
+  c->kernel = kc;
+
+  p.n_phases = d->kind == SNB_CONVT_4X4_S2 ? 4 : 1;
+  p.taps = d->kind == SNB_CONV_3X3 ? 9 : (d->kind == SNB_CONV_1X1 ? 1 : 4);
+  if (d->kind == SNB_CONV_3X3) {
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        p.tap_dy[0][ky * 3 + kx] = static_cast<int8_t>(ky - 1);
+        p.tap_dx[0][ky * 3 + kx] = static_cast<int8_t>(kx - 1);
+      }
+  } else if (d->kind == SNB_CONVT_4X4_S2) {
+    // out[2y+py] gathers in[y+dy] * W[ky]:  py=0: (dy=0,ky=1), (dy=-1,ky=3);  py=1: (dy=+1,ky=0), (dy=0,ky=2)
+    // the packed weight tap order is (ty, tx) with ty, tx in {0,1} following that list
+    const int dlist[2][2] = {{0, -1}, {1, 0}};
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int ty = 0; ty < 2; ++ty)
+          for (int tx = 0; tx < 2; ++tx) {
+            p.tap_dy[py * 2 + px][ty * 2 + tx] = static_cast<int8_t>(dlist[py][ty]);
+            p.tap_dx[py * 2 + px][ty * 2 + tx] = static_cast<int8_t>(dlist[px][tx]);
+          }
+  }
+  p.k_chunks = static_cast<int32_t>(d->cin / bk);
+  p.n_tiles = static_cast<int32_t>(d->cout / bn);
+  p.tiles_x = static_cast<int32_t>((d->w + kTileW - 1) / kTileW);
+  p.tiles_y = static_cast<int32_t>((d->h + kTileH - 1) / kTileH);
+  p.n_img = static_cast<int32_t>(d->n);
+  const int64_t total = static_cast<int64_t>(p.n_phases) * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
+  if (total > INT32_MAX) {
+    delete c;
+    return fail(SNB_E_UNSUPPORTED, "too many tiles");
+  }
+  p.total_tiles = static_cast<int32_t>(total);
+  p.relu = d->relu;
+  p.bias = d->d_bias;
+  p.head_w = d->d_head_w;
+  p.head_b = d->head_b;
+  p.head_sigmoid = d->head_sigmoid;
+  p.head_out = d->d_head_out;
+  p.out_w = static_cast<int32_t>(d->w);
+  p.out_h = static_cast<int32_t>(d->h);
+
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->in_cstride * 2, (uint64_t)d->w * d->in_cstride * 2,
+                       (uint64_t)d->h * d->w * d->in_cstride * 2};
+    uint32_t box[4] = {(uint32_t)bk, kTileW, kTileH, 1};
+    rc = encode_map(&p.map_a, const_cast<void*>(d->d_in), 4, dims, str, box, bk * 2);
+    if (rc) { delete c; return rc; }
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->cin, (uint64_t)d->cout, (uint64_t)(p.n_phases * p.taps)};
+    uint64_t str[2] = {(uint64_t)d->cin * 2, (uint64_t)d->cout * d->cin * 2};
+    uint32_t box[3] = {(uint32_t)bk, (uint32_t)bn, 1};
+    rc = encode_map(&p.map_b, const_cast<void*>(d->d_weight), 3, dims, str, box, bk * 2);
+    if (rc) { delete c; return rc; }
+  }
+  if (!head) {
+    const int cw = bn < 64 ? bn : 64;
+    const int s = d->kind == SNB_CONVT_4X4_S2 ? 2 : 1;
+    const int64_t ow = d->w * s, oh = d->h * s;
+    for (int ph = 0; ph < p.n_phases; ++ph) {
+      const int py = ph / 2, px = ph % 2;
+      char* base = static_cast<char*>(d->d_out) + ((int64_t)py * ow + px) * d->out_cstride * 2;
+      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+      uint64_t str[3] = {(uint64_t)s * d->out_cstride * 2, (uint64_t)s * ow * d->out_cstride * 2,
+                         (uint64_t)oh * ow * d->out_cstride * 2};
+      uint32_t box[4] = {(uint32_t)cw, kTileW, kTileH, 1};
+      rc = encode_map(&p.map_d[ph], base, 4, dims, str, box, cw * 2);
+      if (rc) { delete c; return rc; }
+    }
+  }
+
+  cudaError_t e = cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(SNB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kc.smem, cudaGetErrorString(e));
+  }
+  const int sms = sm_count();
+  if (sms <= 0) { delete c; return fail(SNB_E_CUDA, "no CUDA device"); }
+  c->grid = std::min<int>(p.total_tiles, sms);
+  // 2*MACs with the true tap counts (ConvT: every input pixel meets all 16 taps once over the 4 phases)
+  c->flops = 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * (double)(p.n_phases * p.taps);
+  *out = c;
+  return SNB_OK;
+}
+
+extern "C" int snb_conv_launch(const snb_conv* c, void* stream) {
+  if (!c) return fail(SNB_E_INVALID, "snb_conv_launch: null handle");
+  void* args[1] = {const_cast<ConvParams*>(&c->params)};
+  cudaError_t e = cudaLaunchKernel(c->kernel.fn, dim3(c->grid), dim3(256), args, c->kernel.smem, as_stream(stream));
+  if (e != cudaSuccess) return fail(SNB_E_CUDA, "conv launch failed: %s", cudaGetErrorString(e));
+  return SNB_OK;
+}
+
+extern "C" void snb_conv_destroy(snb_conv* c) { delete c; }
+
+extern "C" double snb_conv_flops(const snb_conv* c) { return c ? c->flops : 0.0; }

@@ -1,0 +1,280 @@
+// Single-pass loss / metric reductions (lib/losses.py:31-75, lib/metrics.py:9-40, lib/train_utils.py:92-125).
+// HBM-bound: 4 B logit + 8/1/4 B target per element, read once with 16-byte loads; partial sums stay in
+// registers, are folded with warp shuffles, then one atomic per block (fp64 for the float sums so the result
+// does not depend on the grid shape to fp32 precision; u64 for the integer counts, which are order independent).
+#include <cstdint>
+
+#include "snb_internal.h"
+
+namespace snb {
+
+__device__ __forceinline__ float sigmoid_f32(float x) { return 1.f / (1.f + expf(-x)); }
+
+// F.logsigmoid: min(x, 0) - log1p(exp(-|x|))
+__device__ __forceinline__ float logsigmoid_f32(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+
+template <int DT>
+__device__ __forceinline__ float load_target(const void* t, int64_t i) {
+  if (DT == SNB_DT_I64) return (float)static_cast<const long long*>(t)[i];
+  if (DT == SNB_DT_U8) return (float)static_cast<const uint8_t*>(t)[i];
+  return static_cast<const float*>(t)[i];
+}
+
+template <int DT>
+__device__ __forceinline__ void load_target4(const void* t, int64_t i4, float (&tv)[4]) {
+  if (DT == SNB_DT_I64) {
+    const longlong2* p = static_cast<const longlong2*>(t) + i4 * 2;
+    const longlong2 a = __ldg(p), b = __ldg(p + 1);
+    tv[0] = (float)a.x; tv[1] = (float)a.y; tv[2] = (float)b.x; tv[3] = (float)b.y;
+  } else if (DT == SNB_DT_U8) {
+    const uchar4 a = __ldg(static_cast<const uchar4*>(t) + i4);
+    tv[0] = a.x; tv[1] = a.y; tv[2] = a.z; tv[3] = a.w;
+  } else {
+    const float4 a = __ldg(static_cast<const float4*>(t) + i4);
+    tv[0] = a.x; tv[1] = a.y; tv[2] = a.z; tv[3] = a.w;
+  }
+}
+
+struct LossAcc {
+  float bce, pt, p, t;
+  uint32_t tp, fp, fn, tn;
+};
+
+__device__ __forceinline__ void loss_accumulate(LossAcc& a, float x, float t) {
+  const float p = sigmoid_f32(x);
+  const float z = logsigmoid_f32(x);  // the reference feeds logsigmoid(x) into BCE-with-logits (losses.py:51-53)
+  // binary_cross_entropy_with_logits(z, t) = (1 - t) * z - logsigmoid(z)
+  a.bce += (1.f - t) * z - logsigmoid_f32(z);
+  a.pt += p * t;
+  a.p += p;
+  a.t += t;
+  const bool pred = p > 0.5f;          // metrics.py:31
+  const bool truth = ((int)t & 0xff) != 0;  // target.byte()
+  a.tp += pred && truth;
+  a.fp += pred && !truth;
+  a.fn += !pred && truth;
+  a.tn += !pred && !truth;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) loss_iou_kernel(const float* __restrict__ logits, const void* __restrict__ targets,
+                                                       int64_t n, double* __restrict__ sums,
+                                                       unsigned long long* __restrict__ counts) {
+  LossAcc a{};
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(logits) + i);
+    float tv[4];
+    load_target4<DT>(targets, i, tv);
+    loss_accumulate(a, x.x, tv[0]);
+    loss_accumulate(a, x.y, tv[1]);
+    loss_accumulate(a, x.z, tv[2]);
+    loss_accumulate(a, x.w, tv[3]);
+  }
+  // ragged tail (< 4 elements) handled by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    loss_accumulate(a, logits[i], load_target<DT>(targets, i));
+  }
+
+  __shared__ double s_f[8][4];
+  __shared__ uint32_t s_i[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float f0 = warp_sum(a.bce), f1 = warp_sum(a.pt), f2 = warp_sum(a.p), f3 = warp_sum(a.t);
+  const uint32_t c0 = __reduce_add_sync(0xffffffffu, a.tp), c1 = __reduce_add_sync(0xffffffffu, a.fp);
+  const uint32_t c2 = __reduce_add_sync(0xffffffffu, a.fn), c3 = __reduce_add_sync(0xffffffffu, a.tn);
+  if (lane == 0) {
+    s_f[warp][0] = f0; s_f[warp][1] = f1; s_f[warp][2] = f2; s_f[warp][3] = f3;
+    s_i[warp][0] = c0; s_i[warp][1] = c1; s_i[warp][2] = c2; s_i[warp][3] = c3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double f = 0.0;
+    unsigned long long c = 0;
+    for (int w = 0; w < 8; ++w) { f += s_f[w][threadIdx.x]; c += s_i[w][threadIdx.x]; }
+    atomicAdd(&sums[threadIdx.x], f);
+    atomicAdd(&counts[threadIdx.x], c);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict__ probs, const void* __restrict__ targets,
+                                                        int64_t n, float thr, unsigned long long* __restrict__ counts) {
+  uint32_t c[4] = {0, 0, 0, 0};
+  auto add = [&](float p, float t) {
+    const bool pred = p > thr;
+    const bool truth = ((int)t & 0xff) != 0;
+    c[0] += pred && truth; c[1] += pred && !truth; c[2] += !pred && truth; c[3] += !pred && !truth;
+  };
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(probs) + i);
+    float tv[4];
+    load_target4<DT>(targets, i, tv);
+    add(x.x, tv[0]); add(x.y, tv[1]); add(x.z, tv[2]); add(x.w, tv[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    add(probs[i], load_target<DT>(targets, i));
+  }
+  __shared__ uint32_t s_i[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t v = __reduce_add_sync(0xffffffffu, c[k]);
+    if (lane == 0) s_i[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += s_i[w][threadIdx.x];
+    atomicAdd(&counts[threadIdx.x], t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- PR curve
+constexpr int kMaxThr = 1024;
+// hist[truth][idx], idx = number of thresholds strictly below sigmoid(x); stream-ordered scratch
+__device__ unsigned long long g_pr_hist[2][kMaxThr + 1];
+
+template <int DT>
+__global__ void __launch_bounds__(256) pr_hist_kernel(const float* __restrict__ logits, const void* __restrict__ targets,
+                                                      int64_t n, const float* __restrict__ thr, int n_thr) {
+  extern __shared__ uint32_t sh[];            // [8 warps][2][n_thr+1] then thresholds
+  const int bins = n_thr + 1;
+  uint32_t* hist = sh;
+  float* s_thr = reinterpret_cast<float*>(sh + 8 * 2 * bins);
+  for (int i = threadIdx.x; i < 8 * 2 * bins; i += blockDim.x) hist[i] = 0;
+  for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr[i];
+  __syncthreads();
+  uint32_t* my = hist + (threadIdx.x >> 5) * 2 * bins;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float p = sigmoid_f32(__ldg(logits + i));
+    const int truth = ((int)load_target<DT>(targets, i)) != 0;  // astype(int32) then k*true with k=2
+    // idx = #{k : p > thr[k]} for ascending thresholds (upper-bound style binary search)
+    int lo = 0, hi = n_thr;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (p > s_thr[mid]) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&my[truth * bins + lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * bins; i += blockDim.x) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += hist[w * 2 * bins + i];
+    if (t) atomicAdd(&g_pr_hist[i / bins][i % bins], t);
+  }
+}
+
+__global__ void pr_clear_kernel(int n_thr) {
+  for (int i = threadIdx.x; i < 2 * (kMaxThr + 1); i += blockDim.x) (&g_pr_hist[0][0])[i] = 0;
+}
+
+// pred_k = idx > k.  tp += sum_{idx>k} h[1][idx], fp += sum_{idx>k} h[0][idx], fn/tn the complements.
+__global__ void pr_finalize_kernel(int n_thr, unsigned long long* tp, unsigned long long* tn, unsigned long long* fp,
+                                   unsigned long long* fn) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_thr) return;
+  unsigned long long pos1 = 0, pos0 = 0, neg1 = 0, neg0 = 0;
+  for (int idx = 0; idx <= n_thr; ++idx) {
+    if (idx > k) { pos1 += g_pr_hist[1][idx]; pos0 += g_pr_hist[0][idx]; }
+    else { neg1 += g_pr_hist[1][idx]; neg0 += g_pr_hist[0][idx]; }
+  }
+  tp[k] += pos1; fp[k] += pos0; fn[k] += neg1; tn[k] += neg0;
+}
+
+static int reduce_grid(int64_t n_items) {
+  const int64_t need = (n_items + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+static int check_targets(const void* d_targets, int dt, int64_t n, bool vec) {
+  if (dt != SNB_DT_I64 && dt != SNB_DT_U8 && dt != SNB_DT_F32) return fail(SNB_E_INVALID, "target dtype %d unsupported", dt);
+  if (n < 0) return fail(SNB_E_INVALID, "negative length");
+  const uintptr_t a = reinterpret_cast<uintptr_t>(d_targets);
+  if (vec && ((dt == SNB_DT_I64 && (a & 15)) || (dt == SNB_DT_F32 && (a & 15)) || (dt == SNB_DT_U8 && (a & 3))))
+    return fail(SNB_E_INVALID, "targets must be 16-byte aligned (4-byte for u8)");
+  return SNB_OK;
+}
+
+extern "C" int snb_loss_iou_reduce(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
+                                   double* d_sums, int64_t* d_counts, void* stream) {
+  if (!d_logits || !d_targets || !d_sums || !d_counts) return fail(SNB_E_INVALID, "snb_loss_iou_reduce: null argument");
+  if (int rc = check_targets(d_targets, target_dtype, n, true)) return rc;
+  if (reinterpret_cast<uintptr_t>(d_logits) & 15) return fail(SNB_E_INVALID, "logits must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_sums, 0, 4 * sizeof(double), st));
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), st));
+  if (n == 0) return SNB_OK;
+  const int grid = reduce_grid((n + 3) / 4);
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(d_counts);
+  if (target_dtype == SNB_DT_I64) loss_iou_kernel<SNB_DT_I64><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
+  else if (target_dtype == SNB_DT_U8) loss_iou_kernel<SNB_DT_U8><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
+  else loss_iou_kernel<SNB_DT_F32><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_confusion_counts(const float* d_probs, const void* d_targets, int target_dtype, int64_t n, float thr,
+                                    int64_t* d_counts, void* stream) {
+  if (!d_probs || !d_targets || !d_counts) return fail(SNB_E_INVALID, "snb_confusion_counts: null argument");
+  if (int rc = check_targets(d_targets, target_dtype, n, true)) return rc;
+  if (reinterpret_cast<uintptr_t>(d_probs) & 15) return fail(SNB_E_INVALID, "probs must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), st));
+  if (n == 0) return SNB_OK;
+  const int grid = reduce_grid((n + 3) / 4);
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(d_counts);
+  if (target_dtype == SNB_DT_I64) confusion_kernel<SNB_DT_I64><<<grid, 256, 0, st>>>(d_probs, d_targets, n, thr, cnt);
+  else if (target_dtype == SNB_DT_U8) confusion_kernel<SNB_DT_U8><<<grid, 256, 0, st>>>(d_probs, d_targets, n, thr, cnt);
+  else confusion_kernel<SNB_DT_F32><<<grid, 256, 0, st>>>(d_probs, d_targets, n, thr, cnt);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_pr_curve_update(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
+                                   const float* d_thresholds, int64_t n_thr, uint64_t* d_tp, uint64_t* d_tn,
+                                   uint64_t* d_fp, uint64_t* d_fn, void* stream) {
+  if (!d_logits || !d_targets || !d_thresholds || !d_tp || !d_tn || !d_fp || !d_fn)
+    return fail(SNB_E_INVALID, "snb_pr_curve_update: null argument");
+  if (n_thr < 1 || n_thr > kMaxThr) return fail(SNB_E_INVALID, "n_thr=%lld not in [1, %d]", (long long)n_thr, kMaxThr);
+  if (int rc = check_targets(d_targets, target_dtype, n, false)) return rc;
+  if (n == 0) return SNB_OK;
+  cudaStream_t st = as_stream(stream);
+  const int bins = (int)n_thr + 1;
+  const size_t smem = (size_t)(8 * 2 * bins) * sizeof(uint32_t) + (size_t)n_thr * sizeof(float);
+  pr_clear_kernel<<<1, 256, 0, st>>>((int)n_thr);
+  const int grid = reduce_grid(n);
+#define SNB_PR(DT)                                                                                         \
+  do {                                                                                                     \
+    if (smem > 48 * 1024)                                                                                  \
+      SNB_CUDA_CHECK(cudaFuncSetAttribute(pr_hist_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                     \
+    pr_hist_kernel<DT><<<grid, 256, smem, st>>>(d_logits, d_targets, n, d_thresholds, (int)n_thr);          \
+  } while (0)
+  if (target_dtype == SNB_DT_I64) SNB_PR(SNB_DT_I64);
+  else if (target_dtype == SNB_DT_U8) SNB_PR(SNB_DT_U8);
+  else SNB_PR(SNB_DT_F32);
+#undef SNB_PR
+  SNB_LAUNCH_CHECK();
+  pr_finalize_kernel<<<((int)n_thr + 127) / 128, 128, 0, st>>>(
+      (int)n_thr, reinterpret_cast<unsigned long long*>(d_tp), reinterpret_cast<unsigned long long*>(d_tn),
+      reinterpret_cast<unsigned long long*>(d_fp), reinterpret_cast<unsigned long long*>(d_fn));
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

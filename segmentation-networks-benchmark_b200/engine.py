@@ -1,0 +1,211 @@
+"""Static execution plans for the encoder-decoder bodies (TernausNet family) on top of the C ABI.
+
+A plan is built once per (weights, batch, height, width): NHWC bf16 channel slabs are allocated, every producer
+is pointed at its channel offset inside the consumer's concat slab (so `torch.cat` of
+lib/models/unet16.py:122-127 never runs), weights are packed K-major bf16 per tap, and each layer becomes one
+`snb_conv` handle (TMA descriptors baked in).  `run()` only enqueues kernels on the current stream: no
+allocation, no synchronisation, CUDA-graph capturable.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+
+
+# ------------------------------------------------------------------------------------------- weight packing
+def pack_conv3x3(weight):
+    """nn.Conv2d weight [Cout, Cin, 3, 3] -> bf16 [9][Cout][Cin], tap = ky*3 + kx."""
+    cout, cin = weight.shape[:2]
+    return weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).to(torch.bfloat16).contiguous()
+
+
+def pack_conv1x1(weight):
+    cout, cin = weight.shape[:2]
+    return weight.detach().reshape(1, cout, cin).to(torch.bfloat16).contiguous()
+
+
+def pack_first_conv3x3(weight):
+    """First layer [Cout, C<=3, 3, 3] -> bf16 [1][Cout][32] matching the PATCH32 rows: k = (ky*3+kx)*C + c."""
+    cout, cin = weight.shape[:2]
+    w = weight.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    out = torch.zeros((1, cout, 32), dtype=torch.bfloat16, device=weight.device)
+    out[0, :, :9 * cin] = w.to(torch.bfloat16)
+    return out.contiguous()
+
+
+# out[2y+py] = sum in[y+dy] * W[ky]:  py=0 -> (dy=0, ky=1), (dy=-1, ky=3);  py=1 -> (dy=+1, ky=0), (dy=0, ky=2)
+_CONVT_K = ((1, 3), (0, 2))
+
+
+def pack_convT4x4(weight):
+    """nn.ConvTranspose2d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4] -> bf16 [4 phases * 4 taps][Cout][Cin]."""
+    cin, cout = weight.shape[:2]
+    w = weight.detach()
+    taps = []
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    taps.append(w[:, :, _CONVT_K[py][ty], _CONVT_K[px][tx]].t())
+    return torch.stack(taps).to(torch.bfloat16).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------- slabs
+class Slab:
+    """NHWC bf16 buffer; `view(c0, c)` names a channel range (a concat slot)."""
+
+    def __init__(self, n, h, w, c, device):
+        self.n, self.h, self.w, self.c = n, h, w, c
+        self.t = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+
+    def view(self, c0=0, c=None):
+        return SlabView(self, c0, self.c - c0 if c is None else c)
+
+
+class SlabView:
+    def __init__(self, slab, c0, c):
+        assert 0 <= c0 and c0 + c <= slab.c
+        self.slab, self.c0, self.c = slab, c0, c
+
+    @property
+    def ptr(self):
+        return self.slab.t.data_ptr() + 2 * self.c0
+
+    @property
+    def cstride(self):
+        return self.slab.c
+
+    def torch(self):
+        return self.slab.t[..., self.c0:self.c0 + self.c]
+
+
+class ConvOp:
+    """One snb_conv handle; keeps every tensor it points at alive."""
+
+    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None):
+        self.keep = (src, dst, weight, bias, head)
+        d = N.ConvDesc()
+        d.kind = kind
+        d.relu = 1 if relu else 0
+        d.n, d.h, d.w = src.slab.n, src.slab.h, src.slab.w
+        d.cin, d.in_cstride = src.c, src.cstride
+        d.d_in = src.ptr
+        d.d_weight = weight.data_ptr()
+        d.d_bias = bias.data_ptr()
+        if head is None:
+            d.cout, d.out_cstride = dst.c, dst.cstride
+            d.d_out = dst.ptr
+        else:
+            head_w, head_b, head_sigmoid, head_out = head
+            d.cout, d.out_cstride = 32, 32
+            d.d_out = None
+            d.d_head_w = head_w.data_ptr()
+            d.head_b = float(head_b)
+            d.head_sigmoid = 1 if head_sigmoid else 0
+            d.d_head_out = head_out.data_ptr()
+        if weight.shape[1] != d.cout or weight.shape[2] != d.cin:
+            raise ValueError("packed weight %s does not match cout=%d cin=%d" % (tuple(weight.shape), d.cout, d.cin))
+        self._h = ctypes.c_void_p()
+        N.check(N.lib().snb_conv_create(ctypes.byref(d), ctypes.byref(self._h)))
+        self.flops = N.lib().snb_conv_flops(self._h)
+        self.launches = 1
+
+    def __call__(self, stream):
+        N.check(N.lib().snb_conv_launch(self._h, stream))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().snb_conv_destroy(h)
+            except Exception:
+                pass
+
+
+class PoolOp:
+    def __init__(self, src, dst):
+        self.keep = (src, dst)
+        s = src.slab
+        self.args = (N.c_vp(src.ptr), s.n, s.h, s.w, src.c, src.cstride, N.c_vp(dst.ptr), dst.cstride)
+        self.flops = 0.0
+        self.launches = 1
+
+    def __call__(self, stream):
+        N.check(N.lib().snb_maxpool2x2(*self.args, stream))
+
+
+class VGGUNetPlan:
+    """UNet11 / UNet16 forward (lib/models/unet11.py:106-122, unet16.py:113-131) as a list of kernel launches.
+
+    enc: list of stages, each a list of (weight, bias) nn.Conv2d parameters (3x3, ReLU after each).
+    decs: [center, dec5, dec4, dec3, dec2] as (conv_w, conv_b, convT_w, convT_b); dec1 = (w, b); final = (w, b).
+    """
+
+    def __init__(self, enc, decs, dec1, final, n, h, w, device, sigmoid):
+        if h % 32 or w % 32:
+            raise ValueError("height and width must be multiples of 32 (five 2x2 poolings)")
+        if final[0].shape[0] != 1 or final[0].shape[1] != 32 or dec1[0].shape[0] != 32:
+            raise NotImplementedError("fused head expects num_classes == 1 and num_filters == 32")
+        self.n, self.h, self.w = n, h, w
+        self.device = device
+        self.ops = []
+        f32 = lambda b: b.detach().float().contiguous()
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
+
+        # concat slabs: [decoder output | encoder skip], torch.cat([dec, conv], 1) order
+        skip_c = [st[-1][0].shape[0] for st in enc]                # 64, 128, 256, 512, 512
+        up_c = [d[2].shape[1] for d in decs]                       # center..dec2 ConvT output channels
+        # decs[i] output feeds the slab of encoder stage 4-i (center -> conv5 slab, dec2 -> conv1 slab)
+        slabs = []
+        for s in range(5):
+            hh, ww = h >> s, w >> s
+            slabs.append(S(hh, ww, up_c[4 - s] + skip_c[s]))
+        self.slabs = slabs
+
+        self.x_patch = S(h, w, 32)
+        cur = self.x_patch.view()
+        for s, stage in enumerate(enc):
+            hh, ww = h >> s, w >> s
+            for li, (wt, bs) in enumerate(stage):
+                cout = wt.shape[0]
+                last = li == len(stage) - 1
+                dst = slabs[s].view(up_c[4 - s], cout) if last else S(hh, ww, cout).view()
+                if s == 0 and li == 0:
+                    self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt), f32(bs)))
+                else:
+                    self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt), f32(bs)))
+                cur = dst
+            pooled = S(hh // 2, ww // 2, cur.c).view()
+            self.ops.append(PoolOp(cur, pooled))
+            cur = pooled
+
+        # center consumes the pooled conv5; dec5..dec2 consume the concat slabs
+        for i, (cw, cb, tw, tb) in enumerate(decs):
+            s = 5 - i  # resolution level of this block's input
+            hh, ww = h >> s, w >> s
+            src = cur if i == 0 else slabs[s].view()
+            mid = S(hh, ww, cw.shape[0]).view()
+            self.ops.append(ConvOp(N.CONV_3X3, src, mid, pack_conv3x3(cw), f32(cb)))
+            dst = slabs[s - 1].view(0, tw.shape[1])
+            self.ops.append(ConvOp(N.CONVT_4X4_S2, mid, dst, pack_convT4x4(tw), f32(tb)))
+
+        self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
+        head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid,
+                self.out)
+        self.ops.append(ConvOp(N.CONV_3X3, slabs[0].view(), None, pack_conv3x3(dec1[0]), f32(dec1[1]), head=head))
+        self.flops = sum(op.flops for op in self.ops)
+        self.launches = sum(op.launches for op in self.ops)
+
+    def load_nchw(self, x):
+        """float [n,3,h,w] CUDA tensor -> first-layer operand rows."""
+        x = x.contiguous()
+        N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), x.shape[0], x.shape[1], x.shape[2], x.shape[3],
+                                                N.c_vp(self.x_patch.t.data_ptr()), N.stream_ptr()))
+
+    def run(self):
+        """Enqueue the whole forward on the current stream; result lands in self.out [n,h,w] float32."""
+        st = N.stream_ptr()
+        for op in self.ops:
+            op(st)
+        return self.out

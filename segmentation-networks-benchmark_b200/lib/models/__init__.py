@@ -1,0 +1,3 @@
+"""nn.Module mirrors of the reference's lib/models for the hot path (same class names and state_dict keys)."""
+from .unet11 import UNet11  # noqa: F401
+from .unet16 import UNet16  # noqa: F401

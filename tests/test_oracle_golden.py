@@ -1,0 +1,142 @@
+"""The CPU oracle against the vectors produced by the reference itself (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets_oracle as no
+from oracle import synth
+from oracle import tiles_oracle as to
+
+
+def test_slicer_plan_kats(kats):
+    for c in kats["slicer"]["cases"]:
+        s = to.SlicerOracle(tuple(c["shape"]), c["tile"], c["step"], image_margin=c["margin"])
+        assert [s.margin_left, s.margin_right, s.margin_top, s.margin_bottom] == c["margins"]
+        assert len(s.crops) == c["n_crops"]
+        assert [list(x) for x in s.crops[:3]] == c["crops_head"]
+        assert [list(x) for x in s.crops[-3:]] == c["crops_tail"]
+        assert [sum(x[0] for x in s.crops), sum(x[1] for x in s.crops)] == c["crops_sum"]
+
+
+def test_slicer_plan_errors(kats):
+    for c in kats["slicer"]["errors"]:
+        if c["error"] is None:
+            to.SlicerOracle(tuple(c["shape"]), c["tile"], c["step"], image_margin=c["margin"])
+        else:
+            with pytest.raises(ValueError):
+                to.SlicerOracle(tuple(c["shape"]), c["tile"], c["step"], image_margin=c["margin"])
+
+
+@pytest.mark.parametrize("name", ["u8c3", "f32c1", "u8_2d", "f64c3", "tiny_multi_reflect"])
+def test_split_bit_exact(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "split_merge.npz"))
+    img = g[name + "_image"]
+    tile, step = (int(v) for v in g[name + "_cfg"])
+    s = to.SlicerOracle(img.shape, tile, step)
+    tiles = np.stack(s.split(img))
+    assert tiles.dtype == g[name + "_tiles"].dtype and tiles.shape == g[name + "_tiles"].shape
+    assert np.array_equal(tiles, g[name + "_tiles"])
+    assert np.array_equal(s.cut_patch(img, min(3, len(s.crops) - 1)), g[name + "_cut3"])
+
+
+@pytest.mark.parametrize("weight", ["mean", "pyramid"])
+def test_merge_bit_exact(golden_dir, weight):
+    g = np.load(os.path.join(golden_dir, "split_merge.npz"))
+    s = to.SlicerOracle((37, 53, 3), 16, 8, weight=weight)
+    out = s.merge(list(g["merge_%s_tiles" % weight]))
+    assert out.dtype == np.float32 and np.array_equal(out, g["merge_%s_out" % weight])
+    ident = s.merge(s.split(g["merge_%s_identity_in" % weight]))
+    assert np.array_equal(ident, g["merge_%s_identity_out" % weight])
+    assert np.array_equal(ident, g["merge_%s_identity_in" % weight])  # weighted mean of equal values is exact
+
+
+def test_merge_u8(golden_dir):
+    g = np.load(os.path.join(golden_dir, "split_merge.npz"))
+    s = to.SlicerOracle((37, 53, 3), 16, 8, weight="mean")
+    assert np.array_equal(s.merge(list(g["merge_u8_tiles"]), dtype=np.uint8), g["merge_u8_out"])
+
+
+def test_merge_rejects_wrong_count():
+    s = to.SlicerOracle((37, 53, 3), 16, 8)
+    with pytest.raises(ValueError):
+        s.merge([np.zeros((16, 16, 1), np.float32)])
+
+
+def test_pyramid_weight(golden_dir, kats):
+    g = np.load(os.path.join(golden_dir, "pyramid.npz"))
+    for n in (16, 24, 64):
+        assert np.array_equal(to.pyramid_weight(n, n), g["w%d" % n])
+    assert np.array_equal(to.pyramid_weight_loop(16, 16), g["w16"])
+    w = to.pyramid_weight(512, 512)
+    k = kats["pyramid"]["n512"]
+    assert w.min() == k["min"] and w.max() == k["max"] and w.sum() == k["sum"]
+    assert np.array_equal(w, w.T) and np.array_equal(w, w[::-1]) and np.array_equal(w, w[:, ::-1])
+
+
+def test_normalize_lut(golden_dir):
+    g = np.load(os.path.join(golden_dir, "normalize.npz"))
+    assert np.array_equal(to.normalize_image(g["levels"]), g["out64"])
+    lut = to.normalize_lut()
+    assert lut.shape == (3, 256) and lut.dtype == np.float32
+    assert np.array_equal(lut, g["chw_f32"][:, :, 0])   # [C][256][1] -> [C][256]
+
+
+def test_tta(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tta.npz"))
+    views = np.stack(to.tta_d4_aug(list(g["tiles"])))
+    assert np.array_equal(views, g["views"])
+    deaug = np.stack(to.tta_d4_deaug(list(g["preds"])))
+    assert deaug.dtype == np.float32 and np.array_equal(deaug, g["deaug"])
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_loss_and_metrics(kats, seed):
+    k = kats["loss"]["seed%d" % seed]
+    logits, targets = synth.logits_targets(seed, tuple(k["shape"]))
+    assert float(no.bce_jaccard(logits, targets)) == pytest.approx(k["bce_jaccard"], rel=1e-6)
+    assert float(no.bce_with_sigmoid(logits, targets)) == pytest.approx(k["bce"], rel=1e-6)
+    assert float(no.smooth_jaccard(logits, targets)) == pytest.approx(k["smooth_jaccard"], rel=1e-6)
+    assert float(no.jaccard_score(logits, targets)) == pytest.approx(k["jaccard_score"], rel=1e-6)
+    assert float(no.pixel_accuracy(logits, targets)) == pytest.approx(k["pixel_accuracy"], rel=1e-7)
+    assert no.confusion_counts(torch.sigmoid(logits), targets).tolist() == k["counts"]
+    tp, tn, fp, fn = no.pr_curve_counts(logits, targets)
+    assert tp.tolist() == k["pr_tp"] and tn.tolist() == k["pr_tn"]
+    assert fp.tolist() == k["pr_fp"] and fn.tolist() == k["pr_fn"]
+
+
+@pytest.mark.parametrize("arch", ["unet16", "unet11"])
+def test_model_logits(golden_dir, arch):
+    g = np.load(os.path.join(golden_dir, "models.npz"))
+    sd = synth.vgg_unet_state_dict(arch, seed=1)
+    with torch.no_grad():
+        y = no.unet_vgg_forward(sd, torch.from_numpy(g[arch + "_x"]), arch).numpy()
+    assert y.shape == g[arch + "_logits"].shape
+    assert np.abs(y - g[arch + "_logits"]).max() < 1e-5   # same ATen CPU kernels; order of ops identical
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_predict_tiled_pipeline(golden_dir, tta):
+    """inria_submit.predict_tiled restated with oracle parts only reproduces the reference's merged mask."""
+    g = np.load(os.path.join(golden_dir, "predict_tiled.npz"))
+    key = "tta" if tta else "plain"
+    sd = synth.vgg_unet_state_dict("unet16", seed=2)
+    image = g["image"]
+    assert np.array_equal(image, synth.image_u8(9, 96, 80))
+    x = to.normalize_image(image)
+    s = to.SlicerOracle(x.shape, 64, 32, weight="pyramid")
+    patches = s.split(x)
+    if tta:
+        patches = to.tta_d4_aug(patches)
+    with torch.no_grad():
+        probs = torch.sigmoid(no.unet_vgg_forward(sd, torch.from_numpy(to.to_nchw_float(patches)), "unet16")).numpy()
+    preds = list(np.moveaxis(probs, 1, -1))
+    if tta:
+        preds = to.tta_d4_deaug(preds)
+    assert np.abs(np.stack(preds) - g[key + "_tiles"]).max() < 2e-6
+    merged = s.merge(preds, dtype=np.float32)
+    assert np.abs(merged - g[key + "_merged"]).max() < 2e-6
+    # merge itself is bit-exact when fed the reference's own tiles
+    assert np.array_equal(s.merge(list(g[key + "_tiles"]), dtype=np.float32), g[key + "_merged"])
+    assert np.array_equal(((g[key + "_merged"] > 0.5) * 255).astype(np.uint8), g[key + "_mask"])
