@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Headline benchmark: megapixels/s of tiled UNet16 ("AlbuNet") inference on synthetic 5000x5000 Inria-shaped
+images, 512 tile / 384 step, pyramid-weighted merge (BASELINE.json configs[2]; configs[3] when --gpus > 1).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+A step = one image per rank through split -> UNet16 -> merge -> threshold -> confusion counts (+ NCCL all-reduce of
+the counts and gather of the masks when N > 1).  Rank 0 prints ONE JSON line (see the driver contract in DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGE_HW = 5000
+TILE, STEP = 512, 384
+MPX_PER_IMAGE = IMAGE_HW * IMAGE_HW / 1e6
+METRIC = "megapixels/sec tiled U-Net inference (UNet16/AlbuNet, 5000x5000, 512/384)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p.get("bf16_tflops_sustained", 1400.0)), float(p.get("hbm_gbs", 6650.0)), "measured"
+    return 1400.0, 6650.0, "fallback"   # B200_PROFILING.md: ~1.4 PFLOP/s sustained, 6.65 TB/s
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step(sd, image, n_net_tiles):
+    """The reference algorithm (oracle port) on the host: float64 normalise + split of the whole image, UNet16 fp32
+    on `n_net_tiles` tiles (extrapolated to all 169), pyramid merge of 169 tiles, threshold.  Returns seconds/image."""
+    from oracle import nets_oracle as no
+    from oracle import tiles_oracle as to
+
+    t0 = time.perf_counter()
+    x = to.normalize_image(image)
+    s = to.SlicerOracle(x.shape, TILE, STEP, weight="pyramid")
+    tiles = s.split(x)
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        batch = torch.from_numpy(to.to_nchw_float(tiles[:n_net_tiles]))
+        probs = torch.sigmoid(no.unet_vgg_forward(sd, batch, "unet16")).numpy()
+    t2 = time.perf_counter()
+    preds = [np.moveaxis(probs[i % n_net_tiles], 0, -1) for i in range(len(tiles))]
+    mask = ((s.merge(preds, dtype=np.float32) > 0.5) * 255).astype(np.uint8)
+    t3 = time.perf_counter()
+    assert mask.shape == (IMAGE_HW, IMAGE_HW, 1)
+    return (t1 - t0) + (t2 - t1) * len(tiles) / n_net_tiles + (t3 - t2)
+
+
+def cpu_baseline(n_net_tiles=4, repeats=1):
+    from oracle import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.vgg_unet_state_dict("unet16", seed=0)
+    image = synth.image_u8(0, IMAGE_HW, IMAGE_HW)
+    secs = [cpu_reference_step(sd, image, n_net_tiles) for _ in range(repeats)]
+    return {"value": MPX_PER_IMAGE / min(secs), "unit": "Mpx/s", "cores": cores, "kind": "port",
+            "sample": "full float64 normalise+split and pyramid merge of one 5000x5000 image; UNet16 fp32 (CPU PyTorch) "
+                      "on %d of 169 tiles, net time extrapolated x169/%d" % (n_net_tiles, n_net_tiles)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.vgg_unet_state_dict("unet16", seed=0)
+    image = synth.image_u8(0, IMAGE_HW, IMAGE_HW)
+    n_net = 4
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, image, 2)
+    secs = [cpu_reference_step(sd, image, n_net) for _ in range(args.steps)]
+    sec = sum(secs) / len(secs)
+    value = MPX_PER_IMAGE / sec
+    sample = ("per step: full float64 normalise+split and pyramid merge of one 5000x5000 image, UNet16 fp32 on %d of "
+              "169 tiles extrapolated x169/%d (oracle port of lib/tiles.py + lib/models/unet16.py; the reference "
+              "is Python and cannot travel to the GPU box)" % (n_net, n_net))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: UNet16 tiled inference, 5000x5000x3 u8, tile 512 / step 384, pyramid merge",
+                       "tiles_per_image": 169, "tta": False},
+            "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import torch.distributed as dist
+
+    import snb_b200  # noqa: F401
+    from oracle import synth
+    from snb_b200 import dist as sdist
+    from snb_b200 import inria_submit as sub
+    from snb_b200.engine import ConvOp
+    from snb_b200.lib import metrics
+    from snb_b200.lib.models import UNet16
+
+    rank, world, local_rank = sdist.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    model = UNet16()
+    model.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=0))
+    model = model.to(dev).eval()
+    pred = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), TILE, STEP, batch_size=args.batch, tta=args.tta,
+                              device=dev)
+
+    # distinct synthetic images per rank (weak scaling: one image per rank per step)
+    n_img = 2
+    host_imgs = [torch.from_numpy(synth.image_u8(100 * rank + i, IMAGE_HW, IMAGE_HW)).pin_memory() for i in range(n_img)]
+    dev_imgs = [h.to(dev) for h in host_imgs]
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    gts = [(torch.rand((IMAGE_HW, IMAGE_HW, 1), device=dev, generator=g) > 0.5).to(torch.uint8) for _ in range(n_img)]
+    host_mask = torch.empty((IMAGE_HW, IMAGE_HW, 1), dtype=torch.uint8).pin_memory()
+    host_counts = torch.empty(4, dtype=torch.int64).pin_memory()
+    gathered = [None]
+
+    def exchange(mask, counts):
+        if world > 1:
+            sdist.allreduce_counts(counts)                                    # NCCL all-reduce of int64[4]
+            gathered[0] = sdist.gather_masks(mask.view(1, IMAGE_HW, IMAGE_HW), world)   # NCCL gather of u8 masks
+        return counts
+
+    def step_resident(i):
+        merged, mask = pred.predict_device(dev_imgs[i % n_img])
+        counts = metrics.confusion_counts_from_probs(merged, gts[i % n_img])
+        return exchange(mask, counts)
+
+    def step_e2e(i):
+        d = host_imgs[i % n_img].to(dev, non_blocking=True)                  # H2D from pinned memory
+        merged, mask = pred.predict_device(d)
+        counts = exchange(mask, metrics.confusion_counts_from_probs(merged, gts[i % n_img]))
+        host_mask.copy_(mask, non_blocking=True)                             # D2H of the step's result
+        host_counts.copy_(counts, non_blocking=True)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        fence()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # per-launch conv timing, live in the timed region: one event after every op of every plan run
+    marks = []
+    plan = pred.plan
+    orig_run = plan.run
+
+    def run_marked():
+        st = snb_b200._native.stream_ptr()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.ops) + 1)]
+        ev[0].record()
+        for k, op in enumerate(plan.ops):
+            op(st)
+            ev[k + 1].record()
+        marks.append(ev)
+        return plan.out
+
+    plan.run = run_marked
+    ms_total = timed(step_resident, args.steps)
+    plan.run = orig_run
+    clocks = sampler.summary()
+
+    conv_ms, conv_flops, conv_launches, other_ms = 0.0, 0.0, 0, 0.0
+    for ev in marks:
+        for k, op in enumerate(plan.ops):
+            dt = ev[k].elapsed_time(ev[k + 1])
+            if isinstance(op, ConvOp):
+                conv_ms += dt
+                conv_flops += op.flops
+                conv_launches += 1
+            else:
+                other_ms += dt
+
+    for i in range(min(2, args.warmup)):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    ms_step = ms_total / args.steps
+    value = world * MPX_PER_IMAGE / (ms_step / 1e3)
+    e2e_value = world * MPX_PER_IMAGE / (ms_e2e / args.steps / 1e3)
+    peak_tf, peak_bw, peak_src = measured_peaks()
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: UNet16 tiled inference, 5000x5000x3 u8, tile 512 / step 384, pyramid merge"
+                               + ("; configs[3]: one image per rank per step, NCCL all-reduce of IoU counts + gather of masks"
+                                  if world > 1 else ""),
+                   "tiles_per_image": pred.n_tiles, "tile_batch": pred.batch, "tta": bool(args.tta),
+                   "l2_policy": "no flush needed: per-step working set (activations of %d tiles/batch, ~%.1f GB) >> 126 MB L2; "
+                                "%d images rotate" % (pred.batch, 0.245 * pred.batch, n_img),
+                   "flop_per_image": pred.flops_per_image},
+        "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": IMAGE_HW * IMAGE_HW * 3,
+                "d2h_bytes_per_step": IMAGE_HW * IMAGE_HW + 32},
+        "gpu_launches": (pred.launches_per_image + 1) * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf, "traffic": None,
+                     "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
+                     "peak_source": peak_src + " bf16_tflops_sustained",
+                     "conv_share_of_step": conv_ms / ms_total, "conv_ms_per_step": conv_ms / args.steps,
+                     "pool_ms_per_step": other_ms / args.steps,
+                     "whole_step_tflops": pred.flops_per_image / (ms_step / 1e3) / 1e12},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=13, help="tiles per network launch")
+    ap.add_argument("--tta", action="store_true", help="D4 test-time augmentation (8 views per tile)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+        run_cuda(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,7 +52,7 @@ def vgg_unet_state_dict(arch='unet16', seed=0):
         sd[name + '.block.1.bias'] = _bias(rs, out)
     sd['dec1.conv.weight'] = _he(rs, (32, 96, 3, 3), 96 * 9)
     sd['dec1.conv.bias'] = _bias(rs, 32)
-    sd['final.weight'] = _he(rs, (1, 32, 1, 1), 32, gain=2.0)
+    sd['final.weight'] = _he(rs, (1, 32, 1, 1), 32, gain=0.5)   # logits ~N(0,1): probabilities span (0,1)
     sd['final.bias'] = _bias(rs, 1)
     return sd
 

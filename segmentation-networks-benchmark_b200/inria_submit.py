@@ -1,0 +1,96 @@
+"""Tiled full-resolution inference, the path reference inria_submit.py:237-306 drives, kept on the device.
+
+`predict_tiled(image, model, test_transform, patch_size, batch_size)` keeps the reference signature; underneath,
+`TiledPredictor` holds the whole per-image pipeline on one GPU:
+
+    uint8 HWC image (HBM) --snb_split_norm_u8--> first-layer operand rows of a batch of tiles
+        --VGGUNetPlan.run (tcgen05 convs, sigmoid fused into the last epilogue)--> float32 probabilities
+        --snb_merge (D4 de-augmentation, float64 pyramid-weighted overlap-add, threshold)--> float32 map + uint8 mask
+
+so an image crosses PCIe once in (75 MB) and once out (25 MB) instead of once per batch in each direction
+(inria_submit.py:249,251).  The reference hard-codes tile_step = patch_size // 2 and no way to switch TTA off
+(inria_submit.py:240,243); both are parameters here, defaulting to the reference behaviour.
+"""
+import numpy as np
+import torch
+
+from . import _native as N
+from .lib.augmentations import NormalizeImage, find_normalize
+from .lib.tiles import ImageSlicer
+
+INRIA_MEAN = [0.40273115, 0.45046371, 0.42960134]   # reference lib/datasets/Inria.py:34-35
+INRIA_STD = [3.15086464, 3.29831641, 3.63201004]
+
+
+class TiledPredictor:
+    def __init__(self, model, image_shape, patch_size, tile_step=None, batch_size=1, weight='pyramid', tta=True,
+                 normalize=None, device=None):
+        N.require_cuda()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.image_shape = tuple(image_shape)
+        self.channels = image_shape[2] if len(image_shape) == 3 else 1
+        self.patch_size = patch_size
+        self.tile_step = patch_size // 2 if tile_step is None else tile_step
+        self.views = 8 if tta else 1
+        self.slicer = ImageSlicer(image_shape, patch_size, self.tile_step, weight=weight)
+        self.n_tiles = len(self.slicer.crops)
+        self.batch = max(1, min(int(batch_size), self.n_tiles))
+        norm = normalize if normalize is not None else NormalizeImage(mean=INRIA_MEAN, std=INRIA_STD)
+        with torch.cuda.device(self.device):
+            self.lut = torch.from_numpy(norm.lut()).to(self.device)
+            self.plan = model.plan(self.batch, patch_size, patch_size, sigmoid=True)
+            self.weight = self.slicer.weight_on_device(self.device)
+            T = patch_size
+            self.probs = torch.empty((self.n_tiles, self.views, T, T, 1), dtype=torch.float32, device=self.device)
+            h, w = image_shape[0], image_shape[1]
+            self.merged = torch.empty((h, w, 1), dtype=torch.float32, device=self.device)
+            self.mask = torch.empty((h, w, 1), dtype=torch.uint8, device=self.device)
+        n_chunks = (self.n_tiles + self.batch - 1) // self.batch
+        # kernels enqueued per image: per chunk and view one split + the plan, then one merge
+        self.launches_per_image = n_chunks * self.views * (1 + self.plan.launches) + 1
+        self.flops_per_image = self.plan.flops / self.batch * self.n_tiles * self.views
+
+    def predict_device(self, d_image):
+        """uint8 [H][W][C] CUDA tensor -> (float32 [H][W][1] merged probabilities, uint8 [H][W][1] mask); async."""
+        if d_image.dtype != torch.uint8 or not d_image.is_cuda or tuple(d_image.shape[:2]) != self.image_shape[:2]:
+            raise ValueError("expected a uint8 CUDA image of shape %s" % (self.image_shape,))
+        d_image = d_image.contiguous()
+        lib, st = N.lib(), N.stream_ptr()
+        for begin in range(0, self.n_tiles, self.batch):
+            count = min(self.batch, self.n_tiles - begin)
+            for v in range(self.views):
+                N.check(lib.snb_split_norm_u8(self.slicer.handle, N.ptr(d_image), self.channels, N.ptr(self.lut), v,
+                                              N.LAYOUT_PATCH32, N.c_vp(self.plan.x_patch.t.data_ptr()), begin, count, st))
+                out = self.plan.run()
+                self.probs[begin:begin + count, v, :, :, 0].copy_(out[:count])
+        N.check(lib.snb_merge(self.slicer.handle, N.ptr(self.probs), N.DT_F32, 1, self.views, N.ptr(self.weight),
+                              N.ptr(self.merged), N.DT_F32, N.ptr(self.mask), 0.5, st))
+        return self.merged, self.mask
+
+    def __call__(self, image):
+        """numpy uint8 H x W x C -> numpy float32 H x W x 1 (what reference predict_tiled returns)."""
+        d = torch.from_numpy(np.ascontiguousarray(image)).to(self.device, non_blocking=True)
+        merged, _ = self.predict_device(d)
+        return merged.cpu().numpy()
+
+
+def predict_tiled(image, model, test_transform, patch_size, batch_size, tile_step=None, tta=True, weight='pyramid'):
+    """Reference signature (inria_submit.py:237) plus the knobs it hard-codes.  `image` is the raw uint8 array
+    read_rgb returns; `test_transform` must be the reference-style normalisation (it is folded into a LUT)."""
+    norm = find_normalize(test_transform)
+    if norm is None:
+        raise NotImplementedError("test_transform must be Sequential([ImageOnly(NormalizeImage(...))])")
+    if image.dtype != np.uint8:
+        raise NotImplementedError("the fused pipeline takes the uint8 image (normalisation happens on the device)")
+    cache = model.__dict__.setdefault('_tiled_predictors', {})
+    key = (image.shape, patch_size, tile_step, batch_size, tta, weight, tuple(norm.mean), tuple(norm.std), norm.scale,
+           model._stamp())
+    if key not in cache:
+        cache.clear()
+        cache[key] = TiledPredictor(model, image.shape, patch_size, tile_step, batch_size, weight, tta, norm)
+    return cache[key](image)
+
+
+def mask_from_probability(mask):
+    """inria_submit.py:305."""
+    return ((mask > 0.5) * 255).astype(np.uint8)

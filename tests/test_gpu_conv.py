@@ -1,0 +1,145 @@
+"""-m gpu: the tcgen05 implicit-GEMM convolution through the C ABI against torch fp32 on bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import snb_b200  # noqa: F401
+from snb_b200 import _native as N
+from snb_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rand_slab(n, h, w, c, gen):
+    s = E.Slab(n, h, w, c, "cuda")
+    s.t.copy_(torch.randn((n, h, w, c), device="cuda", generator=gen).to(torch.bfloat16))
+    return s
+
+
+def nchw(view):
+    return view.torch().float().permute(0, 3, 1, 2).contiguous()
+
+
+def check(got, want, tol=2e-2):
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item() + 1e-6
+    assert err <= tol * scale, "max abs err %g vs scale %g" % (err, scale)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,relu", [
+    (1, 8, 16, 64, 64, True),        # exactly one M tile, one K chunk per tap
+    (2, 32, 32, 64, 128, True),
+    (1, 16, 16, 128, 256, False),
+    (1, 24, 40, 256, 512, True),     # two N tiles, ragged spatial tiles (40 = 2.5 x 16)
+    (3, 16, 32, 96, 32, True),       # BK = 32 path (SW64), BN = 32 store path
+    (1, 64, 64, 192, 128, True),
+    (1, 7, 7, 64, 64, True),         # smaller than one tile: TMA OOB fill + clipped store
+])
+def test_conv3x3(cuda, n, h, w, cin, cout, relu):
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
+    src = rand_slab(n, h, w, cin, g)
+    dst = E.Slab(n, h, w, cout, "cuda")
+    dst.t.fill_(float("nan"))
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    op = E.ConvOp(N.CONV_3X3, src.view(), dst.view(), E.pack_conv3x3(wt), bias, relu=relu)
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    want = F.conv2d(nchw(src.view()), bf(wt), bias, padding=1)
+    if relu:
+        want = F.relu(want)
+    check(nchw(dst.view()), want)
+    assert op.flops == 2.0 * n * h * w * cin * cout * 9
+
+
+def test_conv_into_concat_slab_and_from_slab_slice(cuda):
+    """Producer writes at a channel offset of a wider slab; consumer reads a channel range of a slab."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, h, w = 2, 16, 32
+    src = rand_slab(n, h, w, 192, g)
+    dst = E.Slab(n, h, w, 96, "cuda")
+    dst.t.zero_()
+    wt = torch.randn((64, 128, 3, 3), device="cuda", generator=g) * 0.03
+    bias = torch.randn(64, device="cuda", generator=g)
+    op = E.ConvOp(N.CONV_3X3, src.view(64, 128), dst.view(32, 64), E.pack_conv3x3(wt), bias)
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    want = F.relu(F.conv2d(nchw(src.view(64, 128)), bf(wt), bias, padding=1))
+    check(nchw(dst.view(32, 64)), want)
+    assert torch.count_nonzero(dst.t[..., :32]) == 0                      # neighbours in the slab untouched
+
+
+def test_first_layer_as_patch_gemm(cuda):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, h, w = 2, 32, 48
+    x = torch.randn((n, 3, h, w), device="cuda", generator=g)
+    rows = E.Slab(n, h, w, 32, "cuda")
+    N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), n, 3, h, w, N.c_vp(rows.t.data_ptr()), N.stream_ptr()))
+    wt = torch.randn((64, 3, 3, 3), device="cuda", generator=g) * 0.2
+    bias = torch.randn(64, device="cuda", generator=g)
+    dst = E.Slab(n, h, w, 64, "cuda")
+    op = E.ConvOp(N.CONV_1X1, rows.view(), dst.view(), E.pack_first_conv3x3(wt), bias)
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    check(nchw(dst.view()), F.relu(F.conv2d(bf(x), bf(wt), bias, padding=1)))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 16, 64, 64), (2, 16, 16, 512, 256), (1, 32, 32, 128, 32),
+                                            (1, 12, 20, 256, 64)])
+def test_conv_transpose_4x4_s2(cuda, n, h, w, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    src = rand_slab(n, h, w, cin, g)
+    dst = E.Slab(n, 2 * h, 2 * w, cout + 32, "cuda")                      # written at channel offset 0 of a wider slab
+    dst.t.zero_()
+    wt = torch.randn((cin, cout, 4, 4), device="cuda", generator=g) * (2.0 / (4 * cin)) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    op = E.ConvOp(N.CONVT_4X4_S2, src.view(), dst.view(0, cout), E.pack_convT4x4(wt), bias)
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    want = F.relu(F.conv_transpose2d(nchw(src.view()), bf(wt), bias, stride=2, padding=1))
+    check(nchw(dst.view(0, cout)), want)
+    assert torch.count_nonzero(dst.t[..., cout:]) == 0
+    assert op.flops == 2.0 * n * h * w * cin * cout * 16
+
+
+@pytest.mark.parametrize("sigmoid", [False, True])
+def test_fused_head(cuda, sigmoid):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, h, w = 2, 24, 32
+    src = rand_slab(n, h, w, 96, g)
+    wt = torch.randn((32, 96, 3, 3), device="cuda", generator=g) * 0.05
+    bias = torch.randn(32, device="cuda", generator=g) * 0.1
+    hw = torch.randn(32, device="cuda", generator=g) * 0.3
+    out = torch.full((n, h, w), float("nan"), device="cuda")
+    op = E.ConvOp(N.CONV_3X3, src.view(), None, E.pack_conv3x3(wt), bias, head=(hw, 0.125, sigmoid, out))
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    feat = F.relu(F.conv2d(nchw(src.view()), bf(wt), bias, padding=1))
+    want = (feat * hw.view(1, 32, 1, 1)).sum(1) + 0.125
+    if sigmoid:
+        want = torch.sigmoid(want)
+    assert (out - want).abs().max().item() < 2e-3
+
+
+def test_maxpool_and_exit_layout(cuda):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = rand_slab(2, 16, 24, 96, g)
+    dst = E.Slab(2, 8, 12, 64, "cuda")
+    E.PoolOp(src.view(32, 64), dst.view())(N.stream_ptr())
+    want = F.max_pool2d(nchw(src.view(32, 64)), 2, 2)
+    assert torch.equal(nchw(dst.view()), want)
+    out = torch.empty((2, 64, 8, 12), device="cuda")
+    N.check(N.lib().snb_nhwc_bf16_to_nchw_f32(N.c_vp(dst.t.data_ptr()), 2, 8, 12, 64, 64, N.ptr(out), N.stream_ptr()))
+    assert torch.equal(out, want)
+
+
+def test_bad_descriptors_raise(cuda):
+    s = E.Slab(1, 8, 16, 48, "cuda")
+    d = E.Slab(1, 8, 16, 64, "cuda")
+    w = torch.zeros((9, 64, 48), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        E.ConvOp(N.CONV_3X3, s.view(), d.view(), w, torch.zeros(64, device="cuda"))   # cin not a multiple of 32

@@ -1,0 +1,68 @@
+"""-m gpu: fused loss / IoU / PR-curve reductions through the C ABI against the oracle and reference values."""
+import numpy as np
+import pytest
+import torch
+
+import snb_b200  # noqa: F401
+from oracle import nets_oracle as no
+from oracle import synth
+from snb_b200.lib import losses, metrics
+
+pytestmark = pytest.mark.gpu
+
+REL = 2e-6   # float sums: fp32 elementwise, fp64 accumulation; reference sums in fp32 -> tolerance, not bits
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_against_reference_values(cuda, kats, seed):
+    k = kats["loss"]["seed%d" % seed]
+    logits, targets = synth.logits_targets(seed, tuple(k["shape"]))
+    x, t = logits.cuda(), targets.cuda()
+    assert float(losses.BCEWithLogitsLossAndSmoothJaccard()(x, t)) == pytest.approx(k["bce_jaccard"], rel=REL)
+    assert float(losses.BCEWithSigmoidLoss()(x, t)) == pytest.approx(k["bce"], rel=REL)
+    assert float(losses.SmoothJaccardLoss()(x, t)) == pytest.approx(k["smooth_jaccard"], rel=REL)
+    assert float(metrics.JaccardScore()(x, t)) == pytest.approx(k["jaccard_score"], rel=REL)
+    assert float(metrics.PixelAccuracy()(x, t)) == pytest.approx(k["pixel_accuracy"], rel=1e-7)
+    assert metrics.confusion_counts(x, t).tolist() == k["counts"]                       # integer: bit-exact
+    assert metrics.confusion_counts_from_probs(torch.sigmoid(logits).cuda(), t).tolist() == k["counts"]
+    m = metrics.PRCurveMeter()
+    m.update(x, t)
+    assert m.tp.tolist() == k["pr_tp"] and m.tn.tolist() == k["pr_tn"]
+    assert m.fp.tolist() == k["pr_fp"] and m.fn.tolist() == k["pr_fn"]
+    m.update(x, t)                                                                      # accumulates like the reference
+    assert m.tp.tolist() == [2 * v for v in k["pr_tp"]]
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4096 + 7])
+@pytest.mark.parametrize("tdt", [torch.int64, torch.uint8, torch.float32])
+def test_ragged_sizes_and_target_dtypes(cuda, n, tdt):
+    logits, targets = synth.logits_targets(100 + n, (n,))
+    s, c = losses.fused_sums(logits.cuda(), targets.to(tdt).cuda())
+    p = torch.sigmoid(logits.double())
+    z = torch.nn.functional.logsigmoid(logits.double())
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(z, targets.double(), reduction="sum")
+    want = torch.stack([bce, (p * targets).sum(), p.sum(), targets.double().sum()])
+    assert torch.allclose(s.cpu(), want, rtol=1e-5, atol=1e-6)
+    assert c.tolist() == no.confusion_counts(torch.sigmoid(logits), targets).tolist()
+    assert int(c.sum()) == n
+
+
+def test_no_cpu_fallback():
+    logits, targets = synth.logits_targets(0, (16,))
+    with pytest.raises(RuntimeError):
+        losses.fused_sums(logits, targets)
+
+
+def test_full_size_counts_are_additive(cuda):
+    """169 x 512 x 512 elements (one Inria image of tiles): counts of the halves add up to the whole (the multi-GPU
+    all-reduce property) and equal torch's own integer count."""
+    n = 169 * 512 * 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(n, device="cuda", generator=g)
+    t = (torch.rand(n, device="cuda", generator=g) > 0.5).to(torch.uint8)
+    whole = metrics.confusion_counts(x, t)
+    h = n // 2
+    parts = metrics.confusion_counts(x[:h], t[:h]) + metrics.confusion_counts(x[h:], t[h:])
+    assert whole.tolist() == parts.tolist() and int(whole.sum()) == n
+    pred = torch.sigmoid(x) > 0.5
+    assert int(whole[0]) == int((pred & (t != 0)).sum()) and int(whole[3]) == int((~pred & (t == 0)).sum())

@@ -1,0 +1,196 @@
+"""CPU: host-side mirror of the reference interface (ImageSlicer attributes, weight packing, model key names,
+transforms) and the world_size-2 sharding / exchange logic over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import snb_b200  # noqa: F401
+from oracle import nets_oracle as no
+from oracle import synth
+from oracle import tiles_oracle as to
+from snb_b200 import dist as sdist
+from snb_b200 import engine as E
+from snb_b200.lib import augmentations as aug
+from snb_b200.lib.models import UNet11, UNet16
+from snb_b200.lib.tiles import ImageSlicer, compute_patch_weight_loss
+
+
+def test_image_slicer_attributes_match_reference(kats):
+    for c in kats["slicer"]["cases"]:
+        s = ImageSlicer(tuple(c["shape"]), c["tile"], c["step"], image_margin=c["margin"])
+        assert (s.image_height, s.image_width, s.tile_size, s.tile_step) == (c["shape"][0], c["shape"][1], c["tile"], c["step"])
+        assert [s.margin_left, s.margin_right, s.margin_top, s.margin_bottom] == c["margins"]
+        assert len(s.crops) == c["n_crops"] and [list(v) for v in s.crops[:3]] == c["crops_head"]
+        o = to.SlicerOracle(tuple(c["shape"]), c["tile"], c["step"], image_margin=c["margin"])
+        assert s.crops == o.crops
+
+
+def test_image_slicer_errors(kats):
+    for c in kats["slicer"]["errors"]:
+        if c["error"]:
+            with pytest.raises(ValueError):
+                ImageSlicer(tuple(c["shape"]), c["tile"], c["step"], image_margin=c["margin"])
+    with pytest.raises(ValueError):
+        ImageSlicer((64, 64), 32)                       # the default tile_step=0 raises in the reference too
+    with pytest.raises(KeyError):
+        ImageSlicer((64, 64), 32, 16, weight="gauss")
+    s = ImageSlicer((64, 64), 32, 16)
+    with pytest.raises(ValueError):
+        s.merge([np.zeros((32, 32, 1), np.float32)])    # wrong tile count (lib/tiles.py:138-139)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_for_compute():
+    s = ImageSlicer((64, 64), 32, 16)
+    with pytest.raises(RuntimeError):
+        s.split(np.zeros((64, 64), np.uint8))
+    with pytest.raises(RuntimeError):
+        UNet16()(torch.zeros(1, 3, 32, 32))
+
+
+def test_pyramid_weight_is_the_reference_expression(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pyramid.npz"))
+    for n in (16, 24, 64):
+        assert np.array_equal(compute_patch_weight_loss(n, n)[0], g["w%d" % n])
+    assert np.array_equal(ImageSlicer((64, 64), 16, 8, weight="pyramid").compute_weight(16), g["w16"])
+    w = ImageSlicer((64, 64), 16, 8, weight="mean").compute_weight(16)
+    assert w.dtype == np.float32 and np.all(w == 1)
+
+
+def test_normalize_lut_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "normalize.npz"))
+    n = aug.NormalizeImage(mean=to.INRIA_MEAN, std=to.INRIA_STD)
+    assert np.array_equal(n(g["levels"]), g["out64"])
+    assert np.array_equal(n.lut(), g["chw_f32"][:, :, 0])
+    t = aug.Sequential([aug.ImageOnly(n)])
+    assert aug.find_normalize(t) is n and aug.find_normalize(object()) is None
+
+
+def _tap_list_conv(x_nhwc, packed, taps):
+    """CPU emulation of what the kernel computes for one phase: sum over taps of shifted input @ W[tap]^T."""
+    n, h, w, cin = x_nhwc.shape
+    out = torch.zeros((n, h, w, packed.shape[1]))
+    xp = F.pad(x_nhwc, (0, 0, 2, 2, 2, 2))
+    for t, (dy, dx) in enumerate(taps):
+        out += xp[:, 2 + dy:2 + dy + h, 2 + dx:2 + dx + w, :] @ packed[t].float().t()
+    return out
+
+
+def test_conv3x3_packing_is_the_convolution():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((1, 6, 7, 8), generator=g)
+    wt = torch.randn((5, 8, 3, 3), generator=g)
+    taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    got = _tap_list_conv(x, E.pack_conv3x3(wt).float(), taps).permute(0, 3, 1, 2)
+    want = F.conv2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), padding=1)
+    assert torch.allclose(got, want, atol=1e-4)
+
+
+def test_convT_phase_decomposition_is_the_transposed_convolution():
+    """The 4 phases x 4 taps the kernel runs (tap offsets as in conv_tcgen05.cu snb_conv_create) equal
+    nn.ConvTranspose2d(k=4, s=2, p=1)."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((2, 5, 6, 8), generator=g)
+    wt = torch.randn((8, 4, 4, 4), generator=g)
+    packed = E.pack_convT4x4(wt).float()
+    dlist = [[0, -1], [1, 0]]
+    out = torch.zeros((2, 10, 12, 4))
+    for py in range(2):
+        for px in range(2):
+            ph = py * 2 + px
+            taps = [(dlist[py][ty], dlist[px][tx]) for ty in range(2) for tx in range(2)]
+            out[:, py::2, px::2, :] = _tap_list_conv(x, packed[ph * 4:ph * 4 + 4], taps)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2, padding=1)
+    assert torch.allclose(out.permute(0, 3, 1, 2), want, atol=1e-4)
+
+
+def test_first_layer_packing_matches_patch_rows():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((1, 3, 5, 6), generator=g)
+    wt = torch.randn((4, 3, 3, 3), generator=g)
+    cols = F.unfold(x, 3, padding=1).reshape(1, 3, 9, 5, 6).permute(0, 3, 4, 2, 1).reshape(1, 5, 6, 27)
+    rows = torch.zeros((1, 5, 6, 32))
+    rows[..., :27] = cols
+    got = rows @ E.pack_first_conv3x3(wt)[0].float().t()
+    want = F.conv2d(x, wt.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(got, want, atol=1e-4)
+
+
+@pytest.mark.parametrize("arch,cls,n_keys,n_params", [("unet16", UNet16, 76, 32202337), ("unet11", UNet11, 56, 25364513)])
+def test_model_mirrors_accept_reference_state_dict(arch, cls, n_keys, n_params):
+    m = cls()
+    sd = synth.vgg_unet_state_dict(arch, seed=1)
+    assert len(m.state_dict()) == n_keys and sorted(m.state_dict()) == sorted(sd)
+    m.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == n_params and m.num_classes == 1
+    # aliased encoder entries share storage, as in the reference (conv1.0 is encoder.0)
+    assert m.state_dict()["conv1.0.weight"].data_ptr() == m.state_dict()["encoder.0.weight"].data_ptr()
+
+
+def test_d4_helpers_roundtrip_on_cpu_tensors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tta.npz"))
+    views = aug.tta_d4_aug([torch.from_numpy(t) for t in g["tiles"]])
+    assert np.array_equal(torch.stack(views).numpy(), g["views"])
+    deaug = aug.tta_d4_deaug([torch.from_numpy(p) for p in g["preds"]])
+    assert np.array_equal(torch.stack(deaug).numpy(), g["deaug"])
+
+
+def test_shard_range_partitions_everything():
+    for n, world in [(180, 8), (169, 4), (5, 8), (0, 2), (7, 1)]:
+        spans = [sdist.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert [e - b for b, e in (sdist.shard_range(180, r, 8) for r in range(8))] == [23, 23, 23, 23, 22, 22, 22, 22]
+    with pytest.raises(ValueError):
+        sdist.shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, n_images, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sdist.init_from_env(backend="gloo")
+    b, e = sdist.shard_range(n_images, rank, world)
+    counts = torch.zeros(4, dtype=torch.int64)
+    masks = []
+    for i in range(b, e):
+        logits, targets = synth.logits_targets(50 + i, (1, 1, 24, 20))
+        p = torch.sigmoid(logits)
+        counts += no.confusion_counts(p, targets)
+        masks.append(((p > 0.5) * 255).to(torch.uint8).reshape(24, 20))
+    local = torch.stack(masks) if masks else torch.zeros((0, 24, 20), dtype=torch.uint8)
+    total = sdist.allreduce_counts(counts)
+    gathered = sdist.gather_masks(local, n_images)
+    if rank == 0:
+        torch.save({"counts": total, "masks": gathered}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_counts_and_masks_equal_single_process(tmp_path):
+    import torch.multiprocessing as mp
+
+    n_images = 5                                       # uneven split: 3 + 2
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, port, n_images, out), nprocs=2, join=True)
+    got = torch.load(out)
+    counts = torch.zeros(4, dtype=torch.int64)
+    masks = []
+    for i in range(n_images):
+        logits, targets = synth.logits_targets(50 + i, (1, 1, 24, 20))
+        p = torch.sigmoid(logits)
+        counts += no.confusion_counts(p, targets)
+        masks.append(((p > 0.5) * 255).to(torch.uint8).reshape(24, 20))
+    assert got["counts"].tolist() == counts.tolist()
+    assert torch.equal(got["masks"], torch.stack(masks))
