@@ -1,25 +1,33 @@
 // Tap-list implicit-GEMM convolution on the sm_100a tensor cores (tcgen05 + TMEM), fed by TMA.
 //
-// One kernel family covers what UNet16 / UNet11 / ZF_UNET execute (lib/models/unet16.py:8-49,113-131):
+// One kernel family covers what UNet16 / UNet11 execute (lib/models/unet16.py:8-49,113-131):
 //   conv3x3 s1 p1      = 1 phase  x 9 taps  (dy,dx in -1..1)
 //   conv1x1            = 1 phase  x 1 tap
 //   ConvTranspose k4s2 = 4 phases x 4 taps  (sub-pixel decomposition; phase (py,px) writes out[2y+py][2x+px])
 // GEMM view per phase:  D[pixel][cout] = sum_{tap,cin} A[pixel + (dy,dx)][cin] * W[tap][cout][cin]
-//   M tile = 128 output pixels = an 8 x 16 spatial patch of one image (TMA box over NHWC, OOB -> 0 gives the
-//            conv zero padding and ragged edges for free; no im2col buffer exists),
-//   N tile = BN output channels, K step = one tap x BK input channels (BK*2 bytes = one swizzle span).
+//   M tile = 128 output pixels of one image, N tile = BN output channels, K step = one tap x BK input channels
+//   (BK*2 bytes = one swizzle span).  TMA boxes over the NHWC slab give the conv zero padding and ragged edges
+//   for free through out-of-bounds zero fill; no im2col buffer exists.
+//
+// Two main-loop variants share the epilogue:
+//   conv_igemm_kernel (v1, "tap" mode): 16x8 pixel patch; every K step loads its own shifted A box + B box.
+//   conv_halo_kernel  (v2, "halo" mode): 8-wide x 16-tall patch; ONE (8+2)x(16+2) halo box per input-channel chunk
+//     feeds all taps: tap (dy,dx) is just a different start row of the UMMA descriptor (rows are 10 halo pixels
+//     apart: SBO = 10 rows), so the activation traffic L2->smem drops ~6x; weights either stream through their
+//     own ring or, when the whole [phase][tap][Cout][Cin] slab fits, stay resident in shared memory ("bres").
 //
 // Persistent CTAs (<= 1 per SM), warp-specialised:
-//   warp 0  : TMA producer   (A box + B box per K step into an NSTAGES ring, mbarrier expect_tx)
-//   warp 1  : MMA issuer     (one thread: tcgen05.mma kind::f16, accumulators in TMEM, 2 accumulator stages)
+//   warp 0  : TMA producer for A (and for the resident weights)      warp 3: TMA producer for B (v2)
+//   warp 1  : MMA issuer (one thread: tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 accumulator stages)
 //   warp 2  : TMEM allocator
-//   warps 4-7: epilogue      (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled smem -> TMA store into the channel
-//                             slab at its concat offset; or the fused 1x1 head + sigmoid for the last layer)
+//   warps 4-7: epilogue (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled smem -> TMA store into the channel slab at
+//              its concat offset; or the fused 1x1 head + sigmoid of the last layer)
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -28,17 +36,18 @@
 
 namespace snb {
 
-constexpr int kTileW = 16;   // spatial patch of one M tile
-constexpr int kTileH = 8;
-constexpr int kBM = kTileW * kTileH;  // 128 = UMMA M
+constexpr int kBM = 128;  // UMMA M = pixels per tile
 constexpr int kMaxPhases = 4;
 constexpr int kMaxTaps = 9;
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kHaloW = 10, kHaloH = 18;           // halo box of the 8 x 16 patch
+constexpr int kHaloRows = kHaloW * kHaloH;        // 180 smem rows
+constexpr int kMaxAStages = 4, kMaxBStages = 8;
 
 struct alignas(64) ConvParams {
-  CUtensorMap map_a;               // activations (C, W, H, N), box (BK, 16, 8, 1)
+  CUtensorMap map_a;               // activations (C, W, H, N)
   CUtensorMap map_b;               // weights (Cin, Cout, phase*taps), box (BK, BN, 1)
-  CUtensorMap map_d[kMaxPhases];   // outputs per phase (C, W, H, N), box (CW, 16, 8, 1)
+  CUtensorMap map_d[kMaxPhases];   // outputs per phase (C, W, H, N)
   int32_t n_phases, taps;          // taps per phase
   int32_t k_chunks;                // Cin / BK
   int32_t n_tiles;                 // Cout / BN
@@ -47,6 +56,7 @@ struct alignas(64) ConvParams {
   int32_t relu;
   int32_t head_sigmoid;
   int32_t out_w, out_h;            // head output bounds
+  int32_t a_stages, b_stages, bres;  // v2 pipeline shape
   float head_b;
   const float* bias;
   const float* head_w;
@@ -69,6 +79,9 @@ struct ConvCfg {
   static constexpr int NSTAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int SMEM_BYTES = 1024 + NSTAGES * STAGE_BYTES + 2 * OUT_BYTES + CTRL_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages (power of two)
+  // v2
+  static constexpr int HALO_BOX_BYTES = kHaloRows * SWZ;
+  static constexpr int HALO_STAGE_BYTES = (HALO_BOX_BYTES + 1023) / 1024 * 1024;
   static_assert(NSTAGES >= 3, "pipeline too shallow");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0, "swizzle atom alignment");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns");
@@ -78,13 +91,14 @@ struct TileCoord {
   int nt, x0, y0, img, ph;
 };
 
+template <int TW, int TH>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
   c.nt = t % p.n_tiles;
   t /= p.n_tiles;
-  c.x0 = (t % p.tiles_x) * kTileW;
+  c.x0 = (t % p.tiles_x) * TW;
   t /= p.tiles_x;
-  c.y0 = (t % p.tiles_y) * kTileH;
+  c.y0 = (t % p.tiles_y) * TH;
   t /= p.tiles_y;
   c.img = t % p.n_img;
   c.ph = t / p.n_img;
@@ -96,11 +110,96 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Epilogue of one accumulator tile, executed by the 4 epilogue warps (128 threads = 128 TMEM lanes = 128 pixels).
+// TW = patch width in pixels (row r of the tile is pixel (r % TW, r / TW)).
+template <int BN, bool HEAD, int TW>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& tc, uint32_t t_addr,
+                                              uint64_t* tmem_empty_bar, uint8_t* smem_out, uint32_t& n_store,
+                                              int row, int lane, int epi_tid) {
+  constexpr int CW = BN < 64 ? BN : 64;
+  constexpr int OUT_SWZ = CW * 2;
+  constexpr int OUT_BYTES = kBM * OUT_SWZ;
+  if constexpr (HEAD) {
+    static_assert(!HEAD || BN == 32, "fused head needs all channels of a pixel in one thread");
+    uint32_t v[32];
+    tmem_ld_32x32(t_addr, v);
+    tmem_ld_wait();
+    tc05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);
+    float dot = p.head_b;
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias);
+    const float4* w4 = reinterpret_cast<const float4*>(p.head_w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(b4 + i), w = __ldg(w4 + i);
+      float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+      float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+      if (p.relu) {
+        x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+      }
+      dot = fmaf(x0, w.x, dot); dot = fmaf(x1, w.y, dot); dot = fmaf(x2, w.z, dot); dot = fmaf(x3, w.w, dot);
+    }
+    if (p.head_sigmoid) dot = 1.f / (1.f + expf(-dot));
+    const int ox = tc.x0 + (row % TW);
+    const int oy = tc.y0 + (row / TW);
+    if (ox < p.out_w && oy < p.out_h)
+      p.head_out[(static_cast<int64_t>(tc.img) * p.out_h + oy) * p.out_w + ox] = dot;
+  } else {
+    constexpr int NCHUNK = BN / CW;
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c, ++n_store) {
+      uint8_t* sout = smem_out + (n_store & 1) * OUT_BYTES;
+      // the TMA store issued two chunks ago must have finished reading this buffer
+      if (epi_tid == 0) tma_store_wait_read<1>();
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int g = 0; g < CW / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * CW + g * 32, v);
+        tmem_ld_wait();
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + tc.nt * BN + c * CW + g * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 4 x 16-byte chunks of 8 channels
+          const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+          float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
+                        __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
+                        __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
+                        __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          const int chunk = g * 4 + j;
+          const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
+          uint4* dst = reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4));
+          *dst = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                            pack_bf16x2(f[6], f[7]));
+        }
+      }
+      if (c == NCHUNK - 1) {
+        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+        tc05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (epi_tid == 0) {
+        tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
+        tma_store_commit();
+      }
+    }
+  }
+}
+
+// =============================================================================================== v1: tap mode
 template <int BN, int BK, bool HEAD>
 __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN, BK>;
   constexpr int NSTAGES = Cfg::NSTAGES;
   constexpr uint32_t IDESC = make_idesc_bf16(kBM, BN);
+  constexpr int TW = 16, TH = 8;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -149,7 +248,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     if (elect_one()) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+        const TileCoord tc = decode_tile<TW, TH>(p, t);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int ax = tc.x0 + p.tap_dx[tc.ph][tap];
           const int ay = tc.y0 + p.tap_dy[tc.ph][tap];
@@ -184,8 +283,8 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
           mbar_wait(&full_bar[s], ph);
           tc05_fence_after();
           const uint32_t a_addr = smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_desc<Cfg::SWZ>(a_addr);
-          const uint64_t bdesc = make_kmajor_desc<Cfg::SWZ>(a_addr + Cfg::A_BYTES);
+          const uint64_t adesc = make_kmajor_desc<Cfg::SWZ>(a_addr, 8 * Cfg::SWZ);
+          const uint64_t bdesc = make_kmajor_desc<Cfg::SWZ>(a_addr + Cfg::A_BYTES, 8 * Cfg::SWZ);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
@@ -199,86 +298,219 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;       // pixel index inside the 8x16 patch
+    const int row = q * 32 + lane;       // pixel index inside the patch
     const int epi_tid = threadIdx.x - 128;
     uint32_t local_tile = 0;
     uint32_t n_store = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = decode_tile<TW, TH>(p, t);
       const uint32_t acc = local_tile & 1;
       const uint32_t acc_ph = (local_tile >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_tile<BN, HEAD, TW>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
+    }
+    if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
+  }
 
-      if constexpr (HEAD) {
-        static_assert(!HEAD || BN == 32, "fused head needs all channels of a pixel in one thread");
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr, v);
-        tmem_ld_wait();
-        tc05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        float dot = p.head_b;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) + __ldg(p.bias + i);
-          if (p.relu) x = fmaxf(x, 0.f);
-          dot = fmaf(x, __ldg(p.head_w + i), dot);
+  tc05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ============================================================================================== v2: halo mode
+// smem: [a_stages x HALO_STAGE][B: b_stages x B_BYTES, or all (phase, chunk, tap) weight boxes when bres][2 x OUT][ctrl]
+//
+// The MMA-issuing thread is the critical resource: tcgen05.mma M=128 x K=16 retires in max(N/2, ~40) cycles
+// (measured, tools/micro/mma_rate.cu), so one thread has to issue an MMA every 64 cycles at N=128.  Everything it
+// needs is therefore precomputed: tap -> descriptor offsets live in a shared-memory table, stage indices advance by
+// compare-and-wrap (no division), descriptors are built from 32-bit halves with immediate K offsets, and the tap
+// loop is fully unrolled (TAPS is a template parameter: 9 for conv3x3, 4 for one ConvTranspose phase).
+__device__ __forceinline__ uint64_t desc_from_halves(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+template <int SWZ>
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  // bits [32,46) SBO>>4, [46,48) version = 1, [61,64) layout type
+  return (sbo_bytes >> 4) | (1u << 14) | ((SWZ == 128 ? 2u : (SWZ == 64 ? 4u : 6u)) << 29);
+}
+
+template <int BN, int BK, bool HEAD, int TAPS>
+__global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN, BK>;
+  constexpr uint32_t IDESC = make_idesc_bf16(kBM, BN);
+  constexpr int TW = 8, TH = 16;
+  constexpr int SWZ = Cfg::SWZ;
+  constexpr uint32_t A_STAGE16 = Cfg::HALO_STAGE_BYTES >> 4;
+  constexpr uint32_t B_BYTES16 = Cfg::B_BYTES >> 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_b_slots = p.bres ? p.n_phases * TAPS * p.k_chunks : p.b_stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + p.a_stages * Cfg::HALO_STAGE_BYTES;
+  uint8_t* smem_out = smem_b + n_b_slots * Cfg::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + (HEAD ? 0 : 2 * Cfg::OUT_BYTES));
+  uint64_t* a_full = bars;                          // [kMaxAStages]
+  uint64_t* a_empty = a_full + kMaxAStages;         // [kMaxAStages]
+  uint64_t* b_full = a_empty + kMaxAStages;         // [kMaxBStages]  (b_full[0] doubles as the bres barrier)
+  uint64_t* b_empty = b_full + kMaxBStages;         // [kMaxBStages]
+  uint64_t* tmem_full = b_empty + kMaxBStages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* s_aoff = tmem_ptr + 4;                  // [kMaxPhases][TAPS] descriptor start offsets (>>4) per tap
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+    if (!HEAD)
+      for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.map_d[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp == 3 && lane < p.n_phases * TAPS) {
+    // tap (dy,dx): the 128 operand rows start (dy+1) halo rows down and (dx+1) pixels right
+    const int ph = lane / TAPS, tap = lane % TAPS;
+    s_aoff[lane] = static_cast<uint32_t>(((p.tap_dy[ph][tap] + 1) * kHaloW + (p.tap_dx[ph][tap] + 1)) * SWZ) >> 4;
+  }
+  tc05_fence_before();
+  __syncthreads();
+  tc05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A producer (+ resident weights)
+    if (elect_one()) {
+      if (p.bres) {
+        mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(n_b_slots) * Cfg::B_BYTES);
+        uint8_t* dst = smem_b;   // slot order (phase, chunk, tap): what the MMA loop walks linearly
+        for (int ph = 0; ph < p.n_phases; ++ph)
+          for (int kc = 0; kc < p.k_chunks; ++kc)
+            for (int tap = 0; tap < TAPS; ++tap, dst += Cfg::B_BYTES)
+              tma_load_3d(&p.map_b, &b_full[0], dst, kc * BK, 0, ph * TAPS + tap);
+      }
+      uint32_t s = 0, par = 1;   // waiting on parity 1 of a fresh barrier returns immediately
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile<TW, TH>(p, t);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&a_empty[s], par);
+          mbar_arrive_expect_tx(&a_full[s], Cfg::HALO_BOX_BYTES);
+          tma_load_4d(&p.map_a, &a_full[s], smem_a + s * Cfg::HALO_STAGE_BYTES, kc * BK, tc.x0 - 1, tc.y0 - 1, tc.img);
+          if (++s == static_cast<uint32_t>(p.a_stages)) { s = 0; par ^= 1; }
         }
-        if (p.head_sigmoid) dot = 1.f / (1.f + expf(-dot));
-        const int ox = tc.x0 + (row & (kTileW - 1));
-        const int oy = tc.y0 + (row >> 4);
-        if (ox < p.out_w && oy < p.out_h)
-          p.head_out[(static_cast<int64_t>(tc.img) * p.out_h + oy) * p.out_w + ox] = dot;
-      } else {
-        constexpr int CW = Cfg::CW;
-        constexpr int NCHUNK = BN / CW;
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ B producer (streamed weights)
+    if (!p.bres && elect_one()) {
+      uint32_t s = 0, par = 1;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile<TW, TH>(p, t);
+        const int n0 = tc.nt * BN, w0 = tc.ph * TAPS;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c, ++n_store) {
-          uint8_t* sout = smem_out + (n_store & 1) * Cfg::OUT_BYTES;
-          // the TMA store issued two chunks ago must have finished reading this buffer
-          if (epi_tid == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-#pragma unroll
-          for (int g = 0; g < CW / 32; ++g) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_addr + c * CW + g * 32, v);
-            tmem_ld_wait();
-            const float* bias = p.bias + tc.nt * BN + c * CW + g * 32;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {  // 4 x 16-byte chunks of 8 channels
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float lo = __uint_as_float(v[j * 8 + 2 * e]) + __ldg(bias + j * 8 + 2 * e);
-                float hi = __uint_as_float(v[j * 8 + 2 * e + 1]) + __ldg(bias + j * 8 + 2 * e + 1);
-                if (p.relu) {
-                  lo = fmaxf(lo, 0.f);
-                  hi = fmaxf(hi, 0.f);
-                }
-                w[e] = pack_bf16x2(lo, hi);
-              }
-              const int chunk = g * 4 + j;
-              const int sw = Cfg::OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
-              uint4* dst = reinterpret_cast<uint4*>(sout + row * Cfg::OUT_SWZ + ((chunk ^ sw) << 4));
-              *dst = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-          if (c == NCHUNK - 1) {
-            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-            tc05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (epi_tid == 0) {
-            tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
-            tma_store_commit();
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(&b_empty[s], par);
+            mbar_arrive_expect_tx(&b_full[s], Cfg::B_BYTES);
+            tma_load_3d(&p.map_b, &b_full[s], smem_b + s * Cfg::B_BYTES, kc * BK, n0, w0 + tap);
+            if (++s == static_cast<uint32_t>(p.b_stages)) { s = 0; par ^= 1; }
           }
         }
       }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (elect_one()) {
+      constexpr uint32_t HI_A = desc_hi<SWZ>(kHaloW * SWZ);   // 8-row groups are one halo row (10 pixels) apart
+      constexpr uint32_t HI_B = desc_hi<SWZ>(8 * SWZ);
+      const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
+      const uint32_t b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+      const bool bres = p.bres != 0;
+      const uint32_t a_stages = p.a_stages, b_stages = p.b_stages;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      uint32_t local_tile = 0;
+      if (bres) {
+        mbar_wait(&b_full[0], 0);
+        tc05_fence_after();
+      }
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+        const int ph = t / (p.total_tiles / p.n_phases);   // phase is the slowest tile coordinate
+        uint32_t aoff[TAPS];
+#pragma unroll
+        for (int i = 0; i < TAPS; ++i) aoff[i] = s_aoff[ph * TAPS + i];
+        const uint32_t acc = local_tile & 1;
+        mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
+        tc05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(ph * p.k_chunks * TAPS) * B_BYTES16;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&a_full[sa], pa);
+          tc05_fence_after();
+          const uint32_t a_lo = a_lo0 + sa * A_STAGE16;
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+            if (!bres) {
+              mbar_wait(&b_full[sb], pb);
+              tc05_fence_after();
+              b_lo = b_lo0 + sb * B_BYTES16;
+            }
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(desc_from_halves(a_lo + aoff[tap] + 2 * k, HI_A), desc_from_halves(b_lo + 2 * k, HI_B),
+                           d_tmem, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            if (!bres) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == b_stages) { sb = 0; pb ^= 1; }
+            } else {
+              b_lo += B_BYTES16;
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == a_stages) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 128;
+    uint32_t local_tile = 0;
+    uint32_t n_store = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+      const TileCoord tc = decode_tile<TW, TH>(p, t);
+      const uint32_t acc = local_tile & 1;
+      const uint32_t acc_ph = (local_tile >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc05_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_tile<BN, HEAD, TW>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
   }
@@ -325,15 +557,21 @@ static int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* di
 }
 
 struct KernelChoice {
-  const void* fn;
-  int smem;
+  const void* fn;        // v1 kernel
+  const void* fn_halo9;  // v2 kernel, 9 taps (conv3x3)
+  const void* fn_halo4;  // v2 kernel, 4 taps per phase (ConvTranspose k4 s2)
+  int smem;              // v1 dynamic smem
   int bn, bk;
+  int halo_stage_bytes, b_bytes, out_bytes;
 };
 
 template <int BN, int BK, bool HEAD>
 static KernelChoice choice() {
-  return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>), ConvCfg<BN, BK>::SMEM_BYTES,
-                      BN, BK};
+  using Cfg = ConvCfg<BN, BK>;
+  return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4>),
+                      Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES, HEAD ? 0 : Cfg::OUT_BYTES};
 }
 
 static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
@@ -359,11 +597,21 @@ static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
   return false;
 }
 
+// SNB_CONV_MODE: 0 = tap mode everywhere, 1 = halo mode with streamed weights, 2 (default) = halo mode with
+// resident weights where they fit.  Read at snb_conv_create time (A/B measurements without a rebuild).
+static int conv_mode() {
+  const char* e = std::getenv("SNB_CONV_MODE");
+  if (!e || !*e) return 2;
+  return std::atoi(e);
+}
+
 }  // namespace snb
 
 struct snb_conv {
   snb::ConvParams params;
   snb::KernelChoice kernel;
+  const void* fn;
+  int smem;
   int grid;
   double flops;
 };
@@ -385,7 +633,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     return fail(SNB_E_INVALID, "bad output slab");
   if (!d->d_in || !d->d_weight || !d->d_bias) return fail(SNB_E_INVALID, "null tensor pointer");
   if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
-      (reinterpret_cast<uintptr_t>(d->d_weight) & 15))
+      (reinterpret_cast<uintptr_t>(d->d_weight) & 15) || (reinterpret_cast<uintptr_t>(d->d_bias) & 15))
     return fail(SNB_E_INVALID, "tensor pointers must be 16-byte aligned");
 
   const int bk = d->cin % 64 == 0 ? 64 : 32;
@@ -424,8 +672,48 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   }
   p.k_chunks = static_cast<int32_t>(d->cin / bk);
   p.n_tiles = static_cast<int32_t>(d->cout / bn);
-  p.tiles_x = static_cast<int32_t>((d->w + kTileW - 1) / kTileW);
-  p.tiles_y = static_cast<int32_t>((d->h + kTileH - 1) / kTileH);
+
+  // ---- main-loop variant and pipeline shape
+  const int mode = conv_mode();
+  const bool halo = mode >= 1 && d->kind != SNB_CONV_1X1;
+  int tile_w = 16, tile_h = 8;
+  c->fn = kc.fn;
+  c->smem = kc.smem;
+  if (halo) {
+    tile_w = 8;
+    tile_h = 16;
+    const int fixed = 1024 /*align*/ + 1024 /*ctrl*/ + 2 * kc.out_bytes;
+    const int64_t w_slots = (int64_t)p.n_phases * p.taps * p.k_chunks;
+    const int64_t w_bytes = w_slots * kc.b_bytes;
+    int a_stages = std::min<int>(3, std::max<int>(2, p.k_chunks + 1));
+    bool bres = mode >= 2 && p.n_tiles == 1 && fixed + 2 * kc.halo_stage_bytes + w_bytes <= kSmemBudget;
+    int b_stages = 0;
+    if (bres) {
+      while (a_stages > 2 && fixed + a_stages * kc.halo_stage_bytes + w_bytes > kSmemBudget) --a_stages;
+      while (a_stages < kMaxAStages && fixed + (a_stages + 1) * kc.halo_stage_bytes + w_bytes <= kSmemBudget &&
+             a_stages < 4)
+        ++a_stages;
+      c->smem = fixed + a_stages * kc.halo_stage_bytes + (int)w_bytes;
+    } else {
+      a_stages = 2;
+      b_stages = (kSmemBudget - fixed - a_stages * kc.halo_stage_bytes) / kc.b_bytes;
+      if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+      if (b_stages < 3) {
+        delete c;
+        return fail(SNB_E_UNSUPPORTED, "halo pipeline does not fit in shared memory");
+      }
+      // a third activation stage if there is room left
+      if (fixed + 3 * kc.halo_stage_bytes + b_stages * kc.b_bytes <= kSmemBudget) a_stages = 3;
+      c->smem = fixed + a_stages * kc.halo_stage_bytes + b_stages * kc.b_bytes;
+    }
+    p.a_stages = a_stages;
+    p.b_stages = b_stages;
+    p.bres = bres ? 1 : 0;
+    c->fn = p.taps == 9 ? kc.fn_halo9 : kc.fn_halo4;
+  }
+
+  p.tiles_x = static_cast<int32_t>((d->w + tile_w - 1) / tile_w);
+  p.tiles_y = static_cast<int32_t>((d->h + tile_h - 1) / tile_h);
   p.n_img = static_cast<int32_t>(d->n);
   const int64_t total = static_cast<int64_t>(p.n_phases) * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
   if (total > INT32_MAX) {
@@ -447,7 +735,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t str[3] = {(uint64_t)d->in_cstride * 2, (uint64_t)d->w * d->in_cstride * 2,
                        (uint64_t)d->h * d->w * d->in_cstride * 2};
-    uint32_t box[4] = {(uint32_t)bk, kTileW, kTileH, 1};
+    uint32_t box[4] = {(uint32_t)bk, (uint32_t)(halo ? kHaloW : tile_w), (uint32_t)(halo ? kHaloH : tile_h), 1};
     rc = encode_map(&p.map_a, const_cast<void*>(d->d_in), 4, dims, str, box, bk * 2);
     if (rc) { delete c; return rc; }
   }
@@ -468,16 +756,16 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
       uint64_t str[3] = {(uint64_t)s * d->out_cstride * 2, (uint64_t)s * ow * d->out_cstride * 2,
                          (uint64_t)oh * ow * d->out_cstride * 2};
-      uint32_t box[4] = {(uint32_t)cw, kTileW, kTileH, 1};
+      uint32_t box[4] = {(uint32_t)cw, (uint32_t)tile_w, (uint32_t)tile_h, 1};
       rc = encode_map(&p.map_d[ph], base, 4, dims, str, box, cw * 2);
       if (rc) { delete c; return rc; }
     }
   }
 
-  cudaError_t e = cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem);
+  cudaError_t e = cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   if (e != cudaSuccess) {
     delete c;
-    return fail(SNB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kc.smem, cudaGetErrorString(e));
+    return fail(SNB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmemBudget, cudaGetErrorString(e));
   }
   const int sms = sm_count();
   if (sms <= 0) { delete c; return fail(SNB_E_CUDA, "no CUDA device"); }
@@ -491,7 +779,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
 extern "C" int snb_conv_launch(const snb_conv* c, void* stream) {
   if (!c) return fail(SNB_E_INVALID, "snb_conv_launch: null handle");
   void* args[1] = {const_cast<ConvParams*>(&c->params)};
-  cudaError_t e = cudaLaunchKernel(c->kernel.fn, dim3(c->grid), dim3(256), args, c->kernel.smem, as_stream(stream));
+  cudaError_t e = cudaLaunchKernel(c->fn, dim3(c->grid), dim3(256), args, c->smem, as_stream(stream));
   if (e != cudaSuccess) return fail(SNB_E_CUDA, "conv launch failed: %s", cudaGetErrorString(e));
   return SNB_OK;
 }

@@ -122,33 +122,58 @@ __global__ void split_norm_nchw_kernel(SlicerGeom g, const uint8_t* __restrict__
   }
 }
 
-// one thread = 8 consecutive k of one pixel's 32-wide patch row -> one 16-byte store
-__global__ void split_norm_patch32_kernel(SlicerGeom g, const uint8_t* __restrict__ src, const float* __restrict__ lut,
-                                          int channels, int tta, uint4* __restrict__ dst, int64_t tile_begin,
-                                          int64_t total) {
+// PATCH32 rows of RY tile rows per block.  Stage 1: the (RY+2) x (T+2) neighbourhood of the strip is gathered once
+// (D4 view map, reflect-101, LUT, bf16) into shared memory as 4 x bf16 per pixel, zeros outside the tile (the conv
+// zero padding).  Stage 2: every thread assembles 8 consecutive k of one pixel from shared memory and writes one
+// 16-byte vector, so global stores are fully coalesced and every source pixel is fetched ~1.3x instead of 27x.
+constexpr int kPatchRY = 8;
+
+__global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, const uint8_t* __restrict__ src,
+                                                                 const float* __restrict__ lut, int channels, int tta,
+                                                                 uint4* __restrict__ dst, int64_t tile_begin) {
+  extern __shared__ uint2 s_px[];                 // [(RY+2)][T+2] pixels, 4 x bf16 each
+  __shared__ float s_lut[4 * 256];
   const int T = (int)g.tile;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int qd = (int)(i & 3);
-    int64_t r = i >> 2;
-    const int x = (int)(r % T); r /= T;
-    const int y = (int)(r % T);
-    const int64_t t = r / T;
-    const int64_t tile = tile_begin + t;
-    const int64_t cy = (tile / g.tiles_x) * g.step, cx = (tile % g.tiles_x) * g.step;
-    float f[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = qd * 8 + e;
-      const int tap = k / channels, c = k - tap * channels;
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      f[e] = (tap < 9 && yy >= 0 && yy < T && xx >= 0 && xx < T)
-                 ? norm_fetch(g, src, lut, channels, tta, cy, cx, yy, xx, c)
-                 : 0.f;
+  const int strips = (T + kPatchRY - 1) / kPatchRY;
+  const int64_t t = blockIdx.x / strips;
+  const int y0 = (int)(blockIdx.x % strips) * kPatchRY;
+  const int64_t tile = tile_begin + t;
+  const int64_t cy = (tile / g.tiles_x) * g.step, cx = (tile % g.tiles_x) * g.step;
+  for (int i = threadIdx.x; i < channels * 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int PW = T + 2;
+  for (int i = threadIdx.x; i < (kPatchRY + 2) * PW; i += blockDim.x) {
+    const int hy = i / PW, hx = i - hy * PW;
+    const int vy = y0 + hy - 1, vx = hx - 1;     // position in the (D4-transformed) tile
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vy >= 0 && vy < T && vx >= 0 && vx < T) {
+      int si, sj;
+      d4_src(tta, vy, vx, T, si, sj);
+      const int64_t sy = reflect101(cy + si - g.margin_top, g.image_h);
+      const int64_t sx = reflect101(cx + sj - g.margin_left, g.image_w);
+      const uint8_t* px = src + (sy * g.image_w + sx) * channels;
+      for (int c = 0; c < channels; ++c) f[c] = s_lut[c * 256 + __ldg(px + c)];
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-    dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                        *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+    s_px[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+  __syncthreads();
+  const unsigned short* s_el = reinterpret_cast<const unsigned short*>(s_px);
+  const int rows = min(kPatchRY, T - y0);
+  for (int i = threadIdx.x; i < rows * T * 4; i += blockDim.x) {
+    const int qd = i & 3;
+    const int pix = i >> 2;
+    const int y = pix / T, x = pix - y * T;
+    unsigned short e[8];
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) {
+      const int k = qd * 8 + k8;
+      const int tap = k / channels, c = k - tap * channels;
+      e[k8] = tap < 9 ? s_el[((y + tap / 3) * PW + x + tap % 3) * 4 + c] : (unsigned short)0;
+    }
+    dst[((t * T + y0 + y) * (int64_t)T + x) * 4 + qd] =
+        make_uint4(e[0] | ((uint32_t)e[1] << 16), e[2] | ((uint32_t)e[3] << 16), e[4] | ((uint32_t)e[5] << 16),
+                   e[6] | ((uint32_t)e[7] << 16));
   }
 }
 
@@ -361,9 +386,14 @@ extern "C" int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int6
   } else if (layout == SNB_LAYOUT_PATCH32) {
     if (channels > 3) return fail(SNB_E_INVALID, "PATCH32 holds 9 taps x <=3 channels");
     if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(SNB_E_INVALID, "PATCH32 destination must be 16-byte aligned");
-    const int64_t total = tile_count * T * T * 4;
-    split_norm_patch32_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        s->g, d_src, d_lut, (int)channels, tta, static_cast<uint4*>(d_dst), tile_begin, total);
+    const int strips = (int)((T + kPatchRY - 1) / kPatchRY);
+    const size_t smem = (size_t)(kPatchRY + 2) * (T + 2) * sizeof(uint2);
+    if (smem > 200 * 1024) return fail(SNB_E_UNSUPPORTED, "tile size %lld too large for the PATCH32 split", (long long)T);
+    if (smem > 48 * 1024)
+      SNB_CUDA_CHECK(cudaFuncSetAttribute(split_norm_patch32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (tile_count * strips > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "too many strips");
+    split_norm_patch32_kernel<<<(unsigned)(tile_count * strips), 256, smem, as_stream(stream)>>>(
+        s->g, d_src, d_lut, (int)channels, tta, static_cast<uint4*>(d_dst), tile_begin);
   } else {
     return fail(SNB_E_INVALID, "unknown layout %d", layout);
   }

@@ -180,17 +180,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand whose K extent is exactly one swizzle span
-// (SWIZZLE_BYTES = 128 or 64): rows are SWIZZLE_BYTES apart, 8-row groups are 8*SWIZZLE_BYTES apart (SBO).
+// (SWIZZLE_BYTES = 128 or 64): rows of a core-matrix group are SWIZZLE_BYTES apart, consecutive 8-row groups are
+// `sbo_bytes` apart (8*SWIZZLE_BYTES for a dense tile; larger when the rows come from a wider halo tile).
+// The swizzle XOR is a function of the absolute shared-memory address bits, so the start address may point at
+// any row of a 1024-byte aligned buffer written by TMA with the same swizzle mode.
 // Field layout (PTX "matrix descriptor", sm_100): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
 // [46,48) version=1, [49,52) base offset, [61,64) layout (2 = SW128, 4 = SW64, 6 = SW32).
 template <int SWIZZLE_BYTES>
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
   static_assert(SWIZZLE_BYTES == 128 || SWIZZLE_BYTES == 64 || SWIZZLE_BYTES == 32, "swizzle");
   const uint64_t layout = SWIZZLE_BYTES == 128 ? 2ull : (SWIZZLE_BYTES == 64 ? 4ull : 6ull);
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((8u * SWIZZLE_BYTES) >> 4) << 32;  // SBO
-  d |= 1ull << 46;                                              // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;  // SBO
+  d |= 1ull << 46;                                   // descriptor version (sm_100)
   d |= layout << 61;
   return d;
 }

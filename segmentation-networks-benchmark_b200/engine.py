@@ -106,6 +106,7 @@ class ConvOp:
             d.d_head_out = head_out.data_ptr()
         if weight.shape[1] != d.cout or weight.shape[2] != d.cin:
             raise ValueError("packed weight %s does not match cout=%d cin=%d" % (tuple(weight.shape), d.cout, d.cin))
+        self.desc = (int(d.kind), int(d.h), int(d.w), int(d.cin), int(d.cout))
         self._h = ctypes.c_void_p()
         N.check(N.lib().snb_conv_create(ctypes.byref(d), ctypes.byref(self._h)))
         self.flops = N.lib().snb_conv_flops(self._h)
