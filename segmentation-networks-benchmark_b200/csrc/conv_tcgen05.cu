@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 template <int BN, bool HEAD, int TW>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& tc, uint32_t t_addr,
                                               uint64_t* tmem_empty_bar, uint8_t* smem_out, uint32_t& n_store,
-                                              int row, int lane, int epi_tid) {
+                                              int row, int lane, int epi_tid, bool release = true) {
   constexpr int CW = BN < 64 ? BN : 64;
   constexpr int OUT_SWZ = CW * 2;
   constexpr int OUT_BYTES = kBM * OUT_SWZ;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
     tmem_ld_wait();
     tc05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty_bar);
+    if (release && lane == 0) mbar_arrive(tmem_empty_bar);
     float dot = p.head_b;
     const float4* b4 = reinterpret_cast<const float4*>(p.bias);
     const float4* w4 = reinterpret_cast<const float4*>(p.head_w);
@@ -177,7 +177,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
                             pack_bf16x2(f[6], f[7]));
         }
       }
-      if (c == NCHUNK - 1) {
+      if (release && c == NCHUNK - 1) {
         // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
         tc05_fence_before();
         __syncwarp();
@@ -340,9 +340,14 @@ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
   return (sbo_bytes >> 4) | (1u << 14) | ((SWZ == 128 ? 2u : (SWZ == 64 ? 4u : 6u)) << 29);
 }
 
-template <int BN, int BK, bool HEAD, int TAPS>
+// NPH = 4 fuses the four sub-pixel phases of a ConvTranspose into one tile (four accumulators of BN columns): the
+// halo box is then loaded once per spatial tile instead of once per phase.
+template <int BN, int BK, bool HEAD, int TAPS, int NPH>
 __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN, BK>;
+  static_assert(NPH == 1 || (NPH == 4 && TAPS == 4 && !HEAD), "phase fusion is for ConvTranspose");
+  constexpr int TCOLS = Cfg::TMEM_COLS * NPH;
+  static_assert(TCOLS <= 512, "TMEM columns");
   constexpr uint32_t IDESC = make_idesc_bf16(kBM, BN);
   constexpr int TW = 8, TH = 16;
   constexpr int SWZ = Cfg::SWZ;
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int n_b_slots = p.bres ? p.n_phases * TAPS * p.k_chunks : p.b_stages;
+  const int n_b_slots = p.bres ? p.n_phases * TAPS * p.k_chunks : p.b_stages;  // n_phases: weight phases
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.a_stages * Cfg::HALO_STAGE_BYTES;
   uint8_t* smem_out = smem_b + n_b_slots * Cfg::B_BYTES;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_ptr, TCOLS);
     tmem_relinquish();
   }
   if (warp == 3 && lane < p.n_phases * TAPS) {
@@ -408,11 +413,19 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     if (elect_one()) {
       if (p.bres) {
         mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(n_b_slots) * Cfg::B_BYTES);
-        uint8_t* dst = smem_b;   // slot order (phase, chunk, tap): what the MMA loop walks linearly
-        for (int ph = 0; ph < p.n_phases; ++ph)
+        uint8_t* dst = smem_b;   // slot order = the order the MMA loop walks: (phase, chunk, tap), or
+                                 // (chunk, phase, tap) when the phases are fused into one tile
+        if (NPH == 1) {
+          for (int ph = 0; ph < p.n_phases; ++ph)
+            for (int kc = 0; kc < p.k_chunks; ++kc)
+              for (int tap = 0; tap < TAPS; ++tap, dst += Cfg::B_BYTES)
+                tma_load_3d(&p.map_b, &b_full[0], dst, kc * BK, 0, ph * TAPS + tap);
+        } else {
           for (int kc = 0; kc < p.k_chunks; ++kc)
-            for (int tap = 0; tap < TAPS; ++tap, dst += Cfg::B_BYTES)
-              tma_load_3d(&p.map_b, &b_full[0], dst, kc * BK, 0, ph * TAPS + tap);
+            for (int ph = 0; ph < NPH; ++ph)
+              for (int tap = 0; tap < TAPS; ++tap, dst += Cfg::B_BYTES)
+                tma_load_3d(&p.map_b, &b_full[0], dst, kc * BK, 0, ph * TAPS + tap);
+        }
       }
       uint32_t s = 0, par = 1;   // waiting on parity 1 of a fresh barrier returns immediately
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -431,13 +444,13 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
       uint32_t s = 0, par = 1;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile<TW, TH>(p, t);
-        const int n0 = tc.nt * BN, w0 = tc.ph * TAPS;
+        const int n0 = tc.nt * BN, w0 = tc.ph * TAPS;   // tc.ph == 0 when the phases are fused
         for (int kc = 0; kc < p.k_chunks; ++kc) {
 #pragma unroll 1
-          for (int tap = 0; tap < TAPS; ++tap) {
+          for (int wt = 0; wt < NPH * TAPS; ++wt) {
             mbar_wait(&b_empty[s], par);
             mbar_arrive_expect_tx(&b_full[s], Cfg::B_BYTES);
-            tma_load_3d(&p.map_b, &b_full[s], smem_b + s * Cfg::B_BYTES, kc * BK, n0, w0 + tap);
+            tma_load_3d(&p.map_b, &b_full[s], smem_b + s * Cfg::B_BYTES, kc * BK, n0, w0 + wt);
             if (++s == static_cast<uint32_t>(p.b_stages)) { s = 0; par ^= 1; }
           }
         }
@@ -459,21 +472,23 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         tc05_fence_after();
       }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
-        const int ph = t / (p.total_tiles / p.n_phases);   // phase is the slowest tile coordinate
-        uint32_t aoff[TAPS];
+        // phase is the slowest tile coordinate (and absent when the phases are fused)
+        const int ph0 = NPH == 1 ? t / (p.total_tiles / p.n_phases) : 0;
+        uint32_t aoff[NPH * TAPS];
 #pragma unroll
-        for (int i = 0; i < TAPS; ++i) aoff[i] = s_aoff[ph * TAPS + i];
+        for (int i = 0; i < NPH * TAPS; ++i) aoff[i] = s_aoff[ph0 * TAPS + i];
         const uint32_t acc = local_tile & 1;
         mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
         tc05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(ph * p.k_chunks * TAPS) * B_BYTES16;
+        const uint32_t d_tmem = tmem_base + acc * (NPH * BN);
+        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(ph0 * p.k_chunks * TAPS) * B_BYTES16;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_full[sa], pa);
           tc05_fence_after();
           const uint32_t a_lo = a_lo0 + sa * A_STAGE16;
 #pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
+          for (int wt = 0; wt < NPH * TAPS; ++wt) {
+            const int tap = wt % TAPS;
             if (!bres) {
               mbar_wait(&b_full[sb], pb);
               tc05_fence_after();
@@ -481,8 +496,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
             }
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ss(desc_from_halves(a_lo + aoff[tap] + 2 * k, HI_A), desc_from_halves(b_lo + 2 * k, HI_B),
-                           d_tmem, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss(desc_from_halves(a_lo + aoff[wt] + 2 * k, HI_A), desc_from_halves(b_lo + 2 * k, HI_B),
+                           d_tmem + (wt / TAPS) * BN, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
             if (!bres) {
               umma_commit(&b_empty[sb]);
               if (++sb == b_stages) { sb = 0; pb ^= 1; }
@@ -504,13 +519,18 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     uint32_t local_tile = 0;
     uint32_t n_store = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
-      const TileCoord tc = decode_tile<TW, TH>(p, t);
+      TileCoord tc = decode_tile<TW, TH>(p, t);
       const uint32_t acc = local_tile & 1;
       const uint32_t acc_ph = (local_tile >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc05_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_tile<BN, HEAD, TW>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
+      const uint32_t t_addr = tmem_base + acc * (NPH * BN) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int ph = 0; ph < NPH; ++ph) {
+        if (NPH > 1) tc.ph = ph;
+        epilogue_tile<BN, HEAD, TW>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid,
+                                    ph == NPH - 1);
+      }
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
   }
@@ -519,7 +539,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   __syncthreads();
   if (warp == 2) {
     tc05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, TCOLS);
   }
 }
 
@@ -560,17 +580,24 @@ struct KernelChoice {
   const void* fn;        // v1 kernel
   const void* fn_halo9;  // v2 kernel, 9 taps (conv3x3)
   const void* fn_halo4;  // v2 kernel, 4 taps per phase (ConvTranspose k4 s2)
+  const void* fn_halo4f; // v2 kernel, ConvTranspose with the 4 phases fused into one tile (BN <= 64), or null
   int smem;              // v1 dynamic smem
   int bn, bk;
   int halo_stage_bytes, b_bytes, out_bytes;
 };
 
 template <int BN, int BK, bool HEAD>
+static const void* fused_phase_kernel() {
+  if constexpr (!HEAD && BN <= 64) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, 4, 4>);
+  else return nullptr;
+}
+
+template <int BN, int BK, bool HEAD>
 static KernelChoice choice() {
   using Cfg = ConvCfg<BN, BK>;
   return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>),
-                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9>),
-                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1>), fused_phase_kernel<BN, BK, HEAD>(),
                       Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES, HEAD ? 0 : Cfg::OUT_BYTES};
 }
 
@@ -597,12 +624,19 @@ static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
   return false;
 }
 
-// SNB_CONV_MODE: 0 = tap mode everywhere, 1 = halo mode with streamed weights, 2 (default) = halo mode with
-// resident weights where they fit.  Read at snb_conv_create time (A/B measurements without a rebuild).
+// SNB_CONV_MODE: 0 = tap mode everywhere, 1 = halo mode with streamed weights, 2 = + resident weights where they
+// fit, 3 (default) = + ConvTranspose phases fused into one tile (Cout <= 64) and N tile narrowed to 128 when the
+// 256-wide tiling would leave the last wave mostly empty.  Read at snb_conv_create time (A/B without a rebuild).
 static int conv_mode() {
   const char* e = std::getenv("SNB_CONV_MODE");
-  if (!e || !*e) return 2;
+  if (!e || !*e) return 3;
   return std::atoi(e);
+}
+
+static double wave_efficiency(int64_t tiles, int sms) {
+  const double waves = (double)tiles / sms;
+  const double full = (double)((tiles + sms - 1) / sms);
+  return full > 0 ? waves / full : 1.0;
 }
 
 }  // namespace snb
@@ -636,11 +670,21 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       (reinterpret_cast<uintptr_t>(d->d_weight) & 15) || (reinterpret_cast<uintptr_t>(d->d_bias) & 15))
     return fail(SNB_E_INVALID, "tensor pointers must be 16-byte aligned");
 
+  const int mode = conv_mode();
+  const int sms = sm_count();
+  if (sms <= 0) return fail(SNB_E_CUDA, "no CUDA device");
   const int bk = d->cin % 64 == 0 ? 64 : 32;
   int bn = 32;
   if (d->cout % 256 == 0) bn = 256;
   else if (d->cout % 128 == 0) bn = 128;
   else if (d->cout % 64 == 0) bn = 64;
+  if (mode >= 3 && bn == 256) {
+    // wave quantisation: with few tiles (deep, low-resolution layers) a 128-wide N tile fills the last wave better
+    const int64_t m_tiles = (int64_t)(d->kind == SNB_CONVT_4X4_S2 ? 4 : 1) * d->n * ((d->h + 15) / 16) * ((d->w + 7) / 8);
+    const double e256 = wave_efficiency(m_tiles * (d->cout / 256), sms);
+    const double e128 = wave_efficiency(m_tiles * (d->cout / 128), sms);
+    if (e256 < 0.85 && e128 > e256 + 0.05) bn = 128;
+  }
   KernelChoice kc;
   if (!pick_kernel(bn, bk, head, &kc)) return fail(SNB_E_UNSUPPORTED, "no kernel for BN=%d BK=%d head=%d", bn, bk, (int)head);
 
@@ -674,8 +718,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   p.n_tiles = static_cast<int32_t>(d->cout / bn);
 
   // ---- main-loop variant and pipeline shape
-  const int mode = conv_mode();
   const bool halo = mode >= 1 && d->kind != SNB_CONV_1X1;
+  const bool fuse_phases = halo && mode >= 3 && d->kind == SNB_CONVT_4X4_S2 && kc.fn_halo4f != nullptr;
   int tile_w = 16, tile_h = 8;
   c->fn = kc.fn;
   c->smem = kc.smem;
@@ -709,13 +753,13 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     p.a_stages = a_stages;
     p.b_stages = b_stages;
     p.bres = bres ? 1 : 0;
-    c->fn = p.taps == 9 ? kc.fn_halo9 : kc.fn_halo4;
+    c->fn = p.taps == 9 ? kc.fn_halo9 : (fuse_phases ? kc.fn_halo4f : kc.fn_halo4);
   }
 
   p.tiles_x = static_cast<int32_t>((d->w + tile_w - 1) / tile_w);
   p.tiles_y = static_cast<int32_t>((d->h + tile_h - 1) / tile_h);
   p.n_img = static_cast<int32_t>(d->n);
-  const int64_t total = static_cast<int64_t>(p.n_phases) * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
+  const int64_t total = static_cast<int64_t>(fuse_phases ? 1 : p.n_phases) * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
   if (total > INT32_MAX) {
     delete c;
     return fail(SNB_E_UNSUPPORTED, "too many tiles");
@@ -767,8 +811,6 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     delete c;
     return fail(SNB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmemBudget, cudaGetErrorString(e));
   }
-  const int sms = sm_count();
-  if (sms <= 0) { delete c; return fail(SNB_E_CUDA, "no CUDA device"); }
   c->grid = std::min<int>(p.total_tiles, sms);
   // 2*MACs with the true tap counts (ConvT: every input pixel meets all 16 taps once over the 4 phases)
   c->flops = 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * (double)(p.n_phases * p.taps);

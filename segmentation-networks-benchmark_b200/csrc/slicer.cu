@@ -128,8 +128,9 @@ __global__ void split_norm_nchw_kernel(SlicerGeom g, const uint8_t* __restrict__
 // 16-byte vector, so global stores are fully coalesced and every source pixel is fetched ~1.3x instead of 27x.
 constexpr int kPatchRY = 8;
 
+template <int channels>
 __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, const uint8_t* __restrict__ src,
-                                                                 const float* __restrict__ lut, int channels, int tta,
+                                                                 const float* __restrict__ lut, int tta,
                                                                  uint4* __restrict__ dst, int64_t tile_begin) {
   extern __shared__ uint2 s_px[];                 // [(RY+2)][T+2] pixels, 4 x bf16 each
   __shared__ float s_lut[4 * 256];
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, c
       const int64_t sy = reflect101(cy + si - g.margin_top, g.image_h);
       const int64_t sx = reflect101(cx + sj - g.margin_left, g.image_w);
       const uint8_t* px = src + (sy * g.image_w + sx) * channels;
+#pragma unroll
       for (int c = 0; c < channels; ++c) f[c] = s_lut[c * 256 + __ldg(px + c)];
     }
     __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
@@ -389,11 +391,19 @@ extern "C" int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int6
     const int strips = (int)((T + kPatchRY - 1) / kPatchRY);
     const size_t smem = (size_t)(kPatchRY + 2) * (T + 2) * sizeof(uint2);
     if (smem > 200 * 1024) return fail(SNB_E_UNSUPPORTED, "tile size %lld too large for the PATCH32 split", (long long)T);
-    if (smem > 48 * 1024)
-      SNB_CUDA_CHECK(cudaFuncSetAttribute(split_norm_patch32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (tile_count * strips > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "too many strips");
-    split_norm_patch32_kernel<<<(unsigned)(tile_count * strips), 256, smem, as_stream(stream)>>>(
-        s->g, d_src, d_lut, (int)channels, tta, static_cast<uint4*>(d_dst), tile_begin);
+#define SNB_SPLIT_P32(C)                                                                                          \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      SNB_CUDA_CHECK(cudaFuncSetAttribute(split_norm_patch32_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                            \
+    split_norm_patch32_kernel<C><<<(unsigned)(tile_count * strips), 256, smem, as_stream(stream)>>>(              \
+        s->g, d_src, d_lut, tta, static_cast<uint4*>(d_dst), tile_begin);                                         \
+  } while (0)
+    if (channels == 3) SNB_SPLIT_P32(3);
+    else if (channels == 2) SNB_SPLIT_P32(2);
+    else SNB_SPLIT_P32(1);
+#undef SNB_SPLIT_P32
   } else {
     return fail(SNB_E_INVALID, "unknown layout %d", layout);
   }
