@@ -159,7 +159,7 @@ def run_cuda(args):
     model.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=0))
     model = model.to(dev).eval()
     pred = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), TILE, STEP, batch_size=args.batch, tta=args.tta,
-                              device=dev)
+                              device=dev, use_graph=args.graph)
 
     # distinct synthetic images per rank (weak scaling: one image per rank per step)
     n_img = 2
@@ -183,8 +183,7 @@ def run_cuda(args):
         return exchange(mask, counts)
 
     def step_e2e(i):
-        d = host_imgs[i % n_img].to(dev, non_blocking=True)                  # H2D from pinned memory
-        merged, mask = pred.predict_device(d)
+        merged, mask = pred.predict_device(host_imgs[i % n_img])             # H2D from pinned memory inside
         counts = exchange(mask, metrics.confusion_counts_from_probs(merged, gts[i % n_img]))
         host_mask.copy_(mask, non_blocking=True)                             # D2H of the step's result
         host_counts.copy_(counts, non_blocking=True)
@@ -211,8 +210,11 @@ def run_cuda(args):
         step_resident(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    ms_total = timed(step_resident, args.steps)          # the timed region: one CUDA-graph replay per image
+    clocks = sampler.summary()
 
-    # per-launch conv timing, live in the timed region: one event after every op of every plan run
+    # Per-launch conv timing with CUDA events.  Events cannot be recorded between the nodes of a replayed graph, so
+    # the same K steps are run once more eagerly, right here, with one event after every launch of every plan run.
     marks = []
     plan = pred.plan
     orig_run = plan.run
@@ -227,10 +229,9 @@ def run_cuda(args):
         marks.append(ev)
         return plan.out
 
-    plan.run = run_marked
-    ms_total = timed(step_resident, args.steps)
-    plan.run = orig_run
-    clocks = sampler.summary()
+    plan.run, pred.use_graph = run_marked, False
+    ms_eager = timed(step_resident, args.steps)
+    plan.run, pred.use_graph = orig_run, args.graph
 
     conv_ms, conv_flops, conv_launches, other_ms = 0.0, 0.0, 0, 0.0
     for ev in marks:
@@ -261,7 +262,7 @@ def run_cuda(args):
         "config": {"workload": "configs[2]: UNet16 tiled inference, 5000x5000x3 u8, tile 512 / step 384, pyramid merge"
                                + ("; configs[3]: one image per rank per step, NCCL all-reduce of IoU counts + gather of masks"
                                   if world > 1 else ""),
-                   "tiles_per_image": pred.n_tiles, "tile_batch": pred.batch, "tta": bool(args.tta),
+                   "tiles_per_image": pred.n_tiles, "tile_batch": pred.batch, "tta": bool(args.tta), "cuda_graph": bool(args.graph),
                    "l2_policy": "no flush needed: per-step working set (activations of %d tiles/batch, ~%.1f GB) >> 126 MB L2; "
                                 "%d images rotate" % (pred.batch, 0.245 * pred.batch, n_img),
                    "flop_per_image": pred.flops_per_image},
@@ -273,7 +274,10 @@ def run_cuda(args):
                      "frac": achieved / peak_tf, "traffic": None,
                      "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
                      "peak_source": peak_src + " bf16_tflops_sustained",
-                     "conv_share_of_step": conv_ms / ms_total, "conv_ms_per_step": conv_ms / args.steps,
+                     "timing": "CUDA events after every launch in an eager re-run of the same K steps (the timed "
+                               "region itself replays a CUDA graph); shares are of that eager pass",
+                     "conv_share_of_step": conv_ms / ms_eager, "conv_ms_per_step": conv_ms / args.steps,
+                     "eager_ms_per_step": ms_eager / args.steps,
                      "pool_ms_per_step": other_ms / args.steps,
                      "whole_step_tflops": pred.flops_per_image / (ms_step / 1e3) / 1e12},
     }
@@ -291,6 +295,7 @@ def main():
     ap.add_argument("--batch", type=int, default=13, help="tiles per network launch")
     ap.add_argument("--tta", action="store_true", help="D4 test-time augmentation (8 views per tile)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
