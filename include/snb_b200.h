@@ -126,6 +126,10 @@ typedef struct snb_conv_desc {
   float head_b;
   int32_t head_sigmoid;
   float* d_head_out;     /* float [n][h][w]                                                 */
+  /* optional fused nn.MaxPool2d(2,2) of the (bias, ReLU) output: a second bf16 slab [n][h/2][w/2] written from the
+   * same epilogue (conv3x3 only; h, w even) */
+  void* d_pool_out;      /* bf16, first channel written, or NULL                            */
+  int64_t pool_cstride;  /* pixel stride of the pooled slab, in channels                    */
 } snb_conv_desc;
 
 typedef struct snb_conv snb_conv;

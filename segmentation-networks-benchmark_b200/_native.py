@@ -48,6 +48,8 @@ class ConvDesc(ctypes.Structure):
         ("head_b", ctypes.c_float),
         ("head_sigmoid", ctypes.c_int32),
         ("d_head_out", c_vp),
+        ("d_pool_out", c_vp),
+        ("pool_cstride", c_i64),
     ]
 
 

@@ -48,6 +48,7 @@ struct alignas(64) ConvParams {
   CUtensorMap map_a;               // activations (C, W, H, N)
   CUtensorMap map_b;               // weights (Cin, Cout, phase*taps), box (BK, BN, 1)
   CUtensorMap map_d[kMaxPhases];   // outputs per phase (C, W, H, N)
+  CUtensorMap map_p;               // fused 2x2 max-pool output (C, W/2, H/2, N), box (CW, TW/2, TH/2, 1)
   int32_t n_phases, taps;          // taps per phase
   int32_t k_chunks;                // Cin / BK
   int32_t n_tiles;                 // Cout / BN
@@ -57,6 +58,7 @@ struct alignas(64) ConvParams {
   int32_t head_sigmoid;
   int32_t out_w, out_h;            // head output bounds
   int32_t a_stages, b_stages, bres;  // v2 pipeline shape
+  int32_t pool;                      // also write the 2x2 max-pooled tile through map_p
   float head_b;
   const float* bias;
   const float* head_w;
@@ -82,6 +84,7 @@ struct ConvCfg {
   // v2
   static constexpr int HALO_BOX_BYTES = kHaloRows * SWZ;
   static constexpr int HALO_STAGE_BYTES = (HALO_BOX_BYTES + 1023) / 1024 * 1024;
+  static constexpr int POOL_BYTES = (kBM / 4) * OUT_SWZ;   // staging of the pooled tile (32 pixels)
   static_assert(NSTAGES >= 3, "pipeline too shallow");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0, "swizzle atom alignment");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns");
@@ -103,6 +106,20 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   c.img = t % p.n_img;
   c.ph = t / p.n_img;
   return c;
+}
+
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
+  return make_uint4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                    __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -147,9 +164,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       p.head_out[(static_cast<int64_t>(tc.img) * p.out_h + oy) * p.out_w + ox] = dot;
   } else {
     constexpr int NCHUNK = BN / CW;
+    constexpr int POOL_BYTES = (kBM / 4) * OUT_SWZ;
+    // 2x2 max-pool partners of pixel (x, y) sit 1 and TW lanes away; lanes with even x and even y keep the result
+    const bool pool_keep = ((lane & 1) | (lane & TW)) == 0;
+    const int prow = ((row / TW) >> 1) * (TW / 2) + ((row % TW) >> 1);
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c, ++n_store) {
       uint8_t* sout = smem_out + (n_store & 1) * OUT_BYTES;
+      uint8_t* spool = smem_out + 2 * OUT_BYTES + (n_store & 1) * POOL_BYTES;
       // the TMA store issued two chunks ago must have finished reading this buffer
       if (epi_tid == 0) tma_store_wait_read<1>();
       named_bar_sync(1, 128);
@@ -173,8 +195,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
           const int chunk = g * 4 + j;
           const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
           uint4* dst = reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4));
-          *dst = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                            pack_bf16x2(f[6], f[7]));
+          uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                pack_bf16x2(f[6], f[7]));
+          *dst = pk;
+          if (p.pool) {
+            pk = bf16x8_max(pk, shfl_xor_u4(pk, 1));
+            pk = bf16x8_max(pk, shfl_xor_u4(pk, TW));
+            if (pool_keep) {
+              const int swp = OUT_SWZ == 128 ? (prow & 7) : ((prow >> 1) & 3);
+              *reinterpret_cast<uint4*>(spool + prow * OUT_SWZ + ((chunk ^ swp) << 4)) = pk;
+            }
+          }
         }
       }
       if (release && c == NCHUNK - 1) {
@@ -187,6 +218,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       named_bar_sync(1, 128);
       if (epi_tid == 0) {
         tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
+        if (p.pool) tma_store_4d(&p.map_p, spool, tc.nt * BN + c * CW, tc.x0 >> 1, tc.y0 >> 1, tc.img);
         tma_store_commit();
       }
     }
@@ -360,7 +392,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.a_stages * Cfg::HALO_STAGE_BYTES;
   uint8_t* smem_out = smem_b + n_b_slots * Cfg::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + (HEAD ? 0 : 2 * Cfg::OUT_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + (HEAD ? 0 : 2 * Cfg::OUT_BYTES + 2 * Cfg::POOL_BYTES));
   uint64_t* a_full = bars;                          // [kMaxAStages]
   uint64_t* a_empty = a_full + kMaxAStages;         // [kMaxAStages]
   uint64_t* b_full = a_empty + kMaxAStages;         // [kMaxBStages]  (b_full[0] doubles as the bres barrier)
@@ -378,6 +410,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     tma_prefetch_desc(&p.map_b);
     if (!HEAD)
       for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.map_d[i]);
+    if (p.pool) tma_prefetch_desc(&p.map_p);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kMaxAStages; ++i) {
@@ -583,7 +616,7 @@ struct KernelChoice {
   const void* fn_halo4f; // v2 kernel, ConvTranspose with the 4 phases fused into one tile (BN <= 64), or null
   int smem;              // v1 dynamic smem
   int bn, bk;
-  int halo_stage_bytes, b_bytes, out_bytes;
+  int halo_stage_bytes, b_bytes, out_bytes, pool_bytes;
 };
 
 template <int BN, int BK, bool HEAD>
@@ -598,7 +631,8 @@ static KernelChoice choice() {
   return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>),
                       reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1>),
                       reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1>), fused_phase_kernel<BN, BK, HEAD>(),
-                      Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES, HEAD ? 0 : Cfg::OUT_BYTES};
+                      Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES, HEAD ? 0 : Cfg::OUT_BYTES,
+                      HEAD ? 0 : Cfg::POOL_BYTES};
 }
 
 static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
@@ -666,6 +700,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (!head && (!d->d_out || d->out_cstride < d->cout || d->out_cstride % 8 != 0))
     return fail(SNB_E_INVALID, "bad output slab");
   if (!d->d_in || !d->d_weight || !d->d_bias) return fail(SNB_E_INVALID, "null tensor pointer");
+  const bool pool = d->d_pool_out != nullptr;
+  if (pool && (head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
+               d->pool_cstride % 8 != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
+    return fail(SNB_E_INVALID, "fused max-pool needs a conv3x3 without head, even h and w and a valid pooled slab");
   if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
       (reinterpret_cast<uintptr_t>(d->d_weight) & 15) || (reinterpret_cast<uintptr_t>(d->d_bias) & 15))
     return fail(SNB_E_INVALID, "tensor pointers must be 16-byte aligned");
@@ -719,6 +757,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
 
   // ---- main-loop variant and pipeline shape
   const bool halo = mode >= 1 && d->kind != SNB_CONV_1X1;
+  if (pool && !halo) {
+    delete c;
+    return fail(SNB_E_UNSUPPORTED, "fused max-pool is only available in halo mode (SNB_CONV_MODE >= 1)");
+  }
   const bool fuse_phases = halo && mode >= 3 && d->kind == SNB_CONVT_4X4_S2 && kc.fn_halo4f != nullptr;
   int tile_w = 16, tile_h = 8;
   c->fn = kc.fn;
@@ -726,7 +768,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (halo) {
     tile_w = 8;
     tile_h = 16;
-    const int fixed = 1024 /*align*/ + 1024 /*ctrl*/ + 2 * kc.out_bytes;
+    const int fixed = 1024 /*align*/ + 1024 /*ctrl*/ + 2 * kc.out_bytes + 2 * kc.pool_bytes;
     const int64_t w_slots = (int64_t)p.n_phases * p.taps * p.k_chunks;
     const int64_t w_bytes = w_slots * kc.b_bytes;
     int a_stages = std::min<int>(3, std::max<int>(2, p.k_chunks + 1));
@@ -804,6 +846,17 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       rc = encode_map(&p.map_d[ph], base, 4, dims, str, box, cw * 2);
       if (rc) { delete c; return rc; }
     }
+  }
+
+  p.pool = pool ? 1 : 0;
+  if (pool) {
+    const int cw = bn < 64 ? bn : 64;
+    uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)(d->w / 2), (uint64_t)(d->h / 2), (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->pool_cstride * 2, (uint64_t)(d->w / 2) * d->pool_cstride * 2,
+                       (uint64_t)(d->h / 2) * (d->w / 2) * d->pool_cstride * 2};
+    uint32_t box[4] = {(uint32_t)cw, (uint32_t)(tile_w / 2), (uint32_t)(tile_h / 2), 1};
+    rc = encode_map(&p.map_p, d->d_pool_out, 4, dims, str, box, cw * 2);
+    if (rc) { delete c; return rc; }
   }
 
   cudaError_t e = cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);

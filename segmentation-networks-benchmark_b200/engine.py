@@ -7,6 +7,7 @@ lib/models/unet16.py:122-127 never runs), weights are packed K-major bf16 per ta
 allocation, no synchronisation, CUDA-graph capturable.
 """
 import ctypes
+import os
 
 import torch
 
@@ -83,8 +84,8 @@ class SlabView:
 class ConvOp:
     """One snb_conv handle; keeps every tensor it points at alive."""
 
-    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None):
-        self.keep = (src, dst, weight, bias, head)
+    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None):
+        self.keep = (src, dst, weight, bias, head, pool_dst)
         d = N.ConvDesc()
         d.kind = kind
         d.relu = 1 if relu else 0
@@ -104,6 +105,9 @@ class ConvOp:
             d.head_b = float(head_b)
             d.head_sigmoid = 1 if head_sigmoid else 0
             d.d_head_out = head_out.data_ptr()
+        if pool_dst is not None:
+            d.d_pool_out = pool_dst.ptr
+            d.pool_cstride = pool_dst.cstride
         if weight.shape[1] != d.cout or weight.shape[2] != d.cin:
             raise ValueError("packed weight %s does not match cout=%d cin=%d" % (tuple(weight.shape), d.cout, d.cin))
         self.desc = (int(d.kind), int(d.h), int(d.w), int(d.cin), int(d.cout))
@@ -151,6 +155,8 @@ class VGGUNetPlan:
         self.n, self.h, self.w = n, h, w
         self.device = device
         self.ops = []
+        # SNB_CONV_MODE=0 (tap-mode A/B runs) has no fused pooling; SNB_FUSE_POOL=0 keeps the separate kernel
+        fuse_pool = os.environ.get("SNB_CONV_MODE", "3") != "0" and os.environ.get("SNB_FUSE_POOL", "1") != "0"
         f32 = lambda b: b.detach().float().contiguous()
         S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
 
@@ -172,13 +178,17 @@ class VGGUNetPlan:
                 cout = wt.shape[0]
                 last = li == len(stage) - 1
                 dst = slabs[s].view(up_c[4 - s], cout) if last else S(hh, ww, cout).view()
+                # the stage's last conv also writes the 2x2 max-pooled tensor from its epilogue
+                pooled = S(hh // 2, ww // 2, cout).view() if last else None
+                fuse = pooled is not None and fuse_pool and not (s == 0 and li == 0)
                 if s == 0 and li == 0:
                     self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt), f32(bs)))
                 else:
-                    self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt), f32(bs)))
+                    self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt), f32(bs),
+                                           pool_dst=pooled if fuse else None))
                 cur = dst
-            pooled = S(hh // 2, ww // 2, cur.c).view()
-            self.ops.append(PoolOp(cur, pooled))
+            if not fuse:
+                self.ops.append(PoolOp(cur, pooled))
             cur = pooled
 
         # center consumes the pooled conv5; dec5..dec2 consume the concat slabs

@@ -150,3 +150,26 @@ def test_bad_descriptors_raise(cuda):
     w = torch.zeros((9, 64, 48), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(ValueError):
         E.ConvOp(N.CONV_3X3, s.view(), d.view(), w, torch.zeros(64, device="cuda"))   # cin not a multiple of 32
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 64, 64), (1, 16, 24, 128, 256), (1, 48, 40, 64, 128),
+                                            (1, 32, 16, 256, 512)])
+def test_fused_maxpool_epilogue(cuda, conv_mode, n, h, w, cin, cout):
+    """The stage-final conv writes conv output and its 2x2 max-pool from the same epilogue (lib/models/unet16.py:64)."""
+    if conv_mode == 0:
+        pytest.skip("tap mode keeps the separate pooling kernel")
+    g = torch.Generator(device="cuda").manual_seed(cin + 3 * cout)
+    src = rand_slab(n, h, w, cin, g)
+    dst = E.Slab(n, h, w, cout + 32, "cuda")
+    pooled = E.Slab(n, h // 2, w // 2, cout, "cuda")
+    dst.t.zero_()
+    pooled.t.fill_(float("nan"))
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    op = E.ConvOp(N.CONV_3X3, src.view(), dst.view(32, cout), E.pack_conv3x3(wt), bias, pool_dst=pooled.view())
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    want = F.relu(F.conv2d(nchw(src.view()), bf(wt), bias, padding=1))
+    check(nchw(dst.view(32, cout)), want)
+    # the pooled tensor is exactly the max-pool of what the kernel itself stored
+    assert torch.equal(nchw(pooled.view()), F.max_pool2d(nchw(dst.view(32, cout)), 2, 2))
