@@ -49,6 +49,7 @@ struct alignas(64) ConvParams {
   CUtensorMap map_b;               // weights (Cin, Cout, phase*taps), box (BK, BN, 1)
   CUtensorMap map_d[kMaxPhases];   // outputs per phase (C, W, H, N)
   CUtensorMap map_p;               // fused 2x2 max-pool output (C, W/2, H/2, N), box (CW, TW/2, TH/2, 1)
+  CUtensorMap map_bh;              // weights with a half-height box (BK, BN/2, 1): multicast halves in CTA pairs
   int32_t n_phases, taps;          // taps per phase
   int32_t k_chunks;                // Cin / BK
   int32_t n_tiles;                 // Cout / BN
@@ -59,6 +60,7 @@ struct alignas(64) ConvParams {
   int32_t out_w, out_h;            // head output bounds
   int32_t a_stages, b_stages, bres;  // v2 pipeline shape
   int32_t pool;                      // also write the 2x2 max-pooled tile through map_p
+  int32_t m_pairs;                   // CTA-pair kernels: spatial tiles per phase / 2
   float head_b;
   const float* bias;
   const float* head_w;
@@ -105,6 +107,24 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   t /= p.tiles_y;
   c.img = t % p.n_img;
   c.ph = t / p.n_img;
+  return c;
+}
+
+// CTA-pair order: consecutive tile ids (2j, 2j+1) are two spatial tiles with the same N tile and phase, so the two
+// CTAs of a cluster walk identical (chunk, tap) sequences and can share every weight box.
+template <int TW, int TH>
+__device__ __forceinline__ TileCoord decode_tile_pair(const ConvParams& p, int u) {
+  TileCoord c;
+  const int r = u & 1;
+  int v = u >> 1;
+  c.nt = v % p.n_tiles;
+  v /= p.n_tiles;
+  int m = (v % p.m_pairs) * 2 + r;
+  c.ph = v / p.m_pairs;
+  c.x0 = (m % p.tiles_x) * TW;
+  m /= p.tiles_x;
+  c.y0 = (m % p.tiles_y) * TH;
+  c.img = m / p.tiles_y;
   return c;
 }
 
@@ -374,8 +394,12 @@ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
 
 // NPH = 4 fuses the four sub-pixel phases of a ConvTranspose into one tile (four accumulators of BN columns): the
 // halo box is then loaded once per spatial tile instead of once per phase.
-template <int BN, int BK, bool HEAD, int TAPS, int NPH>
+// CL = 2 runs CTA pairs (thread-block cluster of 2) on two spatial tiles of the same N tile: each CTA fetches half of
+// every weight box and TMA-multicasts it into both CTAs' shared memory, halving the L2->SM weight traffic that
+// bounds the large layers (32 KB per tap per CTA at BN=256 otherwise).
+template <int BN, int BK, bool HEAD, int TAPS, int NPH, int CL>
 __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(CL == 1 || (CL == 2 && NPH == 1 && !HEAD && BN >= 128), "CTA pairs are for the streamed-weight layers");
   using Cfg = ConvCfg<BN, BK>;
   static_assert(NPH == 1 || (NPH == 4 && TAPS == 4 && !HEAD), "phase fusion is for ConvTranspose");
   constexpr int TCOLS = Cfg::TMEM_COLS * NPH;
@@ -419,7 +443,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], CL);   // every CTA of the cluster must have consumed a multicast stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -438,8 +462,10 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   }
   tc05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anything is multicast into them
   tc05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  auto decode = [&](int t) { return CL > 1 ? decode_tile_pair<TW, TH>(p, t) : decode_tile<TW, TH>(p, t); };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (+ resident weights)
@@ -462,7 +488,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
       }
       uint32_t s = 0, par = 1;   // waiting on parity 1 of a fresh barrier returns immediately
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile<TW, TH>(p, t);
+        const TileCoord tc = decode(t);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_empty[s], par);
           mbar_arrive_expect_tx(&a_full[s], Cfg::HALO_BOX_BYTES);
@@ -474,16 +500,23 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (streamed weights)
     if (!p.bres && elect_one()) {
+      const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
       uint32_t s = 0, par = 1;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile<TW, TH>(p, t);
+        const TileCoord tc = decode(t);
         const int n0 = tc.nt * BN, w0 = tc.ph * TAPS;   // tc.ph == 0 when the phases are fused
         for (int kc = 0; kc < p.k_chunks; ++kc) {
 #pragma unroll 1
           for (int wt = 0; wt < NPH * TAPS; ++wt) {
             mbar_wait(&b_empty[s], par);
             mbar_arrive_expect_tx(&b_full[s], Cfg::B_BYTES);
-            tma_load_3d(&p.map_b, &b_full[s], smem_b + s * Cfg::B_BYTES, kc * BK, n0, w0 + wt);
+            if (CL == 1) {
+              tma_load_3d(&p.map_b, &b_full[s], smem_b + s * Cfg::B_BYTES, kc * BK, n0, w0 + wt);
+            } else {
+              // my half of the box (BN/2 weight rows) goes to both CTAs; the peer sends the other half
+              tma_load_3d_mc(&p.map_bh, &b_full[s], smem_b + s * Cfg::B_BYTES + cta_rank * (Cfg::B_BYTES / 2), kc * BK,
+                             n0 + static_cast<int>(cta_rank) * (BN / 2), w0 + wt, static_cast<uint16_t>(0x3));
+            }
             if (++s == static_cast<uint32_t>(p.b_stages)) { s = 0; par ^= 1; }
           }
         }
@@ -532,7 +565,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
               umma_bf16_ss(desc_from_halves(a_lo + aoff[wt] + 2 * k, HI_A), desc_from_halves(b_lo + 2 * k, HI_B),
                            d_tmem + (wt / TAPS) * BN, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
             if (!bres) {
-              umma_commit(&b_empty[sb]);
+              if (CL == 1) umma_commit(&b_empty[sb]);
+              else umma_commit_mc(&b_empty[sb], static_cast<uint16_t>(0x3));
               if (++sb == b_stages) { sb = 0; pb ^= 1; }
             } else {
               b_lo += B_BYTES16;
@@ -552,7 +586,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     uint32_t local_tile = 0;
     uint32_t n_store = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
-      TileCoord tc = decode_tile<TW, TH>(p, t);
+      TileCoord tc = decode(t);
       const uint32_t acc = local_tile & 1;
       const uint32_t acc_ph = (local_tile >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
@@ -570,6 +604,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
 
   tc05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
   if (warp == 2) {
     tc05_fence_after();
     tmem_dealloc(tmem_base, TCOLS);
@@ -614,6 +649,8 @@ struct KernelChoice {
   const void* fn_halo9;  // v2 kernel, 9 taps (conv3x3)
   const void* fn_halo4;  // v2 kernel, 4 taps per phase (ConvTranspose k4 s2)
   const void* fn_halo4f; // v2 kernel, ConvTranspose with the 4 phases fused into one tile (BN <= 64), or null
+  const void* fn_pair9;  // v2 kernel in CTA pairs with multicast weights (BN >= 128), or null
+  const void* fn_pair4;
   int smem;              // v1 dynamic smem
   int bn, bk;
   int halo_stage_bytes, b_bytes, out_bytes, pool_bytes;
@@ -621,7 +658,13 @@ struct KernelChoice {
 
 template <int BN, int BK, bool HEAD>
 static const void* fused_phase_kernel() {
-  if constexpr (!HEAD && BN <= 64) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, 4, 4>);
+  if constexpr (!HEAD && BN <= 64) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, 4, 4, 1>);
+  else return nullptr;
+}
+
+template <int BN, int BK, bool HEAD, int TAPS>
+static const void* pair_kernel() {
+  if constexpr (!HEAD && BN >= 128) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, TAPS, 1, 2>);
   else return nullptr;
 }
 
@@ -629,8 +672,9 @@ template <int BN, int BK, bool HEAD>
 static KernelChoice choice() {
   using Cfg = ConvCfg<BN, BK>;
   return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>),
-                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1>),
-                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1>), fused_phase_kernel<BN, BK, HEAD>(),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1, 1>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1, 1>), fused_phase_kernel<BN, BK, HEAD>(),
+                      pair_kernel<BN, BK, HEAD, 9>(), pair_kernel<BN, BK, HEAD, 4>(),
                       Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES, HEAD ? 0 : Cfg::OUT_BYTES,
                       HEAD ? 0 : Cfg::POOL_BYTES};
 }
@@ -659,8 +703,9 @@ static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
 }
 
 // SNB_CONV_MODE: 0 = tap mode everywhere, 1 = halo mode with streamed weights, 2 = + resident weights where they
-// fit, 3 (default) = + ConvTranspose phases fused into one tile (Cout <= 64) and N tile narrowed to 128 when the
-// 256-wide tiling would leave the last wave mostly empty.  Read at snb_conv_create time (A/B without a rebuild).
+// fit, 3 = + ConvTranspose phases fused into one tile (Cout <= 64) and N tile narrowed to 128 when the 256-wide tiling
+// would leave the last wave mostly empty (default), 4 = + CTA pairs with multicast weights for the streamed-weight
+// layers (measured: no gain, the large layers are power-bound, not L2-bound).  Read at snb_conv_create time.
 static int conv_mode() {
   const char* e = std::getenv("SNB_CONV_MODE");
   if (!e || !*e) return 3;
@@ -681,6 +726,7 @@ struct snb_conv {
   const void* fn;
   int smem;
   int grid;
+  int cluster;   // 1, or 2 for the CTA-pair kernels
   double flops;
 };
 
@@ -728,6 +774,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
 
   snb_conv* c = new (std::nothrow) snb_conv();
   if (!c) return fail(SNB_E_INVALID, "out of host memory");
+  c->cluster = 1;
   ConvParams& p = c->params;
   std::memset(&p, 0, sizeof(p));
   c->kernel = kc;
@@ -784,7 +831,11 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       a_stages = 2;
       b_stages = (kSmemBudget - fixed - a_stages * kc.halo_stage_bytes) / kc.b_bytes;
       if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-      if (b_stages < 3) {
+      if (const char* e = std::getenv("SNB_B_STAGES")) {   // pipeline-depth experiments
+        const int v = std::atoi(e);
+        if (v >= 2 && v < b_stages) b_stages = v;
+      }
+      if (b_stages < 2) {
         delete c;
         return fail(SNB_E_UNSUPPORTED, "halo pipeline does not fit in shared memory");
       }
@@ -796,6 +847,14 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     p.b_stages = b_stages;
     p.bres = bres ? 1 : 0;
     c->fn = p.taps == 9 ? kc.fn_halo9 : (fuse_phases ? kc.fn_halo4f : kc.fn_halo4);
+    // CTA pairs: streamed weights, an even number of spatial tiles per phase, and a pair kernel for this shape
+    const int64_t m_tiles = (int64_t)d->n * ((d->h + tile_h - 1) / tile_h) * ((d->w + tile_w - 1) / tile_w);
+    const void* fn_pair = p.taps == 9 ? kc.fn_pair9 : kc.fn_pair4;
+    if (mode >= 4 && !bres && !fuse_phases && fn_pair && m_tiles % 2 == 0 && sms >= 2) {
+      c->fn = fn_pair;
+      c->cluster = 2;
+      p.m_pairs = static_cast<int32_t>(m_tiles / 2);
+    }
   }
 
   p.tiles_x = static_cast<int32_t>((d->w + tile_w - 1) / tile_w);
@@ -831,6 +890,11 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     uint32_t box[3] = {(uint32_t)bk, (uint32_t)bn, 1};
     rc = encode_map(&p.map_b, const_cast<void*>(d->d_weight), 3, dims, str, box, bk * 2);
     if (rc) { delete c; return rc; }
+    if (c->cluster == 2) {
+      uint32_t half[3] = {(uint32_t)bk, (uint32_t)(bn / 2), 1};
+      rc = encode_map(&p.map_bh, const_cast<void*>(d->d_weight), 3, dims, str, half, bk * 2);
+      if (rc) { delete c; return rc; }
+    }
   }
   if (!head) {
     const int cw = bn < 64 ? bn : 64;
@@ -865,6 +929,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     return fail(SNB_E_CUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmemBudget, cudaGetErrorString(e));
   }
   c->grid = std::min<int>(p.total_tiles, sms);
+  if (c->cluster == 2) c->grid &= ~1;   // whole CTA pairs; total_tiles is even
   // 2*MACs with the true tap counts (ConvT: every input pixel meets all 16 taps once over the 4 phases)
   c->flops = 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * (double)(p.n_phases * p.taps);
   *out = c;
@@ -874,7 +939,24 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
 extern "C" int snb_conv_launch(const snb_conv* c, void* stream) {
   if (!c) return fail(SNB_E_INVALID, "snb_conv_launch: null handle");
   void* args[1] = {const_cast<ConvParams*>(&c->params)};
-  cudaError_t e = cudaLaunchKernel(c->fn, dim3(c->grid), dim3(256), args, c->smem, as_stream(stream));
+  cudaError_t e;
+  if (c->cluster == 1) {
+    e = cudaLaunchKernel(c->fn, dim3(c->grid), dim3(256), args, c->smem, as_stream(stream));
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c->grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = c->smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = c->cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelExC(&cfg, c->fn, args);
+  }
   if (e != cudaSuccess) return fail(SNB_E_CUDA, "conv launch failed: %s", cudaGetErrorString(e));
   return SNB_OK;
 }

@@ -10,7 +10,7 @@ from snb_b200 import engine as E
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["tap", "halo", "halo+bres"], autouse=True)
+@pytest.fixture(params=[0, 1, 2, 4], ids=["tap", "halo", "halo+bres", "pairs"], autouse=True)
 def conv_mode(request, monkeypatch):
     """Every test runs against the three main-loop variants (SNB_CONV_MODE is read at snb_conv_create)."""
     monkeypatch.setenv("SNB_CONV_MODE", str(request.param))

@@ -35,7 +35,7 @@ for _ in range(reps):
     for k in range(len(plan.ops)):
         acc[k] += ev[k].elapsed_time(ev[k + 1]) / reps
 tot = sum(acc)
-print("mode=%s batch=%d tile=%d total %.3f ms  (%.1f TFLOP/s)" % (os.environ.get("SNB_CONV_MODE", "2"), batch, T, tot,
+print("mode=%s batch=%d tile=%d total %.3f ms  (%.1f TFLOP/s)" % (os.environ.get("SNB_CONV_MODE", "default"), batch, T, tot,
                                                                 plan.flops / tot / 1e9))
 for k, op in enumerate(plan.ops):
     if isinstance(op, ConvOp):
