@@ -130,6 +130,10 @@ typedef struct snb_conv_desc {
    * same epilogue (conv3x3 only; h, w even) */
   void* d_pool_out;      /* bf16, first channel written, or NULL                            */
   int64_t pool_cstride;  /* pixel stride of the pooled slab, in channels                    */
+  /* nn.Upsample(scale_factor=2) (nearest) fused into the store: d_out is then a slab of [n][2h][2w] pixels and every
+   * output pixel is written to its 2x2 block (lib/models/zf_unet.py:42,78-90); conv3x3 / conv1x1 only */
+  int32_t out_upsample2x;
+  int32_t reserved0;
 } snb_conv_desc;
 
 typedef struct snb_conv snb_conv;

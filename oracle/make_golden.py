@@ -35,6 +35,7 @@ from lib.common import InMemoryDataset  # noqa: E402
 from lib.datasets.Inria import INRIA_MEAN, INRIA_STD  # noqa: E402
 from lib.models.unet11 import UNet11  # noqa: E402
 from lib.models.unet16 import UNet16  # noqa: E402
+from lib.models.zf_unet import ZF_UNET  # noqa: E402
 from lib.tiles import ImageSlicer, compute_patch_weight_loss  # noqa: E402
 from lib.train_utils import PRCurveMeter  # noqa: E402
 
@@ -164,6 +165,35 @@ def model_vectors():
     np.savez_compressed(os.path.join(OUT, "models.npz"), **d)
 
 
+def zf_unet_vectors():
+    """BASELINE configs[0]: ZF_UNET 224 forward + BCE-soft-Jaccard loss + IoU on a synthetic 8x3x224x224 batch (eval),
+    plus a small 2x3x64x96 case whose full logits are stored."""
+    m = ZF_UNET()
+    sd = synth.zf_unet_state_dict(seed=4)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.eval()
+    d = {}
+    x_small = torch.from_numpy(np.random.RandomState(6).standard_normal((2, 3, 64, 96)).astype(np.float32))
+    x, y = synth.logits_targets(8, (8, 1, 224, 224))
+    x224 = torch.from_numpy(np.random.RandomState(8).standard_normal((8, 3, 224, 224)).astype(np.float32))
+    with torch.no_grad():
+        d["small_x"] = x_small.numpy()
+        d["small_logits"] = m(x_small).numpy()
+        logits = m(x224)
+    d["cfg1_logits_sample"] = logits[:, :, ::7, ::7].numpy()          # 8 x 1 x 32 x 32 subsample of the 224 logits
+    loss = ref_losses.BCEWithLogitsLossAndSmoothJaccard()
+    loss.bce_loss.size_average = True
+    loss.bce_loss.reduce = True
+    pred = torch.sigmoid(logits) > 0.5
+    t = y.bool()
+    np.savez_compressed(os.path.join(OUT, "zf_unet.npz"), **d)
+    return dict(bce_jaccard=float(loss(logits, y)), jaccard_score=float(ref_metrics.JaccardScore()(logits, y)),
+                pixel_accuracy=float(ref_metrics.PixelAccuracy()(logits, y)),
+                counts=[int((pred & t).sum()), int((pred & ~t).sum()), int((~pred & t).sum()), int((~pred & ~t).sum())],
+                logit_min=float(logits.min()), logit_max=float(logits.max()))
+
+
 def predict_tiled_vector():
     """inria_submit.predict_tiled (:237-257) on CPU: same calls, without .cuda(); tile 64 / step 32, with and
     without D4 TTA, plus the submit threshold (:305)."""
@@ -200,7 +230,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(),
+    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(),
                 torch_version=torch.__version__, numpy_version=np.__version__)
     split_merge_vectors()
     normalize_vectors()

@@ -45,6 +45,43 @@ def unet_vgg_forward(sd, x, arch='unet16', quant=None):
     return F.conv2d(x, w, b)   # the 1x1 head stays fp32 on the device path too
 
 
+ZF_BLOCKS = ['conv_224', 'conv_112', 'conv_56', 'conv_28', 'conv_14', 'conv_7', 'up_conv_14', 'up_conv_28',
+             'up_conv_56', 'up_conv_112', 'up_conv_224']
+
+
+def _conv_bn_relu(x, sd, prefix, quant=None, fold=False):
+    """_Conv3BN.forward in eval mode (lib/models/zf_unet.py:5-17).  With fold=True the BatchNorm is folded into the
+    conv first (what the device path does), which matters only when `quant` rounds the folded weights."""
+    w, b = sd[prefix + '.conv.weight'], sd[prefix + '.conv.bias']
+    g, beta = sd[prefix + '.bn.weight'], sd[prefix + '.bn.bias']
+    mean, var = sd[prefix + '.bn.running_mean'], sd[prefix + '.bn.running_var']
+    if fold:
+        scale = g / torch.sqrt(var + 1e-5)
+        w, b = w * scale.view(-1, 1, 1, 1), (b - mean) * scale + beta
+        if quant is not None:
+            x, w = quant(x), quant(w)
+        return F.relu(F.conv2d(x, w, b, padding=1))
+    y = F.conv2d(x, w, b, padding=1)
+    return F.relu(F.batch_norm(y, mean, var, g, beta, training=False, eps=1e-5))
+
+
+def zf_unet_forward(sd, x, quant=None, fold=False):
+    """ZF_UNET.forward in eval mode (lib/models/zf_unet.py:60-95): Dropout2d inactive, nearest x2 upsampling."""
+    def block(t, name):
+        t = _conv_bn_relu(t, sd, name + '.l1', quant, fold)
+        return _conv_bn_relu(t, sd, name + '.l2', quant, fold)
+
+    skips = []
+    for name in ZF_BLOCKS[:5]:
+        x = block(x, name)
+        skips.append(x)
+        x = F.max_pool2d(x, 2)
+    x = block(x, 'conv_7')
+    for name, skip in zip(ZF_BLOCKS[6:], skips[::-1]):
+        x = block(torch.cat([F.interpolate(x, scale_factor=2, mode='nearest'), skip], 1), name)
+    return F.conv2d(x, sd['conv_final.weight'], sd['conv_final.bias'])
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 

@@ -57,6 +57,33 @@ def vgg_unet_state_dict(arch='unet16', seed=0):
     return sd
 
 
+def zf_unet_state_dict(seed=0, filters=32):
+    """Random ZF_UNET state_dict (reference key names); BatchNorm buffers randomised so the folding is exercised
+    (running_mean~N(0,0.1), running_var~U(0.5,1.5), weight~U(0.5,1.5), bias~N(0,0.1))."""
+    rs = np.random.RandomState(seed)
+    f = filters
+    io = [('conv_224', 3, f), ('conv_112', f, 2 * f), ('conv_56', 2 * f, 4 * f), ('conv_28', 4 * f, 8 * f),
+          ('conv_14', 8 * f, 16 * f), ('conv_7', 16 * f, 32 * f), ('up_conv_14', 48 * f, 16 * f),
+          ('up_conv_28', 24 * f, 8 * f), ('up_conv_56', 12 * f, 4 * f), ('up_conv_112', 6 * f, 2 * f),
+          ('up_conv_224', 3 * f, f)]
+    sd = {}
+    for name, cin, cout in io:
+        for layer, ci in (('l1', cin), ('l2', cout)):
+            pre = '%s.%s.' % (name, layer)
+            # gain 0.8: with the randomised BatchNorm scales (mean square ~1.2) activations keep O(1) magnitude over the
+            # 22 layers, so the bf16 rounding noise of the logits stays ~1e-2 (probabilities inside the 2e-2 band)
+            sd[pre + 'conv.weight'] = _he(rs, (cout, ci, 3, 3), ci * 9, gain=0.8)
+            sd[pre + 'conv.bias'] = _bias(rs, cout)
+            sd[pre + 'bn.weight'] = torch.from_numpy(rs.uniform(0.5, 1.5, cout).astype(np.float32))
+            sd[pre + 'bn.bias'] = torch.from_numpy((rs.standard_normal(cout) * 0.1).astype(np.float32))
+            sd[pre + 'bn.running_mean'] = torch.from_numpy((rs.standard_normal(cout) * 0.1).astype(np.float32))
+            sd[pre + 'bn.running_var'] = torch.from_numpy(rs.uniform(0.5, 1.5, cout).astype(np.float32))
+            sd[pre + 'bn.num_batches_tracked'] = torch.tensor(7, dtype=torch.int64)
+    sd['conv_final.weight'] = _he(rs, (1, f, 1, 1), f, gain=1.5)
+    sd['conv_final.bias'] = _bias(rs, 1)
+    return sd
+
+
 def image_u8(seed, h, w, c=3, smooth=True):
     """Inria-shaped synthetic uint8 image; low-pass structure so masks are not pure noise."""
     rs = np.random.RandomState(seed)

@@ -50,6 +50,8 @@ class ConvDesc(ctypes.Structure):
         ("d_head_out", c_vp),
         ("d_pool_out", c_vp),
         ("pool_cstride", c_i64),
+        ("out_upsample2x", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
     ]
 
 

@@ -61,6 +61,7 @@ struct alignas(64) ConvParams {
   int32_t a_stages, b_stages, bres;  // v2 pipeline shape
   int32_t pool;                      // also write the 2x2 max-pooled tile through map_p
   int32_t m_pairs;                   // CTA-pair kernels: spatial tiles per phase / 2
+  int32_t up2x;                      // store every tile through all 4 map_d (nearest 2x upsample of the output)
   float head_b;
   const float* bias;
   const float* head_w;
@@ -237,7 +238,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (epi_tid == 0) {
-        tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
+        if (p.up2x) {
+#pragma unroll
+          for (int rep = 0; rep < 4; ++rep)
+            tma_store_4d(&p.map_d[rep], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
+        } else {
+          tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
+        }
         if (p.pool) tma_store_4d(&p.map_p, spool, tc.nt * BN + c * CW, tc.x0 >> 1, tc.y0 >> 1, tc.img);
         tma_store_commit();
       }
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
     if (!HEAD)
-      for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.map_d[i]);
+      for (int i = 0; i < (p.up2x ? 4 : p.n_phases); ++i) tma_prefetch_desc(&p.map_d[i]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
     if (!HEAD)
-      for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.map_d[i]);
+      for (int i = 0; i < (p.up2x ? 4 : p.n_phases); ++i) tma_prefetch_desc(&p.map_d[i]);
     if (p.pool) tma_prefetch_desc(&p.map_p);
   }
   if (warp == 1 && lane == 0) {
@@ -746,6 +753,9 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (!head && (!d->d_out || d->out_cstride < d->cout || d->out_cstride % 8 != 0))
     return fail(SNB_E_INVALID, "bad output slab");
   if (!d->d_in || !d->d_weight || !d->d_bias) return fail(SNB_E_INVALID, "null tensor pointer");
+  const bool up2x = d->out_upsample2x != 0;
+  if (up2x && (head || d->kind == SNB_CONVT_4X4_S2))
+    return fail(SNB_E_INVALID, "out_upsample2x applies to conv3x3 / conv1x1 without a fused head");
   const bool pool = d->d_pool_out != nullptr;
   if (pool && (head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
                d->pool_cstride % 8 != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
@@ -898,9 +908,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   }
   if (!head) {
     const int cw = bn < 64 ? bn : 64;
-    const int s = d->kind == SNB_CONVT_4X4_S2 ? 2 : 1;
+    const int s = (d->kind == SNB_CONVT_4X4_S2 || up2x) ? 2 : 1;
     const int64_t ow = d->w * s, oh = d->h * s;
-    for (int ph = 0; ph < p.n_phases; ++ph) {
+    p.up2x = up2x ? 1 : 0;
+    for (int ph = 0; ph < (up2x ? 4 : p.n_phases); ++ph) {
       const int py = ph / 2, px = ph % 2;
       char* base = static_cast<char*>(d->d_out) + ((int64_t)py * ow + px) * d->out_cstride * 2;
       uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};

@@ -84,7 +84,7 @@ class SlabView:
 class ConvOp:
     """One snb_conv handle; keeps every tensor it points at alive."""
 
-    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None):
+    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False):
         self.keep = (src, dst, weight, bias, head, pool_dst)
         d = N.ConvDesc()
         d.kind = kind
@@ -105,6 +105,7 @@ class ConvOp:
             d.head_b = float(head_b)
             d.head_sigmoid = 1 if head_sigmoid else 0
             d.d_head_out = head_out.data_ptr()
+        d.out_upsample2x = 1 if upsample2x else 0
         if pool_dst is not None:
             d.d_pool_out = pool_dst.ptr
             d.pool_cstride = pool_dst.cstride
@@ -220,3 +221,77 @@ class VGGUNetPlan:
         for op in self.ops:
             op(st)
         return self.out
+
+
+def fold_bn(conv_w, conv_b, bn):
+    """conv -> BatchNorm2d(eval) as one conv: w' = w * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var + eps) + beta."""
+    if bn is None:
+        return conv_w.detach().float(), conv_b.detach().float()
+    gamma, beta, mean, var, eps = bn
+    scale = gamma.detach().float() / torch.sqrt(var.detach().float() + eps)
+    return conv_w.detach().float() * scale.view(-1, 1, 1, 1), (conv_b.detach().float() - mean.detach().float()) * scale + beta.detach().float()
+
+
+class ZFUNetPlan:
+    """ZF_UNET forward (lib/models/zf_unet.py:60-95) in eval mode: BatchNorm folded into the conv weights, Dropout2d
+    off, MaxPool2d fused into the producing conv's epilogue, nn.Upsample(2) fused into the producing conv's store
+    (the tile is TMA-stored to the 2x2 replicated positions of the consumer's concat slab), final 1x1 fused as head.
+
+    blocks: 11 double-conv modules in forward order (conv_224, conv_112, conv_56, conv_28, conv_14, conv_7, up_conv_14,
+    up_conv_28, up_conv_56, up_conv_112, up_conv_224), each ((w1, b1, bn1), (w2, b2, bn2)); final = (w, b).
+    """
+
+    def __init__(self, blocks, final, n, h, w, device, sigmoid):
+        if h % 32 or w % 32:
+            raise ValueError("height and width must be multiples of 32 (five 2x2 poolings)")
+        filters = blocks[0][0][0].shape[0]
+        if final[0].shape[0] != 1 or filters != 32:
+            raise NotImplementedError("fused head expects num_classes == 1 and filters == 32")
+        self.n, self.h, self.w, self.device = n, h, w, device
+        self.ops = []
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
+        enc_c = [blocks[i][1][0].shape[0] for i in range(5)]          # 32, 64, 128, 256, 512
+        up_c = [blocks[5][1][0].shape[0]] + [blocks[6 + i][1][0].shape[0] for i in range(4)]  # channels unpooled into level 4..0
+        # concat slabs per level: [unpool(deeper) | encoder skip]  (torch.cat([self.unpool(..), conv_X], dim=1))
+        slabs = [S(h >> l, w >> l, up_c[4 - l] + enc_c[l]) for l in range(5)]
+        self.slabs = slabs
+
+        def conv(src, dst, layer, first=False, **kw):
+            wt, bs = fold_bn(*layer)
+            if first:
+                self.ops.append(ConvOp(N.CONV_1X1, src, dst, pack_first_conv3x3(wt), bs.contiguous(), **kw))
+            else:
+                self.ops.append(ConvOp(N.CONV_3X3, src, dst, pack_conv3x3(wt), bs.contiguous(), **kw))
+
+        self.x_patch = S(h, w, 32)
+        cur = self.x_patch.view()
+        for l in range(5):                                             # encoder: double conv, skip into the slab, pool
+            hh, ww = h >> l, w >> l
+            l1, l2 = blocks[l]
+            mid = S(hh, ww, enc_c[l]).view()
+            conv(cur, mid, l1, first=(l == 0))
+            pooled = S(hh // 2, ww // 2, enc_c[l]).view()
+            conv(mid, slabs[l].view(up_c[4 - l], enc_c[l]), l2, pool_dst=pooled)
+            cur = pooled
+        for i in range(5):                                             # conv_7, up_conv_14 .. up_conv_112: store upsampled
+            lvl = 5 - i                                                # resolution level of this block
+            hh, ww = h >> lvl, w >> lvl
+            l1, l2 = blocks[5 + i]
+            src = cur if i == 0 else slabs[lvl].view()
+            c_out = l1[0].shape[0]
+            mid = S(hh, ww, c_out).view()
+            conv(src, mid, l1)
+            conv(mid, slabs[lvl - 1].view(0, c_out), l2, upsample2x=True)
+        l1, l2 = blocks[10]                                            # up_conv_224 + conv_final
+        mid = S(h, w, 32).view()
+        conv(slabs[0].view(), mid, l1)
+        self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
+        wt, bs = fold_bn(*l2)
+        head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid,
+                self.out)
+        self.ops.append(ConvOp(N.CONV_3X3, mid, None, pack_conv3x3(wt), bs.contiguous(), head=head))
+        self.flops = sum(op.flops for op in self.ops)
+        self.launches = sum(op.launches for op in self.ops)
+
+    load_nchw = VGGUNetPlan.load_nchw
+    run = VGGUNetPlan.run

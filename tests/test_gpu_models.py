@@ -50,3 +50,52 @@ def test_plan_tracks_weight_updates(cuda):
         m.final.bias.add_(1.0)
         b = m(x)
     assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+def test_zf_unet_against_reference_vectors(cuda, golden_dir):
+    from snb_b200.lib.models import ZF_UNET
+
+    g = np.load(os.path.join(golden_dir, "zf_unet.npz"))
+    m = ZF_UNET()
+    m.load_state_dict(synth.zf_unet_state_dict(seed=4), strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["small_x"]).cuda()).cpu()
+    ref = torch.from_numpy(g["small_logits"])
+    assert y.shape == ref.shape
+    p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    sd = synth.zf_unet_state_dict(seed=4)
+    with torch.no_grad():
+        q = no.zf_unet_forward(sd, torch.from_numpy(g["small_x"]), quant=no.bf16_round, fold=True)
+    assert (y - q).abs().max().item() < 0.02 * max(1.0, q.abs().max().item())
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.from_numpy(g["small_x"]).cuda())
+
+
+def test_config1_zf_unet_loss_and_metrics(cuda, golden_dir, kats):
+    """BASELINE configs[0] on the device: ZF_UNET 8x3x224x224 -> bce_jaccard, JaccardScore, PixelAccuracy."""
+    from snb_b200.lib import losses, metrics
+    from snb_b200.lib.models import ZF_UNET
+
+    g = np.load(os.path.join(golden_dir, "zf_unet.npz"))
+    k = kats["zf_unet_cfg1"]
+    m = ZF_UNET()
+    m.load_state_dict(synth.zf_unet_state_dict(seed=4))
+    m = m.cuda().eval()
+    x = torch.from_numpy(np.random.RandomState(8).standard_normal((8, 3, 224, 224)).astype(np.float32)).cuda()
+    _, targets = synth.logits_targets(8, (8, 1, 224, 224))
+    t = targets.cuda()
+    with torch.no_grad():
+        logits = m(x)
+    ref = torch.from_numpy(g["cfg1_logits_sample"])
+    p_err = (torch.sigmoid(logits[:, :, ::7, ::7].cpu()) - torch.sigmoid(ref)).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    # scalars are smooth functions of the probabilities: bf16 forward noise moves them by ~1e-3 relative
+    assert float(losses.BCEWithLogitsLossAndSmoothJaccard()(logits, t)) == pytest.approx(k["bce_jaccard"], rel=5e-3)
+    assert float(metrics.JaccardScore()(logits, t)) == pytest.approx(k["jaccard_score"], rel=2e-2)
+    assert float(metrics.PixelAccuracy()(logits, t)) == pytest.approx(k["pixel_accuracy"], abs=2e-3)
+    # integer counts are bit-exact GIVEN identical masks: count on the device what torch counts on the same logits
+    c = metrics.confusion_counts(logits, t).tolist()
+    assert c == no.confusion_counts(torch.sigmoid(logits.cpu()), targets).tolist() and sum(c) == targets.numel()

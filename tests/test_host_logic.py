@@ -15,7 +15,7 @@ from oracle import tiles_oracle as to
 from snb_b200 import dist as sdist
 from snb_b200 import engine as E
 from snb_b200.lib import augmentations as aug
-from snb_b200.lib.models import UNet11, UNet16
+from snb_b200.lib.models import UNet11, UNet16, ZF_UNET
 from snb_b200.lib.tiles import ImageSlicer, compute_patch_weight_loss
 
 
@@ -194,3 +194,22 @@ def test_world_size_2_counts_and_masks_equal_single_process(tmp_path):
         masks.append(((p > 0.5) * 255).to(torch.uint8).reshape(24, 20))
     assert got["counts"].tolist() == counts.tolist()
     assert torch.equal(got["masks"], torch.stack(masks))
+
+
+def test_zf_unet_mirror_accepts_reference_state_dict():
+    m = ZF_UNET()
+    sd = synth.zf_unet_state_dict(seed=4)
+    assert len(m.state_dict()) == 156 and sorted(m.state_dict()) == sorted(sd)
+    m.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 31454721 and m.num_classes == 1
+
+
+def test_bn_folding_is_exact_algebra():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 8, 9, 7), generator=g)
+    w, b = torch.randn((5, 8, 3, 3), generator=g), torch.randn(5, generator=g)
+    gamma, beta = torch.rand(5, generator=g) + 0.5, torch.randn(5, generator=g)
+    mean, var = torch.randn(5, generator=g) * 0.1, torch.rand(5, generator=g) + 0.5
+    wf, bf = E.fold_bn(w, b, (gamma, beta, mean, var, 1e-5))
+    want = F.batch_norm(F.conv2d(x, w, b, padding=1), mean, var, gamma, beta, training=False, eps=1e-5)
+    assert torch.allclose(F.conv2d(x, wf, bf, padding=1), want, atol=1e-4)

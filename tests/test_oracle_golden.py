@@ -140,3 +140,23 @@ def test_predict_tiled_pipeline(golden_dir, tta):
     # merge itself is bit-exact when fed the reference's own tiles
     assert np.array_equal(s.merge(list(g[key + "_tiles"]), dtype=np.float32), g[key + "_merged"])
     assert np.array_equal(((g[key + "_merged"] > 0.5) * 255).astype(np.uint8), g[key + "_mask"])
+
+
+def test_zf_unet_logits_and_config1(golden_dir, kats):
+    """BASELINE configs[0]: ZF_UNET forward (eval, randomised BatchNorm buffers) + bce_jaccard + IoU + accuracy."""
+    g = np.load(os.path.join(golden_dir, "zf_unet.npz"))
+    sd = synth.zf_unet_state_dict(seed=4)
+    with torch.no_grad():
+        y = no.zf_unet_forward(sd, torch.from_numpy(g["small_x"])).numpy()
+        y_fold = no.zf_unet_forward(sd, torch.from_numpy(g["small_x"]), fold=True).numpy()
+    assert np.abs(y - g["small_logits"]).max() < 1e-4
+    assert np.abs(y_fold - g["small_logits"]).max() < 1e-3       # folding BatchNorm into the conv is the same function
+    k = kats["zf_unet_cfg1"]
+    x224 = torch.from_numpy(np.random.RandomState(8).standard_normal((8, 3, 224, 224)).astype(np.float32))
+    _, targets = synth.logits_targets(8, (8, 1, 224, 224))
+    with torch.no_grad():
+        logits = no.zf_unet_forward(sd, x224)
+    assert np.abs(logits[:, :, ::7, ::7].numpy() - g["cfg1_logits_sample"]).max() < 2e-4
+    assert float(no.bce_jaccard(logits, targets)) == pytest.approx(k["bce_jaccard"], rel=1e-5)
+    assert float(no.jaccard_score(logits, targets)) == pytest.approx(k["jaccard_score"], rel=1e-4)
+    assert float(no.pixel_accuracy(logits, targets)) == pytest.approx(k["pixel_accuracy"], abs=1e-5)
