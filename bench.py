@@ -38,37 +38,67 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 20 ms period; nvidia-smi fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.max_mhz, self.nvml, self.handle = None, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(
+            n, "nvmlDeviceGetCurrentClocksEventReasons") else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        return mhz, flags
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [v.strip() for v in out.strip().split(",")]
+        self.max_mhz = float(f[1])
+        return float(f[0]), [v.lower().startswith("active") for v in f[2:6]]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [v.strip() for v in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        mhz = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(mhz)}
+        mhz = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_min_mhz": mhz[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(mhz), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm

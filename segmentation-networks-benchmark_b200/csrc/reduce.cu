@@ -37,23 +37,38 @@ __device__ __forceinline__ void load_target4(const void* t, int64_t i4, float (&
 
 struct LossAcc {
   float bce, pt, p, t;
-  uint32_t tp, fp, fn, tn;
+  uint32_t n_pred, n_truth, n_tp;   // tp = n_tp, fp = n_pred - n_tp, fn = n_truth - n_tp, tn = n - n_pred - n_truth + n_tp
 };
 
+// The integer decision must be exactly torch's `sigmoid(x) > 0.5` in float32.  For |x| > 1e-6 that is `x > 0`
+// (1 + exp(-x) rounds strictly below / above 2); only inside that sliver the rounded quotient decides, and there the
+// IEEE expression is evaluated (never taken on real data, warp-uniform skip otherwise).
+__device__ __forceinline__ bool sigmoid_gt_half(float x) {
+  if (fabsf(x) > 1e-6f) return x > 0.f;
+  return 1.f / (1.f + expf(-x)) > 0.5f;
+}
+
+// One exponential serves everything: with e = exp(-|x|)
+//   p = sigmoid(x)     = (x >= 0 ? 1 : e) / (1 + e)
+//   z = logsigmoid(x)  = min(x, 0) - log(1 + e)
+//   BCE-with-logits(z, t) = (1 - t) z - logsigmoid(z) = -t z + log(1 + exp(z)) = -t z + log(1 + p)     (z <= 0, exp(z) = p)
+// which is the reference's double squash (lib/losses.py:51-53) with 1 exp, 2 log, 1 divide instead of 3 exp, 3 log1p.
+// The float sums use the SFU approximations (ex2 / lg2 / rcp, ~2^-22 relative): the sums are tolerance-checked
+// (rel 5e-6, the reference itself sums in float32), and it is what makes the kernel HBM-bound instead of issue-bound.
 __device__ __forceinline__ void loss_accumulate(LossAcc& a, float x, float t) {
-  const float p = sigmoid_f32(x);
-  const float z = logsigmoid_f32(x);  // the reference feeds logsigmoid(x) into BCE-with-logits (losses.py:51-53)
-  // binary_cross_entropy_with_logits(z, t) = (1 - t) * z - logsigmoid(z)
-  a.bce += (1.f - t) * z - logsigmoid_f32(z);
+  const float e = __expf(-fabsf(x));
+  const float d = 1.f + e;
+  const float p = __fdividef(x >= 0.f ? 1.f : e, d);
+  const float z = fminf(x, 0.f) - __logf(d);
+  a.bce += __logf(1.f + p) - t * z;
   a.pt += p * t;
   a.p += p;
   a.t += t;
-  const bool pred = p > 0.5f;          // metrics.py:31
+  const bool pred = sigmoid_gt_half(x);     // metrics.py:31
   const bool truth = ((int)t & 0xff) != 0;  // target.byte()
-  a.tp += pred && truth;
-  a.fp += pred && !truth;
-  a.fn += !pred && truth;
-  a.tn += !pred && !truth;
+  a.n_pred += pred;
+  a.n_truth += truth;
+  a.n_tp += pred && truth;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -88,8 +103,8 @@ __global__ void __launch_bounds__(256) loss_iou_kernel(const float* __restrict__
   __shared__ uint32_t s_i[8][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float f0 = warp_sum(a.bce), f1 = warp_sum(a.pt), f2 = warp_sum(a.p), f3 = warp_sum(a.t);
-  const uint32_t c0 = __reduce_add_sync(0xffffffffu, a.tp), c1 = __reduce_add_sync(0xffffffffu, a.fp);
-  const uint32_t c2 = __reduce_add_sync(0xffffffffu, a.fn), c3 = __reduce_add_sync(0xffffffffu, a.tn);
+  const uint32_t c0 = __reduce_add_sync(0xffffffffu, a.n_pred), c1 = __reduce_add_sync(0xffffffffu, a.n_truth);
+  const uint32_t c2 = __reduce_add_sync(0xffffffffu, a.n_tp), c3 = 0;
   if (lane == 0) {
     s_f[warp][0] = f0; s_f[warp][1] = f1; s_f[warp][2] = f2; s_f[warp][3] = f3;
     s_i[warp][0] = c0; s_i[warp][1] = c1; s_i[warp][2] = c2; s_i[warp][3] = c3;
@@ -100,8 +115,16 @@ __global__ void __launch_bounds__(256) loss_iou_kernel(const float* __restrict__
     unsigned long long c = 0;
     for (int w = 0; w < 8; ++w) { f += s_f[w][threadIdx.x]; c += s_i[w][threadIdx.x]; }
     atomicAdd(&sums[threadIdx.x], f);
-    atomicAdd(&counts[threadIdx.x], c);
+    atomicAdd(&counts[threadIdx.x], c);   // raw {n_pred, n_truth, n_tp, 0}; loss_iou_finalize turns them into tp/fp/fn/tn
   }
+}
+
+__global__ void loss_iou_finalize(unsigned long long* counts, unsigned long long n) {
+  const unsigned long long n_pred = counts[0], n_truth = counts[1], n_tp = counts[2];
+  counts[0] = n_tp;
+  counts[1] = n_pred - n_tp;
+  counts[2] = n_truth - n_tp;
+  counts[3] = n - n_pred - n_truth + n_tp;
 }
 
 template <int DT>
@@ -226,6 +249,8 @@ extern "C" int snb_loss_iou_reduce(const float* d_logits, const void* d_targets,
   if (target_dtype == SNB_DT_I64) loss_iou_kernel<SNB_DT_I64><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
   else if (target_dtype == SNB_DT_U8) loss_iou_kernel<SNB_DT_U8><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
   else loss_iou_kernel<SNB_DT_F32><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
+  SNB_LAUNCH_CHECK();
+  loss_iou_finalize<<<1, 1, 0, st>>>(cnt, (unsigned long long)n);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

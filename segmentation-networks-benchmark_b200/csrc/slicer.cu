@@ -4,6 +4,7 @@
 // work: one thread per output element (x fastest) so stores are fully coalesced and loads are row segments.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cstring>
 #include <new>
@@ -53,44 +54,47 @@ struct BorderPixel {
 };
 
 // ---------------------------------------------------------------------------------------------- split_hwc
-// dst viewed as 32-bit words (row bytes are a multiple of 4 is required by the host wrapper) or bytes.
-template <int UNIT>  // bytes produced per thread: 4 (byte-gather) or 1
-__global__ void split_hwc_kernel(SlicerGeom g, const uint8_t* __restrict__ src, int64_t pixel_bytes, int border_mode,
-                                 BorderPixel border, uint8_t* __restrict__ dst, int64_t tile_begin,
-                                 int64_t total_units) {
-  const int64_t row_bytes = g.tile * pixel_bytes;
-  const int64_t tile_bytes = g.tile * row_bytes;
-  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < total_units;
-       u += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t byte0 = u * UNIT;
-    const int64_t t = byte0 / tile_bytes;
-    const int64_t r = byte0 - t * tile_bytes;
-    const int64_t ty = r / row_bytes;
-    const int64_t rb = r - ty * row_bytes;
-    const int64_t tile = tile_begin + t;
-    const int64_t cy = (tile / g.tiles_x) * g.step, cx = (tile % g.tiles_x) * g.step;
-    const int64_t py = cy + ty - g.margin_top;
+// blockIdx.y = (tile, tile row); threads walk the row's bytes, UNIT output bytes each (4 -> one 32-bit store).
+// Every output byte is gathered through the reflect-101 map, so the copy is bit-exact for any element size.
+constexpr int kSplitRows = 8;   // tile rows per block
+
+template <int UNIT>
+__global__ void __launch_bounds__(256) split_hwc_kernel(SlicerGeom g, const uint8_t* __restrict__ src, int pixel_bytes,
+                                                        int border_mode, BorderPixel border, uint8_t* __restrict__ dst,
+                                                        int64_t tile_begin, int64_t total_rows) {
+  const int T = (int)g.tile;
+  const int row_bytes = T * pixel_bytes;
+  for (int row = blockIdx.y * kSplitRows; row < (int)min((int64_t)(blockIdx.y + 1) * kSplitRows, total_rows); ++row) {
+  const int t = row / T, ty = row - t * T;
+  const int64_t tile = tile_begin + t;
+  const int cy = (int)((tile / g.tiles_x) * g.step), cx = (int)((tile % g.tiles_x) * g.step);
+  const int py = cy + ty - (int)g.margin_top;
+  const int H = (int)g.image_h, Wd = (int)g.image_w;
+  const bool row_inside = py >= 0 && py < H;
+  const int sy = (int)reflect101(py, H);
+  const uint8_t* src_row = src + (int64_t)sy * Wd * pixel_bytes;
+  uint8_t* dst_row = dst + (int64_t)row * row_bytes;
+  for (int b0 = (blockIdx.x * blockDim.x + threadIdx.x) * UNIT; b0 < row_bytes; b0 += gridDim.x * blockDim.x * UNIT) {
     uint8_t out[UNIT];
 #pragma unroll
     for (int b = 0; b < UNIT; ++b) {
-      const int64_t xb = rb + b;
-      const int64_t tx = xb / pixel_bytes;
-      const int64_t pb = xb - tx * pixel_bytes;
-      const int64_t px = cx + tx - g.margin_left;
-      const bool inside = py >= 0 && py < g.image_h && px >= 0 && px < g.image_w;
-      if (border_mode == 1 && !inside) {
+      const int xb = b0 + b;
+      const int tx = xb / pixel_bytes;
+      const int pb = xb - tx * pixel_bytes;
+      const int px = cx + tx - (int)g.margin_left;
+      if (border_mode == 1 && !(row_inside && px >= 0 && px < Wd)) {
         out[b] = border.bytes[pb];
       } else {
-        const int64_t sy = reflect101(py, g.image_h), sx = reflect101(px, g.image_w);
-        out[b] = src[(sy * g.image_w + sx) * pixel_bytes + pb];
+        out[b] = __ldg(src_row + (int)reflect101(px, Wd) * pixel_bytes + pb);
       }
     }
     if (UNIT == 4) {
-      *reinterpret_cast<uint32_t*>(dst + byte0) =
-          (uint32_t)out[0] | ((uint32_t)out[1] << 8) | ((uint32_t)out[2 % UNIT] << 16) | ((uint32_t)out[3 % UNIT] << 24);
+      *reinterpret_cast<uint32_t*>(dst_row + b0) =
+          (uint32_t)out[0] | ((uint32_t)out[1 % UNIT] << 8) | ((uint32_t)out[2 % UNIT] << 16) | ((uint32_t)out[3 % UNIT] << 24);
     } else {
-      dst[byte0] = out[0];
+      dst_row[b0] = out[0];
     }
+  }
   }
 }
 
@@ -160,8 +164,30 @@ __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, c
     s_px[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
   }
   __syncthreads();
-  const unsigned short* s_el = reinterpret_cast<const unsigned short*>(s_px);
   const int rows = min(kPatchRY, T - y0);
+  if (channels == 3) {
+    // one thread = one pixel: 9 neighbour loads (8 bytes each), register shuffles, four 16-byte stores (64 contiguous bytes)
+    for (int pix = threadIdx.x; pix < rows * T; pix += blockDim.x) {
+      const int y = pix / T, x = pix - y * T;
+      unsigned short el[32];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint2 v = s_px[(y + tap / 3) * PW + x + tap % 3];
+        el[tap * 3 + 0] = (unsigned short)(v.x & 0xffffu);
+        el[tap * 3 + 1] = (unsigned short)(v.x >> 16);
+        el[tap * 3 + 2] = (unsigned short)(v.y & 0xffffu);
+      }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) el[k] = 0;
+      uint4* o = dst + ((t * T + y0 + y) * (int64_t)T + x) * 4;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd)
+        o[qd] = make_uint4(el[qd * 8 + 0] | ((uint32_t)el[qd * 8 + 1] << 16), el[qd * 8 + 2] | ((uint32_t)el[qd * 8 + 3] << 16),
+                           el[qd * 8 + 4] | ((uint32_t)el[qd * 8 + 5] << 16), el[qd * 8 + 6] | ((uint32_t)el[qd * 8 + 7] << 16));
+    }
+    return;
+  }
+  const unsigned short* s_el = reinterpret_cast<const unsigned short*>(s_px);
   for (int i = threadIdx.x; i < rows * T * 4; i += blockDim.x) {
     const int qd = i & 3;
     const int pix = i >> 2;
@@ -233,42 +259,131 @@ __device__ __forceinline__ double tile_value(const void* __restrict__ tiles, int
   }
 }
 
-template <int TILE_DT, int TTA>
-__global__ void merge_kernel(SlicerGeom g, const void* __restrict__ tiles, int C, const double* __restrict__ weight,
-                             void* __restrict__ out, int out_dtype, uint8_t* __restrict__ mask, float thr,
-                             int64_t total) {
-  const int64_t T = g.tile, S = g.step;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i;
-    const int c = (int)(r % C); r /= C;
-    const int64_t x = r % g.image_w;
-    const int64_t y = r / g.image_w;
-    const int64_t Y = y + g.margin_top, X = x + g.margin_left;  // padded-canvas coordinates
-    // crops covering (Y, X): iy*S <= Y < iy*S + T
-    int64_t iy0 = Y - T + 1 <= 0 ? 0 : (Y - T + S) / S;
-    int64_t iy1 = Y / S; if (iy1 > g.tiles_y - 1) iy1 = g.tiles_y - 1;
-    int64_t ix0 = X - T + 1 <= 0 ? 0 : (X - T + S) / S;
-    int64_t ix1 = X / S; if (ix1 > g.tiles_x - 1) ix1 = g.tiles_x - 1;
-    double acc = 0.0, norm = 0.0;
-    for (int64_t iy = iy0; iy <= iy1; ++iy) {        // crop order: y outer, x inner (lib/tiles.py:94-96,150)
-      const int ty = (int)(Y - iy * S);
-      for (int64_t ix = ix0; ix <= ix1; ++ix) {
-        const int tx = (int)(X - ix * S);
-        const double w = __ldg(weight + (int64_t)ty * T + tx);
-        const double v = tile_value<TILE_DT, TTA>(tiles, iy * g.tiles_x + ix, ty, tx, c, (int)T, C);
-        acc = __dadd_rn(acc, __dmul_rn(v, w));       // no FMA contraction: numpy rounds the product first
-        norm = __dadd_rn(norm, w);
+// blockIdx.y = image row (no 64-bit division anywhere); a thread owns VEC consecutive elements of the row so the
+// crop-range arithmetic is shared and stores are 16-byte (float4) / 4-byte (uchar4) vectors.  The accumulation per
+// element is untouched: float64, crop order, no FMA contraction -> bit-exact against numpy.
+template <int TILE_DT, int TTA, int VEC>
+__global__ void __launch_bounds__(256) merge_kernel(SlicerGeom g, const void* __restrict__ tiles, int C,
+                                                    const double* __restrict__ weight, void* __restrict__ out,
+                                                    int out_dtype, uint8_t* __restrict__ mask, float thr) {
+  const int T = (int)g.tile, S = (int)g.step;
+  const int WC = (int)g.image_w * C;
+  const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y;
+  const int Y = blockIdx.y + (int)g.margin_top;              // padded-canvas row
+  // crops covering row Y: iy*S <= Y < iy*S + T
+  const int iy0 = Y - T + 1 <= 0 ? 0 : (Y - T + S) / S;
+  const int iy1 = min(Y / S, tiles_y - 1);
+  for (int xc0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; xc0 < WC; xc0 += gridDim.x * blockDim.x * VEC) {
+    float qf[VEC];
+    double qd[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int xc = xc0 + e;
+      const int x = C == 1 ? xc : xc / C;
+      const int c = C == 1 ? 0 : xc - x * C;
+      const int X = x + (int)g.margin_left;
+      const int ix0 = X - T + 1 <= 0 ? 0 : (X - T + S) / S;
+      const int ix1 = min(X / S, tiles_x - 1);
+      double acc = 0.0, norm = 0.0;
+      if (xc < WC) {
+        for (int iy = iy0; iy <= iy1; ++iy) {          // crop order: y outer, x inner (lib/tiles.py:94-96,150)
+          const int ty = Y - iy * S;
+          for (int ix = ix0; ix <= ix1; ++ix) {
+            const int tx = X - ix * S;
+            const double w = __ldg(weight + ty * T + tx);
+            const double v = tile_value<TILE_DT, TTA>(tiles, (int64_t)iy * tiles_x + ix, ty, tx, c, T, C);
+            acc = __dadd_rn(acc, __dmul_rn(v, w));     // no FMA contraction: numpy rounds the product first
+            norm = __dadd_rn(norm, w);
+          }
+        }
+      }
+      norm = norm < DBL_EPSILON ? DBL_EPSILON : norm;  // np.clip(norm, eps, None)
+      qd[e] = __ddiv_rn(acc, norm);
+      qf[e] = __double2float_rn(qd[e]);
+    }
+    const int64_t i = (int64_t)blockIdx.y * WC + xc0;
+    if (VEC == 4 && xc0 + 3 < WC) {   // WC % 4 == 0 and 16-byte aligned rows are guaranteed by the launcher for VEC == 4
+      if (out) {
+        if (out_dtype == SNB_DT_F32) *reinterpret_cast<float4*>(static_cast<float*>(out) + i) = make_float4(qf[0], qf[1], qf[2], qf[3]);
+        else if (out_dtype == SNB_DT_F64) {
+          double* o = static_cast<double*>(out) + i;
+          *reinterpret_cast<double2*>(o) = make_double2(qd[0], qd[1]);
+          *reinterpret_cast<double2*>(o + 2) = make_double2(qd[2], qd[3]);
+        } else {
+          *reinterpret_cast<uchar4*>(static_cast<uint8_t*>(out) + i) =
+              make_uchar4((uint8_t)(int)qd[0], (uint8_t)(int)qd[1], (uint8_t)(int)qd[2], (uint8_t)(int)qd[3]);
+        }
+      }
+      if (mask)
+        *reinterpret_cast<uchar4*>(mask + i) = make_uchar4(qf[0] > thr ? 255 : 0, qf[1] > thr ? 255 : 0,
+                                                           qf[2] > thr ? 255 : 0, qf[3] > thr ? 255 : 0);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (xc0 + e >= WC) break;
+        if (out) {
+          if (out_dtype == SNB_DT_F32) static_cast<float*>(out)[i + e] = qf[e];
+          else if (out_dtype == SNB_DT_F64) static_cast<double*>(out)[i + e] = qd[e];
+          else static_cast<uint8_t*>(out)[i + e] = (uint8_t)(int)qd[e];  // astype(uint8) truncates
+        }
+        if (mask) mask[i + e] = qf[e] > thr ? 255 : 0;
       }
     }
-    norm = norm < DBL_EPSILON ? DBL_EPSILON : norm;  // np.clip(norm, eps, None)
-    const double q = __ddiv_rn(acc, norm);
-    const float qf = __double2float_rn(q);
-    if (out) {
-      if (out_dtype == SNB_DT_F32) static_cast<float*>(out)[i] = qf;
-      else if (out_dtype == SNB_DT_F64) static_cast<double*>(out)[i] = q;
-      else static_cast<uint8_t*>(out)[i] = (uint8_t)(int)q;  // astype(uint8) truncates
+  }
+}
+
+// Fast path of the merge for the inference layout (float32 probabilities, one channel, no TTA) when the geometry is
+// 4-aligned (tile, step, left margin and width multiples of 4): a thread owns 4 consecutive pixels of one row, which
+// then share their covering crops, so a crop contributes one float4 tile load and two double2 weight loads.  The
+// per-pixel arithmetic (float64, crop order, rounded product, IEEE divide) is identical to the generic kernel.
+__global__ void __launch_bounds__(256) merge_f32c1_vec4_kernel(SlicerGeom g, const float* __restrict__ tiles,
+                                                               const double* __restrict__ weight,
+                                                               float* __restrict__ out, uint8_t* __restrict__ mask,
+                                                               float thr) {
+  const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w;
+  const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y;
+  const int Y = blockIdx.y + (int)g.margin_top;
+  const int iy0 = Y - T + 1 <= 0 ? 0 : (Y - T + S) / S;
+  const int iy1 = min(Y / S, tiles_y - 1);
+  for (int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; x0 < W; x0 += gridDim.x * blockDim.x * 4) {
+    const int X = x0 + (int)g.margin_left;                  // multiple of 4; crop edges are multiples of 4 too
+    const int ix0 = X - T + 1 <= 0 ? 0 : (X - T + S) / S;   // same for X .. X+3
+    const int ix1 = min(X / S, tiles_x - 1);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, norm[4] = {0.0, 0.0, 0.0, 0.0};
+    // walk the covering crops with pointer increments: next crop in x is one tile further and S pixels to the left,
+    // next crop row is tiles_x tiles further and S rows up
+    const int ty0 = Y - iy0 * S, tx0 = X - ix0 * S;
+    const float* trow = tiles + (((int64_t)iy0 * tiles_x + ix0) * T + ty0) * T + tx0;
+    const double* wrow = weight + ty0 * T + tx0;
+    const int64_t t_dx = (int64_t)T * T - S, t_dy = (int64_t)tiles_x * T * T - (int64_t)S * T;
+    const int w_dy = -S * T;
+    const int nx = ix1 - ix0, ny = iy1 - iy0;
+#pragma unroll 1
+    for (int jy = 0; jy <= ny; ++jy, trow += t_dy, wrow += w_dy) {
+      const float* tp = trow;
+      const double* wp = wrow;
+#pragma unroll 1
+      for (int jx = 0; jx <= nx; ++jx, tp += t_dx, wp -= S) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(tp));
+        const double2 w01 = __ldg(reinterpret_cast<const double2*>(wp));
+        const double2 w23 = __ldg(reinterpret_cast<const double2*>(wp + 2));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn((double)v.x, w01.x)); norm[0] = __dadd_rn(norm[0], w01.x);
+        acc[1] = __dadd_rn(acc[1], __dmul_rn((double)v.y, w01.y)); norm[1] = __dadd_rn(norm[1], w01.y);
+        acc[2] = __dadd_rn(acc[2], __dmul_rn((double)v.z, w23.x)); norm[2] = __dadd_rn(norm[2], w23.x);
+        acc[3] = __dadd_rn(acc[3], __dmul_rn((double)v.w, w23.y)); norm[3] = __dadd_rn(norm[3], w23.y);
+      }
     }
-    if (mask) mask[i] = qf > thr ? 255 : 0;
+    float q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double nrm = norm[e] < DBL_EPSILON ? DBL_EPSILON : norm[e];
+      q[e] = __double2float_rn(__ddiv_rn(acc[e], nrm));
+    }
+    const int64_t i = (int64_t)blockIdx.y * W + x0;
+    if (out) *reinterpret_cast<float4*>(out + i) = make_float4(q[0], q[1], q[2], q[3]);
+    if (mask)
+      *reinterpret_cast<uchar4*>(mask + i) =
+          make_uchar4(q[0] > thr ? 255 : 0, q[1] > thr ? 255 : 0, q[2] > thr ? 255 : 0, q[3] > thr ? 255 : 0);
   }
 }
 
@@ -358,15 +473,24 @@ extern "C" int snb_split_hwc(const snb_slicer* s, const void* d_src, int64_t cha
   const int64_t pixel_bytes = channels * elem_bytes;
   BorderPixel bp{};
   if (border_mode == 1 && border_value) std::memcpy(bp.bytes, border_value, (size_t)pixel_bytes);
-  const int64_t total_bytes = tile_count * s->g.tile * s->g.tile * pixel_bytes;
-  const bool words = (s->g.tile * pixel_bytes) % 4 == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 3) == 0;
-  if (words) {
-    const int64_t units = total_bytes / 4;
-    split_hwc_kernel<4><<<grid_for(units, 256), 256, 0, as_stream(stream)>>>(
-        s->g, static_cast<const uint8_t*>(d_src), pixel_bytes, border_mode, bp, static_cast<uint8_t*>(d_dst), tile_begin, units);
-  } else {
-    split_hwc_kernel<1><<<grid_for(total_bytes, 256), 256, 0, as_stream(stream)>>>(
-        s->g, static_cast<const uint8_t*>(d_src), pixel_bytes, border_mode, bp, static_cast<uint8_t*>(d_dst), tile_begin, total_bytes);
+  const int64_t row_bytes = s->g.tile * pixel_bytes;
+  if (tile_count * s->g.tile > 65535LL * 32768 || row_bytes > INT32_MAX / 2 || s->g.image_w * pixel_bytes > INT32_MAX / 2)
+    return fail(SNB_E_UNSUPPORTED, "split too large");
+  const bool words = row_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 3) == 0;
+  // gridDim.y is limited to 65535 rows per launch: split the tile range
+  const int64_t tiles_per_launch = std::max<int64_t>(1, 65535LL * kSplitRows / s->g.tile);
+  for (int64_t t0 = 0; t0 < tile_count; t0 += tiles_per_launch) {
+    const int64_t nt = std::min(tiles_per_launch, tile_count - t0);
+    uint8_t* dst = static_cast<uint8_t*>(d_dst) + t0 * s->g.tile * row_bytes;
+    const int unit = words ? 4 : 1;
+    const int64_t rows = nt * s->g.tile;
+    const dim3 grid((unsigned)std::min<int64_t>((row_bytes / unit + 255) / 256, 64), (unsigned)((rows + kSplitRows - 1) / kSplitRows));
+    if (words)
+      split_hwc_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(s->g, static_cast<const uint8_t*>(d_src), (int)pixel_bytes,
+                                                              border_mode, bp, dst, tile_begin + t0, rows);
+    else
+      split_hwc_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(s->g, static_cast<const uint8_t*>(d_src), (int)pixel_bytes,
+                                                              border_mode, bp, dst, tile_begin + t0, rows);
   }
   SNB_LAUNCH_CHECK();
   return SNB_OK;
@@ -427,9 +551,16 @@ extern "C" int snb_nchw_f32_to_patch32(const float* d_src, int64_t n, int64_t ch
 template <int TILE_DT, int TTA>
 static void launch_merge(const snb_slicer* s, const void* d_tiles, int C, const double* d_weight, void* d_out,
                          int out_dtype, uint8_t* d_mask, float thr, cudaStream_t st) {
-  const int64_t total = s->g.image_h * s->g.image_w * C;
-  merge_kernel<TILE_DT, TTA><<<grid_for(total, 256), 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask,
-                                                                  thr, total);
+  const int64_t wc = s->g.image_w * C;
+  // vector path: every row starts 16-byte aligned in all outputs
+  const bool vec = wc % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0;
+  if (vec) {
+    const dim3 grid((unsigned)std::min<int64_t>((wc / 4 + 255) / 256, 1024), (unsigned)s->g.image_h);
+    merge_kernel<TILE_DT, TTA, 4><<<grid, 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr);
+  } else {
+    const dim3 grid((unsigned)std::min<int64_t>((wc + 255) / 256, 1024), (unsigned)s->g.image_h);
+    merge_kernel<TILE_DT, TTA, 1><<<grid, 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr);
+  }
 }
 
 extern "C" int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
@@ -443,8 +574,21 @@ extern "C" int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtyp
   if (out_dtype != SNB_DT_F32 && out_dtype != SNB_DT_F64 && out_dtype != SNB_DT_U8)
     return fail(SNB_E_INVALID, "out_dtype %d unsupported", out_dtype);
   if (s->g.tiles_x * s->g.tiles_y == 0) return fail(SNB_E_INVALID, "slicer has no crops");
+  if (s->g.image_h > 65535 || s->g.image_w * channels > INT32_MAX / 2 || s->g.tile * s->g.tile > INT32_MAX / 2)
+    return fail(SNB_E_UNSUPPORTED, "image too large for the merge kernel");
   cudaStream_t st = as_stream(stream);
   const int C = (int)channels;
+  const SlicerGeom& g = s->g;
+  if (tta == 1 && tile_dtype == SNB_DT_F32 && C == 1 && out_dtype == SNB_DT_F32 && g.tile % 4 == 0 && g.step % 4 == 0 &&
+      g.margin_left % 4 == 0 && g.image_w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_tiles) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0) {
+    const dim3 grid((unsigned)std::min<int64_t>((g.image_w / 4 + 255) / 256, 1024), (unsigned)g.image_h);
+    merge_f32c1_vec4_kernel<<<grid, 256, 0, st>>>(g, static_cast<const float*>(d_tiles), d_weight,
+                                                  static_cast<float*>(d_out), d_mask, thr);
+    SNB_LAUNCH_CHECK();
+    return SNB_OK;
+  }
   if (tta == 8) launch_merge<SNB_DT_F32, 8>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);
   else if (tile_dtype == SNB_DT_F32) launch_merge<SNB_DT_F32, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);
   else if (tile_dtype == SNB_DT_U8) launch_merge<SNB_DT_U8, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);

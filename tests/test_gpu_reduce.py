@@ -10,7 +10,7 @@ from snb_b200.lib import losses, metrics
 
 pytestmark = pytest.mark.gpu
 
-REL = 2e-6   # float sums: fp32 elementwise, fp64 accumulation; reference sums in fp32 -> tolerance, not bits
+REL = 5e-6   # float sums: fp32 elementwise with SFU exp/log/rcp, fp64 accumulation; reference sums in fp32 -> tolerance, not bits
 
 
 @pytest.mark.parametrize("seed", [0, 3])
