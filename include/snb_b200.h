@@ -108,6 +108,8 @@ SNB_API int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, 
 #define SNB_CONV_3X3 0      /* k3 s1 p1: 1 phase x 9 taps, tap = ky*3+kx                     */
 #define SNB_CONV_1X1 1      /* k1: 1 phase x 1 tap                                           */
 #define SNB_CONVT_4X4_S2 2  /* ConvTranspose2d k4 s2 p1: 4 sub-pixel phases x 4 taps         */
+#define SNB_CONVT_3X3_S2 3  /* ConvTranspose2d k3 s2 p0 cropped to [0,2h) x [0,2w) (lib/models/tiramisu.py:62-90):
+                               4 phases x 4 tap slots, unused slots carry zero weights       */
 
 typedef struct snb_conv_desc {
   int32_t kind;          /* SNB_CONV_*                                                      */
@@ -146,6 +148,13 @@ SNB_API double snb_conv_flops(const snb_conv* c);
 /* nn.MaxPool2d(2,2) on NHWC bf16 slabs; h, w even; channels multiple of 8 */
 SNB_API int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                    void* d_out, int64_t out_cstride, void* stream);
+
+/* Pre-activation BatchNorm2d(eval) + ReLU of FCDenseNet's DenseLayer / TransitionDown (lib/models/tiramisu.py:12-13,
+ * 50-51): out[.., c] = max(in[.., c] * scale[c] + shift[c], 0) for c < channels, 0 for channels <= c < channels_pad
+ * (scale = gamma / sqrt(var + eps), shift = beta - mean * scale, float).  NHWC bf16 slabs, channels % 8 == 0. */
+SNB_API int snb_bn_relu_nhwc(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                     const float* d_scale, const float* d_shift, void* d_out, int64_t channels_pad,
+                     int64_t out_cstride, void* stream);
 
 /* bf16 NHWC slab -> float NCHW (leaving the network through the nn.Module interface) */
 SNB_API int snb_nhwc_bf16_to_nchw_f32(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels,

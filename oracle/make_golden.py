@@ -36,6 +36,7 @@ from lib.datasets.Inria import INRIA_MEAN, INRIA_STD  # noqa: E402
 from lib.models.unet11 import UNet11  # noqa: E402
 from lib.models.unet16 import UNet16  # noqa: E402
 from lib.models.zf_unet import ZF_UNET  # noqa: E402
+from lib.models.tiramisu import FCDenseNet67  # noqa: E402
 from lib.tiles import ImageSlicer, compute_patch_weight_loss  # noqa: E402
 from lib.train_utils import PRCurveMeter  # noqa: E402
 
@@ -194,6 +195,21 @@ def zf_unet_vectors():
                 logit_min=float(logits.min()), logit_max=float(logits.max()))
 
 
+def fcdensenet_vectors():
+    """BASELINE configs[4] model: FCDenseNet67(n_classes=1) in eval mode with randomised BatchNorm buffers."""
+    m = FCDenseNet67(n_classes=1)
+    sd = synth.fcdensenet_state_dict(seed=5)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys and len(m.state_dict()) == 434
+    m.eval()
+    x = torch.from_numpy(np.random.RandomState(12).standard_normal((2, 3, 64, 96)).astype(np.float32))
+    x224 = torch.from_numpy(np.random.RandomState(13).standard_normal((1, 3, 224, 224)).astype(np.float32))
+    with torch.no_grad():
+        y, y224 = m(x).numpy(), m(x224).numpy()
+    np.savez_compressed(os.path.join(OUT, "fcdensenet67.npz"), x=x.numpy(), logits=y, logits224=y224)
+    return dict(params=int(sum(p.numel() for p in m.parameters())), logit_min=float(y.min()), logit_max=float(y.max()))
+
+
 def predict_tiled_vector():
     """inria_submit.predict_tiled (:237-257) on CPU: same calls, without .cuda(); tile 64 / step 32, with and
     without D4 TTA, plus the submit threshold (:305)."""
@@ -230,7 +246,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(),
+    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(), fcdensenet67=fcdensenet_vectors(),
                 torch_version=torch.__version__, numpy_version=np.__version__)
     split_merge_vectors()
     normalize_vectors()

@@ -82,6 +82,47 @@ def zf_unet_forward(sd, x, quant=None, fold=False):
     return F.conv2d(x, sd['conv_final.weight'], sd['conv_final.bias'])
 
 
+def _bn_relu_conv(x, sd, prefix, quant=None, padding=1):
+    """DenseLayer / TransitionDown front: BatchNorm2d(eval) -> ReLU -> conv (lib/models/tiramisu.py:9-19,47-59)."""
+    y = F.relu(F.batch_norm(x, sd[prefix + '.norm.running_mean'], sd[prefix + '.norm.running_var'],
+                            sd[prefix + '.norm.weight'], sd[prefix + '.norm.bias'], training=False, eps=1e-5))
+    w, b = sd[prefix + '.conv.weight'], sd[prefix + '.conv.bias']
+    if quant is not None:
+        y, w = quant(y), quant(w)
+    return F.conv2d(y, w, b, padding=padding)
+
+
+def fcdensenet_forward(sd, x, down_blocks=(5, 5, 5, 5, 5), up_blocks=(5, 5, 5, 5, 5), bottleneck_layers=5, quant=None):
+    """FCDenseNet.forward in eval mode (lib/models/tiramisu.py:168-184); returns the finalConv logits (the reference
+    defines a LogSoftmax but never applies it).  `quant` models bf16 storage of every activation the device keeps."""
+    q = quant if quant is not None else (lambda t: t)
+
+    def dense_block(t, prefix, n_layers, upsample):
+        new = []
+        for k in range(n_layers):
+            out = q(_bn_relu_conv(t, sd, '%s.layers.%d' % (prefix, k), quant))
+            t = torch.cat([t, out], 1)
+            new.append(out)
+        return torch.cat(new, 1) if upsample else t
+
+    w, b = sd['firstconv.weight'], sd['firstconv.bias']
+    out = q(F.conv2d(q(x), q(w), b, padding=1))
+    skips = []
+    for i, n_layers in enumerate(down_blocks):
+        out = dense_block(out, 'denseBlocksDown.%d' % i, n_layers, False)
+        skips.append(out)
+        out = F.max_pool2d(q(_bn_relu_conv(out, sd, 'transDownBlocks.%d' % i, quant, padding=0)), 2)
+    out = dense_block(out, 'bottleneck.bottleneck', bottleneck_layers, True)
+    for i, n_layers in enumerate(up_blocks):
+        skip = skips.pop()
+        w, b = sd['transUpBlocks.%d.convTrans.weight' % i], sd['transUpBlocks.%d.convTrans.bias' % i]
+        up = q(F.conv_transpose2d(q(out), q(w), b, stride=2))
+        oy, ox = (up.shape[2] - skip.shape[2]) // 2, (up.shape[3] - skip.shape[3]) // 2
+        up = up[:, :, oy:oy + skip.shape[2], ox:ox + skip.shape[3]]
+        out = dense_block(torch.cat([up, skip], 1), 'denseBlocksUp.%d' % i, n_layers, i < len(up_blocks) - 1)
+    return F.conv2d(q(out), q(sd['finalConv.weight']), sd['finalConv.bias'])
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 

@@ -84,6 +84,51 @@ def zf_unet_state_dict(seed=0, filters=32):
     return sd
 
 
+def fcdensenet_state_dict(seed=0, down_blocks=(5, 5, 5, 5, 5), up_blocks=(5, 5, 5, 5, 5), bottleneck_layers=5, growth=16,
+                          first=48, n_classes=1):
+    """Random FCDenseNet state_dict with the reference key names (434 entries for FCDenseNet67) and randomised BatchNorm
+    buffers."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+
+    def bn(prefix, c):
+        sd[prefix + '.weight'] = torch.from_numpy(rs.uniform(0.5, 1.5, c).astype(np.float32))
+        sd[prefix + '.bias'] = torch.from_numpy((rs.standard_normal(c) * 0.1).astype(np.float32))
+        sd[prefix + '.running_mean'] = torch.from_numpy((rs.standard_normal(c) * 0.1).astype(np.float32))
+        sd[prefix + '.running_var'] = torch.from_numpy(rs.uniform(0.5, 1.5, c).astype(np.float32))
+        sd[prefix + '.num_batches_tracked'] = torch.tensor(3, dtype=torch.int64)
+
+    def dense_block(prefix, cin, n_layers):
+        for k in range(n_layers):
+            c = cin + k * growth
+            bn('%s.layers.%d.norm' % (prefix, k), c)
+            sd['%s.layers.%d.conv.weight' % (prefix, k)] = _he(rs, (growth, c, 3, 3), c * 9)
+            sd['%s.layers.%d.conv.bias' % (prefix, k)] = _bias(rs, growth)
+
+    sd['firstconv.weight'] = _he(rs, (first, 3, 3, 3), 27)
+    sd['firstconv.bias'] = _bias(rs, first)
+    cur, skips = first, []
+    for i, n_layers in enumerate(down_blocks):
+        dense_block('denseBlocksDown.%d' % i, cur, n_layers)
+        cur += growth * n_layers
+        skips.insert(0, cur)
+        bn('transDownBlocks.%d.norm' % i, cur)
+        sd['transDownBlocks.%d.conv.weight' % i] = _he(rs, (cur, cur, 1, 1), cur)
+        sd['transDownBlocks.%d.conv.bias' % i] = _bias(rs, cur)
+    dense_block('bottleneck.bottleneck', cur, bottleneck_layers)
+    prev = growth * bottleneck_layers
+    for i, n_layers in enumerate(up_blocks):
+        sd['transUpBlocks.%d.convTrans.weight' % i] = _he(rs, (prev, prev, 3, 3), prev * 2.25)
+        sd['transUpBlocks.%d.convTrans.bias' % i] = _bias(rs, prev)
+        cur = prev + skips[i]
+        dense_block('denseBlocksUp.%d' % i, cur, n_layers)
+        prev = growth * n_layers
+        cur += prev
+    sd['finalConv.weight'] = _he(rs, (n_classes, cur, 1, 1), cur, gain=0.1)   # logits ~N(0,1) over the 288-wide concat
+    sd['finalConv.bias'] = _bias(rs, n_classes)
+    return sd
+
+
 def image_u8(seed, h, w, c=3, smooth=True):
     """Inria-shaped synthetic uint8 image; low-pass structure so masks are not pure noise."""
     rs = np.random.RandomState(seed)

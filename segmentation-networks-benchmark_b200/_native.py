@@ -20,7 +20,7 @@ SNB_E_UNSUPPORTED = -4
 
 DT_U8, DT_F32, DT_F64, DT_I64 = 0, 1, 2, 3
 LAYOUT_NCHW_F32, LAYOUT_PATCH32 = 0, 1
-CONV_3X3, CONV_1X1, CONVT_4X4_S2 = 0, 1, 2
+CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2 = 0, 1, 2, 3
 
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
@@ -73,6 +73,7 @@ SIGNATURES = {
     "snb_conv_destroy": (None, [c_vp]),
     "snb_conv_flops": (ctypes.c_double, [c_vp]),
     "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
     "snb_confusion_counts": (c_int, [c_vp, c_vp, c_int, c_i64, ctypes.c_float, c_vp, c_vp]),

@@ -45,6 +45,31 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int H,
   }
 }
 
+// one thread = 8 channels of one pixel (16-byte vector in, 16-byte vector out)
+__global__ void bn_relu_kernel(const uint4* __restrict__ in, int CV, int CPV, int in_sv, const float* __restrict__ scale,
+                               const float* __restrict__ shift, uint4* __restrict__ out, int out_sv, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CPV);
+    const int64_t pix = i / CPV;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (cv < CV) {
+      const uint4 v = __ldg(in + pix * in_sv + cv);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * cv), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * cv + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cv), b1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cv + 1);
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const float2 x0 = __bfloat1622float2(pv[0]), x1 = __bfloat1622float2(pv[1]);
+      const float2 x2 = __bfloat1622float2(pv[2]), x3 = __bfloat1622float2(pv[3]);
+      __nv_bfloat162 o[4];
+      o[0] = __floats2bfloat162_rn(fmaxf(fmaf(x0.x, s0.x, b0.x), 0.f), fmaxf(fmaf(x0.y, s0.y, b0.y), 0.f));
+      o[1] = __floats2bfloat162_rn(fmaxf(fmaf(x1.x, s0.z, b0.z), 0.f), fmaxf(fmaf(x1.y, s0.w, b0.w), 0.f));
+      o[2] = __floats2bfloat162_rn(fmaxf(fmaf(x2.x, s1.x, b1.x), 0.f), fmaxf(fmaf(x2.y, s1.y, b1.y), 0.f));
+      o[3] = __floats2bfloat162_rn(fmaxf(fmaf(x3.x, s1.z, b1.z), 0.f), fmaxf(fmaf(x3.y, s1.w, b1.w), 0.f));
+      r = *reinterpret_cast<uint4*>(o);
+    }
+    out[pix * out_sv + cv] = r;
+  }
+}
+
 static int aux_grid(int64_t total) {
   const int64_t need = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -67,6 +92,25 @@ extern "C" int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w,
   maxpool2x2_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
                                                                      (int)(channels / 8), (int)(in_cstride / 8),
                                                                      static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_bn_relu_nhwc(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                                const float* d_scale, const float* d_shift, void* d_out, int64_t channels_pad,
+                                int64_t out_cstride, void* stream) {
+  if (!d_in || !d_scale || !d_shift || !d_out) return fail(SNB_E_INVALID, "snb_bn_relu_nhwc: null argument");
+  if (n <= 0 || h <= 0 || w <= 0) return fail(SNB_E_INVALID, "bad shape");
+  if (channels <= 0 || channels % 8 || channels_pad < channels || channels_pad % 8 || in_cstride % 8 || out_cstride % 8 ||
+      in_cstride < channels || out_cstride < channels_pad)
+    return fail(SNB_E_INVALID, "channel counts and strides must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_scale) & 15) || (reinterpret_cast<uintptr_t>(d_shift) & 15))
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
+  const int64_t total = n * h * w * (channels_pad / 8);
+  bn_relu_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)(channels / 8),
+                                                                  (int)(channels_pad / 8), (int)(in_cstride / 8), d_scale,
+                                                                  d_shift, static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

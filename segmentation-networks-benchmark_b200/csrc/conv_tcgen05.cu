@@ -742,19 +742,20 @@ using namespace snb;
 extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (!d || !out) return fail(SNB_E_INVALID, "snb_conv_create: null argument");
   *out = nullptr;
-  if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_4X4_S2) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
+  if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_3X3_S2) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
+  const bool is_convt = d->kind == SNB_CONVT_4X4_S2 || d->kind == SNB_CONVT_3X3_S2;
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
   if (d->cin <= 0 || d->cin % 32 != 0) return fail(SNB_E_INVALID, "cin=%lld must be a positive multiple of 32", (long long)d->cin);
   if (d->cout <= 0 || d->cout % 32 != 0) return fail(SNB_E_INVALID, "cout=%lld must be a positive multiple of 32", (long long)d->cout);
   if (d->in_cstride < d->cin || d->in_cstride % 8 != 0) return fail(SNB_E_INVALID, "bad in_cstride");
   const bool head = d->d_head_w != nullptr;
-  if (head && (d->cout != 32 || d->kind == SNB_CONVT_4X4_S2 || !d->d_head_out))
+  if (head && (d->cout != 32 || is_convt || !d->d_head_out))
     return fail(SNB_E_INVALID, "fused head needs cout == 32, a plain conv and an output pointer");
   if (!head && (!d->d_out || d->out_cstride < d->cout || d->out_cstride % 8 != 0))
     return fail(SNB_E_INVALID, "bad output slab");
   if (!d->d_in || !d->d_weight || !d->d_bias) return fail(SNB_E_INVALID, "null tensor pointer");
   const bool up2x = d->out_upsample2x != 0;
-  if (up2x && (head || d->kind == SNB_CONVT_4X4_S2))
+  if (up2x && (head || is_convt))
     return fail(SNB_E_INVALID, "out_upsample2x applies to conv3x3 / conv1x1 without a fused head");
   const bool pool = d->d_pool_out != nullptr;
   if (pool && (head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
@@ -774,7 +775,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   else if (d->cout % 64 == 0) bn = 64;
   if (mode >= 3 && bn == 256) {
     // wave quantisation: with few tiles (deep, low-resolution layers) a 128-wide N tile fills the last wave better
-    const int64_t m_tiles = (int64_t)(d->kind == SNB_CONVT_4X4_S2 ? 4 : 1) * d->n * ((d->h + 15) / 16) * ((d->w + 7) / 8);
+    const int64_t m_tiles = (int64_t)(is_convt ? 4 : 1) * d->n * ((d->h + 15) / 16) * ((d->w + 7) / 8);
     const double e256 = wave_efficiency(m_tiles * (d->cout / 256), sms);
     const double e128 = wave_efficiency(m_tiles * (d->cout / 128), sms);
     if (e256 < 0.85 && e128 > e256 + 0.05) bn = 128;
@@ -789,7 +790,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   std::memset(&p, 0, sizeof(p));
   c->kernel = kc;
 
-  p.n_phases = d->kind == SNB_CONVT_4X4_S2 ? 4 : 1;
+  p.n_phases = is_convt ? 4 : 1;
   p.taps = d->kind == SNB_CONV_3X3 ? 9 : (d->kind == SNB_CONV_1X1 ? 1 : 4);
   if (d->kind == SNB_CONV_3X3) {
     for (int ky = 0; ky < 3; ++ky)
@@ -797,10 +798,12 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
         p.tap_dy[0][ky * 3 + kx] = static_cast<int8_t>(ky - 1);
         p.tap_dx[0][ky * 3 + kx] = static_cast<int8_t>(kx - 1);
       }
-  } else if (d->kind == SNB_CONVT_4X4_S2) {
-    // out[2y+py] gathers in[y+dy] * W[ky]:  py=0: (dy=0,ky=1), (dy=-1,ky=3);  py=1: (dy=+1,ky=0), (dy=0,ky=2)
+  } else if (is_convt) {
+    // k4 s2 p1: out[2y+py] gathers in[y+dy] * W[ky]:  py=0: (dy=0,ky=1), (dy=-1,ky=3);  py=1: (dy=+1,ky=0), (dy=0,ky=2)
+    // k3 s2 p0: out[2y+py] gathers                    py=0: (dy=0,ky=0), (dy=-1,ky=2);  py=1: (dy=0,ky=1), (unused slot)
     // the packed weight tap order is (ty, tx) with ty, tx in {0,1} following that list
-    const int dlist[2][2] = {{0, -1}, {1, 0}};
+    const int d4[2][2] = {{0, -1}, {1, 0}}, d3[2][2] = {{0, -1}, {0, 0}};
+    const int (*dlist)[2] = d->kind == SNB_CONVT_4X4_S2 ? d4 : d3;
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px)
         for (int ty = 0; ty < 2; ++ty)
@@ -818,7 +821,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     delete c;
     return fail(SNB_E_UNSUPPORTED, "fused max-pool is only available in halo mode (SNB_CONV_MODE >= 1)");
   }
-  const bool fuse_phases = halo && mode >= 3 && d->kind == SNB_CONVT_4X4_S2 && kc.fn_halo4f != nullptr;
+  const bool fuse_phases = halo && mode >= 3 && is_convt && kc.fn_halo4f != nullptr;
   int tile_w = 16, tile_h = 8;
   c->fn = kc.fn;
   c->smem = kc.smem;
@@ -908,7 +911,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   }
   if (!head) {
     const int cw = bn < 64 ? bn : 64;
-    const int s = (d->kind == SNB_CONVT_4X4_S2 || up2x) ? 2 : 1;
+    const int s = (is_convt || up2x) ? 2 : 1;
     const int64_t ow = d->w * s, oh = d->h * s;
     p.up2x = up2x ? 1 : 0;
     for (int ph = 0; ph < (up2x ? 4 : p.n_phases); ++ph) {
@@ -942,7 +945,9 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   c->grid = std::min<int>(p.total_tiles, sms);
   if (c->cluster == 2) c->grid &= ~1;   // whole CTA pairs; total_tiles is even
   // 2*MACs with the true tap counts (ConvT: every input pixel meets all 16 taps once over the 4 phases)
-  c->flops = 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * (double)(p.n_phases * p.taps);
+  // (k3 s2 p0 cropped: 9 real taps per input pixel, the other 7 slots hold zero weights)
+  c->flops = 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout *
+             (double)(d->kind == SNB_CONVT_3X3_S2 ? 9 : p.n_phases * p.taps);
   *out = c;
   return SNB_OK;
 }

@@ -295,3 +295,196 @@ class ZFUNetPlan:
 
     load_nchw = VGGUNetPlan.load_nchw
     run = VGGUNetPlan.run
+
+
+# ---------------------------------------------------------------------------------------------- FCDenseNet
+# out[2y+py] = sum in[y+dy] * W[ky] for ConvTranspose2d(k=3, s=2, p=0) cropped to [0, 2h): py=0 -> (dy=0, ky=0),
+# (dy=-1, ky=2); py=1 -> (dy=0, ky=1) and one unused slot (zero weights)
+_CONVT3_K = ((0, 2), (1, None))
+
+
+def pack_convT3x3(weight, cin_pad, cout_pad):
+    """nn.ConvTranspose2d(k=3, s=2, p=0) weight [Cin, Cout, 3, 3] -> bf16 [16 tap slots][cout_pad][cin_pad]."""
+    cin, cout = weight.shape[:2]
+    w = weight.detach().float()
+    out = torch.zeros((16, cout_pad, cin_pad), dtype=torch.float32, device=weight.device)
+    i = 0
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    ky, kx = _CONVT3_K[py][ty], _CONVT3_K[px][tx]
+                    if ky is not None and kx is not None:
+                        out[i, :cout, :cin] = w[:, :, ky, kx].t()
+                    i += 1
+    return out.to(torch.bfloat16).contiguous()
+
+
+def pad_conv_weight(weight, cin_map, cin_pad, cout_pad):
+    """[Cout, Cin, kh, kw] -> zero-padded [cout_pad, cin_pad, kh, kw] with input channel j moved to slab position
+    cin_map[j] (the slab keeps concat members in a different order than torch.cat)."""
+    cout, cin = weight.shape[:2]
+    out = torch.zeros((cout_pad, cin_pad) + tuple(weight.shape[2:]), dtype=torch.float32, device=weight.device)
+    out[:cout, cin_map] = weight.detach().float()
+    return out
+
+
+class BnReluOp:
+    """relu(batch_norm_eval(x)) of a slab range into a scratch slab (snb_bn_relu_nhwc)."""
+
+    def __init__(self, src, dst, scale, shift):
+        self.keep = (src, dst, scale, shift)
+        s = src.slab
+        self.args = (N.c_vp(src.ptr), s.n, s.h, s.w, src.c, src.cstride, N.c_vp(scale.data_ptr()),
+                     N.c_vp(shift.data_ptr()), N.c_vp(dst.ptr), dst.c, dst.cstride)
+        self.flops = 0.0
+        self.launches = 1
+
+    def __call__(self, stream):
+        N.check(N.lib().snb_bn_relu_nhwc(*self.args, stream))
+
+
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+class FCDenseNetPlan:
+    """FCDenseNet forward (lib/models/tiramisu.py:168-184) in eval mode.
+
+    One slab per resolution level holds [dense-block input | down features | TransitionUp output | up features | 16
+    zero channels]; every producer writes at its channel offset (no torch.cat), narrow outputs (growth rate 16, first
+    conv 48, ConvT 80) are stored as 32-wide tiles whose zero tail lands on the slot of the layer that runs next.
+    The per-consumer pre-activation BatchNorm+ReLU runs as an elementwise kernel into a scratch slab which the
+    convolution then reads (fusing it into the operand path of the conv kernel is the next step).
+    `spec` comes from snb_b200.lib.models.tiramisu.FCDenseNet._spec().
+    """
+
+    def __init__(self, spec, n, h, w, device, sigmoid):
+        L = len(spec['down'])
+        if h % (1 << L) or w % (1 << L):
+            raise ValueError("height and width must be multiples of %d" % (1 << L))
+        if spec['final'][0].shape[0] != 1:
+            raise NotImplementedError("fused head expects n_classes == 1")
+        self.n, self.h, self.w, self.device = n, h, w, device
+        self.ops = []
+        g = spec['growth']
+        dev = device
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, dev)
+        f32 = lambda t: t.detach().float().contiguous()
+
+        def bn_params(bn, cmap, cpad):
+            gamma, beta, mean, var, eps = bn
+            scale = gamma.detach().float() / torch.sqrt(var.detach().float() + eps)
+            shift = beta.detach().float() - mean.detach().float() * scale
+            sc = torch.zeros(cpad, dtype=torch.float32, device=dev)
+            sh = torch.zeros(cpad, dtype=torch.float32, device=dev)
+            sc[cmap], sh[cmap] = scale, shift
+            return sc, sh
+
+        def padded_bias(b, cpad):
+            out = torch.zeros(cpad, dtype=torch.float32, device=dev)
+            out[:b.numel()] = b.detach().float()
+            return out
+
+        # ---- slabs: level l holds c_in[l] + down + (up part on the way back)
+        c_first = spec['first'][0].shape[0]
+        c_in, c = [], c_first
+        for layers in spec['down']:
+            c_in.append(c)
+            c += g * len(layers)
+        c_bott_in = c
+        n_bott = len(spec['bottleneck'])
+        up_prev = [g * n_bott] + [g * len(b) for b in spec['up'][:-1]]      # channels arriving through each TransitionUp
+        slabs = []
+        for l in range(L):
+            skip = c_in[l] + g * len(spec['down'][l])
+            i_up = L - 1 - l                                                 # up block that runs at level l
+            slabs.append(S(h >> l, w >> l, _pad32(skip + up_prev[i_up] + g * len(spec['up'][i_up])) + 32))
+        bott = S(h >> L, w >> L, _pad32(c_bott_in + g * n_bott) + 32)
+        for sl in slabs + [bott]:
+            sl.t.zero_()                                                     # zero tails are read as K padding
+        self.slabs, self.bott = slabs, bott
+        max_c = max(sl.c for sl in slabs + [bott])
+        scratch = [S(h >> l, w >> l, max_c) for l in range(L + 1)]          # bn-relu output per level
+        for sc in scratch:
+            sc.t.zero_()
+
+        def dense_layer(slab, lvl, cin, cmap, layer, out_off):
+            """BN -> ReLU -> conv3x3(cin -> g) reading slab[0:cin], writing slab[out_off : out_off + 32]."""
+            bn, wt, bs = layer
+            cpad = _pad32(cin)
+            sc, sh = bn_params(bn, cmap, cpad)
+            z = scratch[lvl].view(0, cpad)
+            self.ops.append(BnReluOp(slab.view(0, cpad), z, sc, sh))
+            wp = pad_conv_weight(wt, cmap, cpad, 32)
+            self.ops.append(ConvOp(N.CONV_3X3, z, slab.view(out_off, 32), pack_conv3x3(wp), padded_bias(bs, 32), relu=False))
+
+        # ---- first conv: 3 -> 48 (no activation), stored 64 wide
+        self.x_patch = S(h, w, 32)
+        wf, bf = spec['first']
+        cf_pad = _pad32(c_first) if c_first % 64 == 0 else (c_first + 63) // 64 * 64
+        wfp = torch.zeros((cf_pad, wf.shape[1], 3, 3), dtype=torch.float32, device=dev)
+        wfp[:c_first] = wf.detach().float()
+        self.ops.append(ConvOp(N.CONV_1X1, self.x_patch.view(), slabs[0].view(0, cf_pad), pack_first_conv3x3(wfp),
+                               padded_bias(bf, cf_pad), relu=False))
+
+        # ---- down path
+        ident = lambda k: torch.arange(k, device=dev)
+        for l in range(L):
+            cur = c_in[l]
+            for layer in spec['down'][l]:
+                dense_layer(slabs[l], l, cur, ident(cur), layer, cur)
+                cur += g
+            # TransitionDown: BN -> ReLU -> conv1x1(cur -> cur) -> maxpool, into the next level's input channels
+            bn, wt, bs = spec['trans_down'][l]
+            cpad = _pad32(cur)
+            sc, sh = bn_params(bn, ident(cur), cpad)
+            z = scratch[l].view(0, cpad)
+            self.ops.append(BnReluOp(slabs[l].view(0, cpad), z, sc, sh))
+            tmp = S(h >> l, w >> l, cpad)
+            wp = pad_conv_weight(wt, ident(cur), cpad, cpad)
+            self.ops.append(ConvOp(N.CONV_1X1, z, tmp.view(), pack_conv1x1(wp), padded_bias(bs, cpad), relu=False))
+            dst = (slabs[l + 1] if l + 1 < L else bott).view(0, cur)
+            self.ops.append(PoolOp(tmp.view(0, cur), dst))
+
+        # ---- bottleneck: dense layers on the growing slab; its output is only the new features
+        cur = c_bott_in
+        for layer in spec['bottleneck']:
+            dense_layer(bott, L, cur, ident(cur), layer, cur)
+            cur += g
+        new_src = bott.view(c_bott_in, _pad32(g * n_bott))                   # 80 new channels + zero tail
+
+        # ---- up path
+        for i in range(L):
+            l = L - 1 - i
+            skip = c_in[l] + g * len(spec['down'][l])
+            cu = up_prev[i]
+            wt, bs = spec['trans_up'][i]
+            cu_pad = _pad32(cu)
+            # TransitionUp: ConvTranspose2d(k3, s2) cropped to the skip size, written right after the skip channels
+            self.ops.append(ConvOp(N.CONVT_3X3_S2, new_src, slabs[l].view(skip, cu_pad),
+                                   pack_convT3x3(wt, new_src.c, cu_pad), padded_bias(bs, cu_pad), relu=False))
+            # reference channel order of the block input is [up | skip | new...]; the slab holds [skip | up | new...]
+            cur = skip + cu
+            base_map = torch.cat([torch.arange(skip, skip + cu, device=dev), torch.arange(0, skip, device=dev)])
+            for k, layer in enumerate(spec['up'][i]):
+                cmap = torch.cat([base_map, torch.arange(skip + cu, cur, device=dev)])
+                dense_layer(slabs[l], l, cur, cmap, layer, cur)
+                cur += g
+            new_src = slabs[l].view(skip + cu, _pad32(g * len(spec['up'][i])))
+            last_cur, last_map = cur, torch.cat([base_map, torch.arange(skip + cu, cur, device=dev)])
+
+        # ---- final 1x1 conv (C -> 1) through the fused head: a 32-row conv whose row 0 is the real filter
+        wt, bs = spec['final']
+        cpad = _pad32(last_cur)
+        wp = pad_conv_weight(wt, last_map, cpad, 32)
+        self.out = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        pick = torch.zeros(32, dtype=torch.float32, device=dev)
+        pick[0] = 1.0
+        self.ops.append(ConvOp(N.CONV_1X1, slabs[0].view(0, cpad), None, pack_conv1x1(wp), padded_bias(bs, 32), relu=False,
+                               head=(pick, 0.0, sigmoid, self.out)))
+        self.flops = sum(op.flops for op in self.ops)
+        self.launches = sum(op.launches for op in self.ops)
+
+    load_nchw = VGGUNetPlan.load_nchw
+    run = VGGUNetPlan.run

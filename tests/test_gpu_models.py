@@ -99,3 +99,27 @@ def test_config1_zf_unet_loss_and_metrics(cuda, golden_dir, kats):
     # integer counts are bit-exact GIVEN identical masks: count on the device what torch counts on the same logits
     c = metrics.confusion_counts(logits, t).tolist()
     assert c == no.confusion_counts(torch.sigmoid(logits.cpu()), targets).tolist() and sum(c) == targets.numel()
+
+
+def test_fcdensenet67_against_reference_vectors(cuda, golden_dir):
+    """BASELINE configs[4] model: Tiramisu-67 (dense-block slabs, pre-activation BN+ReLU, ConvT k3 s2 + crop)."""
+    from snb_b200.lib.models import FCDenseNet67
+
+    g = np.load(os.path.join(golden_dir, "fcdensenet67.npz"))
+    m = FCDenseNet67(n_classes=1)
+    m.load_state_dict(synth.fcdensenet_state_dict(seed=5), strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).cuda()).cpu()
+        y224 = m(torch.from_numpy(np.random.RandomState(13).standard_normal((1, 3, 224, 224)).astype(np.float32)).cuda()).cpu()
+        y_again = m(torch.from_numpy(g["x"]).cuda()).cpu()               # slabs are reused: stale data must not leak
+    ref = torch.from_numpy(g["logits"])
+    assert y.shape == ref.shape and torch.equal(y, y_again)
+    p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    p_err224 = (torch.sigmoid(y224) - torch.sigmoid(torch.from_numpy(g["logits224"]))).abs().max().item()
+    assert p_err224 < BF16_PROB_TOL, p_err224
+    sd = synth.fcdensenet_state_dict(seed=5)
+    with torch.no_grad():
+        q = no.fcdensenet_forward(sd, torch.from_numpy(g["x"]), quant=no.bf16_round)
+    assert (y - q).abs().max().item() < 0.03 * max(1.0, q.abs().max().item())

@@ -15,7 +15,7 @@ from oracle import tiles_oracle as to
 from snb_b200 import dist as sdist
 from snb_b200 import engine as E
 from snb_b200.lib import augmentations as aug
-from snb_b200.lib.models import UNet11, UNet16, ZF_UNET
+from snb_b200.lib.models import FCDenseNet67, UNet11, UNet16, ZF_UNET
 from snb_b200.lib.tiles import ImageSlicer, compute_patch_weight_loss
 
 
@@ -213,3 +213,28 @@ def test_bn_folding_is_exact_algebra():
     wf, bf = E.fold_bn(w, b, (gamma, beta, mean, var, 1e-5))
     want = F.batch_norm(F.conv2d(x, w, b, padding=1), mean, var, gamma, beta, training=False, eps=1e-5)
     assert torch.allclose(F.conv2d(x, wf, bf, padding=1), want, atol=1e-4)
+
+
+def test_fcdensenet67_mirror_accepts_reference_state_dict():
+    m = FCDenseNet67(n_classes=1)
+    sd = synth.fcdensenet_state_dict(seed=5)
+    assert len(m.state_dict()) == 434 and sorted(m.state_dict()) == sorted(sd)
+    m.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 3460353 and m.num_classes == 1
+
+
+def test_convT3x3_phase_decomposition_is_the_cropped_transposed_convolution():
+    """Tap slots of SNB_CONVT_3X3_S2 (conv_tcgen05.cu) equal ConvTranspose2d(k=3, s=2, p=0) cropped to [0, 2h) x [0, 2w)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, 5, 6, 8), generator=g)
+    wt = torch.randn((8, 4, 3, 3), generator=g)
+    packed = E.pack_convT3x3(wt, 8, 4).float()
+    dlist = [[0, -1], [0, 0]]
+    out = torch.zeros((2, 10, 12, 4))
+    for py in range(2):
+        for px in range(2):
+            ph = py * 2 + px
+            taps = [(dlist[py][ty], dlist[px][tx]) for ty in range(2) for tx in range(2)]
+            out[:, py::2, px::2, :] = _tap_list_conv(x, packed[ph * 4:ph * 4 + 4], taps)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2)[:, :, :10, :12]
+    assert torch.allclose(out.permute(0, 3, 1, 2), want, atol=1e-4)

@@ -160,3 +160,12 @@ def test_zf_unet_logits_and_config1(golden_dir, kats):
     assert float(no.bce_jaccard(logits, targets)) == pytest.approx(k["bce_jaccard"], rel=1e-5)
     assert float(no.jaccard_score(logits, targets)) == pytest.approx(k["jaccard_score"], rel=1e-4)
     assert float(no.pixel_accuracy(logits, targets)) == pytest.approx(k["pixel_accuracy"], abs=1e-5)
+
+
+def test_fcdensenet67_logits(golden_dir, kats):
+    g = np.load(os.path.join(golden_dir, "fcdensenet67.npz"))
+    sd = synth.fcdensenet_state_dict(seed=5)
+    assert len(sd) == 434 and kats["fcdensenet67"]["params"] == 3460353
+    with torch.no_grad():
+        y = no.fcdensenet_forward(sd, torch.from_numpy(g["x"])).numpy()
+    assert np.abs(y - g["logits"]).max() < 1e-4
