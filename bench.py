@@ -26,6 +26,13 @@ IMAGE_HW = 5000
 TILE, STEP = 512, 384
 MPX_PER_IMAGE = IMAGE_HW * IMAGE_HW / 1e6
 METRIC = "megapixels/sec tiled U-Net inference (UNet16/AlbuNet, 5000x5000, 512/384)"
+# secondary workloads (--model): name -> (constructor, synthetic state_dict, tile, step, default tile batch, label)
+MODELS = {
+    "unet16": ("UNet16", lambda s: s.vgg_unet_state_dict("unet16", seed=0), 512, 384, 13, "configs[2]: UNet16"),
+    "unet11": ("UNet11", lambda s: s.vgg_unet_state_dict("unet11", seed=0), 512, 384, 13, "UNet11 (TernausNet-VGG11)"),
+    "zf_unet": ("ZF_UNET", lambda s: s.zf_unet_state_dict(seed=0), 224, 112, 44, "ZF_UNET"),
+    "fcdensenet67": ("FCDenseNet67", lambda s: s.fcdensenet_state_dict(seed=0), 224, 112, 44, "configs[4]: FCDenseNet67"),
+}
 
 
 def measured_peaks():
@@ -177,19 +184,24 @@ def run_cuda(args):
     from snb_b200 import inria_submit as sub
     from snb_b200.engine import ConvOp
     from snb_b200.lib import metrics
-    from snb_b200.lib.models import UNet16
-
     rank, world, local_rank = sdist.init_from_env()
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    model = UNet16()
-    model.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=0))
+    from snb_b200.lib import models as M
+
+    cls_name, make_sd, tile, step, default_batch, label = MODELS[args.model]
+    tile, step = args.tile or tile, args.step or step
+    cls = getattr(M, cls_name)
+    model = cls(n_classes=1) if args.model == "fcdensenet67" else cls()
+    model.load_state_dict(make_sd(synth))
     model = model.to(dev).eval()
-    pred = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), TILE, STEP, batch_size=args.batch, tta=args.tta,
-                              device=dev, use_graph=args.graph)
+    pred = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=args.batch or default_batch,
+                              tta=args.tta, device=dev, use_graph=args.graph)
+    metric = METRIC if args.model == "unet16" and (tile, step) == (TILE, STEP) else (
+        "megapixels/sec tiled inference (%s, 5000x5000, %d/%d)" % (cls_name, tile, step))
 
     # distinct synthetic images per rank (weak scaling: one image per rank per step)
     n_img = 2
@@ -212,10 +224,13 @@ def run_cuda(args):
         counts = metrics.confusion_counts_from_probs(merged, gts[i % n_img])
         return exchange(mask, counts)
 
+    streamer = sub.StreamingPredictor(pred)
+
     def step_e2e(i):
-        merged, mask = pred.predict_device(host_imgs[i % n_img])             # H2D from pinned memory inside
-        counts = exchange(mask, metrics.confusion_counts_from_probs(merged, gts[i % n_img]))
-        host_mask.copy_(mask, non_blocking=True)                             # D2H of the step's result
+        # H2D of this step's image from pinned memory and D2H of its mask both happen inside the timed region, on a
+        # copy stream that overlaps the neighbouring images' compute (the public host-to-host API)
+        streamer.submit(host_imgs[i % n_img], host_imgs[(i + 1) % n_img])
+        counts = exchange(pred.mask, metrics.confusion_counts_from_probs(pred.merged, gts[i % n_img]))
         host_counts.copy_(counts, non_blocking=True)
 
     def fence():
@@ -276,32 +291,47 @@ def run_cuda(args):
 
     for i in range(min(2, args.warmup)):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    streamer.flush()
+
+    def e2e_steps(i):
+        step_e2e(i)
+        if i == args.steps - 1:
+            streamer.flush()                                                 # the last mask lands on the host inside the region
+
+    ms_e2e = timed(e2e_steps, args.steps)
 
     ms_step = ms_total / args.steps
     value = world * MPX_PER_IMAGE / (ms_step / 1e3)
     e2e_value = world * MPX_PER_IMAGE / (ms_e2e / args.steps / 1e3)
     peak_tf, peak_bw, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    # DRAM bytes per conv launch from the committed ncu --set full capture of the same plan (profiles/), headline config only
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_conv_summary.json")
+    if args.model == "unet16" and pred.batch == 13 and os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = float(json.load(fh)["mean_dram_bytes_per_launch"])
     if rank != 0:
         return
     line = {
-        "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "configs[2]: UNet16 tiled inference, 5000x5000x3 u8, tile 512 / step 384, pyramid merge"
+        "config": {"workload": "%s tiled inference, 5000x5000x3 u8, tile %d / step %d, pyramid merge" % (label, tile, step)
                                + ("; configs[3]: one image per rank per step, NCCL all-reduce of IoU counts + gather of masks"
                                   if world > 1 else ""),
                    "tiles_per_image": pred.n_tiles, "tile_batch": pred.batch, "tta": bool(args.tta), "cuda_graph": bool(args.graph),
-                   "l2_policy": "no flush needed: per-step working set (activations of %d tiles/batch, ~%.1f GB) >> 126 MB L2; "
-                                "%d images rotate" % (pred.batch, 0.245 * pred.batch, n_img),
+                   "l2_policy": "no flush needed: per-step working set (activations of %d tiles/batch, GBs) >> 126 MB L2; "
+                                "%d images rotate" % (pred.batch, n_img),
                    "flop_per_image": pred.flops_per_image},
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": IMAGE_HW * IMAGE_HW * 3,
                 "d2h_bytes_per_step": IMAGE_HW * IMAGE_HW + 32},
         "gpu_launches": (pred.launches_per_image + 1) * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": None,
+                     "frac": achieved / peak_tf, "traffic": traffic,
+                     "traffic_note": "mean dram__bytes_read+write per conv launch (23 halo-kernel launches of one 13-tile plan run, "
+                                     "ncu --set full, profiles/r01_ncu_conv_summary.json); algorithmic FLOPs per launch vary per layer",
                      "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
                      "peak_source": peak_src + " bf16_tflops_sustained",
                      "timing": "CUDA events after every launch in an eager re-run of the same K steps (the timed "
@@ -322,7 +352,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=13, help="tiles per network launch")
+    ap.add_argument("--batch", type=int, default=0, help="tiles per network launch (default: per model)")
+    ap.add_argument("--model", default="unet16", choices=sorted(MODELS), help="secondary workloads; the headline is unet16")
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--step", type=int, default=0)
     ap.add_argument("--tta", action="store_true", help="D4 test-time augmentation (8 views per tile)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch eagerly instead of replaying a CUDA graph")

@@ -42,7 +42,7 @@ constexpr int kMaxTaps = 9;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kHaloW = 10, kHaloH = 18;           // halo box of the 8 x 16 patch
 constexpr int kHaloRows = kHaloW * kHaloH;        // 180 smem rows
-constexpr int kMaxAStages = 4, kMaxBStages = 8;
+constexpr int kMaxAStages = 8, kMaxBStages = 8;
 
 struct alignas(64) ConvParams {
   CUtensorMap map_a;               // activations (C, W, H, N)
@@ -836,9 +836,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     int b_stages = 0;
     if (bres) {
       while (a_stages > 2 && fixed + a_stages * kc.halo_stage_bytes + w_bytes > kSmemBudget) --a_stages;
-      while (a_stages < kMaxAStages && fixed + (a_stages + 1) * kc.halo_stage_bytes + w_bytes <= kSmemBudget &&
-             a_stages < 4)
-        ++a_stages;
+      // resident weights leave room: deepen the activation ring (short K loops need several tiles of TMA lookahead)
+      int a_cap = kMaxAStages;
+      if (const char* e = std::getenv("SNB_A_STAGES")) a_cap = std::max(2, std::min(kMaxAStages, std::atoi(e)));
+      while (a_stages < a_cap && fixed + (a_stages + 1) * kc.halo_stage_bytes + w_bytes <= kSmemBudget) ++a_stages;
       c->smem = fixed + a_stages * kc.halo_stage_bytes + (int)w_bytes;
     } else {
       a_stages = 2;

@@ -60,3 +60,26 @@ def test_merge_of_reference_tiles_is_bit_exact(cuda, golden_dir):
     for key in ("plain", "tta"):
         out = s.merge(list(g[key + "_tiles"]), dtype=np.float32)
         assert np.array_equal(out, g[key + "_merged"])
+
+
+def test_streaming_predictor_matches_direct_calls(cuda, golden_dir, model):
+    """Overlapped H2D / compute / D2H pipeline returns, one call late, exactly the masks of direct calls."""
+    g = np.load(os.path.join(golden_dir, "predict_tiled.npz"))
+    rs = np.random.RandomState(3)
+    images = [g["image"]] + [rs.randint(0, 256, g["image"].shape).astype(np.uint8) for _ in range(4)]
+    p = sub.TiledPredictor(model, g["image"].shape, 64, 32, batch_size=4, tta=False)
+    want = []
+    for im in images:
+        _, mask = p.predict_device(torch.from_numpy(im).cuda())
+        want.append(mask.cpu().clone())
+    s = sub.StreamingPredictor(p)
+    pinned = [torch.from_numpy(im).pin_memory() for im in images]
+    got = []
+    for i, im in enumerate(pinned):
+        prev = s.submit(im, pinned[i + 1] if i + 1 < len(pinned) else None)
+        if prev is not None:
+            got.append(prev.clone())
+    got.append(s.flush().clone())
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
