@@ -198,6 +198,9 @@ def run_cuda(args):
     model = cls(n_classes=1) if args.model == "fcdensenet67" else cls()
     model.load_state_dict(make_sd(synth))
     model = model.to(dev).eval()
+    if args.shard == "tile":
+        run_tile_sharded(args, model, tile, step, default_batch, dev, rank, world, label, cls_name)
+        return
     pred = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=args.batch or default_batch,
                               tta=args.tta, device=dev, use_graph=args.graph)
     metric = METRIC if args.model == "unet16" and (tile, step) == (TILE, STEP) else (
@@ -346,6 +349,62 @@ def run_cuda(args):
     print(json.dumps(line), flush=True)
 
 
+def run_tile_sharded(args, model, tile, step, default_batch, dev, rank, world, label, cls_name):
+    """--shard tile: ONE image per step split by crop range over all ranks (strong scaling of single-image latency);
+    NCCL all-gather of the float32 probability tiles, every rank merges, counts all-reduce is not needed."""
+    import torch.distributed as dist
+
+    from oracle import synth
+    from snb_b200 import inria_submit as sub
+    from snb_b200.lib import metrics
+
+    pred = sub.TileShardedPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=args.batch or default_batch,
+                                    tta=args.tta, device=dev, use_graph=args.graph)
+    imgs = [torch.from_numpy(synth.image_u8(i, IMAGE_HW, IMAGE_HW)).to(dev) for i in range(2)]
+    g = torch.Generator(device=dev).manual_seed(1000)
+    gt = (torch.rand((IMAGE_HW, IMAGE_HW, 1), device=dev, generator=g) > 0.5).to(torch.uint8)
+
+    def step_fn(i):
+        merged, mask = pred.predict_device(imgs[i % 2])
+        return metrics.confusion_counts_from_probs(merged, gt)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_fn(i)
+    fence()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        counts = step_fn(i)
+    e1.record()
+    fence()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # every rank must hold the same mask bytes
+    digest = pred.local.mask.to(torch.int64).sum().reshape(1)
+    lo, hi = digest.clone(), digest.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms_step = float(ms.item()) / args.steps
+    print(json.dumps({
+        "metric": "megapixels/sec tiled inference, ONE image sharded by tile (%s, 5000x5000, %d/%d)" % (cls_name, tile, step),
+        "value": MPX_PER_IMAGE / (ms_step / 1e3), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "%s, one image per step split by crop range over %d ranks, NCCL all-gather of probability "
+                               "tiles, merge on every rank" % (label, world), "tiles_per_rank": pred.max_count,
+                   "masks_identical_across_ranks": bool(lo.item() == hi.item()), "counts": counts.tolist()},
+        "gpu_launches": (pred.local.launches_per_image + 2) * args.steps}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -354,6 +413,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="tiles per network launch (default: per model)")
     ap.add_argument("--model", default="unet16", choices=sorted(MODELS), help="secondary workloads; the headline is unet16")
+    ap.add_argument("--shard", default="image", choices=["image", "tile"],
+                    help="multi-GPU partitioning: one image per rank per step (weak, default) or one image split by tile (strong)")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--step", type=int, default=0)
     ap.add_argument("--tta", action="store_true", help="D4 test-time augmentation (8 views per tile)")

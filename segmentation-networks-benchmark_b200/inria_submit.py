@@ -24,7 +24,7 @@ INRIA_STD = [3.15086464, 3.29831641, 3.63201004]
 
 class TiledPredictor:
     def __init__(self, model, image_shape, patch_size, tile_step=None, batch_size=1, weight='pyramid', tta=True,
-                 normalize=None, device=None, use_graph=True):
+                 normalize=None, device=None, use_graph=True, tile_range=None, merge=True):
         N.require_cuda()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.image_shape = tuple(image_shape)
@@ -34,7 +34,13 @@ class TiledPredictor:
         self.views = 8 if tta else 1
         self.slicer = ImageSlicer(image_shape, patch_size, self.tile_step, weight=weight)
         self.n_tiles = len(self.slicer.crops)
-        self.batch = max(1, min(int(batch_size), self.n_tiles))
+        # tile_range = (begin, end): this predictor only runs those crops (tile-sharded multi-GPU mode); with merge=False
+        # the caller exchanges self.probs and calls merge_probs() itself
+        self.tile_begin, self.tile_end = (0, self.n_tiles) if tile_range is None else tile_range
+        if not (0 <= self.tile_begin <= self.tile_end <= self.n_tiles):
+            raise ValueError("tile_range outside the %d crops" % self.n_tiles)
+        self.do_merge = merge
+        self.batch = max(1, min(int(batch_size), max(1, self.tile_end - self.tile_begin)))
         norm = normalize if normalize is not None else NormalizeImage(mean=INRIA_MEAN, std=INRIA_STD)
         with torch.cuda.device(self.device):
             self.lut = torch.from_numpy(norm.lut()).to(self.device)
@@ -48,10 +54,11 @@ class TiledPredictor:
             self.image = torch.empty((h, w, self.channels), dtype=torch.uint8, device=self.device)
         self.use_graph = use_graph
         self._graph = None
-        n_chunks = (self.n_tiles + self.batch - 1) // self.batch
+        n_local = self.tile_end - self.tile_begin
+        n_chunks = (n_local + self.batch - 1) // self.batch
         # kernels enqueued per image: per chunk and view one split + the plan, then one merge
-        self.launches_per_image = n_chunks * self.views * (1 + self.plan.launches) + 1
-        self.flops_per_image = self.plan.flops / self.batch * self.n_tiles * self.views
+        self.launches_per_image = n_chunks * self.views * (1 + self.plan.launches) + (1 if merge else 0)
+        self.flops_per_image = self.plan.flops / self.batch * n_local * self.views
 
     def predict_device(self, d_image):
         """uint8 [H][W][C] CUDA tensor -> (float32 [H][W][1] merged probabilities, uint8 [H][W][1] mask); async.
@@ -75,21 +82,68 @@ class TiledPredictor:
 
     def _enqueue(self, d_image):
         lib, st = N.lib(), N.stream_ptr()
-        for begin in range(0, self.n_tiles, self.batch):
-            count = min(self.batch, self.n_tiles - begin)
+        for begin in range(self.tile_begin, self.tile_end, self.batch):
+            count = min(self.batch, self.tile_end - begin)
             for v in range(self.views):
                 N.check(lib.snb_split_norm_u8(self.slicer.handle, N.ptr(d_image), self.channels, N.ptr(self.lut), v,
                                               N.LAYOUT_PATCH32, N.c_vp(self.plan.x_patch.t.data_ptr()), begin, count, st))
                 out = self.plan.run()
                 self.probs[begin:begin + count, v, :, :, 0].copy_(out[:count])
-        N.check(lib.snb_merge(self.slicer.handle, N.ptr(self.probs), N.DT_F32, 1, self.views, N.ptr(self.weight),
-                              N.ptr(self.merged), N.DT_F32, N.ptr(self.mask), 0.5, st))
+        if self.do_merge:
+            self.merge_probs()
+        return self.merged, self.mask
+
+    def merge_probs(self):
+        """Weighted overlap-add of self.probs (all crops) into self.merged / self.mask on the current stream."""
+        N.check(N.lib().snb_merge(self.slicer.handle, N.ptr(self.probs), N.DT_F32, 1, self.views, N.ptr(self.weight),
+                                  N.ptr(self.merged), N.DT_F32, N.ptr(self.mask), 0.5, N.stream_ptr()))
         return self.merged, self.mask
 
     def __call__(self, image):
         """numpy uint8 H x W x C -> numpy float32 H x W x 1 (what reference predict_tiled returns)."""
         merged, _ = self.predict_device(torch.from_numpy(np.ascontiguousarray(image)))
         return merged.cpu().numpy()
+
+
+class TileShardedPredictor:
+    """One image across all ranks (BASELINE configs[3], "sharded by tile"): rank r runs the contiguous crop range
+    dist.shard_range(n_tiles, r, world), the float32 probability tiles are all-gathered over NCCL (177 MB per image,
+    never partial float accumulators: SURVEY 8e), and every rank merges all crops in crop order, so the mask is
+    byte-identical to the single-GPU result.  Strong scaling of single-image latency."""
+
+    def __init__(self, model, image_shape, patch_size, tile_step=None, batch_size=1, weight='pyramid', tta=True,
+                 normalize=None, device=None, use_graph=True):
+        import torch.distributed as dist
+
+        from . import dist as sdist
+
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        probe = ImageSlicer(image_shape, patch_size, patch_size // 2 if tile_step is None else tile_step, weight=weight)
+        n_tiles = len(probe.crops)
+        self.ranges = [sdist.shard_range(n_tiles, r, self.world) for r in range(self.world)]
+        self.local = TiledPredictor(model, image_shape, patch_size, tile_step, batch_size, weight, tta, normalize, device,
+                                    use_graph, tile_range=self.ranges[self.rank], merge=False)
+        self.max_count = max(e - b for b, e in self.ranges)
+        p = self.local
+        row = p.probs[0].numel()
+        self.send = torch.zeros((self.max_count, row), dtype=torch.float32, device=p.device)
+        self.recv = torch.empty((self.world * self.max_count, row), dtype=torch.float32, device=p.device)
+
+    def predict_device(self, d_image):
+        import torch.distributed as dist
+
+        p = self.local
+        p.predict_device(d_image)
+        if self.world > 1:
+            flat = p.probs.view(p.n_tiles, -1)
+            b, e = self.ranges[self.rank]
+            self.send[:e - b].copy_(flat[b:e])
+            dist.all_gather_into_tensor(self.recv, self.send)
+            for r, (rb, re) in enumerate(self.ranges):
+                if r != self.rank and re > rb:
+                    flat[rb:re].copy_(self.recv[r * self.max_count:r * self.max_count + (re - rb)])
+        return p.merge_probs()
 
 
 class StreamingPredictor:

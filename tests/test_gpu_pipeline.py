@@ -83,3 +83,26 @@ def test_streaming_predictor_matches_direct_calls(cuda, golden_dir, model):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_tile_range_predictors_reassemble_the_full_result(cuda, golden_dir, model):
+    """Tile-sharded mode on one device: two predictors own disjoint crop ranges, their probability tiles are
+    combined and merged -> identical bytes to the unsharded predictor (what TileShardedPredictor does over NCCL)."""
+    g = np.load(os.path.join(golden_dir, "predict_tiled.npz"))
+    d = torch.from_numpy(g["image"]).cuda()
+    full = sub.TiledPredictor(model, g["image"].shape, 64, 32, batch_size=4, tta=False)
+    merged, mask = full.predict_device(d)
+    merged, mask = merged.clone(), mask.clone()
+    n = full.n_tiles
+    a = sub.TiledPredictor(model, g["image"].shape, 64, 32, batch_size=4, tta=False, tile_range=(0, n // 2), merge=False)
+    b = sub.TiledPredictor(model, g["image"].shape, 64, 32, batch_size=4, tta=False, tile_range=(n // 2, n), merge=False)
+    a.predict_device(d)
+    b.predict_device(d)
+    a.probs[n // 2:].copy_(b.probs[n // 2:])
+    m2, k2 = a.merge_probs()
+    assert torch.equal(m2, merged) and torch.equal(k2, mask)
+    with pytest.raises(ValueError):
+        sub.TiledPredictor(model, g["image"].shape, 64, 32, tile_range=(0, n + 1))
+    single = sub.TileShardedPredictor(model, g["image"].shape, 64, 32, batch_size=4, tta=False)   # world size 1
+    m3, k3 = single.predict_device(d)
+    assert torch.equal(m3, merged) and torch.equal(k3, mask)
