@@ -10,12 +10,20 @@ import snb_b200  # noqa: E402,F401
 from oracle import synth  # noqa: E402
 from snb_b200 import _native as N  # noqa: E402
 from snb_b200.engine import ConvOp  # noqa: E402
-from snb_b200.lib.models import UNet16  # noqa: E402
+from snb_b200.lib import models as M  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 13
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-m = UNet16()
-m.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=0))
+name = sys.argv[3] if len(sys.argv) > 3 else "unet16"
+if name == "fcdensenet67":
+    m = M.FCDenseNet67(n_classes=1)
+    m.load_state_dict(synth.fcdensenet_state_dict(seed=0))
+elif name == "zf_unet":
+    m = M.ZF_UNET()
+    m.load_state_dict(synth.zf_unet_state_dict(seed=0))
+else:
+    m = getattr(M, {"unet16": "UNet16", "unet11": "UNet11"}[name])()
+    m.load_state_dict(synth.vgg_unet_state_dict(name, seed=0))
 m = m.cuda().eval()
 plan = m.plan(batch, T, T, sigmoid=True)
 plan.x_patch.t.normal_()
@@ -43,4 +51,8 @@ for k, op in enumerate(plan.ops):
         print("%2d conv kind=%d %4dx%-4d cin=%4d cout=%4d  %8.3f ms %8.1f TF/s" % (
             k, d[0], d[1], d[2], d[3], d[4], acc[k], op.flops / acc[k] / 1e9))
     else:
-        print("%2d pool %38s %8.3f ms" % (k, "", acc[k]))
+        print("%2d %-8s %35s %8.3f ms" % (k, type(op).__name__, "", acc[k]))
+by = {}
+for k, op in enumerate(plan.ops):
+    by[type(op).__name__] = by.get(type(op).__name__, 0.0) + acc[k]
+print("by op type:", {k: round(v, 3) for k, v in by.items()})
