@@ -198,6 +198,8 @@ def run_cuda(args):
     model = cls(n_classes=1) if args.model == "fcdensenet67" else cls()
     model.load_state_dict(make_sd(synth))
     model = model.to(dev).eval()
+    if args.precision != "bf16":
+        model.set_precision(args.precision)
     if args.shard == "tile":
         run_tile_sharded(args, model, tile, step, default_batch, dev, rank, world, label, cls_name)
         return
@@ -318,7 +320,7 @@ def run_cuda(args):
         return
     line = {
         "metric": metric, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
         "data": "synthetic",
         "config": {"workload": "%s tiled inference, 5000x5000x3 u8, tile %d / step %d, pyramid merge" % (label, tile, step)
                                + ("; configs[3]: one image per rank per step, NCCL all-reduce of IoU counts + gather of masks"
@@ -413,6 +415,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="tiles per network launch (default: per model)")
     ap.add_argument("--model", default="unet16", choices=sorted(MODELS), help="secondary workloads; the headline is unet16")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="bf16 (headline) or tf32 = fp32 storage with TF32 tensor-core products (the 1e-4 'fp32 mode')")
     ap.add_argument("--shard", default="image", choices=["image", "tile"],
                     help="multi-GPU partitioning: one image per rank per step (weak, default) or one image split by tile (strong)")
     ap.add_argument("--tile", type=int, default=0)

@@ -81,12 +81,14 @@ SNB_API int snb_split_hwc(const snb_slicer* s, const void* d_src, int64_t channe
  *                                                       k = (ky*3+kx)*3 + c, zero outside the tile, k>=27 zero) */
 #define SNB_LAYOUT_NCHW_F32 0
 #define SNB_LAYOUT_PATCH32 1
+#define SNB_LAYOUT_PATCH32_F32 2 /* same rows as PATCH32 but float rounded to TF32 (128 bytes per pixel): TF32 mode */
 SNB_API int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int64_t channels, const float* d_lut,
                       int tta, int layout, void* d_dst, int64_t tile_begin, int64_t tile_count, void* stream);
 
-/* float [n][3][H][W] (the nn.Module.forward input) -> PATCH32 rows, same definition as above */
+/* float [n][3][H][W] (the nn.Module.forward input) -> PATCH32 rows, same definition as above; out_f32 != 0 writes
+ * the SNB_LAYOUT_PATCH32_F32 form */
 SNB_API int snb_nchw_f32_to_patch32(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w,
-                            void* d_dst, void* stream);
+                            void* d_dst, int out_f32, void* stream);
 
 /* ImageSlicer.merge (lib/tiles.py:137-161): weighted overlap-add in float64 in crop order, clip of the norm at
  * DBL_EPSILON, divide, cast, crop.  d_tiles [n_tiles][T][T][C] of tile_dtype (SNB_DT_*), d_weight double[T][T].
@@ -104,12 +106,17 @@ SNB_API int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, 
 /* ------------------------------------------------------------------------------------------ convolutions */
 /* Activations are NHWC bf16 inside channel slabs: pixel stride = *_cstride channels, so a producer can write
  * straight into its slot of a concat buffer (torch.cat of lib/models/unet16.py:122-127 never materialises).
- * Weights are pre-packed bf16 [phase][tap][Cout][Cin] (K-major), bias is float[Cout]. */
+ * Weights are pre-packed bf16 (or fp32 in TF32 mode) [phase][tap][Cout][Cin] (K-major), bias is float[Cout]. */
 #define SNB_CONV_3X3 0      /* k3 s1 p1: 1 phase x 9 taps, tap = ky*3+kx                     */
 #define SNB_CONV_1X1 1      /* k1: 1 phase x 1 tap                                           */
 #define SNB_CONVT_4X4_S2 2  /* ConvTranspose2d k4 s2 p1: 4 sub-pixel phases x 4 taps         */
 #define SNB_CONVT_3X3_S2 3  /* ConvTranspose2d k3 s2 p0 cropped to [0,2h) x [0,2w) (lib/models/tiramisu.py:62-90):
                                4 phases x 4 tap slots, unused slots carry zero weights       */
+
+/* storage / arithmetic type of activations and weights of a convolution */
+#define SNB_CONV_BF16 0     /* bf16 storage, tcgen05 kind::f16, fp32 accumulation (default)  */
+#define SNB_CONV_TF32 1     /* fp32 storage rounded to TF32, tcgen05 kind::tf32, fp32 accumulation: the "fp32 mode"
+                               whose probabilities stay within 1e-4 of the fp32 reference    */
 
 typedef struct snb_conv_desc {
   int32_t kind;          /* SNB_CONV_*                                                      */
@@ -135,7 +142,8 @@ typedef struct snb_conv_desc {
   /* nn.Upsample(scale_factor=2) (nearest) fused into the store: d_out is then a slab of [n][2h][2w] pixels and every
    * output pixel is written to its 2x2 block (lib/models/zf_unet.py:42,78-90); conv3x3 / conv1x1 only */
   int32_t out_upsample2x;
-  int32_t reserved0;
+  int32_t dtype;         /* SNB_CONV_BF16 / SNB_CONV_TF32: element type of d_in, d_out, d_pool_out and d_weight
+                            (bias and the head stay float); channel counts are multiples of 64 bytes / element size */
 } snb_conv_desc;
 
 typedef struct snb_conv snb_conv;
@@ -145,9 +153,10 @@ SNB_API void snb_conv_destroy(snb_conv* c);
 /* algorithmic FLOPs of one launch (2*MACs, padding excluded), for roofline bookkeeping */
 SNB_API double snb_conv_flops(const snb_conv* c);
 
-/* nn.MaxPool2d(2,2) on NHWC bf16 slabs; h, w even; channels multiple of 8 */
+/* nn.MaxPool2d(2,2) on NHWC slabs of bf16 (elem_bytes 2) or float (elem_bytes 4); h, w even; channel counts and
+ * strides multiples of 16 bytes */
 SNB_API int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
-                   void* d_out, int64_t out_cstride, void* stream);
+                   void* d_out, int64_t out_cstride, int elem_bytes, void* stream);
 
 /* Pre-activation BatchNorm2d(eval) + ReLU of FCDenseNet's DenseLayer / TransitionDown (lib/models/tiramisu.py:12-13,
  * 50-51): out[.., c] = max(in[.., c] * scale[c] + shift[c], 0) for c < channels, 0 for channels <= c < channels_pad

@@ -19,8 +19,9 @@ SNB_E_CUDA = -3
 SNB_E_UNSUPPORTED = -4
 
 DT_U8, DT_F32, DT_F64, DT_I64 = 0, 1, 2, 3
-LAYOUT_NCHW_F32, LAYOUT_PATCH32 = 0, 1
+LAYOUT_NCHW_F32, LAYOUT_PATCH32, LAYOUT_PATCH32_F32 = 0, 1, 2
 CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2 = 0, 1, 2, 3
+CONV_BF16, CONV_TF32 = 0, 1
 
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
@@ -51,7 +52,7 @@ class ConvDesc(ctypes.Structure):
         ("d_pool_out", c_vp),
         ("pool_cstride", c_i64),
         ("out_upsample2x", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
     ]
 
 
@@ -66,13 +67,13 @@ SIGNATURES = {
     "snb_slicer_crops": (c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "snb_split_hwc": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_split_norm_u8": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp]),
-    "snb_nchw_f32_to_patch32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "snb_nchw_f32_to_patch32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
     "snb_merge": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_float, c_vp]),
     "snb_conv_create": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
     "snb_conv_launch": (c_int, [c_vp, c_vp]),
     "snb_conv_destroy": (None, [c_vp]),
     "snb_conv_flops": (ctypes.c_double, [c_vp]),
-    "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp]),
     "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),

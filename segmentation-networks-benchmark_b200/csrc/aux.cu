@@ -17,7 +17,16 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
-__global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int H, int W, int CV /*channels/8*/, int in_sv /*cstride/8*/,
+__device__ __forceinline__ uint4 f32x4_max(uint4 a, uint4 b) {
+  return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+
+// CV / in_sv / out_sv count 16-byte vectors (8 bf16 or 4 floats)
+template <bool F32>
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int H, int W, int CV, int in_sv,
                                   uint4* __restrict__ out, int out_sv, int64_t total) {
   const int OH = H / 2, OW = W / 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -29,7 +38,8 @@ __global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int H, int W, in
     const int64_t base = ((n * H + 2 * oy) * W + 2 * ox) * in_sv + cv;
     const uint4 a = __ldg(in + base), b = __ldg(in + base + in_sv);
     const uint4 c = __ldg(in + base + (int64_t)W * in_sv), d = __ldg(in + base + (int64_t)W * in_sv + in_sv);
-    out[((n * OH + oy) * OW + ox) * out_sv + cv] = bf16x8_max(bf16x8_max(a, b), bf16x8_max(c, d));
+    out[((n * OH + oy) * OW + ox) * out_sv + cv] =
+        F32 ? f32x4_max(f32x4_max(a, b), f32x4_max(c, d)) : bf16x8_max(bf16x8_max(a, b), bf16x8_max(c, d));
   }
 }
 
@@ -81,17 +91,24 @@ static int aux_grid(int64_t total) {
 using namespace snb;
 
 extern "C" int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
-                              void* d_out, int64_t out_cstride, void* stream) {
+                              void* d_out, int64_t out_cstride, int elem_bytes, void* stream) {
+  if (elem_bytes != 2 && elem_bytes != 4) return fail(SNB_E_INVALID, "elem_bytes must be 2 (bf16) or 4 (float)");
+  const int64_t V = 16 / elem_bytes;   // elements per 16-byte vector
   if (!d_in || !d_out) return fail(SNB_E_INVALID, "snb_maxpool2x2: null argument");
   if (n <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return fail(SNB_E_INVALID, "maxpool needs even positive h, w");
-  if (channels <= 0 || channels % 8 || in_cstride % 8 || out_cstride % 8 || in_cstride < channels || out_cstride < channels)
-    return fail(SNB_E_INVALID, "channel counts and strides must be multiples of 8");
+  if (channels <= 0 || channels % V || in_cstride % V || out_cstride % V || in_cstride < channels || out_cstride < channels)
+    return fail(SNB_E_INVALID, "channel counts and strides must be multiples of 16 bytes");
   if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
     return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
-  const int64_t total = n * (h / 2) * (w / 2) * (channels / 8);
-  maxpool2x2_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
-                                                                     (int)(channels / 8), (int)(in_cstride / 8),
-                                                                     static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  const int64_t total = n * (h / 2) * (w / 2) * (channels / V);
+  if (elem_bytes == 4)
+    maxpool2x2_kernel<true><<<aux_grid(total), 256, 0, as_stream(stream)>>>(
+        static_cast<const uint4*>(d_in), (int)h, (int)w, (int)(channels / V), (int)(in_cstride / V),
+        static_cast<uint4*>(d_out), (int)(out_cstride / V), total);
+  else
+    maxpool2x2_kernel<false><<<aux_grid(total), 256, 0, as_stream(stream)>>>(
+        static_cast<const uint4*>(d_in), (int)h, (int)w, (int)(channels / V), (int)(in_cstride / V),
+        static_cast<uint4*>(d_out), (int)(out_cstride / V), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -70,14 +70,16 @@ struct alignas(64) ConvParams {
   int8_t tap_dx[kMaxPhases][kMaxTaps];
 };
 
-template <int BN, int BK>
+// EB = element bytes of activations / weights: 2 = bf16, 4 = fp32 storage consumed as TF32.  BK counts elements, so a
+// K chunk is always one swizzle span of SWZ = BK * EB bytes (128 or 64) and one MMA consumes 32 bytes of it.
+template <int BN, int BK, int EB = 2>
 struct ConvCfg {
-  static constexpr int SWZ = BK * 2;                    // bytes per operand row = swizzle span
+  static constexpr int SWZ = BK * EB;                   // bytes per operand row = swizzle span
   static constexpr int A_BYTES = kBM * SWZ;
   static constexpr int B_BYTES = BN * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int CW = BN < 64 ? BN : 64;          // channels per output store chunk
-  static constexpr int OUT_SWZ = CW * 2;
+  static constexpr int CW = BN < 128 / EB ? BN : 128 / EB;   // channels per output store chunk (<= 128 bytes)
+  static constexpr int OUT_SWZ = CW * EB;
   static constexpr int OUT_BYTES = kBM * OUT_SWZ;
   static constexpr int CTRL_BYTES = 1024;               // barriers + tmem pointer
   static constexpr int RAW_STAGES = (kSmemBudget - 1024 /*align slack*/ - 2 * OUT_BYTES - CTRL_BYTES) / STAGE_BYTES;
@@ -143,6 +145,13 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
 }
 
+__device__ __forceinline__ uint4 f32x4_max(uint4 a, uint4 b) {
+  return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -150,12 +159,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // Epilogue of one accumulator tile, executed by the 4 epilogue warps (128 threads = 128 TMEM lanes = 128 pixels).
 // TW = patch width in pixels (row r of the tile is pixel (r % TW, r / TW)).
-template <int BN, bool HEAD, int TW>
+template <int BN, bool HEAD, int TW, int EB>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& tc, uint32_t t_addr,
                                               uint64_t* tmem_empty_bar, uint8_t* smem_out, uint32_t& n_store,
                                               int row, int lane, int epi_tid, bool release = true) {
-  constexpr int CW = BN < 64 ? BN : 64;
-  constexpr int OUT_SWZ = CW * 2;
+  constexpr int CW = BN < 128 / EB ? BN : 128 / EB;
+  constexpr int OUT_SWZ = CW * EB;
   constexpr int OUT_BYTES = kBM * OUT_SWZ;
   if constexpr (HEAD) {
     static_assert(!HEAD || BN == 32, "fused head needs all channels of a pixel in one thread");
@@ -213,18 +222,33 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
           }
-          const int chunk = g * 4 + j;
           const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
-          uint4* dst = reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4));
-          uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                pack_bf16x2(f[6], f[7]));
-          *dst = pk;
-          if (p.pool) {
-            pk = bf16x8_max(pk, shfl_xor_u4(pk, 1));
-            pk = bf16x8_max(pk, shfl_xor_u4(pk, TW));
-            if (pool_keep) {
-              const int swp = OUT_SWZ == 128 ? (prow & 7) : ((prow >> 1) & 3);
-              *reinterpret_cast<uint4*>(spool + prow * OUT_SWZ + ((chunk ^ swp) << 4)) = pk;
+          const int swp = OUT_SWZ == 128 ? (prow & 7) : ((prow >> 1) & 3);
+          if constexpr (EB == 2) {
+            const int chunk = g * 4 + j;
+            uint4* dst = reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4));
+            uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                  pack_bf16x2(f[6], f[7]));
+            *dst = pk;
+            if (p.pool) {
+              pk = bf16x8_max(pk, shfl_xor_u4(pk, 1));
+              pk = bf16x8_max(pk, shfl_xor_u4(pk, TW));
+              if (pool_keep) *reinterpret_cast<uint4*>(spool + prow * OUT_SWZ + ((chunk ^ swp) << 4)) = pk;
+            }
+          } else {
+            // fp32 storage: 8 channels = two 16-byte chunks; values are rounded to TF32 so that the next layer's
+            // tensor-core read (which drops the low mantissa bits) sees exactly what is stored
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int chunk = g * 8 + j * 2 + h;
+              uint4 pk = make_uint4(__float_as_uint(round_tf32(f[4 * h + 0])), __float_as_uint(round_tf32(f[4 * h + 1])),
+                                    __float_as_uint(round_tf32(f[4 * h + 2])), __float_as_uint(round_tf32(f[4 * h + 3])));
+              *reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4)) = pk;
+              if (p.pool) {
+                pk = f32x4_max(pk, shfl_xor_u4(pk, 1));
+                pk = f32x4_max(pk, shfl_xor_u4(pk, TW));
+                if (pool_keep) *reinterpret_cast<uint4*>(spool + prow * OUT_SWZ + ((chunk ^ swp) << 4)) = pk;
+              }
             }
           }
         }
@@ -253,11 +277,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
 }
 
 // =============================================================================================== v1: tap mode
-template <int BN, int BK, bool HEAD>
+template <int BN, int BK, bool HEAD, int EB>
 __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN, BK>;
+  using Cfg = ConvCfg<BN, BK, EB>;
   constexpr int NSTAGES = Cfg::NSTAGES;
-  constexpr uint32_t IDESC = make_idesc_bf16(kBM, BN);
+  constexpr uint32_t IDESC = make_idesc(kBM, BN, EB == 2 ? 1u : 2u);
   constexpr int TW = 16, TH = 8;
 
   extern __shared__ uint8_t smem_raw[];
@@ -345,9 +369,9 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
           const uint64_t adesc = make_kmajor_desc<Cfg::SWZ>(a_addr, 8 * Cfg::SWZ);
           const uint64_t bdesc = make_kmajor_desc<Cfg::SWZ>(a_addr + Cfg::A_BYTES, 8 * Cfg::SWZ);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-            umma_bf16_ss(adesc + 2 * k, bdesc + 2 * k, d_tmem, IDESC, (ks > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < Cfg::SWZ / 32; ++k) {
+            // advance 32 bytes (16 bf16 / 8 tf32) along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_ss<EB>(adesc + 2 * k, bdesc + 2 * k, d_tmem, IDESC, (ks > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
         }
@@ -368,7 +392,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       mbar_wait(&tmem_full[acc], acc_ph);
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_tile<BN, HEAD, TW>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
+      epilogue_tile<BN, HEAD, TW, EB>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
   }
@@ -404,14 +428,14 @@ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
 // CL = 2 runs CTA pairs (thread-block cluster of 2) on two spatial tiles of the same N tile: each CTA fetches half of
 // every weight box and TMA-multicasts it into both CTAs' shared memory, halving the L2->SM weight traffic that
 // bounds the large layers (32 KB per tap per CTA at BN=256 otherwise).
-template <int BN, int BK, bool HEAD, int TAPS, int NPH, int CL>
+template <int BN, int BK, bool HEAD, int TAPS, int NPH, int CL, int EB>
 __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
   static_assert(CL == 1 || (CL == 2 && NPH == 1 && !HEAD && BN >= 128), "CTA pairs are for the streamed-weight layers");
-  using Cfg = ConvCfg<BN, BK>;
+  using Cfg = ConvCfg<BN, BK, EB>;
   static_assert(NPH == 1 || (NPH == 4 && TAPS == 4 && !HEAD), "phase fusion is for ConvTranspose");
   constexpr int TCOLS = Cfg::TMEM_COLS * NPH;
   static_assert(TCOLS <= 512, "TMEM columns");
-  constexpr uint32_t IDESC = make_idesc_bf16(kBM, BN);
+  constexpr uint32_t IDESC = make_idesc(kBM, BN, EB == 2 ? 1u : 2u);
   constexpr int TW = 8, TH = 16;
   constexpr int SWZ = Cfg::SWZ;
   constexpr uint32_t A_STAGE16 = Cfg::HALO_STAGE_BYTES >> 4;
@@ -568,8 +592,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
               b_lo = b_lo0 + sb * B_BYTES16;
             }
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ss(desc_from_halves(a_lo + aoff[wt] + 2 * k, HI_A), desc_from_halves(b_lo + 2 * k, HI_B),
+            for (int k = 0; k < SWZ / 32; ++k)
+              umma_ss<EB>(desc_from_halves(a_lo + aoff[wt] + 2 * k, HI_A), desc_from_halves(b_lo + 2 * k, HI_B),
                            d_tmem + (wt / TAPS) * BN, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
             if (!bres) {
               if (CL == 1) umma_commit(&b_empty[sb]);
@@ -602,7 +626,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
 #pragma unroll 1
       for (int ph = 0; ph < NPH; ++ph) {
         if (NPH > 1) tc.ph = ph;
-        epilogue_tile<BN, HEAD, TW>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid,
+        epilogue_tile<BN, HEAD, TW, EB>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid,
                                     ph == NPH - 1);
       }
     }
@@ -635,16 +659,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map over up to 4 dims; strides in bytes for dims 1..rank-1
+// bf16 / fp32 tensor map over up to 4 dims; strides in bytes for dims 1..rank-1
 static int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                      const uint32_t* box, int swizzle_bytes) {
+                      const uint32_t* box, int swizzle_bytes, int elem_bytes = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(SNB_E_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, estr,
+  CUresult r = fn(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SNB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -663,48 +687,55 @@ struct KernelChoice {
   int halo_stage_bytes, b_bytes, out_bytes, pool_bytes;
 };
 
-template <int BN, int BK, bool HEAD>
+template <int BN, int BK, bool HEAD, int EB>
 static const void* fused_phase_kernel() {
-  if constexpr (!HEAD && BN <= 64) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, 4, 4, 1>);
+  if constexpr (!HEAD && BN <= 64) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, 4, 4, 1, EB>);
   else return nullptr;
 }
 
-template <int BN, int BK, bool HEAD, int TAPS>
+template <int BN, int BK, bool HEAD, int TAPS, int EB>
 static const void* pair_kernel() {
-  if constexpr (!HEAD && BN >= 128) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, TAPS, 1, 2>);
+  // CTA pairs are a measured no-gain variant: only built for the bf16 path
+  if constexpr (!HEAD && BN >= 128 && EB == 2) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, TAPS, 1, 2, EB>);
   else return nullptr;
 }
 
-template <int BN, int BK, bool HEAD>
+template <int BN, int BK, bool HEAD, int EB>
 static KernelChoice choice() {
-  using Cfg = ConvCfg<BN, BK>;
-  return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD>),
-                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1, 1>),
-                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1, 1>), fused_phase_kernel<BN, BK, HEAD>(),
-                      pair_kernel<BN, BK, HEAD, 9>(), pair_kernel<BN, BK, HEAD, 4>(),
-                      Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES, HEAD ? 0 : Cfg::OUT_BYTES,
-                      HEAD ? 0 : Cfg::POOL_BYTES};
+  using Cfg = ConvCfg<BN, BK, EB>;
+  return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD, EB>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1, 1, EB>),
+                      reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1, 1, EB>),
+                      fused_phase_kernel<BN, BK, HEAD, EB>(), pair_kernel<BN, BK, HEAD, 9, EB>(),
+                      pair_kernel<BN, BK, HEAD, 4, EB>(), Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES,
+                      HEAD ? 0 : Cfg::OUT_BYTES, HEAD ? 0 : Cfg::POOL_BYTES};
 }
 
-static bool pick_kernel(int bn, int bk, bool head, KernelChoice* out) {
-  if (head) {
-    if (bn != 32) return false;
-    *out = bk == 64 ? choice<32, 64, true>() : choice<32, 32, true>();
-    return true;
+// bk in elements; eb = element bytes (2 = bf16, 4 = tf32): the row is bk * eb = 64 or 128 bytes either way
+static bool pick_kernel(int bn, int bk, bool head, int eb, KernelChoice* out) {
+#define SNB_PICK(BN_, BK_, EB_)                          \
+  if (bn == BN_ && bk == BK_ && eb == EB_) {             \
+    *out = head ? choice<32, BK_, true, EB_>() : choice<BN_, BK_, false, EB_>(); \
+    return true;                                         \
   }
-#define SNB_PICK(BN_, BK_)                  \
-  if (bn == BN_ && bk == BK_) {             \
-    *out = choice<BN_, BK_, false>();       \
-    return true;                            \
-  }
-  SNB_PICK(32, 32)
-  SNB_PICK(32, 64)
-  SNB_PICK(64, 32)
-  SNB_PICK(64, 64)
-  SNB_PICK(128, 32)
-  SNB_PICK(128, 64)
-  SNB_PICK(256, 32)
-  SNB_PICK(256, 64)
+  if (head && bn != 32) return false;
+  SNB_PICK(32, 32, 2)
+  SNB_PICK(32, 64, 2)
+  SNB_PICK(32, 16, 4)
+  SNB_PICK(32, 32, 4)
+  if (head) return false;
+  SNB_PICK(64, 32, 2)
+  SNB_PICK(64, 64, 2)
+  SNB_PICK(128, 32, 2)
+  SNB_PICK(128, 64, 2)
+  SNB_PICK(256, 32, 2)
+  SNB_PICK(256, 64, 2)
+  SNB_PICK(64, 16, 4)
+  SNB_PICK(64, 32, 4)
+  SNB_PICK(128, 16, 4)
+  SNB_PICK(128, 32, 4)
+  SNB_PICK(256, 16, 4)
+  SNB_PICK(256, 32, 4)
 #undef SNB_PICK
   return false;
 }
@@ -745,13 +776,18 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_3X3_S2) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
   const bool is_convt = d->kind == SNB_CONVT_4X4_S2 || d->kind == SNB_CONVT_3X3_S2;
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
-  if (d->cin <= 0 || d->cin % 32 != 0) return fail(SNB_E_INVALID, "cin=%lld must be a positive multiple of 32", (long long)d->cin);
+  if (d->dtype != SNB_CONV_BF16 && d->dtype != SNB_CONV_TF32) return fail(SNB_E_INVALID, "unknown conv dtype %d", d->dtype);
+  const int eb = d->dtype == SNB_CONV_TF32 ? 4 : 2;     // element bytes of activations and weights
+  const int cmul = 64 / eb;                             // channel granularity: one 64-byte operand row
+  const int calign = 16 / eb;                           // slab strides are whole 16-byte vectors
+  if (d->cin <= 0 || d->cin % cmul != 0)
+    return fail(SNB_E_INVALID, "cin=%lld must be a positive multiple of %d", (long long)d->cin, cmul);
   if (d->cout <= 0 || d->cout % 32 != 0) return fail(SNB_E_INVALID, "cout=%lld must be a positive multiple of 32", (long long)d->cout);
-  if (d->in_cstride < d->cin || d->in_cstride % 8 != 0) return fail(SNB_E_INVALID, "bad in_cstride");
+  if (d->in_cstride < d->cin || d->in_cstride % calign != 0) return fail(SNB_E_INVALID, "bad in_cstride");
   const bool head = d->d_head_w != nullptr;
   if (head && (d->cout != 32 || is_convt || !d->d_head_out))
     return fail(SNB_E_INVALID, "fused head needs cout == 32, a plain conv and an output pointer");
-  if (!head && (!d->d_out || d->out_cstride < d->cout || d->out_cstride % 8 != 0))
+  if (!head && (!d->d_out || d->out_cstride < d->cout || d->out_cstride % calign != 0))
     return fail(SNB_E_INVALID, "bad output slab");
   if (!d->d_in || !d->d_weight || !d->d_bias) return fail(SNB_E_INVALID, "null tensor pointer");
   const bool up2x = d->out_upsample2x != 0;
@@ -759,7 +795,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     return fail(SNB_E_INVALID, "out_upsample2x applies to conv3x3 / conv1x1 without a fused head");
   const bool pool = d->d_pool_out != nullptr;
   if (pool && (head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
-               d->pool_cstride % 8 != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
+               d->pool_cstride % calign != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
     return fail(SNB_E_INVALID, "fused max-pool needs a conv3x3 without head, even h and w and a valid pooled slab");
   if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
       (reinterpret_cast<uintptr_t>(d->d_weight) & 15) || (reinterpret_cast<uintptr_t>(d->d_bias) & 15))
@@ -768,7 +804,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   const int mode = conv_mode();
   const int sms = sm_count();
   if (sms <= 0) return fail(SNB_E_CUDA, "no CUDA device");
-  const int bk = d->cin % 64 == 0 ? 64 : 32;
+  const int bk = (d->cin * eb) % 128 == 0 ? 128 / eb : 64 / eb;   // elements per K chunk: a 128- or 64-byte row
   int bn = 32;
   if (d->cout % 256 == 0) bn = 256;
   else if (d->cout % 128 == 0) bn = 128;
@@ -781,7 +817,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     if (e256 < 0.85 && e128 > e256 + 0.05) bn = 128;
   }
   KernelChoice kc;
-  if (!pick_kernel(bn, bk, head, &kc)) return fail(SNB_E_UNSUPPORTED, "no kernel for BN=%d BK=%d head=%d", bn, bk, (int)head);
+  if (!pick_kernel(bn, bk, head, eb, &kc)) return fail(SNB_E_UNSUPPORTED, "no kernel for BN=%d BK=%d head=%d eb=%d", bn, bk, (int)head, eb);
 
   snb_conv* c = new (std::nothrow) snb_conv();
   if (!c) return fail(SNB_E_INVALID, "out of host memory");
@@ -890,51 +926,51 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   p.out_h = static_cast<int32_t>(d->h);
 
   int rc;
+  const uint64_t E = (uint64_t)eb;
   {
     uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
-    uint64_t str[3] = {(uint64_t)d->in_cstride * 2, (uint64_t)d->w * d->in_cstride * 2,
-                       (uint64_t)d->h * d->w * d->in_cstride * 2};
+    uint64_t str[3] = {(uint64_t)d->in_cstride * E, (uint64_t)d->w * d->in_cstride * E,
+                       (uint64_t)d->h * d->w * d->in_cstride * E};
     uint32_t box[4] = {(uint32_t)bk, (uint32_t)(halo ? kHaloW : tile_w), (uint32_t)(halo ? kHaloH : tile_h), 1};
-    rc = encode_map(&p.map_a, const_cast<void*>(d->d_in), 4, dims, str, box, bk * 2);
+    rc = encode_map(&p.map_a, const_cast<void*>(d->d_in), 4, dims, str, box, bk * eb, eb);
     if (rc) { delete c; return rc; }
   }
   {
     uint64_t dims[3] = {(uint64_t)d->cin, (uint64_t)d->cout, (uint64_t)(p.n_phases * p.taps)};
-    uint64_t str[2] = {(uint64_t)d->cin * 2, (uint64_t)d->cout * d->cin * 2};
+    uint64_t str[2] = {(uint64_t)d->cin * E, (uint64_t)d->cout * d->cin * E};
     uint32_t box[3] = {(uint32_t)bk, (uint32_t)bn, 1};
-    rc = encode_map(&p.map_b, const_cast<void*>(d->d_weight), 3, dims, str, box, bk * 2);
+    rc = encode_map(&p.map_b, const_cast<void*>(d->d_weight), 3, dims, str, box, bk * eb, eb);
     if (rc) { delete c; return rc; }
     if (c->cluster == 2) {
       uint32_t half[3] = {(uint32_t)bk, (uint32_t)(bn / 2), 1};
-      rc = encode_map(&p.map_bh, const_cast<void*>(d->d_weight), 3, dims, str, half, bk * 2);
+      rc = encode_map(&p.map_bh, const_cast<void*>(d->d_weight), 3, dims, str, half, bk * eb, eb);
       if (rc) { delete c; return rc; }
     }
   }
+  const int cw = bn < 128 / eb ? bn : 128 / eb;   // channels per store chunk (ConvCfg::CW)
   if (!head) {
-    const int cw = bn < 64 ? bn : 64;
     const int s = (is_convt || up2x) ? 2 : 1;
     const int64_t ow = d->w * s, oh = d->h * s;
     p.up2x = up2x ? 1 : 0;
     for (int ph = 0; ph < (up2x ? 4 : p.n_phases); ++ph) {
       const int py = ph / 2, px = ph % 2;
-      char* base = static_cast<char*>(d->d_out) + ((int64_t)py * ow + px) * d->out_cstride * 2;
+      char* base = static_cast<char*>(d->d_out) + ((int64_t)py * ow + px) * d->out_cstride * eb;
       uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
-      uint64_t str[3] = {(uint64_t)s * d->out_cstride * 2, (uint64_t)s * ow * d->out_cstride * 2,
-                         (uint64_t)oh * ow * d->out_cstride * 2};
+      uint64_t str[3] = {(uint64_t)s * d->out_cstride * E, (uint64_t)s * ow * d->out_cstride * E,
+                         (uint64_t)oh * ow * d->out_cstride * E};
       uint32_t box[4] = {(uint32_t)cw, (uint32_t)tile_w, (uint32_t)tile_h, 1};
-      rc = encode_map(&p.map_d[ph], base, 4, dims, str, box, cw * 2);
+      rc = encode_map(&p.map_d[ph], base, 4, dims, str, box, cw * eb, eb);
       if (rc) { delete c; return rc; }
     }
   }
 
   p.pool = pool ? 1 : 0;
   if (pool) {
-    const int cw = bn < 64 ? bn : 64;
     uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)(d->w / 2), (uint64_t)(d->h / 2), (uint64_t)d->n};
-    uint64_t str[3] = {(uint64_t)d->pool_cstride * 2, (uint64_t)(d->w / 2) * d->pool_cstride * 2,
-                       (uint64_t)(d->h / 2) * (d->w / 2) * d->pool_cstride * 2};
+    uint64_t str[3] = {(uint64_t)d->pool_cstride * E, (uint64_t)(d->w / 2) * d->pool_cstride * E,
+                       (uint64_t)(d->h / 2) * (d->w / 2) * d->pool_cstride * E};
     uint32_t box[4] = {(uint32_t)cw, (uint32_t)(tile_w / 2), (uint32_t)(tile_h / 2), 1};
-    rc = encode_map(&p.map_p, d->d_pool_out, 4, dims, str, box, cw * 2);
+    rc = encode_map(&p.map_p, d->d_pool_out, 4, dims, str, box, cw * eb, eb);
     if (rc) { delete c; return rc; }
   }
 

@@ -132,11 +132,21 @@ __global__ void split_norm_nchw_kernel(SlicerGeom g, const uint8_t* __restrict__
 // 16-byte vector, so global stores are fully coalesced and every source pixel is fetched ~1.3x instead of 27x.
 constexpr int kPatchRY = 8;
 
-template <int channels>
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// F32 = false: bf16 rows (64 bytes per pixel);  F32 = true: float rows rounded to TF32 (128 bytes per pixel), the
+// first-layer operand of the TF32 ("fp32 mode") path.
+template <int channels, bool F32>
 __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, const uint8_t* __restrict__ src,
                                                                  const float* __restrict__ lut, int tta,
                                                                  uint4* __restrict__ dst, int64_t tile_begin) {
-  extern __shared__ uint2 s_px[];                 // [(RY+2)][T+2] pixels, 4 x bf16 each
+  extern __shared__ uint4 s_raw[];                // [(RY+2)][T+2] pixels: 4 x bf16 (8 bytes) or 4 x float (16 bytes) each
+  uint2* s_px = reinterpret_cast<uint2*>(s_raw);
+  float4* s_pf = reinterpret_cast<float4*>(s_raw);
   __shared__ float s_lut[4 * 256];
   const int T = (int)g.tile;
   const int strips = (T + kPatchRY - 1) / kPatchRY;
@@ -160,11 +170,34 @@ __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, c
 #pragma unroll
       for (int c = 0; c < channels; ++c) f[c] = s_lut[c * 256 + __ldg(px + c)];
     }
-    __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
-    s_px[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    if (F32) {
+      s_pf[i] = make_float4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+      s_px[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
   }
   __syncthreads();
   const int rows = min(kPatchRY, T - y0);
+  if (F32) {
+    // one thread = one pixel: 32 floats = eight 16-byte stores (k = tap * channels + c, zero beyond 9 * channels)
+    const float* s_el = reinterpret_cast<const float*>(s_raw);
+    for (int pix = threadIdx.x; pix < rows * T; pix += blockDim.x) {
+      const int y = pix / T, x = pix - y * T;
+      float el[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int tap = k / channels, c = k - tap * channels;
+        el[k] = tap < 9 ? s_el[((y + tap / 3) * PW + x + tap % 3) * 4 + c] : 0.f;
+      }
+      uint4* o = dst + ((t * T + y0 + y) * (int64_t)T + x) * 8;
+#pragma unroll
+      for (int qd = 0; qd < 8; ++qd)
+        o[qd] = make_uint4(__float_as_uint(el[qd * 4]), __float_as_uint(el[qd * 4 + 1]), __float_as_uint(el[qd * 4 + 2]),
+                           __float_as_uint(el[qd * 4 + 3]));
+    }
+    return;
+  }
   if (channels == 3) {
     // one thread = one pixel: 9 neighbour loads (8 bytes each), register shuffles, four 16-byte stores (64 contiguous bytes)
     for (int pix = threadIdx.x; pix < rows * T; pix += blockDim.x) {
@@ -205,27 +238,36 @@ __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, c
   }
 }
 
+// one thread = one 16-byte vector of a pixel's patch row: 8 bf16 (4 vectors per pixel) or 4 TF32-rounded floats (8)
+template <bool F32>
 __global__ void nchw_to_patch32_kernel(const float* __restrict__ src, int channels, int H, int W,
                                        uint4* __restrict__ dst, int64_t total) {
+  constexpr int VPP = F32 ? 8 : 4;     // vectors per pixel
+  constexpr int EPV = F32 ? 4 : 8;     // elements per vector
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int qd = (int)(i & 3);
-    int64_t r = i >> 2;
+    const int qd = (int)(i % VPP);
+    int64_t r = i / VPP;
     const int x = (int)(r % W); r /= W;
     const int y = (int)(r % H);
     const int64_t n = r / H;
     const float* img = src + n * channels * (int64_t)H * W;
     float f[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = qd * 8 + e;
+    for (int e = 0; e < EPV; ++e) {
+      const int k = qd * EPV + e;
       const int tap = k / channels, c = k - tap * channels;
       const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
       f[e] = (tap < 9 && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((int64_t)c * H + yy) * W + xx) : 0.f;
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-    dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                        *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    if (F32) {
+      dst[i] = make_uint4(__float_as_uint(to_tf32(f[0])), __float_as_uint(to_tf32(f[1])), __float_as_uint(to_tf32(f[2])),
+                          __float_as_uint(to_tf32(f[3])));
+    } else {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+      dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                          *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    }
   }
 }
 
@@ -509,24 +551,31 @@ extern "C" int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int6
     const int64_t total = tile_count * channels * T * T;
     split_norm_nchw_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
         s->g, d_src, d_lut, (int)channels, tta, static_cast<float*>(d_dst), tile_begin, total);
-  } else if (layout == SNB_LAYOUT_PATCH32) {
+  } else if (layout == SNB_LAYOUT_PATCH32 || layout == SNB_LAYOUT_PATCH32_F32) {
+    const bool f32 = layout == SNB_LAYOUT_PATCH32_F32;
     if (channels > 3) return fail(SNB_E_INVALID, "PATCH32 holds 9 taps x <=3 channels");
     if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(SNB_E_INVALID, "PATCH32 destination must be 16-byte aligned");
     const int strips = (int)((T + kPatchRY - 1) / kPatchRY);
-    const size_t smem = (size_t)(kPatchRY + 2) * (T + 2) * sizeof(uint2);
+    const size_t smem = (size_t)(kPatchRY + 2) * (T + 2) * (f32 ? sizeof(float4) : sizeof(uint2));
     if (smem > 200 * 1024) return fail(SNB_E_UNSUPPORTED, "tile size %lld too large for the PATCH32 split", (long long)T);
     if (tile_count * strips > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "too many strips");
-#define SNB_SPLIT_P32(C)                                                                                          \
+#define SNB_SPLIT_P32(C, F)                                                                                       \
   do {                                                                                                            \
     if (smem > 48 * 1024)                                                                                         \
-      SNB_CUDA_CHECK(cudaFuncSetAttribute(split_norm_patch32_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      SNB_CUDA_CHECK(cudaFuncSetAttribute(split_norm_patch32_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                            \
-    split_norm_patch32_kernel<C><<<(unsigned)(tile_count * strips), 256, smem, as_stream(stream)>>>(              \
+    split_norm_patch32_kernel<C, F><<<(unsigned)(tile_count * strips), 256, smem, as_stream(stream)>>>(           \
         s->g, d_src, d_lut, tta, static_cast<uint4*>(d_dst), tile_begin);                                         \
   } while (0)
-    if (channels == 3) SNB_SPLIT_P32(3);
-    else if (channels == 2) SNB_SPLIT_P32(2);
-    else SNB_SPLIT_P32(1);
+    if (f32) {
+      if (channels == 3) SNB_SPLIT_P32(3, true);
+      else if (channels == 2) SNB_SPLIT_P32(2, true);
+      else SNB_SPLIT_P32(1, true);
+    } else {
+      if (channels == 3) SNB_SPLIT_P32(3, false);
+      else if (channels == 2) SNB_SPLIT_P32(2, false);
+      else SNB_SPLIT_P32(1, false);
+    }
 #undef SNB_SPLIT_P32
   } else {
     return fail(SNB_E_INVALID, "unknown layout %d", layout);
@@ -536,14 +585,18 @@ extern "C" int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int6
 }
 
 extern "C" int snb_nchw_f32_to_patch32(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w,
-                                       void* d_dst, void* stream) {
+                                       void* d_dst, int out_f32, void* stream) {
   if (!d_src || !d_dst) return fail(SNB_E_INVALID, "snb_nchw_f32_to_patch32: null argument");
   if (channels < 1 || channels > 3) return fail(SNB_E_INVALID, "PATCH32 holds 9 taps x <=3 channels");
   if (n <= 0 || h <= 0 || w <= 0) return fail(SNB_E_INVALID, "bad shape");
   if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(SNB_E_INVALID, "destination must be 16-byte aligned");
-  const int64_t total = n * h * w * 4;
-  nchw_to_patch32_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_src, (int)channels, (int)h, (int)w,
-                                                                               static_cast<uint4*>(d_dst), total);
+  const int64_t total = n * h * w * (out_f32 ? 8 : 4);
+  if (out_f32)
+    nchw_to_patch32_kernel<true><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_src, (int)channels, (int)h, (int)w,
+                                                                                       static_cast<uint4*>(d_dst), total);
+  else
+    nchw_to_patch32_kernel<false><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_src, (int)channels, (int)h, (int)w,
+                                                                                        static_cast<uint4*>(d_dst), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

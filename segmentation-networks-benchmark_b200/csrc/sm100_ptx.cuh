@@ -168,6 +168,36 @@ __device__ __forceinline__ void umma_bf16_ss(uint64_t adesc, uint64_t bdesc, uin
       : "memory");
 }
 
+// same with fp32 operands read as TF32 (K = 8 elements = 32 bytes per instruction)
+__device__ __forceinline__ void umma_tf32_ss(uint64_t adesc, uint64_t bdesc, uint32_t tmem_d, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// EB = operand element bytes: 2 -> bf16 (kind::f16), 4 -> fp32 storage consumed as TF32 (kind::tf32)
+template <int EB>
+__device__ __forceinline__ void umma_ss(uint64_t adesc, uint64_t bdesc, uint32_t tmem_d, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (EB == 2) umma_bf16_ss(adesc, bdesc, tmem_d, idesc, accumulate);
+  else umma_tf32_ss(adesc, bdesc, tmem_d, idesc, accumulate);
+}
+
+// round-to-nearest fp32 -> tf32 (10-bit mantissa, low 13 bits cleared): stored activations are then exactly what
+// the tensor core consumes (it ignores the low mantissa bits)
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // arrives (count 1) on the mbarrier once all previously issued MMAs of this thread have completed;
 // implies tcgen05.fence::before_thread_sync
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -228,6 +258,12 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   d |= 1ull << 46;                                   // descriptor version (sm_100)
   d |= layout << 61;
   return d;
+}
+
+// Instruction descriptor with A/B both K-major and fp32 accumulation; fmt: 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major) and fp32 accumulation.

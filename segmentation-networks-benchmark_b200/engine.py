@@ -14,24 +14,39 @@ import torch
 from . import _native as N
 
 
+# ------------------------------------------------------------------------------------------- precision
+PRECISIONS = {"bf16": torch.bfloat16, "tf32": torch.float32}
+
+
+def round_tf32(t):
+    """fp32 -> nearest TF32 value (10-bit mantissa, ties away from zero like cvt.rna.tf32.f32), still stored as fp32."""
+    bits = t.detach().float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def to_storage(t, dtype):
+    """Weights in their device storage type: bf16, or fp32 rounded to TF32 for the TF32 ("fp32 mode") path."""
+    return round_tf32(t) if dtype == torch.float32 else t.detach().to(torch.bfloat16)
+
+
 # ------------------------------------------------------------------------------------------- weight packing
-def pack_conv3x3(weight):
-    """nn.Conv2d weight [Cout, Cin, 3, 3] -> bf16 [9][Cout][Cin], tap = ky*3 + kx."""
+def pack_conv3x3(weight, dtype=torch.bfloat16):
+    """nn.Conv2d weight [Cout, Cin, 3, 3] -> [9][Cout][Cin] in `dtype`, tap = ky*3 + kx."""
     cout, cin = weight.shape[:2]
-    return weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).to(torch.bfloat16).contiguous()
+    return to_storage(weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin), dtype).contiguous()
 
 
-def pack_conv1x1(weight):
+def pack_conv1x1(weight, dtype=torch.bfloat16):
     cout, cin = weight.shape[:2]
-    return weight.detach().reshape(1, cout, cin).to(torch.bfloat16).contiguous()
+    return to_storage(weight.detach().reshape(1, cout, cin), dtype).contiguous()
 
 
-def pack_first_conv3x3(weight):
-    """First layer [Cout, C<=3, 3, 3] -> bf16 [1][Cout][32] matching the PATCH32 rows: k = (ky*3+kx)*C + c."""
+def pack_first_conv3x3(weight, dtype=torch.bfloat16):
+    """First layer [Cout, C<=3, 3, 3] -> [1][Cout][32] matching the PATCH32 rows: k = (ky*3+kx)*C + c."""
     cout, cin = weight.shape[:2]
     w = weight.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
-    out = torch.zeros((1, cout, 32), dtype=torch.bfloat16, device=weight.device)
-    out[0, :, :9 * cin] = w.to(torch.bfloat16)
+    out = torch.zeros((1, cout, 32), dtype=dtype, device=weight.device)
+    out[0, :, :9 * cin] = to_storage(w, dtype)
     return out.contiguous()
 
 
@@ -39,8 +54,8 @@ def pack_first_conv3x3(weight):
 _CONVT_K = ((1, 3), (0, 2))
 
 
-def pack_convT4x4(weight):
-    """nn.ConvTranspose2d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4] -> bf16 [4 phases * 4 taps][Cout][Cin]."""
+def pack_convT4x4(weight, dtype=torch.bfloat16):
+    """nn.ConvTranspose2d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4] -> [4 phases * 4 taps][Cout][Cin] in `dtype`."""
     cin, cout = weight.shape[:2]
     w = weight.detach()
     taps = []
@@ -49,16 +64,16 @@ def pack_convT4x4(weight):
             for ty in range(2):
                 for tx in range(2):
                     taps.append(w[:, :, _CONVT_K[py][ty], _CONVT_K[px][tx]].t())
-    return torch.stack(taps).to(torch.bfloat16).contiguous()
+    return to_storage(torch.stack(taps), dtype).contiguous()
 
 
 # --------------------------------------------------------------------------------------------------- slabs
 class Slab:
-    """NHWC bf16 buffer; `view(c0, c)` names a channel range (a concat slot)."""
+    """NHWC buffer (bf16, or fp32 in TF32 mode); `view(c0, c)` names a channel range (a concat slot)."""
 
-    def __init__(self, n, h, w, c, device):
+    def __init__(self, n, h, w, c, device, dtype=torch.bfloat16):
         self.n, self.h, self.w, self.c = n, h, w, c
-        self.t = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+        self.t = torch.empty((n, h, w, c), dtype=dtype, device=device)
 
     def view(self, c0=0, c=None):
         return SlabView(self, c0, self.c - c0 if c is None else c)
@@ -71,7 +86,7 @@ class SlabView:
 
     @property
     def ptr(self):
-        return self.slab.t.data_ptr() + 2 * self.c0
+        return self.slab.t.data_ptr() + self.slab.t.element_size() * self.c0
 
     @property
     def cstride(self):
@@ -88,6 +103,9 @@ class ConvOp:
         self.keep = (src, dst, weight, bias, head, pool_dst)
         d = N.ConvDesc()
         d.kind = kind
+        d.dtype = N.CONV_TF32 if src.slab.t.dtype == torch.float32 else N.CONV_BF16
+        if weight.dtype != src.slab.t.dtype:
+            raise ValueError("weights (%s) and activations (%s) must share the storage type" % (weight.dtype, src.slab.t.dtype))
         d.relu = 1 if relu else 0
         d.n, d.h, d.w = src.slab.n, src.slab.h, src.slab.w
         d.cin, d.in_cstride = src.c, src.cstride
@@ -133,7 +151,7 @@ class PoolOp:
     def __init__(self, src, dst):
         self.keep = (src, dst)
         s = src.slab
-        self.args = (N.c_vp(src.ptr), s.n, s.h, s.w, src.c, src.cstride, N.c_vp(dst.ptr), dst.cstride)
+        self.args = (N.c_vp(src.ptr), s.n, s.h, s.w, src.c, src.cstride, N.c_vp(dst.ptr), dst.cstride, s.t.element_size())
         self.flops = 0.0
         self.launches = 1
 
@@ -148,18 +166,19 @@ class VGGUNetPlan:
     decs: [center, dec5, dec4, dec3, dec2] as (conv_w, conv_b, convT_w, convT_b); dec1 = (w, b); final = (w, b).
     """
 
-    def __init__(self, enc, decs, dec1, final, n, h, w, device, sigmoid):
+    def __init__(self, enc, decs, dec1, final, n, h, w, device, sigmoid, dtype=torch.bfloat16):
         if h % 32 or w % 32:
             raise ValueError("height and width must be multiples of 32 (five 2x2 poolings)")
         if final[0].shape[0] != 1 or final[0].shape[1] != 32 or dec1[0].shape[0] != 32:
             raise NotImplementedError("fused head expects num_classes == 1 and num_filters == 32")
         self.n, self.h, self.w = n, h, w
         self.device = device
+        self.dtype = dtype
         self.ops = []
         # SNB_CONV_MODE=0 (tap-mode A/B runs) has no fused pooling; SNB_FUSE_POOL=0 keeps the separate kernel
         fuse_pool = os.environ.get("SNB_CONV_MODE", "3") != "0" and os.environ.get("SNB_FUSE_POOL", "1") != "0"
         f32 = lambda b: b.detach().float().contiguous()
-        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device, dtype)
 
         # concat slabs: [decoder output | encoder skip], torch.cat([dec, conv], 1) order
         skip_c = [st[-1][0].shape[0] for st in enc]                # 64, 128, 256, 512, 512
@@ -183,9 +202,9 @@ class VGGUNetPlan:
                 pooled = S(hh // 2, ww // 2, cout).view() if last else None
                 fuse = pooled is not None and fuse_pool and not (s == 0 and li == 0)
                 if s == 0 and li == 0:
-                    self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt), f32(bs)))
+                    self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt, dtype), f32(bs)))
                 else:
-                    self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt), f32(bs),
+                    self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt, dtype), f32(bs),
                                            pool_dst=pooled if fuse else None))
                 cur = dst
             if not fuse:
@@ -198,14 +217,14 @@ class VGGUNetPlan:
             hh, ww = h >> s, w >> s
             src = cur if i == 0 else slabs[s].view()
             mid = S(hh, ww, cw.shape[0]).view()
-            self.ops.append(ConvOp(N.CONV_3X3, src, mid, pack_conv3x3(cw), f32(cb)))
+            self.ops.append(ConvOp(N.CONV_3X3, src, mid, pack_conv3x3(cw, dtype), f32(cb)))
             dst = slabs[s - 1].view(0, tw.shape[1])
-            self.ops.append(ConvOp(N.CONVT_4X4_S2, mid, dst, pack_convT4x4(tw), f32(tb)))
+            self.ops.append(ConvOp(N.CONVT_4X4_S2, mid, dst, pack_convT4x4(tw, dtype), f32(tb)))
 
         self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
         head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid,
                 self.out)
-        self.ops.append(ConvOp(N.CONV_3X3, slabs[0].view(), None, pack_conv3x3(dec1[0]), f32(dec1[1]), head=head))
+        self.ops.append(ConvOp(N.CONV_3X3, slabs[0].view(), None, pack_conv3x3(dec1[0], dtype), f32(dec1[1]), head=head))
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
 
@@ -213,7 +232,8 @@ class VGGUNetPlan:
         """float [n,3,h,w] CUDA tensor -> first-layer operand rows."""
         x = x.contiguous()
         N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), x.shape[0], x.shape[1], x.shape[2], x.shape[3],
-                                                N.c_vp(self.x_patch.t.data_ptr()), N.stream_ptr()))
+                                                N.c_vp(self.x_patch.t.data_ptr()),
+                                                1 if self.x_patch.t.dtype == torch.float32 else 0, N.stream_ptr()))
 
     def run(self):
         """Enqueue the whole forward on the current stream; result lands in self.out [n,h,w] float32."""
@@ -241,7 +261,8 @@ class ZFUNetPlan:
     up_conv_28, up_conv_56, up_conv_112, up_conv_224), each ((w1, b1, bn1), (w2, b2, bn2)); final = (w, b).
     """
 
-    def __init__(self, blocks, final, n, h, w, device, sigmoid):
+    def __init__(self, blocks, final, n, h, w, device, sigmoid, dtype=torch.bfloat16):
+        self.dtype = dtype
         if h % 32 or w % 32:
             raise ValueError("height and width must be multiples of 32 (five 2x2 poolings)")
         filters = blocks[0][0][0].shape[0]
@@ -249,7 +270,7 @@ class ZFUNetPlan:
             raise NotImplementedError("fused head expects num_classes == 1 and filters == 32")
         self.n, self.h, self.w, self.device = n, h, w, device
         self.ops = []
-        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device, dtype)
         enc_c = [blocks[i][1][0].shape[0] for i in range(5)]          # 32, 64, 128, 256, 512
         up_c = [blocks[5][1][0].shape[0]] + [blocks[6 + i][1][0].shape[0] for i in range(4)]  # channels unpooled into level 4..0
         # concat slabs per level: [unpool(deeper) | encoder skip]  (torch.cat([self.unpool(..), conv_X], dim=1))
@@ -259,9 +280,9 @@ class ZFUNetPlan:
         def conv(src, dst, layer, first=False, **kw):
             wt, bs = fold_bn(*layer)
             if first:
-                self.ops.append(ConvOp(N.CONV_1X1, src, dst, pack_first_conv3x3(wt), bs.contiguous(), **kw))
+                self.ops.append(ConvOp(N.CONV_1X1, src, dst, pack_first_conv3x3(wt, dtype), bs.contiguous(), **kw))
             else:
-                self.ops.append(ConvOp(N.CONV_3X3, src, dst, pack_conv3x3(wt), bs.contiguous(), **kw))
+                self.ops.append(ConvOp(N.CONV_3X3, src, dst, pack_conv3x3(wt, dtype), bs.contiguous(), **kw))
 
         self.x_patch = S(h, w, 32)
         cur = self.x_patch.view()
@@ -289,7 +310,7 @@ class ZFUNetPlan:
         wt, bs = fold_bn(*l2)
         head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid,
                 self.out)
-        self.ops.append(ConvOp(N.CONV_3X3, mid, None, pack_conv3x3(wt), bs.contiguous(), head=head))
+        self.ops.append(ConvOp(N.CONV_3X3, mid, None, pack_conv3x3(wt, dtype), bs.contiguous(), head=head))
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
 
@@ -366,6 +387,7 @@ class FCDenseNetPlan:
         if spec['final'][0].shape[0] != 1:
             raise NotImplementedError("fused head expects n_classes == 1")
         self.n, self.h, self.w, self.device = n, h, w, device
+        self.dtype = torch.bfloat16     # the pre-activation BN+ReLU kernel is bf16 only
         self.ops = []
         g = spec['growth']
         dev = device

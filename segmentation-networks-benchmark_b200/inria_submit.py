@@ -85,8 +85,9 @@ class TiledPredictor:
         for begin in range(self.tile_begin, self.tile_end, self.batch):
             count = min(self.batch, self.tile_end - begin)
             for v in range(self.views):
+                layout = N.LAYOUT_PATCH32_F32 if self.plan.x_patch.t.dtype == torch.float32 else N.LAYOUT_PATCH32
                 N.check(lib.snb_split_norm_u8(self.slicer.handle, N.ptr(d_image), self.channels, N.ptr(self.lut), v,
-                                              N.LAYOUT_PATCH32, N.c_vp(self.plan.x_patch.t.data_ptr()), begin, count, st))
+                                              layout, N.c_vp(self.plan.x_patch.t.data_ptr()), begin, count, st))
                 out = self.plan.run()
                 self.probs[begin:begin + count, v, :, :, 0].copy_(out[:count])
         if self.do_merge:
@@ -222,7 +223,7 @@ def predict_tiled(image, model, test_transform, patch_size, batch_size, tile_ste
         raise NotImplementedError("the fused pipeline takes the uint8 image (normalisation happens on the device)")
     cache = model.__dict__.setdefault('_tiled_predictors', {})
     key = (image.shape, patch_size, tile_step, batch_size, tta, weight, tuple(norm.mean), tuple(norm.std), norm.scale,
-           model._stamp())
+           getattr(model, 'precision', 'bf16'), model._stamp())
     if key not in cache:
         cache.clear()
         cache[key] = TiledPredictor(model, image.shape, patch_size, tile_step, batch_size, weight, tta, norm)

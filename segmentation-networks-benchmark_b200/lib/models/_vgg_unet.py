@@ -4,7 +4,7 @@ import torch
 from torch import nn
 
 from ... import _native as N
-from ...engine import VGGUNetPlan
+from ...engine import PRECISIONS, VGGUNetPlan
 
 
 def conv3x3(in_, out):
@@ -53,7 +53,18 @@ def vgg_features(cfg):
 
 
 class VGGUNetBase(nn.Module):
-    """forward(x: float[N,3,H,W] cuda) -> logits float[N,1,H,W]; plans are cached per input shape."""
+    """forward(x: float[N,3,H,W] cuda) -> logits float[N,1,H,W]; plans are cached per input shape.
+
+    `precision` selects the arithmetic of the convolutions: 'bf16' (default; probabilities within 2e-2 of the fp32
+    reference) or 'tf32' (fp32 storage, TF32 tensor-core products, fp32 accumulation; within 1e-4)."""
+
+    precision = 'bf16'
+
+    def set_precision(self, precision):
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+        self.precision = precision
+        return self
 
     def _stages(self):
         raise NotImplementedError
@@ -71,7 +82,10 @@ class VGGUNetBase(nn.Module):
         if self.__dict__.get('_plan_stamp') != stamp:
             cache.clear()
             self.__dict__['_plan_stamp'] = stamp
-        key = (n, h, w, bool(sigmoid))
+        precision = getattr(self, 'precision', 'bf16')
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+        key = (n, h, w, bool(sigmoid), precision)
         if key not in cache:
             dev = next(self.parameters()).device
             if dev.type != 'cuda':
@@ -81,7 +95,8 @@ class VGGUNetBase(nn.Module):
                     for d in self._decoders()]
             with torch.no_grad():
                 cache[key] = VGGUNetPlan(enc, decs, (self.dec1.conv.weight, self.dec1.conv.bias),
-                                         (self.final.weight, self.final.bias), n, h, w, dev, sigmoid)
+                                         (self.final.weight, self.final.bias), n, h, w, dev, sigmoid,
+                                         PRECISIONS[precision])
         return cache[key]
 
     def forward(self, x):

@@ -8,7 +8,7 @@ import torch
 from torch import nn
 
 from ... import _native as N
-from ...engine import ZFUNetPlan
+from ...engine import PRECISIONS, ZFUNetPlan
 
 
 class _Conv3BN(nn.Module):
@@ -53,6 +53,14 @@ class ZF_UNET(nn.Module):
         self.up_conv_224 = _DoubleConvModule(2 * f + f, f, dropout_val, batch_norm)
         self.conv_final = nn.Conv2d(f, num_classes, 1)
 
+    precision = 'bf16'    # or 'tf32': fp32 storage + TF32 tensor-core products (probabilities within 1e-4)
+
+    def set_precision(self, precision):
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+        self.precision = precision
+        return self
+
     def _blocks(self):
         return [self.conv_224, self.conv_112, self.conv_56, self.conv_28, self.conv_14, self.conv_7, self.up_conv_14,
                 self.up_conv_28, self.up_conv_56, self.up_conv_112, self.up_conv_224]
@@ -68,14 +76,18 @@ class ZF_UNET(nn.Module):
         if self.__dict__.get('_plan_stamp') != stamp:
             cache.clear()
             self.__dict__['_plan_stamp'] = stamp
-        key = (n, h, w, bool(sigmoid))
+        precision = getattr(self, 'precision', 'bf16')
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+        key = (n, h, w, bool(sigmoid), precision)
         if key not in cache:
             dev = self.conv_final.weight.device
             if dev.type != 'cuda':
                 raise RuntimeError("ZF_UNET runs on CUDA devices only (no CPU fallback); call .cuda()")
             blocks = [(b.l1.folded(), b.l2.folded()) for b in self._blocks()]
             with torch.no_grad():
-                cache[key] = ZFUNetPlan(blocks, (self.conv_final.weight, self.conv_final.bias), n, h, w, dev, sigmoid)
+                cache[key] = ZFUNetPlan(blocks, (self.conv_final.weight, self.conv_final.bias), n, h, w, dev, sigmoid,
+                                        PRECISIONS[precision])
         return cache[key]
 
     def forward(self, x):

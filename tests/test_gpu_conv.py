@@ -85,7 +85,7 @@ def test_first_layer_as_patch_gemm(cuda):
     n, h, w = 2, 32, 48
     x = torch.randn((n, 3, h, w), device="cuda", generator=g)
     rows = E.Slab(n, h, w, 32, "cuda")
-    N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), n, 3, h, w, N.c_vp(rows.t.data_ptr()), N.stream_ptr()))
+    N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), n, 3, h, w, N.c_vp(rows.t.data_ptr()), 0, N.stream_ptr()))
     wt = torch.randn((64, 3, 3, 3), device="cuda", generator=g) * 0.2
     bias = torch.randn(64, device="cuda", generator=g)
     dst = E.Slab(n, h, w, 64, "cuda")
@@ -173,3 +173,80 @@ def test_fused_maxpool_epilogue(cuda, conv_mode, n, h, w, cin, cout):
     check(nchw(dst.view(32, cout)), want)
     # the pooled tensor is exactly the max-pool of what the kernel itself stored
     assert torch.equal(nchw(pooled.view()), F.max_pool2d(nchw(dst.view(32, cout)), 2, 2))
+
+
+# ------------------------------------------------------------------------------------------------ TF32 ("fp32 mode")
+def rand_slab_f32(n, h, w, c, gen):
+    s = E.Slab(n, h, w, c, "cuda", torch.float32)
+    s.t.copy_(E.round_tf32(torch.randn((n, h, w, c), device="cuda", generator=gen)))
+    return s
+
+
+def nchw32(view):
+    return view.torch().permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("kind,n,h,w,cin,cout", [
+    ("c3", 1, 16, 16, 32, 32), ("c3", 2, 32, 24, 64, 128), ("c3", 1, 16, 32, 48, 64), ("c3", 1, 24, 40, 128, 512),
+    ("ct", 1, 8, 16, 64, 64), ("ct", 2, 16, 16, 128, 32), ("ct", 1, 12, 20, 256, 256)])
+def test_tf32_convolutions(cuda, conv_mode, kind, n, h, w, cin, cout):
+    """fp32 storage + kind::tf32: operands are TF32-representable, so the only difference to torch fp32 is the
+    accumulation order (well inside the 1e-4 budget of the fp32 mode)."""
+    if conv_mode == 4:
+        pytest.skip("CTA pairs are built for bf16 only")
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    src = rand_slab_f32(n, h, w, cin, g)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    if kind == "c3":
+        dst = E.Slab(n, h, w, cout + 16, "cuda", torch.float32)
+        dst.t.zero_()
+        pooled = E.Slab(n, h // 2, w // 2, cout, "cuda", torch.float32)
+        wt = E.round_tf32(torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5)
+        fuse = conv_mode != 0
+        op = E.ConvOp(N.CONV_3X3, src.view(), dst.view(16, cout), E.pack_conv3x3(wt, torch.float32), bias,
+                      pool_dst=pooled.view() if fuse else None)
+        op(N.stream_ptr())
+        want = F.relu(F.conv2d(nchw32(src.view()), wt, bias, padding=1))
+        got = nchw32(dst.view(16, cout))
+        if fuse:
+            assert torch.equal(nchw32(pooled.view()), F.max_pool2d(got, 2, 2))
+        assert torch.count_nonzero(dst.t[..., :16]) == 0
+    else:
+        dst = E.Slab(n, 2 * h, 2 * w, cout, "cuda", torch.float32)
+        wt = E.round_tf32(torch.randn((cin, cout, 4, 4), device="cuda", generator=g) * (2.0 / (4 * cin)) ** 0.5)
+        op = E.ConvOp(N.CONVT_4X4_S2, src.view(), dst.view(), E.pack_convT4x4(wt, torch.float32), bias)
+        op(N.stream_ptr())
+        want = F.relu(F.conv_transpose2d(nchw32(src.view()), wt, bias, stride=2, padding=1))
+        got = nchw32(dst.view())
+    torch.cuda.synchronize()
+    # stored outputs are rounded to TF32 (2^-11 relative); the accumulation itself agrees to ~1e-6
+    assert (got - E.round_tf32(want)).abs().max().item() <= 1.5e-3 * want.abs().max().item()
+    assert (got - want).abs().max().item() <= 6e-4 * want.abs().max().item()
+
+
+def test_tf32_first_layer_and_head(cuda, conv_mode):
+    if conv_mode == 4:
+        pytest.skip("CTA pairs are built for bf16 only")
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(21)
+    n, h, w = 2, 32, 48
+    x = torch.randn((n, 3, h, w), device="cuda", generator=g)
+    rows = E.Slab(n, h, w, 32, "cuda", torch.float32)
+    N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), n, 3, h, w, N.c_vp(rows.t.data_ptr()), 1, N.stream_ptr()))
+    wt = E.round_tf32(torch.randn((64, 3, 3, 3), device="cuda", generator=g) * 0.2)
+    bias = torch.randn(64, device="cuda", generator=g)
+    dst = E.Slab(n, h, w, 64, "cuda", torch.float32)
+    E.ConvOp(N.CONV_1X1, rows.view(), dst.view(), E.pack_first_conv3x3(wt, torch.float32), bias)(N.stream_ptr())
+    want = F.relu(F.conv2d(E.round_tf32(x), wt, bias, padding=1))
+    assert (nchw32(dst.view()) - want).abs().max().item() <= 6e-4 * want.abs().max().item()
+    # fused 1x1 head on a 96 -> 32 conv
+    src = rand_slab_f32(n, h, w, 96, g)
+    w2 = E.round_tf32(torch.randn((32, 96, 3, 3), device="cuda", generator=g) * 0.05)
+    b2 = torch.randn(32, device="cuda", generator=g) * 0.1
+    hw = torch.randn(32, device="cuda", generator=g) * 0.3
+    out = torch.empty((n, h, w), device="cuda")
+    E.ConvOp(N.CONV_3X3, src.view(), None, E.pack_conv3x3(w2, torch.float32), b2, head=(hw, 0.125, True, out))(N.stream_ptr())
+    feat = F.relu(F.conv2d(nchw32(src.view()), w2, b2, padding=1))
+    want = torch.sigmoid((feat * hw.view(1, 32, 1, 1)).sum(1) + 0.125)
+    assert (out - want).abs().max().item() < 2e-6

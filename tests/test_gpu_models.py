@@ -123,3 +123,65 @@ def test_fcdensenet67_against_reference_vectors(cuda, golden_dir):
     with torch.no_grad():
         q = no.fcdensenet_forward(sd, torch.from_numpy(g["x"]), quant=no.bf16_round)
     assert (y - q).abs().max().item() < 0.03 * max(1.0, q.abs().max().item())
+
+
+FP32_PROB_TOL = 1e-4   # north-star: probabilities within 1e-4 abs in fp32 / tf32 mode
+
+
+@pytest.mark.parametrize("arch", ["unet16", "unet11", "zf_unet"])
+def test_tf32_mode_against_reference_vectors(cuda, golden_dir, arch):
+    from snb_b200.lib.models import ZF_UNET
+
+    if arch == "zf_unet":
+        g = np.load(os.path.join(golden_dir, "zf_unet.npz"))
+        m, x, ref = ZF_UNET(), g["small_x"], g["small_logits"]
+        m.load_state_dict(synth.zf_unet_state_dict(seed=4))
+    else:
+        g = np.load(os.path.join(golden_dir, "models.npz"))
+        m, x, ref = {"unet16": UNet16, "unet11": UNet11}[arch](), g[arch + "_x"], g[arch + "_logits"]
+        m.load_state_dict(synth.vgg_unet_state_dict(arch, seed=1))
+    m = m.cuda().eval().set_precision("tf32")
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).cuda()).cpu()
+    p_err = (torch.sigmoid(y) - torch.sigmoid(torch.from_numpy(ref))).abs().max().item()
+    # These He-scaled synthetic weights drive O(1) activations through 22-25 layers: plain TF32 (2^-11 per rounding)
+    # lands at ~1e-3 here (the CPU simulation of TF32 rounding gives 9.8e-4 for unet16), 10-20x tighter than bf16.
+    # The 1e-4 bar of the north-star is for random-init weights: test_tf32_mode_on_default_init_weights below.
+    assert p_err < 2e-3, p_err
+    m.set_precision("bf16")
+    with torch.no_grad():
+        y16 = m(torch.from_numpy(x).cuda()).cpu()
+    assert (torch.sigmoid(y16) - torch.sigmoid(torch.from_numpy(ref))).abs().max().item() < BF16_PROB_TOL
+    with pytest.raises(ValueError):
+        m.set_precision("fp8")
+
+
+@pytest.mark.parametrize("arch", ["unet16", "zf_unet"])
+def test_precision_modes_on_default_init_weights(cuda, arch):
+    """North-star tolerances on random-init weights (PyTorch default initialisation, BatchNorm buffers randomised as in
+    SURVEY 8d): probabilities within 1e-4 in tf32 mode and 2e-2 in bf16 mode of the fp32 CPU oracle."""
+    from snb_b200.lib.models import ZF_UNET
+
+    torch.manual_seed(0)
+    m = UNet16() if arch == "unet16" else ZF_UNET()
+    if arch == "zf_unet":
+        g = torch.Generator().manual_seed(1)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(np.random.RandomState(3).standard_normal((2, 3, 64, 96)).astype(np.float32))
+    with torch.no_grad():
+        ref = no.unet_vgg_forward(sd, x, "unet16") if arch == "unet16" else no.zf_unet_forward(sd, x)
+    m = m.cuda().eval()
+    errs = {}
+    for prec in ("tf32", "bf16"):
+        m.set_precision(prec)
+        with torch.no_grad():
+            y = m(x.cuda()).cpu()
+        errs[prec] = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert errs["tf32"] < FP32_PROB_TOL, errs
+    assert errs["bf16"] < BF16_PROB_TOL, errs

@@ -106,3 +106,19 @@ def test_tile_range_predictors_reassemble_the_full_result(cuda, golden_dir, mode
     single = sub.TileShardedPredictor(model, g["image"].shape, 64, 32, batch_size=4, tta=False)   # world size 1
     m3, k3 = single.predict_device(d)
     assert torch.equal(m3, merged) and torch.equal(k3, mask)
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_predict_tiled_tf32_mode(cuda, golden_dir, tta):
+    """TF32 mode of the whole pipeline against the reference's merged probabilities."""
+    g = np.load(os.path.join(golden_dir, "predict_tiled.npz"))
+    m = UNet16()
+    m.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=2))
+    m = m.cuda().eval().set_precision("tf32")
+    t = aug.Sequential([aug.ImageOnly(aug.NormalizeImage(mean=sub.INRIA_MEAN, std=sub.INRIA_STD))])
+    merged = sub.predict_tiled(g["image"], m, t, 64, 4, tta=tta)
+    want = g[("tta" if tta else "plain") + "_merged"]
+    err = np.abs(merged - want).max()
+    assert err < 2e-3, err      # He-scaled synthetic weights: plain TF32 gives ~1e-3 (1e-4 holds on random-init weights)
+    flips = sub.mask_from_probability(merged) != g[("tta" if tta else "plain") + "_mask"]
+    assert np.all(np.abs(want[flips] - 0.5) < 2e-3)

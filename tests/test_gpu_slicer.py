@@ -127,7 +127,7 @@ def test_split_norm_layouts(cuda, tta):
     assert torch.equal(rows.cpu().float(), want_rows.to(torch.bfloat16).float())
     # nn.Module entry: NCHW fp32 -> PATCH32
     rows2 = torch.empty_like(rows)
-    N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(out), n, 3, T, T, N.ptr(rows2), N.stream_ptr()))
+    N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(out), n, 3, T, T, N.ptr(rows2), 0, N.stream_ptr()))
     assert torch.equal(rows2, rows)
 
 
