@@ -141,6 +141,11 @@ typedef struct snb_conv_desc {
   int64_t pool_cstride;  /* pixel stride of the pooled slab, in channels                    */
   /* nn.Upsample(scale_factor=2) (nearest) fused into the store: d_out is then a slab of [n][2h][2w] pixels and every
    * output pixel is written to its 2x2 block (lib/models/zf_unet.py:42,78-90); conv3x3 / conv1x1 only */
+  /* optional pre-activation of the INPUT, y = max(x * scale[c] + shift[c], 0) per input channel, applied inside the
+   * kernel to the operand tiles before the multiply (FCDenseNet's per-consumer BatchNorm2d(eval) + ReLU,
+   * lib/models/tiramisu.py:12-13); the conv's zero padding applies after it.  bf16 conv3x3 with cout == 32 only */
+  const float* d_pre_scale; /* float[cin] or NULL                                           */
+  const float* d_pre_shift; /* float[cin]                                                   */
   int32_t out_upsample2x;
   int32_t dtype;         /* SNB_CONV_BF16 / SNB_CONV_TF32: element type of d_in, d_out, d_pool_out and d_weight
                             (bias and the head stay float); channel counts are multiples of 64 bytes / element size */

@@ -51,6 +51,8 @@ class ConvDesc(ctypes.Structure):
         ("d_head_out", c_vp),
         ("d_pool_out", c_vp),
         ("pool_cstride", c_i64),
+        ("d_pre_scale", c_vp),
+        ("d_pre_shift", c_vp),
         ("out_upsample2x", ctypes.c_int32),
         ("dtype", ctypes.c_int32),
     ]

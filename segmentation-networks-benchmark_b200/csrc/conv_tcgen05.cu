@@ -66,6 +66,8 @@ struct alignas(64) ConvParams {
   const float* bias;
   const float* head_w;
   float* head_out;
+  const float* pre_scale;          // optional pre-activation y = relu(x * scale[c] + shift[c]) applied to the A operand
+  const float* pre_shift;
   int8_t tap_dy[kMaxPhases][kMaxTaps];
   int8_t tap_dx[kMaxPhases][kMaxTaps];
 };
@@ -428,8 +430,14 @@ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
 // CL = 2 runs CTA pairs (thread-block cluster of 2) on two spatial tiles of the same N tile: each CTA fetches half of
 // every weight box and TMA-multicasts it into both CTAs' shared memory, halving the L2->SM weight traffic that
 // bounds the large layers (32 KB per tap per CTA at BN=256 otherwise).
-template <int BN, int BK, bool HEAD, int TAPS, int NPH, int CL, int EB>
-__global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+//
+// PRE = true adds eight "prologue" warps (8-15) that rewrite every halo stage in place after TMA lands it and before
+// the MMA reads it: y = relu(x * scale[c] + shift[c]) per input channel, zero outside the image (the convolution's
+// zero padding applies AFTER the pre-activation).  This is FCDenseNet's per-consumer BatchNorm+ReLU
+// (lib/models/tiramisu.py:12-13) fused into the operand path instead of a separate pass over the slab.
+template <int BN, int BK, bool HEAD, int TAPS, int NPH, int CL, int EB, bool PRE = false>
+__global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!PRE || (EB == 2 && NPH == 1 && CL == 1), "the fused pre-activation is built for bf16 conv3x3");
   static_assert(CL == 1 || (CL == 2 && NPH == 1 && !HEAD && BN >= 128), "CTA pairs are for the streamed-weight layers");
   using Cfg = ConvCfg<BN, BK, EB>;
   static_assert(NPH == 1 || (NPH == 4 && TAPS == 4 && !HEAD), "phase fusion is for ConvTranspose");
@@ -454,7 +462,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   uint64_t* b_empty = b_full + kMaxBStages;         // [kMaxBStages]
   uint64_t* tmem_full = b_empty + kMaxBStages;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;             // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_ready = tmem_empty + 2;               // [kMaxAStages] stage rewritten by the prologue warps (PRE)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + kMaxAStages);
   uint32_t* s_aoff = tmem_ptr + 4;                  // [kMaxPhases][TAPS] descriptor start offsets (>>4) per tap
 
   const int warp = threadIdx.x >> 5;
@@ -471,6 +480,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     for (int i = 0; i < kMaxAStages; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+      mbar_init(&a_ready[i], 8);    // one arrival per prologue warp
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&b_full[i], 1);
@@ -580,7 +590,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * (NPH * BN);
         uint32_t b_lo = b_lo0 + static_cast<uint32_t>(ph0 * p.k_chunks * TAPS) * B_BYTES16;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(&a_full[sa], pa);
+          mbar_wait(PRE ? &a_ready[sa] : &a_full[sa], pa);
           tc05_fence_after();
           const uint32_t a_lo = a_lo0 + sa * A_STAGE16;
 #pragma unroll
@@ -609,7 +619,49 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         umma_commit(&tmem_full[acc]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (PRE && warp >= 8) {
+    // ------------------------------------------------------------------ prologue: pre-activation of the A operand
+    constexpr int CPR = SWZ / 16;            // 16-byte chunks (8 channels) per operand row
+    constexpr int RSTEP = 256 / CPR;         // rows covered by the 256 prologue threads per sweep
+    const int tt = threadIdx.x - 256;
+    const int jl = tt % CPR;                 // logical chunk = channels [8 jl, 8 jl + 8) of the K chunk
+    const int r0 = tt / CPR;
+    uint32_t s = 0, par = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode(t);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const float4* sc4 = reinterpret_cast<const float4*>(p.pre_scale + kc * BK + jl * 8);
+        const float4* sh4 = reinterpret_cast<const float4*>(p.pre_shift + kc * BK + jl * 8);
+        const float4 s0 = __ldg(sc4), s1 = __ldg(sc4 + 1), b0 = __ldg(sh4), b1 = __ldg(sh4 + 1);
+        mbar_wait(&a_full[s], par);
+        uint8_t* base = smem_a + s * Cfg::HALO_STAGE_BYTES;
+#pragma unroll 3
+        for (int r = r0; r < kHaloRows; r += RSTEP) {
+          const int hy = r / kHaloW, hx = r - hy * kHaloW;
+          const bool inside = static_cast<unsigned>(tc.x0 - 1 + hx) < static_cast<unsigned>(p.out_w) &&
+                              static_cast<unsigned>(tc.y0 - 1 + hy) < static_cast<unsigned>(p.out_h);
+          const int phys = jl ^ (SWZ == 128 ? (r & 7) : ((r >> 1) & 3));   // the swizzle TMA applied to this row
+          uint4* ptr = reinterpret_cast<uint4*>(base + r * SWZ + (phys << 4));
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (inside) {
+            const uint4 v = *ptr;
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const float2 x0 = __bfloat1622float2(pv[0]), x1 = __bfloat1622float2(pv[1]);
+            const float2 x2 = __bfloat1622float2(pv[2]), x3 = __bfloat1622float2(pv[3]);
+            o.x = pack_bf16x2(fmaxf(fmaf(x0.x, s0.x, b0.x), 0.f), fmaxf(fmaf(x0.y, s0.y, b0.y), 0.f));
+            o.y = pack_bf16x2(fmaxf(fmaf(x1.x, s0.z, b0.z), 0.f), fmaxf(fmaf(x1.y, s0.w, b0.w), 0.f));
+            o.z = pack_bf16x2(fmaxf(fmaf(x2.x, s1.x, b1.x), 0.f), fmaxf(fmaf(x2.y, s1.y, b1.y), 0.f));
+            o.w = pack_bf16x2(fmaxf(fmaf(x3.x, s1.z, b1.z), 0.f), fmaxf(fmaf(x3.y, s1.w, b1.w), 0.f));
+          }
+          *ptr = o;
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
+        if (++s == static_cast<uint32_t>(p.a_stages)) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -682,6 +734,7 @@ struct KernelChoice {
   const void* fn_halo4f; // v2 kernel, ConvTranspose with the 4 phases fused into one tile (BN <= 64), or null
   const void* fn_pair9;  // v2 kernel in CTA pairs with multicast weights (BN >= 128), or null
   const void* fn_pair4;
+  const void* fn_pre9;   // v2 kernel, conv3x3 with the fused pre-activation prologue (BN = 32, bf16), or null
   int smem;              // v1 dynamic smem
   int bn, bk;
   int halo_stage_bytes, b_bytes, out_bytes, pool_bytes;
@@ -701,13 +754,19 @@ static const void* pair_kernel() {
 }
 
 template <int BN, int BK, bool HEAD, int EB>
+static const void* pre_kernel() {
+  if constexpr (!HEAD && BN == 32 && EB == 2) return reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, false, 9, 1, 1, EB, true>);
+  else return nullptr;
+}
+
+template <int BN, int BK, bool HEAD, int EB>
 static KernelChoice choice() {
   using Cfg = ConvCfg<BN, BK, EB>;
   return KernelChoice{reinterpret_cast<const void*>(&conv_igemm_kernel<BN, BK, HEAD, EB>),
                       reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 9, 1, 1, EB>),
                       reinterpret_cast<const void*>(&conv_halo_kernel<BN, BK, HEAD, 4, 1, 1, EB>),
                       fused_phase_kernel<BN, BK, HEAD, EB>(), pair_kernel<BN, BK, HEAD, 9, EB>(),
-                      pair_kernel<BN, BK, HEAD, 4, EB>(), Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES,
+                      pair_kernel<BN, BK, HEAD, 4, EB>(), pre_kernel<BN, BK, HEAD, EB>(), Cfg::SMEM_BYTES, BN, BK, Cfg::HALO_STAGE_BYTES, Cfg::B_BYTES,
                       HEAD ? 0 : Cfg::OUT_BYTES, HEAD ? 0 : Cfg::POOL_BYTES};
 }
 
@@ -765,6 +824,7 @@ struct snb_conv {
   int smem;
   int grid;
   int cluster;   // 1, or 2 for the CTA-pair kernels
+  int threads;   // 256, or 512 with the pre-activation prologue warps
   double flops;
 };
 
@@ -793,6 +853,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   const bool up2x = d->out_upsample2x != 0;
   if (up2x && (head || is_convt))
     return fail(SNB_E_INVALID, "out_upsample2x applies to conv3x3 / conv1x1 without a fused head");
+  const bool pre = d->d_pre_scale != nullptr;
+  if (pre && (!d->d_pre_shift || d->kind != SNB_CONV_3X3 || head || eb != 2 || d->cout != 32 ||
+              (reinterpret_cast<uintptr_t>(d->d_pre_scale) & 15) || (reinterpret_cast<uintptr_t>(d->d_pre_shift) & 15)))
+    return fail(SNB_E_INVALID, "fused pre-activation needs a bf16 conv3x3 with cout == 32 and 16-byte aligned scale / shift");
   const bool pool = d->d_pool_out != nullptr;
   if (pool && (head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
                d->pool_cstride % calign != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
@@ -822,6 +886,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   snb_conv* c = new (std::nothrow) snb_conv();
   if (!c) return fail(SNB_E_INVALID, "out of host memory");
   c->cluster = 1;
+  c->threads = 256;
   ConvParams& p = c->params;
   std::memset(&p, 0, sizeof(p));
   c->kernel = kc;
@@ -853,6 +918,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
 
   // ---- main-loop variant and pipeline shape
   const bool halo = mode >= 1 && d->kind != SNB_CONV_1X1;
+  if (pre && (!halo || kc.fn_pre9 == nullptr)) {
+    delete c;
+    return fail(SNB_E_UNSUPPORTED, "fused pre-activation is only available in halo mode (SNB_CONV_MODE >= 1)");
+  }
   if (pool && !halo) {
     delete c;
     return fail(SNB_E_UNSUPPORTED, "fused max-pool is only available in halo mode (SNB_CONV_MODE >= 1)");
@@ -897,10 +966,14 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     p.b_stages = b_stages;
     p.bres = bres ? 1 : 0;
     c->fn = p.taps == 9 ? kc.fn_halo9 : (fuse_phases ? kc.fn_halo4f : kc.fn_halo4);
+    if (pre) {
+      c->fn = kc.fn_pre9;
+      c->threads = 512;
+    }
     // CTA pairs: streamed weights, an even number of spatial tiles per phase, and a pair kernel for this shape
     const int64_t m_tiles = (int64_t)d->n * ((d->h + tile_h - 1) / tile_h) * ((d->w + tile_w - 1) / tile_w);
     const void* fn_pair = p.taps == 9 ? kc.fn_pair9 : kc.fn_pair4;
-    if (mode >= 4 && !bres && !fuse_phases && fn_pair && m_tiles % 2 == 0 && sms >= 2) {
+    if (mode >= 4 && !bres && !fuse_phases && !pre && fn_pair && m_tiles % 2 == 0 && sms >= 2) {
       c->fn = fn_pair;
       c->cluster = 2;
       p.m_pairs = static_cast<int32_t>(m_tiles / 2);
@@ -922,6 +995,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   p.head_b = d->head_b;
   p.head_sigmoid = d->head_sigmoid;
   p.head_out = d->d_head_out;
+  p.pre_scale = d->d_pre_scale;
+  p.pre_shift = d->d_pre_shift;
   p.out_w = static_cast<int32_t>(d->w);
   p.out_h = static_cast<int32_t>(d->h);
 
@@ -994,7 +1069,7 @@ extern "C" int snb_conv_launch(const snb_conv* c, void* stream) {
   void* args[1] = {const_cast<ConvParams*>(&c->params)};
   cudaError_t e;
   if (c->cluster == 1) {
-    e = cudaLaunchKernel(c->fn, dim3(c->grid), dim3(256), args, c->smem, as_stream(stream));
+    e = cudaLaunchKernel(c->fn, dim3(c->grid), dim3(c->threads), args, c->smem, as_stream(stream));
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->grid);

@@ -99,8 +99,8 @@ class SlabView:
 class ConvOp:
     """One snb_conv handle; keeps every tensor it points at alive."""
 
-    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False):
-        self.keep = (src, dst, weight, bias, head, pool_dst)
+    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False, pre=None):
+        self.keep = (src, dst, weight, bias, head, pool_dst, pre)
         d = N.ConvDesc()
         d.kind = kind
         d.dtype = N.CONV_TF32 if src.slab.t.dtype == torch.float32 else N.CONV_BF16
@@ -124,6 +124,8 @@ class ConvOp:
             d.head_sigmoid = 1 if head_sigmoid else 0
             d.d_head_out = head_out.data_ptr()
         d.out_upsample2x = 1 if upsample2x else 0
+        if pre is not None:
+            d.d_pre_scale, d.d_pre_shift = pre[0].data_ptr(), pre[1].data_ptr()
         if pool_dst is not None:
             d.d_pool_out = pool_dst.ptr
             d.pool_cstride = pool_dst.cstride
@@ -387,7 +389,9 @@ class FCDenseNetPlan:
         if spec['final'][0].shape[0] != 1:
             raise NotImplementedError("fused head expects n_classes == 1")
         self.n, self.h, self.w, self.device = n, h, w, device
-        self.dtype = torch.bfloat16     # the pre-activation BN+ReLU kernel is bf16 only
+        self.dtype = torch.bfloat16     # the pre-activation BN+ReLU path is bf16 only
+        # SNB_FUSE_PRE=0 keeps the separate BN+ReLU pass (A/B runs); tap mode has no prologue warps
+        fuse_pre = os.environ.get("SNB_FUSE_PRE", "1") != "0" and os.environ.get("SNB_CONV_MODE", "3") != "0"
         self.ops = []
         g = spec['growth']
         dev = device
@@ -436,9 +440,14 @@ class FCDenseNetPlan:
             bn, wt, bs = layer
             cpad = _pad32(cin)
             sc, sh = bn_params(bn, cmap, cpad)
+            wp = pad_conv_weight(wt, cmap, cpad, 32)
+            if fuse_pre:
+                # BatchNorm+ReLU applied to the operand tiles inside the conv kernel: the slab is read once, in place
+                self.ops.append(ConvOp(N.CONV_3X3, slab.view(0, cpad), slab.view(out_off, 32), pack_conv3x3(wp),
+                                       padded_bias(bs, 32), relu=False, pre=(sc, sh)))
+                return
             z = scratch[lvl].view(0, cpad)
             self.ops.append(BnReluOp(slab.view(0, cpad), z, sc, sh))
-            wp = pad_conv_weight(wt, cmap, cpad, 32)
             self.ops.append(ConvOp(N.CONV_3X3, z, slab.view(out_off, 32), pack_conv3x3(wp), padded_bias(bs, 32), relu=False))
 
         # ---- first conv: 3 -> 48 (no activation), stored 64 wide

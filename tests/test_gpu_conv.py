@@ -250,3 +250,25 @@ def test_tf32_first_layer_and_head(cuda, conv_mode):
     feat = F.relu(F.conv2d(nchw32(src.view()), w2, b2, padding=1))
     want = torch.sigmoid((feat * hw.view(1, 32, 1, 1)).sum(1) + 0.125)
     assert (out - want).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("n,h,w,cin", [(1, 16, 16, 64), (2, 24, 40, 96), (1, 7, 7, 160), (3, 32, 16, 448)])
+def test_fused_preactivation_prologue(cuda, conv_mode, n, h, w, cin):
+    """conv3x3(relu(x * scale + shift)) with the pre-activation applied to the operand tiles inside the kernel
+    (FCDenseNet DenseLayer, lib/models/tiramisu.py:9-19); zero padding applies after the activation."""
+    if conv_mode == 0:
+        pytest.skip("tap mode has no prologue warps")
+    g = torch.Generator(device="cuda").manual_seed(cin)
+    src = rand_slab(n, h, w, cin + 32, g)                       # wider slab: the conv reads the first cin channels
+    dst = E.Slab(n, h, w, 32, "cuda")
+    wt = torch.randn((32, cin, 3, 3), device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(32, device="cuda", generator=g)
+    scale = torch.rand(cin, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cin, device="cuda", generator=g) * 0.3 + 0.2      # positive shifts make relu(shift) != 0 at the border
+    op = E.ConvOp(N.CONV_3X3, src.view(0, cin), dst.view(), E.pack_conv3x3(wt), bias, relu=False, pre=(scale, shift))
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    x = nchw(src.view(0, cin))
+    z = bf(F.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)))
+    want = F.conv2d(z, bf(wt), bias, padding=1)
+    check(nchw(dst.view()), want)
