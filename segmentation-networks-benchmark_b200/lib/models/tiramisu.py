@@ -11,43 +11,48 @@ from ... import _native as N
 from ...engine import FCDenseNetPlan
 
 
-class DenseLayer(nn.Sequential):
-    def __init__(self, in_channels, growth_rate):
-        super().__init__()
-        self.add_module('norm', nn.BatchNorm2d(in_channels))
-        self.add_module('relu', nn.ReLU(True))
-        self.add_module('conv', nn.Conv2d(in_channels, growth_rate, kernel_size=3, stride=1, padding=1, bias=True))
-        self.add_module('drop', nn.Dropout2d(0.2))
+def _named_sequential(cls_name, parts):
+    """nn.Sequential subclass instance whose children carry the reference's names ('norm', 'relu', 'conv', ...)."""
+    seq = type(cls_name, (nn.Sequential,), {})()
+    for name, module in parts:
+        seq.add_module(name, module)
+    return seq
+
+
+def DenseLayer(in_channels, growth_rate):
+    """BN -> ReLU -> conv3x3(in -> growth) -> Dropout2d(0.2)   (parameter holder; tiramisu.py:9-19)."""
+    return _named_sequential('DenseLayer', [
+        ('norm', nn.BatchNorm2d(in_channels)), ('relu', nn.ReLU(True)),
+        ('conv', nn.Conv2d(in_channels, growth_rate, kernel_size=3, stride=1, padding=1, bias=True)),
+        ('drop', nn.Dropout2d(0.2))])
+
+
+def TransitionDown(channels):
+    """BN -> ReLU -> conv1x1 -> Dropout2d(0.2) -> MaxPool2d(2)   (tiramisu.py:47-59)."""
+    return _named_sequential('TransitionDown', [
+        ('norm', nn.BatchNorm2d(num_features=channels)), ('relu', nn.ReLU(inplace=True)),
+        ('conv', nn.Conv2d(channels, channels, kernel_size=1, stride=1, padding=0, bias=True)),
+        ('drop', nn.Dropout2d(0.2)), ('maxpool', nn.MaxPool2d(2))])
 
 
 class DenseBlock(nn.Module):
+    """`layers[k]` sees the block input plus the k earlier outputs (tiramisu.py:22-44)."""
+
     def __init__(self, in_channels, growth_rate, n_layers, upsample=False):
         super().__init__()
         self.upsample = upsample
-        self.layers = nn.ModuleList([DenseLayer(in_channels + i * growth_rate, growth_rate) for i in range(n_layers)])
-
-
-class TransitionDown(nn.Sequential):
-    def __init__(self, in_channels):
-        super().__init__()
-        self.add_module('norm', nn.BatchNorm2d(num_features=in_channels))
-        self.add_module('relu', nn.ReLU(inplace=True))
-        self.add_module('conv', nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0, bias=True))
-        self.add_module('drop', nn.Dropout2d(0.2))
-        self.add_module('maxpool', nn.MaxPool2d(2))
+        widths = [in_channels + k * growth_rate for k in range(n_layers)]
+        self.layers = nn.ModuleList(DenseLayer(c, growth_rate) for c in widths)
 
 
 class TransitionUp(nn.Module):
     def __init__(self, in_channels, out_channels):
         super().__init__()
-        self.convTrans = nn.ConvTranspose2d(in_channels=in_channels, out_channels=out_channels, kernel_size=3, stride=2,
-                                            padding=0, bias=True)
+        self.convTrans = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=3, stride=2, padding=0, bias=True)
 
 
-class Bottleneck(nn.Sequential):
-    def __init__(self, in_channels, growth_rate, n_layers):
-        super().__init__()
-        self.add_module('bottleneck', DenseBlock(in_channels, growth_rate, n_layers, upsample=True))
+def Bottleneck(in_channels, growth_rate, n_layers):
+    return _named_sequential('Bottleneck', [('bottleneck', DenseBlock(in_channels, growth_rate, n_layers, upsample=True))])
 
 
 def _bn(m):
@@ -59,37 +64,28 @@ class FCDenseNet(nn.Module):
                  growth_rate=16, out_chans_first_conv=48, n_classes=12):
         super().__init__()
         self.num_classes = n_classes
-        self.down_blocks = down_blocks
-        self.up_blocks = up_blocks
-        self.growth_rate = growth_rate
-        skip_connection_channel_counts = []
-        self.add_module('firstconv', nn.Conv2d(in_channels=in_channels, out_channels=out_chans_first_conv, kernel_size=3,
-                                               stride=1, padding=1, bias=True))
-        cur = out_chans_first_conv
-        self.denseBlocksDown = nn.ModuleList([])
-        self.transDownBlocks = nn.ModuleList([])
-        for i in range(len(down_blocks)):
-            self.denseBlocksDown.append(DenseBlock(cur, growth_rate, down_blocks[i]))
-            cur += growth_rate * down_blocks[i]
-            skip_connection_channel_counts.insert(0, cur)
-            self.transDownBlocks.append(TransitionDown(cur))
-        self.add_module('bottleneck', Bottleneck(cur, growth_rate, bottleneck_layers))
-        prev = growth_rate * bottleneck_layers
-        cur += prev
-        self.transUpBlocks = nn.ModuleList([])
-        self.denseBlocksUp = nn.ModuleList([])
-        for i in range(len(up_blocks) - 1):
-            self.transUpBlocks.append(TransitionUp(prev, prev))
-            cur = prev + skip_connection_channel_counts[i]
-            self.denseBlocksUp.append(DenseBlock(cur, growth_rate, up_blocks[i], upsample=True))
-            prev = growth_rate * up_blocks[i]
-            cur += prev
-        self.transUpBlocks.append(TransitionUp(prev, prev))
-        cur = prev + skip_connection_channel_counts[-1]
-        self.denseBlocksUp.append(DenseBlock(cur, growth_rate, up_blocks[-1], upsample=False))
-        cur += growth_rate * up_blocks[-1]
-        self.finalConv = nn.Conv2d(in_channels=cur, out_channels=n_classes, kernel_size=1, stride=1, padding=0, bias=True)
-        self.softmax = nn.LogSoftmax(dim=1)
+        self.down_blocks, self.up_blocks, self.growth_rate = down_blocks, up_blocks, growth_rate
+        g = growth_rate
+
+        # channel schedule: widths entering each down block, the skips they leave, and what each TransitionUp carries
+        down_in, skips, c = [], [], out_chans_first_conv
+        for n_layers in down_blocks:
+            down_in.append(c)
+            c += g * n_layers
+            skips.append(c)
+        carried = [g * bottleneck_layers] + [g * n for n in up_blocks[:-1]]
+        up_in = [carried[i] + skips[-1 - i] for i in range(len(up_blocks))]
+
+        self.firstconv = nn.Conv2d(in_channels, out_chans_first_conv, kernel_size=3, stride=1, padding=1, bias=True)
+        self.denseBlocksDown = nn.ModuleList(DenseBlock(ci, g, n) for ci, n in zip(down_in, down_blocks))
+        self.transDownBlocks = nn.ModuleList(TransitionDown(sk) for sk in skips)
+        self.bottleneck = Bottleneck(skips[-1], g, bottleneck_layers)
+        self.transUpBlocks = nn.ModuleList(TransitionUp(cc, cc) for cc in carried)
+        last = len(up_blocks) - 1
+        self.denseBlocksUp = nn.ModuleList(DenseBlock(ci, g, n, upsample=(i != last))
+                                           for i, (ci, n) in enumerate(zip(up_in, up_blocks)))
+        self.finalConv = nn.Conv2d(up_in[-1] + g * up_blocks[-1], n_classes, kernel_size=1, stride=1, padding=0, bias=True)
+        self.softmax = nn.LogSoftmax(dim=1)     # defined, never applied by forward (as in the reference)
 
     def _spec(self):
         layer = lambda m: (_bn(m.norm), m.conv.weight, m.conv.bias)

@@ -20,13 +20,14 @@ class UNet11(VGGUNetBase):
         self.conv4 = nn.Sequential(e[11], self.relu, e[13], self.relu)
         self.conv5 = nn.Sequential(e[16], self.relu, e[18], self.relu)
 
-        self.center = DecoderBlock(256 + num_filters * 8, num_filters * 8 * 2, num_filters * 8, is_deconv=True)
-        self.dec5 = DecoderBlock(512 + num_filters * 8, num_filters * 8 * 2, num_filters * 8, is_deconv=True)
-        self.dec4 = DecoderBlock(512 + num_filters * 8, num_filters * 8 * 2, num_filters * 4, is_deconv=True)
-        self.dec3 = DecoderBlock(256 + num_filters * 4, num_filters * 4 * 2, num_filters * 2, is_deconv=True)
-        self.dec2 = DecoderBlock(128 + num_filters * 2, num_filters * 2 * 2, num_filters, is_deconv=True)
-        self.dec1 = ConvRelu(64 + num_filters, num_filters)
-        self.final = nn.Conv2d(num_filters, num_classes, kernel_size=1)
+        nf = num_filters
+        # (name, channels in, middle, out): decoder inputs are [previous decoder output | encoder skip]
+        for name, c_in, mid, out in [('center', 256 + nf * 8, nf * 16, nf * 8), ('dec5', 512 + nf * 8, nf * 16, nf * 8),
+                                     ('dec4', 512 + nf * 8, nf * 16, nf * 4), ('dec3', 256 + nf * 4, nf * 8, nf * 2),
+                                     ('dec2', 128 + nf * 2, nf * 4, nf)]:
+            setattr(self, name, DecoderBlock(c_in, mid, out, is_deconv=True))
+        self.dec1 = ConvRelu(64 + nf, nf)
+        self.final = nn.Conv2d(nf, num_classes, kernel_size=1)
 
     def _stages(self):
         e = self.encoder

@@ -26,13 +26,14 @@ class UNet16(VGGUNetBase):
         self.conv4 = nn.Sequential(e[17], self.relu, e[19], self.relu, e[21], self.relu)
         self.conv5 = nn.Sequential(e[24], self.relu, e[26], self.relu, e[28], self.relu)
 
-        self.center = DecoderBlock(512, num_filters * 8 * 2, num_filters * 8)
-        self.dec5 = DecoderBlock(512 + num_filters * 8, num_filters * 8 * 2, num_filters * 8)
-        self.dec4 = DecoderBlock(512 + num_filters * 8, num_filters * 8 * 2, num_filters * 8)
-        self.dec3 = DecoderBlock(256 + num_filters * 8, num_filters * 4 * 2, num_filters * 2)
-        self.dec2 = DecoderBlock(128 + num_filters * 2, num_filters * 2 * 2, num_filters)
-        self.dec1 = ConvRelu(64 + num_filters, num_filters)
-        self.final = nn.Conv2d(num_filters, num_classes, kernel_size=1)
+        nf = num_filters
+        # (name, channels in, middle, out): decoder inputs are [previous decoder output | encoder skip]
+        for name, c_in, mid, out in [('center', 512, nf * 16, nf * 8), ('dec5', 512 + nf * 8, nf * 16, nf * 8),
+                                     ('dec4', 512 + nf * 8, nf * 16, nf * 8), ('dec3', 256 + nf * 8, nf * 8, nf * 2),
+                                     ('dec2', 128 + nf * 2, nf * 4, nf)]:
+            setattr(self, name, DecoderBlock(c_in, mid, out))
+        self.dec1 = ConvRelu(64 + nf, nf)
+        self.final = nn.Conv2d(nf, num_classes, kernel_size=1)
 
     def _stages(self):
         e = self.encoder

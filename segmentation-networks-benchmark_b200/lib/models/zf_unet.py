@@ -40,17 +40,15 @@ class ZF_UNET(nn.Module):
         self.pool = nn.MaxPool2d(2)
         self.unpool = nn.Upsample(scale_factor=2)
         f = filters
-        self.conv_224 = _DoubleConvModule(input_channels, f, dropout_val, batch_norm)
-        self.conv_112 = _DoubleConvModule(f, 2 * f, dropout_val, batch_norm)
-        self.conv_56 = _DoubleConvModule(2 * f, 4 * f, dropout_val, batch_norm)
-        self.conv_28 = _DoubleConvModule(4 * f, 8 * f, dropout_val, batch_norm)
-        self.conv_14 = _DoubleConvModule(8 * f, 16 * f, dropout_val, batch_norm)
-        self.conv_7 = _DoubleConvModule(16 * f, 32 * f, dropout_val, batch_norm)
-        self.up_conv_14 = _DoubleConvModule(32 * f + 16 * f, 16 * f, dropout_val, batch_norm)
-        self.up_conv_28 = _DoubleConvModule(16 * f + 8 * f, 8 * f, dropout_val, batch_norm)
-        self.up_conv_56 = _DoubleConvModule(8 * f + 4 * f, 4 * f, dropout_val, batch_norm)
-        self.up_conv_112 = _DoubleConvModule(4 * f + 2 * f, 2 * f, dropout_val, batch_norm)
-        self.up_conv_224 = _DoubleConvModule(2 * f + f, f, dropout_val, batch_norm)
+        # (attribute name, input channels, output channels): encoder widths double per level, the decoder blocks
+        # consume [upsampled deeper features | skip] (lib/models/zf_unet.py:44-58 keeps these exact names)
+        table = [('conv_224', input_channels, f), ('conv_112', f, 2 * f), ('conv_56', 2 * f, 4 * f),
+                 ('conv_28', 4 * f, 8 * f), ('conv_14', 8 * f, 16 * f), ('conv_7', 16 * f, 32 * f)]
+        for level, name in enumerate(['up_conv_14', 'up_conv_28', 'up_conv_56', 'up_conv_112', 'up_conv_224']):
+            wide = (32 * f) >> level                      # channels arriving through the x2 upsampling
+            table.append((name, wide + wide // 2, wide // 2))
+        for name, c_in, c_out in table:
+            setattr(self, name, _DoubleConvModule(c_in, c_out, dropout_val, batch_norm))
         self.conv_final = nn.Conv2d(f, num_classes, 1)
 
     precision = 'bf16'    # or 'tf32': fp32 storage + TF32 tensor-core products (probabilities within 1e-4)
