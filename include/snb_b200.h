@@ -110,6 +110,9 @@ SNB_API int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, 
 #define SNB_CONV_3X3 0      /* k3 s1 p1: 1 phase x 9 taps, tap = ky*3+kx                     */
 #define SNB_CONV_1X1 1      /* k1: 1 phase x 1 tap                                           */
 #define SNB_CONVT_4X4_S2 2  /* ConvTranspose2d k4 s2 p1: 4 sub-pixel phases x 4 taps         */
+#define SNB_CONV_2X2 4       /* Conv2d k2 s1 p1: 4 taps (dy,dx in {-1,0}), output (h+1) x (w+1); also the body of a
+                               stride-2 conv3x3 after space-to-depth (lib/models/linknet.py:62, resnet34 via :39-48) */
+#define SNB_CONVT_3X3_S2_FULL 5 /* ConvTranspose2d k3 s2 p0 uncropped: output (2h+1) x (2w+1) (lib/models/linknet.py:58) */
 #define SNB_CONVT_3X3_S2 3  /* ConvTranspose2d k3 s2 p0 cropped to [0,2h) x [0,2w) (lib/models/tiramisu.py:62-90):
                                4 phases x 4 tap slots, unused slots carry zero weights       */
 
@@ -146,6 +149,15 @@ typedef struct snb_conv_desc {
    * lib/models/tiramisu.py:12-13); the conv's zero padding applies after it.  bf16 conv3x3 with cout == 32 only */
   const float* d_pre_scale; /* float[cin] or NULL                                           */
   const float* d_pre_shift; /* float[cin]                                                   */
+  /* epilogue extras of the ResNet / LinkNet blocks (lib/models/linknet.py:39-48,77-80): an activation slope
+   * (relu != 0: y = x > 0 ? x : act_slope * x, so 0 = ReLU, 0.01 = the InPlaceABN / nn.LeakyReLU default) and a residual
+   * tensor with the output's pixel grid, added before (res_after_act = 0, BasicBlock) or after the activation (skip) */
+  float act_slope;
+  int32_t res_after_act;
+  const void* d_residual;   /* same element type as d_out, first channel read, or NULL                */
+  int64_t res_cstride;
+  int32_t valid;            /* conv3x3: no padding, output (h-2) x (w-2) (lib/models/linknet.py:60); conv2x2: padding on
+                               top/left only, output h x w (a stride-2 conv3x3 after space-to-depth) */
   int32_t out_upsample2x;
   int32_t dtype;         /* SNB_CONV_BF16 / SNB_CONV_TF32: element type of d_in, d_out, d_pool_out and d_weight
                             (bias and the head stay float); channel counts are multiples of 64 bytes / element size */
@@ -162,6 +174,19 @@ SNB_API double snb_conv_flops(const snb_conv* c);
  * strides multiples of 16 bytes */
 SNB_API int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                    void* d_out, int64_t out_cstride, int elem_bytes, void* stream);
+
+/* ResNet-34 encoder helpers of LinkNet34 (lib/models/linknet.py:39-48), NHWC bf16 slabs, channels % 8 == 0:
+ *   snb_space_to_depth2: out[n][y][x][(py*2+px)*C + c] = in[n][2y+py][2x+px][c]   (h, w even) -- turns the stride-2
+ *                        conv3x3 / conv1x1 of a down-sampling BasicBlock into SNB_CONV_2X2 / SNB_CONV_1X1 launches
+ *   snb_maxpool3x3s2:    nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+ *   snb_stem7x7_rows:    float [n][C][h][w] -> bf16 rows [n][ceil(h/2)][ceil(w/2)][k_pad] of the stride-2 7x7 p3 stem,
+ *                        k = (ky*7+kx)*C + c, zero for k >= 49*C: the stem becomes a conv1x1 over these rows */
+SNB_API int snb_space_to_depth2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                        void* d_out, int64_t out_cstride, void* stream);
+SNB_API int snb_maxpool3x3s2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                     void* d_out, int64_t out_cstride, void* stream);
+SNB_API int snb_stem7x7_rows(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w, void* d_dst,
+                     int64_t k_pad, void* stream);
 
 /* Pre-activation BatchNorm2d(eval) + ReLU of FCDenseNet's DenseLayer / TransitionDown (lib/models/tiramisu.py:12-13,
  * 50-51): out[.., c] = max(in[.., c] * scale[c] + shift[c], 0) for c < channels, 0 for channels <= c < channels_pad

@@ -28,6 +28,31 @@ for name in ("tensorboardX", "matplotlib", "matplotlib.pyplot", "seaborn"):
     sys.modules.setdefault(name, types.ModuleType(name))
 collections.Iterable = collections.abc.Iterable
 
+def _install_inplace_abn_shim():
+    """Pure-torch stand-in for the un-vendored `inplace_abn` CUDA extension (mapillary/inplace_abn, no pinned version),
+    implementing the calls lib/modules/abn/functions.py makes on the eval path with that library's published forward:
+    y = (x - mean) / sqrt(var + eps) * (|weight| + eps) + bias, in place; leaky_relu in place."""
+    m = types.ModuleType("inplace_abn")
+
+    def forward(x, mean, var, weight, bias, affine, eps):
+        g = (weight.abs() + eps) if affine else torch.ones_like(mean)
+        b = bias if affine else torch.zeros_like(mean)
+        x.sub_(mean.view(1, -1, 1, 1)).div_(torch.sqrt(var.view(1, -1, 1, 1) + eps)).mul_(g.view(1, -1, 1, 1)).add_(b.view(1, -1, 1, 1))
+        return True
+
+    def leaky_relu_forward(x, slope):
+        x.copy_(torch.nn.functional.leaky_relu(x, slope))
+        return True
+
+    def mean_var(x):
+        return x.mean(dim=(0, 2, 3)), x.var(dim=(0, 2, 3), unbiased=False)
+
+    m.forward, m.leaky_relu_forward, m.mean_var = forward, leaky_relu_forward, mean_var
+    sys.modules["inplace_abn"] = m
+
+
+_install_inplace_abn_shim()
+
 from lib import augmentations as aug  # noqa: E402
 from lib import losses as ref_losses  # noqa: E402
 from lib import metrics as ref_metrics  # noqa: E402
@@ -37,6 +62,7 @@ from lib.models.unet11 import UNet11  # noqa: E402
 from lib.models.unet16 import UNet16  # noqa: E402
 from lib.models.zf_unet import ZF_UNET  # noqa: E402
 from lib.models.tiramisu import FCDenseNet67  # noqa: E402
+from lib.models.linknet import LinkNet34  # noqa: E402
 from lib.tiles import ImageSlicer, compute_patch_weight_loss  # noqa: E402
 from lib.train_utils import PRCurveMeter  # noqa: E402
 
@@ -210,6 +236,22 @@ def fcdensenet_vectors():
     return dict(params=int(sum(p.numel() for p in m.parameters())), logit_min=float(y.min()), logit_max=float(y.max()))
 
 
+def linknet34_vectors():
+    """LinkNet34 (eval mode; InPlaceABN through the pure-torch shim of the un-vendored backend: parity unpinned)."""
+    m = LinkNet34(pretrained=False)
+    sd = synth.linknet34_state_dict(seed=6)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.eval()
+    x = torch.from_numpy(np.random.RandomState(14).standard_normal((2, 3, 64, 96)).astype(np.float32))
+    x256 = torch.from_numpy(np.random.RandomState(15).standard_normal((1, 3, 256, 256)).astype(np.float32))
+    with torch.no_grad():
+        y, y256 = m(x).numpy(), m(x256).numpy()
+    np.savez_compressed(os.path.join(OUT, "linknet34.npz"), x=x.numpy(), logits=y, logits256=y256)
+    return dict(params=int(sum(p.numel() for p in m.parameters())), n_keys=len(m.state_dict()),
+                logit_min=float(y.min()), logit_max=float(y.max()))
+
+
 def predict_tiled_vector():
     """inria_submit.predict_tiled (:237-257) on CPU: same calls, without .cuda(); tile 64 / step 32, with and
     without D4 TTA, plus the submit threshold (:305)."""
@@ -246,7 +288,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(), fcdensenet67=fcdensenet_vectors(),
+    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(), fcdensenet67=fcdensenet_vectors(), linknet34=linknet34_vectors(),
                 torch_version=torch.__version__, numpy_version=np.__version__)
     split_merge_vectors()
     normalize_vectors()

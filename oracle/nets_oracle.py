@@ -123,6 +123,63 @@ def fcdensenet_forward(sd, x, down_blocks=(5, 5, 5, 5, 5), up_blocks=(5, 5, 5, 5
     return F.conv2d(q(out), q(sd['finalConv.weight']), sd['finalConv.bias'])
 
 
+RESNET34_BLOCKS = (3, 4, 6, 3)
+
+
+def _bn_eval(x, sd, prefix):
+    return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'],
+                        sd[prefix + '.bias'], training=False, eps=1e-5)
+
+
+def inplace_abn_eval(x, sd, prefix, eps=1e-5, slope=0.01):
+    """InPlaceABN in eval mode (lib/modules/abn/functions.py:62-100 with mapillary/inplace_abn's forward kernel, the
+    un-vendored third-party backend): (x - mean) / sqrt(var + eps) * (|weight| + eps) + bias, then leaky_relu(slope).
+    The |weight| + eps scale is that library's published forward (it keeps the transform invertible); no version is
+    pinned by the reference and no test of the reference covers it -> parity unpinned."""
+    mean, var = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
+    gamma = sd[prefix + '.weight'].abs() + eps
+    y = (x - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + eps) * gamma.view(1, -1, 1, 1)
+    return F.leaky_relu(y + sd[prefix + '.bias'].view(1, -1, 1, 1), slope)
+
+
+def linknet34_forward(sd, x, quant=None):
+    """LinkNet34.forward in eval mode (lib/models/linknet.py:65-90; encoder = torchvision resnet34 layers)."""
+    q = quant if quant is not None else (lambda t: t)
+
+    def conv(t, key, **kw):
+        return F.conv2d(q(t), q(sd[key + '.weight']), sd.get(key + '.bias'), **kw)
+
+    x = F.relu(_bn_eval(conv(x, 'firstconv', stride=2, padding=3), sd, 'firstbn'))
+    x = F.max_pool2d(q(x), 3, 2, 1)
+    feats = []
+    for li, n_blocks in enumerate(RESNET34_BLOCKS):
+        for b in range(n_blocks):
+            pre = 'encoder%d.%d' % (li + 1, b)
+            stride = 2 if (li > 0 and b == 0) else 1
+            ident = x
+            out = F.relu(_bn_eval(conv(x, pre + '.conv1', stride=stride, padding=1), sd, pre + '.bn1'))
+            out = _bn_eval(conv(q(out), pre + '.conv2', padding=1), sd, pre + '.bn2')
+            if pre + '.downsample.0.weight' in sd:
+                ident = q(_bn_eval(conv(x, pre + '.downsample.0', stride=stride), sd, pre + '.downsample.1'))
+            x = q(F.relu(out + ident))
+        feats.append(x)
+    e1, e2, e3, e4 = feats
+
+    def decoder(t, name):
+        t = q(inplace_abn_eval(conv(t, name + '.conv1'), sd, name + '.abn1'))
+        t = F.conv_transpose2d(t, q(sd[name + '.deconv2.weight']), sd[name + '.deconv2.bias'], stride=2, padding=1)
+        t = q(inplace_abn_eval(t, sd, name + '.abn2'))
+        return inplace_abn_eval(conv(t, name + '.conv3'), sd, name + '.abn3')
+
+    d4 = q(decoder(e4, 'decoder4') + e3)
+    d3 = q(decoder(d4, 'decoder3') + e2)
+    d2 = q(decoder(d3, 'decoder2') + e1)
+    d1 = q(decoder(d2, 'decoder1'))
+    f = F.leaky_relu(F.conv_transpose2d(d1, q(sd['finaldeconv1.weight']), sd['finaldeconv1.bias'], stride=2), 0.01)
+    f = F.leaky_relu(conv(q(f), 'finalconv2'), 0.01)
+    return conv(q(f), 'finalconv3', padding=1)
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 

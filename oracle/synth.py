@@ -129,6 +129,59 @@ def fcdensenet_state_dict(seed=0, down_blocks=(5, 5, 5, 5, 5), up_blocks=(5, 5, 
     return sd
 
 
+def linknet34_state_dict(seed=0):
+    """Random LinkNet34 state_dict with the reference key names (294 entries); BatchNorm / InPlaceABN buffers randomised,
+    some InPlaceABN weights negative so that the |weight| + eps scale of the backend matters."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+
+    def bn(prefix, c, tracked=True, signed=False):
+        wgt = rs.uniform(0.5, 1.5, c).astype(np.float32)
+        if signed:
+            wgt *= np.where(rs.rand(c) < 0.25, -1.0, 1.0).astype(np.float32)
+        sd[prefix + '.weight'] = torch.from_numpy(wgt)
+        sd[prefix + '.bias'] = torch.from_numpy((rs.standard_normal(c) * 0.1).astype(np.float32))
+        sd[prefix + '.running_mean'] = torch.from_numpy((rs.standard_normal(c) * 0.1).astype(np.float32))
+        sd[prefix + '.running_var'] = torch.from_numpy(rs.uniform(0.5, 1.5, c).astype(np.float32))
+        if tracked:
+            sd[prefix + '.num_batches_tracked'] = torch.tensor(5, dtype=torch.int64)
+
+    sd['firstconv.weight'] = _he(rs, (64, 3, 7, 7), 147)
+    bn('firstbn', 64)
+    filters, inplanes = [64, 128, 256, 512], 64
+    for li, (planes, blocks) in enumerate(zip(filters, (3, 4, 6, 3))):
+        for b in range(blocks):
+            pre = 'encoder%d.%d' % (li + 1, b)
+            cin = inplanes if b == 0 else planes
+            sd[pre + '.conv1.weight'] = _he(rs, (planes, cin, 3, 3), cin * 9, gain=0.8)
+            bn(pre + '.bn1', planes)
+            sd[pre + '.conv2.weight'] = _he(rs, (planes, planes, 3, 3), planes * 9, gain=0.5)
+            bn(pre + '.bn2', planes)
+            if b == 0 and li > 0:
+                sd[pre + '.downsample.0.weight'] = _he(rs, (planes, cin, 1, 1), cin, gain=0.7)
+                bn(pre + '.downsample.1', planes)
+        inplanes = planes
+    for i in range(4, 0, -1):
+        cin, cout = filters[i - 1], filters[max(i - 2, 0)]
+        q, pre = cin // 4, 'decoder%d' % i
+        sd[pre + '.conv1.weight'] = _he(rs, (q, cin, 1, 1), cin)
+        sd[pre + '.conv1.bias'] = _bias(rs, q)
+        bn(pre + '.abn1', q, tracked=False, signed=True)
+        sd[pre + '.deconv2.weight'] = _he(rs, (q, q, 4, 4), q * 4)
+        sd[pre + '.deconv2.bias'] = _bias(rs, q)
+        bn(pre + '.abn2', q, tracked=False, signed=True)
+        sd[pre + '.conv3.weight'] = _he(rs, (cout, q, 1, 1), q, gain=0.7)
+        sd[pre + '.conv3.bias'] = _bias(rs, cout)
+        bn(pre + '.abn3', cout, tracked=False, signed=True)
+    sd['finaldeconv1.weight'] = _he(rs, (64, 32, 3, 3), 64 * 2.25)
+    sd['finaldeconv1.bias'] = _bias(rs, 32)
+    sd['finalconv2.weight'] = _he(rs, (32, 32, 3, 3), 32 * 9)
+    sd['finalconv2.bias'] = _bias(rs, 32)
+    sd['finalconv3.weight'] = _he(rs, (1, 32, 2, 2), 32 * 4, gain=0.12)   # logits within +-3: bf16 noise stays < 2e-2 in probability
+    sd['finalconv3.bias'] = _bias(rs, 1)
+    return sd
+
+
 def image_u8(seed, h, w, c=3, smooth=True):
     """Inria-shaped synthetic uint8 image; low-pass structure so masks are not pure noise."""
     rs = np.random.RandomState(seed)

@@ -20,7 +20,7 @@ SNB_E_UNSUPPORTED = -4
 
 DT_U8, DT_F32, DT_F64, DT_I64 = 0, 1, 2, 3
 LAYOUT_NCHW_F32, LAYOUT_PATCH32, LAYOUT_PATCH32_F32 = 0, 1, 2
-CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2 = 0, 1, 2, 3
+CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2, CONV_2X2, CONVT_3X3_S2_FULL = 0, 1, 2, 3, 4, 5
 CONV_BF16, CONV_TF32 = 0, 1
 
 c_i64 = ctypes.c_int64
@@ -53,6 +53,11 @@ class ConvDesc(ctypes.Structure):
         ("pool_cstride", c_i64),
         ("d_pre_scale", c_vp),
         ("d_pre_shift", c_vp),
+        ("act_slope", ctypes.c_float),
+        ("res_after_act", ctypes.c_int32),
+        ("d_residual", c_vp),
+        ("res_cstride", c_i64),
+        ("valid", ctypes.c_int32),
         ("out_upsample2x", ctypes.c_int32),
         ("dtype", ctypes.c_int32),
     ]
@@ -76,6 +81,9 @@ SIGNATURES = {
     "snb_conv_destroy": (None, [c_vp]),
     "snb_conv_flops": (ctypes.c_double, [c_vp]),
     "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "snb_space_to_depth2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_maxpool3x3s2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_stem7x7_rows": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),

@@ -80,6 +80,73 @@ __global__ void bn_relu_kernel(const uint4* __restrict__ in, int CV, int CPV, in
   }
 }
 
+// space-to-depth: out[n][y][x][(py*2+px)*C + c] = in[n][2y+py][2x+px][c]; a stride-2 conv3x3 over `in` becomes a
+// 4-tap stride-1 conv over `out` (SNB_CONV_2X2 taps), a stride-2 conv1x1 a plain conv1x1 on channels [0, C)
+__global__ void space_to_depth_kernel(const uint4* __restrict__ in, int H, int W, int CV, int in_sv,
+                                      uint4* __restrict__ out, int out_sv, int64_t total) {
+  const int OH = H / 2, OW = W / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int cv = (int)(r % CV); r /= CV;
+    const int q = (int)(r % 4); r /= 4;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int64_t n = r / OH;
+    out[((n * OH + oy) * OW + ox) * out_sv + q * CV + cv] =
+        __ldg(in + ((n * H + 2 * oy + (q >> 1)) * W + 2 * ox + (q & 1)) * in_sv + cv);
+  }
+}
+
+// nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC bf16 (torchvision resnet stem)
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int H, int W, int CV, int in_sv,
+                                    uint4* __restrict__ out, int out_sv, int64_t total) {
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int cv = (int)(r % CV); r /= CV;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int64_t n = r / OH;
+    uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf pairs
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * oy + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * ox + dx;
+        if (x < 0 || x >= W) continue;
+        m = bf16x8_max(m, __ldg(in + ((n * H + y) * W + x) * in_sv + cv));
+      }
+    }
+    out[((n * OH + oy) * OW + ox) * out_sv + cv] = m;
+  }
+}
+
+// stride-2 7x7 p3 stem as a GEMM operand: rows[n][y][x][k], k = (ky*7 + kx)*C + c for k < 49*C, zero up to KP
+__global__ void stem7x7_rows_kernel(const float* __restrict__ src, int C, int H, int W, int KP, uint4* __restrict__ dst,
+                                    int64_t total) {
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2, VPP = KP / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % VPP);
+    int64_t r = i / VPP;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int64_t n = r / OH;
+    const float* img = src + n * C * (int64_t)H * W;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = v * 8 + e;
+      const int tap = k / C, c = k - tap * C;
+      const int y = 2 * oy + tap / 7 - 3, x = 2 * ox + tap % 7 - 3;
+      f[e] = (tap < 49 && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + ((int64_t)c * H + y) * W + x) : 0.f;
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+    dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                        *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+  }
+}
+
 static int aux_grid(int64_t total) {
   const int64_t need = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -109,6 +176,53 @@ extern "C" int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w,
     maxpool2x2_kernel<false><<<aux_grid(total), 256, 0, as_stream(stream)>>>(
         static_cast<const uint4*>(d_in), (int)h, (int)w, (int)(channels / V), (int)(in_cstride / V),
         static_cast<uint4*>(d_out), (int)(out_cstride / V), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+static int check_bf16_slabs(const void* d_in, const void* d_out, int64_t n, int64_t h, int64_t w, int64_t channels,
+                            int64_t in_cstride, int64_t out_cstride, int64_t out_channels) {
+  if (!d_in || !d_out) return fail(SNB_E_INVALID, "null argument");
+  if (n <= 0 || h <= 0 || w <= 0) return fail(SNB_E_INVALID, "bad shape");
+  if (channels <= 0 || channels % 8 || in_cstride % 8 || out_cstride % 8 || in_cstride < channels || out_cstride < out_channels)
+    return fail(SNB_E_INVALID, "channel counts and strides must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
+  return SNB_OK;
+}
+
+extern "C" int snb_space_to_depth2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                                   void* d_out, int64_t out_cstride, void* stream) {
+  if (int rc = check_bf16_slabs(d_in, d_out, n, h, w, channels, in_cstride, out_cstride, 4 * channels)) return rc;
+  if ((h & 1) || (w & 1)) return fail(SNB_E_INVALID, "space-to-depth needs even h, w");
+  const int64_t total = n * (h / 2) * (w / 2) * 4 * (channels / 8);
+  space_to_depth_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
+                                                                         (int)(channels / 8), (int)(in_cstride / 8),
+                                                                         static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_maxpool3x3s2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                                void* d_out, int64_t out_cstride, void* stream) {
+  if (int rc = check_bf16_slabs(d_in, d_out, n, h, w, channels, in_cstride, out_cstride, channels)) return rc;
+  const int64_t total = n * ((h + 1) / 2) * ((w + 1) / 2) * (channels / 8);
+  maxpool3x3s2_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
+                                                                       (int)(channels / 8), (int)(in_cstride / 8),
+                                                                       static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_stem7x7_rows(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w, void* d_dst,
+                                int64_t k_pad, void* stream) {
+  if (!d_src || !d_dst) return fail(SNB_E_INVALID, "snb_stem7x7_rows: null argument");
+  if (n <= 0 || h <= 0 || w <= 0 || channels <= 0) return fail(SNB_E_INVALID, "bad shape");
+  if (k_pad < 49 * channels || k_pad % 32) return fail(SNB_E_INVALID, "k_pad must be a multiple of 32 covering 49 * channels");
+  if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(SNB_E_INVALID, "destination must be 16-byte aligned");
+  const int64_t total = n * ((h + 1) / 2) * ((w + 1) / 2) * (k_pad / 8);
+  stem7x7_rows_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(d_src, (int)channels, (int)h, (int)w, (int)k_pad,
+                                                                       static_cast<uint4*>(d_dst), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

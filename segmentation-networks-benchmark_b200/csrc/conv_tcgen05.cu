@@ -66,6 +66,13 @@ struct alignas(64) ConvParams {
   const float* bias;
   const float* head_w;
   float* head_out;
+  const void* residual;            // optional tensor added in the epilogue (same grid as the output), or null
+  int32_t res_cstride;             // its pixel stride in channels
+  int32_t res_after_act;           // 0: act(conv + bias + res) (ResNet block); 1: act(conv + bias) + res (LinkNet skip)
+  int32_t load_dx;                 // offset added to the halo-box origin (+1 for a 'valid' conv3x3: the tile grid is
+                                   // the output grid and tap (dy,dx) reads input pixel (x+1+dx, y+1+dy))
+  int32_t in_w, in_h;              // input extent (pre-activation prologue masks with it)
+  float act_slope;                 // leaky-ReLU slope of the activation (0 = ReLU); only used when relu != 0
   const float* pre_scale;          // optional pre-activation y = relu(x * scale[c] + shift[c]) applied to the A operand
   const float* pre_shift;
   int8_t tap_dy[kMaxPhases][kMaxTaps];
@@ -185,7 +192,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
       float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
       if (p.relu) {
-        x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+        x0 = x0 > 0.f ? x0 : x0 * p.act_slope; x1 = x1 > 0.f ? x1 : x1 * p.act_slope;
+        x2 = x2 > 0.f ? x2 : x2 * p.act_slope; x3 = x3 > 0.f ? x3 : x3 * p.act_slope;
       }
       dot = fmaf(x0, w.x, dot); dot = fmaf(x1, w.y, dot); dot = fmaf(x2, w.z, dot); dot = fmaf(x3, w.w, dot);
     }
@@ -200,6 +208,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
     // 2x2 max-pool partners of pixel (x, y) sit 1 and TW lanes away; lanes with even x and even y keep the result
     const bool pool_keep = ((lane & 1) | (lane & TW)) == 0;
     const int prow = ((row / TW) >> 1) * (TW / 2) + ((row % TW) >> 1);
+    // residual operand: same pixel grid as the stored output (only used by single-phase convs)
+    const int rx = tc.x0 + (row % TW), ry = tc.y0 + (row / TW);
+    const bool res_ok = rx < p.out_w && ry < p.out_h;
+    const int64_t res_pix = ((static_cast<int64_t>(tc.img) * p.out_h + ry) * p.out_w + rx) * p.res_cstride;
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c, ++n_store) {
       uint8_t* sout = smem_out + (n_store & 1) * OUT_BYTES;
@@ -220,9 +232,36 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
                         __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
                         __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
                         __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+          float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (p.residual != nullptr && res_ok) {
+            const int64_t ro = res_pix + tc.nt * BN + c * CW + g * 32 + j * 8;
+            if constexpr (EB == 2) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + ro));
+              const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __bfloat1622float2(pr[e]);
+                res[2 * e] = t2.x;
+                res[2 * e + 1] = t2.y;
+              }
+            } else {
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + ro));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + ro) + 1);
+              res[0] = r0.x; res[1] = r0.y; res[2] = r0.z; res[3] = r0.w;
+              res[4] = r1.x; res[5] = r1.y; res[6] = r1.z; res[7] = r1.w;
+            }
+          }
+          if (!p.res_after_act) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += res[e];
+          }
           if (p.relu) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.act_slope;
+          }
+          if (p.res_after_act) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += res[e];
           }
           const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
           const int swp = OUT_SWZ == 128 ? (prow & 7) : ((prow >> 1) & 3);
@@ -533,7 +572,8 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_empty[s], par);
           mbar_arrive_expect_tx(&a_full[s], Cfg::HALO_BOX_BYTES);
-          tma_load_4d(&p.map_a, &a_full[s], smem_a + s * Cfg::HALO_STAGE_BYTES, kc * BK, tc.x0 - 1, tc.y0 - 1, tc.img);
+          tma_load_4d(&p.map_a, &a_full[s], smem_a + s * Cfg::HALO_STAGE_BYTES, kc * BK, tc.x0 - 1 + p.load_dx,
+                      tc.y0 - 1 + p.load_dx, tc.img);
           if (++s == static_cast<uint32_t>(p.a_stages)) { s = 0; par ^= 1; }
         }
       }
@@ -638,8 +678,8 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
 #pragma unroll 3
         for (int r = r0; r < kHaloRows; r += RSTEP) {
           const int hy = r / kHaloW, hx = r - hy * kHaloW;
-          const bool inside = static_cast<unsigned>(tc.x0 - 1 + hx) < static_cast<unsigned>(p.out_w) &&
-                              static_cast<unsigned>(tc.y0 - 1 + hy) < static_cast<unsigned>(p.out_h);
+          const bool inside = static_cast<unsigned>(tc.x0 - 1 + p.load_dx + hx) < static_cast<unsigned>(p.in_w) &&
+                              static_cast<unsigned>(tc.y0 - 1 + p.load_dx + hy) < static_cast<unsigned>(p.in_h);
           const int phys = jl ^ (SWZ == 128 ? (r & 7) : ((r >> 1) & 3));   // the swizzle TMA applied to this row
           uint4* ptr = reinterpret_cast<uint4*>(base + r * SWZ + (phys << 4));
           uint4 o = make_uint4(0u, 0u, 0u, 0u);
@@ -833,8 +873,20 @@ using namespace snb;
 extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (!d || !out) return fail(SNB_E_INVALID, "snb_conv_create: null argument");
   *out = nullptr;
-  if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_3X3_S2) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
-  const bool is_convt = d->kind == SNB_CONVT_4X4_S2 || d->kind == SNB_CONVT_3X3_S2;
+  if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_3X3_S2_FULL) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
+  const bool is_convt3 = d->kind == SNB_CONVT_3X3_S2 || d->kind == SNB_CONVT_3X3_S2_FULL;
+  const bool is_convt = d->kind == SNB_CONVT_4X4_S2 || is_convt3;
+  // valid: conv3x3 without padding ((h-2) x (w-2) outputs); conv k2 with top/left padding only (h x w outputs)
+  const bool valid = d->valid != 0;
+  if (valid && !((d->kind == SNB_CONV_3X3 && d->h >= 3 && d->w >= 3) || d->kind == SNB_CONV_2X2))
+    return fail(SNB_E_INVALID, "valid mode applies to conv3x3 (inputs of at least 3x3) and conv2x2");
+  // tile grid (where accumulators are computed), store offset and output extent per kind
+  const int grid_pad = ((d->kind == SNB_CONV_2X2 && !valid) || d->kind == SNB_CONVT_3X3_S2_FULL) ? 1 : 0;
+  const int load_dx = (valid && d->kind == SNB_CONV_3X3) ? 1 : 0;
+  const int64_t grid_h = d->h + grid_pad - 2 * load_dx, grid_w = d->w + grid_pad - 2 * load_dx;
+  const int64_t osc = is_convt ? 2 : 1;   // output pixels per grid pixel and axis (before out_upsample2x)
+  const int64_t out_h = d->kind == SNB_CONVT_3X3_S2_FULL ? 2 * d->h + 1 : grid_h * osc;
+  const int64_t out_w = d->kind == SNB_CONVT_3X3_S2_FULL ? 2 * d->w + 1 : grid_w * osc;
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
   if (d->dtype != SNB_CONV_BF16 && d->dtype != SNB_CONV_TF32) return fail(SNB_E_INVALID, "unknown conv dtype %d", d->dtype);
   const int eb = d->dtype == SNB_CONV_TF32 ? 4 : 2;     // element bytes of activations and weights
@@ -857,8 +909,12 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (pre && (!d->d_pre_shift || d->kind != SNB_CONV_3X3 || head || eb != 2 || d->cout != 32 ||
               (reinterpret_cast<uintptr_t>(d->d_pre_scale) & 15) || (reinterpret_cast<uintptr_t>(d->d_pre_shift) & 15)))
     return fail(SNB_E_INVALID, "fused pre-activation needs a bf16 conv3x3 with cout == 32 and 16-byte aligned scale / shift");
+  const bool has_res = d->d_residual != nullptr;
+  if (has_res && (is_convt || head || up2x || d->res_cstride < d->cout || d->res_cstride % calign != 0 ||
+                  (reinterpret_cast<uintptr_t>(d->d_residual) & 15)))
+    return fail(SNB_E_INVALID, "the residual operand needs a plain conv without head and a 16-byte aligned slab");
   const bool pool = d->d_pool_out != nullptr;
-  if (pool && (head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
+  if (pool && (valid || head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
                d->pool_cstride % calign != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
     return fail(SNB_E_INVALID, "fused max-pool needs a conv3x3 without head, even h and w and a valid pooled slab");
   if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
@@ -875,7 +931,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   else if (d->cout % 64 == 0) bn = 64;
   if (mode >= 3 && bn == 256) {
     // wave quantisation: with few tiles (deep, low-resolution layers) a 128-wide N tile fills the last wave better
-    const int64_t m_tiles = (int64_t)(is_convt ? 4 : 1) * d->n * ((d->h + 15) / 16) * ((d->w + 7) / 8);
+    const int64_t m_tiles = (int64_t)(is_convt ? 4 : 1) * d->n * ((grid_h + 15) / 16) * ((grid_w + 7) / 8);
     const double e256 = wave_efficiency(m_tiles * (d->cout / 256), sms);
     const double e128 = wave_efficiency(m_tiles * (d->cout / 128), sms);
     if (e256 < 0.85 && e128 > e256 + 0.05) bn = 128;
@@ -899,12 +955,19 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
         p.tap_dy[0][ky * 3 + kx] = static_cast<int8_t>(ky - 1);
         p.tap_dx[0][ky * 3 + kx] = static_cast<int8_t>(kx - 1);
       }
+  } else if (d->kind == SNB_CONV_2X2) {
+    // k2 s1 p1: out[y][x] = sum in[y+ky-1][x+kx-1] * W[ky][kx]; tap = ky*2 + kx; output is (h+1) x (w+1)
+    for (int ky = 0; ky < 2; ++ky)
+      for (int kx = 0; kx < 2; ++kx) {
+        p.tap_dy[0][ky * 2 + kx] = static_cast<int8_t>(ky - 1);
+        p.tap_dx[0][ky * 2 + kx] = static_cast<int8_t>(kx - 1);
+      }
   } else if (is_convt) {
     // k4 s2 p1: out[2y+py] gathers in[y+dy] * W[ky]:  py=0: (dy=0,ky=1), (dy=-1,ky=3);  py=1: (dy=+1,ky=0), (dy=0,ky=2)
     // k3 s2 p0: out[2y+py] gathers                    py=0: (dy=0,ky=0), (dy=-1,ky=2);  py=1: (dy=0,ky=1), (unused slot)
     // the packed weight tap order is (ty, tx) with ty, tx in {0,1} following that list
     const int d4[2][2] = {{0, -1}, {1, 0}}, d3[2][2] = {{0, -1}, {0, 0}};
-    const int (*dlist)[2] = d->kind == SNB_CONVT_4X4_S2 ? d4 : d3;
+    const int (*dlist)[2] = d->kind == SNB_CONVT_4X4_S2 ? d4 : d3;   // the FULL variant only widens the tile grid
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px)
         for (int ty = 0; ty < 2; ++ty)
@@ -918,6 +981,10 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
 
   // ---- main-loop variant and pipeline shape
   const bool halo = mode >= 1 && d->kind != SNB_CONV_1X1;
+  if ((valid || grid_pad || has_res) && !halo && d->kind != SNB_CONV_1X1) {
+    delete c;
+    return fail(SNB_E_UNSUPPORTED, "this layer shape needs halo mode (SNB_CONV_MODE >= 1)");
+  }
   if (pre && (!halo || kc.fn_pre9 == nullptr)) {
     delete c;
     return fail(SNB_E_UNSUPPORTED, "fused pre-activation is only available in halo mode (SNB_CONV_MODE >= 1)");
@@ -971,7 +1038,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       c->threads = 512;
     }
     // CTA pairs: streamed weights, an even number of spatial tiles per phase, and a pair kernel for this shape
-    const int64_t m_tiles = (int64_t)d->n * ((d->h + tile_h - 1) / tile_h) * ((d->w + tile_w - 1) / tile_w);
+    const int64_t m_tiles = (int64_t)d->n * ((grid_h + tile_h - 1) / tile_h) * ((grid_w + tile_w - 1) / tile_w);
     const void* fn_pair = p.taps == 9 ? kc.fn_pair9 : kc.fn_pair4;
     if (mode >= 4 && !bres && !fuse_phases && !pre && fn_pair && m_tiles % 2 == 0 && sms >= 2) {
       c->fn = fn_pair;
@@ -980,8 +1047,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     }
   }
 
-  p.tiles_x = static_cast<int32_t>((d->w + tile_w - 1) / tile_w);
-  p.tiles_y = static_cast<int32_t>((d->h + tile_h - 1) / tile_h);
+  p.tiles_x = static_cast<int32_t>((grid_w + tile_w - 1) / tile_w);
+  p.tiles_y = static_cast<int32_t>((grid_h + tile_h - 1) / tile_h);
   p.n_img = static_cast<int32_t>(d->n);
   const int64_t total = static_cast<int64_t>(fuse_phases ? 1 : p.n_phases) * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
   if (total > INT32_MAX) {
@@ -997,8 +1064,15 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   p.head_out = d->d_head_out;
   p.pre_scale = d->d_pre_scale;
   p.pre_shift = d->d_pre_shift;
-  p.out_w = static_cast<int32_t>(d->w);
-  p.out_h = static_cast<int32_t>(d->h);
+  p.out_w = static_cast<int32_t>(out_w);
+  p.out_h = static_cast<int32_t>(out_h);
+  p.in_w = static_cast<int32_t>(d->w);
+  p.in_h = static_cast<int32_t>(d->h);
+  p.load_dx = load_dx;
+  p.act_slope = d->act_slope;
+  p.residual = d->d_residual;
+  p.res_cstride = static_cast<int32_t>(d->res_cstride);
+  p.res_after_act = d->res_after_act;
 
   int rc;
   const uint64_t E = (uint64_t)eb;
@@ -1025,12 +1099,14 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   const int cw = bn < 128 / eb ? bn : 128 / eb;   // channels per store chunk (ConvCfg::CW)
   if (!head) {
     const int s = (is_convt || up2x) ? 2 : 1;
-    const int64_t ow = d->w * s, oh = d->h * s;
+    // full output extent and, per phase, the sub-grid a phase writes (strided view into the full tensor)
+    const int64_t ow = up2x ? 2 * out_w : out_w, oh = up2x ? 2 * out_h : out_h;
     p.up2x = up2x ? 1 : 0;
-    for (int ph = 0; ph < (up2x ? 4 : p.n_phases); ++ph) {
+    for (int ph = 0; ph < ((up2x || is_convt) ? 4 : 1); ++ph) {
       const int py = ph / 2, px = ph % 2;
       char* base = static_cast<char*>(d->d_out) + ((int64_t)py * ow + px) * d->out_cstride * eb;
-      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+      const int64_t pw = s == 1 ? ow : (ow - px + 1) / 2, phh = s == 1 ? oh : (oh - py + 1) / 2;
+      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)pw, (uint64_t)phh, (uint64_t)d->n};
       uint64_t str[3] = {(uint64_t)s * d->out_cstride * E, (uint64_t)s * ow * d->out_cstride * E,
                          (uint64_t)oh * ow * d->out_cstride * E};
       uint32_t box[4] = {(uint32_t)cw, (uint32_t)tile_w, (uint32_t)tile_h, 1};
@@ -1058,8 +1134,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (c->cluster == 2) c->grid &= ~1;   // whole CTA pairs; total_tiles is even
   // 2*MACs with the true tap counts (ConvT: every input pixel meets all 16 taps once over the 4 phases)
   // (k3 s2 p0 cropped: 9 real taps per input pixel, the other 7 slots hold zero weights)
-  c->flops = 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout *
-             (double)(d->kind == SNB_CONVT_3X3_S2 ? 9 : p.n_phases * p.taps);
+  c->flops = is_convt ? 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * (is_convt3 ? 9.0 : 16.0)
+                      : 2.0 * (double)d->n * out_h * out_w * (double)d->cin * d->cout * (double)p.taps;
   *out = c;
   return SNB_OK;
 }

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -429,6 +430,174 @@ __global__ void __launch_bounds__(256) merge_f32c1_vec4_kernel(SlicerGeom g, con
   }
 }
 
+// a / b with b loop-invariant: y = RN(1/b) once per thread (__drcp_rn), then two FMA correction steps per quotient.
+// q1 is already within half an ulp plus 2^-104 of a/b; by Markstein's theorem (y correctly rounded, q1 faithful, r1 exact)
+// q2 = RN(q1 + r1*y) IS the correctly rounded quotient, i.e. bit-equal to numpy's float64 division (tests/
+// test_host_logic.py checks the sequence against exact rational arithmetic).  Valid while nothing under/overflows: the
+// caller keeps b in [2^-60, 2^60] and routes a outside [2^-823, 2^777) to __ddiv_rn.
+__device__ __forceinline__ double div_by_invariant(double a, double b, double y) {
+  const uint32_t e = (static_cast<uint32_t>(__double2hiint(a)) >> 20) & 0x7ffu;
+  if (e - 200u < 1600u) {
+    const double q0 = __dmul_rn(a, y);
+    const double r0 = __fma_rn(-b, q0, a);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-b, q1, a);
+    return __fma_rn(r1, y, q1);
+  }
+  return __ddiv_rn(a, b);
+}
+
+__device__ __forceinline__ void ld_w4(const double* __restrict__ p, double (&w)[4]) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+  w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+}
+
+// acc += v * w in the reference's arithmetic (rounded product, then rounded sum), norm += w
+__device__ __forceinline__ void acc4(const float4 v, const double (&w)[4], double (&acc)[4]) {
+  acc[0] = __dadd_rn(acc[0], __dmul_rn((double)v.x, w[0]));
+  acc[1] = __dadd_rn(acc[1], __dmul_rn((double)v.y, w[1]));
+  acc[2] = __dadd_rn(acc[2], __dmul_rn((double)v.z, w[2]));
+  acc[3] = __dadd_rn(acc[3], __dmul_rn((double)v.w, w[3]));
+}
+
+// Periodic formulation of the float32 / one-channel merge for tile <= 2 * step (at most two covering crops per axis).
+// Canvas pixel X = kx*step + r is covered by crop kx at tile column r and, when r < tile - step, by crop kx-1 at column
+// r + step: the weights a pixel needs depend only on its residues (X mod step, Y mod step).  A thread therefore owns
+// four consecutive residues of one image row, loads its <= 16 float64 weights ONCE, precomputes the (loop-invariant)
+// norm and its reciprocal, and walks the ~13 periods of the row: per pixel only the tile values move (177 MB read,
+// 125 MB written per 5000x5000 image; the gather kernel above re-reads 16 B of weights per covering crop and pixel
+// through L2, ~700 MB).  Pixels covered by a single crop are q = RN32(RN64(RN64(v*w) / w)) = v exactly (the float64 round
+// trip perturbs v by < 2^-52 relative, far inside the float32 rounding interval), so they are copied when w >= eps.
+// Accumulation order (crop order: y outer, x inner), rounded products and the IEEE quotient are those of
+// lib/tiles.py:146-161, hence bit-exact.
+__global__ void __launch_bounds__(256) merge_f32c1_period_kernel(SlicerGeom g, const float* __restrict__ tiles,
+                                                                 const double* __restrict__ weight,
+                                                                 float* __restrict__ out, uint8_t* __restrict__ mask,
+                                                                 float thr) {
+  const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w, H = (int)g.image_h;
+  const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y, ov = T - S, ml = (int)g.margin_left;
+  const int r = threadIdx.x * 4;
+  const int y = blockIdx.x * blockDim.y + threadIdx.y;
+  if (r >= S || y >= H) return;
+  const int Y = y + (int)g.margin_top;
+  const int ky = Y / S, ry = Y - ky * S;
+  const bool up = ky >= 1 && ry < ov;                 // crop row ky-1 covers Y (first in crop order)
+  const bool two_rows = up && ky <= tiles_y - 1;
+  const int iy0 = up ? ky - 1 : ky;
+  const int ty0 = Y - iy0 * S;
+  const bool hasA = r < ov;                           // the crop to the left (kx-1) also covers the pixel
+  double wA0[4] = {0, 0, 0, 0}, wB0[4], wA1[4] = {0, 0, 0, 0}, wB1[4] = {0, 0, 0, 0};
+  ld_w4(weight + ty0 * T + r, wB0);
+  if (hasA) ld_w4(weight + ty0 * T + r + S, wA0);
+  if (two_rows) {
+    ld_w4(weight + (ty0 - S) * T + r, wB1);
+    if (hasA) ld_w4(weight + (ty0 - S) * T + r + S, wA1);
+  }
+  // interior periods: every crop of the pattern exists
+  double nrm[4], rcp[4];
+  bool fast = true, copy = !hasA && !two_rows;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    double n = 0.0;
+    if (hasA) n = __dadd_rn(n, wA0[e]);
+    n = __dadd_rn(n, wB0[e]);
+    if (two_rows) {
+      if (hasA) n = __dadd_rn(n, wA1[e]);
+      n = __dadd_rn(n, wB1[e]);
+    }
+    copy = copy && wB0[e] >= DBL_EPSILON && wB0[e] < 0x1p60;
+    n = n < DBL_EPSILON ? DBL_EPSILON : n;            // np.clip(norm, eps, None)
+    fast = fast && n < 0x1p60;                        // NaN / huge weights take the IEEE division
+    nrm[e] = n;
+    rcp[e] = __drcp_rn(n);
+  }
+  // periods with an output pixel: ml <= kx*S + r <= ml + W - 4
+  const int kx_lo = ml > r ? (ml - r + S - 1) / S : 0;
+  int kx_hi = ml + W - 4 - r >= 0 ? (ml + W - 4 - r) / S : -1;
+  kx_hi = min(kx_hi, tiles_x - 1 + (hasA ? 1 : 0));
+  const int64_t TT = (int64_t)T * T;
+  const float* pB0 = tiles + ((int64_t)iy0 * tiles_x * T + ty0) * T + r;      // crop (iy0, kx = 0), advanced by kx*TT
+  const int64_t dA = S - TT, d1 = (int64_t)tiles_x * TT - (int64_t)S * T;       // crop to the left / crop row below
+  float* orow = out ? out + (int64_t)y * W - ml + r : nullptr;
+  uint8_t* mrow = mask ? mask + (int64_t)y * W - ml + r : nullptr;
+
+  auto emit = [&](int kx, const float (&q)[4]) {
+    const int64_t o = (int64_t)kx * S;
+    if (orow) *reinterpret_cast<float4*>(orow + o) = make_float4(q[0], q[1], q[2], q[3]);
+    if (mrow)
+      *reinterpret_cast<uchar4*>(mrow + o) =
+          make_uchar4(q[0] > thr ? 255 : 0, q[1] > thr ? 255 : 0, q[2] > thr ? 255 : 0, q[3] > thr ? 255 : 0);
+  };
+  // a period at the canvas edge: some crops of the pattern do not exist; norm on the fly, IEEE division
+  auto edge = [&](int kx) {
+    const bool useA = hasA && kx >= 1, useB = kx <= tiles_x - 1;
+    const float* p = pB0 + kx * TT;
+    double acc[4] = {0, 0, 0, 0}, n[4] = {0, 0, 0, 0};
+    if (useA) {
+      acc4(__ldg(reinterpret_cast<const float4*>(p + dA)), wA0, acc);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wA0[e]);
+    }
+    if (useB) {
+      acc4(__ldg(reinterpret_cast<const float4*>(p)), wB0, acc);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wB0[e]);
+    }
+    if (two_rows) {
+      if (useA) {
+        acc4(__ldg(reinterpret_cast<const float4*>(p + d1 + dA)), wA1, acc);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wA1[e]);
+      }
+      if (useB) {
+        acc4(__ldg(reinterpret_cast<const float4*>(p + d1)), wB1, acc);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wB1[e]);
+      }
+    }
+    float q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = __double2float_rn(__ddiv_rn(acc[e], n[e] < DBL_EPSILON ? DBL_EPSILON : n[e]));
+    emit(kx, q);
+  };
+
+  int k0 = kx_lo, k1 = kx_hi;
+  if (k0 <= k1 && hasA && k0 == 0) edge(k0++);
+  if (k0 <= k1 && k1 >= tiles_x) edge(k1--);
+  if (copy) {
+#pragma unroll 4
+    for (int kx = k0; kx <= k1; ++kx) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(pB0 + kx * TT));
+      const float q[4] = {v.x, v.y, v.z, v.w};
+      emit(kx, q);
+    }
+    return;
+  }
+#pragma unroll 2
+  for (int kx = k0; kx <= k1; ++kx) {
+    const float* p = pB0 + kx * TT;
+    float4 vA0 = make_float4(0.f, 0.f, 0.f, 0.f), vA1 = vA0, vB1 = vA0;
+    const float4 vB0 = __ldg(reinterpret_cast<const float4*>(p));
+    if (hasA) vA0 = __ldg(reinterpret_cast<const float4*>(p + dA));
+    if (two_rows) {
+      vB1 = __ldg(reinterpret_cast<const float4*>(p + d1));
+      if (hasA) vA1 = __ldg(reinterpret_cast<const float4*>(p + d1 + dA));
+    }
+    double acc[4] = {0, 0, 0, 0};
+    if (hasA) acc4(vA0, wA0, acc);
+    acc4(vB0, wB0, acc);
+    if (two_rows) {
+      if (hasA) acc4(vA1, wA1, acc);
+      acc4(vB1, wB1, acc);
+    }
+    float q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      q[e] = __double2float_rn(fast ? div_by_invariant(acc[e], nrm[e], rcp[e]) : __ddiv_rn(acc[e], nrm[e]));
+    emit(kx, q);
+  }
+}
+
 static int grid_for(int64_t total, int block) {
   const int64_t need = (total + block - 1) / block;
   const int64_t cap = (int64_t)sm_count() * 16;  // grid-stride: a few waves of resident CTAs
@@ -636,9 +805,17 @@ extern "C" int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtyp
       g.margin_left % 4 == 0 && g.image_w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_tiles) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0) {
-    const dim3 grid((unsigned)std::min<int64_t>((g.image_w / 4 + 255) / 256, 1024), (unsigned)g.image_h);
-    merge_f32c1_vec4_kernel<<<grid, 256, 0, st>>>(g, static_cast<const float*>(d_tiles), d_weight,
-                                                  static_cast<float*>(d_out), d_mask, thr);
+    static const bool use_gather = std::getenv("SNB_MERGE_GATHER") != nullptr;   // A/B switch for profiles/
+    if (g.tile <= 2 * g.step && g.step / 4 <= 256 && !use_gather) {
+      // periodic kernel: blockDim = (step / 4 residue groups, rows that fit in 256 threads)
+      const int bx = (int)(g.step / 4), by = std::max(1, 256 / bx);
+      merge_f32c1_period_kernel<<<(unsigned)((g.image_h + by - 1) / by), dim3(bx, by), 0, st>>>(
+          g, static_cast<const float*>(d_tiles), d_weight, static_cast<float*>(d_out), d_mask, thr);
+    } else {
+      const dim3 grid((unsigned)std::min<int64_t>((g.image_w / 4 + 255) / 256, 1024), (unsigned)g.image_h);
+      merge_f32c1_vec4_kernel<<<grid, 256, 0, st>>>(g, static_cast<const float*>(d_tiles), d_weight,
+                                                    static_cast<float*>(d_out), d_mask, thr);
+    }
     SNB_LAUNCH_CHECK();
     return SNB_OK;
   }

@@ -99,8 +99,9 @@ class SlabView:
 class ConvOp:
     """One snb_conv handle; keeps every tensor it points at alive."""
 
-    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False, pre=None):
-        self.keep = (src, dst, weight, bias, head, pool_dst, pre)
+    def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False, pre=None,
+                 act_slope=0.0, residual=None, res_after_act=False, valid=False):
+        self.keep = (src, dst, weight, bias, head, pool_dst, pre, residual)
         d = N.ConvDesc()
         d.kind = kind
         d.dtype = N.CONV_TF32 if src.slab.t.dtype == torch.float32 else N.CONV_BF16
@@ -124,6 +125,11 @@ class ConvOp:
             d.head_sigmoid = 1 if head_sigmoid else 0
             d.d_head_out = head_out.data_ptr()
         d.out_upsample2x = 1 if upsample2x else 0
+        d.act_slope = float(act_slope)
+        d.valid = 1 if valid else 0
+        if residual is not None:
+            d.d_residual, d.res_cstride = residual.ptr, residual.cstride
+            d.res_after_act = 1 if res_after_act else 0
         if pre is not None:
             d.d_pre_scale, d.d_pre_shift = pre[0].data_ptr(), pre[1].data_ptr()
         if pool_dst is not None:
@@ -518,4 +524,181 @@ class FCDenseNetPlan:
         self.launches = sum(op.launches for op in self.ops)
 
     load_nchw = VGGUNetPlan.load_nchw
+    run = VGGUNetPlan.run
+
+
+# ------------------------------------------------------------------------------------------------ LinkNet34
+def pack_conv3x3_s2(weight, dtype=torch.bfloat16):
+    """Stride-2 conv3x3 (padding 1) as a 4-tap conv over the space-to-depth tensor: [Cout, Cin, 3, 3] ->
+    [4 taps][Cout][4 * Cin]; tap (ty, tx) reads the 2x2 block at offset (ty - 1, tx - 1), block channel
+    (py*2+px)*Cin + ci holds input pixel (2y'+py, 2x'+px).  Row 2y+ky-1 is (block y-1, py=1) for ky=0 and
+    (block y, py=ky-1) for ky=1,2; unused (tap, parity) pairs stay zero."""
+    cout, cin = weight.shape[:2]
+    w = weight.detach().float()
+    out = torch.zeros((4, cout, 4 * cin), dtype=torch.float32, device=weight.device)
+    kmap = {(0, 1): 0, (1, 0): 1, (1, 1): 2}          # (tap index t, parity p) -> kernel index
+    for (ty, py), ky in kmap.items():
+        for (tx, px), kx in kmap.items():
+            q = py * 2 + px
+            out[ty * 2 + tx, :, q * cin:(q + 1) * cin] = w[:, :, ky, kx]
+    return to_storage(out, dtype).contiguous()
+
+
+def pack_conv2x2(weight, cin_pad=None, cout_pad=None, dtype=torch.bfloat16):
+    """nn.Conv2d(k=2, padding=1) weight [Cout, Cin, 2, 2] -> [4][cout_pad][cin_pad], tap = ky*2 + kx."""
+    cout, cin = weight.shape[:2]
+    out = torch.zeros((4, cout_pad or cout, cin_pad or cin), dtype=torch.float32, device=weight.device)
+    out[:, :cout, :cin] = weight.detach().float().permute(2, 3, 0, 1).reshape(4, cout, cin)
+    return to_storage(out, dtype).contiguous()
+
+
+def pack_stem7x7(weight, k_pad, dtype=torch.bfloat16):
+    """Stride-2 7x7 stem [Cout, C, 7, 7] -> [1][Cout][k_pad] matching snb_stem7x7_rows: k = (ky*7+kx)*C + c."""
+    cout, cin = weight.shape[:2]
+    out = torch.zeros((1, cout, k_pad), dtype=torch.float32, device=weight.device)
+    out[0, :, :49 * cin] = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, 49 * cin)
+    return to_storage(out, dtype).contiguous()
+
+
+def _pad_mat(w, cout_pad, cin_pad):
+    out = torch.zeros((cout_pad, cin_pad) + tuple(w.shape[2:]), dtype=torch.float32, device=w.device)
+    out[:w.shape[0], :w.shape[1]] = w
+    return out
+
+
+def _pad_vec(b, n):
+    out = torch.zeros(n, dtype=torch.float32, device=b.device)
+    out[:b.numel()] = b
+    return out
+
+
+class SimpleOp:
+    """A helper-kernel launch with fixed arguments (space-to-depth, 3x3/s2 max-pool)."""
+
+    def __init__(self, fn_name, args, keep):
+        self.fn_name, self.args, self.keep = fn_name, args, keep
+        self.flops, self.launches = 0.0, 1
+
+    def __call__(self, stream):
+        N.check(getattr(N.lib(), self.fn_name)(*self.args, stream))
+
+
+class LinkNet34Plan:
+    """LinkNet34 forward (lib/models/linknet.py:65-90) in eval mode on the native kernels.
+
+    ResNet-34 encoder: BatchNorm folded into the (bias-free) convolutions; the 7x7/s2 stem is a GEMM over im2col rows;
+    stride-2 blocks run on a space-to-depth copy (conv3x3/s2 -> 4-tap conv, 1x1/s2 -> conv1x1 on its first quarter);
+    the block's identity / down-sample branch enters the second conv's epilogue as a residual operand before the ReLU.
+    Decoders: conv1x1 -> ConvTranspose k4s2 -> conv1x1, each with InPlaceABN folded (scale |w|+eps as in mapillary's
+    kernel, leaky-ReLU 0.01 in the epilogue); the additive skips `decoderK(x) + eK` are residual operands applied
+    after the activation.  Head: ConvTranspose k3s2 (uncropped, 2h+1) -> valid conv3x3 -> conv k2 p1, Dropout2d off.
+    `spec` comes from snb_b200.lib.models.linknet.LinkNet34._spec().
+    """
+
+    STEM_K = 160
+
+    def __init__(self, spec, n, h, w, device, sigmoid):
+        if h % 32 or w % 32:
+            raise ValueError("height and width must be multiples of 32")
+        if spec['final3'][0].shape[0] != 1:
+            raise NotImplementedError("fused head expects num_classes == 1")
+        self.n, self.h, self.w, self.device = n, h, w, device
+        self.dtype = torch.bfloat16
+        self.ops = []
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
+        p32 = lambda c: (c + 31) // 32 * 32
+
+        def fold(wt, bias, bn, transposed=False):
+            """conv (+ optional bias) followed by BatchNorm(eval) / InPlaceABN(eval) -> (weight, bias) in fp32."""
+            gamma, beta, mean, var, eps, abn = bn
+            g = (gamma.detach().float().abs() + eps) if abn else gamma.detach().float()
+            scale = g / torch.sqrt(var.detach().float() + eps)
+            b0 = bias.detach().float() if bias is not None else torch.zeros_like(scale)
+            shape = (1, -1, 1, 1) if transposed else (-1, 1, 1, 1)
+            return wt.detach().float() * scale.view(shape), (b0 - mean.detach().float()) * scale + beta.detach().float()
+
+        # ---- stem: 7x7/s2 conv + BN + ReLU as a GEMM over im2col rows, then MaxPool 3x3/s2
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        self.x_rows = S(h2, w2, self.STEM_K)
+        wt, bs = fold(spec['stem'][0], None, spec['stem'][1])
+        stem = S(h2, w2, 64)
+        self.ops.append(ConvOp(N.CONV_1X1, self.x_rows.view(), stem.view(), pack_stem7x7(wt, self.STEM_K), bs.contiguous()))
+        cur = S(h4, w4, 64)
+        self.ops.append(SimpleOp("snb_maxpool3x3s2", (N.c_vp(stem.view().ptr), n, h2, w2, 64, 64, N.c_vp(cur.view().ptr), 64),
+                                 (stem, cur)))
+        cur, ch, hh, ww = cur.view(), 64, h4, w4
+
+        # ---- encoders (BasicBlocks)
+        skips = []
+        for blocks in spec['encoders']:
+            for blk in blocks:
+                cout = blk['conv1'].shape[0]
+                if blk['down'] is not None:                      # stride-2 block
+                    hh, ww = hh // 2, ww // 2
+                    x4 = S(hh, ww, 4 * ch)
+                    self.ops.append(SimpleOp("snb_space_to_depth2", (N.c_vp(cur.ptr), n, 2 * hh, 2 * ww, ch, cur.cstride,
+                                                                     N.c_vp(x4.view().ptr), 4 * ch), (cur, x4)))
+                    w1, b1 = fold(blk['conv1'], None, blk['bn1'])
+                    t = S(hh, ww, cout).view()
+                    self.ops.append(ConvOp(N.CONV_2X2, x4.view(), t, pack_conv3x3_s2(w1), b1.contiguous(), valid=True))
+                    wd, bd = fold(blk['down'][0], None, blk['down'][1])
+                    ident = S(hh, ww, cout).view()
+                    self.ops.append(ConvOp(N.CONV_1X1, x4.view(0, ch), ident, pack_conv1x1(wd), bd.contiguous(), relu=False))
+                else:
+                    w1, b1 = fold(blk['conv1'], None, blk['bn1'])
+                    t = S(hh, ww, cout).view()
+                    self.ops.append(ConvOp(N.CONV_3X3, cur, t, pack_conv3x3(w1), b1.contiguous()))
+                    ident = cur
+                w2_, b2 = fold(blk['conv2'], None, blk['bn2'])
+                y = S(hh, ww, cout).view()
+                self.ops.append(ConvOp(N.CONV_3X3, t, y, pack_conv3x3(w2_), b2.contiguous(), residual=ident))
+                cur, ch = y, cout
+            skips.append(cur)
+
+        # ---- decoders with additive skips
+        def decoder(x, cin, spec_d, n_out, hh, ww, skip):
+            mid = cin // 4
+            mp = p32(mid)
+            w1, b1 = fold(spec_d['conv1'][0], spec_d['conv1'][1], spec_d['abn1'])
+            a = S(hh, ww, mp).view()
+            self.ops.append(ConvOp(N.CONV_1X1, x, a, pack_conv1x1(_pad_mat(w1, mp, cin)), _pad_vec(b1, mp), act_slope=0.01))
+            w2_, b2 = fold(spec_d['deconv2'][0], spec_d['deconv2'][1], spec_d['abn2'], transposed=True)
+            b_ = S(2 * hh, 2 * ww, mp).view()
+            self.ops.append(ConvOp(N.CONVT_4X4_S2, a, b_, pack_convT4x4(_pad_mat(w2_, mp, mp)), _pad_vec(b2, mp), act_slope=0.01))
+            w3, b3 = fold(spec_d['conv3'][0], spec_d['conv3'][1], spec_d['abn3'])
+            y = S(2 * hh, 2 * ww, n_out).view()
+            self.ops.append(ConvOp(N.CONV_1X1, b_, y, pack_conv1x1(_pad_mat(w3, n_out, mp)), b3.contiguous(), act_slope=0.01,
+                                   residual=skip, res_after_act=True))
+            return y
+
+        e1, e2, e3, e4 = skips
+        h32, w32 = h // 32, w // 32
+        d4 = decoder(e4, 512, spec['decoders'][3], 256, h32, w32, e3)
+        d3 = decoder(d4, 256, spec['decoders'][2], 128, 2 * h32, 2 * w32, e2)
+        d2 = decoder(d3, 128, spec['decoders'][1], 64, 4 * h32, 4 * w32, e1)
+        d1 = decoder(d2, 64, spec['decoders'][0], 64, 8 * h32, 8 * w32, None)
+
+        # ---- final classifier: ConvT k3 s2 (2h+1) -> LeakyReLU -> conv3x3 valid (2h-1) -> LeakyReLU -> conv k2 p1 (2h)
+        wt, bs = spec['final1']
+        f1 = S(h + 1, w + 1, 32)
+        self.ops.append(ConvOp(N.CONVT_3X3_S2_FULL, d1, f1.view(), pack_convT3x3(wt, 64, 32), bs.detach().float().contiguous(),
+                               act_slope=0.01))
+        wt, bs = spec['final2']
+        f3 = S(h - 1, w - 1, 32)
+        self.ops.append(ConvOp(N.CONV_3X3, f1.view(), f3.view(), pack_conv3x3(wt), bs.detach().float().contiguous(),
+                               act_slope=0.01, valid=True))
+        wt, bs = spec['final3']
+        self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
+        pick = torch.zeros(32, dtype=torch.float32, device=device)
+        pick[0] = 1.0
+        self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, pack_conv2x2(wt, 32, 32), _pad_vec(bs.detach().float(), 32),
+                               relu=False, head=(pick, 0.0, sigmoid, self.out)))
+        self.flops = sum(op.flops for op in self.ops)
+        self.launches = sum(op.launches for op in self.ops) + 1
+
+    def load_nchw(self, x):
+        x = x.contiguous()
+        N.check(N.lib().snb_stem7x7_rows(N.ptr(x), x.shape[0], x.shape[1], x.shape[2], x.shape[3],
+                                         N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K, N.stream_ptr()))
+
     run = VGGUNetPlan.run

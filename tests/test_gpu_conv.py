@@ -272,3 +272,109 @@ def test_fused_preactivation_prologue(cuda, conv_mode, n, h, w, cin):
     z = bf(F.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)))
     want = F.conv2d(z, bf(wt), bias, padding=1)
     check(nchw(dst.view()), want)
+
+
+# ------------------------------------------------------------------------- LinkNet34 layer shapes (lib/models/linknet.py)
+def _need_halo(conv_mode):
+    if conv_mode == 0:
+        pytest.skip("valid / widened-grid / residual convolutions exist in halo mode only")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 64, 64), (2, 24, 40, 64, 128), (1, 8, 8, 256, 512), (1, 32, 32, 128, 256)])
+def test_stride2_conv3x3_via_space_to_depth(cuda, conv_mode, n, h, w, cin, cout):
+    """resnet34 down-sampling block: conv3x3 stride 2 padding 1 == 4-tap conv over the space-to-depth tensor; the
+    stride-2 conv1x1 of the shortcut == conv1x1 over its first channel quarter."""
+    _need_halo(conv_mode)
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    src = rand_slab(n, h, w, cin, g)
+    x4 = E.Slab(n, h // 2, w // 2, 4 * cin, "cuda")
+    N.check(N.lib().snb_space_to_depth2(N.c_vp(src.view().ptr), n, h, w, cin, cin, N.c_vp(x4.view().ptr), 4 * cin, N.stream_ptr()))
+    want4 = F.pixel_unshuffle(nchw(src.view()), 2)                        # channel = c*4 + py*2 + px
+    want4 = want4.view(n, cin, 4, h // 2, w // 2).transpose(1, 2).reshape(n, 4 * cin, h // 2, w // 2)
+    assert torch.equal(nchw(x4.view()), want4)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    dst = E.Slab(n, h // 2, w // 2, cout, "cuda")
+    dst.t.fill_(float("nan"))
+    op = E.ConvOp(N.CONV_2X2, x4.view(), dst.view(), E.pack_conv3x3_s2(wt), bias, valid=True)
+    op(N.stream_ptr())
+    check(nchw(dst.view()), F.relu(F.conv2d(nchw(src.view()), bf(wt), bias, stride=2, padding=1)))
+    w1 = torch.randn((cout, cin, 1, 1), device="cuda", generator=g) * (1.0 / cin) ** 0.5
+    d1 = E.Slab(n, h // 2, w // 2, cout, "cuda")
+    E.ConvOp(N.CONV_1X1, x4.view(0, cin), d1.view(), E.pack_conv1x1(w1), bias, relu=False)(N.stream_ptr())
+    check(nchw(d1.view()), F.conv2d(nchw(src.view()), bf(w1), bias, stride=2))
+
+
+@pytest.mark.parametrize("n,h,w,c,after", [(1, 16, 16, 64, False), (2, 24, 40, 128, False), (1, 8, 16, 512, False),
+                                           (2, 16, 24, 256, True)])
+def test_residual_and_leaky_epilogue(cuda, conv_mode, n, h, w, c, after):
+    """BasicBlock tail relu(conv + identity) and LinkNet skip leaky(conv) + skip, the residual read in the epilogue."""
+    _need_halo(conv_mode)
+    g = torch.Generator(device="cuda").manual_seed(c + after)
+    src, res = rand_slab(n, h, w, c, g), rand_slab(n, h, w, c + 32, g)
+    wt = torch.randn((c, c, 3, 3), device="cuda", generator=g) * (2.0 / (9 * c)) ** 0.5
+    bias = torch.randn(c, device="cuda", generator=g)
+    dst = E.Slab(n, h, w, c, "cuda")
+    slope = 0.01 if after else 0.0
+    E.ConvOp(N.CONV_3X3, src.view(), dst.view(), E.pack_conv3x3(wt), bias, act_slope=slope, residual=res.view(32, c),
+             res_after_act=after)(N.stream_ptr())
+    y, r = F.conv2d(nchw(src.view()), bf(wt), bias, padding=1), nchw(res.view(32, c))
+    want = F.leaky_relu(y, slope) + r if after else F.relu(y + r)
+    check(nchw(dst.view()), want)
+    # conv1x1 with the skip added after the leaky-ReLU (decoder conv3 + encoder feature)
+    w1 = torch.randn((c, c, 1, 1), device="cuda", generator=g) * (1.0 / c) ** 0.5
+    d1 = E.Slab(n, h, w, c, "cuda")
+    E.ConvOp(N.CONV_1X1, src.view(), d1.view(), E.pack_conv1x1(w1), bias, act_slope=0.01, residual=res.view(0, c),
+             res_after_act=True)(N.stream_ptr())
+    check(nchw(d1.view()), F.leaky_relu(F.conv2d(nchw(src.view()), bf(w1), bias), 0.01) + nchw(res.view(0, c)))
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 16, 16), (2, 24, 40), (1, 33, 17)])
+def test_linknet_head_layers(cuda, conv_mode, n, h, w):
+    """finaldeconv1 (ConvTranspose k3 s2, uncropped 2h+1), finalconv2 (valid conv3x3), finalconv3 (conv k2 p1, h+1)."""
+    _need_halo(conv_mode)
+    g = torch.Generator(device="cuda").manual_seed(h * w)
+    src = rand_slab(n, h, w, 64, g)
+    wt = torch.randn((64, 32, 3, 3), device="cuda", generator=g) * 0.1
+    bias = torch.randn(32, device="cuda", generator=g)
+    f1 = E.Slab(n, 2 * h + 1, 2 * w + 1, 32, "cuda")
+    f1.t.fill_(float("nan"))
+    op = E.ConvOp(N.CONVT_3X3_S2_FULL, src.view(), f1.view(), E.pack_convT3x3(wt, 64, 32), bias, act_slope=0.01)
+    op(N.stream_ptr())
+    check(nchw(f1.view()), F.leaky_relu(F.conv_transpose2d(nchw(src.view()), bf(wt), bias, stride=2), 0.01))
+    assert op.flops == 2.0 * n * h * w * 64 * 32 * 9
+    w2 = torch.randn((32, 32, 3, 3), device="cuda", generator=g) * 0.08
+    f2 = E.Slab(n, 2 * h - 1, 2 * w - 1, 32, "cuda")
+    f2.t.fill_(float("nan"))
+    E.ConvOp(N.CONV_3X3, f1.view(), f2.view(), E.pack_conv3x3(w2), bias, act_slope=0.01, valid=True)(N.stream_ptr())
+    check(nchw(f2.view()), F.leaky_relu(F.conv2d(nchw(f1.view()), bf(w2)[:, :, :, :], bias), 0.01))
+    w3 = torch.randn((32, 32, 2, 2), device="cuda", generator=g) * 0.1
+    f3 = E.Slab(n, 2 * h, 2 * w, 32, "cuda")
+    f3.t.fill_(float("nan"))
+    E.ConvOp(N.CONV_2X2, f2.view(), f3.view(), E.pack_conv2x2(w3), bias, relu=False)(N.stream_ptr())
+    check(nchw(f3.view()), F.conv2d(nchw(f2.view()), bf(w3), bias, padding=1))
+    # the same layer through the fused head (channel 0 picked), as LinkNet34Plan runs finalconv3
+    out = torch.full((n, 2 * h, 2 * w), float("nan"), device="cuda")
+    pick = torch.zeros(32, device="cuda")
+    pick[0] = 1.0
+    E.ConvOp(N.CONV_2X2, f2.view(), None, E.pack_conv2x2(w3), bias, relu=False, head=(pick, 0.0, False, out))(N.stream_ptr())
+    want = F.conv2d(nchw(f2.view()), bf(w3), bias, padding=1)[:, 0]
+    assert (out - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
+
+
+def test_resnet_stem_helpers(cuda):
+    """7x7/s2 stem rows (im2col for a K=160 GEMM) and MaxPool2d(3, 2, 1) against torch."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    n, h, w = 2, 32, 48
+    x = torch.randn((n, 3, h, w), device="cuda", generator=g)
+    rows = E.Slab(n, h // 2, w // 2, 160, "cuda")
+    N.check(N.lib().snb_stem7x7_rows(N.ptr(x), n, 3, h, w, N.c_vp(rows.t.data_ptr()), 160, N.stream_ptr()))
+    wt = torch.randn((64, 3, 7, 7), device="cuda", generator=g) * 0.1
+    bias = torch.randn(64, device="cuda", generator=g)
+    stem = E.Slab(n, h // 2, w // 2, 64, "cuda")
+    E.ConvOp(N.CONV_1X1, rows.view(), stem.view(), E.pack_stem7x7(wt, 160), bias)(N.stream_ptr())
+    check(nchw(stem.view()), F.relu(F.conv2d(bf(x), bf(wt), bias, stride=2, padding=3)))
+    pooled = E.Slab(n, h // 4, w // 4, 64, "cuda")
+    N.check(N.lib().snb_maxpool3x3s2(N.c_vp(stem.view().ptr), n, h // 2, w // 2, 64, 64, N.c_vp(pooled.view().ptr), 64,
+                                     N.stream_ptr()))
+    assert torch.equal(nchw(pooled.view()), F.max_pool2d(nchw(stem.view()), 3, 2, 1))

@@ -185,3 +185,29 @@ def test_precision_modes_on_default_init_weights(cuda, arch):
         errs[prec] = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
     assert errs["tf32"] < FP32_PROB_TOL, errs
     assert errs["bf16"] < BF16_PROB_TOL, errs
+
+
+def test_linknet34_against_reference_vectors(cuda, golden_dir):
+    """BASELINE configs[1] model, eval mode: ResNet-34 encoder (BN folded, stride-2 blocks via space-to-depth, residual
+    epilogues) + LinkNet decoders (InPlaceABN folded with the |weight| + eps scale, leaky-ReLU, additive skips)."""
+    from snb_b200.lib.models import LinkNet34
+
+    g = np.load(os.path.join(golden_dir, "linknet34.npz"))
+    m = LinkNet34(pretrained=False)
+    res = m.load_state_dict(synth.linknet34_state_dict(seed=6), strict=True)       # the reference's 294 keys
+    assert not res.missing_keys and not res.unexpected_keys
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).cuda()).cpu()
+        y256 = m(torch.from_numpy(np.random.RandomState(15).standard_normal((1, 3, 256, 256)).astype(np.float32)).cuda()).cpu()
+        y_again = m(torch.from_numpy(g["x"]).cuda()).cpu()
+    ref = torch.from_numpy(g["logits"])
+    assert y.shape == ref.shape == (2, 1, 64, 96) and torch.equal(y, y_again)
+    p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    p_err256 = (torch.sigmoid(y256) - torch.sigmoid(torch.from_numpy(g["logits256"]))).abs().max().item()
+    assert p_err256 < BF16_PROB_TOL, p_err256
+    sd = synth.linknet34_state_dict(seed=6)
+    with torch.no_grad():
+        q = no.linknet34_forward(sd, torch.from_numpy(g["x"]), quant=no.bf16_round)
+    assert (y - q).abs().max().item() < 0.03 * max(1.0, q.abs().max().item())

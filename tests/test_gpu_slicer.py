@@ -146,3 +146,58 @@ def test_full_size_roundtrip_properties(cuda):
     assert torch.equal(merged, img)                                                # weighted mean of equal values
     ones = s.merge(torch.full((169, 512, 512, 1), 0.25, device="cuda"))
     assert torch.equal(ones, torch.full_like(ones, 0.25))
+
+
+@pytest.mark.parametrize("shape,tile,step,weight", [
+    ((200, 264), 64, 32, "pyramid"),     # tile = 2 * step: every pixel sees the crop to its left
+    ((120, 200), 64, 48, "pyramid"),     # narrow overlap band (16 px), margins 4
+    ((100, 64), 64, 64, "pyramid"),      # no overlap, one crop column: pure copy path
+    ((50, 72), 128, 64, "pyramid"),      # single crop, margins 28 / 39
+    ((96, 80), 64, 32, "mean"),
+    ((333, 520), 128, 96, "pyramid"),    # odd height, several periods
+])
+def test_merge_periodic_kernel_bit_exact(cuda, shape, tile, step, weight):
+    """The float32 one-channel fast path (merge_f32c1_period_kernel: loop-invariant norm, FMA-corrected division by an
+    invariant, copy of single-cover pixels) against the numpy restatement of lib/tiles.py:137-161, bit for bit, with
+    values that stress the division (zeros, float32 denormals, 1e30) and the threshold output."""
+    rs = np.random.RandomState(11)
+    so = to.SlicerOracle(shape, tile, step, weight=weight)
+    s = ImageSlicer(shape, tile, step, weight=weight)
+    assert s.margin_left % 4 == 0 and shape[1] % 4 == 0           # geometry of the fast path
+    tiles = rs.rand(len(so.crops), tile, tile, 1).astype(np.float32)
+    special = rs.rand(*tiles.shape)
+    tiles[special < 0.05] = 0.0
+    tiles[(special > 0.05) & (special < 0.07)] = 1e-42
+    tiles[(special > 0.07) & (special < 0.08)] = 1e30
+    want = so.merge(list(tiles))
+    t = torch.from_numpy(tiles).cuda()
+    out = torch.full(shape + (1,), float("nan"), dtype=torch.float32, device="cuda")
+    mask = torch.full(shape + (1,), 7, dtype=torch.uint8, device="cuda")
+    N.check(N.lib().snb_merge(s.handle, N.ptr(t), N.DT_F32, 1, 1, N.ptr(s.weight_on_device()), N.ptr(out), N.DT_F32,
+                              N.ptr(mask), 0.5, N.stream_ptr()))
+    got = out.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(mask.cpu().numpy(), ((want > 0.5) * 255).astype(np.uint8))
+
+
+def test_merge_full_size_random_rows_against_oracle(cuda):
+    """BASELINE size: 169 random probability tiles; rows sampled across all crop-row patterns are compared bit for bit
+    with the float64 numpy accumulation of lib/tiles.py:146-161 restricted to those rows."""
+    s = ImageSlicer((5000, 5000, 1), 512, 384, weight="pyramid")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tiles = torch.rand((169, 512, 512, 1), device="cuda", generator=g)
+    merged = s.merge(tiles)[..., 0].cpu().numpy()
+    w = s.weight_on_device().cpu().numpy()
+    rows = [0, 1, 67, 68, 323, 324, 325, 451, 452, 2500, 4547, 4548, 4931, 4932, 4999]
+    th = tiles[..., 0].cpu().numpy()
+    for y in rows:
+        Y = y + 60
+        acc, nrm = np.zeros(5120, np.float64), np.zeros(5120, np.float64)
+        for iy in range(13):
+            ty = Y - iy * 384
+            if 0 <= ty < 512:
+                for ix in range(13):
+                    acc[ix * 384:ix * 384 + 512] += th[iy * 13 + ix, ty].astype(np.float64) * w[ty]
+                    nrm[ix * 384:ix * 384 + 512] += w[ty]
+        want = (acc / np.clip(nrm, np.finfo(np.float64).eps, None)).astype(np.float32)[60:5060]
+        assert np.array_equal(merged[y].view(np.uint32), want.view(np.uint32)), y

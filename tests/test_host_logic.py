@@ -238,3 +238,33 @@ def test_convT3x3_phase_decomposition_is_the_cropped_transposed_convolution():
             out[:, py::2, px::2, :] = _tap_list_conv(x, packed[ph * 4:ph * 4 + 4], taps)
     want = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2)[:, :, :10, :12]
     assert torch.allclose(out.permute(0, 3, 1, 2), want, atol=1e-4)
+
+
+def test_fma_division_by_invariant_is_correctly_rounded():
+    """The merge kernel divides by a loop-invariant norm with y = RN(1/b), q0 = RN(a*y) and two FMA corrections
+    (csrc/slicer.cu div_by_invariant).  Emulate that sequence with exact rational arithmetic and compare with the
+    correctly rounded quotient numpy computes (lib/tiles.py:159), on weighted sums shaped like the merge's."""
+    import random
+    import struct
+    from fractions import Fraction as Fr
+
+    def fma(a, b, c):
+        return float(Fr(a) * Fr(b) + Fr(c))          # Fraction -> float rounds to nearest even
+
+    rnd = random.Random(7)
+    for i in range(6000):
+        if i % 3:
+            k = rnd.randint(1, 4)
+            ws = [rnd.uniform(0.006, 3.2) for _ in range(k)]
+            vs = [float(np.float32(rnd.random())) for _ in range(k)]
+            a = b = 0.0
+            for v, w in zip(vs, ws):
+                a, b = a + v * w, b + w
+        else:                                         # arbitrary significands
+            a = struct.unpack("d", struct.pack("Q", (rnd.randint(900, 1100) << 52) | rnd.getrandbits(52)))[0]
+            b = struct.unpack("d", struct.pack("Q", (rnd.randint(1000, 1040) << 52) | rnd.getrandbits(52)))[0]
+        y = float(1 / Fr(b))
+        q = float(Fr(a) * Fr(y))
+        for _ in range(2):
+            q = fma(fma(-b, q, a), y, q)
+        assert q == a / b, (a, b)

@@ -169,3 +169,15 @@ def test_fcdensenet67_logits(golden_dir, kats):
     with torch.no_grad():
         y = no.fcdensenet_forward(sd, torch.from_numpy(g["x"])).numpy()
     assert np.abs(y - g["logits"]).max() < 1e-4
+
+
+def test_linknet34_logits(golden_dir, kats):
+    """BASELINE configs[1] model in eval mode; the reference ran with a pure-torch stand-in for the un-vendored
+    `inplace_abn` backend (oracle/make_golden.py), so this row is "parity unpinned" at that boundary."""
+    g = np.load(os.path.join(golden_dir, "linknet34.npz"))
+    sd = synth.linknet34_state_dict(seed=6)
+    assert len(sd) == kats["linknet34"]["n_keys"] == 294 and kats["linknet34"]["params"] == 21794721
+    with torch.no_grad():
+        y = no.linknet34_forward(sd, torch.from_numpy(g["x"])).numpy()
+    assert y.shape == g["logits"].shape == (2, 1, 64, 96)
+    assert np.abs(y - g["logits"]).max() < 1e-4
