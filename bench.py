@@ -31,6 +31,7 @@ MODELS = {
     "unet16": ("UNet16", lambda s: s.vgg_unet_state_dict("unet16", seed=0), 512, 384, 13, "configs[2]: UNet16"),
     "unet11": ("UNet11", lambda s: s.vgg_unet_state_dict("unet11", seed=0), 512, 384, 13, "UNet11 (TernausNet-VGG11)"),
     "zf_unet": ("ZF_UNET", lambda s: s.zf_unet_state_dict(seed=0), 224, 112, 44, "ZF_UNET"),
+    "linknet34": ("LinkNet34", lambda s: s.linknet34_state_dict(seed=0), 512, 384, 13, "LinkNet34 (configs[1] model, eval forward)"),
     "fcdensenet67": ("FCDenseNet67", lambda s: s.fcdensenet_state_dict(seed=0), 224, 112, 44, "configs[4]: FCDenseNet67"),
 }
 

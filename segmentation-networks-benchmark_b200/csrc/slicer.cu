@@ -9,7 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 
+#include "sm100_ptx.cuh"
 #include "snb_internal.h"
 
 namespace snb {
@@ -430,172 +432,455 @@ __global__ void __launch_bounds__(256) merge_f32c1_vec4_kernel(SlicerGeom g, con
   }
 }
 
-// a / b with b loop-invariant: y = RN(1/b) once per thread (__drcp_rn), then two FMA correction steps per quotient.
-// q1 is already within half an ulp plus 2^-104 of a/b; by Markstein's theorem (y correctly rounded, q1 faithful, r1 exact)
-// q2 = RN(q1 + r1*y) IS the correctly rounded quotient, i.e. bit-equal to numpy's float64 division (tests/
-// test_host_logic.py checks the sequence against exact rational arithmetic).  Valid while nothing under/overflows: the
-// caller keeps b in [2^-60, 2^60] and routes a outside [2^-823, 2^777) to __ddiv_rn.
-__device__ __forceinline__ double div_by_invariant(double a, double b, double y) {
-  const uint32_t e = (static_cast<uint32_t>(__double2hiint(a)) >> 20) & 0x7ffu;
-  if (e - 200u < 1600u) {
-    const double q0 = __dmul_rn(a, y);
-    const double r0 = __fma_rn(-b, q0, a);
-    const double q1 = __fma_rn(r0, y, q0);
-    const double r1 = __fma_rn(-b, q1, a);
-    return __fma_rn(r1, y, q1);
-  }
-  return __ddiv_rn(a, b);
-}
-
-__device__ __forceinline__ void ld_w4(const double* __restrict__ p, double (&w)[4]) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
-  w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
-}
-
-// acc += v * w in the reference's arithmetic (rounded product, then rounded sum), norm += w
-__device__ __forceinline__ void acc4(const float4 v, const double (&w)[4], double (&acc)[4]) {
-  acc[0] = __dadd_rn(acc[0], __dmul_rn((double)v.x, w[0]));
-  acc[1] = __dadd_rn(acc[1], __dmul_rn((double)v.y, w[1]));
-  acc[2] = __dadd_rn(acc[2], __dmul_rn((double)v.z, w[2]));
-  acc[3] = __dadd_rn(acc[3], __dmul_rn((double)v.w, w[3]));
-}
-
-// Periodic formulation of the float32 / one-channel merge for tile <= 2 * step (at most two covering crops per axis).
+// ---- periodic merge (float32 probabilities, one channel, tile <= 2 * step) ----------------------------------------
 // Canvas pixel X = kx*step + r is covered by crop kx at tile column r and, when r < tile - step, by crop kx-1 at column
-// r + step: the weights a pixel needs depend only on its residues (X mod step, Y mod step).  A thread therefore owns
-// four consecutive residues of one image row, loads its <= 16 float64 weights ONCE, precomputes the (loop-invariant)
-// norm and its reciprocal, and walks the ~13 periods of the row: per pixel only the tile values move (177 MB read,
-// 125 MB written per 5000x5000 image; the gather kernel above re-reads 16 B of weights per covering crop and pixel
-// through L2, ~700 MB).  Pixels covered by a single crop are q = RN32(RN64(RN64(v*w) / w)) = v exactly (the float64 round
-// trip perturbs v by < 2^-52 relative, far inside the float32 rounding interval), so they are copied when w >= eps.
-// Accumulation order (crop order: y outer, x inner), rounded products and the IEEE quotient are those of
+// r + step: the weights a pixel needs depend only on its residues (X mod step, Y mod step).  A thread owns PX
+// consecutive residues of one image row, reads its <= 4*PX float64 weights ONCE, precomputes the loop-invariant norm and
+// its correctly rounded reciprocal, and walks the periods of the row: per pixel only the tile values move.
+//   * single-cover pixels: q = RN32(RN64(RN64(v*w) / w)) = v exactly (the float64 round trip perturbs v by < 2^-52
+//     relative, far inside the float32 rounding interval), so they are copied when eps <= w < 2^60;
+//   * a / b with b invariant: y = RN(1/b) (__drcp_rn), q0 = RN(a*y), then two FMA corrections.  q1 is within half an ulp
+//     + 2^-104 of a/b; by Markstein's theorem (y correctly rounded, q1 faithful, r1 = a - b*q1 exact) q2 = RN(q1 + r1*y)
+//     IS the correctly rounded quotient, i.e. bit-equal to numpy's float64 division (tests/test_host_logic.py checks
+//     the sequence against exact rational arithmetic).  Valid while nothing under/overflows: b is kept in
+//     [eps, 2^60) and a float32 result in [2^-100, FLT_MAX] proves a was in range; anything else (except a == 0, for
+//     which the sequence returns +0 exactly) takes the IEEE division;
+//   * periods at the canvas edge (a crop of the pattern does not exist) and exotic weights take a slow, obviously
+//     correct routine.
+// Accumulation order (crop order: y outer, x inner), rounded products and the quotient are those of
 // lib/tiles.py:146-161, hence bit-exact.
-__global__ void __launch_bounds__(256) merge_f32c1_period_kernel(SlicerGeom g, const float* __restrict__ tiles,
-                                                                 const double* __restrict__ weight,
-                                                                 float* __restrict__ out, uint8_t* __restrict__ mask,
-                                                                 float thr) {
-  const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w, H = (int)g.image_h;
-  const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y, ov = T - S, ml = (int)g.margin_left;
-  const int r = threadIdx.x * 4;
-  const int y = blockIdx.x * blockDim.y + threadIdx.y;
-  if (r >= S || y >= H) return;
-  const int Y = y + (int)g.margin_top;
-  const int ky = Y / S, ry = Y - ky * S;
-  const bool up = ky >= 1 && ry < ov;                 // crop row ky-1 covers Y (first in crop order)
-  const bool two_rows = up && ky <= tiles_y - 1;
-  const int iy0 = up ? ky - 1 : ky;
-  const int ty0 = Y - iy0 * S;
-  const bool hasA = r < ov;                           // the crop to the left (kx-1) also covers the pixel
-  double wA0[4] = {0, 0, 0, 0}, wB0[4], wA1[4] = {0, 0, 0, 0}, wB1[4] = {0, 0, 0, 0};
-  ld_w4(weight + ty0 * T + r, wB0);
-  if (hasA) ld_w4(weight + ty0 * T + r + S, wA0);
-  if (two_rows) {
-    ld_w4(weight + (ty0 - S) * T + r, wB1);
-    if (hasA) ld_w4(weight + (ty0 - S) * T + r + S, wA1);
-  }
-  // interior periods: every crop of the pattern exists
-  double nrm[4], rcp[4];
-  bool fast = true, copy = !hasA && !two_rows;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    double n = 0.0;
-    if (hasA) n = __dadd_rn(n, wA0[e]);
-    n = __dadd_rn(n, wB0[e]);
-    if (two_rows) {
-      if (hasA) n = __dadd_rn(n, wA1[e]);
-      n = __dadd_rn(n, wB1[e]);
-    }
-    copy = copy && wB0[e] >= DBL_EPSILON && wB0[e] < 0x1p60;
-    n = n < DBL_EPSILON ? DBL_EPSILON : n;            // np.clip(norm, eps, None)
-    fast = fast && n < 0x1p60;                        // NaN / huge weights take the IEEE division
-    nrm[e] = n;
-    rcp[e] = __drcp_rn(n);
-  }
-  // periods with an output pixel: ml <= kx*S + r <= ml + W - 4
-  const int kx_lo = ml > r ? (ml - r + S - 1) / S : 0;
-  int kx_hi = ml + W - 4 - r >= 0 ? (ml + W - 4 - r) / S : -1;
-  kx_hi = min(kx_hi, tiles_x - 1 + (hasA ? 1 : 0));
-  const int64_t TT = (int64_t)T * T;
-  const float* pB0 = tiles + ((int64_t)iy0 * tiles_x * T + ty0) * T + r;      // crop (iy0, kx = 0), advanced by kx*TT
-  const int64_t dA = S - TT, d1 = (int64_t)tiles_x * TT - (int64_t)S * T;       // crop to the left / crop row below
-  float* orow = out ? out + (int64_t)y * W - ml + r : nullptr;
-  uint8_t* mrow = mask ? mask + (int64_t)y * W - ml + r : nullptr;
+//
+// Operands are staged in shared memory by 1-D bulk copies (cp.async.bulk -> mbarrier): a row needs the tile row `ty` of
+// every crop in its 1-2 covering crop rows (tiles_x * T floats each, contiguous per crop) and the matching weight rows
+// (T doubles).  Bytes in flight per SM are then set by the staged rows (30-60 KB each), not by registers, and every
+// tile element is read from HBM exactly once, every output byte written once (algorithmic traffic).
+__device__ __forceinline__ float div_by_invariant_fast(double a, double b, double y) {
+  const double q0 = __dmul_rn(a, y);
+  const double r0 = __fma_rn(-b, q0, a);
+  const double q1 = __fma_rn(r0, y, q0);
+  const double r1 = __fma_rn(-b, q1, a);
+  return __double2float_rn(__fma_rn(r1, y, q1));
+}
+// the fast quotient is proven when its float32 value is in [2^-100, FLT_MAX] (a was in range) or a == 0 (it returned +0)
+__device__ __forceinline__ bool div_by_invariant_ok(float f, double a) {
+  return (fabsf(f) >= 0x1p-100f && fabsf(f) <= FLT_MAX) || a == 0.0;
+}
 
-  auto emit = [&](int kx, const float (&q)[4]) {
-    const int64_t o = (int64_t)kx * S;
-    if (orow) *reinterpret_cast<float4*>(orow + o) = make_float4(q[0], q[1], q[2], q[3]);
-    if (mrow)
-      *reinterpret_cast<uchar4*>(mrow + o) =
-          make_uchar4(q[0] > thr ? 255 : 0, q[1] > thr ? 255 : 0, q[2] > thr ? 255 : 0, q[3] > thr ? 255 : 0);
-  };
-  // a period at the canvas edge: some crops of the pattern do not exist; norm on the fly, IEEE division
-  auto edge = [&](int kx) {
-    const bool useA = hasA && kx >= 1, useB = kx <= tiles_x - 1;
-    const float* p = pB0 + kx * TT;
-    double acc[4] = {0, 0, 0, 0}, n[4] = {0, 0, 0, 0};
-    if (useA) {
-      acc4(__ldg(reinterpret_cast<const float4*>(p + dA)), wA0, acc);
+template <int PX>
+__device__ __forceinline__ void lds_px(const float* p, float (&v)[PX]) {
+  if constexpr (PX == 4) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else if constexpr (PX == 2) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+  else v[0] = *p;
+}
+
+template <int PX>
+__device__ __forceinline__ void lds_w(const double* p, double (&w)[PX]) {
+  if constexpr (PX >= 2) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wA0[e]);
+    for (int e = 0; e < PX; e += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(p + e);
+      w[e] = t.x; w[e + 1] = t.y;
     }
-    if (useB) {
-      acc4(__ldg(reinterpret_cast<const float4*>(p)), wB0, acc);
+  } else w[0] = *p;
+}
+
+// acc += v * w in the reference's arithmetic (rounded product, then rounded sum)
+template <int PX>
+__device__ __forceinline__ void accp(const float (&v)[PX], const double (&w)[PX], double (&acc)[PX]) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wB0[e]);
-    }
-    if (two_rows) {
+  for (int e = 0; e < PX; ++e) acc[e] = __dadd_rn(acc[e], __dmul_rn((double)v[e], w[e]));
+}
+
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+__device__ __forceinline__ void store_px(float* o, uint8_t* m, const float (&q)[PX], float thr) {
+  if constexpr (HAS_OUT) {
+    if constexpr (PX == 4) *reinterpret_cast<float4*>(o) = make_float4(q[0], q[1], q[2], q[3]);
+    else if constexpr (PX == 2) *reinterpret_cast<float2*>(o) = make_float2(q[0], q[1]);
+    else *o = q[0];
+  }
+  if constexpr (HAS_MASK) {
+    if constexpr (PX == 4)
+      *reinterpret_cast<uchar4*>(m) = make_uchar4(q[0] > thr ? 255 : 0, q[1] > thr ? 255 : 0, q[2] > thr ? 255 : 0, q[3] > thr ? 255 : 0);
+    else if constexpr (PX == 2) *reinterpret_cast<uchar2*>(m) = make_uchar2(q[0] > thr ? 255 : 0, q[1] > thr ? 255 : 0);
+    else *m = q[0] > thr ? 255 : 0;
+  }
+}
+
+// One period, any crop pattern, any weights: norm on the fly, IEEE division.  Self-contained (re-reads its weights from
+// shared memory) and not inlined: it runs for the 1-2 edge periods of a row and for exotic weights only.
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+__device__ __noinline__ void merge_slow_period(const double* sw0, const double* sw1, const float* st0r, int row2_off, int T,
+                                               int S, int tiles_x, int r, bool two_rows, int kx, float* o, uint8_t* m,
+                                               float thr) {
+  const bool useA = r < T - S && kx >= 1, useB = kx <= tiles_x - 1;
+  float q[PX];
+#pragma unroll
+  for (int e = 0; e < PX; ++e) {
+    double acc = 0.0, n = 0.0;
+    for (int row = 0; row < (two_rows ? 2 : 1); ++row) {
+      const double* sw = row ? sw1 : sw0;
+      const float* st = st0r + row * row2_off + kx * T + e;
       if (useA) {
-        acc4(__ldg(reinterpret_cast<const float4*>(p + d1 + dA)), wA1, acc);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wA1[e]);
+        const double w = sw[r + S + e];
+        acc = __dadd_rn(acc, __dmul_rn((double)st[S - T], w));
+        n = __dadd_rn(n, w);
       }
       if (useB) {
-        acc4(__ldg(reinterpret_cast<const float4*>(p + d1)), wB1, acc);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) n[e] = __dadd_rn(n[e], wB1[e]);
+        const double w = sw[r + e];
+        acc = __dadd_rn(acc, __dmul_rn((double)st[0], w));
+        n = __dadd_rn(n, w);
       }
     }
-    float q[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) q[e] = __double2float_rn(__ddiv_rn(acc[e], n[e] < DBL_EPSILON ? DBL_EPSILON : n[e]));
-    emit(kx, q);
-  };
+    q[e] = __double2float_rn(__ddiv_rn(acc, n < DBL_EPSILON ? DBL_EPSILON : n));   // np.clip(norm, eps, None)
+  }
+  store_px<PX, HAS_OUT, HAS_MASK>(o, m, q, thr);
+}
 
-  int k0 = kx_lo, k1 = kx_hi;
-  if (k0 <= k1 && hasA && k0 == 0) edge(k0++);
-  if (k0 <= k1 && k1 >= tiles_x) edge(k1--);
+// U interior periods of one thread, `pstep` floats / `ostep` pixels apart: every load is issued first, the U * PX
+// accumulate-and-divide chains are independent (they interleave in the FP64 pipe), and ONE deferred branch covers the
+// never-taken IEEE-division fallback, so nothing serialises the chains.
+template <int PX, bool A, bool TWO, int U, bool HAS_OUT, bool HAS_MASK>
+__device__ __forceinline__ void merge_periods(const float* p, int row2_off, int dA, int pstep, int ostep,
+                                              const double (&wA0)[PX], const double (&wB0)[PX], const double (&wA1)[PX],
+                                              const double (&wB1)[PX], const double (&nrm)[PX], const double (&rcp)[PX],
+                                              float* o, uint8_t* m, float thr) {
+  float vA0[U][PX], vB0[U][PX], vA1[U][PX], vB1[U][PX];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float* pu = p + u * pstep;
+    if constexpr (A) lds_px<PX>(pu + dA, vA0[u]);
+    lds_px<PX>(pu, vB0[u]);
+    if constexpr (TWO) {
+      if constexpr (A) lds_px<PX>(pu + row2_off + dA, vA1[u]);
+      lds_px<PX>(pu + row2_off, vB1[u]);
+    }
+  }
+  double acc[U][PX];
+  float q[U][PX];
+  bool ok = true;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+#pragma unroll
+    for (int e = 0; e < PX; ++e) acc[u][e] = 0.0;
+    if constexpr (A) accp<PX>(vA0[u], wA0, acc[u]);
+    accp<PX>(vB0[u], wB0, acc[u]);
+    if constexpr (TWO) {
+      if constexpr (A) accp<PX>(vA1[u], wA1, acc[u]);
+      accp<PX>(vB1[u], wB1, acc[u]);
+    }
+#pragma unroll
+    for (int e = 0; e < PX; ++e) {
+      q[u][e] = div_by_invariant_fast(acc[u][e], nrm[e], rcp[e]);
+      ok = ok && div_by_invariant_ok(q[u][e], acc[u][e]);
+    }
+  }
+  if (!ok) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < PX; ++e) q[u][e] = __double2float_rn(__ddiv_rn(acc[u][e], nrm[e]));
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) store_px<PX, HAS_OUT, HAS_MASK>(o + u * ostep, m + u * ostep, q[u], thr);
+}
+
+// interior periods of one thread: `n` periods, `kstep` periods apart; A = the crop to the left also covers the pixel,
+// TWO = two crop rows cover the image row
+template <int PX, bool A, bool TWO, bool HAS_OUT, bool HAS_MASK>
+__device__ __forceinline__ void merge_interior(const float* p, int row2_off, int dA, int pstep, int ostep, int n,
+                                               const double (&wA0)[PX], const double (&wB0)[PX], const double (&wA1)[PX],
+                                               const double (&wB1)[PX], const double (&nrm)[PX], const double (&rcp)[PX],
+                                               float* o, uint8_t* m, float thr) {
+  constexpr int U = PX >= 4 ? 2 : 4;                  // 8 independent chains in flight (4 for PX == 1)
+  int it = 0;
+#pragma unroll 1
+  for (; it + U <= n; it += U, p += U * pstep, o += U * ostep, m += U * ostep)
+    merge_periods<PX, A, TWO, U, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
+#pragma unroll 1
+  for (; it < n; ++it, p += pstep, o += ostep, m += ostep)
+    merge_periods<PX, A, TWO, 1, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
+}
+
+// All periods kx = kfirst, kfirst + kstep, ... <= kx_hi of one thread (residues r .. r+PX-1) for one staged image row.
+// sw0/sw1: weight rows of the first/second covering crop row; st0r = staged tile rows + r (crop kx at kx*T, second crop
+// row row2_off floats further); orow/mrow = output row pointers at canvas x = 0 (pixel X lives at orow[X - ml]).
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+__device__ __forceinline__ void merge_row(int T, int S, int tiles_x, int ml, int r, bool two_rows, const double* sw0,
+                                          const double* sw1, const float* st0r, int row2_off, int kfirst, int kx_hi,
+                                          int kstep, float* out_row, uint8_t* mask_row, float thr) {
+  if (kfirst > kx_hi) return;
+  const bool hasA = r < T - S;
+  double wA0[PX], wB0[PX], wA1[PX], wB1[PX];
+#pragma unroll
+  for (int e = 0; e < PX; ++e) wA0[e] = wA1[e] = wB1[e] = 0.0;
+  lds_w<PX>(sw0 + r, wB0);
+  if (hasA) lds_w<PX>(sw0 + r + S, wA0);
+  if (two_rows) {
+    lds_w<PX>(sw1 + r, wB1);
+    if (hasA) lds_w<PX>(sw1 + r + S, wA1);
+  }
+  // single crop row: every pixel covered by ONE crop (no left neighbour, or an edge period) is a copy when the
+  // weight allows it; edge_copy says the same for the A-only / B-only edge periods of threads that have a left crop
+  bool w_ok = true, wa_ok = true;
+#pragma unroll
+  for (int e = 0; e < PX; ++e) {
+    w_ok = w_ok && wB0[e] >= DBL_EPSILON && wB0[e] < 0x1p60;
+    wa_ok = wa_ok && wA0[e] >= DBL_EPSILON && wA0[e] < 0x1p60;
+  }
+  const bool copy = !hasA && !two_rows && w_ok;
+  double nrm[PX], rcp[PX];
+  bool fast = true;
+#pragma unroll
+  for (int e = 0; e < PX; ++e) nrm[e] = rcp[e] = 1.0;
+  if (!copy) {
+#pragma unroll
+    for (int e = 0; e < PX; ++e) {
+      double n = 0.0;
+      if (hasA) n = __dadd_rn(n, wA0[e]);
+      n = __dadd_rn(n, wB0[e]);
+      if (two_rows) {
+        if (hasA) n = __dadd_rn(n, wA1[e]);
+        n = __dadd_rn(n, wB1[e]);
+      }
+      n = n < DBL_EPSILON ? DBL_EPSILON : n;          // np.clip(norm, eps, None)
+      fast = fast && n < 0x1p60;                      // NaN / huge weights take the slow routine
+      nrm[e] = n;
+      rcp[e] = __drcp_rn(n);
+    }
+  }
+  int kx = kfirst;
+  int n = (kx_hi - kx) / kstep + 1;
+  const int off0 = r - ml;                            // pixel of period kx sits at out_row[kx*S + off0]
+  auto slow = [&](int k) {
+    merge_slow_period<PX, HAS_OUT, HAS_MASK>(sw0, sw1, st0r, row2_off, T, S, tiles_x, r, two_rows, k,
+                                             HAS_OUT ? out_row + (k * S + off0) : nullptr,
+                                             HAS_MASK ? mask_row + (k * S + off0) : nullptr, thr);
+  };
+  // an edge period of a single-crop-row image row is covered by one crop: copy from column `col` of crop slot `k`
+  auto edge = [&](int k, bool from_left, bool ok_w) {
+    if (!two_rows && ok_w) {
+      float q[PX];
+      lds_px<PX>(st0r + k * T + (from_left ? S - T : 0), q);
+      store_px<PX, HAS_OUT, HAS_MASK>(HAS_OUT ? out_row + (k * S + off0) : nullptr,
+                                      HAS_MASK ? mask_row + (k * S + off0) : nullptr, q, thr);
+    } else {
+      slow(k);
+    }
+  };
+  if (!fast) {
+    for (; n > 0; --n, kx += kstep) slow(kx);
+    return;
+  }
+  if (hasA && kx == 0) { edge(0, false, w_ok); kx += kstep; --n; }    // no crop to the left of the first one
+  if (n > 0 && kx + (n - 1) * kstep >= tiles_x) { edge(kx + (n - 1) * kstep, true, wa_ok); --n; }   // right part of the last crop
+  if (n <= 0) return;
+  const float* p = st0r + kx * T;
+  float* o = HAS_OUT ? out_row + (kx * S + off0) : nullptr;
+  uint8_t* m = HAS_MASK ? mask_row + (kx * S + off0) : nullptr;
+  const int pstep = kstep * T, ostep = kstep * S, dA = S - T;
   if (copy) {
 #pragma unroll 4
-    for (int kx = k0; kx <= k1; ++kx) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(pB0 + kx * TT));
-      const float q[4] = {v.x, v.y, v.z, v.w};
-      emit(kx, q);
+    for (int it = 0; it < n; ++it, p += pstep, o += ostep, m += ostep) {
+      float q[PX];
+      lds_px<PX>(p, q);
+      store_px<PX, HAS_OUT, HAS_MASK>(o, m, q, thr);
+    }
+  } else if (two_rows) {
+    if (hasA) merge_interior<PX, true, true, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, n, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
+    else merge_interior<PX, false, true, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, n, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
+  } else {
+    if (hasA) merge_interior<PX, true, false, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, n, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
+    else merge_interior<PX, false, false, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, n, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
+  }
+}
+
+// geometry of image row y: covering crop rows (crop order) and the tile row of the first one
+struct MergeRow {
+  int n_rows, iy0, ty0;
+};
+__device__ __forceinline__ MergeRow merge_row_geom(int y, int mt, int T, int S, int tiles_y) {
+  const int Y = y + mt;
+  const int ky = Y / S, ry = Y - ky * S;
+  const bool up = ky >= 1 && ry < T - S;              // crop row ky-1 covers Y (first in crop order)
+  MergeRow g;
+  g.n_rows = (up && ky <= tiles_y - 1) ? 2 : 1;
+  g.iy0 = up ? ky - 1 : ky;
+  g.ty0 = Y - g.iy0 * S;
+  return g;
+}
+
+// bulk copies of one row's operands, issued by a full warp: the weight rows and the tile rows of crops [ix0, ix0 + nx);
+// stage = [sw0[T] | sw1[T] | st0[nx_max*T] | st1[nx_max*T]]
+__device__ __forceinline__ void merge_stage_row(const MergeRow& mr, int T, int S, int tiles_x, int ix0, int nx, int nx_max,
+                                                const float* tiles, const double* weight, double* sw0, uint64_t* bar,
+                                                int lane) {
+  float* st0 = reinterpret_cast<float*>(sw0 + 2 * T);
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(mr.n_rows * (T * 8 + nx * T * 4)));
+  __syncwarp();
+  for (int i = lane; i < mr.n_rows * (nx + 1); i += 32) {
+    if (i < mr.n_rows) {
+      bulk_load_1d(sw0 + i * T, weight + (mr.ty0 - i * S) * T, (uint32_t)T * 8, bar);
+    } else {
+      const int j = i - mr.n_rows, rr = j / nx, ix = j - rr * nx;
+      bulk_load_1d(st0 + (rr * nx_max + ix) * T,
+                   tiles + (((int64_t)(mr.iy0 + rr) * tiles_x + ix0 + ix) * T + (mr.ty0 - rr * S)) * T, (uint32_t)T * 4, bar);
+    }
+  }
+}
+
+// ---- variant 1: one CTA per (image row, segment of `kp` periods), S / PX threads, several CTAs resident per SM
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+__global__ void __launch_bounds__(1024 / PX > 256 ? 512 : 256) merge_f32c1_staged_kernel(
+    SlicerGeom g, const float* __restrict__ tiles, const double* __restrict__ weight, float* __restrict__ out,
+    uint8_t* __restrict__ mask, float thr, int xs, int kp) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w;
+  const int tiles_x = (int)g.tiles_x, ml = (int)g.margin_left;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(merge_smem);
+  double* sw0 = reinterpret_cast<double*>(merge_smem + 16);
+  const int y = blockIdx.x / xs, seg = blockIdx.x - y * xs;
+  // periods [k0, k1] of this segment need crops [k0 - 1, k1] clipped to the crop grid
+  const int k0 = seg * kp, k1 = min(k0 + kp - 1, tiles_x);
+  const int ix0 = max(k0 - 1, 0), nx = min(k1, tiles_x - 1) - ix0 + 1, nx_max = kp + 1;
+  const MergeRow mr = merge_row_geom(y, (int)g.margin_top, T, S, (int)g.tiles_y);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) merge_stage_row(mr, T, S, tiles_x, ix0, nx, nx_max, tiles, weight, sw0, bar, threadIdx.x);
+  const int r = threadIdx.x * PX;
+  if (r >= S) return;
+  // periods with an output pixel: ml <= kx*S + r <= ml + W - PX; the last one may be the right part of the last crop
+  const int kx_lo = max(ml > r ? (ml - r + S - 1) / S : 0, k0);
+  int kx_hi = ml + W - PX - r >= 0 ? (ml + W - PX - r) / S : -1;
+  kx_hi = min(min(kx_hi, tiles_x - 1 + (r < T - S ? 1 : 0)), k1);
+  mbar_wait(bar, 0);
+  merge_row<PX, HAS_OUT, HAS_MASK>(T, S, tiles_x, ml, r, mr.n_rows == 2, sw0, sw0 + T,
+                                   reinterpret_cast<const float*>(sw0 + 2 * T) + r - ix0 * T, nx_max * T, kx_lo, kx_hi, 1,
+                                   out + (int64_t)y * W, mask + (int64_t)y * W, thr);
+}
+
+// ---- variant 2: persistent CTAs (one per SM) with a producer warp keeping a ring of staged rows full; 24 consumer
+// warps share a staged row: consumer (kgroup, residue group) handles periods kx = kx_lo + kgroup, + KG, ...
+constexpr int kMergeConsumers = 768;
+
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+__global__ void __launch_bounds__(kMergeConsumers + 32, 1) merge_f32c1_ring_kernel(
+    SlicerGeom g, const float* __restrict__ tiles, const double* __restrict__ weight, float* __restrict__ out,
+    uint8_t* __restrict__ mask, float thr, int n_stages, int stage_bytes) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w, H = (int)g.image_h;
+  const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y, ml = (int)g.margin_left, mt = (int)g.margin_top;
+  uint64_t* full = reinterpret_cast<uint64_t*>(merge_smem);      // [8]
+  uint64_t* empty = full + 8;                                    // [8]
+  uint8_t* stage0 = merge_smem + 128;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kMergeConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    int s = 0;
+    uint32_t par = 1;                                  // waiting on parity 1 of a fresh barrier returns immediately
+    for (int y = blockIdx.x; y < H; y += gridDim.x) {
+      const MergeRow mr = merge_row_geom(y, mt, T, S, tiles_y);
+      mbar_wait(&empty[s], par);
+      merge_stage_row(mr, T, S, tiles_x, 0, tiles_x, tiles_x, tiles, weight,
+                      reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes), &full[s], lane);
+      if (++s == n_stages) { s = 0; par ^= 1; }
     }
     return;
   }
-#pragma unroll 2
-  for (int kx = k0; kx <= k1; ++kx) {
-    const float* p = pB0 + kx * TT;
-    float4 vA0 = make_float4(0.f, 0.f, 0.f, 0.f), vA1 = vA0, vB1 = vA0;
-    const float4 vB0 = __ldg(reinterpret_cast<const float4*>(p));
-    if (hasA) vA0 = __ldg(reinterpret_cast<const float4*>(p + dA));
-    if (two_rows) {
-      vB1 = __ldg(reinterpret_cast<const float4*>(p + d1));
-      if (hasA) vA1 = __ldg(reinterpret_cast<const float4*>(p + d1 + dA));
-    }
-    double acc[4] = {0, 0, 0, 0};
-    if (hasA) acc4(vA0, wA0, acc);
-    acc4(vB0, wB0, acc);
-    if (two_rows) {
-      if (hasA) acc4(vA1, wA1, acc);
-      acc4(vB1, wB1, acc);
-    }
-    float q[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      q[e] = __double2float_rn(fast ? div_by_invariant(acc[e], nrm[e], rcp[e]) : __ddiv_rn(acc[e], nrm[e]));
-    emit(kx, q);
+  const int ctid = threadIdx.x - 32;
+  const int RG = S / PX;                               // residue groups per period
+  const int KG = kMergeConsumers / RG;                 // period groups
+  const int kgroup = ctid / RG;
+  const int r = (ctid - kgroup * RG) * PX;
+  const int kx_lo = ml > r ? (ml - r + S - 1) / S : 0;
+  int kx_hi = ml + W - PX - r >= 0 ? (ml + W - PX - r) / S : -1;
+  kx_hi = min(kx_hi, tiles_x - 1 + (r < T - S ? 1 : 0));
+  if (kgroup >= KG) kx_hi = -1;                        // spare threads only take part in the barriers
+  int s = 0;
+  uint32_t par = 0;
+  for (int y = blockIdx.x; y < H; y += gridDim.x) {
+    const MergeRow mr = merge_row_geom(y, mt, T, S, tiles_y);
+    const double* sw0 = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+    mbar_wait(&full[s], par);
+    merge_row<PX, HAS_OUT, HAS_MASK>(T, S, tiles_x, ml, r, mr.n_rows == 2, sw0, sw0 + T,
+                                     reinterpret_cast<const float*>(sw0 + 2 * T) + r, tiles_x * T, kx_lo + kgroup, kx_hi, KG,
+                                     out + (int64_t)y * W, mask + (int64_t)y * W, thr);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);              // this warp is done reading the stage
+    if (++s == n_stages) { s = 0; par ^= 1; }
   }
+}
+
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+static bool launch_merge_ring(const SlicerGeom& g, const float* tiles, const double* weight, float* out, uint8_t* mask,
+                              float thr, cudaStream_t st) {
+  const int64_t stage = 16 * g.tile + 8 * g.tile * g.tiles_x;
+  if (g.step / PX > kMergeConsumers || g.step % PX) return false;
+  int n_stages = (int)std::min<int64_t>(8, (227 * 1024 - 128) / stage);
+  if (const char* e = std::getenv("SNB_MERGE_STAGES")) n_stages = std::min(n_stages, std::max(1, std::atoi(e)));
+  if (n_stages < 2) return false;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(merge_f32c1_ring_kernel<PX, HAS_OUT, HAS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess)
+      return false;
+    configured = true;
+  }
+  const int grid = (int)std::min<int64_t>(sm_count(), g.image_h);
+  merge_f32c1_ring_kernel<PX, HAS_OUT, HAS_MASK><<<grid, kMergeConsumers + 32, 128 + (size_t)n_stages * stage, st>>>(
+      g, tiles, weight, out, mask, thr, n_stages, (int)stage);
+  return true;
+}
+
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const double* weight, float* out, uint8_t* mask,
+                                float thr, cudaStream_t st) {
+  const int threads = (int)((g.step / PX + 31) / 32 * 32);
+  if (g.step % PX || threads > (1024 / PX > 256 ? 512 : 256)) return false;
+  // A CTA walks `kp` periods of one row (xs segments per row).  Measured on B200 (tools/merge_bench.py): ~10-14 periods
+  // per thread amortise the per-row setup (weights, norm, reciprocal) best; fewer periods lose to that setup and to the
+  // weight rows every CTA stages, more periods (one CTA per 45-period row at 224/112) leave too few CTAs per SM.
+  const int64_t periods = g.tiles_x + 1;
+  int64_t xs = periods <= 16 ? 1 : (periods + 9) / 10;
+  if (const char* e = std::getenv("SNB_MERGE_XS")) xs = std::max(1, std::min<int>((int)periods, std::atoi(e)));
+  int64_t kp = (periods + xs - 1) / xs;
+  while (kp > 1 && 16 + 2 * (g.tile * 8 + (kp + 1) * g.tile * 4) > 100 * 1024) --kp;   // >= 2 CTAs per SM
+  xs = (periods + kp - 1) / kp;
+  const size_t smem = 16 + 2 * (size_t)(g.tile * 8 + (kp + 1) * g.tile * 4);
+  if (smem > 227 * 1024 || g.image_h * xs > INT32_MAX) return false;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess)
+      return false;
+    configured = true;
+  }
+  merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK><<<(unsigned)(g.image_h * xs), threads, smem, st>>>(
+      g, tiles, weight, out, mask, thr, (int)xs, (int)kp);
+  return true;
+}
+
+// mode: 's' = CTA per row, 'r' = persistent ring; px = pixels per thread
+template <bool HAS_OUT, bool HAS_MASK>
+static bool launch_merge_periodic(char mode, int px, const SlicerGeom& g, const float* tiles, const double* weight,
+                                  float* out, uint8_t* mask, float thr, cudaStream_t st) {
+  if (mode == 'r') {
+    if (px == 1) return launch_merge_ring<1, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
+    if (px == 2) return launch_merge_ring<2, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
+    return launch_merge_ring<4, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
+  }
+  if (px == 1) return launch_merge_staged<1, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
+  if (px == 2) return launch_merge_staged<2, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
+  return launch_merge_staged<4, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
 }
 
 static int grid_for(int64_t total, int block) {
@@ -805,13 +1090,22 @@ extern "C" int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtyp
       g.margin_left % 4 == 0 && g.image_w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_tiles) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0) {
-    static const bool use_gather = std::getenv("SNB_MERGE_GATHER") != nullptr;   // A/B switch for profiles/
-    if (g.tile <= 2 * g.step && g.step / 4 <= 256 && !use_gather) {
-      // periodic kernel: blockDim = (step / 4 residue groups, rows that fit in 256 threads)
-      const int bx = (int)(g.step / 4), by = std::max(1, 256 / bx);
-      merge_f32c1_period_kernel<<<(unsigned)((g.image_h + by - 1) / by), dim3(bx, by), 0, st>>>(
-          g, static_cast<const float*>(d_tiles), d_weight, static_cast<float*>(d_out), d_mask, thr);
-    } else {
+    // SNB_MERGE_MODE: "staged1|2|4" = CTA per row, "ring1|2|4" = persistent ring, "gather" = the per-pixel gather kernel
+    const char* mode_env = std::getenv("SNB_MERGE_MODE");
+    const std::string mm = mode_env ? mode_env : "staged2";
+    bool done = false;
+    if (g.tile <= 2 * g.step && mm != "gather" && mm.size() >= 5) {
+      const float* tp = static_cast<const float*>(d_tiles);
+      float* op = static_cast<float*>(d_out);
+      const char mode = mm[0];
+      const int px = mm.back() - '0';
+      if (px == 1 || px == 2 || px == 4) {
+        if (op && d_mask) done = launch_merge_periodic<true, true>(mode, px, g, tp, d_weight, op, d_mask, thr, st);
+        else if (op) done = launch_merge_periodic<true, false>(mode, px, g, tp, d_weight, op, d_mask, thr, st);
+        else done = launch_merge_periodic<false, true>(mode, px, g, tp, d_weight, op, d_mask, thr, st);
+      }
+    }
+    if (!done) {
       const dim3 grid((unsigned)std::min<int64_t>((g.image_w / 4 + 255) / 256, 1024), (unsigned)g.image_h);
       merge_f32c1_vec4_kernel<<<grid, 256, 0, st>>>(g, static_cast<const float*>(d_tiles), d_weight,
                                                     static_cast<float*>(d_out), d_mask, thr);

@@ -619,7 +619,11 @@ class LinkNet34Plan:
 
         # ---- stem: 7x7/s2 conv + BN + ReLU as a GEMM over im2col rows, then MaxPool 3x3/s2
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        # network input: normalised float NCHW (what the tiled predictor's split kernel writes with LAYOUT_NCHW_F32)
+        self.x_nchw = torch.empty((n, 3, h, w), dtype=torch.float32, device=device)
         self.x_rows = S(h2, w2, self.STEM_K)
+        self.ops.append(SimpleOp("snb_stem7x7_rows", (N.c_vp(self.x_nchw.data_ptr()), n, 3, h, w,
+                                                      N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K), (self.x_nchw, self.x_rows)))
         wt, bs = fold(spec['stem'][0], None, spec['stem'][1])
         stem = S(h2, w2, 64)
         self.ops.append(ConvOp(N.CONV_1X1, self.x_rows.view(), stem.view(), pack_stem7x7(wt, self.STEM_K), bs.contiguous()))
@@ -694,11 +698,9 @@ class LinkNet34Plan:
         self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, pack_conv2x2(wt, 32, 32), _pad_vec(bs.detach().float(), 32),
                                relu=False, head=(pick, 0.0, sigmoid, self.out)))
         self.flops = sum(op.flops for op in self.ops)
-        self.launches = sum(op.launches for op in self.ops) + 1
+        self.launches = sum(op.launches for op in self.ops)
 
     def load_nchw(self, x):
-        x = x.contiguous()
-        N.check(N.lib().snb_stem7x7_rows(N.ptr(x), x.shape[0], x.shape[1], x.shape[2], x.shape[3],
-                                         N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K, N.stream_ptr()))
+        self.x_nchw.copy_(x)
 
     run = VGGUNetPlan.run

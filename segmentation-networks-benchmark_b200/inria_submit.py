@@ -85,9 +85,14 @@ class TiledPredictor:
         for begin in range(self.tile_begin, self.tile_end, self.batch):
             count = min(self.batch, self.tile_end - begin)
             for v in range(self.views):
-                layout = N.LAYOUT_PATCH32_F32 if self.plan.x_patch.t.dtype == torch.float32 else N.LAYOUT_PATCH32
+                x_nchw = getattr(self.plan, "x_nchw", None)
+                if x_nchw is not None:      # plans that take normalised float NCHW tiles (LinkNet34's 7x7 stem)
+                    layout, target = N.LAYOUT_NCHW_F32, x_nchw.data_ptr()
+                else:                       # first conv3x3 as a K=32 GEMM over PATCH32 rows
+                    layout = N.LAYOUT_PATCH32_F32 if self.plan.x_patch.t.dtype == torch.float32 else N.LAYOUT_PATCH32
+                    target = self.plan.x_patch.t.data_ptr()
                 N.check(lib.snb_split_norm_u8(self.slicer.handle, N.ptr(d_image), self.channels, N.ptr(self.lut), v,
-                                              layout, N.c_vp(self.plan.x_patch.t.data_ptr()), begin, count, st))
+                                              layout, N.c_vp(target), begin, count, st))
                 out = self.plan.run()
                 self.probs[begin:begin + count, v, :, :, 0].copy_(out[:count])
         if self.do_merge:

@@ -122,3 +122,28 @@ def test_predict_tiled_tf32_mode(cuda, golden_dir, tta):
     assert err < 2e-3, err      # He-scaled synthetic weights: plain TF32 gives ~1e-3 (1e-4 holds on random-init weights)
     flips = sub.mask_from_probability(merged) != g[("tta" if tta else "plain") + "_mask"]
     assert np.all(np.abs(want[flips] - 0.5) < 2e-3)
+
+
+def test_linknet34_through_the_tiled_predictor(cuda):
+    """LinkNet34 takes normalised float NCHW tiles (7x7 stem) instead of PATCH32 rows: split -> net -> merge on the
+    device against the oracle pipeline (normalise, split, LinkNet34 eval forward, sigmoid, pyramid merge)."""
+    from oracle import nets_oracle as no
+    from oracle import tiles_oracle as to
+    from snb_b200.lib.models import LinkNet34
+
+    sd = synth.linknet34_state_dict(seed=6)
+    m = LinkNet34(pretrained=False)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    image = synth.image_u8(12, 150, 130)
+    p = sub.TiledPredictor(m, image.shape, 64, 32, batch_size=5, tta=False)
+    merged, mask = p.predict_device(torch.from_numpy(image).cuda())
+    merged2, _ = p.predict_device(torch.from_numpy(image).cuda())               # CUDA-graph replay
+    assert torch.equal(merged, merged2)
+    x = to.normalize_image(image)
+    s = to.SlicerOracle(x.shape, 64, 32, weight="pyramid")
+    with torch.no_grad():
+        probs = torch.sigmoid(no.linknet34_forward(sd, torch.from_numpy(to.to_nchw_float(s.split(x))))).numpy()
+    want = s.merge(list(np.moveaxis(probs, 1, -1)), dtype=np.float32)
+    assert np.abs(merged.cpu().numpy() - want).max() < 2e-2
+    assert torch.equal(mask, ((merged > 0.5) * 255).to(torch.uint8))
