@@ -73,6 +73,7 @@ struct alignas(64) ConvParams {
                                    // the output grid and tap (dy,dx) reads input pixel (x+1+dx, y+1+dy))
   int32_t in_w, in_h;              // input extent (pre-activation prologue masks with it)
   float act_slope;                 // leaky-ReLU slope of the activation (0 = ReLU); only used when relu != 0
+  int32_t ext;                     // residual operand or leaky slope present: run the EXT epilogue body
   const float* pre_scale;          // optional pre-activation y = relu(x * scale[c] + shift[c]) applied to the A operand
   const float* pre_shift;
   int8_t tap_dy[kMaxPhases][kMaxTaps];
@@ -168,7 +169,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // Epilogue of one accumulator tile, executed by the 4 epilogue warps (128 threads = 128 TMEM lanes = 128 pixels).
 // TW = patch width in pixels (row r of the tile is pixel (r % TW, r / TW)).
-template <int BN, bool HEAD, int TW, int EB>
+// EXT = the ResNet / LinkNet extras (residual operand, leaky-ReLU slope); the VGG / UNet layers run the lean EXT = false
+// body: the high-resolution layers (K = 32..576 per 128 x 64 outputs) are bound by this epilogue, where the extra
+// selects and predicated adds cost 10-35 %.
+template <int BN, bool HEAD, int TW, int EB, bool EXT>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& tc, uint32_t t_addr,
                                               uint64_t* tmem_empty_bar, uint8_t* smem_out, uint32_t& n_store,
                                               int row, int lane, int epi_tid, bool release = true) {
@@ -192,8 +196,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
       float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
       if (p.relu) {
-        x0 = x0 > 0.f ? x0 : x0 * p.act_slope; x1 = x1 > 0.f ? x1 : x1 * p.act_slope;
-        x2 = x2 > 0.f ? x2 : x2 * p.act_slope; x3 = x3 > 0.f ? x3 : x3 * p.act_slope;
+        if constexpr (EXT) {
+          x0 = x0 > 0.f ? x0 : x0 * p.act_slope; x1 = x1 > 0.f ? x1 : x1 * p.act_slope;
+          x2 = x2 > 0.f ? x2 : x2 * p.act_slope; x3 = x3 > 0.f ? x3 : x3 * p.act_slope;
+        } else {
+          x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+        }
       }
       dot = fmaf(x0, w.x, dot); dot = fmaf(x1, w.y, dot); dot = fmaf(x2, w.z, dot); dot = fmaf(x3, w.w, dot);
     }
@@ -232,36 +240,43 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
                         __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
                         __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
                         __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
-          float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (p.residual != nullptr && res_ok) {
-            const int64_t ro = res_pix + tc.nt * BN + c * CW + g * 32 + j * 8;
-            if constexpr (EB == 2) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + ro));
-              const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          if constexpr (EXT) {
+            float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.residual != nullptr && res_ok) {
+              const int64_t ro = res_pix + tc.nt * BN + c * CW + g * 32 + j * 8;
+              if constexpr (EB == 2) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + ro));
+                const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t2 = __bfloat1622float2(pr[e]);
-                res[2 * e] = t2.x;
-                res[2 * e + 1] = t2.y;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = __bfloat1622float2(pr[e]);
+                  res[2 * e] = t2.x;
+                  res[2 * e + 1] = t2.y;
+                }
+              } else {
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + ro));
+                const float4 r1 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + ro) + 1);
+                res[0] = r0.x; res[1] = r0.y; res[2] = r0.z; res[3] = r0.w;
+                res[4] = r1.x; res[5] = r1.y; res[6] = r1.z; res[7] = r1.w;
               }
-            } else {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + ro));
-              const float4 r1 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + ro) + 1);
-              res[0] = r0.x; res[1] = r0.y; res[2] = r0.z; res[3] = r0.w;
-              res[4] = r1.x; res[5] = r1.y; res[6] = r1.z; res[7] = r1.w;
             }
-          }
-          if (!p.res_after_act) {
+            if (!p.res_after_act) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] += res[e];
-          }
-          if (p.relu) {
+              for (int e = 0; e < 8; ++e) f[e] += res[e];
+            }
+            if (p.relu) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.act_slope;
-          }
-          if (p.res_after_act) {
+              for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.act_slope;
+            }
+            if (p.res_after_act) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] += res[e];
+              for (int e = 0; e < 8; ++e) f[e] += res[e];
+            }
+          } else {
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
           }
           const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
           const int swp = OUT_SWZ == 128 ? (prow & 7) : ((prow >> 1) & 3);
@@ -433,7 +448,8 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       mbar_wait(&tmem_full[acc], acc_ph);
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_tile<BN, HEAD, TW, EB>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
+      if (p.ext) epilogue_tile<BN, HEAD, TW, EB, true>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
+      else epilogue_tile<BN, HEAD, TW, EB, false>(p, tc, t_addr, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid);
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
   }
@@ -718,8 +734,12 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
 #pragma unroll 1
       for (int ph = 0; ph < NPH; ++ph) {
         if (NPH > 1) tc.ph = ph;
-        epilogue_tile<BN, HEAD, TW, EB>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane, epi_tid,
-                                    ph == NPH - 1);
+        if (p.ext)
+          epilogue_tile<BN, HEAD, TW, EB, true>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane,
+                                                epi_tid, ph == NPH - 1);
+        else
+          epilogue_tile<BN, HEAD, TW, EB, false>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane,
+                                                 epi_tid, ph == NPH - 1);
       }
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
@@ -1073,6 +1093,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   p.residual = d->d_residual;
   p.res_cstride = static_cast<int32_t>(d->res_cstride);
   p.res_after_act = d->res_after_act;
+  p.ext = (has_res || d->act_slope != 0.f) ? 1 : 0;
 
   int rc;
   const uint64_t E = (uint64_t)eb;
