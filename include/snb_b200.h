@@ -22,6 +22,7 @@
  *   snb_loss_iou_*     BCEWithLogitsLossAndSmoothJaccard / JaccardScore /      lib/losses.py:31-75,
  *                      PixelAccuracy partial sums and integer counts           lib/metrics.py:9-40
  *   snb_pr_curve_*     PRCurveMeter.update                                     lib/train_utils.py:109-125
+ *   snb_abn_*          the `inplace_abn` backend calls of InPlaceABN            lib/modules/abn/functions.py:62-122
  *
  * Conventions: every pointer named `d_*` is a DEVICE pointer owned by the caller; sizes are int64_t; `stream`
  * is a cudaStream_t passed as void* (0 = legacy default stream).  All entry points enqueue work on `stream`
@@ -187,6 +188,24 @@ SNB_API int snb_maxpool3x3s2(const void* d_in, int64_t n, int64_t h, int64_t w, 
                      void* d_out, int64_t out_cstride, void* stream);
 SNB_API int snb_stem7x7_rows(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w, void* d_dst,
                      int64_t k_pad, void* stream);
+
+/* InPlaceABN (lib/modules/abn/bn.py:47-103, functions.py:62-122): in-place activated batch norm on a contiguous NCHW
+ * float tensor, hw = H * W.  The reference delegates the arithmetic to the external `inplace_abn` extension
+ * (mean_var, forward, leaky_relu_forward/backward, elu_forward/backward, edz_eydz, backward; functions.py:46-118),
+ * which is not vendored and has no pinned version: these entry points replace exactly that call surface.
+ *   activation: 0 none, 1 leaky_relu(slope), 2 elu.  d_weight / d_bias NULL = not affine.
+ *   forward : training != 0 -> batch mean / biased variance into d_mean / d_var (float[c]) and the momentum update of the
+ *             running statistics with the unbiased variance (functions.py:84-85); else the running statistics are used.
+ *             y = (x - mean) / sqrt(var + eps) * (|weight| + eps) + bias, activation, written over x.
+ *   backward: z = forward output, dz = its gradient, d_var = the variance the forward used.  dx may alias dz.
+ *             eval mode reproduces the reference (edz = eydz = 0: functions.py:110-112), so dweight = dbias = 0 there.
+ *   d_workspace: double[2 * c] scratch. */
+SNB_API int snb_abn_forward(float* d_x, int64_t n, int64_t c, int64_t hw, const float* d_weight, const float* d_bias,
+                    float* d_running_mean, float* d_running_var, int training, float momentum, float eps,
+                    int activation, float slope, float* d_mean, float* d_var, double* d_workspace, void* stream);
+SNB_API int snb_abn_backward(const float* d_z, const float* d_dz, int64_t n, int64_t c, int64_t hw, const float* d_var,
+                     const float* d_weight, const float* d_bias, int training, float eps, int activation, float slope,
+                     float* d_dx, float* d_dweight, float* d_dbias, double* d_workspace, void* stream);
 
 /* Pre-activation BatchNorm2d(eval) + ReLU of FCDenseNet's DenseLayer / TransitionDown (lib/models/tiramisu.py:12-13,
  * 50-51): out[.., c] = max(in[.., c] * scale[c] + shift[c], 0) for c < channels, 0 for channels <= c < channels_pad

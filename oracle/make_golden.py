@@ -47,7 +47,36 @@ def _install_inplace_abn_shim():
     def mean_var(x):
         return x.mean(dim=(0, 2, 3)), x.var(dim=(0, 2, 3), unbiased=False)
 
+    # backward half of the backend as published (inplace_abn_cuda.cu: leaky_relu_backward, edz_eydz, backward)
+    def leaky_relu_backward(z, dz, slope):
+        neg = z < 0
+        dz[neg] *= slope
+        z[neg] /= slope
+        return True
+
+    def _gamma_beta(z, weight, bias, affine, eps):
+        c = z.shape[1]
+        g = (weight.abs() + eps) if affine else torch.ones(c)
+        b = bias if affine else torch.zeros(c)
+        return g.view(1, -1, 1, 1), b.view(1, -1, 1, 1)
+
+    def edz_eydz(z, dz, weight, bias, affine, eps):
+        g, b = _gamma_beta(z, weight, bias, affine, eps)
+        y = (z - b) / g
+        return dz.sum(dim=(0, 2, 3)), (y * dz).sum(dim=(0, 2, 3))
+
+    def backward(z, dz, var, weight, bias, edz, eydz, affine, eps):
+        g, b = _gamma_beta(z, weight, bias, affine, eps)
+        count = z.numel() // z.shape[1]
+        y = (z - b) / g
+        mul = g * torch.rsqrt(var.view(1, -1, 1, 1) + eps)
+        dx = (dz - (edz / count).view(1, -1, 1, 1) - y * (eydz / count).view(1, -1, 1, 1)) * mul
+        dweight = torch.where(weight > 0, eydz, -eydz) if affine else dz.new_empty(0)
+        dbias = edz if affine else dz.new_empty(0)
+        return dx, dweight, dbias
+
     m.forward, m.leaky_relu_forward, m.mean_var = forward, leaky_relu_forward, mean_var
+    m.leaky_relu_backward, m.edz_eydz, m.backward = leaky_relu_backward, edz_eydz, backward
     sys.modules["inplace_abn"] = m
 
 
@@ -252,6 +281,46 @@ def linknet34_vectors():
                 logit_min=float(y.min()), logit_max=float(y.max()))
 
 
+def inplace_abn_vectors():
+    """lib.modules.abn.functions.InPlaceABN (the reference's own autograd glue: running-statistics update, saved tensors,
+    eval-mode shortcut) driven through the pure-torch stand-in for the un-vendored backend: training and eval mode,
+    forward outputs, updated running statistics and all three gradients."""
+    from lib.modules.abn.functions import InPlaceABN as RefABN
+
+    class Ctx:
+        """Stand-in for the autograd context: torch >= 2 rejects the reference's mark_dirty(x, running_mean,
+        running_var) ("dirty tensors must be outputs"), so its forward / backward bodies are called directly."""
+
+        def mark_dirty(self, *tensors):
+            pass
+
+        def save_for_backward(self, *tensors):
+            self.saved_tensors = tensors
+
+    rs = np.random.RandomState(21)
+    out = {}
+    x0 = rs.standard_normal((3, 6, 5, 8)).astype(np.float32) * 1.5 + 0.3
+    w0 = (rs.uniform(0.5, 1.5, 6) * np.where(rs.rand(6) < 0.4, -1, 1)).astype(np.float32)
+    b0 = (rs.standard_normal(6) * 0.2).astype(np.float32)
+    rm0 = (rs.standard_normal(6) * 0.1).astype(np.float32)
+    rv0 = rs.uniform(0.5, 1.5, 6).astype(np.float32)
+    g0 = rs.standard_normal(x0.shape).astype(np.float32)
+    out.update(x=x0, weight=w0, bias=b0, running_mean=rm0, running_var=rv0, grad=g0)
+    for mode, training in (("train", True), ("eval", False)):
+        w, b = torch.from_numpy(w0.copy()), torch.from_numpy(b0.copy())
+        rm, rv = torch.from_numpy(rm0.copy()), torch.from_numpy(rv0.copy())
+        ctx = Ctx()
+        with torch.no_grad():
+            z = RefABN.forward(ctx, torch.from_numpy(x0.copy()), w, b, rm, rv, training, 0.1, 1e-5, "leaky_relu", 0.01)
+            zc = z.clone()
+            grads = RefABN.backward(ctx, torch.from_numpy(g0.copy()))
+        out[mode + "_z"] = zc.numpy()
+        out[mode + "_running_mean"], out[mode + "_running_var"] = rm.numpy(), rv.numpy()
+        out[mode + "_dx"], out[mode + "_dweight"], out[mode + "_dbias"] = [t.numpy() for t in grads[:3]]
+    np.savez_compressed(os.path.join(OUT, "abn.npz"), **out)
+    return dict(shape=list(x0.shape))
+
+
 def predict_tiled_vector():
     """inria_submit.predict_tiled (:237-257) on CPU: same calls, without .cuda(); tile 64 / step 32, with and
     without D4 TTA, plus the submit threshold (:305)."""
@@ -288,7 +357,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(), fcdensenet67=fcdensenet_vectors(), linknet34=linknet34_vectors(),
+    kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(), fcdensenet67=fcdensenet_vectors(), linknet34=linknet34_vectors(), inplace_abn=inplace_abn_vectors(),
                 torch_version=torch.__version__, numpy_version=np.__version__)
     split_merge_vectors()
     normalize_vectors()

@@ -180,6 +180,65 @@ def linknet34_forward(sd, x, quant=None):
     return conv(q(f), 'finalconv3', padding=1)
 
 
+
+# ------------------------------------------------------------------------------------------------ InPlaceABN
+def _abn_act_forward(y, activation, slope):
+    if activation == 'leaky_relu':
+        return F.leaky_relu(y, slope)
+    if activation == 'elu':
+        return F.elu(y)
+    return y
+
+
+def inplace_abn_forward(x, weight, bias, running_mean, running_var, training=True, momentum=0.1, eps=1e-5,
+                        activation='leaky_relu', slope=0.01):
+    """InPlaceABN.forward (lib/modules/abn/functions.py:62-100) with the arithmetic of the un-vendored backend
+    (mapillary/inplace_abn, no pinned version -> parity unpinned): biased batch variance, running statistics updated with
+    the unbiased one (:84-85), y = (x - mean) * rsqrt(var + eps) * (|weight| + eps) + bias, then the activation.
+    Returns (z, var used, new running_mean, new running_var); nothing is modified in place."""
+    dims = [0] + list(range(2, x.dim()))
+    count = x.numel() // x.shape[1]
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    if training:
+        mean, var = x.mean(dim=dims), x.var(dim=dims, unbiased=False)
+        running_mean = running_mean * (1 - momentum) + momentum * mean
+        running_var = running_var * (1 - momentum) + momentum * var * count / (count - 1)
+    else:
+        mean, var = running_mean, running_var
+    gamma = weight.abs() + eps if weight is not None else torch.ones_like(mean)
+    beta = bias if bias is not None else torch.zeros_like(mean)
+    y = (x - mean.view(shape)) * (torch.rsqrt(var + eps) * gamma).view(shape) + beta.view(shape)
+    return _abn_act_forward(y, activation, slope), var, running_mean, running_var
+
+
+def inplace_abn_backward(z, dz, var, weight, bias, training=True, eps=1e-5, activation='leaky_relu', slope=0.01):
+    """InPlaceABN.backward (functions.py:102-122): undo the activation on (z, dz), edz / eydz reductions in training mode
+    (zeros in eval mode, the reference's own shortcut at :110-112), then the backend's backward:
+    dx = (dy - edz/count - xhat * eydz/count) * gamma * rsqrt(var + eps), dweight = eydz * sign(weight), dbias = edz."""
+    dims = [0] + list(range(2, z.dim()))
+    count = z.numel() // z.shape[1]
+    shape = [1, -1] + [1] * (z.dim() - 2)
+    if activation == 'leaky_relu':
+        dy = torch.where(z < 0, dz * slope, dz)
+        y = torch.where(z < 0, z / slope, z)
+    elif activation == 'elu':
+        dy = torch.where(z < 0, dz * (z + 1), dz)
+        y = torch.where(z < 0, torch.log1p(z), z)
+    else:
+        dy, y = dz, z
+    gamma = weight.abs() + eps if weight is not None else torch.ones_like(var)
+    beta = bias if bias is not None else torch.zeros_like(var)
+    xhat = (y - beta.view(shape)) / gamma.view(shape)
+    if training:
+        edz, eydz = dy.sum(dim=dims), (xhat * dy).sum(dim=dims)
+    else:
+        edz, eydz = torch.zeros_like(var), torch.zeros_like(var)
+    dx = (dy - (edz / count).view(shape) - xhat * (eydz / count).view(shape)) * (gamma * torch.rsqrt(var + eps)).view(shape)
+    if weight is None:
+        return dx, None, None
+    return dx, torch.where(weight > 0, eydz, -eydz), edz
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 

@@ -84,6 +84,10 @@ SIGNATURES = {
     "snb_space_to_depth2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_maxpool3x3s2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_stem7x7_rows": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_abn_forward": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float,
+                                c_int, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
+    "snb_abn_backward": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, ctypes.c_float, c_int,
+                                 ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),

@@ -1,0 +1,275 @@
+// InPlaceABN (in-place activated batch norm) on NCHW float32 tensors: the operator lib/modules/abn/functions.py:62-122
+// drives through the external `inplace_abn` extension (mapillary/inplace_abn; not vendored in the reference, no pinned
+// version -> parity unpinned at that boundary).  The arithmetic follows that library's published kernels:
+//   mean_var   : per-channel mean and BIASED variance over N x H x W
+//   forward    : y = (x - mean) / sqrt(var + eps) * (|weight| + eps) + bias, then the activation, in place
+//   edz_eydz   : after undoing the activation (z -> y, dz -> dy): edz = sum(dy), eydz = sum(xhat * dy),
+//                xhat = (y - bias) / (|weight| + eps)
+//   backward   : dx = (dy - edz / count - xhat * eydz / count) * (|weight| + eps) / sqrt(var + eps),
+//                dweight = eydz * sign(weight), dbias = edz     (eval mode: edz = eydz = 0 in dx, functions.py:110-112)
+// and the reference's own glue (functions.py:77-87): running_mean/var momentum update with the unbiased variance.
+// Everything is HBM-bound: per element 4 B read + 4 B written (forward), 8 B read + 4 B written (backward), plus one
+// 4 B (8 B) reduction pass in training mode.  One CTA per (channel, image-slab) slice, float4 loads when H*W % 4 == 0,
+// warp-shuffle + shared-memory block reduction, float64 atomics for the cross-CTA sums.
+#include <algorithm>
+#include <cstdint>
+
+#include "snb_internal.h"
+
+namespace snb {
+
+constexpr int kAbnThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of two doubles; result valid in thread 0
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double sa[kAbnThreads / 32], sb[kAbnThreads / 32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    a = l < kAbnThreads / 32 ? sa[l] : 0.0;
+    b = l < kAbnThreads / 32 ? sb[l] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+// activation codes: 0 none, 1 leaky_relu(slope), 2 elu
+__device__ __forceinline__ float act_fwd(float y, int act, float slope) {
+  if (act == 1) return y >= 0.f ? y : y * slope;
+  if (act == 2) return y >= 0.f ? y : expm1f(y);
+  return y;
+}
+// undo the activation: z -> y (pre-activation value), dz -> dy (leaky_relu_backward / elu_backward of the backend)
+__device__ __forceinline__ void act_bwd(float& z, float& dz, int act, float slope) {
+  if (act == 1) {
+    if (z < 0.f) { dz *= slope; z /= slope; }
+  } else if (act == 2) {
+    if (z < 0.f) { dz *= z + 1.f; z = log1pf(z); }
+  }
+}
+
+// grid = (C, slabs): CTA (c, s) reduces images n = s, s + slabs, ... of channel c.  sums[2c], sums[2c+1] += (sum x, sum x^2)
+__global__ void __launch_bounds__(kAbnThreads) abn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t HW,
+                                                                 double* __restrict__ sums) {
+  const int c = blockIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const float* p = x + ((int64_t)n * C + c) * HW;
+    if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      float fs = 0.f, fq = 0.f;   // float partials per thread over <= HW/1024 elements, folded into double below
+      int cnt = 0;
+      for (int64_t i = threadIdx.x; i < HW / 4; i += kAbnThreads) {
+        const float4 v = __ldg(p4 + i);
+        fs += (v.x + v.y) + (v.z + v.w);
+        fq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        if (++cnt == 16) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
+      }
+      s += fs;
+      q += fq;
+    } else {
+      for (int64_t i = threadIdx.x; i < HW; i += kAbnThreads) {
+        const double v = __ldg(p + i);
+        s += v;
+        q += v * v;
+      }
+    }
+  }
+  block_sum2(s, q);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 2 * c, s);
+    atomicAdd(sums + 2 * c + 1, q);
+  }
+}
+
+// mean / biased var from the sums; running stats update of functions.py:84-85 (unbiased variance, momentum)
+__global__ void abn_finalize_stats_kernel(const double* __restrict__ sums, int C, double count, float momentum,
+                                          float* __restrict__ mean, float* __restrict__ var,
+                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[2 * c] / count;
+  double v = sums[2 * c + 1] / count - m * m;
+  v = v < 0.0 ? 0.0 : v;
+  mean[c] = (float)m;
+  var[c] = (float)v;
+  if (running_mean) running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * (float)m;
+  if (running_var) running_var[c] = running_var[c] * (1.f - momentum) + (float)(momentum * v * count / (count - 1.0));
+}
+
+// grid = (N * C planes, chunks of the plane)
+__global__ void __launch_bounds__(kAbnThreads) abn_forward_kernel(float* __restrict__ x, int C, int64_t HW,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ var,
+                                                                   const float* __restrict__ weight,
+                                                                   const float* __restrict__ bias, float eps, int act,
+                                                                   float slope) {
+  const int64_t plane = blockIdx.x;
+  const int c = (int)(plane % C);
+  const float g = weight ? fabsf(__ldg(weight + c)) + eps : 1.f;
+  const float b = bias ? __ldg(bias + c) : 0.f;
+  const float m = __ldg(mean + c);
+  const float mul = g / sqrtf(__ldg(var + c) + eps);   // (x - mean) * invstd * gamma + beta, one rounding of the scale
+  float* p = x + plane * HW;
+  if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (int64_t i = blockIdx.y * (int64_t)kAbnThreads + threadIdx.x; i < HW / 4; i += (int64_t)gridDim.y * kAbnThreads) {
+      float4 v = p4[i];
+      v.x = act_fwd((v.x - m) * mul + b, act, slope);
+      v.y = act_fwd((v.y - m) * mul + b, act, slope);
+      v.z = act_fwd((v.z - m) * mul + b, act, slope);
+      v.w = act_fwd((v.w - m) * mul + b, act, slope);
+      p4[i] = v;
+    }
+  } else {
+    for (int64_t i = blockIdx.y * (int64_t)kAbnThreads + threadIdx.x; i < HW; i += (int64_t)gridDim.y * kAbnThreads)
+      p[i] = act_fwd((p[i] - m) * mul + b, act, slope);
+  }
+}
+
+// sums[2c] += sum(dy), sums[2c+1] += sum(xhat * dy) over the slabs of channel c
+__global__ void __launch_bounds__(kAbnThreads) abn_bwd_reduce_kernel(const float* __restrict__ z,
+                                                                      const float* __restrict__ dz, int N, int C,
+                                                                      int64_t HW, const float* __restrict__ weight,
+                                                                      const float* __restrict__ bias, float eps, int act,
+                                                                      float slope, double* __restrict__ sums) {
+  const int c = blockIdx.x;
+  const float g = weight ? fabsf(__ldg(weight + c)) + eps : 1.f;
+  const float b = bias ? __ldg(bias + c) : 0.f;
+  double s = 0.0, q = 0.0;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const int64_t base = ((int64_t)n * C + c) * HW;
+    float fs = 0.f, fq = 0.f;
+    int cnt = 0;
+    for (int64_t i = threadIdx.x; i < HW; i += kAbnThreads) {
+      float zz = __ldg(z + base + i), dd = __ldg(dz + base + i);
+      act_bwd(zz, dd, act, slope);
+      fs += dd;
+      fq += (zz - b) / g * dd;
+      if (++cnt == 32) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
+    }
+    s += fs;
+    q += fq;
+  }
+  block_sum2(s, q);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 2 * c, s);
+    atomicAdd(sums + 2 * c + 1, q);
+  }
+}
+
+// dx (may alias dz); z is restored to the pre-activation value only in registers
+__global__ void __launch_bounds__(kAbnThreads) abn_backward_kernel(const float* __restrict__ z, const float* dz, int C,
+                                                                    int64_t HW, const float* __restrict__ var,
+                                                                    const float* __restrict__ weight,
+                                                                    const float* __restrict__ bias,
+                                                                    const double* __restrict__ sums, double count,
+                                                                    int training, float eps, int act, float slope,
+                                                                    float* dx) {
+  const int64_t plane = blockIdx.x;
+  const int c = (int)(plane % C);
+  const float g = weight ? fabsf(__ldg(weight + c)) + eps : 1.f;
+  const float b = bias ? __ldg(bias + c) : 0.f;
+  const float mul = g / sqrtf(__ldg(var + c) + eps);
+  const float edz = training ? (float)(sums[2 * c] / count) : 0.f;
+  const float eydz = training ? (float)(sums[2 * c + 1] / count) : 0.f;
+  const int64_t base = plane * HW;
+  for (int64_t i = blockIdx.y * (int64_t)kAbnThreads + threadIdx.x; i < HW; i += (int64_t)gridDim.y * kAbnThreads) {
+    float zz = __ldg(z + base + i), dd = dz[base + i];
+    act_bwd(zz, dd, act, slope);
+    const float xhat = (zz - b) / g;
+    dx[base + i] = (dd - edz - xhat * eydz) * mul;
+  }
+}
+
+__global__ void abn_param_grads_kernel(const double* __restrict__ sums, const float* __restrict__ weight, int C,
+                                       float* __restrict__ dweight, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dweight) dweight[c] = (float)(__ldg(weight + c) > 0.f ? sums[2 * c + 1] : -sums[2 * c + 1]);
+  if (dbias) dbias[c] = (float)sums[2 * c];
+}
+
+static int abn_check(const void* x, int64_t n, int64_t c, int64_t hw, int act) {
+  if (!x) return fail(SNB_E_INVALID, "null tensor");
+  if (n <= 0 || c <= 0 || hw <= 0 || c > INT32_MAX || n > INT32_MAX || n * c > INT32_MAX)
+    return fail(SNB_E_INVALID, "bad shape n=%lld c=%lld hw=%lld", (long long)n, (long long)c, (long long)hw);
+  if (act < 0 || act > 2) return fail(SNB_E_INVALID, "activation must be 0 (none), 1 (leaky_relu) or 2 (elu)");
+  return SNB_OK;
+}
+
+static dim3 plane_grid(int64_t planes, int64_t hw) {
+  // enough CTAs for a few waves; a plane is split only when there are few planes
+  int64_t per_plane = (hw / 4 + kAbnThreads * 8 - 1) / (kAbnThreads * 8);
+  const int64_t cap = std::max<int64_t>(1, (int64_t)sm_count() * 32 / planes);
+  per_plane = std::max<int64_t>(1, std::min(per_plane, cap));
+  return dim3((unsigned)planes, (unsigned)per_plane);
+}
+
+static dim3 stats_grid(int64_t n, int64_t c) {
+  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)sm_count() * 8 / c));
+  return dim3((unsigned)c, (unsigned)slabs);
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int snb_abn_forward(float* d_x, int64_t n, int64_t c, int64_t hw, const float* d_weight, const float* d_bias,
+                               float* d_running_mean, float* d_running_var, int training, float momentum, float eps,
+                               int activation, float slope, float* d_mean, float* d_var, double* d_workspace,
+                               void* stream) {
+  if (int rc = abn_check(d_x, n, c, hw, activation)) return rc;
+  if ((d_weight == nullptr) != (d_bias == nullptr)) return fail(SNB_E_INVALID, "weight and bias come together (affine)");
+  if (!d_running_mean || !d_running_var) return fail(SNB_E_INVALID, "running statistics are required");
+  cudaStream_t st = as_stream(stream);
+  const float* mean = d_running_mean;
+  const float* var = d_running_var;
+  if (training) {
+    if (!d_mean || !d_var || !d_workspace) return fail(SNB_E_INVALID, "training mode needs mean / var outputs and a workspace");
+    if (n * hw < 2) return fail(SNB_E_INVALID, "training mode needs more than one value per channel");
+    SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * c, st));
+    abn_stats_kernel<<<stats_grid(n, c), kAbnThreads, 0, st>>>(d_x, (int)n, (int)c, hw, d_workspace);
+    abn_finalize_stats_kernel<<<(unsigned)((c + 127) / 128), 128, 0, st>>>(d_workspace, (int)c, (double)(n * hw), momentum,
+                                                                         d_mean, d_var, d_running_mean, d_running_var);
+    mean = d_mean;
+    var = d_var;
+  }
+  abn_forward_kernel<<<plane_grid(n * c, hw), kAbnThreads, 0, st>>>(d_x, (int)c, hw, mean, var, d_weight, d_bias, eps,
+                                                                   activation, slope);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_abn_backward(const float* d_z, const float* d_dz, int64_t n, int64_t c, int64_t hw, const float* d_var,
+                                const float* d_weight, const float* d_bias, int training, float eps, int activation,
+                                float slope, float* d_dx, float* d_dweight, float* d_dbias, double* d_workspace,
+                                void* stream) {
+  if (int rc = abn_check(d_z, n, c, hw, activation)) return rc;
+  if (!d_dz || !d_dx || !d_var || !d_workspace) return fail(SNB_E_INVALID, "snb_abn_backward: null argument");
+  if ((d_weight == nullptr) != (d_bias == nullptr)) return fail(SNB_E_INVALID, "weight and bias come together (affine)");
+  if ((d_dweight || d_dbias) && !d_weight) return fail(SNB_E_INVALID, "parameter gradients need the parameters");
+  cudaStream_t st = as_stream(stream);
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * c, st));
+  // eval mode: the reference passes edz = eydz = 0 to the backend (functions.py:110-112, its "TODO"), so dx has no
+  // mean terms and dweight = dbias = 0; reproduced as is
+  if (training)
+    abn_bwd_reduce_kernel<<<stats_grid(n, c), kAbnThreads, 0, st>>>(d_z, d_dz, (int)n, (int)c, hw, d_weight, d_bias, eps,
+                                                                   activation, slope, d_workspace);
+  abn_backward_kernel<<<plane_grid(n * c, hw), kAbnThreads, 0, st>>>(d_z, d_dz, (int)c, hw, d_var, d_weight, d_bias,
+                                                                    d_workspace, (double)(n * hw), training, eps,
+                                                                    activation, slope, d_dx);
+  if (d_dweight || d_dbias)
+    abn_param_grads_kernel<<<(unsigned)((c + 127) / 128), 128, 0, st>>>(d_workspace, d_weight, (int)c, d_dweight, d_dbias);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

@@ -16,19 +16,7 @@ from torch import nn
 
 from ... import _native as N
 from ...engine import LinkNet34Plan
-
-
-class InPlaceABN(nn.Module):
-    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, activation="leaky_relu", slope=0.01):
-        super().__init__()
-        if not affine or activation != "leaky_relu":
-            raise NotImplementedError("only the affine leaky_relu form used by LinkNet34 is supported")
-        self.num_features, self.eps, self.momentum, self.slope = num_features, eps, momentum, slope
-        self.affine, self.activation = affine, activation
-        self.weight = nn.Parameter(torch.ones(num_features))
-        self.bias = nn.Parameter(torch.zeros(num_features))
-        self.register_buffer('running_mean', torch.zeros(num_features))
-        self.register_buffer('running_var', torch.ones(num_features))
+from ..modules.abn import InPlaceABN
 
 
 class BasicBlock(nn.Module):

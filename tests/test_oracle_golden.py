@@ -181,3 +181,22 @@ def test_linknet34_logits(golden_dir, kats):
         y = no.linknet34_forward(sd, torch.from_numpy(g["x"])).numpy()
     assert y.shape == g["logits"].shape == (2, 1, 64, 96)
     assert np.abs(y - g["logits"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_inplace_abn_restatement(golden_dir, mode):
+    """oracle InPlaceABN forward / backward against the reference's own functions.py bodies (driven through the pure-torch
+    stand-in for the un-vendored `inplace_abn` backend: parity unpinned at that boundary, pinned for the glue)."""
+    g = np.load(os.path.join(golden_dir, "abn.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    training = mode == "train"
+    z, var, rm, rv = no.inplace_abn_forward(t("x"), t("weight"), t("bias"), t("running_mean"), t("running_var"), training)
+    assert np.abs(z.numpy() - g[mode + "_z"]).max() < 1e-5
+    assert np.abs(rm.numpy() - g[mode + "_running_mean"]).max() < 1e-6
+    assert np.abs(rv.numpy() - g[mode + "_running_var"]).max() < 1e-6
+    dx, dw, db = no.inplace_abn_backward(z, t("grad"), var, t("weight"), t("bias"), training)
+    assert np.abs(dx.numpy() - g[mode + "_dx"]).max() < 1e-5
+    assert np.abs(dw.numpy() - g[mode + "_dweight"]).max() < 2e-4
+    assert np.abs(db.numpy() - g[mode + "_dbias"]).max() < 2e-4
+    if not training:
+        assert not g["eval_dweight"].any() and not g["eval_dbias"].any()    # the reference's eval-mode shortcut
