@@ -227,6 +227,14 @@ SNB_API int snb_nhwc_bf16_to_nchw_f32(const void* d_in, int64_t n, int64_t h, in
 SNB_API int snb_loss_iou_reduce(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
                         double* d_sums, int64_t* d_counts, void* stream);
 
+/* Gradient of the fused loss with respect to the logits (what autograd computes through lib/losses.py:31-75):
+ * grad[i] = grad_out * d/dx_i [ c_bce * sum_i BCE_i + c_jac * SmoothJaccard ], with d_sums = the float64[4] output of
+ * snb_loss_iou_reduce on the same tensors (no host round trip) and d_grad_out a device scalar (NULL = 1).
+ * bce_jaccard: c_bce = bce_weight / ((bce_weight + jaccard_weight) * n), c_jac = jaccard_weight / (bce_weight +
+ * jaccard_weight), smooth = 100. */
+SNB_API int snb_loss_grad(const float* d_logits, const void* d_targets, int target_dtype, int64_t n, const double* d_sums,
+                  const float* d_grad_out, float c_bce, float c_jac, float smooth, float* d_grad_logits, void* stream);
+
 /* Same integer counts from probabilities already on the device (mask parity path): pred = prob > thr. */
 SNB_API int snb_confusion_counts(const float* d_probs, const void* d_targets, int target_dtype, int64_t n, float thr,
                          int64_t* d_counts, void* stream);

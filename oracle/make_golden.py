@@ -203,6 +203,23 @@ def loss_vectors():
             counts=[int((pred & t).sum()), int((pred & ~t).sum()), int((~pred & t).sum()), int((~pred & ~t).sum())],
             pr_tp=[int(v) for v in meter.tp], pr_tn=[int(v) for v in meter.tn],
             pr_fp=[int(v) for v in meter.fp], pr_fn=[int(v) for v in meter.fn])
+    # gradients of the three losses with respect to the logits (torch autograd through the reference's modules)
+    grads = {}
+    for seed, shape in [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))]:
+        logits, targets = synth.logits_targets(seed, shape)
+        for name, mod in (("bce_jaccard", ref_losses.BCEWithLogitsLossAndSmoothJaccard()),
+                          ("smooth_jaccard", ref_losses.SmoothJaccardLoss()),
+                          ("bce", ref_losses.BCEWithSigmoidLoss.__new__(ref_losses.BCEWithSigmoidLoss))):
+            if name == "bce":
+                torch.nn.Module.__init__(mod)
+                mod.size_average, mod.reduce = True, True
+            if name == "bce_jaccard":
+                mod.bce_loss.size_average, mod.bce_loss.reduce = True, True
+            x = logits.clone().requires_grad_(True)
+            (mod(x, targets) * 3.0).backward()          # a non-unit upstream gradient
+            g = x.grad.numpy().reshape(-1)
+            grads["seed%d_%s" % (seed, name)] = g if g.size < 5000 else g[::97].copy()
+    np.savez_compressed(os.path.join(OUT, "loss_grad.npz"), **grads)
     return out
 
 

@@ -91,6 +91,7 @@ SIGNATURES = {
     "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "snb_loss_grad": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp]),
     "snb_confusion_counts": (c_int, [c_vp, c_vp, c_int, c_i64, ctypes.c_float, c_vp, c_vp]),
     "snb_pr_curve_update": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }

@@ -222,6 +222,31 @@ static int reduce_grid(int64_t n_items) {
   return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
+// Gradient of c_bce * sum_i bce_i + c_jac * jaccard with respect to the logits (lib/losses.py:31-75 under autograd):
+//   bce_i = BCE-with-logits(z, t), z = logsigmoid(x):  d/dx = (sigmoid(z) - t) * dz/dx = (p / (1 + p) - t) * (1 - p)
+//   jaccard = 1 - A / D, A = sum p t + smooth, D = sum p + sum t - sum p t + smooth:
+//             d/dp_i = (A (1 - t_i) - t_i D) / D^2,  dp/dx = p (1 - p)
+// sums = {sum bce, sum p t, sum p, sum t} from snb_loss_iou_reduce of the same tensors; grad_out = upstream scalar
+// gradient on the device (NULL = 1), so no host synchronisation is needed.  4 B + target read, 4 B written per element.
+template <int DT>
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, const void* __restrict__ targets,
+                                                        int64_t n, const double* __restrict__ sums,
+                                                        const float* __restrict__ grad_out, float c_bce, float c_jac,
+                                                        float smooth, float* __restrict__ grad) {
+  const double A = sums[1] + smooth, D = sums[2] + sums[3] - sums[1] + smooth;
+  const float g = grad_out ? __ldg(grad_out) : 1.f;
+  const float jb = (float)(A / (D * D)) * c_jac * g;        // coefficient of (1 - t)
+  const float jt = (float)(1.0 / D) * c_jac * g;            // coefficient of t
+  const float cb = c_bce * g;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(logits + i);
+    const float t = load_target<DT>(targets, i);
+    const float p = sigmoid_f32(x);
+    const float q = 1.f - p;
+    grad[i] = q * (cb * (p / (1.f + p) - t) + p * (jb * (1.f - t) - jt * t));
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -251,6 +276,24 @@ extern "C" int snb_loss_iou_reduce(const float* d_logits, const void* d_targets,
   else loss_iou_kernel<SNB_DT_F32><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, cnt);
   SNB_LAUNCH_CHECK();
   loss_iou_finalize<<<1, 1, 0, st>>>(cnt, (unsigned long long)n);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_loss_grad(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
+                             const double* d_sums, const float* d_grad_out, float c_bce, float c_jac, float smooth,
+                             float* d_grad_logits, void* stream) {
+  if (!d_logits || !d_targets || !d_sums || !d_grad_logits) return fail(SNB_E_INVALID, "snb_loss_grad: null argument");
+  if (int rc = check_targets(d_targets, target_dtype, n, false)) return rc;
+  if (n == 0) return SNB_OK;
+  cudaStream_t st = as_stream(stream);
+  const int grid = reduce_grid(n);
+  if (target_dtype == SNB_DT_I64)
+    loss_grad_kernel<SNB_DT_I64><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, d_grad_out, c_bce, c_jac, smooth, d_grad_logits);
+  else if (target_dtype == SNB_DT_U8)
+    loss_grad_kernel<SNB_DT_U8><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, d_grad_out, c_bce, c_jac, smooth, d_grad_logits);
+  else
+    loss_grad_kernel<SNB_DT_F32><<<grid, 256, 0, st>>>(d_logits, d_targets, n, d_sums, d_grad_out, c_bce, c_jac, smooth, d_grad_logits);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

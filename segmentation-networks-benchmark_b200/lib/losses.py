@@ -3,8 +3,9 @@
 `snb_loss_iou_reduce` returns {sum bce, sum p*t, sum p, sum t} (+ integer tp/fp/fn/tn) in a single pass over
 logits and targets; the classes below turn those partial sums into the reference's scalars with the same
 formulas, including its quirk of feeding logsigmoid(x) into BCE-with-logits (lib/losses.py:51-53).
-Forward only (inference / validation path, torch_train.py:240-305): the outputs are 0-dim CUDA tensors that
-do not carry autograd history.
+When the logits require grad the scalar carries autograd history: the backward is one elementwise kernel
+(`snb_loss_grad`) that rebuilds d loss / d logits from the same four sums, so `loss.backward()` works as in
+torch_train.py:186-189 without any host synchronisation.
 """
 import torch
 from torch.nn.modules.loss import _Loss
@@ -36,6 +37,38 @@ def fused_sums(outputs, targets):
     return sums, counts
 
 
+class _FusedLoss(torch.autograd.Function):
+    """c_bce * sum_i BCE_i + c_jac * SmoothJaccard(smooth) as one reduction (forward) and one elementwise kernel
+    (backward); covers SmoothJaccardLoss, BCEWithSigmoidLoss and their weighted combination."""
+
+    @staticmethod
+    def forward(ctx, outputs, targets, c_bce, c_jac, smooth):
+        sums, _ = fused_sums(outputs, targets)
+        ctx.save_for_backward(outputs, targets, sums)
+        ctx.coef = (float(c_bce), float(c_jac), float(smooth))
+        jac = 1 - (sums[1] + smooth) / (sums[2] + sums[3] - sums[1] + smooth)
+        return (sums[0] * c_bce).float() + jac.float() * c_jac if c_jac else (sums[0] * c_bce).float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        outputs, targets, sums = ctx.saved_tensors
+        c_bce, c_jac, smooth = ctx.coef
+        x = outputs.detach().float().contiguous()
+        t = targets.detach()
+        if t.dtype not in _TARGET_DT:
+            t = t.float()
+        t = t.contiguous()
+        grad = torch.empty_like(x)
+        g = grad_out.detach().float().contiguous()
+        N.check(N.lib().snb_loss_grad(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(sums), N.ptr(g), c_bce,
+                                      c_jac, smooth, N.ptr(grad), N.stream_ptr()))
+        return grad.view_as(outputs).to(outputs.dtype), None, None, None, None
+
+
+def _needs_grad(outputs):
+    return torch.is_grad_enabled() and outputs.requires_grad
+
+
 class SmoothJaccardLoss(_Loss):
     """1 - (I + smooth) / (U - I + smooth), I = sum p*t, U = sum p + sum t (lib/losses.py:31-43)."""
 
@@ -44,6 +77,8 @@ class SmoothJaccardLoss(_Loss):
         self.smooth = smooth
 
     def forward(self, output, target):
+        if _needs_grad(output):
+            return _FusedLoss.apply(output, target, 0.0, 1.0, self.smooth)
         s, _ = fused_sums(output, target)
         intersection, union = s[1], s[2] + s[3]
         jac = (intersection + self.smooth) / (union - intersection + self.smooth)
@@ -59,12 +94,13 @@ class BCEWithSigmoidLoss(_Loss):
         self.reduce = reduce
 
     def forward(self, outputs, targets):
-        s, _ = fused_sums(outputs, targets)
-        if self.reduce and not self.size_average:
-            return s[0].float()
         if not self.reduce:
             raise NotImplementedError("reduce=False (per-element loss) is not on the fused path")
-        return (s[0] / outputs.numel()).float()
+        scale = 1.0 / outputs.numel() if self.size_average else 1.0
+        if _needs_grad(outputs):
+            return _FusedLoss.apply(outputs, targets, scale, 0.0, 0.0)
+        s, _ = fused_sums(outputs, targets)
+        return (s[0] * scale).float()
 
 
 class BCEWithLogitsLossAndSmoothJaccard(_Loss):
@@ -78,6 +114,10 @@ class BCEWithLogitsLossAndSmoothJaccard(_Loss):
         self.jaccard_weight = jaccard_weight
 
     def forward(self, outputs, targets):
+        if _needs_grad(outputs):
+            tot = float(self.bce_weight + self.jaccard_weight)
+            return _FusedLoss.apply(outputs, targets, self.bce_weight / (tot * outputs.numel()), self.jaccard_weight / tot,
+                                    self.jac_loss.smooth)
         s, _ = fused_sums(outputs, targets)  # one pass feeds both terms
         bce = s[0] / outputs.numel()
         smooth = self.jac_loss.smooth

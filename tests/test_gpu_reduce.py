@@ -1,4 +1,6 @@
 """-m gpu: fused loss / IoU / PR-curve reductions through the C ABI against the oracle and reference values."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -66,3 +68,31 @@ def test_full_size_counts_are_additive(cuda):
     assert whole.tolist() == parts.tolist() and int(whole.sum()) == n
     pred = torch.sigmoid(x) > 0.5
     assert int(whole[0]) == int((pred & (t != 0)).sum()) and int(whole[3]) == int((~pred & (t == 0)).sum())
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))])
+@pytest.mark.parametrize("target_dtype", [torch.int64, torch.uint8, torch.float32])
+def test_loss_backward_against_reference_gradients(cuda, golden_dir, seed, shape, target_dtype):
+    """loss.backward() through the fused reduction + snb_loss_grad == torch autograd through the reference's modules
+    (tests/golden/loss_grad.npz), with a non-unit upstream gradient, for all three losses."""
+    from snb_b200.lib import losses
+
+    g = np.load(os.path.join(golden_dir, "loss_grad.npz"))
+    logits, targets = synth.logits_targets(seed, shape)
+    t = targets.to(target_dtype).cuda()
+    for name, mod in (("bce_jaccard", losses.BCEWithLogitsLossAndSmoothJaccard()),
+                      ("smooth_jaccard", losses.SmoothJaccardLoss()), ("bce", losses.BCEWithSigmoidLoss())):
+        x = logits.cuda().requires_grad_(True)
+        loss = mod(x, t)
+        assert loss.requires_grad and loss.dim() == 0
+        (loss * 3.0).backward()
+        got = x.grad.cpu().numpy().reshape(-1)
+        want = g["seed%d_%s" % (seed, name)]
+        got = got if got.size < 5000 else got[::97]
+        assert x.grad.shape == logits.shape
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), name
+    # without grad the forward-only path is taken and the value is the same
+    with torch.no_grad():
+        v = losses.BCEWithLogitsLossAndSmoothJaccard()(logits.cuda(), t)
+    x = logits.cuda().requires_grad_(True)
+    assert float(v) == pytest.approx(float(losses.BCEWithLogitsLossAndSmoothJaccard()(x, t).detach()), rel=1e-6)

@@ -200,3 +200,17 @@ def test_inplace_abn_restatement(golden_dir, mode):
     assert np.abs(db.numpy() - g[mode + "_dbias"]).max() < 2e-4
     if not training:
         assert not g["eval_dweight"].any() and not g["eval_dbias"].any()    # the reference's eval-mode shortcut
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))])
+def test_loss_gradients(golden_dir, seed, shape):
+    """d loss / d logits of the oracle restatements under autograd == the reference modules' (lib/losses.py:31-75)."""
+    g = np.load(os.path.join(golden_dir, "loss_grad.npz"))
+    logits, targets = synth.logits_targets(seed, shape)
+    for name, fn in (("bce_jaccard", no.bce_jaccard), ("smooth_jaccard", no.smooth_jaccard), ("bce", no.bce_with_sigmoid)):
+        x = logits.clone().requires_grad_(True)
+        (fn(x, targets) * 3.0).backward()
+        got = x.grad.numpy().reshape(-1)
+        want = g["seed%d_%s" % (seed, name)]
+        got = got if got.size < 5000 else got[::97]
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
