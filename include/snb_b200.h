@@ -176,6 +176,21 @@ SNB_API double snb_conv_flops(const snb_conv* c);
 SNB_API int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                    void* d_out, int64_t out_cstride, int elem_bytes, void* stream);
 
+/* conv3x3 (stride 1, padding 1) with exactly 16 output channels -- FCDenseNet's growth-rate layers
+ * (lib/models/tiramisu.py:9-19: BatchNorm -> ReLU -> Conv2d(cin, 16, 3, padding=1)) -- as one N = 144 GEMM per tile
+ * (the nine taps live in the GEMM's N dimension; the epilogue adds the nine shifted partial planes).  NHWC bf16 slabs.
+ *   d_weight: bf16 [144][cin], row tap * 16 + co holds W[co][:, ky, kx], tap = ky * 3 + kx; cin % 32 == 0
+ *   d_pre_scale / d_pre_shift: float[cin] pre-activation y = relu(x * scale + shift) applied to the operand (or NULL)
+ *   d_out: first of the 16 output channels inside the destination slab (32-byte aligned, out_cstride % 16 == 0);
+ *          out = conv + bias, no activation */
+typedef struct snb_conv_scatter snb_conv_scatter;
+SNB_API int snb_conv_scatter_create(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t cin, int64_t in_cstride,
+                            const void* d_weight, const float* d_bias, const float* d_pre_scale,
+                            const float* d_pre_shift, void* d_out, int64_t out_cstride, snb_conv_scatter** out);
+SNB_API int snb_conv_scatter_launch(const snb_conv_scatter* c, void* stream);
+SNB_API void snb_conv_scatter_destroy(snb_conv_scatter* c);
+SNB_API double snb_conv_scatter_flops(const snb_conv_scatter* c);
+
 /* ResNet-34 encoder helpers of LinkNet34 (lib/models/linknet.py:39-48), NHWC bf16 slabs, channels % 8 == 0:
  *   snb_space_to_depth2: out[n][y][x][(py*2+px)*C + c] = in[n][2y+py][2x+px][c]   (h, w even) -- turns the stride-2
  *                        conv3x3 / conv1x1 of a down-sampling BasicBlock into SNB_CONV_2X2 / SNB_CONV_1X1 launches

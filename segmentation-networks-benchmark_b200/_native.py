@@ -80,6 +80,11 @@ SIGNATURES = {
     "snb_conv_launch": (c_int, [c_vp, c_vp]),
     "snb_conv_destroy": (None, [c_vp]),
     "snb_conv_flops": (ctypes.c_double, [c_vp]),
+    "snb_conv_scatter_create": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                        ctypes.POINTER(c_vp)]),
+    "snb_conv_scatter_launch": (c_int, [c_vp, c_vp]),
+    "snb_conv_scatter_destroy": (None, [c_vp]),
+    "snb_conv_scatter_flops": (ctypes.c_double, [c_vp]),
     "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp]),
     "snb_space_to_depth2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_maxpool3x3s2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),

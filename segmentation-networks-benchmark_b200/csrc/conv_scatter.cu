@@ -1,0 +1,415 @@
+// conv3x3 (stride 1, padding 1) with a NARROW output (Cout = 16: FCDenseNet's growth-rate layers,
+// lib/models/tiramisu.py:9-19) as ONE wide GEMM per tile instead of nine narrow ones.
+//
+// The tap-list kernels of conv_tcgen05.cu issue, per K chunk, one MMA group per tap with N = Cout.  A tcgen05.mma
+// M=128 x K=16 retires in max(N/2, 32 + N/4) cycles (tools/micro/mma_rate.cu), so at N = 32 (16 real channels) every
+// MMA pays 40 cycles for 8 cycles of useful work and the dense layers run at ~10 % of the tensor peak.  Here the taps
+// move into the N dimension:
+//     P[p][tap*16 + co] = sum_ci  X[p][ci] * W[co][ci][tap]          one GEMM, M = 128 input pixels, N = 144, K = Cin
+//     out[q][co]        = bias[co] + sum_tap P[q + (dy,dx)(tap)][tap*16 + co]
+// i.e. every input pixel is multiplied ONCE with all nine filter taps (N = 144 -> 72 cycles per MMA, 4x the useful work
+// per cycle), and the epilogue adds the nine shifted partial planes.  A tile is an 8 x 16 patch of INPUT pixels (plain
+// TMA box, out-of-bounds zero fill = the conv padding); its 6 x 14 interior pixels are the outputs it owns, so tiles
+// step by (6, 14) and 34 % of the MMA rows are halo recompute -- still ~3.3x fewer tensor cycles per output.
+//
+// Warp roles (256 threads; 512 with the pre-activation prologue): 0 TMA producer (activation ring + weights: resident
+// when all K chunks fit next to the pipeline, else streamed through their own ring), 1 MMA issuer, 2 TMEM allocator,
+// 4-7 epilogue (tcgen05.ld -> fp32 partial planes in shared memory -> shifted 9-term sum + bias -> bf16 -> 32-byte
+// stores at the slab's channel offset), 8-15 prologue: y = relu(x * scale[c] + shift[c]) rewritten into the staged
+// activation tile (FCDenseNet's per-consumer BatchNorm + ReLU), zero outside the image.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "sm100_ptx.cuh"
+#include "snb_internal.h"
+
+namespace snb {
+
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+               int swizzle_bytes, int elem_bytes);
+
+constexpr int kScM = 128;                 // MMA rows = input pixels of the 8 x 16 patch
+constexpr int kScPW = 8, kScPH = 16;      // patch
+constexpr int kScOW = 6, kScOH = 14;      // outputs owned by a tile
+constexpr int kScCout = 16;
+constexpr int kScN = 9 * kScCout;         // 144 GEMM columns
+constexpr int kScAcc = 256;               // TMEM columns per accumulator stage (144 used)
+constexpr int kScMaxStages = 8;
+constexpr int kScPBytes = 9 * kScM * kScCout * 4;   // fp32 partial planes [tap][channel quad][pixel] of float4
+constexpr int kScSmemBudget = 227 * 1024;
+
+struct alignas(64) ScatterParams {
+  CUtensorMap map_a;   // activations (C, W, H, N), box (BK, 8, 16, 1)
+  CUtensorMap map_b;   // weights (Cin, 144, 1), box (BK, 144, 1)
+  int32_t k_chunks, tiles_x, tiles_y, n_img, total_tiles;
+  int32_t w, h;
+  int32_t a_stages, b_stages, bres;
+  const float* bias;
+  const float* pre_scale;
+  const float* pre_shift;
+  __nv_bfloat16* out;
+  int64_t out_cstride;
+};
+
+struct ScTile {
+  int x0, y0, img;   // origin of the OUTPUT block; the input patch starts at (x0 - 1, y0 - 1)
+};
+
+__device__ __forceinline__ ScTile sc_decode(const ScatterParams& p, int t) {
+  ScTile c;
+  c.x0 = (t % p.tiles_x) * kScOW;
+  t /= p.tiles_x;
+  c.y0 = (t % p.tiles_y) * kScOH;
+  c.img = t / p.tiles_y;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t sc_pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// smem: [a_stages x A_BYTES][B: b_stages (or all k_chunks when resident) x B_BYTES][P: 73,728 B][ctrl]
+template <int BK, bool PRE>
+__global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const __grid_constant__ ScatterParams p) {
+  constexpr int SWZ = BK * 2;
+  constexpr int A_BYTES = kScM * SWZ;
+  constexpr int B_BYTES = kScN * SWZ;            // 144 rows: a multiple of 1024 for SWZ = 128 and 64
+  constexpr uint32_t IDESC = make_idesc(kScM, kScN, 1u);
+  static_assert(B_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "swizzle atom alignment");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_b_slots = p.bres ? p.k_chunks : p.b_stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + p.a_stages * A_BYTES;
+  float* smem_p = reinterpret_cast<float*>(smem_b + n_b_slots * B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_p) + kScPBytes);
+  uint64_t* a_full = bars;                          // [kScMaxStages]
+  uint64_t* a_empty = a_full + kScMaxStages;
+  uint64_t* b_full = a_empty + kScMaxStages;        // b_full[0] doubles as the resident-weights barrier
+  uint64_t* b_empty = b_full + kScMaxStages;
+  uint64_t* a_ready = b_empty + kScMaxStages;       // stage rewritten by the prologue warps (PRE)
+  uint64_t* tmem_full = a_ready + kScMaxStages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kScMaxStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+      mbar_init(&a_ready[i], 8);   // one arrival per prologue warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 2 * kScAcc);
+    tmem_relinquish();
+  }
+  tc05_fence_before();
+  __syncthreads();
+  tc05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      if (p.bres) {
+        mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(p.k_chunks) * B_BYTES);
+        for (int kc = 0; kc < p.k_chunks; ++kc)
+          tma_load_3d(&p.map_b, &b_full[0], smem_b + kc * B_BYTES, kc * BK, 0, 0);
+      }
+      uint32_t sa = 0, pa = 1, sb = 0, pb = 1;   // waiting on parity 1 of a fresh barrier returns immediately
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const ScTile tc = sc_decode(p, t);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&a_empty[sa], pa);
+          mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
+          tma_load_4d(&p.map_a, &a_full[sa], smem_a + sa * A_BYTES, kc * BK, tc.x0 - 1, tc.y0 - 1, tc.img);
+          if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
+          if (!p.bres) {
+            mbar_wait(&b_empty[sb], pb);
+            mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+            tma_load_3d(&p.map_b, &b_full[sb], smem_b + sb * B_BYTES, kc * BK, 0, 0);
+            if (++sb == static_cast<uint32_t>(p.b_stages)) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (elect_one()) {
+      const bool bres = p.bres != 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, local_tile = 0;
+      if (bres) {
+        mbar_wait(&b_full[0], 0);
+        tc05_fence_after();
+      }
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+        const uint32_t acc = local_tile & 1;
+        mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
+        tc05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kScAcc;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(PRE ? &a_ready[sa] : &a_full[sa], pa);
+          if (!bres) mbar_wait(&b_full[sb], pb);
+          tc05_fence_after();
+          const uint64_t adesc = make_kmajor_desc<SWZ>(smem_u32(smem_a + sa * A_BYTES), 8 * SWZ);
+          const uint64_t bdesc = make_kmajor_desc<SWZ>(smem_u32(smem_b + (bres ? kc : (int)sb) * B_BYTES), 8 * SWZ);
+#pragma unroll
+          for (int k = 0; k < SWZ / 32; ++k)
+            umma_ss<2>(adesc + 2 * k, bdesc + 2 * k, d_tmem, IDESC, (kc > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&a_empty[sa]);
+          if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
+          if (!bres) {
+            umma_commit(&b_empty[sb]);
+            if (++sb == static_cast<uint32_t>(p.b_stages)) { sb = 0; pb ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (PRE && warp >= 8) {
+    // ------------------------------------------------------------------ prologue: pre-activation of the A operand
+    constexpr int CPR = SWZ / 16;            // 16-byte chunks (8 channels) per operand row
+    constexpr int RSTEP = 256 / CPR;         // rows covered by the 256 prologue threads per sweep
+    const int tt = threadIdx.x - 256;
+    const int jl = tt % CPR;                 // logical chunk = channels [8 jl, 8 jl + 8) of the K chunk
+    const int r0 = tt / CPR;
+    uint32_t s = 0, par = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const ScTile tc = sc_decode(p, t);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const float4* sc4 = reinterpret_cast<const float4*>(p.pre_scale + kc * BK + jl * 8);
+        const float4* sh4 = reinterpret_cast<const float4*>(p.pre_shift + kc * BK + jl * 8);
+        const float4 s0 = __ldg(sc4), s1 = __ldg(sc4 + 1), b0 = __ldg(sh4), b1 = __ldg(sh4 + 1);
+        mbar_wait(&a_full[s], par);
+        uint8_t* base = smem_a + s * A_BYTES;
+#pragma unroll 2
+        for (int r = r0; r < kScM; r += RSTEP) {
+          const int hy = r / kScPW, hx = r - hy * kScPW;
+          const bool inside = static_cast<unsigned>(tc.x0 - 1 + hx) < static_cast<unsigned>(p.w) &&
+                              static_cast<unsigned>(tc.y0 - 1 + hy) < static_cast<unsigned>(p.h);
+          const int phys = jl ^ (SWZ == 128 ? (r & 7) : ((r >> 1) & 3));   // the swizzle TMA applied to this row
+          uint4* ptr = reinterpret_cast<uint4*>(base + r * SWZ + (phys << 4));
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (inside) {
+            const uint4 v = *ptr;
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const float2 x0 = __bfloat1622float2(pv[0]), x1 = __bfloat1622float2(pv[1]);
+            const float2 x2 = __bfloat1622float2(pv[2]), x3 = __bfloat1622float2(pv[3]);
+            o.x = sc_pack_bf16x2(fmaxf(fmaf(x0.x, s0.x, b0.x), 0.f), fmaxf(fmaf(x0.y, s0.y, b0.y), 0.f));
+            o.y = sc_pack_bf16x2(fmaxf(fmaf(x1.x, s0.z, b0.z), 0.f), fmaxf(fmaf(x1.y, s0.w, b0.w), 0.f));
+            o.z = sc_pack_bf16x2(fmaxf(fmaf(x2.x, s1.x, b1.x), 0.f), fmaxf(fmaf(x2.y, s1.y, b1.y), 0.f));
+            o.w = sc_pack_bf16x2(fmaxf(fmaf(x3.x, s1.z, b1.z), 0.f), fmaxf(fmaf(x3.y, s1.w, b1.w), 0.f));
+          }
+          *ptr = o;
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
+        if (++s == static_cast<uint32_t>(p.a_stages)) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue (128 threads = 128 patch pixels)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                     // patch pixel (row % 8, row / 8)
+    const int px = row % kScPW, py = row / kScPW;
+    const bool interior = px >= 1 && px <= kScOW && py >= 1 && py <= kScOH;
+    float bias[kScCout];
+#pragma unroll
+    for (int c = 0; c < kScCout; c += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      bias[c] = b.x; bias[c + 1] = b.y; bias[c + 2] = b.z; bias[c + 3] = b.w;
+    }
+    uint32_t local_tile = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+      const ScTile tc = sc_decode(p, t);
+      const uint32_t acc = local_tile & 1;
+      mbar_wait(&tmem_full[acc], (local_tile >> 1) & 1);
+      tc05_fence_after();
+      const uint32_t t_addr = tmem_base + acc * kScAcc + (static_cast<uint32_t>(q * 32) << 16);
+      // partial planes: P[tap][channel quad j][pixel] as float4 (fp32): consecutive pixels (= lanes) are 16 bytes
+      // apart, so the stores here and the shifted loads below are bank-conflict free
+      float4* p4 = reinterpret_cast<float4*>(smem_p);
+#pragma unroll 3
+      for (int tap = 0; tap < 9; ++tap) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_addr + tap * kScCout, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          p4[(tap * 4 + j) * kScM + row] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+      tc05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      named_bar_sync(1, 128);
+      const int ox = tc.x0 + px - 1, oy = tc.y0 + py - 1;
+      if (interior && ox < p.w && oy < p.h) {
+        float o[kScCout];
+#pragma unroll
+        for (int c = 0; c < kScCout; ++c) o[c] = bias[c];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          // out(q) += P[tap][q + (ky-1, kx-1)]: the partial product of the input pixel this tap reads
+          const int src = row + (tap / 3 - 1) * kScPW + (tap % 3 - 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 a = p4[(tap * 4 + j) * kScM + src];
+            o[4 * j] += a.x; o[4 * j + 1] += a.y; o[4 * j + 2] += a.z; o[4 * j + 3] += a.w;
+          }
+        }
+        __nv_bfloat16* dst = p.out + ((static_cast<int64_t>(tc.img) * p.h + oy) * p.w + ox) * p.out_cstride;
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        d4[0] = make_uint4(sc_pack_bf16x2(o[0], o[1]), sc_pack_bf16x2(o[2], o[3]), sc_pack_bf16x2(o[4], o[5]),
+                           sc_pack_bf16x2(o[6], o[7]));
+        d4[1] = make_uint4(sc_pack_bf16x2(o[8], o[9]), sc_pack_bf16x2(o[10], o[11]), sc_pack_bf16x2(o[12], o[13]),
+                           sc_pack_bf16x2(o[14], o[15]));
+      }
+      named_bar_sync(1, 128);   // the planes may be overwritten by the next tile
+    }
+  }
+
+  tc05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc05_fence_after();
+    tmem_dealloc(tmem_base, 2 * kScAcc);
+  }
+}
+
+}  // namespace snb
+
+struct snb_conv_scatter {
+  snb::ScatterParams params;
+  const void* fn;
+  int smem, grid, threads;
+  double flops;
+};
+
+using namespace snb;
+
+extern "C" int snb_conv_scatter_create(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t cin, int64_t in_cstride,
+                                       const void* d_weight, const float* d_bias, const float* d_pre_scale,
+                                       const float* d_pre_shift, void* d_out, int64_t out_cstride,
+                                       snb_conv_scatter** out) {
+  if (!out) return fail(SNB_E_INVALID, "snb_conv_scatter_create: null output");
+  *out = nullptr;
+  if (!d_in || !d_weight || !d_bias || !d_out) return fail(SNB_E_INVALID, "null tensor pointer");
+  if (n <= 0 || h <= 0 || w <= 0) return fail(SNB_E_INVALID, "bad input shape");
+  if (cin <= 0 || cin % 32 != 0) return fail(SNB_E_INVALID, "cin=%lld must be a positive multiple of 32", (long long)cin);
+  if (in_cstride < cin || in_cstride % 8 != 0 || out_cstride < kScCout || out_cstride % 8 != 0)
+    return fail(SNB_E_INVALID, "bad channel strides");
+  if ((d_pre_scale == nullptr) != (d_pre_shift == nullptr)) return fail(SNB_E_INVALID, "pre_scale and pre_shift come together");
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 31) ||
+      (reinterpret_cast<uintptr_t>(d_weight) & 15) || (reinterpret_cast<uintptr_t>(d_bias) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_pre_scale) & 15) || (reinterpret_cast<uintptr_t>(d_pre_shift) & 15) ||
+      (out_cstride * 2) % 32 != 0)
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned (the 16-channel output slot 32-byte aligned)");
+  const int sms = sm_count();
+  if (sms <= 0) return fail(SNB_E_CUDA, "no CUDA device");
+  const bool pre = d_pre_scale != nullptr;
+  const int bk = cin % 64 == 0 ? 64 : 32;
+  const int swz = bk * 2;
+  const int a_bytes = kScM * swz, b_bytes = kScN * swz;
+
+  snb_conv_scatter* c = new (std::nothrow) snb_conv_scatter();
+  if (!c) return fail(SNB_E_INVALID, "out of host memory");
+  ScatterParams& p = c->params;
+  std::memset(&p, 0, sizeof(p));
+  p.k_chunks = static_cast<int32_t>(cin / bk);
+  p.tiles_x = static_cast<int32_t>((w + kScOW - 1) / kScOW);
+  p.tiles_y = static_cast<int32_t>((h + kScOH - 1) / kScOH);
+  p.n_img = static_cast<int32_t>(n);
+  const int64_t total = (int64_t)p.n_img * p.tiles_y * p.tiles_x;
+  if (total > INT32_MAX) { delete c; return fail(SNB_E_UNSUPPORTED, "too many tiles"); }
+  p.total_tiles = static_cast<int32_t>(total);
+  p.w = static_cast<int32_t>(w);
+  p.h = static_cast<int32_t>(h);
+  p.bias = d_bias;
+  p.pre_scale = d_pre_scale;
+  p.pre_shift = d_pre_shift;
+  p.out = static_cast<__nv_bfloat16*>(d_out);
+  p.out_cstride = out_cstride;
+
+  // pipeline shape: resident weights when every K chunk fits next to >= 2 activation stages
+  const int fixed = 1024 /*align*/ + 1024 /*ctrl*/ + kScPBytes;
+  const int64_t w_bytes = (int64_t)p.k_chunks * b_bytes;
+  int a_stages, b_stages = 0;
+  bool bres = fixed + 2 * a_bytes + w_bytes <= kScSmemBudget;
+  if (const char* e = std::getenv("SNB_SCATTER_BRES")) bres = bres && std::atoi(e) != 0;
+  if (bres) {
+    a_stages = static_cast<int>(std::min<int64_t>(kScMaxStages, (kScSmemBudget - fixed - w_bytes) / a_bytes));
+    c->smem = fixed + a_stages * a_bytes + (int)w_bytes;
+  } else {
+    // one activation stage per weight stage
+    a_stages = b_stages = std::min(kScMaxStages, (kScSmemBudget - fixed) / (a_bytes + b_bytes));
+    if (a_stages < 2) { delete c; return fail(SNB_E_UNSUPPORTED, "scatter pipeline does not fit in shared memory"); }
+    c->smem = fixed + a_stages * (a_bytes + b_bytes);
+  }
+  p.a_stages = a_stages;
+  p.b_stages = b_stages;
+  p.bres = bres ? 1 : 0;
+
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    uint64_t str[3] = {(uint64_t)in_cstride * 2, (uint64_t)w * in_cstride * 2, (uint64_t)h * w * in_cstride * 2};
+    uint32_t box[4] = {(uint32_t)bk, (uint32_t)kScPW, (uint32_t)kScPH, 1};
+    rc = encode_map(&p.map_a, const_cast<void*>(d_in), 4, dims, str, box, swz, 2);
+    if (rc) { delete c; return rc; }
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)cin, (uint64_t)kScN, 1};
+    uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)kScN * cin * 2};
+    uint32_t box[3] = {(uint32_t)bk, (uint32_t)kScN, 1};
+    rc = encode_map(&p.map_b, const_cast<void*>(d_weight), 3, dims, str, box, swz, 2);
+    if (rc) { delete c; return rc; }
+  }
+  if (bk == 64) c->fn = pre ? (const void*)&conv_scatter_kernel<64, true> : (const void*)&conv_scatter_kernel<64, false>;
+  else c->fn = pre ? (const void*)&conv_scatter_kernel<32, true> : (const void*)&conv_scatter_kernel<32, false>;
+  c->threads = pre ? 512 : 256;
+  cudaError_t e = cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kScSmemBudget);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(SNB_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  }
+  c->grid = std::min<int>(p.total_tiles, sms);
+  c->flops = 2.0 * (double)n * h * w * (double)cin * kScCout * 9.0;
+  *out = c;
+  return SNB_OK;
+}
+
+extern "C" int snb_conv_scatter_launch(const snb_conv_scatter* c, void* stream) {
+  if (!c) return fail(SNB_E_INVALID, "snb_conv_scatter_launch: null handle");
+  void* args[1] = {const_cast<ScatterParams*>(&c->params)};
+  cudaError_t e = cudaLaunchKernel(c->fn, dim3(c->grid), dim3(c->threads), args, c->smem, as_stream(stream));
+  if (e != cudaSuccess) return fail(SNB_E_CUDA, "conv scatter launch failed: %s", cudaGetErrorString(e));
+  return SNB_OK;
+}
+
+extern "C" void snb_conv_scatter_destroy(snb_conv_scatter* c) { delete c; }
+
+extern "C" double snb_conv_scatter_flops(const snb_conv_scatter* c) { return c ? c->flops : 0.0; }

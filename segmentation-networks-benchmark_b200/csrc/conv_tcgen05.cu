@@ -771,8 +771,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 / fp32 tensor map over up to 4 dims; strides in bytes for dims 1..rank-1
-static int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+// bf16 / fp32 tensor map over up to 4 dims; strides in bytes for dims 1..rank-1 (shared with conv_scatter.cu)
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box, int swizzle_bytes, int elem_bytes = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(SNB_E_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");

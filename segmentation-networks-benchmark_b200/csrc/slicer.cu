@@ -484,6 +484,17 @@ __device__ __forceinline__ void lds_w(const double* p, double (&w)[PX]) {
   } else w[0] = *p;
 }
 
+template <int PX>
+__device__ __forceinline__ void ldg_w(const double* __restrict__ p, double (&w)[PX]) {
+  if constexpr (PX >= 2) {
+#pragma unroll
+    for (int e = 0; e < PX; e += 2) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(p + e));
+      w[e] = t.x; w[e + 1] = t.y;
+    }
+  } else w[0] = __ldg(p);
+}
+
 // acc += v * w in the reference's arithmetic (rounded product, then rounded sum)
 template <int PX>
 __device__ __forceinline__ void accp(const float (&v)[PX], const double (&w)[PX], double (&acc)[PX]) {
@@ -507,7 +518,7 @@ __device__ __forceinline__ void store_px(float* o, uint8_t* m, const float (&q)[
 }
 
 // One period, any crop pattern, any weights: norm on the fly, IEEE division.  Self-contained (re-reads its weights from
-// shared memory) and not inlined: it runs for the 1-2 edge periods of a row and for exotic weights only.
+// global memory) and not inlined: it runs for the 1-2 edge periods of a row and for exotic weights only.
 template <int PX, bool HAS_OUT, bool HAS_MASK>
 __device__ __noinline__ void merge_slow_period(const double* sw0, const double* sw1, const float* st0r, int row2_off, int T,
                                                int S, int tiles_x, int r, bool two_rows, int kx, float* o, uint8_t* m,
@@ -521,12 +532,12 @@ __device__ __noinline__ void merge_slow_period(const double* sw0, const double* 
       const double* sw = row ? sw1 : sw0;
       const float* st = st0r + row * row2_off + kx * T + e;
       if (useA) {
-        const double w = sw[r + S + e];
+        const double w = __ldg(sw + r + S + e);
         acc = __dadd_rn(acc, __dmul_rn((double)st[S - T], w));
         n = __dadd_rn(n, w);
       }
       if (useB) {
-        const double w = sw[r + e];
+        const double w = __ldg(sw + r + e);
         acc = __dadd_rn(acc, __dmul_rn((double)st[0], w));
         n = __dadd_rn(n, w);
       }
@@ -601,53 +612,74 @@ __device__ __forceinline__ void merge_interior(const float* p, int row2_off, int
     merge_periods<PX, A, TWO, 1, HAS_OUT, HAS_MASK>(p, row2_off, dA, pstep, ostep, wA0, wB0, wA1, wB1, nrm, rcp, o, m, thr);
 }
 
-// All periods kx = kfirst, kfirst + kstep, ... <= kx_hi of one thread (residues r .. r+PX-1) for one staged image row.
-// sw0/sw1: weight rows of the first/second covering crop row; st0r = staged tile rows + r (crop kx at kx*T, second crop
-// row row2_off floats further); orow/mrow = output row pointers at canvas x = 0 (pixel X lives at orow[X - ml]).
-template <int PX, bool HAS_OUT, bool HAS_MASK>
-__device__ __forceinline__ void merge_row(int T, int S, int tiles_x, int ml, int r, bool two_rows, const double* sw0,
-                                          const double* sw1, const float* st0r, int row2_off, int kfirst, int kx_hi,
-                                          int kstep, float* out_row, uint8_t* mask_row, float thr) {
-  if (kfirst > kx_hi) return;
-  const bool hasA = r < T - S;
+// The <= 4 * PX float64 weights of one thread for one image row, fetched from global memory (the 2 MB table is L2
+// resident) BEFORE the thread waits for its staged tile rows, so the fetch latency hides behind the bulk copies and the
+// weights cost no shared memory (4 instead of 3 resident CTAs per SM at 512 / 384).
+template <int PX>
+struct MergeWeights {
   double wA0[PX], wB0[PX], wA1[PX], wB1[PX];
+  double nrm[PX], rcp[PX];          // interior norm (clipped at eps) and its correctly rounded reciprocal
+  bool w_ok, wa_ok, copy, fast;     // weight of the own / left crop allows the copy shortcut; single-cover thread; fast division usable
+};
+
+template <int PX>
+__device__ __forceinline__ void merge_fetch_weights(const double* __restrict__ gw0, const double* __restrict__ gw1, int r,
+                                                    int S, bool hasA, bool two_rows, MergeWeights<PX>& w) {
 #pragma unroll
-  for (int e = 0; e < PX; ++e) wA0[e] = wA1[e] = wB1[e] = 0.0;
-  lds_w<PX>(sw0 + r, wB0);
-  if (hasA) lds_w<PX>(sw0 + r + S, wA0);
+  for (int e = 0; e < PX; ++e) w.wA0[e] = w.wA1[e] = w.wB1[e] = 0.0;
+  ldg_w<PX>(gw0 + r, w.wB0);
+  if (hasA) ldg_w<PX>(gw0 + r + S, w.wA0);
   if (two_rows) {
-    lds_w<PX>(sw1 + r, wB1);
-    if (hasA) lds_w<PX>(sw1 + r + S, wA1);
+    ldg_w<PX>(gw1 + r, w.wB1);
+    if (hasA) ldg_w<PX>(gw1 + r + S, w.wA1);
   }
   // single crop row: every pixel covered by ONE crop (no left neighbour, or an edge period) is a copy when the
-  // weight allows it; edge_copy says the same for the A-only / B-only edge periods of threads that have a left crop
+  // weight allows it (w_ok / wa_ok: own crop / crop to the left)
   bool w_ok = true, wa_ok = true;
 #pragma unroll
   for (int e = 0; e < PX; ++e) {
-    w_ok = w_ok && wB0[e] >= DBL_EPSILON && wB0[e] < 0x1p60;
-    wa_ok = wa_ok && wA0[e] >= DBL_EPSILON && wA0[e] < 0x1p60;
+    w_ok = w_ok && w.wB0[e] >= DBL_EPSILON && w.wB0[e] < 0x1p60;
+    wa_ok = wa_ok && w.wA0[e] >= DBL_EPSILON && w.wA0[e] < 0x1p60;
   }
   const bool copy = !hasA && !two_rows && w_ok;
-  double nrm[PX], rcp[PX];
   bool fast = true;
 #pragma unroll
-  for (int e = 0; e < PX; ++e) nrm[e] = rcp[e] = 1.0;
+  for (int e = 0; e < PX; ++e) w.nrm[e] = w.rcp[e] = 1.0;
   if (!copy) {
 #pragma unroll
     for (int e = 0; e < PX; ++e) {
       double n = 0.0;
-      if (hasA) n = __dadd_rn(n, wA0[e]);
-      n = __dadd_rn(n, wB0[e]);
+      if (hasA) n = __dadd_rn(n, w.wA0[e]);
+      n = __dadd_rn(n, w.wB0[e]);
       if (two_rows) {
-        if (hasA) n = __dadd_rn(n, wA1[e]);
-        n = __dadd_rn(n, wB1[e]);
+        if (hasA) n = __dadd_rn(n, w.wA1[e]);
+        n = __dadd_rn(n, w.wB1[e]);
       }
       n = n < DBL_EPSILON ? DBL_EPSILON : n;          // np.clip(norm, eps, None)
       fast = fast && n < 0x1p60;                      // NaN / huge weights take the slow routine
-      nrm[e] = n;
-      rcp[e] = __drcp_rn(n);
+      w.nrm[e] = n;
+      w.rcp[e] = __drcp_rn(n);
     }
   }
+  w.w_ok = w_ok; w.wa_ok = wa_ok; w.copy = copy; w.fast = fast;
+}
+
+// All periods kx = kfirst, kfirst + kstep, ... <= kx_hi of one thread (residues r .. r+PX-1) for one staged image row.
+// sw0/sw1: global weight rows of the first/second covering crop row; st0r = staged tile rows + r (crop kx at kx*T, second
+// crop row row2_off floats further); out_row/mask_row = output row pointers (pixel X lives at out_row[X - ml]).
+template <int PX, bool HAS_OUT, bool HAS_MASK>
+__device__ __forceinline__ void merge_row(int T, int S, int tiles_x, int ml, int r, bool two_rows, const double* sw0,
+                                          const double* sw1, const MergeWeights<PX>& mw, const float* st0r, int row2_off,
+                                          int kfirst, int kx_hi, int kstep, float* out_row, uint8_t* mask_row, float thr) {
+  if (kfirst > kx_hi) return;
+  const bool hasA = r < T - S;
+  const double (&wA0)[PX] = mw.wA0;
+  const double (&wB0)[PX] = mw.wB0;
+  const double (&wA1)[PX] = mw.wA1;
+  const double (&wB1)[PX] = mw.wB1;
+  const double (&nrm)[PX] = mw.nrm;
+  const double (&rcp)[PX] = mw.rcp;
+  const bool w_ok = mw.w_ok, wa_ok = mw.wa_ok, copy = mw.copy, fast = mw.fast;
   int kx = kfirst;
   int n = (kx_hi - kx) / kstep + 1;
   const int off0 = r - ml;                            // pixel of period kx sits at out_row[kx*S + off0]
@@ -709,56 +741,57 @@ __device__ __forceinline__ MergeRow merge_row_geom(int y, int mt, int T, int S, 
   return g;
 }
 
-// bulk copies of one row's operands, issued by a full warp: the weight rows and the tile rows of crops [ix0, ix0 + nx);
-// stage = [sw0[T] | sw1[T] | st0[nx_max*T] | st1[nx_max*T]]
+// bulk copies of one row's tile rows, issued by a full warp: crops [ix0, ix0 + nx) of the 1-2 covering crop rows;
+// stage = [st0[nx_max*T] | st1[nx_max*T]]
 __device__ __forceinline__ void merge_stage_row(const MergeRow& mr, int T, int S, int tiles_x, int ix0, int nx, int nx_max,
-                                                const float* tiles, const double* weight, double* sw0, uint64_t* bar,
-                                                int lane) {
-  float* st0 = reinterpret_cast<float*>(sw0 + 2 * T);
-  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(mr.n_rows * (T * 8 + nx * T * 4)));
+                                                const float* tiles, float* st0, uint64_t* bar, int lane) {
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(mr.n_rows * nx * T * 4));
   __syncwarp();
-  for (int i = lane; i < mr.n_rows * (nx + 1); i += 32) {
-    if (i < mr.n_rows) {
-      bulk_load_1d(sw0 + i * T, weight + (mr.ty0 - i * S) * T, (uint32_t)T * 8, bar);
-    } else {
-      const int j = i - mr.n_rows, rr = j / nx, ix = j - rr * nx;
-      bulk_load_1d(st0 + (rr * nx_max + ix) * T,
-                   tiles + (((int64_t)(mr.iy0 + rr) * tiles_x + ix0 + ix) * T + (mr.ty0 - rr * S)) * T, (uint32_t)T * 4, bar);
-    }
+  for (int j = lane; j < mr.n_rows * nx; j += 32) {
+    const int rr = j / nx, ix = j - rr * nx;
+    bulk_load_1d(st0 + (rr * nx_max + ix) * T,
+                 tiles + (((int64_t)(mr.iy0 + rr) * tiles_x + ix0 + ix) * T + (mr.ty0 - rr * S)) * T, (uint32_t)T * 4, bar);
   }
 }
 
 // ---- variant 1: one CTA per (image row, segment of `kp` periods), S / PX threads, several CTAs resident per SM
+// threads per CTA = step / PX (<= kStagedThreads<PX>); PX = 2 is compiled for 3 resident CTAs of <= 256 threads (a 64-register cap for 4 CTAs spills and loses 20 %)
+template <int PX> constexpr int kStagedThreads = PX == 1 ? 512 : 256;
+template <int PX> constexpr int kStagedMinBlocks = PX == 2 ? 3 : 1;
+
 template <int PX, bool HAS_OUT, bool HAS_MASK>
-__global__ void __launch_bounds__(1024 / PX > 256 ? 512 : 256) merge_f32c1_staged_kernel(
+__global__ void __launch_bounds__(kStagedThreads<PX>, kStagedMinBlocks<PX>) merge_f32c1_staged_kernel(
     SlicerGeom g, const float* __restrict__ tiles, const double* __restrict__ weight, float* __restrict__ out,
     uint8_t* __restrict__ mask, float thr, int xs, int kp) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w;
   const int tiles_x = (int)g.tiles_x, ml = (int)g.margin_left;
   uint64_t* bar = reinterpret_cast<uint64_t*>(merge_smem);
-  double* sw0 = reinterpret_cast<double*>(merge_smem + 16);
+  float* st0 = reinterpret_cast<float*>(merge_smem + 16);
   const int y = blockIdx.x / xs, seg = blockIdx.x - y * xs;
   // periods [k0, k1] of this segment need crops [k0 - 1, k1] clipped to the crop grid
   const int k0 = seg * kp, k1 = min(k0 + kp - 1, tiles_x);
-  const int ix0 = max(k0 - 1, 0), nx = min(k1, tiles_x - 1) - ix0 + 1, nx_max = kp + 1;
+  const int ix0 = max(k0 - 1, 0), nx = min(k1, tiles_x - 1) - ix0 + 1, nx_max = min(kp + 1, tiles_x);
   const MergeRow mr = merge_row_geom(y, (int)g.margin_top, T, S, (int)g.tiles_y);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
   }
   __syncthreads();
-  if (threadIdx.x < 32) merge_stage_row(mr, T, S, tiles_x, ix0, nx, nx_max, tiles, weight, sw0, bar, threadIdx.x);
+  if (threadIdx.x < 32) merge_stage_row(mr, T, S, tiles_x, ix0, nx, nx_max, tiles, st0, bar, threadIdx.x);
   const int r = threadIdx.x * PX;
   if (r >= S) return;
   // periods with an output pixel: ml <= kx*S + r <= ml + W - PX; the last one may be the right part of the last crop
   const int kx_lo = max(ml > r ? (ml - r + S - 1) / S : 0, k0);
   int kx_hi = ml + W - PX - r >= 0 ? (ml + W - PX - r) / S : -1;
   kx_hi = min(min(kx_hi, tiles_x - 1 + (r < T - S ? 1 : 0)), k1);
+  const double* gw0 = weight + mr.ty0 * T;
+  const double* gw1 = weight + (mr.ty0 - S) * T;       // only dereferenced when two crop rows cover the image row
+  MergeWeights<PX> mw;
+  if (kx_lo <= kx_hi) merge_fetch_weights<PX>(gw0, gw1, r, S, r < T - S, mr.n_rows == 2, mw);
   mbar_wait(bar, 0);
-  merge_row<PX, HAS_OUT, HAS_MASK>(T, S, tiles_x, ml, r, mr.n_rows == 2, sw0, sw0 + T,
-                                   reinterpret_cast<const float*>(sw0 + 2 * T) + r - ix0 * T, nx_max * T, kx_lo, kx_hi, 1,
-                                   out + (int64_t)y * W, mask + (int64_t)y * W, thr);
+  merge_row<PX, HAS_OUT, HAS_MASK>(T, S, tiles_x, ml, r, mr.n_rows == 2, gw0, gw1, mw, st0 + r - ix0 * T, nx_max * T, kx_lo,
+                                   kx_hi, 1, out + (int64_t)y * W, mask + (int64_t)y * W, thr);
 }
 
 // ---- variant 2: persistent CTAs (one per SM) with a producer warp keeping a ring of staged rows full; 24 consumer
@@ -790,8 +823,8 @@ __global__ void __launch_bounds__(kMergeConsumers + 32, 1) merge_f32c1_ring_kern
     for (int y = blockIdx.x; y < H; y += gridDim.x) {
       const MergeRow mr = merge_row_geom(y, mt, T, S, tiles_y);
       mbar_wait(&empty[s], par);
-      merge_stage_row(mr, T, S, tiles_x, 0, tiles_x, tiles_x, tiles, weight,
-                      reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes), &full[s], lane);
+      merge_stage_row(mr, T, S, tiles_x, 0, tiles_x, tiles_x, tiles,
+                      reinterpret_cast<float*>(stage0 + (size_t)s * stage_bytes), &full[s], lane);
       if (++s == n_stages) { s = 0; par ^= 1; }
     }
     return;
@@ -809,11 +842,14 @@ __global__ void __launch_bounds__(kMergeConsumers + 32, 1) merge_f32c1_ring_kern
   uint32_t par = 0;
   for (int y = blockIdx.x; y < H; y += gridDim.x) {
     const MergeRow mr = merge_row_geom(y, mt, T, S, tiles_y);
-    const double* sw0 = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+    const float* st0 = reinterpret_cast<const float*>(stage0 + (size_t)s * stage_bytes);
+    const double* gw0 = weight + mr.ty0 * T;
+    const double* gw1 = weight + (mr.ty0 - S) * T;
+    MergeWeights<PX> mw;
+    if (kx_lo + kgroup <= kx_hi) merge_fetch_weights<PX>(gw0, gw1, r, S, r < T - S, mr.n_rows == 2, mw);
     mbar_wait(&full[s], par);
-    merge_row<PX, HAS_OUT, HAS_MASK>(T, S, tiles_x, ml, r, mr.n_rows == 2, sw0, sw0 + T,
-                                     reinterpret_cast<const float*>(sw0 + 2 * T) + r, tiles_x * T, kx_lo + kgroup, kx_hi, KG,
-                                     out + (int64_t)y * W, mask + (int64_t)y * W, thr);
+    merge_row<PX, HAS_OUT, HAS_MASK>(T, S, tiles_x, ml, r, mr.n_rows == 2, gw0, gw1, mw, st0 + r, tiles_x * T,
+                                     kx_lo + kgroup, kx_hi, KG, out + (int64_t)y * W, mask + (int64_t)y * W, thr);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);              // this warp is done reading the stage
     if (++s == n_stages) { s = 0; par ^= 1; }
@@ -823,7 +859,7 @@ __global__ void __launch_bounds__(kMergeConsumers + 32, 1) merge_f32c1_ring_kern
 template <int PX, bool HAS_OUT, bool HAS_MASK>
 static bool launch_merge_ring(const SlicerGeom& g, const float* tiles, const double* weight, float* out, uint8_t* mask,
                               float thr, cudaStream_t st) {
-  const int64_t stage = 16 * g.tile + 8 * g.tile * g.tiles_x;
+  const int64_t stage = 8 * g.tile * g.tiles_x;
   if (g.step / PX > kMergeConsumers || g.step % PX) return false;
   int n_stages = (int)std::min<int64_t>(8, (227 * 1024 - 128) / stage);
   if (const char* e = std::getenv("SNB_MERGE_STAGES")) n_stages = std::min(n_stages, std::max(1, std::atoi(e)));
@@ -845,7 +881,7 @@ template <int PX, bool HAS_OUT, bool HAS_MASK>
 static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const double* weight, float* out, uint8_t* mask,
                                 float thr, cudaStream_t st) {
   const int threads = (int)((g.step / PX + 31) / 32 * 32);
-  if (g.step % PX || threads > (1024 / PX > 256 ? 512 : 256)) return false;
+  if (g.step % PX || threads > kStagedThreads<PX>) return false;
   // A CTA walks `kp` periods of one row (xs segments per row).  Measured on B200 (tools/merge_bench.py): ~10-14 periods
   // per thread amortise the per-row setup (weights, norm, reciprocal) best; fewer periods lose to that setup and to the
   // weight rows every CTA stages, more periods (one CTA per 45-period row at 224/112) leave too few CTAs per SM.
@@ -853,9 +889,9 @@ static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const d
   int64_t xs = periods <= 16 ? 1 : (periods + 9) / 10;
   if (const char* e = std::getenv("SNB_MERGE_XS")) xs = std::max(1, std::min<int>((int)periods, std::atoi(e)));
   int64_t kp = (periods + xs - 1) / xs;
-  while (kp > 1 && 16 + 2 * (g.tile * 8 + (kp + 1) * g.tile * 4) > 100 * 1024) --kp;   // >= 2 CTAs per SM
+  while (kp > 1 && 16 + 2 * std::min(kp + 1, g.tiles_x) * g.tile * 4 > 100 * 1024) --kp;   // >= 2 CTAs per SM
   xs = (periods + kp - 1) / kp;
-  const size_t smem = 16 + 2 * (size_t)(g.tile * 8 + (kp + 1) * g.tile * 4);
+  const size_t smem = 16 + 2 * (size_t)(std::min(kp + 1, g.tiles_x) * g.tile * 4);
   if (smem > 227 * 1024 || g.image_h * xs > INT32_MAX) return false;
   static bool configured = false;
   if (!configured) {

@@ -155,6 +155,41 @@ class ConvOp:
                 pass
 
 
+def pack_conv3x3_scatter(weight, dtype=torch.bfloat16):
+    """[16, Cin, 3, 3] -> [144][Cin] for snb_conv_scatter: row tap * 16 + co = W[co][:, ky, kx], tap = ky * 3 + kx."""
+    cout, cin = weight.shape[:2]
+    assert cout == 16
+    return to_storage(weight.detach().float().permute(2, 3, 0, 1).reshape(9 * cout, cin), dtype).contiguous()
+
+
+class ScatterConvOp:
+    """conv3x3 with 16 output channels as one N = 144 GEMM per tile (csrc/conv_scatter.cu); keeps its tensors alive."""
+
+    def __init__(self, src, dst, weight, bias, pre=None):
+        if dst.c != 16 or weight.shape != (144, src.c):
+            raise ValueError("scatter conv needs 16 output channels and a [144][cin] weight")
+        self.keep = (src, dst, weight, bias, pre)
+        self.desc = (0, src.slab.h, src.slab.w, src.c, 16)
+        self._h = ctypes.c_void_p()
+        N.check(N.lib().snb_conv_scatter_create(
+            N.c_vp(src.ptr), src.slab.n, src.slab.h, src.slab.w, src.c, src.cstride, N.ptr(weight), N.ptr(bias),
+            N.ptr(pre[0]) if pre is not None else N.c_vp(0), N.ptr(pre[1]) if pre is not None else N.c_vp(0),
+            N.c_vp(dst.ptr), dst.cstride, ctypes.byref(self._h)))
+        self.flops = N.lib().snb_conv_scatter_flops(self._h)
+        self.launches = 1
+
+    def __call__(self, stream):
+        N.check(N.lib().snb_conv_scatter_launch(self._h, stream))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().snb_conv_scatter_destroy(h)
+            except Exception:
+                pass
+
+
 class PoolOp:
     def __init__(self, src, dst):
         self.keep = (src, dst)
@@ -398,6 +433,12 @@ class FCDenseNetPlan:
         self.dtype = torch.bfloat16     # the pre-activation BN+ReLU path is bf16 only
         # SNB_FUSE_PRE=0 keeps the separate BN+ReLU pass (A/B runs); tap mode has no prologue warps
         fuse_pre = os.environ.get("SNB_FUSE_PRE", "1") != "0" and os.environ.get("SNB_CONV_MODE", "3") != "0"
+        # SNB_SCATTER=0 keeps the tap-list kernel for the growth-rate layers (A/B runs)
+        scatter = os.environ.get("SNB_SCATTER", "1") != "0"
+        # measured on B200 (profiles/): both formulations are bound by the shared-memory operand bandwidth of the
+        # tensor core (128 B/clk: the tap-list kernel re-reads the activation rows once per tap, the scatter kernel
+        # pays for its fp32 partial planes once per tile), so the scatter kernel wins from ~160 input channels on
+        scatter_min_cin = int(os.environ.get("SNB_SCATTER_MIN_CIN", "160"))
         self.ops = []
         g = spec['growth']
         dev = device
@@ -447,6 +488,12 @@ class FCDenseNetPlan:
             cpad = _pad32(cin)
             sc, sh = bn_params(bn, cmap, cpad)
             wp = pad_conv_weight(wt, cmap, cpad, 32)
+            if scatter and g == 16 and fuse_pre and wt.shape[0] == 16 and out_off % 16 == 0 and cpad >= scatter_min_cin:
+                # growth-rate conv as ONE N = 144 GEMM per tile (taps in the N dimension), BN+ReLU in the operand path
+                w16 = pad_conv_weight(wt, cmap, cpad, 16)
+                self.ops.append(ScatterConvOp(slab.view(0, cpad), slab.view(out_off, 16), pack_conv3x3_scatter(w16),
+                                              padded_bias(bs, 16), pre=(sc, sh)))
+                return
             if fuse_pre:
                 # BatchNorm+ReLU applied to the operand tiles inside the conv kernel: the slab is read once, in place
                 self.ops.append(ConvOp(N.CONV_3X3, slab.view(0, cpad), slab.view(out_off, 32), pack_conv3x3(wp),

@@ -378,3 +378,38 @@ def test_resnet_stem_helpers(cuda):
     N.check(N.lib().snb_maxpool3x3s2(N.c_vp(stem.view().ptr), n, h // 2, w // 2, 64, 64, N.c_vp(pooled.view().ptr), 64,
                                      N.stream_ptr()))
     assert torch.equal(nchw(pooled.view()), F.max_pool2d(nchw(stem.view()), 3, 2, 1))
+
+
+@pytest.mark.parametrize("n,h,w,cin,pre", [
+    (1, 14, 6, 32, False),           # exactly one tile, BK = 32
+    (2, 28, 24, 64, True),           # 2 x 4 tiles, BK = 64
+    (1, 224, 224, 96, True),         # FCDenseNet67 first dense block shapes, BK = 32
+    (3, 20, 13, 288, True),          # ragged tiles, resident weights (4.5 chunks -> BK = 32, 9 chunks)
+    (1, 7, 7, 448, True),            # smaller than a tile, streamed weights (do not fit next to the pipeline)
+    (2, 56, 56, 640, False),         # streamed weights, many K chunks
+])
+def test_scatter_conv3x3_cout16(cuda, conv_mode, n, h, w, cin, pre):
+    """FCDenseNet growth-rate layer relu(bn(x)) -> conv3x3(cin -> 16) as one N = 144 GEMM per tile
+    (csrc/conv_scatter.cu) against torch; written into 16 channels in the middle of a wider slab."""
+    if conv_mode != 1:
+        pytest.skip("independent of SNB_CONV_MODE: run once")
+    g = torch.Generator(device="cuda").manual_seed(cin + h)
+    src = rand_slab(n, h, w, cin + 32, g)
+    dst = E.Slab(n, h, w, 64, "cuda")
+    dst.t.fill_(7.0)
+    wt = torch.randn((16, cin, 3, 3), device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(16, device="cuda", generator=g)
+    scale = torch.rand(cin, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cin, device="cuda", generator=g) * 0.3 + 0.2
+    op = E.ScatterConvOp(src.view(0, cin), dst.view(32, 16), E.pack_conv3x3_scatter(wt), bias,
+                         pre=(scale, shift) if pre else None)
+    op(N.stream_ptr())
+    op(N.stream_ptr())                                                  # relaunch: barriers / TMEM are per launch
+    torch.cuda.synchronize()
+    x = nchw(src.view(0, cin))
+    if pre:
+        x = bf(F.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)))
+    want = F.conv2d(x, bf(wt), bias, padding=1)
+    check(nchw(dst.view(32, 16)), want)
+    assert torch.all(dst.t[..., :32] == 7.0) and torch.all(dst.t[..., 48:] == 7.0)      # neighbours untouched
+    assert op.flops == 2.0 * n * h * w * cin * 16 * 9
