@@ -222,6 +222,18 @@ SNB_API int snb_abn_backward(const float* d_z, const float* d_dz, int64_t n, int
                      const float* d_weight, const float* d_bias, int training, float eps, int activation, float slope,
                      float* d_dx, float* d_dweight, float* d_dbias, double* d_workspace, void* stream);
 
+/* Training-mode BatchNorm2d / InPlaceABN on an NHWC bf16 slab (LinkNet34 in train() mode: torchvision BasicBlock bn1/bn2,
+ * lib/models/linknet.py:16-31 abn1-3): batch statistics over `pixels` = N*H*W, running statistics updated in place with
+ * momentum and the unbiased variance, then out = act(x * scale + shift [+ residual]) [+ residual];
+ * abn != 0 uses gamma = |weight| + eps (the InPlaceABN backend); act_slope >= 0: leaky-ReLU with that slope (0 = ReLU),
+ * act_slope < 0: no activation.  d_scale / d_shift / d_mean / d_var: float[channels] outputs (the fused normalisation and
+ * the statistics, kept for the backward pass); d_workspace: double[2 * channels].  channels % 8 == 0, <= 2048. */
+SNB_API int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t channels, int64_t in_cstride, const float* d_gamma,
+                      const float* d_beta, int abn, float eps, float momentum, float* d_running_mean,
+                      float* d_running_var, float act_slope, const void* d_residual, int64_t res_cstride,
+                      int res_after_act, void* d_out, int64_t out_cstride, float* d_scale, float* d_shift, float* d_mean,
+                      float* d_var, double* d_workspace, void* stream);
+
 /* Pre-activation BatchNorm2d(eval) + ReLU of FCDenseNet's DenseLayer / TransitionDown (lib/models/tiramisu.py:12-13,
  * 50-51): out[.., c] = max(in[.., c] * scale[c] + shift[c], 0) for c < channels, 0 for channels <= c < channels_pad
  * (scale = gamma / sqrt(var + eps), shift = beta - mean * scale, float).  NHWC bf16 slabs, channels % 8 == 0. */

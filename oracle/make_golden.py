@@ -293,7 +293,34 @@ def linknet34_vectors():
     x256 = torch.from_numpy(np.random.RandomState(15).standard_normal((1, 3, 256, 256)).astype(np.float32))
     with torch.no_grad():
         y, y256 = m(x).numpy(), m(x256).numpy()
-    np.savez_compressed(os.path.join(OUT, "linknet34.npz"), x=x.numpy(), logits=y, logits256=y256)
+    # train() mode with Dropout2d off (BASELINE configs[1] as specified in SURVEY 8d): batch statistics everywhere.  torch >= 2
+    # rejects the reference autograd function's mark_dirty(x, running_mean, running_var), so `inplace_abn` inside
+    # lib.modules.abn.bn is pointed at the reference's own InPlaceABN.forward body with a stand-in context (no edit of the
+    # reference; forward only)
+    import lib.modules.abn.bn as ref_bn
+    from lib.modules.abn.functions import InPlaceABN as RefABN
+
+    class Ctx:
+        def mark_dirty(self, *t):
+            pass
+
+        def save_for_backward(self, *t):
+            self.saved_tensors = t
+
+    orig = ref_bn.inplace_abn
+    ref_bn.inplace_abn = lambda *a: RefABN.forward(Ctx(), *a)
+    m.train()
+    m.finaldrop1.p = 0.0
+    xt = torch.from_numpy(np.random.RandomState(16).standard_normal((4, 3, 64, 64)).astype(np.float32))
+    with torch.no_grad():
+        yt = m(xt).numpy()
+    ref_bn.inplace_abn = orig
+    sd_after = m.state_dict()
+    stats = {k.replace('.', '__'): sd_after[k].numpy() for k in (
+        'firstbn.running_mean', 'firstbn.running_var', 'encoder2.0.downsample.1.running_var', 'encoder4.2.bn2.running_mean',
+        'decoder4.abn1.running_var', 'decoder1.abn2.running_mean', 'decoder1.abn3.running_var')}
+    np.savez_compressed(os.path.join(OUT, "linknet34.npz"), x=x.numpy(), logits=y, logits256=y256, train_x=xt.numpy(),
+                        train_logits=yt, **stats)
     return dict(params=int(sum(p.numel() for p in m.parameters())), n_keys=len(m.state_dict()),
                 logit_min=float(y.min()), logit_max=float(y.max()))
 

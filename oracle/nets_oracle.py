@@ -239,6 +239,60 @@ def inplace_abn_backward(z, dz, var, weight, bias, training=True, eps=1e-5, acti
     return dx, torch.where(weight > 0, eydz, -eydz), edz
 
 
+
+def linknet34_forward_train(sd, x, quant=None):
+    """LinkNet34.forward in train() mode with Dropout2d inactive (lib/models/linknet.py:65-90): every BatchNorm2d /
+    InPlaceABN normalises with batch statistics and updates its running statistics (momentum 0.1, unbiased variance).
+    Returns (logits, {buffer name: updated value}); `sd` is not modified."""
+    q = quant if quant is not None else (lambda t: t)
+    new = {}
+
+    def conv(t, key, **kw):
+        return F.conv2d(q(t), q(sd[key + '.weight']), sd.get(key + '.bias'), **kw)
+
+    def bn(t, prefix):
+        rm, rv = sd[prefix + '.running_mean'].clone(), sd[prefix + '.running_var'].clone()
+        y = F.batch_norm(t, rm, rv, sd[prefix + '.weight'], sd[prefix + '.bias'], training=True, momentum=0.1, eps=1e-5)
+        new[prefix + '.running_mean'], new[prefix + '.running_var'] = rm, rv
+        return y
+
+    def abn(t, prefix):
+        z, _, rm, rv = inplace_abn_forward(t, sd[prefix + '.weight'], sd[prefix + '.bias'], sd[prefix + '.running_mean'],
+                                           sd[prefix + '.running_var'], True, 0.1, 1e-5, 'leaky_relu', 0.01)
+        new[prefix + '.running_mean'], new[prefix + '.running_var'] = rm, rv
+        return z
+
+    x = F.relu(bn(conv(x, 'firstconv', stride=2, padding=3), 'firstbn'))
+    x = F.max_pool2d(q(x), 3, 2, 1)
+    feats = []
+    for li, n_blocks in enumerate(RESNET34_BLOCKS):
+        for b in range(n_blocks):
+            pre = 'encoder%d.%d' % (li + 1, b)
+            stride = 2 if (li > 0 and b == 0) else 1
+            ident = x
+            out = q(F.relu(bn(q(conv(x, pre + '.conv1', stride=stride, padding=1)), pre + '.bn1')))
+            out = bn(q(conv(out, pre + '.conv2', padding=1)), pre + '.bn2')
+            if pre + '.downsample.0.weight' in sd:
+                ident = q(bn(q(conv(x, pre + '.downsample.0', stride=stride)), pre + '.downsample.1'))
+            x = q(F.relu(out + ident))
+        feats.append(x)
+    e1, e2, e3, e4 = feats
+
+    def decoder(t, name):
+        t = q(abn(q(conv(t, name + '.conv1')), name + '.abn1'))
+        t = F.conv_transpose2d(t, q(sd[name + '.deconv2.weight']), sd[name + '.deconv2.bias'], stride=2, padding=1)
+        t = q(abn(q(t), name + '.abn2'))
+        return abn(q(conv(t, name + '.conv3')), name + '.abn3')
+
+    d4 = q(decoder(e4, 'decoder4') + e3)
+    d3 = q(decoder(d4, 'decoder3') + e2)
+    d2 = q(decoder(d3, 'decoder2') + e1)
+    d1 = q(decoder(d2, 'decoder1'))
+    f = F.leaky_relu(F.conv_transpose2d(d1, q(sd['finaldeconv1.weight']), sd['finaldeconv1.bias'], stride=2), 0.01)
+    f = F.leaky_relu(conv(q(f), 'finalconv2'), 0.01)
+    return conv(q(f), 'finalconv3', padding=1), new
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 

@@ -11,6 +11,8 @@
 // Everything is HBM-bound: per element 4 B read + 4 B written (forward), 8 B read + 4 B written (backward), plus one
 // 4 B (8 B) reduction pass in training mode.  One CTA per (channel, image-slab) slice, float4 loads when H*W % 4 == 0,
 // warp-shuffle + shared-memory block reduction, float64 atomics for the cross-CTA sums.
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cstdint>
 
@@ -199,6 +201,110 @@ __global__ void abn_param_grads_kernel(const double* __restrict__ sums, const fl
   if (dbias) dbias[c] = (float)sums[2 * c];
 }
 
+// ---- training-mode BatchNorm2d / InPlaceABN on the engine's NHWC bf16 slabs (LinkNet34 train-mode forward) ----------
+// One thread = 8 channels (one 16-byte vector) of a strided set of pixels; per-thread float partials, shared-memory
+// float atomics across the pixel lanes of a CTA, then one float64 atomic per channel and CTA.
+constexpr int kBnMaxCV = 256;   // <= 2048 channels
+
+__global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restrict__ in, int CV, int in_sv, int64_t pixels,
+                                                            double* __restrict__ sums) {
+  __shared__ float sh[kBnMaxCV * 16];
+  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  if (pl < ppb) {
+    for (int64_t pix = blockIdx.x * (int64_t)ppb + pl; pix < pixels; pix += (int64_t)gridDim.x * ppb) {
+      const uint4 u = __ldg(in + pix * in_sv + v);
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = __bfloat1622float2(pv[e]);
+        s[2 * e] += x.x; s[2 * e + 1] += x.y;
+        q[2 * e] += x.x * x.x; q[2 * e + 1] += x.y * x.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sh[(v * 8 + e) * 2], s[e]);
+      atomicAdd(&sh[(v * 8 + e) * 2 + 1], q[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) atomicAdd(sums + i, (double)sh[i]);
+}
+
+// mean / biased variance -> fused scale and shift of the normalisation; running statistics as nn.BatchNorm2d and
+// functions.py:84-85 update them (momentum, unbiased variance).  abn != 0: gamma = |weight| + eps (InPlaceABN backend)
+__global__ void bn_finalize_nhwc_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, int abn, float eps, float momentum,
+                                        float* __restrict__ running_mean, float* __restrict__ running_var,
+                                        float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                        float* __restrict__ var_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[2 * c] / count;
+  double v = sums[2 * c + 1] / count - m * m;
+  v = v < 0.0 ? 0.0 : v;
+  const float g = gamma ? (abn ? fabsf(gamma[c]) + eps : gamma[c]) : 1.f;
+  const float sc = g * rsqrtf((float)v + eps);
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - (float)m * sc;
+  if (mean_out) mean_out[c] = (float)m;
+  if (var_out) var_out[c] = (float)v;
+  if (running_mean) running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * (float)m;
+  if (running_var && count > 1.0)
+    running_var[c] = running_var[c] * (1.f - momentum) + (float)(momentum * v * count / (count - 1.0));
+}
+
+// out = act(x * scale + shift (+ residual before the activation)) (+ residual after it); act: slope >= 0 -> leaky-ReLU
+// with that slope (0 = ReLU), slope < 0 -> identity
+__global__ void __launch_bounds__(256) bn_apply_nhwc_kernel(const uint4* __restrict__ in, int CV, int in_sv,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            float slope, const uint4* __restrict__ res, int res_sv,
+                                                            int res_after_act, uint4* __restrict__ out, int out_sv,
+                                                            int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t pix = i / CV;
+    const uint4 u = __ldg(in + pix * in_sv + cv);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * cv), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * cv + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cv), b1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * cv + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float f[8], r[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __bfloat1622float2(pv[e]);
+      f[2 * e] = fmaf(x.x, sc[2 * e], sh[2 * e]);
+      f[2 * e + 1] = fmaf(x.y, sc[2 * e + 1], sh[2 * e + 1]);
+      r[2 * e] = r[2 * e + 1] = 0.f;
+    }
+    if (res) {
+      const uint4 ru = __ldg(res + pix * res_sv + cv);
+      const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&ru);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = __bfloat1622float2(pr[e]);
+        r[2 * e] = x.x; r[2 * e + 1] = x.y;
+      }
+    }
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = f[e] + (res_after_act ? 0.f : r[e]);
+      if (slope >= 0.f) y = y > 0.f ? y : y * slope;
+      f[e] = y + (res_after_act ? r[e] : 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    out[pix * out_sv + cv] = *reinterpret_cast<uint4*>(o);
+  }
+}
+
 static int abn_check(const void* x, int64_t n, int64_t c, int64_t hw, int act) {
   if (!x) return fail(SNB_E_INVALID, "null tensor");
   if (n <= 0 || c <= 0 || hw <= 0 || c > INT32_MAX || n > INT32_MAX || n * c > INT32_MAX)
@@ -270,6 +376,42 @@ extern "C" int snb_abn_backward(const float* d_z, const float* d_dz, int64_t n, 
                                                                     activation, slope, d_dx);
   if (d_dweight || d_dbias)
     abn_param_grads_kernel<<<(unsigned)((c + 127) / 128), 128, 0, st>>>(d_workspace, d_weight, (int)c, d_dweight, d_dbias);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t channels, int64_t in_cstride, const float* d_gamma,
+                                 const float* d_beta, int abn, float eps, float momentum, float* d_running_mean,
+                                 float* d_running_var, float act_slope, const void* d_residual, int64_t res_cstride,
+                                 int res_after_act, void* d_out, int64_t out_cstride, float* d_scale, float* d_shift,
+                                 float* d_mean, float* d_var, double* d_workspace, void* stream) {
+  if (!d_in || !d_out || !d_scale || !d_shift || !d_workspace) return fail(SNB_E_INVALID, "snb_bn_train_nhwc: null argument");
+  if (pixels < 2 || channels <= 0 || channels % 8 || channels / 8 > kBnMaxCV)
+    return fail(SNB_E_INVALID, "bad shape: pixels=%lld channels=%lld", (long long)pixels, (long long)channels);
+  if (in_cstride % 8 || out_cstride % 8 || in_cstride < channels || out_cstride < channels ||
+      (d_residual && (res_cstride % 8 || res_cstride < channels)))
+    return fail(SNB_E_INVALID, "channel strides must be multiples of 8 covering the channels");
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_residual) & 15) || (reinterpret_cast<uintptr_t>(d_scale) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_shift) & 15))
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int cv = (int)(channels / 8);
+  // threads per CTA: a multiple of the vectors per pixel
+  const int threads = cv >= 256 ? cv : (256 / cv) * cv;
+  const int ppb = threads / cv;
+  const int64_t want = (pixels + ppb * 4 - 1) / (ppb * 4);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
+  bn_stats_nhwc_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
+  bn_finalize_nhwc_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, (int)channels, (double)pixels, d_gamma,
+                                                                            d_beta, abn, eps, momentum, d_running_mean,
+                                                                            d_running_var, d_scale, d_shift, d_mean, d_var);
+  const int64_t total = pixels * cv;
+  const int agrid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16));
+  bn_apply_nhwc_kernel<<<agrid, 256, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), d_scale, d_shift,
+                                              act_slope, static_cast<const uint4*>(d_residual), (int)(res_cstride / 8),
+                                              res_after_act, static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -751,3 +751,159 @@ class LinkNet34Plan:
         self.x_nchw.copy_(x)
 
     run = VGGUNetPlan.run
+
+
+class BnTrainOp:
+    """Training-mode BatchNorm2d / InPlaceABN on an NHWC bf16 slab (snb_bn_train_nhwc): batch statistics, in-place update
+    of the module's running statistics, normalise + activation (+ residual before or after it).  `bn` = (weight, bias,
+    running_mean, running_var, eps, momentum); parameters are read through their own pointers (no copies) unless the
+    slab is wider than the layer (zero-padded channels), in which case padded temporaries are used and the running
+    statistics are copied back."""
+
+    def __init__(self, src, dst, bn, abn, slope, residual=None, res_after_act=False):
+        weight, bias, rmean, rvar, eps, momentum = bn
+        c, cpad, dev = weight.numel(), src.c, src.slab.t.device
+        if dst.c != cpad or (residual is not None and residual.c != cpad):
+            raise ValueError("source, destination and residual must have the same channel count")
+        self.padded = c != cpad
+        f = lambda t: t.detach()
+        if self.padded:
+            pad = lambda t, fill: torch.cat([f(t).float(), torch.full((cpad - c,), fill, dtype=torch.float32, device=dev)])
+            self.gamma, self.beta = pad(weight, 0.0), pad(bias, 0.0)
+            self.rmean, self.rvar = pad(rmean, 0.0), pad(rvar, 1.0)
+            self.module_stats = (rmean, rvar, c)
+        else:
+            self.gamma, self.beta, self.rmean, self.rvar = f(weight), f(bias), rmean, rvar
+        for t in (self.gamma, self.beta, self.rmean, self.rvar):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("BatchNorm parameters and buffers must be contiguous float32")
+        self.scale = torch.empty(cpad, dtype=torch.float32, device=dev)
+        self.shift = torch.empty(cpad, dtype=torch.float32, device=dev)
+        self.mean = torch.empty(cpad, dtype=torch.float32, device=dev)     # kept for the backward pass
+        self.var = torch.empty(cpad, dtype=torch.float32, device=dev)
+        self.work = torch.empty(2 * cpad, dtype=torch.float64, device=dev)
+        self.keep = (src, dst, residual, weight, bias, rmean, rvar)
+        self.pixels = src.slab.n * src.slab.h * src.slab.w
+        self.args = (N.c_vp(src.ptr), self.pixels, cpad, src.cstride, N.ptr(self.gamma), N.ptr(self.beta), 1 if abn else 0,
+                     float(eps), float(momentum), N.ptr(self.rmean), N.ptr(self.rvar), float(slope),
+                     N.c_vp(residual.ptr if residual is not None else 0), residual.cstride if residual is not None else 0,
+                     1 if res_after_act else 0, N.c_vp(dst.ptr), dst.cstride, N.ptr(self.scale), N.ptr(self.shift),
+                     N.ptr(self.mean), N.ptr(self.var), N.ptr(self.work))
+        self.flops, self.launches = 0.0, 3
+
+    def __call__(self, stream):
+        N.check(N.lib().snb_bn_train_nhwc(*self.args, stream))
+        if self.padded:
+            rmean, rvar, c = self.module_stats
+            rmean.copy_(self.rmean[:c])
+            rvar.copy_(self.rvar[:c])
+
+
+class LinkNet34TrainPlan:
+    """LinkNet34.forward in train() mode (lib/models/linknet.py:65-90): the same convolution kernels as LinkNet34Plan but
+    nothing is folded -- every BatchNorm2d / InPlaceABN runs on batch statistics (BnTrainOp), updates the module's running
+    statistics in place, and keeps the raw convolution output, mean and variance (what the backward pass will need).
+    Dropout2d must be inactive (p == 0: BASELINE configs[1] as specified in SURVEY 8d).  `model` is the LinkNet34 module."""
+
+    STEM_K = 160
+
+    def __init__(self, model, n, h, w, device):
+        if h % 32 or w % 32:
+            raise ValueError("height and width must be multiples of 32")
+        if model.finaldrop1.p != 0:
+            raise NotImplementedError("Dropout2d with p > 0 is not built for the training-mode forward (set finaldrop1.p = 0)")
+        if model.finalconv3.weight.shape[0] != 1:
+            raise NotImplementedError("fused head expects num_classes == 1")
+        self.n, self.h, self.w, self.device = n, h, w, device
+        self.ops, self.bn_modules = [], []
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
+        p32 = lambda c: (c + 31) // 32 * 32
+        zeros = lambda c: torch.zeros(c, dtype=torch.float32, device=device)
+        f32 = lambda t: t.detach().float().contiguous()
+
+        def bn_of(m):
+            return (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum)
+
+        def conv_bn(kind, src, wpacked, bias, cout, hh, ww, m, abn, slope, residual=None, res_after_act=False, **kw):
+            raw = S(hh, ww, cout).view()
+            self.ops.append(ConvOp(kind, src, raw, wpacked, bias, relu=False, **kw))
+            out = S(hh, ww, cout).view()
+            self.ops.append(BnTrainOp(raw, out, bn_of(m), abn, slope, residual, res_after_act))
+            if isinstance(m, torch.nn.BatchNorm2d):
+                self.bn_modules.append(m)
+            return out
+
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        self.x_nchw = torch.empty((n, 3, h, w), dtype=torch.float32, device=device)
+        self.x_rows = S(h2, w2, self.STEM_K)
+        self.ops.append(SimpleOp("snb_stem7x7_rows", (N.c_vp(self.x_nchw.data_ptr()), n, 3, h, w,
+                                                      N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K), (self.x_nchw, self.x_rows)))
+        stem = conv_bn(N.CONV_1X1, self.x_rows.view(), pack_stem7x7(f32(model.firstconv.weight), self.STEM_K), zeros(64), 64,
+                       h2, w2, model.firstbn, False, 0.0)
+        cur = S(h4, w4, 64)
+        self.ops.append(SimpleOp("snb_maxpool3x3s2", (N.c_vp(stem.ptr), n, h2, w2, 64, 64, N.c_vp(cur.view().ptr), 64),
+                                 (stem, cur)))
+        cur, ch, hh, ww = cur.view(), 64, h4, w4
+
+        skips = []
+        for li in range(1, 5):
+            for blk in getattr(model, 'encoder%d' % li):
+                cout = blk.conv1.weight.shape[0]
+                if blk.downsample is not None:
+                    hh, ww = hh // 2, ww // 2
+                    x4 = S(hh, ww, 4 * ch)
+                    self.ops.append(SimpleOp("snb_space_to_depth2", (N.c_vp(cur.ptr), n, 2 * hh, 2 * ww, ch, cur.cstride,
+                                                                     N.c_vp(x4.view().ptr), 4 * ch), (cur, x4)))
+                    t = conv_bn(N.CONV_2X2, x4.view(), pack_conv3x3_s2(f32(blk.conv1.weight)), zeros(cout), cout, hh, ww,
+                                blk.bn1, False, 0.0, valid=True)
+                    ident = conv_bn(N.CONV_1X1, x4.view(0, ch), pack_conv1x1(f32(blk.downsample[0].weight)), zeros(cout), cout,
+                                    hh, ww, blk.downsample[1], False, -1.0)
+                else:
+                    t = conv_bn(N.CONV_3X3, cur, pack_conv3x3(f32(blk.conv1.weight)), zeros(cout), cout, hh, ww, blk.bn1,
+                                False, 0.0)
+                    ident = cur
+                cur = conv_bn(N.CONV_3X3, t, pack_conv3x3(f32(blk.conv2.weight)), zeros(cout), cout, hh, ww, blk.bn2, False,
+                              0.0, residual=ident)
+                ch = cout
+            skips.append(cur)
+
+        def decoder(x, cin, d, n_out, hh, ww, skip):
+            mid = cin // 4
+            mp = p32(mid)
+            a = conv_bn(N.CONV_1X1, x, pack_conv1x1(_pad_mat(f32(d.conv1.weight), mp, cin)), _pad_vec(f32(d.conv1.bias), mp), mp,
+                        hh, ww, d.abn1, True, d.abn1.slope)
+            b_ = conv_bn(N.CONVT_4X4_S2, a, pack_convT4x4(_pad_mat(f32(d.deconv2.weight), mp, mp)),
+                         _pad_vec(f32(d.deconv2.bias), mp), mp, 2 * hh, 2 * ww, d.abn2, True, d.abn2.slope)
+            return conv_bn(N.CONV_1X1, b_, pack_conv1x1(_pad_mat(f32(d.conv3.weight), n_out, mp)), f32(d.conv3.bias), n_out,
+                           2 * hh, 2 * ww, d.abn3, True, d.abn3.slope, residual=skip, res_after_act=True)
+
+        e1, e2, e3, e4 = skips
+        h32, w32 = h // 32, w // 32
+        d4 = decoder(e4, 512, model.decoder4, 256, h32, w32, e3)
+        d3 = decoder(d4, 256, model.decoder3, 128, 2 * h32, 2 * w32, e2)
+        d2 = decoder(d3, 128, model.decoder2, 64, 4 * h32, 4 * w32, e1)
+        d1 = decoder(d2, 64, model.decoder1, 64, 8 * h32, 8 * w32, None)
+
+        slope1, slope2 = model.finalrelu1.negative_slope, model.finalrelu2.negative_slope
+        f1 = S(h + 1, w + 1, 32)
+        self.ops.append(ConvOp(N.CONVT_3X3_S2_FULL, d1, f1.view(), pack_convT3x3(model.finaldeconv1.weight, 64, 32),
+                               f32(model.finaldeconv1.bias), act_slope=slope1))
+        f3 = S(h - 1, w - 1, 32)
+        self.ops.append(ConvOp(N.CONV_3X3, f1.view(), f3.view(), pack_conv3x3(f32(model.finalconv2.weight)),
+                               f32(model.finalconv2.bias), act_slope=slope2, valid=True))
+        self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
+        pick = torch.zeros(32, dtype=torch.float32, device=device)
+        pick[0] = 1.0
+        self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, pack_conv2x2(f32(model.finalconv3.weight), 32, 32),
+                               _pad_vec(f32(model.finalconv3.bias), 32), relu=False, head=(pick, 0.0, False, self.out)))
+        self.flops = sum(op.flops for op in self.ops)
+        self.launches = sum(op.launches for op in self.ops)
+
+    def load_nchw(self, x):
+        self.x_nchw.copy_(x)
+
+    def run(self):
+        out = VGGUNetPlan.run(self)
+        for m in self.bn_modules:            # nn.BatchNorm2d bookkeeping (momentum is fixed, the counter only counts)
+            m.num_batches_tracked += 1
+        return out

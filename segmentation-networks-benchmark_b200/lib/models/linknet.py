@@ -5,8 +5,9 @@ layers, `decoder1..4.{conv1,abn1,deconv2,abn2,conv3,abn3}`, `finaldeconv1`, `fin
 is rebuilt here with torchvision's module names so no torchvision import is needed; `pretrained=True` cannot download
 weights in this environment and, like every other model here, starts from random initialisation.
 
-Forward runs on the native engine in eval mode only (BatchNorm / InPlaceABN running statistics, Dropout2d inactive).
-Training-mode forward and the backward pass (BASELINE configs[1]) are not built.  `InPlaceABN` holds the parameters of
+Forward runs on the native engine in eval mode (BatchNorm / InPlaceABN folded into the convolutions) and in train mode
+(batch statistics, running statistics updated in place, Dropout2d p must be 0).  The backward pass through the
+convolutions (BASELINE configs[1]) is not built.  `InPlaceABN` holds the parameters of
 mapillary's in-place activated batch norm (lib/modules/abn/bn.py:47-103); in eval mode it is
 leaky_relu((x - mean) / sqrt(var + eps) * (|weight| + eps) + bias, 0.01) -- the `|weight| + eps` scale is that
 library's forward; the library is not vendored in the reference and has no pinned version (parity unpinned).
@@ -15,7 +16,7 @@ import torch
 from torch import nn
 
 from ... import _native as N
-from ...engine import LinkNet34Plan
+from ...engine import LinkNet34Plan, LinkNet34TrainPlan
 from ..modules.abn import InPlaceABN
 
 
@@ -110,17 +111,39 @@ class LinkNet34(nn.Module):
                 cache[key] = LinkNet34Plan(self._spec(), n, h, w, dev, sigmoid)
         return cache[key]
 
+    def plan_train(self, n, h, w):
+        """Training-mode plan (batch statistics); rebuilt whenever a parameter or buffer object changed version other than
+        through the plan's own running-statistics updates, i.e. after every optimiser step (packing the weights again is
+        the cost of that; a repack-in-place path belongs to the backward work)."""
+        cache = self.__dict__.setdefault('_train_plans', {})
+        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self.__dict__.get('_train_stamp') != stamp:
+            cache.clear()
+            self.__dict__['_train_stamp'] = stamp
+        key = (n, h, w)
+        if key not in cache:
+            dev = self.finalconv3.weight.device
+            if dev.type != 'cuda':
+                raise RuntimeError("LinkNet34 runs on CUDA devices only (no CPU fallback); call .cuda()")
+            with torch.no_grad():
+                cache[key] = LinkNet34TrainPlan(self, n, h, w, dev)
+        return cache[key]
+
     def forward(self, x):
+        """eval(): folded BatchNorm / InPlaceABN (running statistics).  train(): batch statistics, running statistics
+        updated in place (FORWARD ONLY: the returned logits carry no autograd history; the backward of the convolutions
+        is not built)."""
         N.require_cuda()
-        if self.training:
-            raise NotImplementedError("LinkNet34 on the native engine is inference only: call .eval() (training-mode "
-                                      "batch statistics and the backward pass are not built)")
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected input of shape [N, 3, H, W]")
         with torch.cuda.device(x.device):
-            p = self.plan(x.shape[0], x.shape[2], x.shape[3], sigmoid=False)
-            p.load_nchw(x.float())
+            if self.training:
+                p = self.plan_train(x.shape[0], x.shape[2], x.shape[3])
+                self.__dict__.pop('_plan_stamp', None)        # the eval plans fold the running statistics: rebuild them
+            else:
+                p = self.plan(x.shape[0], x.shape[2], x.shape[3], sigmoid=False)
+            p.load_nchw(x.detach().float())
             out = p.run()
         return out.unsqueeze(1).clone()

@@ -211,3 +211,81 @@ def test_linknet34_against_reference_vectors(cuda, golden_dir):
     with torch.no_grad():
         q = no.linknet34_forward(sd, torch.from_numpy(g["x"]), quant=no.bf16_round)
     assert (y - q).abs().max().item() < 0.03 * max(1.0, q.abs().max().item())
+
+
+def test_linknet34_train_mode_forward(cuda, golden_dir):
+    """BASELINE configs[1] forward half: LinkNet34 in train() mode (batch statistics in every BatchNorm2d / InPlaceABN,
+    running statistics updated in place, Dropout2d p = 0) against the reference module's own train-mode output."""
+    from snb_b200.lib.models import LinkNet34
+
+    g = np.load(os.path.join(golden_dir, "linknet34.npz"))
+    sd = synth.linknet34_state_dict(seed=6)
+    m = LinkNet34(pretrained=False)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    x = torch.from_numpy(g["train_x"]).cuda()
+    with pytest.raises(NotImplementedError):
+        m(x)                                                           # Dropout2d(p=0.5) active: not built
+    m.finaldrop1.p = 0.0
+    y = m(x).cpu()
+    ref = torch.from_numpy(g["train_logits"])
+    assert y.shape == ref.shape == (4, 1, 64, 64)
+    p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    got = m.state_dict()
+    for k in g.files:
+        if "__" in k:
+            name = k.replace("__", ".")
+            want = torch.from_numpy(g[k])
+            before = sd[name]
+            # the update is momentum * (batch statistic - old value) of bf16 activations, down to 16 samples per channel
+            # in encoder4: compare the applied change, 10 % of its largest entry (bf16 noise of ~30 layers; measured 3.6 %)
+            delta_err = ((got[name].cpu() - before) - (want - before)).abs().max().item()
+            assert delta_err < 0.1 * max(1e-2, (want - before).abs().max().item()), (name, delta_err)
+    assert int(m.firstbn.num_batches_tracked) == 6 and int(m.encoder3[2].bn1.num_batches_tracked) == 6
+    # eval() afterwards folds the UPDATED running statistics
+    m.eval()
+    with torch.no_grad():
+        ye = m(torch.from_numpy(g["x"]).cuda()).cpu()
+    sd2 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        qe = no.linknet34_forward(sd2, torch.from_numpy(g["x"]))
+    assert (torch.sigmoid(ye) - torch.sigmoid(qe)).abs().max().item() < BF16_PROB_TOL
+
+
+@pytest.mark.parametrize("c,abn,slope,res,after", [(64, False, 0.0, True, False), (128, True, 0.01, True, True),
+                                                  (32, True, 0.01, False, False), (512, False, -1.0, False, False)])
+def test_bn_train_nhwc_against_torch(cuda, c, abn, slope, res, after):
+    """snb_bn_train_nhwc on an NHWC bf16 slab: batch statistics, running-statistics update, activation, residual."""
+    from snb_b200 import engine as E
+
+    g = torch.Generator(device="cuda").manual_seed(c)
+    n, h, w = 3, 12, 20
+    src = E.Slab(n, h, w, c, "cuda")
+    src.t.copy_((torch.randn((n, h, w, c), device="cuda", generator=g) * 1.7 + 0.4).to(torch.bfloat16))
+    rs = E.Slab(n, h, w, c, "cuda")
+    rs.t.copy_(torch.randn((n, h, w, c), device="cuda", generator=g).to(torch.bfloat16))
+    dst = E.Slab(n, h, w, c, "cuda")
+    wgt = (torch.rand(c, device="cuda", generator=g) + 0.5) * torch.where(torch.rand(c, device="cuda", generator=g) < 0.3, -1.0, 1.0)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    rm, rv = torch.randn(c, device="cuda", generator=g) * 0.1, torch.rand(c, device="cuda", generator=g) + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    op = E.BnTrainOp(src.view(), dst.view(), (wgt, bias, rm, rv, 1e-5, 0.1), abn, slope, rs.view() if res else None, after)
+    op(snb_b200._native.stream_ptr())
+    x = src.t.float().permute(0, 3, 1, 2)
+    r = rs.t.float().permute(0, 3, 1, 2) if res else 0.0
+    mean, var = x.mean(dim=(0, 2, 3)), x.var(dim=(0, 2, 3), unbiased=False)
+    gamma = wgt.abs() + 1e-5 if abn else wgt
+    y = (x - mean.view(1, -1, 1, 1)) * (gamma * torch.rsqrt(var + 1e-5)).view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    if not after:
+        y = y + r
+    if slope >= 0:
+        y = torch.nn.functional.leaky_relu(y, slope)
+    if after:
+        y = y + r
+    got = dst.t.float().permute(0, 3, 1, 2)
+    assert (got - y).abs().max().item() < 2e-2 * max(1.0, y.abs().max().item())       # bf16 output rounding
+    cnt = n * h * w
+    assert (rm - (rm0 * 0.9 + 0.1 * mean)).abs().max().item() < 1e-5
+    assert (rv - (rv0 * 0.9 + 0.1 * var * cnt / (cnt - 1))).abs().max().item() < 1e-4
+    assert (op.mean - mean).abs().max().item() < 1e-5 and (op.var - var).abs().max().item() < 1e-4

@@ -214,3 +214,16 @@ def test_loss_gradients(golden_dir, seed, shape):
         want = g["seed%d_%s" % (seed, name)]
         got = got if got.size < 5000 else got[::97]
         assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+
+
+def test_linknet34_train_mode_forward(golden_dir):
+    """train() mode (batch statistics, Dropout2d off): oracle restatement against the reference module run with its own
+    InPlaceABN.forward body (tests/golden/linknet34.npz train_*), logits and updated running statistics."""
+    g = np.load(os.path.join(golden_dir, "linknet34.npz"))
+    sd = synth.linknet34_state_dict(seed=6)
+    with torch.no_grad():
+        y, new = no.linknet34_forward_train(sd, torch.from_numpy(g["train_x"]))
+    assert np.abs(y.numpy() - g["train_logits"]).max() < 1e-5
+    for k in g.files:
+        if "__" in k:
+            assert np.abs(new[k.replace("__", ".")].numpy() - g[k]).max() < 1e-6, k
