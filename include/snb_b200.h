@@ -204,6 +204,27 @@ SNB_API int snb_maxpool3x3s2(const void* d_in, int64_t n, int64_t h, int64_t w, 
 SNB_API int snb_stem7x7_rows(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w, void* d_dst,
                      int64_t k_pad, void* stream);
 
+/* Generic convolution gradients on NHWC bf16 slabs (the backward half of the LinkNet34 training step; torch_train.py:186-189
+ * runs them through autograd + cuDNN).  One geometry: small[n,oy,ox,co] = sum big[n, oy*s+ky-p, ox*s+kx-p, ci] * W[co][ci][ky][kx].
+ * nn.Conv2d: big = input, small = output.  nn.ConvTranspose2d(Cin_t, Cout_t): big = its OUTPUT (ci = Cout_t), small = its
+ * INPUT (co = Cin_t), weight [Cin_t][Cout_t][kh][kw] = W[co][ci][kh][kw] unchanged.  Weights and weight gradients are
+ * float tensors in the PyTorch layout.
+ *   snb_conv_generic_fwd   small = conv(big) (+ bias[co])            -> the input gradient of a ConvTranspose2d
+ *   snb_conv_generic_dgrad big = conv^T(small) (+ bias[ci])          -> the input gradient of a Conv2d
+ *   snb_conv_generic_wgrad dW[co][ci][ky][kx] = sum_p small[p][co] * big[p*s + k - p][ci]   (zeroed, then fp32 atomics)
+ * small_h / small_w must equal (big + 2p - k) / s + 1 (SNB_E_SHAPE otherwise). */
+typedef struct snb_conv_geom {
+  int64_t n, big_h, big_w, big_c, big_cstride;
+  int64_t small_h, small_w, small_c, small_cstride;
+  int64_t kh, kw, stride, pad;
+} snb_conv_geom;
+SNB_API int snb_conv_generic_fwd(const snb_conv_geom* g, const void* d_big, const float* d_weight, const float* d_bias,
+                         void* d_small, void* stream);
+SNB_API int snb_conv_generic_dgrad(const snb_conv_geom* g, const void* d_small, const float* d_weight, const float* d_bias,
+                           void* d_big, void* stream);
+SNB_API int snb_conv_generic_wgrad(const snb_conv_geom* g, const void* d_big, const void* d_small, float* d_dweight,
+                           void* stream);
+
 /* InPlaceABN (lib/modules/abn/bn.py:47-103, functions.py:62-122): in-place activated batch norm on a contiguous NCHW
  * float tensor, hw = H * W.  The reference delegates the arithmetic to the external `inplace_abn` extension
  * (mean_var, forward, leaky_relu_forward/backward, elu_forward/backward, edz_eydz, backward; functions.py:46-118),

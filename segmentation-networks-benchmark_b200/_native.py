@@ -64,6 +64,12 @@ class ConvDesc(ctypes.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/snb_b200.h declares
+class ConvGeom(ctypes.Structure):
+    """struct snb_conv_geom (include/snb_b200.h)."""
+    _fields_ = [(k, c_i64) for k in ("n", "big_h", "big_w", "big_c", "big_cstride", "small_h", "small_w", "small_c",
+                                     "small_cstride", "kh", "kw", "stride", "pad")]
+
+
 SIGNATURES = {
     "snb_version": (c_int, []),
     "snb_last_error": (ctypes.c_char_p, []),
@@ -85,6 +91,9 @@ SIGNATURES = {
     "snb_conv_scatter_launch": (c_int, [c_vp, c_vp]),
     "snb_conv_scatter_destroy": (None, [c_vp]),
     "snb_conv_scatter_flops": (ctypes.c_double, [c_vp]),
+    "snb_conv_generic_fwd": (c_int, [ctypes.POINTER(ConvGeom), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "snb_conv_generic_dgrad": (c_int, [ctypes.POINTER(ConvGeom), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "snb_conv_generic_wgrad": (c_int, [ctypes.POINTER(ConvGeom), c_vp, c_vp, c_vp, c_vp]),
     "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp]),
     "snb_space_to_depth2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_maxpool3x3s2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
