@@ -104,6 +104,11 @@ SIGNATURES = {
                                  ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "snb_bn_train_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp,
                                   ctypes.c_float, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "snb_bn_backward_nhwc": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_float,
+                                     ctypes.c_float, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "snb_channel_sum_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "snb_maxpool3x3s2_backward": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "snb_ew_nhwc": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, ctypes.c_float, c_vp]),
     "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),

@@ -305,6 +305,106 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc_kernel(const uint4* __restr
   }
 }
 
+// ---- backward of snb_bn_train_nhwc: out = act(x * scale + shift + r_before) + r_after ---------------------------------
+// dz = dOut * act'(u), u recomputed exactly as the forward computed it (same fma on the same bf16 inputs, so the mask
+// is identical); sums[2c] += sum dz, sums[2c+1] += sum dz * xhat, xhat = (x - mean) * rsqrt(var + eps)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc_kernel(const uint4* __restrict__ x, int CV, int x_sv,
+                                                                 const uint4* __restrict__ g, int g_sv,
+                                                                 const uint4* __restrict__ rb, int rb_sv,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean, const float* __restrict__ var,
+                                                                 float eps, float slope, int64_t pixels,
+                                                                 double* __restrict__ sums) {
+  __shared__ float sh[kBnMaxCV * 16];
+  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
+  if (pl < ppb) {
+    float sc[8], sf[8], mu[8], is[8], s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = __ldg(scale + v * 8 + e); sf[e] = __ldg(shift + v * 8 + e);
+      mu[e] = __ldg(mean + v * 8 + e); is[e] = rsqrtf(__ldg(var + v * 8 + e) + eps);
+      s[e] = q[e] = 0.f;
+    }
+    for (int64_t pix = blockIdx.x * (int64_t)ppb + pl; pix < pixels; pix += (int64_t)gridDim.x * ppb) {
+      const uint4 xu = __ldg(x + pix * x_sv + v), gu = __ldg(g + pix * g_sv + v);
+      uint4 ru = make_uint4(0u, 0u, 0u, 0u);
+      if (rb) ru = __ldg(rb + pix * rb_sv + v);
+      const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xu);
+      const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gu);
+      const __nv_bfloat16* re = reinterpret_cast<const __nv_bfloat16*>(&ru);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = __bfloat162float(xe[e]);
+        const float u = fmaf(xv, sc[e], sf[e]) + __bfloat162float(re[e]);
+        float dz = __bfloat162float(ge[e]);
+        if (slope >= 0.f && !(u > 0.f)) dz *= slope;
+        s[e] += dz;
+        q[e] += dz * (xv - mu[e]) * is[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sh[(v * 8 + e) * 2], s[e]);
+      atomicAdd(&sh[(v * 8 + e) * 2 + 1], q[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) atomicAdd(sums + i, (double)sh[i]);
+}
+
+// dx = gamma' * invstd * (dz - mean(dz) - xhat * mean(dz * xhat)); optionally dz itself (the gradient of r_before)
+__global__ void __launch_bounds__(256) bn_bwd_apply_nhwc_kernel(const uint4* __restrict__ x, int CV, int x_sv,
+                                                                const uint4* __restrict__ g, int g_sv,
+                                                                const uint4* __restrict__ rb, int rb_sv,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                const float* __restrict__ mean, const float* __restrict__ var,
+                                                                float eps, float slope, const double* __restrict__ sums,
+                                                                double count, uint4* __restrict__ dx, int dx_sv,
+                                                                uint4* __restrict__ dres, int dres_sv, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t pix = i / CV;
+    const uint4 xu = __ldg(x + pix * x_sv + cv), gu = __ldg(g + pix * g_sv + cv);
+    uint4 ru = make_uint4(0u, 0u, 0u, 0u);
+    if (rb) ru = __ldg(rb + pix * rb_sv + cv);
+    const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xu);
+    const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gu);
+    const __nv_bfloat16* re = reinterpret_cast<const __nv_bfloat16*>(&ru);
+    __nv_bfloat16 od[8], oz[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cv * 8 + e;
+      const float sc = __ldg(scale + c), is = rsqrtf(__ldg(var + c) + eps);
+      const float xv = __bfloat162float(xe[e]);
+      const float u = fmaf(xv, sc, __ldg(shift + c)) + __bfloat162float(re[e]);
+      float dz = __bfloat162float(ge[e]);
+      if (slope >= 0.f && !(u > 0.f)) dz *= slope;
+      const float xhat = (xv - __ldg(mean + c)) * is;
+      const float edz = (float)(sums[2 * c] / count), eydz = (float)(sums[2 * c + 1] / count);
+      od[e] = __float2bfloat16(sc * (dz - edz - xhat * eydz));      // scale = gamma' * invstd
+      oz[e] = __float2bfloat16(dz);
+    }
+    dx[pix * dx_sv + cv] = *reinterpret_cast<uint4*>(od);
+    if (dres) dres[pix * dres_sv + cv] = *reinterpret_cast<uint4*>(oz);
+  }
+}
+
+__global__ void bn_bwd_params_nhwc_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, int abn, int C,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dgamma) dgamma[c] = (float)((abn && gamma && gamma[c] <= 0.f) ? -sums[2 * c + 1] : sums[2 * c + 1]);
+  if (dbeta) dbeta[c] = (float)sums[2 * c];
+}
+
+// per-channel sum of a bf16 slab (bias gradients): reuses the statistics kernel, keeps sum only
+__global__ void channel_sum_finalize_kernel(const double* __restrict__ sums, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (float)sums[2 * c];
+}
+
 static int abn_check(const void* x, int64_t n, int64_t c, int64_t hw, int act) {
   if (!x) return fail(SNB_E_INVALID, "null tensor");
   if (n <= 0 || c <= 0 || hw <= 0 || c > INT32_MAX || n > INT32_MAX || n * c > INT32_MAX)
@@ -412,6 +512,71 @@ extern "C" int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t chann
   bn_apply_nhwc_kernel<<<agrid, 256, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), d_scale, d_shift,
                                               act_slope, static_cast<const uint4*>(d_residual), (int)(res_cstride / 8),
                                               res_after_act, static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+static int bn_launch_shape(int64_t pixels, int64_t channels, int* threads, int* grid) {
+  const int cv = (int)(channels / 8);
+  *threads = cv >= 256 ? cv : (256 / cv) * cv;
+  const int ppb = *threads / cv;
+  const int64_t want = (pixels + ppb * 4 - 1) / (ppb * 4);
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
+  return cv;
+}
+
+extern "C" int snb_bn_backward_nhwc(const void* d_x, int64_t x_cstride, const void* d_dout, int64_t dout_cstride, int64_t pixels,
+                                    int64_t channels, const float* d_scale, const float* d_shift, const float* d_mean,
+                                    const float* d_var, const float* d_gamma, int abn, float eps, float act_slope,
+                                    const void* d_res_before, int64_t res_cstride, void* d_dx, int64_t dx_cstride,
+                                    void* d_dres, int64_t dres_cstride, float* d_dgamma, float* d_dbeta, double* d_workspace,
+                                    void* stream) {
+  if (!d_x || !d_dout || !d_scale || !d_shift || !d_mean || !d_var || !d_dx || !d_workspace)
+    return fail(SNB_E_INVALID, "snb_bn_backward_nhwc: null argument");
+  if (pixels < 2 || channels <= 0 || channels % 8 || channels / 8 > kBnMaxCV) return fail(SNB_E_INVALID, "bad shape");
+  if (x_cstride % 8 || dout_cstride % 8 || dx_cstride % 8 || x_cstride < channels || dout_cstride < channels ||
+      dx_cstride < channels || (d_res_before && (res_cstride % 8 || res_cstride < channels)) ||
+      (d_dres && (dres_cstride % 8 || dres_cstride < channels)))
+    return fail(SNB_E_INVALID, "channel strides must be multiples of 8 covering the channels");
+  if ((reinterpret_cast<uintptr_t>(d_x) & 15) || (reinterpret_cast<uintptr_t>(d_dout) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_dx) & 15) || (reinterpret_cast<uintptr_t>(d_res_before) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_dres) & 15))
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  int threads, grid;
+  const int cv = bn_launch_shape(pixels, channels, &threads, &grid);
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
+  bn_bwd_reduce_nhwc_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_x), cv, (int)(x_cstride / 8),
+                                                     static_cast<const uint4*>(d_dout), (int)(dout_cstride / 8),
+                                                     static_cast<const uint4*>(d_res_before), (int)(res_cstride / 8), d_scale,
+                                                     d_shift, d_mean, d_var, eps, act_slope, pixels, d_workspace);
+  const int64_t total = pixels * cv;
+  const int agrid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16));
+  bn_bwd_apply_nhwc_kernel<<<agrid, 256, 0, st>>>(static_cast<const uint4*>(d_x), cv, (int)(x_cstride / 8),
+                                                 static_cast<const uint4*>(d_dout), (int)(dout_cstride / 8),
+                                                 static_cast<const uint4*>(d_res_before), (int)(res_cstride / 8), d_scale, d_shift,
+                                                 d_mean, d_var, eps, act_slope, d_workspace, (double)pixels,
+                                                 static_cast<uint4*>(d_dx), (int)(dx_cstride / 8), static_cast<uint4*>(d_dres),
+                                                 (int)(dres_cstride / 8), total);
+  if (d_dgamma || d_dbeta)
+    bn_bwd_params_nhwc_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, d_gamma, abn, (int)channels,
+                                                                                d_dgamma, d_dbeta);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_channel_sum_nhwc(const void* d_in, int64_t pixels, int64_t channels, int64_t in_cstride, float* d_out,
+                                    double* d_workspace, void* stream) {
+  if (!d_in || !d_out || !d_workspace) return fail(SNB_E_INVALID, "snb_channel_sum_nhwc: null argument");
+  if (pixels < 1 || channels <= 0 || channels % 8 || channels / 8 > kBnMaxCV || in_cstride % 8 || in_cstride < channels ||
+      (reinterpret_cast<uintptr_t>(d_in) & 15))
+    return fail(SNB_E_INVALID, "bad shape or alignment");
+  cudaStream_t st = as_stream(stream);
+  int threads, grid;
+  const int cv = bn_launch_shape(pixels, channels, &threads, &grid);
+  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
+  bn_stats_nhwc_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
+  channel_sum_finalize_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, (int)channels, d_out);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -147,6 +147,55 @@ __global__ void stem7x7_rows_kernel(const float* __restrict__ src, int C, int H,
   }
 }
 
+// backward of nn.MaxPool2d(3, 2, 1) on NHWC bf16: gather formulation.  An input pixel receives the gradient of every
+// window whose arg-max it is; the arg-max is recomputed with the forward's scan order (rows, then columns, strict >), so
+// ties (frequent after a ReLU) go to the first maximum, as in PyTorch.
+__global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int in_cs,
+                                        const __nv_bfloat16* __restrict__ dout, int dout_cs, __nv_bfloat16* __restrict__ din,
+                                        int din_cs, int64_t total) {
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int c = (int)(r % C); r /= C;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int64_t n = r / H;
+    float acc = 0.f;
+    for (int oy = max(0, y / 2); oy <= min(OH - 1, (y + 1) / 2); ++oy) {
+      for (int ox = max(0, x / 2); ox <= min(OW - 1, (x + 1) / 2); ++ox) {
+        // window rows 2oy-1 .. 2oy+1 (must contain y), cols 2ox-1 .. 2ox+1
+        if (y < 2 * oy - 1 || y > 2 * oy + 1 || x < 2 * ox - 1 || x > 2 * ox + 1) continue;
+        float best = -INFINITY;
+        int by = -1, bx = -1;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = 2 * oy + dy;
+          if (yy < 0 || yy >= H) continue;
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = 2 * ox + dx;
+            if (xx < 0 || xx >= W) continue;
+            const float v = __bfloat162float(in[((n * H + yy) * W + xx) * in_cs + c]);
+            if (v > best || by < 0) { best = v; by = yy; bx = xx; }
+          }
+        }
+        if (by == y && bx == x) acc += __bfloat162float(dout[((n * OH + oy) * OW + ox) * dout_cs + c]);
+      }
+    }
+    din[((n * H + y) * W + x) * din_cs + c] = __float2bfloat16(acc);
+  }
+}
+
+// elementwise helpers of the backward pass on bf16 slabs: mode 0: out = a + b;  mode 1: out = a * (b > 0 ? 1 : slope)
+// (the gradient through a leaky-ReLU whose OUTPUT is b)
+__global__ void ew_nhwc_kernel(const __nv_bfloat16* __restrict__ a, int a_cs, const __nv_bfloat16* __restrict__ b, int b_cs,
+                               __nv_bfloat16* __restrict__ out, int out_cs, int C, int mode, float slope, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const float av = __bfloat162float(a[pix * a_cs + c]), bv = __bfloat162float(b[pix * b_cs + c]);
+    out[pix * out_cs + c] = __float2bfloat16(mode == 0 ? av + bv : (bv > 0.f ? av : av * slope));
+  }
+}
+
 static int aux_grid(int64_t total) {
   const int64_t need = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -253,6 +302,34 @@ extern "C" int snb_nhwc_bf16_to_nchw_f32(const void* d_in, int64_t n, int64_t h,
   const int64_t total = n * channels * h * w;
   nhwc_to_nchw_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(d_in), (int)h, (int)w,
                                                                        (int)channels, (int)in_cstride, d_out, total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_maxpool3x3s2_backward(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                                         const void* d_dout, int64_t dout_cstride, void* d_din, int64_t din_cstride,
+                                         void* stream) {
+  if (!d_in || !d_dout || !d_din) return fail(SNB_E_INVALID, "snb_maxpool3x3s2_backward: null argument");
+  if (n <= 0 || h <= 0 || w <= 0 || channels <= 0 || in_cstride < channels || dout_cstride < channels || din_cstride < channels)
+    return fail(SNB_E_INVALID, "bad shape");
+  const int64_t total = n * h * w * channels;
+  maxpool3x3s2_bwd_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d_in), (int)h, (int)w, (int)channels, (int)in_cstride,
+      static_cast<const __nv_bfloat16*>(d_dout), (int)dout_cstride, static_cast<__nv_bfloat16*>(d_din), (int)din_cstride, total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_ew_nhwc(const void* d_a, int64_t a_cstride, const void* d_b, int64_t b_cstride, void* d_out,
+                           int64_t out_cstride, int64_t pixels, int64_t channels, int mode, float slope, void* stream) {
+  if (!d_a || !d_b || !d_out) return fail(SNB_E_INVALID, "snb_ew_nhwc: null argument");
+  if (pixels <= 0 || channels <= 0 || a_cstride < channels || b_cstride < channels || out_cstride < channels || mode < 0 || mode > 1)
+    return fail(SNB_E_INVALID, "bad shape or mode");
+  const int64_t total = pixels * channels;
+  ew_nhwc_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(d_a), (int)a_cstride,
+                                                                 static_cast<const __nv_bfloat16*>(d_b), (int)b_cstride,
+                                                                 static_cast<__nv_bfloat16*>(d_out), (int)out_cstride,
+                                                                 (int)channels, mode, slope, total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -115,3 +115,74 @@ def test_geometry_errors(cuda):
     t = torch.zeros(1, device="cuda")
     with pytest.raises(AssertionError):
         N.check(N.lib().snb_conv_generic_fwd(ctypes.byref(gm), N.ptr(t), N.ptr(t), N.c_vp(0), N.ptr(t), N.stream_ptr()))
+
+
+@pytest.mark.parametrize("c,abn,slope,res,after", [(64, False, 0.0, True, False), (128, True, 0.01, True, True),
+                                                  (32, True, 0.01, False, False), (256, False, -1.0, False, False)])
+def test_bn_train_backward_nhwc(cuda, c, abn, slope, res, after):
+    """snb_bn_backward_nhwc against torch autograd through batch_norm(training) + activation + residual."""
+    g = torch.Generator(device="cuda").manual_seed(c + 5)
+    n, h, w = 3, 10, 12
+    x = bf(torch.randn((n, c, h, w), device="cuda", generator=g) * 1.5 + 0.3).requires_grad_(True)
+    r = bf(torch.randn((n, c, h, w), device="cuda", generator=g)).requires_grad_(True)
+    wgt = ((torch.rand(c, device="cuda", generator=g) + 0.5) *
+           torch.where(torch.rand(c, device="cuda", generator=g) < 0.3, -1.0, 1.0)).requires_grad_(True)
+    bias = (torch.randn(c, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    gamma = wgt.abs() + 1e-5 if abn else wgt
+    y = F.batch_norm(x, None, None, gamma, bias, training=True, eps=1e-5)
+    if res and not after:
+        y = y + r
+    if slope >= 0:
+        y = F.leaky_relu(y, slope)
+    if res and after:
+        y = y + r
+    dout = bf(torch.randn(y.shape, device="cuda", generator=g))
+    y.backward(dout)
+    # forward on the device (provides scale / shift / mean / var), then the backward kernel
+    xs, rs, gs = slab_from(x.detach()), slab_from(r.detach()), slab_from(dout)
+    out = E.Slab(n, h, w, c, "cuda")
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    op = E.BnTrainOp(xs.view(), out.view(), (wgt.detach(), bias.detach(), rm, rv, 1e-5, 0.1), abn, slope,
+                     rs.view() if res else None, after)
+    st = N.stream_ptr()
+    op(st)
+    dx, dres = E.Slab(n, h, w, c, "cuda"), E.Slab(n, h, w, c, "cuda")
+    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    work = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    rb = res and not after
+    N.check(N.lib().snb_bn_backward_nhwc(
+        N.c_vp(xs.t.data_ptr()), c, N.c_vp(gs.t.data_ptr()), c, n * h * w, c, N.ptr(op.scale), N.ptr(op.shift), N.ptr(op.mean),
+        N.ptr(op.var), N.ptr(wgt.detach()), 1 if abn else 0, 1e-5, slope, N.c_vp(rs.t.data_ptr() if rb else 0), c,
+        N.c_vp(dx.t.data_ptr()), c, N.c_vp(dres.t.data_ptr() if rb else 0), c, N.ptr(dgamma), N.ptr(dbeta), N.ptr(work), st))
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dx, c), x.grad) < 1e-2
+    assert rel_l2(dgamma, wgt.grad) < 5e-3 and rel_l2(dbeta, bias.grad) < 5e-3
+    if rb:
+        assert rel_l2(nchw(dres, c), r.grad) < 6e-3
+
+
+def test_maxpool_backward_ew_and_channel_sum(cuda):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, c, h, w = 2, 64, 18, 22
+    x = bf(F.relu(torch.randn((n, c, h, w), device="cuda", generator=g))).requires_grad_(True)     # many exact ties at 0
+    y = F.max_pool2d(x, 3, 2, 1)
+    dy = bf(torch.randn(y.shape, device="cuda", generator=g))
+    y.backward(dy)
+    xs, dys = slab_from(x.detach()), slab_from(dy)
+    dxs = E.Slab(n, h, w, c, "cuda")
+    st = N.stream_ptr()
+    N.check(N.lib().snb_maxpool3x3s2_backward(N.c_vp(xs.t.data_ptr()), n, h, w, c, c, N.c_vp(dys.t.data_ptr()), c,
+                                              N.c_vp(dxs.t.data_ptr()), c, st))
+    assert rel_l2(nchw(dxs, c), x.grad) < 4e-3                     # sums of up to 4 bf16 gradients, rounded once
+    # elementwise helpers
+    a, b = slab_from(dy), slab_from(bf(torch.randn(y.shape, device="cuda", generator=g)))
+    o = E.Slab(n, y.shape[2], y.shape[3], c, "cuda")
+    px = n * y.shape[2] * y.shape[3]
+    N.check(N.lib().snb_ew_nhwc(N.c_vp(a.t.data_ptr()), c, N.c_vp(b.t.data_ptr()), c, N.c_vp(o.t.data_ptr()), c, px, c, 0, 0.0, st))
+    assert torch.equal(o.t, (a.t.float() + b.t.float()).to(torch.bfloat16))
+    N.check(N.lib().snb_ew_nhwc(N.c_vp(a.t.data_ptr()), c, N.c_vp(b.t.data_ptr()), c, N.c_vp(o.t.data_ptr()), c, px, c, 1, 0.01, st))
+    assert torch.equal(o.t, torch.where(b.t.float() > 0, a.t.float(), a.t.float() * 0.01).to(torch.bfloat16))
+    s = torch.empty(c, device="cuda")
+    work = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    N.check(N.lib().snb_channel_sum_nhwc(N.c_vp(a.t.data_ptr()), px, c, c, N.ptr(s), N.ptr(work), st))
+    assert (s - a.t.float().sum(dim=(0, 1, 2))).abs().max().item() < 1e-3
