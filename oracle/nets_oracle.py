@@ -240,10 +240,14 @@ def inplace_abn_backward(z, dz, var, weight, bias, training=True, eps=1e-5, acti
 
 
 
-def linknet34_forward_train(sd, x, quant=None):
+def linknet34_forward_train(sd, x, quant=None, linear=False):
     """LinkNet34.forward in train() mode with Dropout2d inactive (lib/models/linknet.py:65-90): every BatchNorm2d /
     InPlaceABN normalises with batch statistics and updates its running statistics (momentum 0.1, unbiased variance).
-    Returns (logits, {buffer name: updated value}); `sd` is not modified."""
+    Returns (logits, {buffer name: updated value}); `sd` is not modified.  linear=True drops every ReLU / leaky-ReLU (a
+    test mode: without activation gates the gradients are not chaotic under bf16 rounding, so the whole backward graph
+    can be compared tightly)."""
+    relu = (lambda t: t) if linear else F.relu
+    leaky = (lambda t, s: t) if linear else F.leaky_relu
     q = quant if quant is not None else (lambda t: t)
     new = {}
 
@@ -258,11 +262,11 @@ def linknet34_forward_train(sd, x, quant=None):
 
     def abn(t, prefix):
         z, _, rm, rv = inplace_abn_forward(t, sd[prefix + '.weight'], sd[prefix + '.bias'], sd[prefix + '.running_mean'],
-                                           sd[prefix + '.running_var'], True, 0.1, 1e-5, 'leaky_relu', 0.01)
+                                           sd[prefix + '.running_var'], True, 0.1, 1e-5, 'none' if linear else 'leaky_relu', 0.01)
         new[prefix + '.running_mean'], new[prefix + '.running_var'] = rm, rv
         return z
 
-    x = F.relu(bn(conv(x, 'firstconv', stride=2, padding=3), 'firstbn'))
+    x = relu(bn(conv(x, 'firstconv', stride=2, padding=3), 'firstbn'))
     x = F.max_pool2d(q(x), 3, 2, 1)
     feats = []
     for li, n_blocks in enumerate(RESNET34_BLOCKS):
@@ -270,11 +274,11 @@ def linknet34_forward_train(sd, x, quant=None):
             pre = 'encoder%d.%d' % (li + 1, b)
             stride = 2 if (li > 0 and b == 0) else 1
             ident = x
-            out = q(F.relu(bn(q(conv(x, pre + '.conv1', stride=stride, padding=1)), pre + '.bn1')))
+            out = q(relu(bn(q(conv(x, pre + '.conv1', stride=stride, padding=1)), pre + '.bn1')))
             out = bn(q(conv(out, pre + '.conv2', padding=1)), pre + '.bn2')
             if pre + '.downsample.0.weight' in sd:
                 ident = q(bn(q(conv(x, pre + '.downsample.0', stride=stride)), pre + '.downsample.1'))
-            x = q(F.relu(out + ident))
+            x = q(relu(out + ident))
         feats.append(x)
     e1, e2, e3, e4 = feats
 
@@ -288,8 +292,8 @@ def linknet34_forward_train(sd, x, quant=None):
     d3 = q(decoder(d4, 'decoder3') + e2)
     d2 = q(decoder(d3, 'decoder2') + e1)
     d1 = q(decoder(d2, 'decoder1'))
-    f = F.leaky_relu(F.conv_transpose2d(d1, q(sd['finaldeconv1.weight']), sd['finaldeconv1.bias'], stride=2), 0.01)
-    f = F.leaky_relu(conv(q(f), 'finalconv2'), 0.01)
+    f = leaky(F.conv_transpose2d(d1, q(sd['finaldeconv1.weight']), sd['finaldeconv1.bias'], stride=2), 0.01)
+    f = leaky(conv(q(f), 'finalconv2'), 0.01)
     return conv(q(f), 'finalconv3', padding=1), new
 
 

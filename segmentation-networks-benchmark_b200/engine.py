@@ -807,7 +807,8 @@ class LinkNet34TrainPlan:
 
     STEM_K = 160
 
-    def __init__(self, model, n, h, w, device):
+    def __init__(self, model, n, h, w, device, linear=False):
+        # linear=True (tests only): every ReLU / leaky-ReLU becomes the identity, so gradients can be compared tightly
         if h % 32 or w % 32:
             raise ValueError("height and width must be multiples of 32")
         if model.finaldrop1.p != 0:
@@ -815,7 +816,8 @@ class LinkNet34TrainPlan:
         if model.finalconv3.weight.shape[0] != 1:
             raise NotImplementedError("fused head expects num_classes == 1")
         self.n, self.h, self.w, self.device = n, h, w, device
-        self.ops, self.bn_modules = [], []
+        self.ops, self.bn_modules, self.tape = [], [], []
+        self.model = model
         S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
         p32 = lambda c: (c + 31) // 32 * 32
         zeros = lambda c: torch.zeros(c, dtype=torch.float32, device=device)
@@ -824,13 +826,21 @@ class LinkNet34TrainPlan:
         def bn_of(m):
             return (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum)
 
-        def conv_bn(kind, src, wpacked, bias, cout, hh, ww, m, abn, slope, residual=None, res_after_act=False, **kw):
+        def conv_bn(kind, src, wpacked, bias, cout, hh, ww, m, abn, slope, residual=None, res_after_act=False, bwd=None, **kw):
+            """conv -> BatchNorm / ABN (batch statistics) -> activation (+ residual).  `bwd` = (conv module, input view of
+            the ORIGINAL geometry, stride, padding): what the backward pass differentiates (the forward may run the same
+            convolution on a space-to-depth copy or on im2col rows)."""
             raw = S(hh, ww, cout).view()
             self.ops.append(ConvOp(kind, src, raw, wpacked, bias, relu=False, **kw))
             out = S(hh, ww, cout).view()
-            self.ops.append(BnTrainOp(raw, out, bn_of(m), abn, slope, residual, res_after_act))
+            slope = -1.0 if linear else slope
+            bnop = BnTrainOp(raw, out, bn_of(m), abn, slope, residual, res_after_act)
+            self.ops.append(bnop)
             if isinstance(m, torch.nn.BatchNorm2d):
                 self.bn_modules.append(m)
+            conv, bsrc, stride, pad = bwd
+            self.tape.append(dict(kind='conv_bn', conv=conv, src=bsrc, stride=stride, pad=pad, raw=raw, out=out, bnop=bnop, bn=m,
+                                  abn=abn, slope=slope, res=residual, res_after=res_after_act))
             return out
 
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
@@ -838,11 +848,15 @@ class LinkNet34TrainPlan:
         self.x_rows = S(h2, w2, self.STEM_K)
         self.ops.append(SimpleOp("snb_stem7x7_rows", (N.c_vp(self.x_nchw.data_ptr()), n, 3, h, w,
                                                       N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K), (self.x_nchw, self.x_rows)))
+        # bf16 NHWC copy of the input image (3 channels in an 8-wide slab): the `big` operand of the stem's weight gradient
+        self.x_nhwc = S(h, w, 8)
+        self.x_nhwc.t.zero_()
         stem = conv_bn(N.CONV_1X1, self.x_rows.view(), pack_stem7x7(f32(model.firstconv.weight), self.STEM_K), zeros(64), 64,
-                       h2, w2, model.firstbn, False, 0.0)
+                       h2, w2, model.firstbn, False, 0.0, bwd=(model.firstconv, self.x_nhwc.view(0, 3), 2, 3))
         cur = S(h4, w4, 64)
         self.ops.append(SimpleOp("snb_maxpool3x3s2", (N.c_vp(stem.ptr), n, h2, w2, 64, 64, N.c_vp(cur.view().ptr), 64),
                                  (stem, cur)))
+        self.tape.append(dict(kind='maxpool', src=stem, out=cur.view()))
         cur, ch, hh, ww = cur.view(), 64, h4, w4
 
         skips = []
@@ -855,15 +869,15 @@ class LinkNet34TrainPlan:
                     self.ops.append(SimpleOp("snb_space_to_depth2", (N.c_vp(cur.ptr), n, 2 * hh, 2 * ww, ch, cur.cstride,
                                                                      N.c_vp(x4.view().ptr), 4 * ch), (cur, x4)))
                     t = conv_bn(N.CONV_2X2, x4.view(), pack_conv3x3_s2(f32(blk.conv1.weight)), zeros(cout), cout, hh, ww,
-                                blk.bn1, False, 0.0, valid=True)
+                                blk.bn1, False, 0.0, valid=True, bwd=(blk.conv1, cur, 2, 1))
                     ident = conv_bn(N.CONV_1X1, x4.view(0, ch), pack_conv1x1(f32(blk.downsample[0].weight)), zeros(cout), cout,
-                                    hh, ww, blk.downsample[1], False, -1.0)
+                                    hh, ww, blk.downsample[1], False, -1.0, bwd=(blk.downsample[0], cur, 2, 0))
                 else:
                     t = conv_bn(N.CONV_3X3, cur, pack_conv3x3(f32(blk.conv1.weight)), zeros(cout), cout, hh, ww, blk.bn1,
-                                False, 0.0)
+                                False, 0.0, bwd=(blk.conv1, cur, 1, 1))
                     ident = cur
                 cur = conv_bn(N.CONV_3X3, t, pack_conv3x3(f32(blk.conv2.weight)), zeros(cout), cout, hh, ww, blk.bn2, False,
-                              0.0, residual=ident)
+                              0.0, residual=ident, bwd=(blk.conv2, t, 1, 1))
                 ch = cout
             skips.append(cur)
 
@@ -871,11 +885,13 @@ class LinkNet34TrainPlan:
             mid = cin // 4
             mp = p32(mid)
             a = conv_bn(N.CONV_1X1, x, pack_conv1x1(_pad_mat(f32(d.conv1.weight), mp, cin)), _pad_vec(f32(d.conv1.bias), mp), mp,
-                        hh, ww, d.abn1, True, d.abn1.slope)
+                        hh, ww, d.abn1, True, d.abn1.slope, bwd=(d.conv1, x, 1, 0))
             b_ = conv_bn(N.CONVT_4X4_S2, a, pack_convT4x4(_pad_mat(f32(d.deconv2.weight), mp, mp)),
-                         _pad_vec(f32(d.deconv2.bias), mp), mp, 2 * hh, 2 * ww, d.abn2, True, d.abn2.slope)
+                         _pad_vec(f32(d.deconv2.bias), mp), mp, 2 * hh, 2 * ww, d.abn2, True, d.abn2.slope,
+                         bwd=(d.deconv2, a.slab.view(0, mid), 2, 1))
             return conv_bn(N.CONV_1X1, b_, pack_conv1x1(_pad_mat(f32(d.conv3.weight), n_out, mp)), f32(d.conv3.bias), n_out,
-                           2 * hh, 2 * ww, d.abn3, True, d.abn3.slope, residual=skip, res_after_act=True)
+                           2 * hh, 2 * ww, d.abn3, True, d.abn3.slope, residual=skip, res_after_act=True,
+                           bwd=(d.conv3, b_.slab.view(0, mid), 1, 0))
 
         e1, e2, e3, e4 = skips
         h32, w32 = h // 32, w // 32
@@ -885,12 +901,17 @@ class LinkNet34TrainPlan:
         d1 = decoder(d2, 64, model.decoder1, 64, 8 * h32, 8 * w32, None)
 
         slope1, slope2 = model.finalrelu1.negative_slope, model.finalrelu2.negative_slope
+        if linear:
+            slope1 = slope2 = 1.0        # leaky-ReLU with slope 1 is the identity
         f1 = S(h + 1, w + 1, 32)
         self.ops.append(ConvOp(N.CONVT_3X3_S2_FULL, d1, f1.view(), pack_convT3x3(model.finaldeconv1.weight, 64, 32),
                                f32(model.finaldeconv1.bias), act_slope=slope1))
+        self.tape.append(dict(kind='conv_act', conv=model.finaldeconv1, src=d1, stride=2, pad=0, out=f1.view(), slope=slope1))
         f3 = S(h - 1, w - 1, 32)
         self.ops.append(ConvOp(N.CONV_3X3, f1.view(), f3.view(), pack_conv3x3(f32(model.finalconv2.weight)),
                                f32(model.finalconv2.bias), act_slope=slope2, valid=True))
+        self.tape.append(dict(kind='conv_act', conv=model.finalconv2, src=f1.view(), stride=1, pad=0, out=f3.view(), slope=slope2))
+        self.tape.append(dict(kind='conv_head', conv=model.finalconv3, src=f3.view(), stride=1, pad=1))
         self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
         pick = torch.zeros(32, dtype=torch.float32, device=device)
         pick[0] = 1.0
@@ -901,9 +922,125 @@ class LinkNet34TrainPlan:
 
     def load_nchw(self, x):
         self.x_nchw.copy_(x)
+        self.x_nhwc.t[..., :3].copy_(x.permute(0, 2, 3, 1))
 
     def run(self):
         out = VGGUNetPlan.run(self)
         for m in self.bn_modules:            # nn.BatchNorm2d bookkeeping (momentum is fixed, the counter only counts)
             m.num_batches_tracked += 1
         return out
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def backward(self, dlogits):
+        """Gradients of every parameter given d loss / d logits (float [N, 1, H, W] or [N, H, W]); walks the tape in
+        reverse: BatchNorm / ABN backward (snb_bn_backward_nhwc), bias gradients (channel sums), generic dgrad / wgrad
+        (csrc/conv_generic.cu), max-pool backward.  Returns {parameter: gradient} (float tensors in the parameter's layout).
+        Activation gradients are bf16 NHWC slabs; gradients flowing into one tensor from several consumers are added."""
+        lib, st = N.lib(), N.stream_ptr()
+        n, dev = self.n, self.device
+        grads, pgrads = {}, {}
+
+        def add_grad(view, gslab):
+            key = id(view.slab)
+            if key in grads:
+                acc = grads[key]
+                N.check(lib.snb_ew_nhwc(N.c_vp(acc.t.data_ptr()), acc.c, N.c_vp(gslab.t.data_ptr()), gslab.c,
+                                        N.c_vp(acc.t.data_ptr()), acc.c, n * acc.h * acc.w, min(acc.c, gslab.c), 0, 0.0, st))
+            else:
+                grads[key] = gslab
+
+        def put(param, g):
+            pgrads[param] = g if param not in pgrads else pgrads[param] + g
+
+        def conv_backward(conv, src, stride, pad, draw, need_dsrc=True):
+            """draw = gradient slab of the convolution's output (bf16, channels = slab width)."""
+            transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+            k = conv.kernel_size[0]
+            cin_t, cout_t = conv.weight.shape[1 if not transposed else 0], conv.weight.shape[0 if not transposed else 1]
+            g = N.ConvGeom()
+            g.n, g.kh, g.kw, g.stride, g.pad = n, k, k, stride, pad
+            if not transposed:      # big = input, small = output
+                g.big_h, g.big_w, g.big_c, g.big_cstride = src.slab.h, src.slab.w, src.c, src.cstride
+                g.small_h, g.small_w, g.small_c, g.small_cstride = draw.h, draw.w, cout_t, draw.c
+                big_ptr, small_ptr = src.ptr, draw.t.data_ptr()
+            else:                   # big = the transposed conv's output, small = its input
+                g.big_h, g.big_w, g.big_c, g.big_cstride = draw.h, draw.w, cout_t, draw.c
+                g.small_h, g.small_w, g.small_c, g.small_cstride = src.slab.h, src.slab.w, src.c, src.cstride
+                big_ptr, small_ptr = draw.t.data_ptr(), src.ptr
+            dw = torch.empty_like(conv.weight, dtype=torch.float32)
+            N.check(lib.snb_conv_generic_wgrad(ctypes.byref(g), N.c_vp(big_ptr), N.c_vp(small_ptr), N.ptr(dw), st))
+            put(conv.weight, dw)
+            if conv.bias is not None:
+                cw = (cout_t + 7) // 8 * 8
+                sums = torch.empty(cw, dtype=torch.float32, device=dev)
+                work = torch.empty(2 * cw, dtype=torch.float64, device=dev)
+                N.check(lib.snb_channel_sum_nhwc(N.c_vp(draw.t.data_ptr()), n * draw.h * draw.w, cw, draw.c, N.ptr(sums),
+                                                 N.ptr(work), st))
+                put(conv.bias, sums[:cout_t].clone())
+            if not need_dsrc:
+                return
+            dsrc = Slab(n, src.slab.h, src.slab.w, src.slab.c, dev)
+            if dsrc.c != src.c:
+                dsrc.t.zero_()      # padded channels of the slab carry no gradient
+            w32 = conv.weight.detach().float().contiguous()
+            if not transposed:
+                N.check(lib.snb_conv_generic_dgrad(ctypes.byref(g), N.c_vp(small_ptr), N.ptr(w32), N.c_vp(0),
+                                                   N.c_vp(dsrc.t.data_ptr()), st))
+            else:
+                g.small_cstride = dsrc.c
+                N.check(lib.snb_conv_generic_fwd(ctypes.byref(g), N.c_vp(big_ptr), N.ptr(w32), N.c_vp(0),
+                                                 N.c_vp(dsrc.t.data_ptr()), st))
+            self._keep.append(w32)
+            add_grad(src, dsrc)
+
+        self._keep = []
+        dl = dlogits.detach().reshape(n, self.h, self.w).float()
+        for node in reversed(self.tape):
+            kind = node['kind']
+            if kind == 'conv_head':
+                draw = Slab(n, self.h, self.w, 8, dev)
+                draw.t.zero_()
+                draw.t[..., 0].copy_(dl)
+                conv_backward(node['conv'], node['src'], node['stride'], node['pad'], draw)
+            elif kind == 'conv_act':
+                out = node['out']
+                g_out = grads.pop(id(out.slab))
+                dz = Slab(n, out.slab.h, out.slab.w, out.slab.c, dev)
+                N.check(lib.snb_ew_nhwc(N.c_vp(g_out.t.data_ptr()), g_out.c, N.c_vp(out.ptr), out.cstride, N.c_vp(dz.t.data_ptr()),
+                                        dz.c, n * dz.h * dz.w, dz.c, 1, float(node['slope']), st))
+                conv_backward(node['conv'], node['src'], node['stride'], node['pad'], dz)
+            elif kind == 'maxpool':
+                src, out = node['src'], node['out']
+                g_out = grads.pop(id(out.slab))
+                dsrc = Slab(n, src.slab.h, src.slab.w, src.slab.c, dev)
+                N.check(lib.snb_maxpool3x3s2_backward(N.c_vp(src.ptr), n, src.slab.h, src.slab.w, src.c, src.cstride,
+                                                      N.c_vp(g_out.t.data_ptr()), g_out.c, N.c_vp(dsrc.t.data_ptr()), dsrc.c, st))
+                add_grad(src, dsrc)
+            else:   # conv_bn
+                out, raw, bnop, m = node['out'], node['raw'], node['bnop'], node['bn']
+                g_out = grads.pop(id(out.slab))
+                res, after = node['res'], node['res_after']
+                if res is not None and after:
+                    add_grad(res, g_out)                      # out = act(bn) + res: the skip sees the same gradient
+                cpad = raw.c
+                draw = Slab(n, raw.slab.h, raw.slab.w, cpad, dev)
+                rb = res is not None and not after
+                dres = Slab(n, raw.slab.h, raw.slab.w, cpad, dev) if rb else None
+                dgamma = torch.empty(cpad, dtype=torch.float32, device=dev)
+                dbeta = torch.empty(cpad, dtype=torch.float32, device=dev)
+                work = torch.empty(2 * cpad, dtype=torch.float64, device=dev)
+                N.check(lib.snb_bn_backward_nhwc(
+                    N.c_vp(raw.ptr), raw.cstride, N.c_vp(g_out.t.data_ptr()), g_out.c, n * raw.slab.h * raw.slab.w, cpad,
+                    N.ptr(bnop.scale), N.ptr(bnop.shift), N.ptr(bnop.mean), N.ptr(bnop.var), N.ptr(bnop.gamma),
+                    1 if node['abn'] else 0, float(m.eps), float(node['slope']), N.c_vp(res.ptr if rb else 0),
+                    res.cstride if rb else 0, N.c_vp(draw.t.data_ptr()), draw.c, N.c_vp(dres.t.data_ptr() if rb else 0),
+                    dres.c if rb else 0, N.ptr(dgamma), N.ptr(dbeta), N.ptr(work), st))
+                c = m.weight.numel()
+                put(m.weight, dgamma[:c].clone())
+                put(m.bias, dbeta[:c].clone())
+                if rb:
+                    add_grad(res, dres)
+                conv_backward(node['conv'], node['src'], node['stride'], node['pad'], draw,
+                              need_dsrc=node['conv'] is not self.model.firstconv)
+                self._keep.extend((dgamma, dbeta, work))
+        return pgrads

@@ -54,6 +54,29 @@ def _bn(m, abn=False):
     return (m.weight, m.bias, m.running_mean, m.running_var, m.eps, abn)
 
 
+class _TrainStep(torch.autograd.Function):
+    """train() forward + backward of LinkNet34 as one autograd node: forward runs LinkNet34TrainPlan, backward walks its
+    tape (BatchNorm / ABN backward, generic dgrad / wgrad, max-pool backward) and hands every parameter its gradient."""
+
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        plan = model.plan_train(x.shape[0], x.shape[2], x.shape[3])
+        plan.load_nchw(x.detach().float())
+        out = plan.run()
+        ctx.plan, ctx.model_params = plan, list(model.parameters())
+        return out.unsqueeze(1).clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        with torch.cuda.device(dout.device):
+            pg = ctx.plan.backward(dout.contiguous())
+        grads = []
+        for p in ctx.model_params:
+            g = pg.get(p)
+            grads.append(None if g is None else g.reshape(p.shape).to(p.dtype))
+        return (None, None) + tuple(grads)
+
+
 class LinkNet34(nn.Module):
     def __init__(self, num_classes=1, num_channels=3, pretrained=True):
         super().__init__()
@@ -126,13 +149,13 @@ class LinkNet34(nn.Module):
             if dev.type != 'cuda':
                 raise RuntimeError("LinkNet34 runs on CUDA devices only (no CPU fallback); call .cuda()")
             with torch.no_grad():
-                cache[key] = LinkNet34TrainPlan(self, n, h, w, dev)
+                cache[key] = LinkNet34TrainPlan(self, n, h, w, dev, linear=bool(self.__dict__.get('_test_linear', False)))
         return cache[key]
 
     def forward(self, x):
         """eval(): folded BatchNorm / InPlaceABN (running statistics).  train(): batch statistics, running statistics
-        updated in place (FORWARD ONLY: the returned logits carry no autograd history; the backward of the convolutions
-        is not built)."""
+        updated in place; with grad enabled the logits are an autograd node whose backward fills every parameter's
+        .grad (LinkNet34TrainPlan.backward).  The gradient with respect to the input image is not computed."""
         N.require_cuda()
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
@@ -140,8 +163,10 @@ class LinkNet34(nn.Module):
             raise ValueError("expected input of shape [N, 3, H, W]")
         with torch.cuda.device(x.device):
             if self.training:
-                p = self.plan_train(x.shape[0], x.shape[2], x.shape[3])
                 self.__dict__.pop('_plan_stamp', None)        # the eval plans fold the running statistics: rebuild them
+                if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                    return _TrainStep.apply(x, self, *self.parameters())
+                p = self.plan_train(x.shape[0], x.shape[2], x.shape[3])
             else:
                 p = self.plan(x.shape[0], x.shape[2], x.shape[3], sigmoid=False)
             p.load_nchw(x.detach().float())

@@ -289,3 +289,84 @@ def test_bn_train_nhwc_against_torch(cuda, c, abn, slope, res, after):
     assert (rm - (rm0 * 0.9 + 0.1 * mean)).abs().max().item() < 1e-5
     assert (rv - (rv0 * 0.9 + 0.1 * var * cnt / (cnt - 1))).abs().max().item() < 1e-4
     assert (op.mean - mean).abs().max().item() < 1e-5 and (op.var - var).abs().max().item() < 1e-4
+
+
+def _linknet_step(sd, x, t, quant=None, linear=False):
+    """torch autograd on the CPU through the restated train-mode forward and B * bce_jaccard (torch_train.py:186-189)."""
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    logits, _ = no.linknet34_forward_train(leaf, x, quant=quant, linear=linear)
+    (no.bce_jaccard(logits, t) * x.shape[0]).backward()
+    return logits.detach(), {k: v.grad for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.grad is not None}
+
+
+def _device_step(sd, x, t, linear=False):
+    from snb_b200.lib import losses
+    from snb_b200.lib.models import LinkNet34
+
+    m = LinkNet34(pretrained=False)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.finaldrop1.p = 0.0
+    m._test_linear = linear
+    logits = m(x.cuda())
+    assert logits.requires_grad
+    (losses.BCEWithLogitsLossAndSmoothJaccard()(logits, t.cuda()) * x.shape[0]).backward()
+    return logits.detach().cpu(), {k: p.grad.cpu() for k, p in m.named_parameters()}
+
+
+def _rel_errors(got, want):
+    """rel-L2 per tensor.  A bias whose effect is removed by a later batch norm's mean subtraction (a conv bias in front of
+    a norm; in the gate-free network every norm bias that reaches another norm) has an exactly zero gradient: the
+    reference holds float noise there (norm < 1e-7), ours must be noise too: bf16 rounding noise, below a tenth of the
+    same module's weight gradient."""
+    live, dead = {}, {}
+    for name, g in got.items():
+        if want[name].norm().item() < 1e-7:
+            dead[name] = g.norm().item() / want[name.replace("bias", "weight")].norm().item()
+        else:
+            live[name] = ((g - want[name]).norm() / want[name].norm()).item()
+    return live, dead
+
+
+def test_linknet34_training_step_gradients(cuda):
+    """BASELINE configs[1]: LinkNet34 forward + backward in train mode (batch statistics, Dropout2d off,
+    loss = B * bce_jaccard) on the device against torch autograd through the fp32 oracle of the same step.
+
+    (1) Gate-free network (every ReLU / leaky-ReLU replaced by the identity in both implementations): all 162 parameter
+        gradients within rel-L2 5e-2 (SURVEY 8d's suggested bf16 tolerance; measured <= 3.4e-2).  This pins the whole
+        backward graph: generic dgrad / wgrad, BatchNorm / ABN backward, residual and skip fan-out, max-pool, head, stem.
+    (2) Real network: with activation gates, per-sample gradients of a 50-layer net are chaotic under bf16 rounding of the
+        FORWARD (0.3 % of the gates flip per layer): a bf16 restatement of the reference itself (the oracle with bf16
+        rounding at the same points) deviates from fp32 by 0.1 in decoder1 and 0.8 in the encoder.  So the device is
+        held to 5e-2 where bf16 allows it (head, decoder1.abn3), to the bf16 oracle's own noise level elsewhere, and to
+        matching gradient norms everywhere."""
+    sd = synth.linknet34_state_dict(seed=6)
+    n, hw = 8, 64
+    rs = np.random.RandomState(31)
+    x = torch.from_numpy(rs.standard_normal((n, 3, hw, hw)).astype(np.float32))
+    t = torch.from_numpy((rs.rand(n, 1, hw, hw) > 0.5).astype(np.int64))
+    # (1) gate-free
+    _, want = _linknet_step(sd, x, t, linear=True)
+    _, got = _device_step(sd, x, t, linear=True)
+    assert set(got) == set(want) and len(got) == 162           # every parameter tensor of the model
+    live, dead = _rel_errors(got, want)
+    worst = sorted(((e, k) for k, e in live.items()), reverse=True)
+    print("gate-free: largest rel-L2 gradient errors:", [(round(e, 4), k) for e, k in worst[:4]])
+    # the stem sits behind the only gate left, the max-pool, whose arg-max flips under bf16 rounding (measured 8e-2)
+    assert all(e < (0.15 if k.startswith("first") else 5e-2) for e, k in worst), worst[:6]
+    assert len(live) >= 100 and max(dead.values()) < 0.1, dead
+    # (2) real network
+    logits_ref, want = _linknet_step(sd, x, t)
+    _, noise = _linknet_step(sd, x, t, quant=no.bf16_round)
+    logits, got = _device_step(sd, x, t)
+    assert (torch.sigmoid(logits) - torch.sigmoid(logits_ref)).abs().max().item() < BF16_PROB_TOL
+    live, dead = _rel_errors(got, want)
+    floor, _ = _rel_errors(noise, want)
+    for name in ("finalconv3.weight", "finalconv3.bias", "finalconv2.weight", "finalconv2.bias", "finaldeconv1.weight",
+                 "finaldeconv1.bias", "decoder1.abn3.weight", "decoder1.abn3.bias"):
+        assert live[name] < 5e-2, (name, live[name])
+    for name, e in live.items():
+        assert e < 1.5 * floor[name] + 5e-2, (name, e, floor[name])
+        ratio = got[name].norm().item() / want[name].norm().item()
+        assert 0.7 < ratio < 1.4, (name, ratio)
+    assert max(dead.values()) < 0.1, dead
