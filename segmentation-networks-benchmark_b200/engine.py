@@ -791,6 +791,15 @@ class BnTrainOp:
                      N.ptr(self.mean), N.ptr(self.var), N.ptr(self.work))
         self.flops, self.launches = 0.0, 3
 
+    def refresh(self):
+        """padded layers keep copies of the parameters: re-read them (running statistics are copied back after each run)"""
+        weight, bias, rmean, rvar = self.keep[3:7]
+        c = weight.numel()
+        self.gamma[:c].copy_(weight.detach())
+        self.beta[:c].copy_(bias.detach())
+        self.rmean[:c].copy_(rmean)
+        self.rvar[:c].copy_(rvar)
+
     def __call__(self, stream):
         N.check(N.lib().snb_bn_train_nhwc(*self.args, stream))
         if self.padded:
@@ -818,6 +827,13 @@ class LinkNet34TrainPlan:
         self.n, self.h, self.w, self.device = n, h, w, device
         self.ops, self.bn_modules, self.tape = [], [], []
         self.model = model
+        self._repack = []     # (device tensor, function recomputing it from the module's current parameters)
+
+        def P(fn):
+            t = fn()
+            self._repack.append((t, fn))
+            return t
+
         S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
         p32 = lambda c: (c + 31) // 32 * 32
         zeros = lambda c: torch.zeros(c, dtype=torch.float32, device=device)
@@ -851,7 +867,7 @@ class LinkNet34TrainPlan:
         # bf16 NHWC copy of the input image (3 channels in an 8-wide slab): the `big` operand of the stem's weight gradient
         self.x_nhwc = S(h, w, 8)
         self.x_nhwc.t.zero_()
-        stem = conv_bn(N.CONV_1X1, self.x_rows.view(), pack_stem7x7(f32(model.firstconv.weight), self.STEM_K), zeros(64), 64,
+        stem = conv_bn(N.CONV_1X1, self.x_rows.view(), P(lambda: pack_stem7x7(f32(model.firstconv.weight), self.STEM_K)), zeros(64), 64,
                        h2, w2, model.firstbn, False, 0.0, bwd=(model.firstconv, self.x_nhwc.view(0, 3), 2, 3))
         cur = S(h4, w4, 64)
         self.ops.append(SimpleOp("snb_maxpool3x3s2", (N.c_vp(stem.ptr), n, h2, w2, 64, 64, N.c_vp(cur.view().ptr), 64),
@@ -868,15 +884,15 @@ class LinkNet34TrainPlan:
                     x4 = S(hh, ww, 4 * ch)
                     self.ops.append(SimpleOp("snb_space_to_depth2", (N.c_vp(cur.ptr), n, 2 * hh, 2 * ww, ch, cur.cstride,
                                                                      N.c_vp(x4.view().ptr), 4 * ch), (cur, x4)))
-                    t = conv_bn(N.CONV_2X2, x4.view(), pack_conv3x3_s2(f32(blk.conv1.weight)), zeros(cout), cout, hh, ww,
+                    t = conv_bn(N.CONV_2X2, x4.view(), P(lambda blk=blk: pack_conv3x3_s2(f32(blk.conv1.weight))), zeros(cout), cout, hh, ww,
                                 blk.bn1, False, 0.0, valid=True, bwd=(blk.conv1, cur, 2, 1))
-                    ident = conv_bn(N.CONV_1X1, x4.view(0, ch), pack_conv1x1(f32(blk.downsample[0].weight)), zeros(cout), cout,
+                    ident = conv_bn(N.CONV_1X1, x4.view(0, ch), P(lambda blk=blk: pack_conv1x1(f32(blk.downsample[0].weight))), zeros(cout), cout,
                                     hh, ww, blk.downsample[1], False, -1.0, bwd=(blk.downsample[0], cur, 2, 0))
                 else:
-                    t = conv_bn(N.CONV_3X3, cur, pack_conv3x3(f32(blk.conv1.weight)), zeros(cout), cout, hh, ww, blk.bn1,
+                    t = conv_bn(N.CONV_3X3, cur, P(lambda blk=blk: pack_conv3x3(f32(blk.conv1.weight))), zeros(cout), cout, hh, ww, blk.bn1,
                                 False, 0.0, bwd=(blk.conv1, cur, 1, 1))
                     ident = cur
-                cur = conv_bn(N.CONV_3X3, t, pack_conv3x3(f32(blk.conv2.weight)), zeros(cout), cout, hh, ww, blk.bn2, False,
+                cur = conv_bn(N.CONV_3X3, t, P(lambda blk=blk: pack_conv3x3(f32(blk.conv2.weight))), zeros(cout), cout, hh, ww, blk.bn2, False,
                               0.0, residual=ident, bwd=(blk.conv2, t, 1, 1))
                 ch = cout
             skips.append(cur)
@@ -884,12 +900,12 @@ class LinkNet34TrainPlan:
         def decoder(x, cin, d, n_out, hh, ww, skip):
             mid = cin // 4
             mp = p32(mid)
-            a = conv_bn(N.CONV_1X1, x, pack_conv1x1(_pad_mat(f32(d.conv1.weight), mp, cin)), _pad_vec(f32(d.conv1.bias), mp), mp,
+            a = conv_bn(N.CONV_1X1, x, P(lambda: pack_conv1x1(_pad_mat(f32(d.conv1.weight), mp, cin))), P(lambda: _pad_vec(f32(d.conv1.bias), mp)), mp,
                         hh, ww, d.abn1, True, d.abn1.slope, bwd=(d.conv1, x, 1, 0))
-            b_ = conv_bn(N.CONVT_4X4_S2, a, pack_convT4x4(_pad_mat(f32(d.deconv2.weight), mp, mp)),
-                         _pad_vec(f32(d.deconv2.bias), mp), mp, 2 * hh, 2 * ww, d.abn2, True, d.abn2.slope,
+            b_ = conv_bn(N.CONVT_4X4_S2, a, P(lambda: pack_convT4x4(_pad_mat(f32(d.deconv2.weight), mp, mp))),
+                         P(lambda: _pad_vec(f32(d.deconv2.bias), mp)), mp, 2 * hh, 2 * ww, d.abn2, True, d.abn2.slope,
                          bwd=(d.deconv2, a.slab.view(0, mid), 2, 1))
-            return conv_bn(N.CONV_1X1, b_, pack_conv1x1(_pad_mat(f32(d.conv3.weight), n_out, mp)), f32(d.conv3.bias), n_out,
+            return conv_bn(N.CONV_1X1, b_, P(lambda: pack_conv1x1(_pad_mat(f32(d.conv3.weight), n_out, mp))), f32(d.conv3.bias), n_out,
                            2 * hh, 2 * ww, d.abn3, True, d.abn3.slope, residual=skip, res_after_act=True,
                            bwd=(d.conv3, b_.slab.view(0, mid), 1, 0))
 
@@ -904,21 +920,32 @@ class LinkNet34TrainPlan:
         if linear:
             slope1 = slope2 = 1.0        # leaky-ReLU with slope 1 is the identity
         f1 = S(h + 1, w + 1, 32)
-        self.ops.append(ConvOp(N.CONVT_3X3_S2_FULL, d1, f1.view(), pack_convT3x3(model.finaldeconv1.weight, 64, 32),
+        self.ops.append(ConvOp(N.CONVT_3X3_S2_FULL, d1, f1.view(), P(lambda: pack_convT3x3(model.finaldeconv1.weight, 64, 32)),
                                f32(model.finaldeconv1.bias), act_slope=slope1))
         self.tape.append(dict(kind='conv_act', conv=model.finaldeconv1, src=d1, stride=2, pad=0, out=f1.view(), slope=slope1))
         f3 = S(h - 1, w - 1, 32)
-        self.ops.append(ConvOp(N.CONV_3X3, f1.view(), f3.view(), pack_conv3x3(f32(model.finalconv2.weight)),
+        self.ops.append(ConvOp(N.CONV_3X3, f1.view(), f3.view(), P(lambda: pack_conv3x3(f32(model.finalconv2.weight))),
                                f32(model.finalconv2.bias), act_slope=slope2, valid=True))
         self.tape.append(dict(kind='conv_act', conv=model.finalconv2, src=f1.view(), stride=1, pad=0, out=f3.view(), slope=slope2))
         self.tape.append(dict(kind='conv_head', conv=model.finalconv3, src=f3.view(), stride=1, pad=1))
         self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
         pick = torch.zeros(32, dtype=torch.float32, device=device)
         pick[0] = 1.0
-        self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, pack_conv2x2(f32(model.finalconv3.weight), 32, 32),
-                               _pad_vec(f32(model.finalconv3.bias), 32), relu=False, head=(pick, 0.0, False, self.out)))
+        self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, P(lambda: pack_conv2x2(f32(model.finalconv3.weight), 32, 32)),
+                               P(lambda: _pad_vec(f32(model.finalconv3.bias), 32)), relu=False, head=(pick, 0.0, False, self.out)))
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
+
+    def refresh(self):
+        """Re-pack the weights from the module's current parameters into the plan's existing buffers (after an optimiser
+        step): no handle, slab or tensor map changes.  Biases, BatchNorm / ABN weights and running statistics that are
+        not padded are read through the parameters' own pointers and need nothing."""
+        with torch.no_grad():
+            for t, fn in self._repack:
+                t.copy_(fn())
+            for op in self.ops:
+                if isinstance(op, BnTrainOp) and op.padded:
+                    op.refresh()
 
     def load_nchw(self, x):
         self.x_nchw.copy_(x)

@@ -135,14 +135,16 @@ class LinkNet34(nn.Module):
         return cache[key]
 
     def plan_train(self, n, h, w):
-        """Training-mode plan (batch statistics); rebuilt whenever a parameter or buffer object changed version other than
-        through the plan's own running-statistics updates, i.e. after every optimiser step (packing the weights again is
-        the cost of that; a repack-in-place path belongs to the backward work)."""
+        """Training-mode plan (batch statistics).  After an optimiser step (same parameter storages, new versions) the
+        cached plans re-pack their weights in place (`LinkNet34TrainPlan.refresh`); a plan is only rebuilt when a parameter
+        was replaced by a different tensor."""
         cache = self.__dict__.setdefault('_train_plans', {})
-        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self.__dict__.get('_train_stamp') != stamp:
+        ptrs = tuple(p.data_ptr() for p in self.parameters())
+        versions = tuple(p._version for p in self.parameters())
+        if self.__dict__.get('_train_ptrs') != ptrs:
             cache.clear()
-            self.__dict__['_train_stamp'] = stamp
+            self.__dict__['_train_ptrs'] = ptrs
+            self.__dict__['_train_versions'] = {}
         key = (n, h, w)
         if key not in cache:
             dev = self.finalconv3.weight.device
@@ -150,6 +152,10 @@ class LinkNet34(nn.Module):
                 raise RuntimeError("LinkNet34 runs on CUDA devices only (no CPU fallback); call .cuda()")
             with torch.no_grad():
                 cache[key] = LinkNet34TrainPlan(self, n, h, w, dev, linear=bool(self.__dict__.get('_test_linear', False)))
+            self.__dict__['_train_versions'][key] = versions
+        elif self.__dict__['_train_versions'].get(key) != versions:
+            cache[key].refresh()
+            self.__dict__['_train_versions'][key] = versions
         return cache[key]
 
     def forward(self, x):

@@ -375,3 +375,37 @@ def test_linknet34_training_step_gradients(cuda):
         ratio = got[name].norm().item() / want[name].norm().item()
         assert 0.5 < ratio < 2.0, (name, ratio)
     assert max(dead.values()) < 0.1, dead
+
+
+def test_linknet34_sgd_steps_reduce_the_loss(cuda):
+    """A few SGD steps on one fixed batch through the native forward / backward: the loss goes down, and the plan that
+    re-packs its weights in place after each optimiser step computes the same forward as a freshly built one."""
+    from snb_b200.lib import losses
+    from snb_b200.lib.models import LinkNet34
+
+    torch.manual_seed(3)
+    m = LinkNet34(pretrained=False).cuda().train()          # PyTorch default initialisation
+    m.finaldrop1.p = 0.0
+    rs = np.random.RandomState(5)
+    x = torch.from_numpy(rs.standard_normal((8, 3, 64, 64)).astype(np.float32)).cuda()
+    yy, xx = np.mgrid[0:64, 0:64]
+    t = torch.from_numpy(((yy // 16 + xx // 16) % 2)[None, None].repeat(8, 0).astype(np.int64)).cuda()   # a learnable pattern
+    opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+    crit = losses.BCEWithLogitsLossAndSmoothJaccard()
+    hist = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = crit(m(x), t)
+        loss.backward()
+        opt.step()
+        hist.append(float(loss.detach()))
+    assert all(np.isfinite(hist)), hist
+    assert hist[-1] < hist[0] - 0.03 and all(b < a + 1e-3 for a, b in zip(hist, hist[1:])), hist   # measured 0.720 -> 0.670
+    # refreshed plan == fresh plan
+    with torch.no_grad():
+        a = m(x)
+        m2 = LinkNet34(pretrained=False).cuda().train()
+        m2.finaldrop1.p = 0.0
+        m2.load_state_dict(m.state_dict())
+        b = m2(x)
+    assert (torch.sigmoid(a) - torch.sigmoid(b)).abs().max().item() < 1e-2
