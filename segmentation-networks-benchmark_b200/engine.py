@@ -838,6 +838,8 @@ class LinkNet34TrainPlan:
         p32 = lambda c: (c + 31) // 32 * 32
         zeros = lambda c: torch.zeros(c, dtype=torch.float32, device=device)
         f32 = lambda t: t.detach().float().contiguous()
+        # SNB_TRAIN_TC_DGRAD=0 keeps the generic CUDA-core dgrad everywhere (A/B runs)
+        tc_dgrad = os.environ.get("SNB_TRAIN_TC_DGRAD", "1") != "0"
 
         def bn_of(m):
             return (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum)
@@ -855,8 +857,26 @@ class LinkNet34TrainPlan:
             if isinstance(m, torch.nn.BatchNorm2d):
                 self.bn_modules.append(m)
             conv, bsrc, stride, pad = bwd
-            self.tape.append(dict(kind='conv_bn', conv=conv, src=bsrc, stride=stride, pad=pad, raw=raw, out=out, bnop=bnop, bn=m,
-                                  abn=abn, slope=slope, res=residual, res_after=res_after_act))
+            node = dict(kind='conv_bn', conv=conv, src=bsrc, stride=stride, pad=pad, raw=raw, out=out, bnop=bnop, bn=m,
+                        abn=abn, slope=slope, res=residual, res_after=res_after_act)
+            # input gradient on the tensor cores where the forward kernels cover it: a stride-1 conv3x3 (padding 1) or
+            # conv1x1 is its own adjoint with the taps flipped and Cin / Cout swapped
+            k = conv.kernel_size[0]
+            if (tc_dgrad and isinstance(conv, torch.nn.Conv2d) and stride == 1 and k in (1, 3) and pad == k // 2 and
+                    bsrc.c0 == 0 and bsrc.slab.c % 32 == 0 and conv is not model.firstconv):
+                cin_pad, cout_pad = bsrc.slab.c, cout
+                draw = S(hh, ww, cout_pad)
+                dsrc = S(bsrc.slab.h, bsrc.slab.w, cin_pad)
+
+                def adjoint(conv=conv, cin_pad=cin_pad, cout_pad=cout_pad, k=k):
+                    wt = _pad_mat(f32(conv.weight), cout_pad, cin_pad)            # [cout_pad, cin_pad, k, k]
+                    wt = wt.flip(2, 3).transpose(0, 1).contiguous()                 # [cin_pad, cout_pad, k, k]
+                    return pack_conv3x3(wt) if k == 3 else pack_conv1x1(wt)
+
+                node['draw'], node['dsrc'] = draw, dsrc
+                node['dgrad_op'] = ConvOp(N.CONV_3X3 if k == 3 else N.CONV_1X1, draw.view(), dsrc.view(), P(adjoint),
+                                          zeros(cin_pad), relu=False)
+            self.tape.append(node)
             return out
 
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
@@ -1050,7 +1070,7 @@ class LinkNet34TrainPlan:
                 if res is not None and after:
                     add_grad(res, g_out)                      # out = act(bn) + res: the skip sees the same gradient
                 cpad = raw.c
-                draw = Slab(n, raw.slab.h, raw.slab.w, cpad, dev)
+                draw = node.get('draw') or Slab(n, raw.slab.h, raw.slab.w, cpad, dev)
                 rb = res is not None and not after
                 dres = Slab(n, raw.slab.h, raw.slab.w, cpad, dev) if rb else None
                 dgamma = torch.empty(cpad, dtype=torch.float32, device=dev)
@@ -1068,6 +1088,9 @@ class LinkNet34TrainPlan:
                 if rb:
                     add_grad(res, dres)
                 conv_backward(node['conv'], node['src'], node['stride'], node['pad'], draw,
-                              need_dsrc=node['conv'] is not self.model.firstconv)
+                              need_dsrc=node['conv'] is not self.model.firstconv and 'dgrad_op' not in node)
+                if 'dgrad_op' in node:
+                    node['dgrad_op'](st)                      # tcgen05: conv with the adjoint weights
+                    add_grad(node['src'], node['dsrc'])
                 self._keep.extend((dgamma, dbeta, work))
         return pgrads
