@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "snb_internal.h"
 
@@ -40,8 +41,8 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvGeom g, const __n
                                                            const __nv_bfloat16* __restrict__ small_,
                                                            const float* __restrict__ w, void* __restrict__ out,
                                                            int64_t out_cs, const float* __restrict__ bias, int k_split) {
-  __shared__ float As[kGK][kGT + 4];
-  __shared__ float Bs[kGK][kGT + 4];
+  __shared__ __align__(16) float As[kGK][kGT + 4];
+  __shared__ __align__(16) float Bs[kGK][kGT + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int taps = g.kh * g.kw;
   const int64_t small_px = (int64_t)g.n * g.sh * g.sw, big_px = (int64_t)g.n * g.bh * g.bw;
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvGeom g, const __n
     }
   }
   const int kc_ch = MODE == 0 ? g.bc : g.sc;   // channels per tap along K (FWD: ci, DGRAD: co)
+  // 8-byte loads of 4 consecutive channels: pixel rows of both slabs start 8-byte aligned
+  const bool vec4 = MODE == 2 && g.big_cs % 4 == 0 && g.small_cs % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(big) & 7) == 0 && (reinterpret_cast<uintptr_t>(small_) & 7) == 0;
 
   for (int64_t k0 = k_begin; k0 < k_end; k0 += kGK) {
     if (MODE == 2) {
@@ -101,15 +105,29 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvGeom g, const __n
       if (p < k_end) {
         const int ox = (int)(p % g.sw), oy = (int)((p / g.sw) % g.sh), nn = (int)(p / ((int64_t)g.sw * g.sh));
         const __nv_bfloat16* sp = small_ + p * g.small_cs;
+        if (vec4 && m0 + wc4 + 3 < g.sc) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(sp + m0 + wc4));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+          const float2 lo = __bfloat1622float2(h[0]), hi = __bfloat1622float2(h[1]);
+          a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (m0 + wc4 + e < g.sc) a[e] = ldbf(sp + m0 + wc4 + e);
+          for (int e = 0; e < 4; ++e)
+            if (m0 + wc4 + e < g.sc) a[e] = ldbf(sp + m0 + wc4 + e);
+        }
         const int iy = oy * g.stride + tap_w / g.kw - g.pad, ix = ox * g.stride + tap_w % g.kw - g.pad;
         if (iy >= 0 && iy < g.bh && ix >= 0 && ix < g.bw) {
           const __nv_bfloat16* bp = big + (((int64_t)nn * g.bh + iy) * g.bw + ix) * g.big_cs;
+          if (vec4 && n0 + wc4 + 3 < g.bc) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(bp + n0 + wc4));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float2 lo = __bfloat1622float2(h[0]), hi = __bfloat1622float2(h[1]);
+            b[0] = lo.x; b[1] = lo.y; b[2] = hi.x; b[3] = hi.y;
+          } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n0 + wc4 + e < g.bc) b[e] = ldbf(bp + n0 + wc4 + e);
+            for (int e = 0; e < 4; ++e)
+              if (n0 + wc4 + e < g.bc) b[e] = ldbf(bp + n0 + wc4 + e);
+          }
         }
       }
 #pragma unroll
@@ -157,11 +175,10 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvGeom g, const __n
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < kGK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      // rows are 68 floats = 17 x 16 bytes apart, so the 4-float groups are 16-byte aligned
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -256,8 +273,11 @@ extern "C" int snb_conv_generic_wgrad(const snb_conv_geom* d, const void* d_big,
   SNB_CUDA_CHECK(cudaMemsetAsync(d_dweight, 0, sizeof(float) * (size_t)g.sc * g.bc * taps, st));
   const int64_t px = (int64_t)g.n * g.sh * g.sw;
   const int tiles = ((g.sc + kGT - 1) / kGT) * ((g.bc + kGT - 1) / kGT) * taps;
-  // split K (pixels) so that a few hundred CTAs are in flight, but keep >= 256 pixels per split
-  int k_split = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * 4 / std::max(1, tiles), px / 256));
+  // split K (pixels): measured on B200 (tools/train_step_bench.py), more and shorter splits win up to ~8 CTAs per SM: the
+  // kernel is latency-bound per CTA (no double buffering), the 64 x 64 fp32 atomics per split are not the limit
+  static const int64_t min_px = [] { const char* e = std::getenv("SNB_WGRAD_MIN_PX"); return e ? (int64_t)std::atoi(e) : 256; }();
+  static const int64_t ctas_per_sm = [] { const char* e = std::getenv("SNB_WGRAD_CTAS"); return e ? (int64_t)std::atoi(e) : 4; }();
+  int k_split = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * ctas_per_sm / std::max(1, tiles), px / min_px));
   k_split = std::min(k_split, 65535 / std::max(1, taps));
   dim3 grid((unsigned)((g.sc + kGT - 1) / kGT), (unsigned)((g.bc + kGT - 1) / kGT), (unsigned)(taps * k_split));
   conv_generic_kernel<2><<<grid, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(d_big),
