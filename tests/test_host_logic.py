@@ -268,3 +268,71 @@ def test_fma_division_by_invariant_is_correctly_rounded():
         for _ in range(2):
             q = fma(fma(-b, q, a), y, q)
         assert q == a / b, (a, b)
+
+
+def _space_to_depth(x_nhwc):
+    """snb_space_to_depth2 on the host: out[n][y][x][(py*2+px)*C + c] = in[n][2y+py][2x+px][c]."""
+    n, h, w, c = x_nhwc.shape
+    return x_nhwc.reshape(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)
+
+
+def test_stride2_conv3x3_packing_is_the_strided_convolution():
+    """resnet34 down-sampling block: conv3x3(stride 2, padding 1) == the 4-tap conv (dy, dx in {-1, 0}) the kernel runs over
+    the space-to-depth tensor with pack_conv3x3_s2 weights; the 1x1/s2 shortcut == conv1x1 over the first quarter."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 8, 10, 6), generator=g)                       # NHWC
+    wt = torch.randn((5, 6, 3, 3), generator=g)
+    taps = [(ty - 1, tx - 1) for ty in range(2) for tx in range(2)]
+    got = _tap_list_conv(_space_to_depth(x), E.pack_conv3x3_s2(wt).float(), taps).permute(0, 3, 1, 2)
+    want = F.conv2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2, padding=1)
+    assert torch.allclose(got, want, atol=1e-4)
+    w1 = torch.randn((5, 6, 1, 1), generator=g)
+    got1 = _space_to_depth(x)[..., :6] @ E.pack_conv1x1(w1)[0].float().t()
+    assert torch.allclose(got1.permute(0, 3, 1, 2), F.conv2d(x.permute(0, 3, 1, 2), w1.to(torch.bfloat16).float(), stride=2), atol=1e-4)
+
+
+def test_linknet_head_and_stem_packing():
+    """conv k2 p1 (finalconv3) as 4 taps over a grid one larger than the input; the 7x7/s2 stem as a GEMM over im2col rows
+    with k = (ky*7+kx)*C + c (snb_stem7x7_rows / pack_stem7x7)."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((1, 5, 7, 4), generator=g)
+    wt = torch.randn((3, 4, 2, 2), generator=g)
+    xp = F.pad(x, (0, 0, 0, 1, 0, 1))                                   # the kernel's tile grid is (h+1) x (w+1)
+    taps = [(ky - 1, kx - 1) for ky in range(2) for kx in range(2)]
+    got = _tap_list_conv(xp, E.pack_conv2x2(wt).float(), taps).permute(0, 3, 1, 2)
+    assert torch.allclose(got, F.conv2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), padding=1), atol=1e-4)
+    img = torch.randn((2, 3, 12, 16), generator=g)
+    ws = torch.randn((6, 3, 7, 7), generator=g)
+    cols = F.unfold(img, 7, padding=3, stride=2).reshape(2, 3, 49, 6, 8).permute(0, 3, 4, 2, 1).reshape(2, 6, 8, 147)
+    rows = torch.zeros((2, 6, 8, 160))
+    rows[..., :147] = cols
+    got = rows @ E.pack_stem7x7(ws, 160)[0].float().t()
+    want = F.conv2d(img, ws.to(torch.bfloat16).float(), stride=2, padding=3).permute(0, 2, 3, 1)
+    assert torch.allclose(got, want, atol=1e-3)
+
+
+def test_scatter_packing_sums_to_the_convolution():
+    """FCDenseNet growth-rate layer as one N = 144 GEMM (csrc/conv_scatter.cu): P[p][tap*16+co] = x[p] . W[co][:, tap], then
+    out[q] = sum_tap P[q + (dy, dx)][tap] -- restated on the host with pack_conv3x3_scatter."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((1, 9, 11, 32), generator=g)
+    wt = torch.randn((16, 32, 3, 3), generator=g)
+    P = (x @ E.pack_conv3x3_scatter(wt).float().t()).reshape(1, 9, 11, 9, 16)        # [n][y][x][tap][co]
+    Pp = F.pad(P, (0, 0, 0, 0, 1, 1, 1, 1))
+    out = sum(Pp[:, ky:ky + 9, kx:kx + 11, ky * 3 + kx] for ky in range(3) for kx in range(3))
+    want = F.conv2d(x.permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out, want, atol=1e-4)
+
+
+def test_adjoint_weights_give_the_input_gradient():
+    """The training plan computes the input gradient of a stride-1 conv3x3 / conv1x1 with the FORWARD kernel on adjoint
+    weights (taps flipped, Cin / Cout swapped): check the transform against torch autograd."""
+    g = torch.Generator().manual_seed(6)
+    for k in (3, 1):
+        x = torch.randn((2, 6, 7, 9), generator=g, requires_grad=True)
+        wt = torch.randn((5, 6, k, k), generator=g)
+        y = F.conv2d(x, wt, padding=k // 2)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        adj = wt.flip(2, 3).transpose(0, 1).contiguous()
+        assert torch.allclose(F.conv2d(dy, adj, padding=k // 2), x.grad, atol=1e-4)
