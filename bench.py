@@ -146,24 +146,55 @@ def cpu_baseline(n_net_tiles=4, repeats=1):
 
 
 def run_reference(args):
+    """Reference arm: the reference algorithm (oracle port) on the host cores.  One full float64 normalise + split and one
+    pyramid merge of a 5000x5000 image are timed once (they do not depend on the step); every timed step then runs UNet16
+    fp32 on `n_net` of the 169 tiles and is extrapolated x169/n_net.  n_net is chosen so that the whole --steps K --warmup W
+    run stays within SNB_REF_BUDGET_S seconds (default 150) whatever K and W the driver passes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import nets_oracle as no
     from oracle import synth
+    from oracle import tiles_oracle as to
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth.vgg_unet_state_dict("unet16", seed=0)
     image = synth.image_u8(0, IMAGE_HW, IMAGE_HW)
-    n_net = 4
+    budget = float(os.environ.get("SNB_REF_BUDGET_S", "150"))
+
+    t0 = time.perf_counter()
+    x = to.normalize_image(image)
+    slicer = to.SlicerOracle(x.shape, TILE, STEP, weight="pyramid")
+    tiles = slicer.split(x)
+    t_split = time.perf_counter() - t0
+
+    def net(n_tiles):
+        t = time.perf_counter()
+        with torch.no_grad():
+            batch = torch.from_numpy(to.to_nchw_float(tiles[:n_tiles]))
+            probs = torch.sigmoid(no.unet_vgg_forward(sd, batch, "unet16")).numpy()
+        return time.perf_counter() - t, probs
+
+    t_one, probs = net(1)                                              # also the warm-up of the ATen kernels
+    preds = [np.moveaxis(probs[0], 0, -1) for _ in range(len(tiles))]
+    t0 = time.perf_counter()
+    mask = ((slicer.merge(preds, dtype=np.float32) > 0.5) * 255).astype(np.uint8)
+    t_merge = time.perf_counter() - t0
+    assert mask.shape == (IMAGE_HW, IMAGE_HW, 1)
+    n_steps = max(1, args.steps + args.warmup)
+    n_net = int(max(1, min(4, (budget - t_split - t_merge) / (n_steps * max(t_one, 1e-3)))))
     for _ in range(args.warmup):
-        cpu_reference_step(sd, image, 2)
-    secs = [cpu_reference_step(sd, image, n_net) for _ in range(args.steps)]
+        net(n_net)
+    secs = []
+    for _ in range(args.steps):
+        t_net, _ = net(n_net)
+        secs.append(t_split + t_net * len(tiles) / n_net + t_merge)
     sec = sum(secs) / len(secs)
     value = MPX_PER_IMAGE / sec
-    sample = ("per step: full float64 normalise+split and pyramid merge of one 5000x5000 image, UNet16 fp32 on %d of "
-              "169 tiles extrapolated x169/%d (oracle port of lib/tiles.py + lib/models/unet16.py; the reference "
-              "is Python and cannot travel to the GPU box)" % (n_net, n_net))
+    sample = ("full float64 normalise+split (%.1f s) and pyramid merge (%.1f s) of one 5000x5000 image timed once; per step "
+              "UNet16 fp32 on %d of 169 tiles extrapolated x169/%d (oracle port of lib/tiles.py + lib/models/unet16.py; the "
+              "reference is Python and cannot travel to the GPU box)" % (t_split, t_merge, n_net, n_net))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
