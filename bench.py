@@ -133,7 +133,7 @@ def cpu_reference_step(sd, image, n_net_tiles):
 
 
 def cpu_baseline(n_net_tiles=4, repeats=1):
-    from oracle import synth
+    from snb_b200 import synth
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -154,7 +154,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import nets_oracle as no
-    from oracle import synth
+    from snb_b200 import synth
     from oracle import tiles_oracle as to
 
     cores = os.cpu_count() or 1
@@ -211,7 +211,7 @@ def run_cuda(args):
     import torch.distributed as dist
 
     import snb_b200  # noqa: F401
-    from oracle import synth
+    from snb_b200 import synth
     from snb_b200 import dist as sdist
     from snb_b200 import inria_submit as sub
     from snb_b200.engine import ConvOp
@@ -388,7 +388,7 @@ def run_tile_sharded(args, model, tile, step, default_batch, dev, rank, world, l
     NCCL all-gather of the float32 probability tiles, every rank merges, counts all-reduce is not needed."""
     import torch.distributed as dist
 
-    from oracle import synth
+    from snb_b200 import synth
     from snb_b200 import inria_submit as sub
     from snb_b200.lib import metrics
 

@@ -6,7 +6,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import snb_b200  # noqa: E402,F401
-from oracle import synth  # noqa: E402
+from snb_b200 import synth  # noqa: E402
 from snb_b200 import _native as N  # noqa: E402
 from snb_b200 import inria_submit as sub  # noqa: E402
 from snb_b200.lib import metrics  # noqa: E402

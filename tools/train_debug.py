@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import snb_b200  # noqa: E402,F401
 from oracle import nets_oracle as no  # noqa: E402
-from oracle import synth  # noqa: E402
+from snb_b200 import synth  # noqa: E402
 from snb_b200.lib import losses  # noqa: E402
 from snb_b200.lib.models import LinkNet34  # noqa: E402
 
