@@ -180,16 +180,37 @@ __global__ void __launch_bounds__(256) pr_hist_kernel(const float* __restrict__ 
   __syncthreads();
   uint32_t* my = hist + (threadIdx.x >> 5) * 2 * bins;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float p = sigmoid_f32(__ldg(logits + i));
-    const int truth = ((int)load_target<DT>(targets, i)) != 0;  // astype(int32) then k*true with k=2
-    // idx = #{k : p > thr[k]} for ascending thresholds (upper-bound style binary search)
-    int lo = 0, hi = n_thr;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (p > s_thr[mid]) lo = mid + 1; else hi = mid;
+  // idx = #{k : p > thr[k]} for ascending thresholds.  The reference's thresholds are (nearly) uniform (arange(0, 1, 1/127),
+  // lib/train_utils.py:97), so a linear guess lands within one bin and two short fix-up loops make it exact for ANY
+  // ascending table (they replace a 7-step binary search per element; the result is the same integer)
+  const float t0 = s_thr[0];
+  const float span = s_thr[n_thr - 1] - t0;
+  const float gscale = span > 0.f ? (float)(n_thr - 1) / span : 0.f;
+  auto bin_of = [&](float p) {
+    int lo = min(n_thr, max(0, __float2int_rd((p - t0) * gscale) + 1));   // NaN -> 0
+    while (lo < n_thr && p > s_thr[lo]) ++lo;
+    while (lo > 0 && !(p > s_thr[lo - 1])) --lo;
+    return lo;
+  };
+  const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(targets) & 15) == 0;
+  if (vec) {
+    for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += stride) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(logits) + i4);
+      float tv[4];
+      load_target4<DT>(targets, i4, tv);
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int truth = ((int)tv[e]) != 0;                         // astype(int32) then k*true with k=2
+        atomicAdd(&my[truth * bins + bin_of(sigmoid_f32(xs[e]))], 1u);
+      }
     }
-    atomicAdd(&my[truth * bins + lo], 1u);
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float p = sigmoid_f32(__ldg(logits + i));
+      const int truth = ((int)load_target<DT>(targets, i)) != 0;
+      atomicAdd(&my[truth * bins + bin_of(p)], 1u);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * bins; i += blockDim.x) {
