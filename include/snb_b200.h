@@ -23,6 +23,11 @@
  *                      PixelAccuracy partial sums and integer counts           lib/metrics.py:9-40
  *   snb_pr_curve_*     PRCurveMeter.update                                     lib/train_utils.py:109-125
  *   snb_abn_*          the `inplace_abn` backend calls of InPlaceABN            lib/modules/abn/functions.py:62-122
+ *   snb_conv_scatter_* Conv2d(cin, 16, 3, padding=1) of FCDenseNet's DenseLayer  lib/models/tiramisu.py:9-19
+ *   snb_bn_train_nhwc, nn.BatchNorm2d / InPlaceABN in train() mode inside         lib/models/linknet.py:16-31,65-90
+ *   snb_bn_backward_*  LinkNet34 (batch statistics; their backward)             (torchvision BasicBlock bn1 / bn2)
+ *   snb_conv_generic_* autograd of nn.Conv2d / nn.ConvTranspose2d (input and     torch_train.py:186-189
+ *                      weight gradients), snb_maxpool3x3s2_backward, snb_loss_grad
  *
  * Conventions: every pointer named `d_*` is a DEVICE pointer owned by the caller; sizes are int64_t; `stream`
  * is a cudaStream_t passed as void* (0 = legacy default stream).  All entry points enqueue work on `stream`
