@@ -158,26 +158,45 @@ __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, c
   const int64_t tile = tile_begin + t;
   const int64_t cy = (tile / g.tiles_x) * g.step, cx = (tile % g.tiles_x) * g.step;
   for (int i = threadIdx.x; i < channels * 256; i += blockDim.x) s_lut[i] = lut[i];
-  __syncthreads();
+  // Source byte offset of neighbourhood pixel (hy, hx) = s_row[hy] + s_col[hx]: in every D4 view the source row depends on
+  // only one of the two view coordinates and the source column on the other, so the view map, the reflect-101 border
+  // and the 64-bit index arithmetic are evaluated once per row / column of the strip instead of once per pixel.
+  // -1 = outside the tile (the convolution's zero padding).
   const int PW = T + 2;
-  for (int i = threadIdx.x; i < (kPatchRY + 2) * PW; i += blockDim.x) {
-    const int hy = i / PW, hx = i - hy * PW;
-    const int vy = y0 + hy - 1, vx = hx - 1;     // position in the (D4-transformed) tile
-    float f[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vy >= 0 && vy < T && vx >= 0 && vx < T) {
+  __shared__ int s_row[kPatchRY + 2];
+  int* s_col = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_raw) + (size_t)(kPatchRY + 2) * PW * (F32 ? 16 : 8));   // [PW]
+  const bool transposed = (tta & 1) != 0;                          // views 1, 3, 5, 7 swap the roles of the coordinates
+  for (int i = threadIdx.x; i < kPatchRY + 2 + PW; i += blockDim.x) {
+    const bool is_row = i < kPatchRY + 2;
+    const int v = is_row ? y0 + i - 1 : i - (kPatchRY + 2) - 1;    // view coordinate vy (rows) or vx (columns)
+    int off = -1;
+    if (v >= 0 && v < T) {
       int si, sj;
-      d4_src(tta, vy, vx, T, si, sj);
-      const int64_t sy = reflect101(cy + si - g.margin_top, g.image_h);
-      const int64_t sx = reflect101(cx + sj - g.margin_left, g.image_w);
-      const uint8_t* px = src + (sy * g.image_w + sx) * channels;
-#pragma unroll
-      for (int c = 0; c < channels; ++c) f[c] = s_lut[c * 256 + __ldg(px + c)];
+      d4_src(tta, is_row ? v : 0, is_row ? 0 : v, T, si, sj);      // only the coordinate that depends on v is used below
+      // rows of a plain view / columns of a transposed view select the source ROW, the others the source COLUMN
+      if (is_row != transposed) off = (int)(reflect101(cy + si - g.margin_top, g.image_h) * g.image_w * channels);
+      else off = (int)(reflect101(cx + sj - g.margin_left, g.image_w) * channels);
     }
-    if (F32) {
-      s_pf[i] = make_float4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
-    } else {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
-      s_px[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    if (is_row) s_row[i] = off; else s_col[i - (kPatchRY + 2)] = off;
+  }
+  __syncthreads();
+  for (int hy = 0; hy < kPatchRY + 2; ++hy) {
+    const int rp = s_row[hy];
+    for (int hx = threadIdx.x; hx < PW; hx += blockDim.x) {
+      const int cp = s_col[hx];
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if ((rp | cp) >= 0) {
+        const uint8_t* px = src + rp + cp;
+#pragma unroll
+        for (int c = 0; c < channels; ++c) f[c] = s_lut[c * 256 + __ldg(px + c)];
+      }
+      const int i = hy * PW + hx;
+      if (F32) {
+        s_pf[i] = make_float4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+        s_px[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
     }
   }
   __syncthreads();
@@ -1046,7 +1065,8 @@ extern "C" int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int6
     if (channels > 3) return fail(SNB_E_INVALID, "PATCH32 holds 9 taps x <=3 channels");
     if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(SNB_E_INVALID, "PATCH32 destination must be 16-byte aligned");
     const int strips = (int)((T + kPatchRY - 1) / kPatchRY);
-    const size_t smem = (size_t)(kPatchRY + 2) * (T + 2) * (f32 ? sizeof(float4) : sizeof(uint2));
+    const size_t smem = (size_t)(kPatchRY + 2) * (T + 2) * (f32 ? sizeof(float4) : sizeof(uint2)) + (size_t)(T + 2) * sizeof(int);
+    if (s->g.image_h * s->g.image_w * channels > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "image too large for 32-bit source offsets");
     if (smem > 200 * 1024) return fail(SNB_E_UNSUPPORTED, "tile size %lld too large for the PATCH32 split", (long long)T);
     if (tile_count * strips > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "too many strips");
 #define SNB_SPLIT_P32(C, F)                                                                                       \
