@@ -294,31 +294,44 @@ SNB_API int snb_nhwc_bf16_to_nchw_f32(const void* d_in, int64_t n, int64_t h, in
                               int64_t in_cstride, float* d_out, void* stream);
 
 /* ----------------------------------------------------------------------------------------- loss / metrics */
-/* One pass over logits/targets (lib/losses.py:36-53, lib/metrics.py:13-36):
- *   p = sigmoid(x); z = logsigmoid(x); bce_i = max(z,0) - z*t + log1p(exp(-|z|))
- *   d_sums[0..3]   = sum bce_i, sum p*t, sum p, sum t                       (double)
- *   d_counts[0..3] = tp, fp, fn, tn at p > 0.5 (float32 compare)            (int64)
- * targets of dtype SNB_DT_I64 / SNB_DT_U8 / SNB_DT_F32.  The outputs are zeroed by the call. */
-SNB_API int snb_loss_iou_reduce(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
-                        double* d_sums, int64_t* d_counts, void* stream);
+/* Every reduction below is ONE kernel launch: blocks park their partials in `d_workspace`, the last block to finish adds
+ * them in a fixed order (deterministic for a given size) and restores the workspace.  The workspace is
+ * snb_reduce_workspace_bytes() bytes, 64-byte aligned, zeroed ONCE by the caller and then only touched by these calls
+ * ("zero at rest"); calls that may overlap on different streams need different workspaces. */
+SNB_API int64_t snb_reduce_workspace_bytes(void);
 
-/* Gradient of the fused loss with respect to the logits (what autograd computes through lib/losses.py:31-75):
- * grad[i] = grad_out * d/dx_i [ c_bce * sum_i BCE_i + c_jac * SmoothJaccard ], with d_sums = the float64[4] output of
- * snb_loss_iou_reduce on the same tensors (no host round trip) and d_grad_out a device scalar (NULL = 1).
+/* One pass over logits/targets (lib/losses.py:18-101, lib/metrics.py:13-36):
+ *   p = sigmoid(x); z = logsigmoid(x); bce_i = max(z,0) - z*t + log1p(exp(-|z|))   (the reference's double squash)
+ *   d_sums[0..4]   = sum bce_i, sum p*t, sum p, sum t, sum focal_i                  (double[5])
+ *                    focal_i = (1 - exp(-bce_i))^gamma * bce_i (FocalLossBinary, lib/losses.py:78-101) when
+ *                    focal_gamma >= 0, else d_sums[4] = 0
+ *   d_counts[0..3] = tp, fp, fn, tn at p > 0.5 (float32 compare)                    (int64[4])
+ *   d_elem_bce     = optional float[n]: bce_i per element (BCEWithSigmoidLoss(reduce=False), lib/losses.py:46-53)
+ * targets of dtype SNB_DT_I64 / SNB_DT_U8 / SNB_DT_F32.  Outputs are overwritten. */
+SNB_API int snb_loss_iou_reduce(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
+                        float focal_gamma, float* d_elem_bce, double* d_sums, int64_t* d_counts, void* d_workspace,
+                        void* stream);
+
+/* Gradient of a fused loss with respect to the logits (what autograd computes through lib/losses.py:18-101):
+ *   grad[i] = g * d/dx_i [ c_bce * sum_i bce_i + c_focal * sum_i focal_i + c_jac * (1 - A / D) ],
+ *   A = sum p*t + smooth_num, D = sum p + sum t - sum p*t + smooth_den,
+ * with d_sums = the double[5] output of snb_loss_iou_reduce on the same tensors (no host round trip) and g = the
+ * upstream gradient on the device: NULL = 1, a scalar, or one float per element when grad_out_per_element != 0.
  * bce_jaccard: c_bce = bce_weight / ((bce_weight + jaccard_weight) * n), c_jac = jaccard_weight / (bce_weight +
- * jaccard_weight), smooth = 100. */
+ * jaccard_weight), smooth_num = smooth_den = 100; JaccardLoss: smooth_num = 0, smooth_den = 1e-7. */
 SNB_API int snb_loss_grad(const float* d_logits, const void* d_targets, int target_dtype, int64_t n, const double* d_sums,
-                  const float* d_grad_out, float c_bce, float c_jac, float smooth, float* d_grad_logits, void* stream);
+                  const float* d_grad_out, int grad_out_per_element, float c_bce, float c_focal, float focal_gamma,
+                  float c_jac, float smooth_num, float smooth_den, float* d_grad_logits, void* stream);
 
 /* Same integer counts from probabilities already on the device (mask parity path): pred = prob > thr. */
 SNB_API int snb_confusion_counts(const float* d_probs, const void* d_targets, int target_dtype, int64_t n, float thr,
-                         int64_t* d_counts, void* stream);
+                         int64_t* d_counts, void* d_workspace, void* stream);
 
 /* PRCurveMeter.update (lib/train_utils.py:109-125): for every threshold k (float32, ascending),
  * pred = sigmoid(x) > thr[k]; adds tp/tn/fp/fn counts into uint64 arrays of length n_thr (accumulating). */
 SNB_API int snb_pr_curve_update(const float* d_logits, const void* d_targets, int target_dtype, int64_t n,
                         const float* d_thresholds, int64_t n_thr, uint64_t* d_tp, uint64_t* d_tn,
-                        uint64_t* d_fp, uint64_t* d_fn, void* stream);
+                        uint64_t* d_fp, uint64_t* d_fn, void* d_workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -223,6 +223,43 @@ def loss_vectors():
     return out
 
 
+def loss_extra_vectors():
+    """JaccardLoss, FocalLossBinary and BCEWithSigmoidLoss(reduce=False) of the reference (lib/losses.py:18-28,46-53,
+    78-101): values and gradients with respect to the logits -> tests/golden/loss_extra.npz."""
+    out = {}
+    for seed, shape in [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))]:
+        logits, targets = synth.logits_targets(seed, shape)
+        sample = (lambda a: a if a.size < 5000 else a[::97].copy())
+
+        def run(tag, mod, upstream=None):
+            x = logits.clone().requires_grad_(True)
+            y = mod(x, targets)
+            if upstream is None:
+                out["seed%d_%s" % (seed, tag)] = np.float64(float(y))
+                (y * 3.0).backward()
+            else:
+                out["seed%d_%s" % (seed, tag)] = sample(y.detach().numpy().reshape(-1))
+                (y * upstream).sum().backward()
+            out["seed%d_%s_grad" % (seed, tag)] = sample(x.grad.numpy().reshape(-1))
+
+        run("jaccard", ref_losses.JaccardLoss())
+        for tag, gamma, avg in (("focal_g2_mean", 2, True), ("focal_g1.5_sum", 1.5, False), ("focal_g0_mean", 0, True)):
+            m = ref_losses.FocalLossBinary.__new__(ref_losses.FocalLossBinary)
+            torch.nn.Module.__init__(m)
+            m.gamma, m.size_average, m.reduce = gamma, avg, True
+            run(tag, m)
+        bce = ref_losses.BCEWithSigmoidLoss.__new__(ref_losses.BCEWithSigmoidLoss)
+        torch.nn.Module.__init__(bce)
+        bce.size_average, bce.reduce = True, False
+        up = torch.from_numpy(np.random.RandomState(40 + seed).standard_normal(shape).astype(np.float32))
+        # (the upstream gradient is regenerated from RandomState(40 + seed) by the tests)
+        run("bce_elem", bce, upstream=up)
+        bce.size_average = False
+        bce.reduce = True
+        run("bce_sum", bce)
+    np.savez_compressed(os.path.join(OUT, "loss_extra.npz"), **out)
+
+
 def model_vectors():
     d = {}
     for arch, cls in (("unet16", UNet16), ("unet11", UNet11)):
@@ -401,6 +438,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1:                 # regenerate single files: python oracle/make_golden.py loss_extra_vectors ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        return
     kats = dict(slicer=slicer_kats(), pyramid=weight_vectors(), loss=loss_vectors(), zf_unet_cfg1=zf_unet_vectors(), fcdensenet67=fcdensenet_vectors(), linknet34=linknet34_vectors(), inplace_abn=inplace_abn_vectors(),
                 torch_version=torch.__version__, numpy_version=np.__version__)
     split_merge_vectors()
@@ -408,6 +449,7 @@ def main():
     tta_vectors()
     model_vectors()
     predict_tiled_vector()
+    loss_extra_vectors()
     with open(os.path.join(OUT, "kats.json"), "w") as fh:
         json.dump(kats, fh, indent=1)
     for f in sorted(os.listdir(OUT)):

@@ -316,6 +316,27 @@ def smooth_jaccard(logits, targets, smooth=100):
     return 1 - (inter + smooth) / (union - inter + smooth)
 
 
+def bce_elements(logits, targets):
+    """lib/losses.py:46-53 with reduce=False: the per-element loss tensor."""
+    return F.binary_cross_entropy_with_logits(F.logsigmoid(logits), targets.float(), reduction='none')
+
+
+def jaccard_loss(logits, targets):
+    """lib/losses.py:18-28."""
+    p = torch.sigmoid(logits)
+    inter = torch.sum(p * targets)
+    union = torch.sum(p) + torch.sum(targets)
+    return 1 - inter / (union - inter + 1e-7)
+
+
+def focal_loss_binary(logits, targets, gamma=2, size_average=True):
+    """lib/losses.py:78-101: logpt = -BCE-with-logits(logsigmoid(x), t); loss = -(1 - exp(logpt))^gamma * logpt."""
+    logpt = -bce_elements(logits, targets)
+    pt = torch.exp(logpt)
+    loss = -((1 - pt).pow(gamma)) * logpt
+    return loss.mean() if size_average else loss.sum()
+
+
 def bce_jaccard(logits, targets, bce_weight=1, jaccard_weight=0.5):
     return (bce_with_sigmoid(logits, targets) * bce_weight + smooth_jaccard(logits, targets) * jaccard_weight) / (
         bce_weight + jaccard_weight)

@@ -111,10 +111,12 @@ SIGNATURES = {
     "snb_ew_nhwc": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, ctypes.c_float, c_vp]),
     "snb_bn_relu_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
-    "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
-    "snb_loss_grad": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp]),
-    "snb_confusion_counts": (c_int, [c_vp, c_vp, c_int, c_i64, ctypes.c_float, c_vp, c_vp]),
-    "snb_pr_curve_update": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "snb_reduce_workspace_bytes": (c_i64, []),
+    "snb_loss_iou_reduce": (c_int, [c_vp, c_vp, c_int, c_i64, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "snb_loss_grad": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                              ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp]),
+    "snb_confusion_counts": (c_int, [c_vp, c_vp, c_int, c_i64, ctypes.c_float, c_vp, c_vp, c_vp]),
+    "snb_pr_curve_update": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None
@@ -168,6 +170,23 @@ def stream_ptr():
     import torch
 
     return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+_reduce_ws = {}
+
+
+def reduce_workspace():
+    """The "zero at rest" workspace of the single-launch reductions (include/snb_b200.h) for the current device and
+    stream: allocated and zeroed once, then only touched by the library."""
+    import torch
+
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    ws = _reduce_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib().snb_reduce_workspace_bytes()), dtype=torch.uint8, device=torch.device("cuda", dev))
+        _reduce_ws[key] = ws
+    return ws
 
 
 def ptr(t):

@@ -59,10 +59,13 @@ __device__ __forceinline__ void act_bwd(float& z, float& dz, int act, float slop
   }
 }
 
-// grid = (C, slabs): CTA (c, s) reduces images n = s, s + slabs, ... of channel c.  sums[2c], sums[2c+1] += (sum x, sum x^2)
+// grid = (C, slabs): CTA (c, s) reduces images n = s, s + slabs, ... of channel c.
+// sums[2c], sums[2c+1] += (sum (x - p), sum (x - p)^2) with the pivot p = the channel's first value: the variance
+// E[(x-p)^2] - E[x-p]^2 then keeps its bits when |mean| >> std (E[x^2] - E[x]^2 cancels catastrophically there).
 __global__ void __launch_bounds__(kAbnThreads) abn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t HW,
                                                                  double* __restrict__ sums) {
   const int c = blockIdx.x;
+  const float pv = __ldg(x + (int64_t)c * HW);
   double s = 0.0, q = 0.0;
   for (int n = blockIdx.y; n < N; n += gridDim.y) {
     const float* p = x + ((int64_t)n * C + c) * HW;
@@ -71,7 +74,8 @@ __global__ void __launch_bounds__(kAbnThreads) abn_stats_kernel(const float* __r
       float fs = 0.f, fq = 0.f;   // float partials per thread over <= HW/1024 elements, folded into double below
       int cnt = 0;
       for (int64_t i = threadIdx.x; i < HW / 4; i += kAbnThreads) {
-        const float4 v = __ldg(p4 + i);
+        float4 v = __ldg(p4 + i);
+        v.x -= pv; v.y -= pv; v.z -= pv; v.w -= pv;
         fs += (v.x + v.y) + (v.z + v.w);
         fq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         if (++cnt == 16) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(kAbnThreads) abn_stats_kernel(const float* __r
       q += fq;
     } else {
       for (int64_t i = threadIdx.x; i < HW; i += kAbnThreads) {
-        const double v = __ldg(p + i);
+        const double v = (double)__ldg(p + i) - (double)pv;
         s += v;
         q += v * v;
       }
@@ -94,14 +98,15 @@ __global__ void __launch_bounds__(kAbnThreads) abn_stats_kernel(const float* __r
 }
 
 // mean / biased var from the sums; running stats update of functions.py:84-85 (unbiased variance, momentum)
-__global__ void abn_finalize_stats_kernel(const double* __restrict__ sums, int C, double count, float momentum,
-                                          float* __restrict__ mean, float* __restrict__ var,
+__global__ void abn_finalize_stats_kernel(const double* __restrict__ sums, const float* __restrict__ x, int64_t HW, int C,
+                                          double count, float momentum, float* __restrict__ mean, float* __restrict__ var,
                                           float* __restrict__ running_mean, float* __restrict__ running_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sums[2 * c] / count;
-  double v = sums[2 * c + 1] / count - m * m;
+  const double ms = sums[2 * c] / count;                       // mean of (x - pivot)
+  double v = sums[2 * c + 1] / count - ms * ms;
   v = v < 0.0 ? 0.0 : v;
+  const double m = ms + (double)__ldg(x + (int64_t)c * HW);
   mean[c] = (float)m;
   var[c] = (float)v;
   if (running_mean) running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * (float)m;
@@ -206,22 +211,34 @@ __global__ void abn_param_grads_kernel(const double* __restrict__ sums, const fl
 // float atomics across the pixel lanes of a CTA, then one float64 atomic per channel and CTA.
 constexpr int kBnMaxCV = 256;   // <= 2048 channels
 
+// PIVOT: accumulate (x - p), (x - p)^2 with p = the channel's value at pixel 0 (see abn_stats_kernel)
+template <bool PIVOT>
 __global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restrict__ in, int CV, int in_sv, int64_t pixels,
                                                             double* __restrict__ sums) {
   __shared__ float sh[kBnMaxCV * 16];
   for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
-  float s[8], q[8];
+  float s[8], q[8], pvt[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = pvt[e] = 0.f;
+  if (PIVOT && pl < ppb) {
+    const uint4 u = __ldg(in + v);
+    const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __bfloat1622float2(pv[e]);
+      pvt[2 * e] = x.x; pvt[2 * e + 1] = x.y;
+    }
+  }
   if (pl < ppb) {
     for (int64_t pix = blockIdx.x * (int64_t)ppb + pl; pix < pixels; pix += (int64_t)gridDim.x * ppb) {
       const uint4 u = __ldg(in + pix * in_sv + v);
       const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 x = __bfloat1622float2(pv[e]);
+        float2 x = __bfloat1622float2(pv[e]);
+        x.x -= pvt[2 * e]; x.y -= pvt[2 * e + 1];
         s[2 * e] += x.x; s[2 * e + 1] += x.y;
         q[2 * e] += x.x * x.x; q[2 * e + 1] += x.y * x.y;
       }
@@ -238,16 +255,18 @@ __global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restr
 
 // mean / biased variance -> fused scale and shift of the normalisation; running statistics as nn.BatchNorm2d and
 // functions.py:84-85 update them (momentum, unbiased variance).  abn != 0: gamma = |weight| + eps (InPlaceABN backend)
-__global__ void bn_finalize_nhwc_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+__global__ void bn_finalize_nhwc_kernel(const double* __restrict__ sums, const __nv_bfloat16* __restrict__ pivot, int C,
+                                        double count, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, int abn, float eps, float momentum,
                                         float* __restrict__ running_mean, float* __restrict__ running_var,
                                         float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                         float* __restrict__ var_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sums[2 * c] / count;
-  double v = sums[2 * c + 1] / count - m * m;
+  const double ms = sums[2 * c] / count;                       // mean of (x - pivot), pivot = pixel 0
+  double v = sums[2 * c + 1] / count - ms * ms;
   v = v < 0.0 ? 0.0 : v;
+  const double m = ms + (double)__bfloat162float(pivot[c]);
   const float g = gamma ? (abn ? fabsf(gamma[c]) + eps : gamma[c]) : 1.f;
   const float sc = g * rsqrtf((float)v + eps);
   scale[c] = sc;
@@ -445,8 +464,9 @@ extern "C" int snb_abn_forward(float* d_x, int64_t n, int64_t c, int64_t hw, con
     if (n * hw < 2) return fail(SNB_E_INVALID, "training mode needs more than one value per channel");
     SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * c, st));
     abn_stats_kernel<<<stats_grid(n, c), kAbnThreads, 0, st>>>(d_x, (int)n, (int)c, hw, d_workspace);
-    abn_finalize_stats_kernel<<<(unsigned)((c + 127) / 128), 128, 0, st>>>(d_workspace, (int)c, (double)(n * hw), momentum,
-                                                                         d_mean, d_var, d_running_mean, d_running_var);
+    abn_finalize_stats_kernel<<<(unsigned)((c + 127) / 128), 128, 0, st>>>(d_workspace, d_x, hw, (int)c, (double)(n * hw),
+                                                                         momentum, d_mean, d_var, d_running_mean,
+                                                                         d_running_var);
     mean = d_mean;
     var = d_var;
   }
@@ -503,8 +523,9 @@ extern "C" int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t chann
   const int64_t want = (pixels + ppb * 4 - 1) / (ppb * 4);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
   SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
-  bn_stats_nhwc_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
-  bn_finalize_nhwc_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, (int)channels, (double)pixels, d_gamma,
+  bn_stats_nhwc_kernel<true><<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
+  bn_finalize_nhwc_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, static_cast<const __nv_bfloat16*>(d_in),
+                                                                            (int)channels, (double)pixels, d_gamma,
                                                                             d_beta, abn, eps, momentum, d_running_mean,
                                                                             d_running_var, d_scale, d_shift, d_mean, d_var);
   const int64_t total = pixels * cv;
@@ -575,7 +596,7 @@ extern "C" int snb_channel_sum_nhwc(const void* d_in, int64_t pixels, int64_t ch
   int threads, grid;
   const int cv = bn_launch_shape(pixels, channels, &threads, &grid);
   SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
-  bn_stats_nhwc_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
+  bn_stats_nhwc_kernel<false><<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
   channel_sum_finalize_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, (int)channels, d_out);
   SNB_LAUNCH_CHECK();
   return SNB_OK;

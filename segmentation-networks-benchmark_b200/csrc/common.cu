@@ -16,14 +16,27 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// SM count of the CURRENT device (cached per device ordinal: a process may drive several GPUs)
 int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  constexpr int kMaxDev = 64;
+  static int cached[kMaxDev] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev >= 0 && dev < kMaxDev && cached[dev] > 0) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  cached = n;
+  if (dev >= 0 && dev < kMaxDev) cached[dev] = n;
   return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices a kernel was configured on
+bool configured_on_this_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  return (*mask >> dev) & 1ull;
+}
+void mark_configured_on_this_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) *mask |= 1ull << dev;
 }
 
 }  // namespace snb

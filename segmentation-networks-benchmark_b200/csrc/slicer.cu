@@ -883,12 +883,12 @@ static bool launch_merge_ring(const SlicerGeom& g, const float* tiles, const dou
   int n_stages = (int)std::min<int64_t>(8, (227 * 1024 - 128) / stage);
   if (const char* e = std::getenv("SNB_MERGE_STAGES")) n_stages = std::min(n_stages, std::max(1, std::atoi(e)));
   if (n_stages < 2) return false;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;     // per device ordinal (the attribute is per device)
+  if (!configured_on_this_device(&configured)) {
     if (cudaFuncSetAttribute(merge_f32c1_ring_kernel<PX, HAS_OUT, HAS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess)
       return false;
-    configured = true;
+    mark_configured_on_this_device(&configured);
   }
   const int grid = (int)std::min<int64_t>(sm_count(), g.image_h);
   merge_f32c1_ring_kernel<PX, HAS_OUT, HAS_MASK><<<grid, kMergeConsumers + 32, 128 + (size_t)n_stages * stage, st>>>(
@@ -912,12 +912,12 @@ static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const d
   xs = (periods + kp - 1) / kp;
   const size_t smem = 16 + 2 * (size_t)(std::min(kp + 1, g.tiles_x) * g.tile * 4);
   if (smem > 227 * 1024 || g.image_h * xs > INT32_MAX) return false;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;     // per device ordinal
+  if (!configured_on_this_device(&configured)) {
     if (cudaFuncSetAttribute(merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess)
       return false;
-    configured = true;
+    mark_configured_on_this_device(&configured);
   }
   merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK><<<(unsigned)(g.image_h * xs), threads, smem, st>>>(
       g, tiles, weight, out, mask, thr, (int)xs, (int)kp);

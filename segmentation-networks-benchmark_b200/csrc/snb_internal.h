@@ -39,6 +39,8 @@ struct SlicerGeom {
 };
 
 int sm_count();
+bool configured_on_this_device(unsigned long long* mask);
+void mark_configured_on_this_device(unsigned long long* mask);
 
 }  // namespace snb
 

@@ -1,8 +1,10 @@
-"""Losses of the hot path (reference lib/losses.py:31-75) on top of ONE fused device reduction.
+"""Losses of the hot path (reference lib/losses.py:18-101, binary classes) on top of ONE fused device reduction.
 
-`snb_loss_iou_reduce` returns {sum bce, sum p*t, sum p, sum t} (+ integer tp/fp/fn/tn) in a single pass over
-logits and targets; the classes below turn those partial sums into the reference's scalars with the same
-formulas, including its quirk of feeding logsigmoid(x) into BCE-with-logits (lib/losses.py:51-53).
+`snb_loss_iou_reduce` returns {sum bce, sum p*t, sum p, sum t, sum focal} (+ integer tp/fp/fn/tn) from ONE kernel launch
+over logits and targets; the classes below (JaccardLoss, SmoothJaccardLoss, BCEWithSigmoidLoss,
+BCEWithLogitsLossAndSmoothJaccard, FocalLossBinary: the binary losses of lib/losses.py:18-101) turn those partial sums
+into the reference's scalars with the same formulas, including its quirk of feeding logsigmoid(x) into BCE-with-logits
+(lib/losses.py:51-53).
 When the logits require grad the scalar carries autograd history: the backward is one elementwise kernel
 (`snb_loss_grad`) that rebuilds d loss / d logits from the same four sums, so `loss.backward()` works as in
 torch_train.py:186-189 without any host synchronisation.
@@ -15,8 +17,7 @@ from .. import _native as N
 _TARGET_DT = {torch.int64: N.DT_I64, torch.uint8: N.DT_U8, torch.float32: N.DT_F32, torch.bool: N.DT_U8}
 
 
-def fused_sums(outputs, targets):
-    """-> (sums float64[4] = [sum bce, sum p*t, sum p, sum t], counts int64[4] = [tp, fp, fn, tn]) on the device."""
+def _prep(outputs, targets):
     N.require_cuda()
     if not outputs.is_cuda or not targets.is_cuda:
         raise RuntimeError("loss/metric reductions run on CUDA tensors only (no CPU fallback)")
@@ -29,44 +30,101 @@ def fused_sums(outputs, targets):
     t = targets.detach()
     if t.dtype not in _TARGET_DT:
         t = t.float()
-    t = t.contiguous()
-    sums = torch.empty(4, dtype=torch.float64, device=x.device)
+    return x, t.contiguous()
+
+
+def fused_sums(outputs, targets, focal_gamma=None, per_element=False):
+    """-> (sums float64[5] = [sum bce, sum p*t, sum p, sum t, sum focal], counts int64[4] = [tp, fp, fn, tn]) on the
+    device, from ONE kernel launch; with per_element=True also the float tensor of per-element BCE values."""
+    x, t = _prep(outputs, targets)
+    sums = torch.empty(5, dtype=torch.float64, device=x.device)
     counts = torch.empty(4, dtype=torch.int64, device=x.device)
-    N.check(N.lib().snb_loss_iou_reduce(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(sums),
-                                        N.ptr(counts), N.stream_ptr()))
-    return sums, counts
+    elem = torch.empty_like(x) if per_element else None
+    with torch.cuda.device(x.device):
+        N.check(N.lib().snb_loss_iou_reduce(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(),
+                                            -1.0 if focal_gamma is None else float(focal_gamma), N.ptr(elem), N.ptr(sums),
+                                            N.ptr(counts), N.ptr(N.reduce_workspace()), N.stream_ptr()))
+    return (sums, counts, elem) if per_element else (sums, counts)
+
+
+def _loss_grad(outputs, targets, sums, grad_out, per_element, c_bce, c_focal, gamma, c_jac, smooth_num, smooth_den):
+    x, t = _prep(outputs, targets)
+    grad = torch.empty_like(x)
+    g = grad_out.detach().float().contiguous()
+    with torch.cuda.device(x.device):
+        N.check(N.lib().snb_loss_grad(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(sums), N.ptr(g),
+                                      1 if per_element else 0, c_bce, c_focal, gamma, c_jac, smooth_num, smooth_den,
+                                      N.ptr(grad), N.stream_ptr()))
+    return grad.view_as(outputs).to(outputs.dtype)
 
 
 class _FusedLoss(torch.autograd.Function):
-    """c_bce * sum_i BCE_i + c_jac * SmoothJaccard(smooth) as one reduction (forward) and one elementwise kernel
-    (backward); covers SmoothJaccardLoss, BCEWithSigmoidLoss and their weighted combination."""
+    """c_bce * sum_i BCE_i + c_focal * sum_i focal_i + c_jac * (1 - (I + s_num) / (U - I + s_den)) as one reduction
+    (forward) and one elementwise kernel (backward); covers JaccardLoss, SmoothJaccardLoss, BCEWithSigmoidLoss,
+    FocalLossBinary and the weighted BCE + Jaccard combination."""
 
     @staticmethod
-    def forward(ctx, outputs, targets, c_bce, c_jac, smooth):
-        sums, _ = fused_sums(outputs, targets)
+    def forward(ctx, outputs, targets, c_bce, c_focal, gamma, c_jac, smooth_num, smooth_den):
+        sums, _ = fused_sums(outputs, targets, focal_gamma=gamma if c_focal else None)
         ctx.save_for_backward(outputs, targets, sums)
-        ctx.coef = (float(c_bce), float(c_jac), float(smooth))
-        jac = 1 - (sums[1] + smooth) / (sums[2] + sums[3] - sums[1] + smooth)
-        return (sums[0] * c_bce).float() + jac.float() * c_jac if c_jac else (sums[0] * c_bce).float()
+        ctx.coef = (float(c_bce), float(c_focal), float(gamma), float(c_jac), float(smooth_num), float(smooth_den))
+        return _combine(sums, *ctx.coef)
 
     @staticmethod
     def backward(ctx, grad_out):
         outputs, targets, sums = ctx.saved_tensors
-        c_bce, c_jac, smooth = ctx.coef
-        x = outputs.detach().float().contiguous()
-        t = targets.detach()
-        if t.dtype not in _TARGET_DT:
-            t = t.float()
-        t = t.contiguous()
-        grad = torch.empty_like(x)
-        g = grad_out.detach().float().contiguous()
-        N.check(N.lib().snb_loss_grad(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(sums), N.ptr(g), c_bce,
-                                      c_jac, smooth, N.ptr(grad), N.stream_ptr()))
-        return grad.view_as(outputs).to(outputs.dtype), None, None, None, None
+        return (_loss_grad(outputs, targets, sums, grad_out, False, *ctx.coef),) + (None,) * 7
+
+
+def _combine(sums, c_bce, c_focal, gamma, c_jac, smooth_num, smooth_den):
+    out = None
+    if c_bce:
+        out = (sums[0] * c_bce).float()
+    if c_focal:
+        f = (sums[4] * c_focal).float()
+        out = f if out is None else out + f
+    if c_jac:
+        jac = 1 - (sums[1] + smooth_num) / (sums[2] + sums[3] - sums[1] + smooth_den)
+        j = jac.float() * c_jac
+        out = j if out is None else out + j
+    return out
+
+
+def _fused(outputs, targets, c_bce=0.0, c_focal=0.0, gamma=0.0, c_jac=0.0, smooth_num=0.0, smooth_den=0.0):
+    if _needs_grad(outputs):
+        return _FusedLoss.apply(outputs, targets, c_bce, c_focal, gamma, c_jac, smooth_num, smooth_den)
+    sums, _ = fused_sums(outputs, targets, focal_gamma=gamma if c_focal else None)
+    return _combine(sums, c_bce, c_focal, gamma, c_jac, smooth_num, smooth_den)
+
+
+class _ElementBCE(torch.autograd.Function):
+    """BCEWithSigmoidLoss(reduce=False): the per-element loss tensor; backward scales the element gradient by the
+    per-element upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, outputs, targets):
+        sums, _, elem = fused_sums(outputs, targets, per_element=True)
+        ctx.save_for_backward(outputs, targets, sums)
+        return elem.view_as(outputs)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        outputs, targets, sums = ctx.saved_tensors
+        return _loss_grad(outputs, targets, sums, grad_out, True, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0), None
 
 
 def _needs_grad(outputs):
     return torch.is_grad_enabled() and outputs.requires_grad
+
+
+class JaccardLoss(_Loss):
+    """1 - I / (U - I + 1e-7), I = sum p*t, U = sum p + sum t (lib/losses.py:18-28)."""
+
+    def __init__(self):
+        super(JaccardLoss, self).__init__()
+
+    def forward(self, output, target):
+        return _fused(output, target, c_jac=1.0, smooth_num=0.0, smooth_den=1e-7)
 
 
 class SmoothJaccardLoss(_Loss):
@@ -77,16 +135,12 @@ class SmoothJaccardLoss(_Loss):
         self.smooth = smooth
 
     def forward(self, output, target):
-        if _needs_grad(output):
-            return _FusedLoss.apply(output, target, 0.0, 1.0, self.smooth)
-        s, _ = fused_sums(output, target)
-        intersection, union = s[1], s[2] + s[3]
-        jac = (intersection + self.smooth) / (union - intersection + self.smooth)
-        return (1 - jac).float()
+        return _fused(output, target, c_jac=1.0, smooth_num=self.smooth, smooth_den=self.smooth)
 
 
 class BCEWithSigmoidLoss(_Loss):
-    """mean BCE-with-logits of logsigmoid(outputs) (lib/losses.py:46-53, the reference's double squash)."""
+    """BCE-with-logits of logsigmoid(outputs) (lib/losses.py:46-53, the reference's double squash): mean
+    (size_average), sum, or the per-element tensor (reduce=False)."""
 
     def __init__(self, size_average=True, reduce=True):
         super().__init__()
@@ -95,12 +149,10 @@ class BCEWithSigmoidLoss(_Loss):
 
     def forward(self, outputs, targets):
         if not self.reduce:
-            raise NotImplementedError("reduce=False (per-element loss) is not on the fused path")
-        scale = 1.0 / outputs.numel() if self.size_average else 1.0
-        if _needs_grad(outputs):
-            return _FusedLoss.apply(outputs, targets, scale, 0.0, 0.0)
-        s, _ = fused_sums(outputs, targets)
-        return (s[0] * scale).float()
+            if _needs_grad(outputs):
+                return _ElementBCE.apply(outputs, targets)
+            return fused_sums(outputs, targets, per_element=True)[2].view_as(outputs)
+        return _fused(outputs, targets, c_bce=1.0 / outputs.numel() if self.size_average else 1.0)
 
 
 class BCEWithLogitsLossAndSmoothJaccard(_Loss):
@@ -114,14 +166,21 @@ class BCEWithLogitsLossAndSmoothJaccard(_Loss):
         self.jaccard_weight = jaccard_weight
 
     def forward(self, outputs, targets):
-        if _needs_grad(outputs):
-            tot = float(self.bce_weight + self.jaccard_weight)
-            return _FusedLoss.apply(outputs, targets, self.bce_weight / (tot * outputs.numel()), self.jaccard_weight / tot,
-                                    self.jac_loss.smooth)
-        s, _ = fused_sums(outputs, targets)  # one pass feeds both terms
-        bce = s[0] / outputs.numel()
+        tot = float(self.bce_weight + self.jaccard_weight)
         smooth = self.jac_loss.smooth
-        jac = 1 - (s[1] + smooth) / (s[2] + s[3] - s[1] + smooth)
-        loss1 = bce.float() * self.bce_weight
-        loss2 = jac.float() * self.jaccard_weight
-        return (loss1 + loss2) / (self.bce_weight + self.jaccard_weight)
+        return _fused(outputs, targets, c_bce=self.bce_weight / (tot * outputs.numel()), c_jac=self.jaccard_weight / tot,
+                      smooth_num=smooth, smooth_den=smooth)         # one pass feeds both terms
+
+
+class FocalLossBinary(_Loss):
+    """mean (or sum) of (1 - pt)^gamma * bce_i, pt = exp(-bce_i), bce_i = the double-squashed BCE above
+    (lib/losses.py:78-101; like the reference, `reduce` is accepted and ignored)."""
+
+    def __init__(self, gamma=2, size_average=True, reduce=True):
+        super(FocalLossBinary, self).__init__()
+        self.gamma = gamma
+        self.size_average = size_average
+        self.reduce = reduce
+
+    def forward(self, outputs, targets):
+        return _fused(outputs, targets, c_focal=1.0 / outputs.numel() if self.size_average else 1.0, gamma=float(self.gamma))

@@ -44,7 +44,7 @@ def confusion_counts(output, target):
     return fused_sums(output, target)[1]
 
 
-def confusion_counts_from_probs(probs, target, threshold=0.5):
+def confusion_counts_from_probs(probs, target, threshold=0.5, out=None):
     """Same counts from probabilities/masks already on the device (`mask > 0.5`, inria_submit.py:305)."""
     N.require_cuda()
     p = probs.detach().float().contiguous()
@@ -54,9 +54,10 @@ def confusion_counts_from_probs(probs, target, threshold=0.5):
     t = t.contiguous()
     if p.numel() != t.numel():
         raise ValueError("probs and target must have the same number of elements")
-    counts = torch.empty(4, dtype=torch.int64, device=p.device)
-    N.check(N.lib().snb_confusion_counts(N.ptr(p), N.ptr(t), _TARGET_DT[t.dtype], p.numel(), float(threshold),
-                                         N.ptr(counts), N.stream_ptr()))
+    counts = torch.empty(4, dtype=torch.int64, device=p.device) if out is None else out
+    with torch.cuda.device(p.device):
+        N.check(N.lib().snb_confusion_counts(N.ptr(p), N.ptr(t), _TARGET_DT[t.dtype], p.numel(), float(threshold),
+                                             N.ptr(counts), N.ptr(N.reduce_workspace()), N.stream_ptr()))
     return counts
 
 
@@ -95,9 +96,10 @@ class PRCurveMeter(object):
         t = t.contiguous()
         self._ensure(x.device)
         a = self._acc
-        N.check(N.lib().snb_pr_curve_update(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(self._thr),
-                                            len(self.thresholds), N.ptr(a[0]), N.ptr(a[1]), N.ptr(a[2]),
-                                            N.ptr(a[3]), N.stream_ptr()))
+        with torch.cuda.device(x.device):
+            N.check(N.lib().snb_pr_curve_update(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(self._thr),
+                                                len(self.thresholds), N.ptr(a[0]), N.ptr(a[1]), N.ptr(a[2]),
+                                                N.ptr(a[3]), N.ptr(N.reduce_workspace()), N.stream_ptr()))
 
     def _get(self, i):
         if self._acc is None:

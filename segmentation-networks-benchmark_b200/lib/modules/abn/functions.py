@@ -43,8 +43,11 @@ class InPlaceABN(autograd.Function):
             raise ValueError("unknown activation %r" % (activation,))
         ctx.training, ctx.momentum, ctx.eps, ctx.activation, ctx.slope = training, momentum, eps, activation, slope
         ctx.affine = weight is not None and bias is not None
-        if not x.is_contiguous():
-            raise ValueError("inplace_abn modifies its input in place and needs a contiguous tensor")
+        # the reference calls x.contiguous() (functions.py:72): a non-contiguous input is copied, and the copy is what gets
+        # normalised and returned
+        in_place = x.is_contiguous()
+        if not in_place:
+            x = x.contiguous()
         n, c, hw = _dims(x)
         weight = weight.contiguous() if ctx.affine else None
         bias = bias.contiguous() if ctx.affine else None
@@ -61,7 +64,8 @@ class InPlaceABN(autograd.Function):
                                             N.ptr(work), N.stream_ptr()))
         # the reference also marks running_mean / running_var dirty in training mode (functions.py:87); torch >= 2 rejects
         # dirty tensors that are not outputs, and buffers need no autograd bookkeeping, so only x is marked
-        ctx.mark_dirty(x)
+        if in_place:
+            ctx.mark_dirty(x)
         ctx.var = var
         ctx.save_for_backward(x, var, weight if ctx.affine else x.new_empty(0), bias if ctx.affine else x.new_empty(0))
         return x

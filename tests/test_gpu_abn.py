@@ -80,3 +80,36 @@ def test_argument_errors(cuda):
     with pytest.raises(ValueError):
         inplace_abn(torch.zeros(2, 4, 3, 3, device="cuda"), m.weight, m.bias, m.running_mean, m.running_var, True, 0.1,
                     1e-5, "swish", 0.01)
+
+
+def test_large_mean_and_non_contiguous_input(cuda):
+    """Batch variance of a channel whose |mean| is 1000x its standard deviation (E[x^2] - E[x]^2 in float32 would lose
+    every bit; the kernels accumulate around a pivot), on a non-contiguous input (the reference copies it,
+    lib/modules/abn/functions.py:72), for the NCHW module and the NHWC slab kernel."""
+    from snb_b200 import engine as E
+    from snb_b200 import _native as N
+
+    gen = torch.Generator().manual_seed(11)
+    n, c, h, w = 4, 16, 24, 24
+    x = torch.randn((n, h, w, c), generator=gen) * 0.05 + 50.0
+    xd = x.cuda().permute(0, 3, 1, 2)                       # NCHW view of NHWC storage: not contiguous
+    assert not xd.is_contiguous()
+    m = InPlaceABN(c).cuda().train()
+    z = m(xd)
+    ref = x.permute(0, 3, 1, 2).double()
+    mean, var = ref.mean(dim=(0, 2, 3)), ref.var(dim=(0, 2, 3), unbiased=False)
+    want = torch.nn.functional.leaky_relu((ref - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + 1e-5) * (1 + 1e-5), 0.01)
+    assert (z.cpu().double() - want).abs().max().item() < 2e-3          # float32 input resolution at 50 is 4e-6 = 1e-4 sigma
+    cnt = n * h * w
+    assert (m.running_var.cpu().double() - (0.9 + 0.1 * var * cnt / (cnt - 1))).abs().max().item() < 1e-6
+    # NHWC bf16 slab kernel: values 50 +- 0.25 in bf16 (step 0.25): variance of the rounded data must be recovered
+    src = E.Slab(n, h, w, c, "cuda")
+    src.t.copy_((torch.randn((n, h, w, c), generator=gen) * 0.5 + 50.0).cuda().to(torch.bfloat16))
+    dst = E.Slab(n, h, w, c, "cuda")
+    ones, zeros = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    op = E.BnTrainOp(src.view(), dst.view(), (ones, zeros, zeros.clone(), ones.clone(), 1e-5, 0.1), False, -1.0)
+    op(N.stream_ptr())
+    xs = src.t.double().cpu()
+    assert (op.mean.cpu().double() - xs.mean(dim=(0, 1, 2))).abs().max().item() < 1e-4
+    v = xs.var(dim=(0, 1, 2), unbiased=False)
+    assert ((op.var.cpu().double() - v).abs() / v).max().item() < 1e-4

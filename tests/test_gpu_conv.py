@@ -10,9 +10,10 @@ from snb_b200 import engine as E
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1, 2, 4], ids=["tap", "halo", "halo+bres", "pairs"], autouse=True)
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["tap", "halo", "halo+bres", "default", "pairs"], autouse=True)
 def conv_mode(request, monkeypatch):
-    """Every test runs against the three main-loop variants (SNB_CONV_MODE is read at snb_conv_create)."""
+    """Every test runs against all main-loop variants, the default (3: fused ConvTranspose phases, wave-aware N tile)
+    included (SNB_CONV_MODE is read at snb_conv_create)."""
     monkeypatch.setenv("SNB_CONV_MODE", str(request.param))
     return request.param
 
@@ -45,6 +46,8 @@ def check(got, want, tol=2e-2):
     (3, 16, 32, 96, 32, True),       # BK = 32 path (SW64), BN = 32 store path
     (1, 64, 64, 192, 128, True),
     (1, 7, 7, 64, 64, True),         # smaller than one tile: TMA OOB fill + clipped store
+    (13, 32, 32, 512, 512, True),    # bench.py's deep layers: 208 tiles of N=256 on 148 SMs -> the default mode narrows N to 128
+    (13, 16, 16, 512, 512, True),
 ])
 def test_conv3x3(cuda, n, h, w, cin, cout, relu):
     g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)

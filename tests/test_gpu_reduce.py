@@ -96,3 +96,59 @@ def test_loss_backward_against_reference_gradients(cuda, golden_dir, seed, shape
         v = losses.BCEWithLogitsLossAndSmoothJaccard()(logits.cuda(), t)
     x = logits.cuda().requires_grad_(True)
     assert float(v) == pytest.approx(float(losses.BCEWithLogitsLossAndSmoothJaccard()(x, t).detach()), rel=1e-6)
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))])
+@pytest.mark.parametrize("target_dtype", [torch.int64, torch.uint8, torch.float32])
+def test_extra_losses_against_reference(cuda, golden_dir, seed, shape, target_dtype):
+    """JaccardLoss, FocalLossBinary (gamma 2 / 1.5 / 0, mean / sum) and BCEWithSigmoidLoss (sum, reduce=False) on the
+    fused reduction: values and gradients against the reference modules (tests/golden/loss_extra.npz)."""
+    g = np.load(os.path.join(golden_dir, "loss_extra.npz"))
+    logits, targets = synth.logits_targets(seed, shape)
+    t = targets.to(target_dtype).cuda()
+    sample = lambda a: a if a.size < 5000 else a[::97]
+    up = torch.from_numpy(np.random.RandomState(40 + seed).standard_normal(shape).astype(np.float32)).cuda()
+    cases = [("jaccard", losses.JaccardLoss(), None, REL),
+             ("focal_g2_mean", losses.FocalLossBinary(gamma=2), None, 2e-5),
+             ("focal_g1.5_sum", losses.FocalLossBinary(gamma=1.5, size_average=False), None, 2e-5),
+             ("focal_g0_mean", losses.FocalLossBinary(gamma=0), None, REL),
+             ("bce_sum", losses.BCEWithSigmoidLoss(size_average=False), None, REL),
+             ("bce_elem", losses.BCEWithSigmoidLoss(reduce=False), up, None)]
+    for tag, mod, upstream, rel in cases:
+        with torch.no_grad():
+            v = mod(logits.cuda(), t)
+        x = logits.cuda().requires_grad_(True)
+        y = mod(x, t)
+        assert y.requires_grad
+        if upstream is None:
+            assert y.dim() == 0 and float(y) == pytest.approx(float(g["seed%d_%s" % (seed, tag)]), rel=rel), tag
+            assert float(v) == pytest.approx(float(y.detach()), rel=1e-6)
+            (y * 3.0).backward()
+        else:
+            assert y.shape == logits.shape and torch.equal(v, y.detach())
+            want_e = g["seed%d_%s" % (seed, tag)]
+            assert np.abs(sample(y.detach().cpu().numpy().reshape(-1)) - want_e).max() < 2e-6 * max(1.0, np.abs(want_e).max())
+            (y * upstream).sum().backward()
+        want = g["seed%d_%s_grad" % (seed, tag)]
+        got = sample(x.grad.cpu().numpy().reshape(-1))
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-12, (tag, np.abs(got - want).max(), np.abs(want).max())
+
+
+def test_reductions_are_single_launch_and_deterministic(cuda):
+    """The workspace returns to rest after every call (back-to-back calls on one workspace agree bit for bit), and
+    two streams use two workspaces."""
+    logits, targets = synth.logits_targets(5, (3, 1, 300, 301))
+    x, t = logits.cuda(), targets.cuda()
+    a = [losses.fused_sums(x, t, focal_gamma=2.0) for _ in range(3)]
+    for s, c in a[1:]:
+        assert torch.equal(s, a[0][0]) and torch.equal(c, a[0][1])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        s2, c2 = losses.fused_sums(x, t, focal_gamma=2.0)
+    side.synchronize()
+    assert torch.equal(s2, a[0][0]) and torch.equal(c2, a[0][1])
+    from snb_b200 import _native as N
+    ws = N.reduce_workspace()
+    torch.cuda.synchronize()
+    assert int(ws[:64].count_nonzero()) == 0        # the ticket is back at rest

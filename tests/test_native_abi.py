@@ -75,7 +75,8 @@ def test_argument_validation_without_gpu():
     # null device pointers and bad ranges are rejected before anything is launched
     assert lib.snb_split_hwc(h, None, 3, 1, 0, None, None, 0, 1, None) == N.SNB_E_INVALID
     assert lib.snb_merge(h, None, N.DT_F32, 1, 1, None, None, N.DT_F32, None, 0.5, None) == N.SNB_E_INVALID
-    assert lib.snb_loss_iou_reduce(None, None, N.DT_I64, 4, None, None, None) == N.SNB_E_INVALID
+    assert lib.snb_loss_iou_reduce(None, None, N.DT_I64, 4, -1.0, None, None, None, None, None) == N.SNB_E_INVALID
+    assert lib.snb_reduce_workspace_bytes() >= 64 * 2048
     d = N.ConvDesc()
     out = ctypes.c_void_p()
     assert lib.snb_conv_create(ctypes.byref(d), ctypes.byref(out)) == N.SNB_E_INVALID

@@ -227,3 +227,30 @@ def test_linknet34_train_mode_forward(golden_dir):
     for k in g.files:
         if "__" in k:
             assert np.abs(new[k.replace("__", ".")].numpy() - g[k]).max() < 1e-6, k
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (8, 1, 224, 224)), (3, (2, 1, 33, 17))])
+def test_extra_losses(golden_dir, seed, shape):
+    """JaccardLoss, FocalLossBinary, BCEWithSigmoidLoss(reduce=False / sum) restatements against the reference modules
+    (lib/losses.py:18-28,46-53,78-101): values and gradients (tests/golden/loss_extra.npz)."""
+    g = np.load(os.path.join(golden_dir, "loss_extra.npz"))
+    logits, targets = synth.logits_targets(seed, shape)
+    sample = lambda a: a if a.size < 5000 else a[::97]
+    up = torch.from_numpy(np.random.RandomState(40 + seed).standard_normal(shape).astype(np.float32))
+    cases = [("jaccard", no.jaccard_loss, None),
+             ("focal_g2_mean", lambda x, t: no.focal_loss_binary(x, t, 2, True), None),
+             ("focal_g1.5_sum", lambda x, t: no.focal_loss_binary(x, t, 1.5, False), None),
+             ("focal_g0_mean", lambda x, t: no.focal_loss_binary(x, t, 0, True), None),
+             ("bce_sum", lambda x, t: no.bce_elements(x, t).sum(), None),
+             ("bce_elem", no.bce_elements, up)]
+    for tag, fn, upstream in cases:
+        x = logits.clone().requires_grad_(True)
+        y = fn(x, targets)
+        if upstream is None:
+            assert float(y) == pytest.approx(float(g["seed%d_%s" % (seed, tag)]), rel=1e-6), tag
+            (y * 3.0).backward()
+        else:
+            assert np.abs(sample(y.detach().numpy().reshape(-1)) - g["seed%d_%s" % (seed, tag)]).max() < 1e-6
+            (y * upstream).sum().backward()
+        want = g["seed%d_%s_grad" % (seed, tag)]
+        assert np.abs(sample(x.grad.numpy().reshape(-1)) - want).max() <= 2e-6 * np.abs(want).max() + 1e-12, tag
