@@ -119,6 +119,8 @@ SNB_API int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, 
 #define SNB_CONV_2X2 4       /* Conv2d k2 s1 p1: 4 taps (dy,dx in {-1,0}), output (h+1) x (w+1); also the body of a
                                stride-2 conv3x3 after space-to-depth (lib/models/linknet.py:62, resnet34 via :39-48) */
 #define SNB_CONVT_3X3_S2_FULL 5 /* ConvTranspose2d k3 s2 p0 uncropped: output (2h+1) x (2w+1) (lib/models/linknet.py:58) */
+#define SNB_CONV_2X2_ADJ 6   /* the adjoint tap set of SNB_CONV_2X2: 4 taps (dy,dx in {0,+1}), output h x w (valid: (h-1) x (w-1)):
+                               input gradients of stride-2 convolutions / of Conv2d k2 p1 (torch_train.py:186-189)            */
 #define SNB_CONVT_3X3_S2 3  /* ConvTranspose2d k3 s2 p0 cropped to [0,2h) x [0,2w) (lib/models/tiramisu.py:62-90):
                                4 phases x 4 tap slots, unused slots carry zero weights       */
 
@@ -162,8 +164,9 @@ typedef struct snb_conv_desc {
   int32_t res_after_act;
   const void* d_residual;   /* same element type as d_out, first channel read, or NULL                */
   int64_t res_cstride;
-  int32_t valid;            /* conv3x3: no padding, output (h-2) x (w-2) (lib/models/linknet.py:60); conv2x2: padding on
-                               top/left only, output h x w (a stride-2 conv3x3 after space-to-depth) */
+  int32_t valid;            /* conv3x3: 1 = no padding, output (h-2) x (w-2) (lib/models/linknet.py:60), 2 = "full", output
+                               (h+2) x (w+2) (the input gradient of the valid conv); conv2x2: 1 = padding on top/left only,
+                               output h x w (a stride-2 conv3x3 after space-to-depth); conv2x2-adjoint: 1 = (h-1) x (w-1) */
   int32_t out_upsample2x;
   int32_t dtype;         /* SNB_CONV_BF16 / SNB_CONV_TF32: element type of d_in, d_out, d_pool_out and d_weight
                             (bias and the head stay float); channel counts are multiples of 64 bytes / element size */
@@ -175,6 +178,28 @@ SNB_API int snb_conv_launch(const snb_conv* c, void* stream);
 SNB_API void snb_conv_destroy(snb_conv* c);
 /* algorithmic FLOPs of one launch (2*MACs, padding excluded), for roofline bookkeeping */
 SNB_API double snb_conv_flops(const snb_conv* c);
+
+/* Weight gradient of a convolution of the kinds above on the tensor cores (autograd of nn.Conv2d / nn.ConvTranspose2d,
+ * torch_train.py:186-189): with X the forward input and dY the gradient of the forward output (both NHWC bf16 slabs),
+ *   d_dweight[(phase * taps + tap)][co][ci] += sum over pixels of dY_phase[pixel][co] * X[pixel + tap offset][ci]
+ * in the tap / phase order of the packed forward weights, as float [phases * taps][dw_cout][dw_cin] (dw_cout >= cout,
+ * dw_cin >= cin; only the cout x cin corner is touched).  The call ACCUMULATES (split-K float atomics): zero the buffer
+ * first.  kind / valid / n / h / w describe the forward convolution (h, w = its input size). */
+typedef struct snb_wgrad_desc {
+  int32_t kind, valid;
+  int64_t n, h, w;
+  int64_t cin, in_cstride;      /* forward input channels read, pixel stride of its slab    */
+  int64_t cout, dout_cstride;   /* forward output channels, pixel stride of the dY slab     */
+  const void* d_in;             /* bf16 X, first channel                                    */
+  const void* d_dout;           /* bf16 dY, first channel (the forward's output extent)     */
+  float* d_dweight;
+  int64_t dw_cout, dw_cin;
+} snb_wgrad_desc;
+typedef struct snb_wgrad snb_wgrad;
+SNB_API int snb_wgrad_create(const snb_wgrad_desc* desc, snb_wgrad** out);
+SNB_API int snb_wgrad_launch(const snb_wgrad* c, void* stream);
+SNB_API void snb_wgrad_destroy(snb_wgrad* c);
+SNB_API double snb_wgrad_flops(const snb_wgrad* c);
 
 /* nn.MaxPool2d(2,2) on NHWC slabs of bf16 (elem_bytes 2) or float (elem_bytes 4); h, w even; channel counts and
  * strides multiples of 16 bytes */
@@ -197,15 +222,40 @@ SNB_API void snb_conv_scatter_destroy(snb_conv_scatter* c);
 SNB_API double snb_conv_scatter_flops(const snb_conv_scatter* c);
 
 /* ResNet-34 encoder helpers of LinkNet34 (lib/models/linknet.py:39-48), NHWC bf16 slabs, channels % 8 == 0:
- *   snb_space_to_depth2: out[n][y][x][(py*2+px)*C + c] = in[n][2y+py][2x+px][c]   (h, w even) -- turns the stride-2
- *                        conv3x3 / conv1x1 of a down-sampling BasicBlock into SNB_CONV_2X2 / SNB_CONV_1X1 launches
+ *   snb_space_to_depth2: out[n][y][x][(py*2+px)*C + c] = in[n][2y+py][2x+px][c] (zero beyond an odd h / w; the output has
+ *                        ceil(h/2) x ceil(w/2) pixels) -- turns the stride-2 conv3x3 / conv1x1 of a down-sampling BasicBlock
+ *                        into SNB_CONV_2X2 / SNB_CONV_1X1 launches, and the gradients of stride-2 transposed convolutions
+ *                        into stride-1 convolutions over the blocked gradient
+ *   snb_depth_to_space2: the inverse, out[n][2y+py][2x+px][c] (+)= in[n][y][x][(py*2+px)*C + c]; (h, w, channels)
+ *                        describe the OUTPUT, accumulate != 0 adds to what the output holds (gradient fan-in)
+ *   snb_scale_nc_nhwc:   out[n][pixel][c] = in[n][pixel][c] * scale[n][c]: nn.Dropout2d (lib/models/linknet.py:57,83) with
+ *                        the keep mask / (1 - p) drawn by the caller, forward and backward
  *   snb_maxpool3x3s2:    nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
  *   snb_stem7x7_rows:    float [n][C][h][w] -> bf16 rows [n][ceil(h/2)][ceil(w/2)][k_pad] of the stride-2 7x7 p3 stem,
  *                        k = (ky*7+kx)*C + c, zero for k >= 49*C: the stem becomes a conv1x1 over these rows */
 SNB_API int snb_space_to_depth2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                         void* d_out, int64_t out_cstride, void* stream);
+SNB_API int snb_depth_to_space2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                        void* d_out, int64_t out_cstride, int accumulate, void* stream);
+SNB_API int snb_scale_nc_nhwc(const void* d_in, int64_t n, int64_t hw, int64_t channels, int64_t in_cstride,
+                      const float* d_scale, void* d_out, int64_t out_cstride, void* stream);
 SNB_API int snb_maxpool3x3s2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                      void* d_out, int64_t out_cstride, void* stream);
+
+/* Multi-segment index gather, one launch for all layers of a plan: for every segment of the DEVICE table d_segs,
+ * dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 for i < count (dst float, or bf16 when dst_bf16 != 0).  first_block = the number
+ * of 1024-element blocks of all earlier segments; total_blocks = their sum over the table.  Re-packs fp32 parameters into
+ * the [phase][tap][Cout][Cin] operands of the forward / input-gradient convolutions after an optimiser step and scatters
+ * packed weight gradients (snb_wgrad_*) back into the parameters' layouts (torch_train.py:186-190). */
+typedef struct snb_gather_seg {
+  const float* src;
+  void* dst;
+  const int32_t* idx;
+  int64_t count;
+  int64_t first_block;
+} snb_gather_seg;
+SNB_API int snb_gather_segments(const snb_gather_seg* d_segs, int64_t n_segs, int64_t total_blocks, int dst_bf16,
+                        void* stream);
 SNB_API int snb_stem7x7_rows(const float* d_src, int64_t n, int64_t channels, int64_t h, int64_t w, void* d_dst,
                      int64_t k_pad, void* stream);
 

@@ -20,7 +20,7 @@ SNB_E_UNSUPPORTED = -4
 
 DT_U8, DT_F32, DT_F64, DT_I64 = 0, 1, 2, 3
 LAYOUT_NCHW_F32, LAYOUT_PATCH32, LAYOUT_PATCH32_F32 = 0, 1, 2
-CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2, CONV_2X2, CONVT_3X3_S2_FULL = 0, 1, 2, 3, 4, 5
+CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2, CONV_2X2, CONVT_3X3_S2_FULL, CONV_2X2_ADJ = 0, 1, 2, 3, 4, 5, 6
 CONV_BF16, CONV_TF32 = 0, 1
 
 c_i64 = ctypes.c_int64
@@ -63,6 +63,14 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class WgradDesc(ctypes.Structure):
+    """struct snb_wgrad_desc (include/snb_b200.h)."""
+
+    _fields_ = [("kind", ctypes.c_int32), ("valid", ctypes.c_int32), ("n", c_i64), ("h", c_i64), ("w", c_i64),
+                ("cin", c_i64), ("in_cstride", c_i64), ("cout", c_i64), ("dout_cstride", c_i64), ("d_in", c_vp),
+                ("d_dout", c_vp), ("d_dweight", c_vp), ("dw_cout", c_i64), ("dw_cin", c_i64)]
+
+
 # name -> (restype, argtypes); every symbol include/snb_b200.h declares
 class ConvGeom(ctypes.Structure):
     """struct snb_conv_geom (include/snb_b200.h)."""
@@ -86,6 +94,10 @@ SIGNATURES = {
     "snb_conv_launch": (c_int, [c_vp, c_vp]),
     "snb_conv_destroy": (None, [c_vp]),
     "snb_conv_flops": (ctypes.c_double, [c_vp]),
+    "snb_wgrad_create": (c_int, [ctypes.POINTER(WgradDesc), ctypes.POINTER(c_vp)]),
+    "snb_wgrad_launch": (c_int, [c_vp, c_vp]),
+    "snb_wgrad_destroy": (None, [c_vp]),
+    "snb_wgrad_flops": (ctypes.c_double, [c_vp]),
     "snb_conv_scatter_create": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                         ctypes.POINTER(c_vp)]),
     "snb_conv_scatter_launch": (c_int, [c_vp, c_vp]),
@@ -96,6 +108,9 @@ SIGNATURES = {
     "snb_conv_generic_wgrad": (c_int, [ctypes.POINTER(ConvGeom), c_vp, c_vp, c_vp, c_vp]),
     "snb_maxpool2x2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp]),
     "snb_space_to_depth2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "snb_depth_to_space2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "snb_scale_nc_nhwc": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "snb_gather_segments": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp]),
     "snb_maxpool3x3s2": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_stem7x7_rows": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "snb_abn_forward": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float,

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsnb_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["common.cu", "slicer.cu", "reduce.cu", "aux.cu", "abn.cu", "conv_scatter.cu", "conv_generic.cu", "conv_tcgen05.cu"]
+SOURCES = ["common.cu", "slicer.cu", "reduce.cu", "aux.cu", "abn.cu", "conv_scatter.cu", "conv_generic.cu", "conv_wgrad.cu", "conv_tcgen05.cu"]
 HEADERS = ["sm100_ptx.cuh", "snb_internal.h", os.path.join("..", "..", "include", "snb_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -84,7 +84,7 @@ __global__ void bn_relu_kernel(const uint4* __restrict__ in, int CV, int CPV, in
 // 4-tap stride-1 conv over `out` (SNB_CONV_2X2 taps), a stride-2 conv1x1 a plain conv1x1 on channels [0, C)
 __global__ void space_to_depth_kernel(const uint4* __restrict__ in, int H, int W, int CV, int in_sv,
                                       uint4* __restrict__ out, int out_sv, int64_t total) {
-  const int OH = H / 2, OW = W / 2;
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;     // odd sizes: the missing last row / column reads as zero
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i;
     const int cv = (int)(r % CV); r /= CV;
@@ -92,8 +92,39 @@ __global__ void space_to_depth_kernel(const uint4* __restrict__ in, int H, int W
     const int ox = (int)(r % OW); r /= OW;
     const int oy = (int)(r % OH);
     const int64_t n = r / OH;
-    out[((n * OH + oy) * OW + ox) * out_sv + q * CV + cv] =
-        __ldg(in + ((n * H + 2 * oy + (q >> 1)) * W + 2 * ox + (q & 1)) * in_sv + cv);
+    const int y = 2 * oy + (q >> 1), x = 2 * ox + (q & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y < H && x < W) v = __ldg(in + ((n * H + y) * W + x) * in_sv + cv);
+    out[((n * OH + oy) * OW + ox) * out_sv + q * CV + cv] = v;
+  }
+}
+
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a));
+  const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&b));
+  const __nv_bfloat162 r = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// inverse of space_to_depth_kernel: out[n][2y+py][2x+px][c] (+)= in[n][y][x][(py*2+px)*C + c]; H, W = the OUTPUT size
+// (rows / columns of the last block beyond an odd size are dropped)
+__global__ void depth_to_space_kernel(const uint4* __restrict__ in, int H, int W, int CV, int in_sv, uint4* __restrict__ out,
+                                      int out_sv, int accumulate, int64_t total) {
+  const int IH = (H + 1) / 2, IW = (W + 1) / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int cv = (int)(r % CV); r /= CV;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int64_t n = r / H;
+    const int q = (y & 1) * 2 + (x & 1);
+    uint4 v = __ldg(in + ((n * IH + (y >> 1)) * IW + (x >> 1)) * in_sv + q * CV + cv);
+    uint4* dst = out + ((n * H + y) * W + x) * out_sv + cv;
+    if (accumulate) {
+      const uint4 o = *dst;
+      v = make_uint4(add_bf16x2(v.x, o.x), add_bf16x2(v.y, o.y), add_bf16x2(v.z, o.z), add_bf16x2(v.w, o.w));
+    }
+    *dst = v;
   }
 }
 
@@ -229,6 +260,64 @@ extern "C" int snb_maxpool2x2(const void* d_in, int64_t n, int64_t h, int64_t w,
   return SNB_OK;
 }
 
+// Multi-segment index gather: dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 for every segment of a device table, ONE launch for all
+// layers of a plan.  Used to (re)pack fp32 parameters into the bf16 [phase][tap][Cout][Cin] operands of the forward and
+// input-gradient convolutions after an optimiser step, and to scatter the packed fp32 weight gradients back into the
+// parameters' own layouts.  A block handles 1024 consecutive elements of one segment.
+namespace snb {
+template <bool DST_BF16>
+__global__ void __launch_bounds__(256) gather_segments_kernel(const snb_gather_seg* __restrict__ segs, int n_segs) {
+  int lo = 0, hi = n_segs - 1;
+  while (lo < hi) {            // last segment whose first_block <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].first_block <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const snb_gather_seg sg = segs[lo];
+  const int64_t base = ((int64_t)blockIdx.x - sg.first_block) * 1024;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = base + k * 256 + threadIdx.x;
+    if (i < sg.count) {
+      const int32_t j = __ldg(sg.idx + i);
+      const float v = j >= 0 ? __ldg(sg.src + j) : 0.f;
+      if (DST_BF16) static_cast<__nv_bfloat16*>(sg.dst)[i] = __float2bfloat16(v);
+      else static_cast<float*>(sg.dst)[i] = v;
+    }
+  }
+}
+}  // namespace snb
+
+extern "C" int snb_gather_segments(const snb_gather_seg* d_segs, int64_t n_segs, int64_t total_blocks, int dst_bf16,
+                                   void* stream) {
+  if (!d_segs || n_segs <= 0 || total_blocks <= 0 || total_blocks > INT32_MAX || n_segs > INT32_MAX)
+    return snb::fail(SNB_E_INVALID, "snb_gather_segments: bad arguments");
+  if (dst_bf16) snb::gather_segments_kernel<true><<<(unsigned)total_blocks, 256, 0, snb::as_stream(stream)>>>(d_segs, (int)n_segs);
+  else snb::gather_segments_kernel<false><<<(unsigned)total_blocks, 256, 0, snb::as_stream(stream)>>>(d_segs, (int)n_segs);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// out[n][y][x][c] *= scale[n][c]  (nn.Dropout2d with a given keep mask / (1 - p), lib/models/linknet.py:57,83; the same
+// kernel is its backward)
+namespace snb {
+__global__ void __launch_bounds__(256) scale_nc_kernel(const uint4* __restrict__ in, int in_sv, const float* __restrict__ scale,
+                                                       int64_t hw, int CV, uint4* __restrict__ out, int out_sv, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t pix = i / CV;
+    const int64_t n = pix / hw;
+    const uint4 u = __ldg(in + pix * in_sv + cv);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + n * CV * 8) + 2 * cv);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + n * CV * 8) + 2 * cv + 1);
+    const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(pv[0]), b = __bfloat1622float2(pv[1]), c = __bfloat1622float2(pv[2]), d = __bfloat1622float2(pv[3]);
+    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x * s0.x, a.y * s0.y), __floats2bfloat162_rn(b.x * s0.z, b.y * s0.w),
+                           __floats2bfloat162_rn(c.x * s1.x, c.y * s1.y), __floats2bfloat162_rn(d.x * s1.z, d.y * s1.w)};
+    out[pix * out_sv + cv] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+}  // namespace snb
+
 static int check_bf16_slabs(const void* d_in, const void* d_out, int64_t n, int64_t h, int64_t w, int64_t channels,
                             int64_t in_cstride, int64_t out_cstride, int64_t out_channels) {
   if (!d_in || !d_out) return fail(SNB_E_INVALID, "null argument");
@@ -243,11 +332,35 @@ static int check_bf16_slabs(const void* d_in, const void* d_out, int64_t n, int6
 extern "C" int snb_space_to_depth2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                                    void* d_out, int64_t out_cstride, void* stream) {
   if (int rc = check_bf16_slabs(d_in, d_out, n, h, w, channels, in_cstride, out_cstride, 4 * channels)) return rc;
-  if ((h & 1) || (w & 1)) return fail(SNB_E_INVALID, "space-to-depth needs even h, w");
-  const int64_t total = n * (h / 2) * (w / 2) * 4 * (channels / 8);
+  const int64_t total = n * ((h + 1) / 2) * ((w + 1) / 2) * 4 * (channels / 8);
   space_to_depth_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
                                                                          (int)(channels / 8), (int)(in_cstride / 8),
                                                                          static_cast<uint4*>(d_out), (int)(out_cstride / 8), total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_depth_to_space2(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
+                                   void* d_out, int64_t out_cstride, int accumulate, void* stream) {
+  // (h, w, channels) describe the OUTPUT; the input holds ceil(h/2) x ceil(w/2) blocks of 4 * channels
+  if (int rc = check_bf16_slabs(d_out, d_in, n, h, w, channels, out_cstride, in_cstride, 4 * channels)) return rc;
+  const int64_t total = n * h * w * (channels / 8);
+  depth_to_space_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)h, (int)w,
+                                                                         (int)(channels / 8), (int)(in_cstride / 8),
+                                                                         static_cast<uint4*>(d_out), (int)(out_cstride / 8),
+                                                                         accumulate, total);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_scale_nc_nhwc(const void* d_in, int64_t n, int64_t hw, int64_t channels, int64_t in_cstride,
+                                 const float* d_scale, void* d_out, int64_t out_cstride, void* stream) {
+  if (int rc = check_bf16_slabs(d_in, d_out, n, hw, 1, channels, in_cstride, out_cstride, channels)) return rc;
+  if (!d_scale || (reinterpret_cast<uintptr_t>(d_scale) & 15)) return fail(SNB_E_INVALID, "scale must be a 16-byte aligned float[n][channels]");
+  const int64_t total = n * hw * (channels / 8);
+  scale_nc_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_in), (int)(in_cstride / 8), d_scale, hw,
+                                                                   (int)(channels / 8), static_cast<uint4*>(d_out),
+                                                                   (int)(out_cstride / 8), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

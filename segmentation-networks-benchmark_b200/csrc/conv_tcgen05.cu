@@ -875,6 +875,59 @@ static double wave_efficiency(int64_t tiles, int sms) {
   return full > 0 ? waves / full : 1.0;
 }
 
+int conv_tap_geometry(int kind, int valid, int64_t h, int64_t w, ConvTapGeom* g) {
+  std::memset(g, 0, sizeof(*g));
+  if (kind < SNB_CONV_3X3 || kind > SNB_CONV_2X2_ADJ) return fail(SNB_E_INVALID, "unknown conv kind %d", kind);
+  const bool is_convt3 = kind == SNB_CONVT_3X3_S2 || kind == SNB_CONVT_3X3_S2_FULL;
+  const bool is_convt = kind == SNB_CONVT_4X4_S2 || is_convt3;
+  if (valid < 0 || valid > 2 || (valid == 2 && kind != SNB_CONV_3X3) ||
+      (valid == 1 && !((kind == SNB_CONV_3X3 && h >= 3 && w >= 3) || kind == SNB_CONV_2X2 || (kind == SNB_CONV_2X2_ADJ && h >= 2 && w >= 2))))
+    return fail(SNB_E_INVALID, "valid mode %d does not apply to conv kind %d at %lld x %lld", valid, kind, (long long)h, (long long)w);
+  // conv2x2 (taps -1, 0): padded = (h+1) x (w+1) outputs, valid = h x w.  conv2x2-adjoint (taps 0, +1): h x w, valid = (h-1) x (w-1)
+  int64_t grow = 0;
+  if ((kind == SNB_CONV_2X2 && !valid) || kind == SNB_CONVT_3X3_S2_FULL) grow = 1;
+  if (kind == SNB_CONV_2X2_ADJ && valid) grow = -1;
+  if (kind == SNB_CONV_3X3) grow = valid == 1 ? -2 : (valid == 2 ? 2 : 0);
+  g->load_off = kind == SNB_CONV_3X3 ? (valid == 1 ? 1 : (valid == 2 ? -1 : 0)) : 0;
+  g->grid_h = h + grow;
+  g->grid_w = w + grow;
+  const int64_t osc = is_convt ? 2 : 1;   // output pixels per grid pixel and axis (before out_upsample2x)
+  g->out_h = kind == SNB_CONVT_3X3_S2_FULL ? 2 * h + 1 : g->grid_h * osc;
+  g->out_w = kind == SNB_CONVT_3X3_S2_FULL ? 2 * w + 1 : g->grid_w * osc;
+  g->n_phases = is_convt ? 4 : 1;
+  g->taps = kind == SNB_CONV_3X3 ? 9 : (kind == SNB_CONV_1X1 ? 1 : 4);
+  g->flop_taps = is_convt3 ? 9.0 : (is_convt ? 16.0 : (double)g->taps);
+  if (kind == SNB_CONV_3X3) {
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        g->tap_dy[0][ky * 3 + kx] = static_cast<int8_t>(ky - 1);
+        g->tap_dx[0][ky * 3 + kx] = static_cast<int8_t>(kx - 1);
+      }
+  } else if (kind == SNB_CONV_2X2 || kind == SNB_CONV_2X2_ADJ) {
+    // k2 s1 p1: out[y][x] = sum in[y+ky-1][x+kx-1] * W[ky][kx]; tap = ky*2 + kx; its adjoint reads in[y+ky][x+kx]
+    const int o = kind == SNB_CONV_2X2 ? -1 : 0;
+    for (int ky = 0; ky < 2; ++ky)
+      for (int kx = 0; kx < 2; ++kx) {
+        g->tap_dy[0][ky * 2 + kx] = static_cast<int8_t>(ky + o);
+        g->tap_dx[0][ky * 2 + kx] = static_cast<int8_t>(kx + o);
+      }
+  } else if (is_convt) {
+    // k4 s2 p1: out[2y+py] gathers in[y+dy] * W[ky]:  py=0: (dy=0,ky=1), (dy=-1,ky=3);  py=1: (dy=+1,ky=0), (dy=0,ky=2)
+    // k3 s2 p0: out[2y+py] gathers                    py=0: (dy=0,ky=0), (dy=-1,ky=2);  py=1: (dy=0,ky=1), (unused slot)
+    // the packed weight tap order is (ty, tx) with ty, tx in {0,1} following that list
+    const int d4[2][2] = {{0, -1}, {1, 0}}, d3[2][2] = {{0, -1}, {0, 0}};
+    const int (*dlist)[2] = kind == SNB_CONVT_4X4_S2 ? d4 : d3;   // the FULL variant only widens the tile grid
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int ty = 0; ty < 2; ++ty)
+          for (int tx = 0; tx < 2; ++tx) {
+            g->tap_dy[py * 2 + px][ty * 2 + tx] = static_cast<int8_t>(dlist[py][ty]);
+            g->tap_dx[py * 2 + px][ty * 2 + tx] = static_cast<int8_t>(dlist[px][tx]);
+          }
+  }
+  return SNB_OK;
+}
+
 }  // namespace snb
 
 struct snb_conv {
@@ -893,21 +946,17 @@ using namespace snb;
 extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (!d || !out) return fail(SNB_E_INVALID, "snb_conv_create: null argument");
   *out = nullptr;
-  if (d->kind < SNB_CONV_3X3 || d->kind > SNB_CONVT_3X3_S2_FULL) return fail(SNB_E_INVALID, "unknown conv kind %d", d->kind);
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
+  ConvTapGeom tgeo;
+  if (int rc = conv_tap_geometry(d->kind, d->valid, d->h, d->w, &tgeo)) return rc;
   const bool is_convt3 = d->kind == SNB_CONVT_3X3_S2 || d->kind == SNB_CONVT_3X3_S2_FULL;
   const bool is_convt = d->kind == SNB_CONVT_4X4_S2 || is_convt3;
-  // valid: conv3x3 without padding ((h-2) x (w-2) outputs); conv k2 with top/left padding only (h x w outputs)
-  const bool valid = d->valid != 0;
-  if (valid && !((d->kind == SNB_CONV_3X3 && d->h >= 3 && d->w >= 3) || d->kind == SNB_CONV_2X2))
-    return fail(SNB_E_INVALID, "valid mode applies to conv3x3 (inputs of at least 3x3) and conv2x2");
-  // tile grid (where accumulators are computed), store offset and output extent per kind
-  const int grid_pad = ((d->kind == SNB_CONV_2X2 && !valid) || d->kind == SNB_CONVT_3X3_S2_FULL) ? 1 : 0;
-  const int load_dx = (valid && d->kind == SNB_CONV_3X3) ? 1 : 0;
-  const int64_t grid_h = d->h + grid_pad - 2 * load_dx, grid_w = d->w + grid_pad - 2 * load_dx;
-  const int64_t osc = is_convt ? 2 : 1;   // output pixels per grid pixel and axis (before out_upsample2x)
-  const int64_t out_h = d->kind == SNB_CONVT_3X3_S2_FULL ? 2 * d->h + 1 : grid_h * osc;
-  const int64_t out_w = d->kind == SNB_CONVT_3X3_S2_FULL ? 2 * d->w + 1 : grid_w * osc;
-  if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
+  const int valid = d->valid;
+  // tile grid (where accumulators are computed), halo-origin offset and output extent per kind
+  const int grid_pad = (tgeo.grid_h != d->h) ? 1 : 0;          // the tile grid differs from the input grid
+  const int load_dx = tgeo.load_off;
+  const int64_t grid_h = tgeo.grid_h, grid_w = tgeo.grid_w;
+  const int64_t out_h = tgeo.out_h, out_w = tgeo.out_w;
   if (d->dtype != SNB_CONV_BF16 && d->dtype != SNB_CONV_TF32) return fail(SNB_E_INVALID, "unknown conv dtype %d", d->dtype);
   const int eb = d->dtype == SNB_CONV_TF32 ? 4 : 2;     // element bytes of activations and weights
   const int cmul = 64 / eb;                             // channel granularity: one 64-byte operand row
@@ -934,7 +983,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
                   (reinterpret_cast<uintptr_t>(d->d_residual) & 15)))
     return fail(SNB_E_INVALID, "the residual operand needs a plain conv without head and a 16-byte aligned slab");
   const bool pool = d->d_pool_out != nullptr;
-  if (pool && (valid || head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
+  if (pool && (valid != 0 || head || d->kind != SNB_CONV_3X3 || (d->h & 1) || (d->w & 1) || d->pool_cstride < d->cout ||
                d->pool_cstride % calign != 0 || (reinterpret_cast<uintptr_t>(d->d_pool_out) & 15)))
     return fail(SNB_E_INVALID, "fused max-pool needs a conv3x3 without head, even h and w and a valid pooled slab");
   if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
@@ -967,41 +1016,17 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   std::memset(&p, 0, sizeof(p));
   c->kernel = kc;
 
-  p.n_phases = is_convt ? 4 : 1;
-  p.taps = d->kind == SNB_CONV_3X3 ? 9 : (d->kind == SNB_CONV_1X1 ? 1 : 4);
-  if (d->kind == SNB_CONV_3X3) {
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        p.tap_dy[0][ky * 3 + kx] = static_cast<int8_t>(ky - 1);
-        p.tap_dx[0][ky * 3 + kx] = static_cast<int8_t>(kx - 1);
-      }
-  } else if (d->kind == SNB_CONV_2X2) {
-    // k2 s1 p1: out[y][x] = sum in[y+ky-1][x+kx-1] * W[ky][kx]; tap = ky*2 + kx; output is (h+1) x (w+1)
-    for (int ky = 0; ky < 2; ++ky)
-      for (int kx = 0; kx < 2; ++kx) {
-        p.tap_dy[0][ky * 2 + kx] = static_cast<int8_t>(ky - 1);
-        p.tap_dx[0][ky * 2 + kx] = static_cast<int8_t>(kx - 1);
-      }
-  } else if (is_convt) {
-    // k4 s2 p1: out[2y+py] gathers in[y+dy] * W[ky]:  py=0: (dy=0,ky=1), (dy=-1,ky=3);  py=1: (dy=+1,ky=0), (dy=0,ky=2)
-    // k3 s2 p0: out[2y+py] gathers                    py=0: (dy=0,ky=0), (dy=-1,ky=2);  py=1: (dy=0,ky=1), (unused slot)
-    // the packed weight tap order is (ty, tx) with ty, tx in {0,1} following that list
-    const int d4[2][2] = {{0, -1}, {1, 0}}, d3[2][2] = {{0, -1}, {0, 0}};
-    const int (*dlist)[2] = d->kind == SNB_CONVT_4X4_S2 ? d4 : d3;   // the FULL variant only widens the tile grid
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px)
-        for (int ty = 0; ty < 2; ++ty)
-          for (int tx = 0; tx < 2; ++tx) {
-            p.tap_dy[py * 2 + px][ty * 2 + tx] = static_cast<int8_t>(dlist[py][ty]);
-            p.tap_dx[py * 2 + px][ty * 2 + tx] = static_cast<int8_t>(dlist[px][tx]);
-          }
-  }
+  p.n_phases = tgeo.n_phases;
+  p.taps = tgeo.taps;
+  static_assert(sizeof(p.tap_dy) == sizeof(tgeo.tap_dy) && sizeof(p.tap_dx) == sizeof(tgeo.tap_dx), "tap tables");
+  std::memcpy(p.tap_dy, tgeo.tap_dy, sizeof(p.tap_dy));
+  std::memcpy(p.tap_dx, tgeo.tap_dx, sizeof(p.tap_dx));
   p.k_chunks = static_cast<int32_t>(d->cin / bk);
   p.n_tiles = static_cast<int32_t>(d->cout / bn);
 
   // ---- main-loop variant and pipeline shape
   const bool halo = mode >= 1 && d->kind != SNB_CONV_1X1;
-  if ((valid || grid_pad || has_res) && !halo && d->kind != SNB_CONV_1X1) {
+  if ((valid != 0 || grid_pad || has_res) && !halo && d->kind != SNB_CONV_1X1) {
     delete c;
     return fail(SNB_E_UNSUPPORTED, "this layer shape needs halo mode (SNB_CONV_MODE >= 1)");
   }
@@ -1155,8 +1180,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (c->cluster == 2) c->grid &= ~1;   // whole CTA pairs; total_tiles is even
   // 2*MACs with the true tap counts (ConvT: every input pixel meets all 16 taps once over the 4 phases)
   // (k3 s2 p0 cropped: 9 real taps per input pixel, the other 7 slots hold zero weights)
-  c->flops = is_convt ? 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * (is_convt3 ? 9.0 : 16.0)
-                      : 2.0 * (double)d->n * out_h * out_w * (double)d->cin * d->cout * (double)p.taps;
+  c->flops = is_convt ? 2.0 * (double)d->n * d->h * d->w * (double)d->cin * d->cout * tgeo.flop_taps
+                      : 2.0 * (double)d->n * out_h * out_w * (double)d->cin * d->cout * tgeo.flop_taps;
   *out = c;
   return SNB_OK;
 }

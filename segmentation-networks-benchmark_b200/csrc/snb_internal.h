@@ -8,6 +8,8 @@
 
 #include "../../include/snb_b200.h"
 
+struct CUtensorMap_st;
+
 namespace snb {
 
 // thread-local last-error buffer; returns `code` so call sites can `return fail(...)`
@@ -39,6 +41,24 @@ struct SlicerGeom {
 };
 
 int sm_count();
+
+// Tap geometry of a convolution kind (shared by the forward kernels, conv_tcgen05.cu, and the weight-gradient kernel,
+// conv_wgrad.cu): tile grid (where accumulators are computed), output extent, tap offsets per phase and the offset added
+// to the halo-box origin.  `valid`: conv3x3 0 = padding 1, 1 = no padding ((h-2) x (w-2) outputs), 2 = "full" ((h+2) x
+// (w+2) outputs: the input gradient of a valid conv3x3); conv2x2 / conv2x2-adjoint: 1 = one output less per axis.
+struct ConvTapGeom {
+  int n_phases, taps;
+  int8_t tap_dy[4][9], tap_dx[4][9];
+  int load_off;
+  int64_t grid_h, grid_w, out_h, out_w;
+  double flop_taps;      // real taps per grid pixel summed over the phases (FLOP accounting)
+};
+int conv_tap_geometry(int kind, int valid, int64_t h, int64_t w, ConvTapGeom* out);
+
+// cuTensorMapEncodeTiled wrapper (conv_tcgen05.cu): bf16 / fp32 map over up to 4 dims, strides in bytes for dims 1..rank-1
+int encode_map(CUtensorMap_st* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+               int swizzle_bytes, int elem_bytes);
+
 bool configured_on_this_device(unsigned long long* mask);
 void mark_configured_on_this_device(unsigned long long* mask);
 

@@ -25,7 +25,10 @@ def round_tf32(t):
 
 
 def to_storage(t, dtype):
-    """Weights in their device storage type: bf16, or fp32 rounded to TF32 for the TF32 ("fp32 mode") path."""
+    """Weights in their device storage type: bf16, or fp32 rounded to TF32 for the TF32 ("fp32 mode") path; float64 keeps the
+    values exactly (index maps and expected gradients in the packed layout)."""
+    if dtype == torch.float64:
+        return t.detach().double()
     return round_tf32(t) if dtype == torch.float32 else t.detach().to(torch.bfloat16)
 
 
@@ -126,7 +129,7 @@ class ConvOp:
             d.d_head_out = head_out.data_ptr()
         d.out_upsample2x = 1 if upsample2x else 0
         d.act_slope = float(act_slope)
-        d.valid = 1 if valid else 0
+        d.valid = int(valid)          # 0 / False = padded, 1 / True = valid, 2 = full (conv3x3)
         if residual is not None:
             d.d_residual, d.res_cstride = residual.ptr, residual.cstride
             d.res_after_act = 1 if res_after_act else 0
@@ -151,6 +154,40 @@ class ConvOp:
         if h is not None and h.value:
             try:
                 N.lib().snb_conv_destroy(h)
+            except Exception:
+                pass
+
+
+class WgradOp:
+    """One snb_wgrad handle: dw[phase * taps + tap][co][ci] += sum_pixels dout[pixel][co] * src[pixel + tap][ci] on the
+    tensor cores (csrc/conv_wgrad.cu), in the packed layout of the forward weights.  `src` / `dout` are the forward
+    conv's input view and the gradient of its output; `dw` a float tensor [T][>= cout][>= cin] the caller zeroes."""
+
+    def __init__(self, kind, src, dout, dw, valid=0, cin=None, cout=None):
+        self.keep = (src, dout, dw)
+        d = N.WgradDesc()
+        d.kind, d.valid = kind, int(valid)
+        d.n, d.h, d.w = src.slab.n, src.slab.h, src.slab.w
+        d.cin, d.in_cstride = (src.c if cin is None else cin), src.cstride
+        d.cout, d.dout_cstride = (dout.c if cout is None else cout), dout.cstride
+        d.d_in, d.d_dout = src.ptr, dout.ptr
+        if dw.dtype != torch.float32 or dw.dim() != 3 or not dw.is_contiguous():
+            raise ValueError("dw must be a contiguous float tensor [taps][cout][cin]")
+        d.d_dweight = dw.data_ptr()
+        d.dw_cout, d.dw_cin = dw.shape[1], dw.shape[2]
+        self._h = ctypes.c_void_p()
+        N.check(N.lib().snb_wgrad_create(ctypes.byref(d), ctypes.byref(self._h)))
+        self.flops = N.lib().snb_wgrad_flops(self._h)
+        self.launches = 1
+
+    def __call__(self, stream):
+        N.check(N.lib().snb_wgrad_launch(self._h, stream))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().snb_wgrad_destroy(h)
             except Exception:
                 pass
 
@@ -367,7 +404,7 @@ class ZFUNetPlan:
 _CONVT3_K = ((0, 2), (1, None))
 
 
-def pack_convT3x3(weight, cin_pad, cout_pad):
+def pack_convT3x3(weight, cin_pad, cout_pad, dtype=torch.bfloat16):
     """nn.ConvTranspose2d(k=3, s=2, p=0) weight [Cin, Cout, 3, 3] -> bf16 [16 tap slots][cout_pad][cin_pad]."""
     cin, cout = weight.shape[:2]
     w = weight.detach().float()
@@ -381,7 +418,7 @@ def pack_convT3x3(weight, cin_pad, cout_pad):
                     if ky is not None and kx is not None:
                         out[i, :cout, :cin] = w[:, :, ky, kx].t()
                     i += 1
-    return out.to(torch.bfloat16).contiguous()
+    return to_storage(out, dtype).contiguous()
 
 
 def pad_conv_weight(weight, cin_map, cin_pad, cout_pad):
@@ -607,8 +644,77 @@ def pack_stem7x7(weight, k_pad, dtype=torch.bfloat16):
     return to_storage(out, dtype).contiguous()
 
 
+# ---- input-gradient operands: every dgrad of LinkNet34 is one of the FORWARD kernels on transformed weights --------------
+def pack_conv_dgrad(weight, cin_pad=None, cout_pad=None, dtype=torch.bfloat16):
+    """Stride-1 conv3x3 (padding 1, or none: run the adjoint with valid=2) / conv1x1 [Cout, Cin, k, k]: the adjoint is the
+    same convolution with the taps flipped and Cin / Cout swapped -> [k*k][cin_pad][cout_pad]."""
+    cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    wt = _pad_mat(weight.detach().double(), cout_pad or cout, cin_pad or cin).flip(2, 3).transpose(0, 1).contiguous()
+    return pack_conv3x3(wt, dtype) if k == 3 else pack_conv1x1(wt, dtype)
+
+
+def pack_conv3x3_s2_dgrad(weight, dtype=torch.bfloat16):
+    """Stride-2 conv3x3 (padding 1) [Cout, Cin, 3, 3]: its input gradient in space-to-depth form is a 4-tap convolution with
+    taps {0,+1}^2 (SNB_CONV_2X2_ADJ) from Cout to 4 * Cin channels: [4][4 * Cin][Cout] = pack_conv3x3_s2 with the taps
+    reversed and transposed; snb_depth_to_space2 then restores the pixel grid."""
+    return to_storage(pack_conv3x3_s2(weight, torch.float64).flip(0).transpose(1, 2), dtype).contiguous()
+
+
+_CONVT_D4 = ((0, -1), (1, 0))      # ConvTranspose k4 s2 p1: input row offset per (phase parity, tap), csrc tap tables
+_CONVT_D3 = ((0, -1), (0, 0))      # ConvTranspose k3 s2 p0
+
+
+def pack_convT4x4_dgrad(weight, cin_pad=None, cout_pad=None, dtype=torch.bfloat16):
+    """nn.ConvTranspose2d(k=4, s=2, p=1) [Cin, Cout, 4, 4]: input gradient = conv3x3 (padding 1) over the space-to-depth
+    copy of the output gradient (4 * cout_pad channels, block = sub-pixel phase) -> [9][cin_pad][4 * cout_pad]; 16 of the
+    36 (tap, phase) blocks are non-zero."""
+    cin, cout = weight.shape[:2]
+    cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
+    w = weight.detach().double()
+    out = torch.zeros((9, cin_pad, 4 * cout_pad), dtype=torch.float64, device=weight.device)
+    for py in range(2):
+        for px in range(2):
+            ph = py * 2 + px
+            for ty in range(2):
+                for tx in range(2):
+                    dy, dx = -_CONVT_D4[py][ty], -_CONVT_D4[px][tx]          # the gradient reads dOut4[r - d]
+                    tap = (dy + 1) * 3 + (dx + 1)
+                    out[tap, :cin, ph * cout_pad:ph * cout_pad + cout] += w[:, :, _CONVT_K[py][ty], _CONVT_K[px][tx]]
+    return to_storage(out, dtype).contiguous()
+
+
+def pack_convT3x3_full_dgrad(weight, cin_pad=None, cout_pad=None, dtype=torch.bfloat16):
+    """nn.ConvTranspose2d(k=3, s=2, p=0) uncropped [Cin, Cout, 3, 3] (output 2h+1): input gradient = 4-tap convolution with
+    taps {0,+1}^2 (SNB_CONV_2X2_ADJ, valid) over the space-to-depth copy of the output gradient (h+1 blocks of
+    4 * cout_pad channels) -> [4][cin_pad][4 * cout_pad]."""
+    cin, cout = weight.shape[:2]
+    cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
+    w = weight.detach().double()
+    out = torch.zeros((4, cin_pad, 4 * cout_pad), dtype=torch.float64, device=weight.device)
+    for py in range(2):
+        for px in range(2):
+            ph = py * 2 + px
+            for ty in range(2):
+                for tx in range(2):
+                    ky, kx = _CONVT3_K[py][ty], _CONVT3_K[px][tx]
+                    if ky is None or kx is None:
+                        continue
+                    sy, sx = -_CONVT_D3[py][ty], -_CONVT_D3[px][tx]
+                    out[sy * 2 + sx, :cin, ph * cout_pad:ph * cout_pad + cout] += w[:, :, ky, kx]
+    return to_storage(out, dtype).contiguous()
+
+
+def pack_conv2x2_dgrad(weight, cin_pad=None, cout_pad=None, dtype=torch.bfloat16):
+    """nn.Conv2d(k=2, padding=1) [Cout, Cin, 2, 2]: input gradient = 4-tap convolution with taps {0,+1}^2 (valid) and the
+    kernel reversed -> [4][cin_pad][cout_pad]."""
+    cout, cin = weight.shape[:2]
+    w = _pad_mat(weight.detach().double(), cout_pad or cout, cin_pad or cin)
+    return to_storage(w.flip(2, 3).permute(2, 3, 1, 0).reshape(4, w.shape[1], w.shape[0]), dtype).contiguous()
+
+
 def _pad_mat(w, cout_pad, cin_pad):
-    out = torch.zeros((cout_pad, cin_pad) + tuple(w.shape[2:]), dtype=torch.float32, device=w.device)
+    out = torch.zeros((cout_pad, cin_pad) + tuple(w.shape[2:]), dtype=w.dtype if w.dtype == torch.float64 else torch.float32,
+                      device=w.device)
     out[:w.shape[0], :w.shape[1]] = w
     return out
 
