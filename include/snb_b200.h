@@ -108,6 +108,13 @@ SNB_API int snb_nchw_f32_to_patch32(const float* d_src, int64_t n, int64_t chann
 #define SNB_DT_I64 3
 SNB_API int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
               const double* d_weight, void* d_out, int out_dtype, uint8_t* d_mask, float thr, void* stream);
+/* The same merge restricted to the image rows [row_begin, row_begin + row_count): only those rows of d_out / d_mask (still
+ * full-image buffers) are written, and only the tiles of the crop rows covering them are read.  This is the per-rank step
+ * of the tile-sharded multi-GPU mode: a rank merges the band of rows it owns from its own tiles plus the seam
+ * tiles its neighbours sent, in crop order, so the bytes equal the single-GPU merge. */
+SNB_API int snb_merge_rows(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
+                   const double* d_weight, void* d_out, int out_dtype, uint8_t* d_mask, float thr, int64_t row_begin,
+                   int64_t row_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------ convolutions */
 /* Activations are NHWC bf16 inside channel slabs: pixel stride = *_cstride channels, so a producer can write

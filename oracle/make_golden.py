@@ -362,6 +362,42 @@ def linknet34_vectors():
                 logit_min=float(y.min()), logit_max=float(y.max()))
 
 
+def linknet34_dropout_vectors():
+    """The reference LinkNet34 in train() mode with its default Dropout2d(p=0.5) ACTIVE (lib/models/linknet.py:57,83): the
+    keep mask torch drew is captured with a forward hook on `finaldrop1`, so a restatement given the same mask must
+    reproduce the logits -> tests/golden/linknet34_dropout.npz."""
+    import lib.modules.abn.bn as ref_bn
+    from lib.modules.abn.functions import InPlaceABN as RefABN
+
+    class Ctx:
+        def mark_dirty(self, *t):
+            pass
+
+        def save_for_backward(self, *t):
+            self.saved_tensors = t
+
+    m = LinkNet34(pretrained=False)
+    m.load_state_dict(synth.linknet34_state_dict(seed=6), strict=True)
+    orig = ref_bn.inplace_abn
+    ref_bn.inplace_abn = lambda *a: RefABN.forward(Ctx(), *a)
+    m.train()
+    assert m.finaldrop1.p == 0.5
+    seen = {}
+    hook = m.finaldrop1.register_forward_hook(
+        lambda mod, inp, out: seen.update(keep=(out.detach().abs().sum(dim=(2, 3)) > 0), inp=inp[0].detach().clone(), out=out.detach().clone()))
+    xt = torch.from_numpy(np.random.RandomState(16).standard_normal((4, 3, 64, 64)).astype(np.float32))
+    torch.manual_seed(123)
+    with torch.no_grad():
+        yt = m(xt).numpy()
+    hook.remove()
+    ref_bn.inplace_abn = orig
+    keep = seen["keep"]
+    # Dropout2d semantics: kept channels are scaled by 1 / (1 - p), dropped ones are zero
+    assert torch.allclose(seen["out"], seen["inp"] * (keep.float() * 2.0).view(4, 64, 1, 1))
+    assert 0.3 < keep.float().mean().item() < 0.7
+    np.savez_compressed(os.path.join(OUT, "linknet34_dropout.npz"), train_x=xt.numpy(), keep=keep.numpy(), train_logits=yt)
+
+
 def inplace_abn_vectors():
     """lib.modules.abn.functions.InPlaceABN (the reference's own autograd glue: running-statistics update, saved tensors,
     eval-mode shortcut) driven through the pure-torch stand-in for the un-vendored backend: training and eval mode,
@@ -450,6 +486,7 @@ def main():
     model_vectors()
     predict_tiled_vector()
     loss_extra_vectors()
+    linknet34_dropout_vectors()
     with open(os.path.join(OUT, "kats.json"), "w") as fh:
         json.dump(kats, fh, indent=1)
     for f in sorted(os.listdir(OUT)):

@@ -240,9 +240,11 @@ def inplace_abn_backward(z, dz, var, weight, bias, training=True, eps=1e-5, acti
 
 
 
-def linknet34_forward_train(sd, x, quant=None, linear=False):
-    """LinkNet34.forward in train() mode with Dropout2d inactive (lib/models/linknet.py:65-90): every BatchNorm2d /
-    InPlaceABN normalises with batch statistics and updates its running statistics (momentum 0.1, unbiased variance).
+def linknet34_forward_train(sd, x, quant=None, linear=False, keep=None, drop_p=0.5):
+    """LinkNet34.forward in train() mode (lib/models/linknet.py:65-90): every BatchNorm2d / InPlaceABN normalises with
+    batch statistics and updates its running statistics (momentum 0.1, unbiased variance).  `keep` = the Dropout2d keep
+    mask [N, 64] of finaldrop1 (:57,83: whole channels of decoder1's output are zeroed, the rest scaled by 1 / (1 - p));
+    None = dropout inactive.
     Returns (logits, {buffer name: updated value}); `sd` is not modified.  linear=True drops every ReLU / leaky-ReLU (a
     test mode: without activation gates the gradients are not chaotic under bf16 rounding, so the whole backward graph
     can be compared tightly)."""
@@ -292,6 +294,8 @@ def linknet34_forward_train(sd, x, quant=None, linear=False):
     d3 = q(decoder(d4, 'decoder3') + e2)
     d2 = q(decoder(d3, 'decoder2') + e1)
     d1 = q(decoder(d2, 'decoder1'))
+    if keep is not None:
+        d1 = q(d1 * (keep.to(d1.dtype) / (1.0 - drop_p)).view(d1.shape[0], 64, 1, 1))
     f = leaky(F.conv_transpose2d(d1, q(sd['finaldeconv1.weight']), sd['finaldeconv1.bias'], stride=2), 0.01)
     f = leaky(conv(q(f), 'finalconv2'), 0.01)
     return conv(q(f), 'finalconv3', padding=1), new

@@ -90,6 +90,7 @@ SIGNATURES = {
     "snb_split_norm_u8": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp]),
     "snb_nchw_f32_to_patch32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
     "snb_merge": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_float, c_vp]),
+    "snb_merge_rows": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_float, c_i64, c_i64, c_vp]),
     "snb_conv_create": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
     "snb_conv_launch": (c_int, [c_vp, c_vp]),
     "snb_conv_destroy": (None, [c_vp]),

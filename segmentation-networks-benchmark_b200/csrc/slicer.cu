@@ -329,11 +329,12 @@ __device__ __forceinline__ double tile_value(const void* __restrict__ tiles, int
 template <int TILE_DT, int TTA, int VEC>
 __global__ void __launch_bounds__(256) merge_kernel(SlicerGeom g, const void* __restrict__ tiles, int C,
                                                     const double* __restrict__ weight, void* __restrict__ out,
-                                                    int out_dtype, uint8_t* __restrict__ mask, float thr) {
+                                                    int out_dtype, uint8_t* __restrict__ mask, float thr, int row0) {
   const int T = (int)g.tile, S = (int)g.step;
   const int WC = (int)g.image_w * C;
   const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y;
-  const int Y = blockIdx.y + (int)g.margin_top;              // padded-canvas row
+  const int y_img = blockIdx.y + row0;                       // image row (row0 = first row of the band being merged)
+  const int Y = y_img + (int)g.margin_top;                   // padded-canvas row
   // crops covering row Y: iy*S <= Y < iy*S + T
   const int iy0 = Y - T + 1 <= 0 ? 0 : (Y - T + S) / S;
   const int iy1 = min(Y / S, tiles_y - 1);
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(256) merge_kernel(SlicerGeom g, const void* __
       qd[e] = __ddiv_rn(acc, norm);
       qf[e] = __double2float_rn(qd[e]);
     }
-    const int64_t i = (int64_t)blockIdx.y * WC + xc0;
+    const int64_t i = (int64_t)y_img * WC + xc0;
     if (VEC == 4 && xc0 + 3 < WC) {   // WC % 4 == 0 and 16-byte aligned rows are guaranteed by the launcher for VEC == 4
       if (out) {
         if (out_dtype == SNB_DT_F32) *reinterpret_cast<float4*>(static_cast<float*>(out) + i) = make_float4(qf[0], qf[1], qf[2], qf[3]);
@@ -403,10 +404,11 @@ __global__ void __launch_bounds__(256) merge_kernel(SlicerGeom g, const void* __
 __global__ void __launch_bounds__(256) merge_f32c1_vec4_kernel(SlicerGeom g, const float* __restrict__ tiles,
                                                                const double* __restrict__ weight,
                                                                float* __restrict__ out, uint8_t* __restrict__ mask,
-                                                               float thr) {
+                                                               float thr, int row0) {
   const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w;
   const int tiles_x = (int)g.tiles_x, tiles_y = (int)g.tiles_y;
-  const int Y = blockIdx.y + (int)g.margin_top;
+  const int y_img = blockIdx.y + row0;
+  const int Y = y_img + (int)g.margin_top;
   const int iy0 = Y - T + 1 <= 0 ? 0 : (Y - T + S) / S;
   const int iy1 = min(Y / S, tiles_y - 1);
   for (int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; x0 < W; x0 += gridDim.x * blockDim.x * 4) {
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(256) merge_f32c1_vec4_kernel(SlicerGeom g, con
       const double nrm = norm[e] < DBL_EPSILON ? DBL_EPSILON : norm[e];
       q[e] = __double2float_rn(__ddiv_rn(acc[e], nrm));
     }
-    const int64_t i = (int64_t)blockIdx.y * W + x0;
+    const int64_t i = (int64_t)y_img * W + x0;
     if (out) *reinterpret_cast<float4*>(out + i) = make_float4(q[0], q[1], q[2], q[3]);
     if (mask)
       *reinterpret_cast<uchar4*>(mask + i) =
@@ -781,13 +783,14 @@ template <int PX> constexpr int kStagedMinBlocks = PX == 2 ? 3 : 1;
 template <int PX, bool HAS_OUT, bool HAS_MASK>
 __global__ void __launch_bounds__(kStagedThreads<PX>, kStagedMinBlocks<PX>) merge_f32c1_staged_kernel(
     SlicerGeom g, const float* __restrict__ tiles, const double* __restrict__ weight, float* __restrict__ out,
-    uint8_t* __restrict__ mask, float thr, int xs, int kp) {
+    uint8_t* __restrict__ mask, float thr, int xs, int kp, int row0) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int T = (int)g.tile, S = (int)g.step, W = (int)g.image_w;
   const int tiles_x = (int)g.tiles_x, ml = (int)g.margin_left;
   uint64_t* bar = reinterpret_cast<uint64_t*>(merge_smem);
   float* st0 = reinterpret_cast<float*>(merge_smem + 16);
-  const int y = blockIdx.x / xs, seg = blockIdx.x - y * xs;
+  const int yb = blockIdx.x / xs, seg = blockIdx.x - yb * xs;
+  const int y = yb + row0;                                     // image row (row0 = first row of the band being merged)
   // periods [k0, k1] of this segment need crops [k0 - 1, k1] clipped to the crop grid
   const int k0 = seg * kp, k1 = min(k0 + kp - 1, tiles_x);
   const int ix0 = max(k0 - 1, 0), nx = min(k1, tiles_x - 1) - ix0 + 1, nx_max = min(kp + 1, tiles_x);
@@ -898,7 +901,7 @@ static bool launch_merge_ring(const SlicerGeom& g, const float* tiles, const dou
 
 template <int PX, bool HAS_OUT, bool HAS_MASK>
 static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const double* weight, float* out, uint8_t* mask,
-                                float thr, cudaStream_t st) {
+                                float thr, cudaStream_t st, int row0, int rows) {
   const int threads = (int)((g.step / PX + 31) / 32 * 32);
   if (g.step % PX || threads > kStagedThreads<PX>) return false;
   // A CTA walks `kp` periods of one row (xs segments per row).  Measured on B200 (tools/merge_bench.py): ~10-14 periods
@@ -911,7 +914,7 @@ static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const d
   while (kp > 1 && 16 + 2 * std::min(kp + 1, g.tiles_x) * g.tile * 4 > 100 * 1024) --kp;   // >= 2 CTAs per SM
   xs = (periods + kp - 1) / kp;
   const size_t smem = 16 + 2 * (size_t)(std::min(kp + 1, g.tiles_x) * g.tile * 4);
-  if (smem > 227 * 1024 || g.image_h * xs > INT32_MAX) return false;
+  if (smem > 227 * 1024 || rows * xs > INT32_MAX) return false;
   static unsigned long long configured = 0;     // per device ordinal
   if (!configured_on_this_device(&configured)) {
     if (cudaFuncSetAttribute(merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -919,23 +922,23 @@ static bool launch_merge_staged(const SlicerGeom& g, const float* tiles, const d
       return false;
     mark_configured_on_this_device(&configured);
   }
-  merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK><<<(unsigned)(g.image_h * xs), threads, smem, st>>>(
-      g, tiles, weight, out, mask, thr, (int)xs, (int)kp);
+  merge_f32c1_staged_kernel<PX, HAS_OUT, HAS_MASK><<<(unsigned)(rows * xs), threads, smem, st>>>(
+      g, tiles, weight, out, mask, thr, (int)xs, (int)kp, row0);
   return true;
 }
 
 // mode: 's' = CTA per row, 'r' = persistent ring; px = pixels per thread
 template <bool HAS_OUT, bool HAS_MASK>
 static bool launch_merge_periodic(char mode, int px, const SlicerGeom& g, const float* tiles, const double* weight,
-                                  float* out, uint8_t* mask, float thr, cudaStream_t st) {
-  if (mode == 'r') {
+                                  float* out, uint8_t* mask, float thr, cudaStream_t st, int row0, int rows) {
+  if (mode == 'r' && row0 == 0 && rows == (int)g.image_h) {     // the persistent ring walks whole images only
     if (px == 1) return launch_merge_ring<1, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
     if (px == 2) return launch_merge_ring<2, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
     return launch_merge_ring<4, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
   }
-  if (px == 1) return launch_merge_staged<1, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
-  if (px == 2) return launch_merge_staged<2, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
-  return launch_merge_staged<4, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st);
+  if (px == 1) return launch_merge_staged<1, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st, row0, rows);
+  if (px == 2) return launch_merge_staged<2, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st, row0, rows);
+  return launch_merge_staged<4, HAS_OUT, HAS_MASK>(g, tiles, weight, out, mask, thr, st, row0, rows);
 }
 
 static int grid_for(int64_t total, int block) {
@@ -1113,23 +1116,38 @@ extern "C" int snb_nchw_f32_to_patch32(const float* d_src, int64_t n, int64_t ch
 
 template <int TILE_DT, int TTA>
 static void launch_merge(const snb_slicer* s, const void* d_tiles, int C, const double* d_weight, void* d_out,
-                         int out_dtype, uint8_t* d_mask, float thr, cudaStream_t st) {
+                         int out_dtype, uint8_t* d_mask, float thr, cudaStream_t st, int row0, int rows) {
   const int64_t wc = s->g.image_w * C;
   // vector path: every row starts 16-byte aligned in all outputs
   const bool vec = wc % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0;
   if (vec) {
-    const dim3 grid((unsigned)std::min<int64_t>((wc / 4 + 255) / 256, 1024), (unsigned)s->g.image_h);
-    merge_kernel<TILE_DT, TTA, 4><<<grid, 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr);
+    const dim3 grid((unsigned)std::min<int64_t>((wc / 4 + 255) / 256, 1024), (unsigned)rows);
+    merge_kernel<TILE_DT, TTA, 4><<<grid, 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, row0);
   } else {
-    const dim3 grid((unsigned)std::min<int64_t>((wc + 255) / 256, 1024), (unsigned)s->g.image_h);
-    merge_kernel<TILE_DT, TTA, 1><<<grid, 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr);
+    const dim3 grid((unsigned)std::min<int64_t>((wc + 255) / 256, 1024), (unsigned)rows);
+    merge_kernel<TILE_DT, TTA, 1><<<grid, 256, 0, st>>>(s->g, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, row0);
   }
 }
+
+extern "C" int snb_merge_rows(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
+                              const double* d_weight, void* d_out, int out_dtype, uint8_t* d_mask, float thr,
+                              int64_t row_begin, int64_t row_count, void* stream);
 
 extern "C" int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
                          const double* d_weight, void* d_out, int out_dtype, uint8_t* d_mask, float thr,
                          void* stream) {
+  if (!s) return fail(SNB_E_INVALID, "snb_merge: null argument");
+  return snb_merge_rows(s, d_tiles, tile_dtype, channels, tta, d_weight, d_out, out_dtype, d_mask, thr, 0, s->g.image_h, stream);
+}
+
+extern "C" int snb_merge_rows(const snb_slicer* s, const void* d_tiles, int tile_dtype, int64_t channels, int tta,
+                              const double* d_weight, void* d_out, int out_dtype, uint8_t* d_mask, float thr,
+                              int64_t row_begin, int64_t row_count, void* stream) {
   if (!s || !d_tiles || !d_weight) return fail(SNB_E_INVALID, "snb_merge: null argument");
+  if (row_begin < 0 || row_count < 0 || row_begin + row_count > s->g.image_h)
+    return fail(SNB_E_INVALID, "rows [%lld, %lld) outside the image", (long long)row_begin, (long long)(row_begin + row_count));
+  if (row_count == 0) return SNB_OK;
+  const int row0 = (int)row_begin, rows = (int)row_count;
   if (!d_out && !d_mask) return fail(SNB_E_INVALID, "snb_merge: no output requested");
   if (channels < 1 || channels > 64) return fail(SNB_E_INVALID, "channels=%lld unsupported", (long long)channels);
   if (tta != 1 && tta != 8) return fail(SNB_E_INVALID, "tta must be 1 or 8");
@@ -1156,23 +1174,23 @@ extern "C" int snb_merge(const snb_slicer* s, const void* d_tiles, int tile_dtyp
       const char mode = mm[0];
       const int px = mm.back() - '0';
       if (px == 1 || px == 2 || px == 4) {
-        if (op && d_mask) done = launch_merge_periodic<true, true>(mode, px, g, tp, d_weight, op, d_mask, thr, st);
-        else if (op) done = launch_merge_periodic<true, false>(mode, px, g, tp, d_weight, op, d_mask, thr, st);
-        else done = launch_merge_periodic<false, true>(mode, px, g, tp, d_weight, op, d_mask, thr, st);
+        if (op && d_mask) done = launch_merge_periodic<true, true>(mode, px, g, tp, d_weight, op, d_mask, thr, st, row0, rows);
+        else if (op) done = launch_merge_periodic<true, false>(mode, px, g, tp, d_weight, op, d_mask, thr, st, row0, rows);
+        else done = launch_merge_periodic<false, true>(mode, px, g, tp, d_weight, op, d_mask, thr, st, row0, rows);
       }
     }
     if (!done) {
-      const dim3 grid((unsigned)std::min<int64_t>((g.image_w / 4 + 255) / 256, 1024), (unsigned)g.image_h);
+      const dim3 grid((unsigned)std::min<int64_t>((g.image_w / 4 + 255) / 256, 1024), (unsigned)rows);
       merge_f32c1_vec4_kernel<<<grid, 256, 0, st>>>(g, static_cast<const float*>(d_tiles), d_weight,
-                                                    static_cast<float*>(d_out), d_mask, thr);
+                                                    static_cast<float*>(d_out), d_mask, thr, row0);
     }
     SNB_LAUNCH_CHECK();
     return SNB_OK;
   }
-  if (tta == 8) launch_merge<SNB_DT_F32, 8>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);
-  else if (tile_dtype == SNB_DT_F32) launch_merge<SNB_DT_F32, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);
-  else if (tile_dtype == SNB_DT_U8) launch_merge<SNB_DT_U8, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);
-  else if (tile_dtype == SNB_DT_F64) launch_merge<SNB_DT_F64, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st);
+  if (tta == 8) launch_merge<SNB_DT_F32, 8>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st, row0, rows);
+  else if (tile_dtype == SNB_DT_F32) launch_merge<SNB_DT_F32, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st, row0, rows);
+  else if (tile_dtype == SNB_DT_U8) launch_merge<SNB_DT_U8, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st, row0, rows);
+  else if (tile_dtype == SNB_DT_F64) launch_merge<SNB_DT_F64, 1>(s, d_tiles, C, d_weight, d_out, out_dtype, d_mask, thr, st, row0, rows);
   else return fail(SNB_E_INVALID, "tile_dtype %d unsupported", tile_dtype);
   SNB_LAUNCH_CHECK();
   return SNB_OK;

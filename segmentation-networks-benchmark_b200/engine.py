@@ -24,6 +24,13 @@ def round_tf32(t):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def _f(t):
+    """detached float32 copy of a parameter, or the float64 tensor itself (index maps are pushed through the pack functions
+    as float64 so that every element keeps its identity)."""
+    t = t.detach()
+    return t if t.dtype == torch.float64 else t.float()
+
+
 def to_storage(t, dtype):
     """Weights in their device storage type: bf16, or fp32 rounded to TF32 for the TF32 ("fp32 mode") path; float64 keeps the
     values exactly (index maps and expected gradients in the packed layout)."""
@@ -103,7 +110,7 @@ class ConvOp:
     """One snb_conv handle; keeps every tensor it points at alive."""
 
     def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False, pre=None,
-                 act_slope=0.0, residual=None, res_after_act=False, valid=False):
+                 act_slope=0.0, residual=None, res_after_act=False, valid=False, real=None):
         self.keep = (src, dst, weight, bias, head, pool_dst, pre, residual)
         d = N.ConvDesc()
         d.kind = kind
@@ -144,6 +151,9 @@ class ConvOp:
         self._h = ctypes.c_void_p()
         N.check(N.lib().snb_conv_create(ctypes.byref(d), ctypes.byref(self._h)))
         self.flops = N.lib().snb_conv_flops(self._h)
+        if real is not None:
+            # algorithmic FLOPs: zero-padded channels do not count; real = (K actually contracted, real Cout)
+            self.flops *= (real[0] / float(d.cin)) * (real[1] / float(d.cout))
         self.launches = 1
 
     def __call__(self, stream):
@@ -282,7 +292,7 @@ class VGGUNetPlan:
                 pooled = S(hh // 2, ww // 2, cout).view() if last else None
                 fuse = pooled is not None and fuse_pool and not (s == 0 and li == 0)
                 if s == 0 and li == 0:
-                    self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt, dtype), f32(bs)))
+                    self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt, dtype), f32(bs), real=(9 * wt.shape[1], cout)))
                 else:
                     self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt, dtype), f32(bs),
                                            pool_dst=pooled if fuse else None))
@@ -305,6 +315,7 @@ class VGGUNetPlan:
         head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid,
                 self.out)
         self.ops.append(ConvOp(N.CONV_3X3, slabs[0].view(), None, pack_conv3x3(dec1[0], dtype), f32(dec1[1]), head=head))
+        self.ops[-1].flops += 2.0 * n * h * w * 32          # the fused 1x1 head (32 -> 1)
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
 
@@ -360,7 +371,8 @@ class ZFUNetPlan:
         def conv(src, dst, layer, first=False, **kw):
             wt, bs = fold_bn(*layer)
             if first:
-                self.ops.append(ConvOp(N.CONV_1X1, src, dst, pack_first_conv3x3(wt, dtype), bs.contiguous(), **kw))
+                self.ops.append(ConvOp(N.CONV_1X1, src, dst, pack_first_conv3x3(wt, dtype), bs.contiguous(),
+                                       real=(9 * wt.shape[1], wt.shape[0]), **kw))
             else:
                 self.ops.append(ConvOp(N.CONV_3X3, src, dst, pack_conv3x3(wt, dtype), bs.contiguous(), **kw))
 
@@ -391,6 +403,7 @@ class ZFUNetPlan:
         head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid,
                 self.out)
         self.ops.append(ConvOp(N.CONV_3X3, mid, None, pack_conv3x3(wt, dtype), bs.contiguous(), head=head))
+        self.ops[-1].flops += 2.0 * n * h * w * 32          # the fused 1x1 head (32 -> 1)
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
 
@@ -407,8 +420,8 @@ _CONVT3_K = ((0, 2), (1, None))
 def pack_convT3x3(weight, cin_pad, cout_pad, dtype=torch.bfloat16):
     """nn.ConvTranspose2d(k=3, s=2, p=0) weight [Cin, Cout, 3, 3] -> bf16 [16 tap slots][cout_pad][cin_pad]."""
     cin, cout = weight.shape[:2]
-    w = weight.detach().float()
-    out = torch.zeros((16, cout_pad, cin_pad), dtype=torch.float32, device=weight.device)
+    w = _f(weight)
+    out = torch.zeros((16, cout_pad, cin_pad), dtype=w.dtype, device=weight.device)
     i = 0
     for py in range(2):
         for px in range(2):
@@ -530,15 +543,17 @@ class FCDenseNetPlan:
                 w16 = pad_conv_weight(wt, cmap, cpad, 16)
                 self.ops.append(ScatterConvOp(slab.view(0, cpad), slab.view(out_off, 16), pack_conv3x3_scatter(w16),
                                               padded_bias(bs, 16), pre=(sc, sh)))
+                self.ops[-1].flops *= cin / float(cpad)
                 return
             if fuse_pre:
                 # BatchNorm+ReLU applied to the operand tiles inside the conv kernel: the slab is read once, in place
                 self.ops.append(ConvOp(N.CONV_3X3, slab.view(0, cpad), slab.view(out_off, 32), pack_conv3x3(wp),
-                                       padded_bias(bs, 32), relu=False, pre=(sc, sh)))
+                                       padded_bias(bs, 32), relu=False, pre=(sc, sh), real=(cin, wt.shape[0])))
                 return
             z = scratch[lvl].view(0, cpad)
             self.ops.append(BnReluOp(slab.view(0, cpad), z, sc, sh))
-            self.ops.append(ConvOp(N.CONV_3X3, z, slab.view(out_off, 32), pack_conv3x3(wp), padded_bias(bs, 32), relu=False))
+            self.ops.append(ConvOp(N.CONV_3X3, z, slab.view(out_off, 32), pack_conv3x3(wp), padded_bias(bs, 32), relu=False,
+                                   real=(cin, wt.shape[0])))
 
         # ---- first conv: 3 -> 48 (no activation), stored 64 wide
         self.x_patch = S(h, w, 32)
@@ -547,7 +562,7 @@ class FCDenseNetPlan:
         wfp = torch.zeros((cf_pad, wf.shape[1], 3, 3), dtype=torch.float32, device=dev)
         wfp[:c_first] = wf.detach().float()
         self.ops.append(ConvOp(N.CONV_1X1, self.x_patch.view(), slabs[0].view(0, cf_pad), pack_first_conv3x3(wfp),
-                               padded_bias(bf, cf_pad), relu=False))
+                               padded_bias(bf, cf_pad), relu=False, real=(9 * wf.shape[1], c_first)))
 
         # ---- down path
         ident = lambda k: torch.arange(k, device=dev)
@@ -564,7 +579,7 @@ class FCDenseNetPlan:
             self.ops.append(BnReluOp(slabs[l].view(0, cpad), z, sc, sh))
             tmp = S(h >> l, w >> l, cpad)
             wp = pad_conv_weight(wt, ident(cur), cpad, cpad)
-            self.ops.append(ConvOp(N.CONV_1X1, z, tmp.view(), pack_conv1x1(wp), padded_bias(bs, cpad), relu=False))
+            self.ops.append(ConvOp(N.CONV_1X1, z, tmp.view(), pack_conv1x1(wp), padded_bias(bs, cpad), relu=False, real=(cur, cur)))
             dst = (slabs[l + 1] if l + 1 < L else bott).view(0, cur)
             self.ops.append(PoolOp(tmp.view(0, cur), dst))
 
@@ -584,7 +599,7 @@ class FCDenseNetPlan:
             cu_pad = _pad32(cu)
             # TransitionUp: ConvTranspose2d(k3, s2) cropped to the skip size, written right after the skip channels
             self.ops.append(ConvOp(N.CONVT_3X3_S2, new_src, slabs[l].view(skip, cu_pad),
-                                   pack_convT3x3(wt, new_src.c, cu_pad), padded_bias(bs, cu_pad), relu=False))
+                                   pack_convT3x3(wt, new_src.c, cu_pad), padded_bias(bs, cu_pad), relu=False, real=(cu, cu)))
             # reference channel order of the block input is [up | skip | new...]; the slab holds [skip | up | new...]
             cur = skip + cu
             base_map = torch.cat([torch.arange(skip, skip + cu, device=dev), torch.arange(0, skip, device=dev)])
@@ -603,7 +618,7 @@ class FCDenseNetPlan:
         pick = torch.zeros(32, dtype=torch.float32, device=dev)
         pick[0] = 1.0
         self.ops.append(ConvOp(N.CONV_1X1, slabs[0].view(0, cpad), None, pack_conv1x1(wp), padded_bias(bs, 32), relu=False,
-                               head=(pick, 0.0, sigmoid, self.out)))
+                               head=(pick, 0.0, sigmoid, self.out), real=(last_cur, 1)))
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
 
@@ -618,8 +633,8 @@ def pack_conv3x3_s2(weight, dtype=torch.bfloat16):
     (py*2+px)*Cin + ci holds input pixel (2y'+py, 2x'+px).  Row 2y+ky-1 is (block y-1, py=1) for ky=0 and
     (block y, py=ky-1) for ky=1,2; unused (tap, parity) pairs stay zero."""
     cout, cin = weight.shape[:2]
-    w = weight.detach().float()
-    out = torch.zeros((4, cout, 4 * cin), dtype=torch.float32, device=weight.device)
+    w = _f(weight)
+    out = torch.zeros((4, cout, 4 * cin), dtype=w.dtype, device=weight.device)
     kmap = {(0, 1): 0, (1, 0): 1, (1, 1): 2}          # (tap index t, parity p) -> kernel index
     for (ty, py), ky in kmap.items():
         for (tx, px), kx in kmap.items():
@@ -631,16 +646,18 @@ def pack_conv3x3_s2(weight, dtype=torch.bfloat16):
 def pack_conv2x2(weight, cin_pad=None, cout_pad=None, dtype=torch.bfloat16):
     """nn.Conv2d(k=2, padding=1) weight [Cout, Cin, 2, 2] -> [4][cout_pad][cin_pad], tap = ky*2 + kx."""
     cout, cin = weight.shape[:2]
-    out = torch.zeros((4, cout_pad or cout, cin_pad or cin), dtype=torch.float32, device=weight.device)
-    out[:, :cout, :cin] = weight.detach().float().permute(2, 3, 0, 1).reshape(4, cout, cin)
+    w = _f(weight)
+    out = torch.zeros((4, cout_pad or cout, cin_pad or cin), dtype=w.dtype, device=weight.device)
+    out[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(4, cout, cin)
     return to_storage(out, dtype).contiguous()
 
 
 def pack_stem7x7(weight, k_pad, dtype=torch.bfloat16):
     """Stride-2 7x7 stem [Cout, C, 7, 7] -> [1][Cout][k_pad] matching snb_stem7x7_rows: k = (ky*7+kx)*C + c."""
     cout, cin = weight.shape[:2]
-    out = torch.zeros((1, cout, k_pad), dtype=torch.float32, device=weight.device)
-    out[0, :, :49 * cin] = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, 49 * cin)
+    w = _f(weight)
+    out = torch.zeros((1, cout, k_pad), dtype=w.dtype, device=weight.device)
+    out[0, :, :49 * cin] = w.permute(0, 2, 3, 1).reshape(cout, 49 * cin)
     return to_storage(out, dtype).contiguous()
 
 
@@ -779,7 +796,8 @@ class LinkNet34Plan:
                                                       N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K), (self.x_nchw, self.x_rows)))
         wt, bs = fold(spec['stem'][0], None, spec['stem'][1])
         stem = S(h2, w2, 64)
-        self.ops.append(ConvOp(N.CONV_1X1, self.x_rows.view(), stem.view(), pack_stem7x7(wt, self.STEM_K), bs.contiguous()))
+        self.ops.append(ConvOp(N.CONV_1X1, self.x_rows.view(), stem.view(), pack_stem7x7(wt, self.STEM_K), bs.contiguous(),
+                               real=(147, 64)))
         cur = S(h4, w4, 64)
         self.ops.append(SimpleOp("snb_maxpool3x3s2", (N.c_vp(stem.view().ptr), n, h2, w2, 64, 64, N.c_vp(cur.view().ptr), 64),
                                  (stem, cur)))
@@ -797,7 +815,8 @@ class LinkNet34Plan:
                                                                      N.c_vp(x4.view().ptr), 4 * ch), (cur, x4)))
                     w1, b1 = fold(blk['conv1'], None, blk['bn1'])
                     t = S(hh, ww, cout).view()
-                    self.ops.append(ConvOp(N.CONV_2X2, x4.view(), t, pack_conv3x3_s2(w1), b1.contiguous(), valid=True))
+                    self.ops.append(ConvOp(N.CONV_2X2, x4.view(), t, pack_conv3x3_s2(w1), b1.contiguous(), valid=True,
+                                           real=(4 * ch * 9 / 16.0, cout)))   # 9 of the 16 (tap, parity) blocks are real
                     wd, bd = fold(blk['down'][0], None, blk['down'][1])
                     ident = S(hh, ww, cout).view()
                     self.ops.append(ConvOp(N.CONV_1X1, x4.view(0, ch), ident, pack_conv1x1(wd), bd.contiguous(), relu=False))
@@ -818,14 +837,16 @@ class LinkNet34Plan:
             mp = p32(mid)
             w1, b1 = fold(spec_d['conv1'][0], spec_d['conv1'][1], spec_d['abn1'])
             a = S(hh, ww, mp).view()
-            self.ops.append(ConvOp(N.CONV_1X1, x, a, pack_conv1x1(_pad_mat(w1, mp, cin)), _pad_vec(b1, mp), act_slope=0.01))
+            self.ops.append(ConvOp(N.CONV_1X1, x, a, pack_conv1x1(_pad_mat(w1, mp, cin)), _pad_vec(b1, mp), act_slope=0.01,
+                                   real=(cin, mid)))
             w2_, b2 = fold(spec_d['deconv2'][0], spec_d['deconv2'][1], spec_d['abn2'], transposed=True)
             b_ = S(2 * hh, 2 * ww, mp).view()
-            self.ops.append(ConvOp(N.CONVT_4X4_S2, a, b_, pack_convT4x4(_pad_mat(w2_, mp, mp)), _pad_vec(b2, mp), act_slope=0.01))
+            self.ops.append(ConvOp(N.CONVT_4X4_S2, a, b_, pack_convT4x4(_pad_mat(w2_, mp, mp)), _pad_vec(b2, mp), act_slope=0.01,
+                                   real=(mid, mid)))
             w3, b3 = fold(spec_d['conv3'][0], spec_d['conv3'][1], spec_d['abn3'])
             y = S(2 * hh, 2 * ww, n_out).view()
             self.ops.append(ConvOp(N.CONV_1X1, b_, y, pack_conv1x1(_pad_mat(w3, n_out, mp)), b3.contiguous(), act_slope=0.01,
-                                   residual=skip, res_after_act=True))
+                                   residual=skip, res_after_act=True, real=(mid, n_out)))
             return y
 
         e1, e2, e3, e4 = skips
@@ -849,7 +870,7 @@ class LinkNet34Plan:
         pick = torch.zeros(32, dtype=torch.float32, device=device)
         pick[0] = 1.0
         self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, pack_conv2x2(wt, 32, 32), _pad_vec(bs.detach().float(), 32),
-                               relu=False, head=(pick, 0.0, sigmoid, self.out)))
+                               relu=False, head=(pick, 0.0, sigmoid, self.out), real=(32, 1)))
         self.flops = sum(op.flops for op in self.ops)
         self.launches = sum(op.launches for op in self.ops)
 
@@ -890,12 +911,26 @@ class BnTrainOp:
         self.work = torch.empty(2 * cpad, dtype=torch.float64, device=dev)
         self.keep = (src, dst, residual, weight, bias, rmean, rvar)
         self.pixels = src.slab.n * src.slab.h * src.slab.w
+        self._cfg = (cpad, abn, eps, momentum, slope, res_after_act)
+        self.rebind()
+        self.flops, self.launches = 0.0, 4
+
+    def rebind(self):
+        """(re)build the argument list after self.gamma / self.beta were pointed at other tensors"""
+        src, dst, residual = self.keep[:3]
+        cpad, abn, eps, momentum, slope, res_after_act = self._cfg
         self.args = (N.c_vp(src.ptr), self.pixels, cpad, src.cstride, N.ptr(self.gamma), N.ptr(self.beta), 1 if abn else 0,
                      float(eps), float(momentum), N.ptr(self.rmean), N.ptr(self.rvar), float(slope),
                      N.c_vp(residual.ptr if residual is not None else 0), residual.cstride if residual is not None else 0,
                      1 if res_after_act else 0, N.c_vp(dst.ptr), dst.cstride, N.ptr(self.scale), N.ptr(self.shift),
                      N.ptr(self.mean), N.ptr(self.var), N.ptr(self.work))
-        self.flops, self.launches = 0.0, 3
+
+    def refresh_stats(self):
+        """padded layers: re-read the module's running statistics (they are copied back after each run)"""
+        rmean, rvar = self.keep[5:7]
+        c = rmean.numel()
+        self.rmean[:c].copy_(rmean)
+        self.rvar[:c].copy_(rvar)
 
     def refresh(self):
         """padded layers keep copies of the parameters: re-read them (running statistics are copied back after each run)"""
@@ -910,293 +945,5 @@ class BnTrainOp:
         N.check(N.lib().snb_bn_train_nhwc(*self.args, stream))
         if self.padded:
             rmean, rvar, c = self.module_stats
-            rmean.copy_(self.rmean[:c])
-            rvar.copy_(self.rvar[:c])
-
-
-class LinkNet34TrainPlan:
-    """LinkNet34.forward in train() mode (lib/models/linknet.py:65-90): the same convolution kernels as LinkNet34Plan but
-    nothing is folded -- every BatchNorm2d / InPlaceABN runs on batch statistics (BnTrainOp), updates the module's running
-    statistics in place, and keeps the raw convolution output, mean and variance (what the backward pass will need).
-    Dropout2d must be inactive (p == 0: BASELINE configs[1] as specified in SURVEY 8d).  `model` is the LinkNet34 module."""
-
-    STEM_K = 160
-
-    def __init__(self, model, n, h, w, device, linear=False):
-        # linear=True (tests only): every ReLU / leaky-ReLU becomes the identity, so gradients can be compared tightly
-        if h % 32 or w % 32:
-            raise ValueError("height and width must be multiples of 32")
-        if model.finaldrop1.p != 0:
-            raise NotImplementedError("Dropout2d with p > 0 is not built for the training-mode forward (set finaldrop1.p = 0)")
-        if model.finalconv3.weight.shape[0] != 1:
-            raise NotImplementedError("fused head expects num_classes == 1")
-        self.n, self.h, self.w, self.device = n, h, w, device
-        self.ops, self.bn_modules, self.tape = [], [], []
-        self.model = model
-        self._repack = []     # (device tensor, function recomputing it from the module's current parameters)
-
-        def P(fn):
-            t = fn()
-            self._repack.append((t, fn))
-            return t
-
-        S = lambda hh, ww, c: Slab(n, hh, ww, c, device)
-        p32 = lambda c: (c + 31) // 32 * 32
-        zeros = lambda c: torch.zeros(c, dtype=torch.float32, device=device)
-        f32 = lambda t: t.detach().float().contiguous()
-        # SNB_TRAIN_TC_DGRAD=0 keeps the generic CUDA-core dgrad everywhere (A/B runs)
-        tc_dgrad = os.environ.get("SNB_TRAIN_TC_DGRAD", "1") != "0"
-
-        def bn_of(m):
-            return (m.weight, m.bias, m.running_mean, m.running_var, m.eps, m.momentum)
-
-        def conv_bn(kind, src, wpacked, bias, cout, hh, ww, m, abn, slope, residual=None, res_after_act=False, bwd=None, **kw):
-            """conv -> BatchNorm / ABN (batch statistics) -> activation (+ residual).  `bwd` = (conv module, input view of
-            the ORIGINAL geometry, stride, padding): what the backward pass differentiates (the forward may run the same
-            convolution on a space-to-depth copy or on im2col rows)."""
-            raw = S(hh, ww, cout).view()
-            self.ops.append(ConvOp(kind, src, raw, wpacked, bias, relu=False, **kw))
-            out = S(hh, ww, cout).view()
-            slope = -1.0 if linear else slope
-            bnop = BnTrainOp(raw, out, bn_of(m), abn, slope, residual, res_after_act)
-            self.ops.append(bnop)
-            if isinstance(m, torch.nn.BatchNorm2d):
-                self.bn_modules.append(m)
-            conv, bsrc, stride, pad = bwd
-            node = dict(kind='conv_bn', conv=conv, src=bsrc, stride=stride, pad=pad, raw=raw, out=out, bnop=bnop, bn=m,
-                        abn=abn, slope=slope, res=residual, res_after=res_after_act)
-            # input gradient on the tensor cores where the forward kernels cover it: a stride-1 conv3x3 (padding 1) or
-            # conv1x1 is its own adjoint with the taps flipped and Cin / Cout swapped
-            k = conv.kernel_size[0]
-            if (tc_dgrad and isinstance(conv, torch.nn.Conv2d) and stride == 1 and k in (1, 3) and pad == k // 2 and
-                    bsrc.c0 == 0 and bsrc.slab.c % 32 == 0 and conv is not model.firstconv):
-                cin_pad, cout_pad = bsrc.slab.c, cout
-                draw = S(hh, ww, cout_pad)
-                dsrc = S(bsrc.slab.h, bsrc.slab.w, cin_pad)
-
-                def adjoint(conv=conv, cin_pad=cin_pad, cout_pad=cout_pad, k=k):
-                    wt = _pad_mat(f32(conv.weight), cout_pad, cin_pad)            # [cout_pad, cin_pad, k, k]
-                    wt = wt.flip(2, 3).transpose(0, 1).contiguous()                 # [cin_pad, cout_pad, k, k]
-                    return pack_conv3x3(wt) if k == 3 else pack_conv1x1(wt)
-
-                node['draw'], node['dsrc'] = draw, dsrc
-                node['dgrad_op'] = ConvOp(N.CONV_3X3 if k == 3 else N.CONV_1X1, draw.view(), dsrc.view(), P(adjoint),
-                                          zeros(cin_pad), relu=False)
-            self.tape.append(node)
-            return out
-
-        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
-        self.x_nchw = torch.empty((n, 3, h, w), dtype=torch.float32, device=device)
-        self.x_rows = S(h2, w2, self.STEM_K)
-        self.ops.append(SimpleOp("snb_stem7x7_rows", (N.c_vp(self.x_nchw.data_ptr()), n, 3, h, w,
-                                                      N.c_vp(self.x_rows.t.data_ptr()), self.STEM_K), (self.x_nchw, self.x_rows)))
-        # bf16 NHWC copy of the input image (3 channels in an 8-wide slab): the `big` operand of the stem's weight gradient
-        self.x_nhwc = S(h, w, 8)
-        self.x_nhwc.t.zero_()
-        stem = conv_bn(N.CONV_1X1, self.x_rows.view(), P(lambda: pack_stem7x7(f32(model.firstconv.weight), self.STEM_K)), zeros(64), 64,
-                       h2, w2, model.firstbn, False, 0.0, bwd=(model.firstconv, self.x_nhwc.view(0, 3), 2, 3))
-        cur = S(h4, w4, 64)
-        self.ops.append(SimpleOp("snb_maxpool3x3s2", (N.c_vp(stem.ptr), n, h2, w2, 64, 64, N.c_vp(cur.view().ptr), 64),
-                                 (stem, cur)))
-        self.tape.append(dict(kind='maxpool', src=stem, out=cur.view()))
-        cur, ch, hh, ww = cur.view(), 64, h4, w4
-
-        skips = []
-        for li in range(1, 5):
-            for blk in getattr(model, 'encoder%d' % li):
-                cout = blk.conv1.weight.shape[0]
-                if blk.downsample is not None:
-                    hh, ww = hh // 2, ww // 2
-                    x4 = S(hh, ww, 4 * ch)
-                    self.ops.append(SimpleOp("snb_space_to_depth2", (N.c_vp(cur.ptr), n, 2 * hh, 2 * ww, ch, cur.cstride,
-                                                                     N.c_vp(x4.view().ptr), 4 * ch), (cur, x4)))
-                    t = conv_bn(N.CONV_2X2, x4.view(), P(lambda blk=blk: pack_conv3x3_s2(f32(blk.conv1.weight))), zeros(cout), cout, hh, ww,
-                                blk.bn1, False, 0.0, valid=True, bwd=(blk.conv1, cur, 2, 1))
-                    ident = conv_bn(N.CONV_1X1, x4.view(0, ch), P(lambda blk=blk: pack_conv1x1(f32(blk.downsample[0].weight))), zeros(cout), cout,
-                                    hh, ww, blk.downsample[1], False, -1.0, bwd=(blk.downsample[0], cur, 2, 0))
-                else:
-                    t = conv_bn(N.CONV_3X3, cur, P(lambda blk=blk: pack_conv3x3(f32(blk.conv1.weight))), zeros(cout), cout, hh, ww, blk.bn1,
-                                False, 0.0, bwd=(blk.conv1, cur, 1, 1))
-                    ident = cur
-                cur = conv_bn(N.CONV_3X3, t, P(lambda blk=blk: pack_conv3x3(f32(blk.conv2.weight))), zeros(cout), cout, hh, ww, blk.bn2, False,
-                              0.0, residual=ident, bwd=(blk.conv2, t, 1, 1))
-                ch = cout
-            skips.append(cur)
-
-        def decoder(x, cin, d, n_out, hh, ww, skip):
-            mid = cin // 4
-            mp = p32(mid)
-            a = conv_bn(N.CONV_1X1, x, P(lambda: pack_conv1x1(_pad_mat(f32(d.conv1.weight), mp, cin))), P(lambda: _pad_vec(f32(d.conv1.bias), mp)), mp,
-                        hh, ww, d.abn1, True, d.abn1.slope, bwd=(d.conv1, x, 1, 0))
-            b_ = conv_bn(N.CONVT_4X4_S2, a, P(lambda: pack_convT4x4(_pad_mat(f32(d.deconv2.weight), mp, mp))),
-                         P(lambda: _pad_vec(f32(d.deconv2.bias), mp)), mp, 2 * hh, 2 * ww, d.abn2, True, d.abn2.slope,
-                         bwd=(d.deconv2, a.slab.view(0, mid), 2, 1))
-            return conv_bn(N.CONV_1X1, b_, P(lambda: pack_conv1x1(_pad_mat(f32(d.conv3.weight), n_out, mp))), f32(d.conv3.bias), n_out,
-                           2 * hh, 2 * ww, d.abn3, True, d.abn3.slope, residual=skip, res_after_act=True,
-                           bwd=(d.conv3, b_.slab.view(0, mid), 1, 0))
-
-        e1, e2, e3, e4 = skips
-        h32, w32 = h // 32, w // 32
-        d4 = decoder(e4, 512, model.decoder4, 256, h32, w32, e3)
-        d3 = decoder(d4, 256, model.decoder3, 128, 2 * h32, 2 * w32, e2)
-        d2 = decoder(d3, 128, model.decoder2, 64, 4 * h32, 4 * w32, e1)
-        d1 = decoder(d2, 64, model.decoder1, 64, 8 * h32, 8 * w32, None)
-
-        slope1, slope2 = model.finalrelu1.negative_slope, model.finalrelu2.negative_slope
-        if linear:
-            slope1 = slope2 = 1.0        # leaky-ReLU with slope 1 is the identity
-        f1 = S(h + 1, w + 1, 32)
-        self.ops.append(ConvOp(N.CONVT_3X3_S2_FULL, d1, f1.view(), P(lambda: pack_convT3x3(model.finaldeconv1.weight, 64, 32)),
-                               f32(model.finaldeconv1.bias), act_slope=slope1))
-        self.tape.append(dict(kind='conv_act', conv=model.finaldeconv1, src=d1, stride=2, pad=0, out=f1.view(), slope=slope1))
-        f3 = S(h - 1, w - 1, 32)
-        self.ops.append(ConvOp(N.CONV_3X3, f1.view(), f3.view(), P(lambda: pack_conv3x3(f32(model.finalconv2.weight))),
-                               f32(model.finalconv2.bias), act_slope=slope2, valid=True))
-        self.tape.append(dict(kind='conv_act', conv=model.finalconv2, src=f1.view(), stride=1, pad=0, out=f3.view(), slope=slope2))
-        self.tape.append(dict(kind='conv_head', conv=model.finalconv3, src=f3.view(), stride=1, pad=1))
-        self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
-        pick = torch.zeros(32, dtype=torch.float32, device=device)
-        pick[0] = 1.0
-        self.ops.append(ConvOp(N.CONV_2X2, f3.view(), None, P(lambda: pack_conv2x2(f32(model.finalconv3.weight), 32, 32)),
-                               P(lambda: _pad_vec(f32(model.finalconv3.bias), 32)), relu=False, head=(pick, 0.0, False, self.out)))
-        self.flops = sum(op.flops for op in self.ops)
-        self.launches = sum(op.launches for op in self.ops)
-
-    def refresh(self):
-        """Re-pack the weights from the module's current parameters into the plan's existing buffers (after an optimiser
-        step): no handle, slab or tensor map changes.  Biases, BatchNorm / ABN weights and running statistics that are
-        not padded are read through the parameters' own pointers and need nothing."""
-        with torch.no_grad():
-            for t, fn in self._repack:
-                t.copy_(fn())
-            for op in self.ops:
-                if isinstance(op, BnTrainOp) and op.padded:
-                    op.refresh()
-
-    def load_nchw(self, x):
-        self.x_nchw.copy_(x)
-        self.x_nhwc.t[..., :3].copy_(x.permute(0, 2, 3, 1))
-
-    def run(self):
-        out = VGGUNetPlan.run(self)
-        for m in self.bn_modules:            # nn.BatchNorm2d bookkeeping (momentum is fixed, the counter only counts)
-            m.num_batches_tracked += 1
-        return out
-
-    # ------------------------------------------------------------------------------------------------ backward
-    def backward(self, dlogits):
-        """Gradients of every parameter given d loss / d logits (float [N, 1, H, W] or [N, H, W]); walks the tape in
-        reverse: BatchNorm / ABN backward (snb_bn_backward_nhwc), bias gradients (channel sums), generic dgrad / wgrad
-        (csrc/conv_generic.cu), max-pool backward.  Returns {parameter: gradient} (float tensors in the parameter's layout).
-        Activation gradients are bf16 NHWC slabs; gradients flowing into one tensor from several consumers are added."""
-        lib, st = N.lib(), N.stream_ptr()
-        n, dev = self.n, self.device
-        grads, pgrads = {}, {}
-
-        def add_grad(view, gslab):
-            key = id(view.slab)
-            if key in grads:
-                acc = grads[key]
-                N.check(lib.snb_ew_nhwc(N.c_vp(acc.t.data_ptr()), acc.c, N.c_vp(gslab.t.data_ptr()), gslab.c,
-                                        N.c_vp(acc.t.data_ptr()), acc.c, n * acc.h * acc.w, min(acc.c, gslab.c), 0, 0.0, st))
-            else:
-                grads[key] = gslab
-
-        def put(param, g):
-            pgrads[param] = g if param not in pgrads else pgrads[param] + g
-
-        def conv_backward(conv, src, stride, pad, draw, need_dsrc=True):
-            """draw = gradient slab of the convolution's output (bf16, channels = slab width)."""
-            transposed = isinstance(conv, torch.nn.ConvTranspose2d)
-            k = conv.kernel_size[0]
-            cin_t, cout_t = conv.weight.shape[1 if not transposed else 0], conv.weight.shape[0 if not transposed else 1]
-            g = N.ConvGeom()
-            g.n, g.kh, g.kw, g.stride, g.pad = n, k, k, stride, pad
-            if not transposed:      # big = input, small = output
-                g.big_h, g.big_w, g.big_c, g.big_cstride = src.slab.h, src.slab.w, src.c, src.cstride
-                g.small_h, g.small_w, g.small_c, g.small_cstride = draw.h, draw.w, cout_t, draw.c
-                big_ptr, small_ptr = src.ptr, draw.t.data_ptr()
-            else:                   # big = the transposed conv's output, small = its input
-                g.big_h, g.big_w, g.big_c, g.big_cstride = draw.h, draw.w, cout_t, draw.c
-                g.small_h, g.small_w, g.small_c, g.small_cstride = src.slab.h, src.slab.w, src.c, src.cstride
-                big_ptr, small_ptr = draw.t.data_ptr(), src.ptr
-            dw = torch.empty_like(conv.weight, dtype=torch.float32)
-            N.check(lib.snb_conv_generic_wgrad(ctypes.byref(g), N.c_vp(big_ptr), N.c_vp(small_ptr), N.ptr(dw), st))
-            put(conv.weight, dw)
-            if conv.bias is not None:
-                cw = (cout_t + 7) // 8 * 8
-                sums = torch.empty(cw, dtype=torch.float32, device=dev)
-                work = torch.empty(2 * cw, dtype=torch.float64, device=dev)
-                N.check(lib.snb_channel_sum_nhwc(N.c_vp(draw.t.data_ptr()), n * draw.h * draw.w, cw, draw.c, N.ptr(sums),
-                                                 N.ptr(work), st))
-                put(conv.bias, sums[:cout_t].clone())
-            if not need_dsrc:
-                return
-            dsrc = Slab(n, src.slab.h, src.slab.w, src.slab.c, dev)
-            if dsrc.c != src.c:
-                dsrc.t.zero_()      # padded channels of the slab carry no gradient
-            w32 = conv.weight.detach().float().contiguous()
-            if not transposed:
-                N.check(lib.snb_conv_generic_dgrad(ctypes.byref(g), N.c_vp(small_ptr), N.ptr(w32), N.c_vp(0),
-                                                   N.c_vp(dsrc.t.data_ptr()), st))
-            else:
-                g.small_cstride = dsrc.c
-                N.check(lib.snb_conv_generic_fwd(ctypes.byref(g), N.c_vp(big_ptr), N.ptr(w32), N.c_vp(0),
-                                                 N.c_vp(dsrc.t.data_ptr()), st))
-            self._keep.append(w32)
-            add_grad(src, dsrc)
-
-        self._keep = []
-        dl = dlogits.detach().reshape(n, self.h, self.w).float()
-        for node in reversed(self.tape):
-            kind = node['kind']
-            if kind == 'conv_head':
-                draw = Slab(n, self.h, self.w, 8, dev)
-                draw.t.zero_()
-                draw.t[..., 0].copy_(dl)
-                conv_backward(node['conv'], node['src'], node['stride'], node['pad'], draw)
-            elif kind == 'conv_act':
-                out = node['out']
-                g_out = grads.pop(id(out.slab))
-                dz = Slab(n, out.slab.h, out.slab.w, out.slab.c, dev)
-                N.check(lib.snb_ew_nhwc(N.c_vp(g_out.t.data_ptr()), g_out.c, N.c_vp(out.ptr), out.cstride, N.c_vp(dz.t.data_ptr()),
-                                        dz.c, n * dz.h * dz.w, dz.c, 1, float(node['slope']), st))
-                conv_backward(node['conv'], node['src'], node['stride'], node['pad'], dz)
-            elif kind == 'maxpool':
-                src, out = node['src'], node['out']
-                g_out = grads.pop(id(out.slab))
-                dsrc = Slab(n, src.slab.h, src.slab.w, src.slab.c, dev)
-                N.check(lib.snb_maxpool3x3s2_backward(N.c_vp(src.ptr), n, src.slab.h, src.slab.w, src.c, src.cstride,
-                                                      N.c_vp(g_out.t.data_ptr()), g_out.c, N.c_vp(dsrc.t.data_ptr()), dsrc.c, st))
-                add_grad(src, dsrc)
-            else:   # conv_bn
-                out, raw, bnop, m = node['out'], node['raw'], node['bnop'], node['bn']
-                g_out = grads.pop(id(out.slab))
-                res, after = node['res'], node['res_after']
-                if res is not None and after:
-                    add_grad(res, g_out)                      # out = act(bn) + res: the skip sees the same gradient
-                cpad = raw.c
-                draw = node.get('draw') or Slab(n, raw.slab.h, raw.slab.w, cpad, dev)
-                rb = res is not None and not after
-                dres = Slab(n, raw.slab.h, raw.slab.w, cpad, dev) if rb else None
-                dgamma = torch.empty(cpad, dtype=torch.float32, device=dev)
-                dbeta = torch.empty(cpad, dtype=torch.float32, device=dev)
-                work = torch.empty(2 * cpad, dtype=torch.float64, device=dev)
-                N.check(lib.snb_bn_backward_nhwc(
-                    N.c_vp(raw.ptr), raw.cstride, N.c_vp(g_out.t.data_ptr()), g_out.c, n * raw.slab.h * raw.slab.w, cpad,
-                    N.ptr(bnop.scale), N.ptr(bnop.shift), N.ptr(bnop.mean), N.ptr(bnop.var), N.ptr(bnop.gamma),
-                    1 if node['abn'] else 0, float(m.eps), float(node['slope']), N.c_vp(res.ptr if rb else 0),
-                    res.cstride if rb else 0, N.c_vp(draw.t.data_ptr()), draw.c, N.c_vp(dres.t.data_ptr() if rb else 0),
-                    dres.c if rb else 0, N.ptr(dgamma), N.ptr(dbeta), N.ptr(work), st))
-                c = m.weight.numel()
-                put(m.weight, dgamma[:c].clone())
-                put(m.bias, dbeta[:c].clone())
-                if rb:
-                    add_grad(res, dres)
-                conv_backward(node['conv'], node['src'], node['stride'], node['pad'], draw,
-                              need_dsrc=node['conv'] is not self.model.firstconv and 'dgrad_op' not in node)
-                if 'dgrad_op' in node:
-                    node['dgrad_op'](st)                      # tcgen05: conv with the adjoint weights
-                    add_grad(node['src'], node['dsrc'])
-                self._keep.extend((dgamma, dbeta, work))
-        return pgrads
+            rmean.data.copy_(self.rmean[:c])       # through .data: the plan's own update must not look like an external
+            rvar.data.copy_(self.rvar[:c])         # modification of the buffers (their version counters stay put)

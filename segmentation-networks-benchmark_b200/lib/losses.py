@@ -123,8 +123,11 @@ class JaccardLoss(_Loss):
     def __init__(self):
         super(JaccardLoss, self).__init__()
 
+    def fused_coefficients(self, numel):
+        return dict(c_jac=1.0, smooth_num=0.0, smooth_den=1e-7)
+
     def forward(self, output, target):
-        return _fused(output, target, c_jac=1.0, smooth_num=0.0, smooth_den=1e-7)
+        return _fused(output, target, **self.fused_coefficients(output.numel()))
 
 
 class SmoothJaccardLoss(_Loss):
@@ -134,8 +137,11 @@ class SmoothJaccardLoss(_Loss):
         super(SmoothJaccardLoss, self).__init__()
         self.smooth = smooth
 
+    def fused_coefficients(self, numel):
+        return dict(c_jac=1.0, smooth_num=self.smooth, smooth_den=self.smooth)
+
     def forward(self, output, target):
-        return _fused(output, target, c_jac=1.0, smooth_num=self.smooth, smooth_den=self.smooth)
+        return _fused(output, target, **self.fused_coefficients(output.numel()))
 
 
 class BCEWithSigmoidLoss(_Loss):
@@ -152,7 +158,10 @@ class BCEWithSigmoidLoss(_Loss):
             if _needs_grad(outputs):
                 return _ElementBCE.apply(outputs, targets)
             return fused_sums(outputs, targets, per_element=True)[2].view_as(outputs)
-        return _fused(outputs, targets, c_bce=1.0 / outputs.numel() if self.size_average else 1.0)
+        return _fused(outputs, targets, **self.fused_coefficients(outputs.numel()))
+
+    def fused_coefficients(self, numel):
+        return dict(c_bce=1.0 / numel if self.size_average else 1.0)
 
 
 class BCEWithLogitsLossAndSmoothJaccard(_Loss):
@@ -165,11 +174,13 @@ class BCEWithLogitsLossAndSmoothJaccard(_Loss):
         self.bce_weight = bce_weight
         self.jaccard_weight = jaccard_weight
 
-    def forward(self, outputs, targets):
+    def fused_coefficients(self, numel):
         tot = float(self.bce_weight + self.jaccard_weight)
         smooth = self.jac_loss.smooth
-        return _fused(outputs, targets, c_bce=self.bce_weight / (tot * outputs.numel()), c_jac=self.jaccard_weight / tot,
-                      smooth_num=smooth, smooth_den=smooth)         # one pass feeds both terms
+        return dict(c_bce=self.bce_weight / (tot * numel), c_jac=self.jaccard_weight / tot, smooth_num=smooth, smooth_den=smooth)
+
+    def forward(self, outputs, targets):
+        return _fused(outputs, targets, **self.fused_coefficients(outputs.numel()))         # one pass feeds both terms
 
 
 class FocalLossBinary(_Loss):
@@ -182,5 +193,29 @@ class FocalLossBinary(_Loss):
         self.size_average = size_average
         self.reduce = reduce
 
+    def fused_coefficients(self, numel):
+        return dict(c_focal=1.0 / numel if self.size_average else 1.0, gamma=float(self.gamma))
+
     def forward(self, outputs, targets):
-        return _fused(outputs, targets, c_focal=1.0 / outputs.numel() if self.size_average else 1.0, gamma=float(self.gamma))
+        return _fused(outputs, targets, **self.fused_coefficients(outputs.numel()))
+
+
+def fused_loss_and_grad(criterion, logits, targets, grad_out, loss_scale=1.0):
+    """loss = criterion(logits, targets) and d (loss_scale * loss) / d logits written into `grad_out` (a float tensor shaped
+    like logits), without autograd: one reduction launch + one elementwise launch, no host synchronisation.  `criterion`
+    is one of the fused losses above.  Returns (loss scalar on the device, sums, counts)."""
+    if not hasattr(criterion, 'fused_coefficients') or getattr(criterion, 'reduce', True) is False:
+        raise NotImplementedError("train_step needs one of the fused scalar losses of snb_b200.lib.losses")
+    k = dict(c_bce=0.0, c_focal=0.0, gamma=0.0, c_jac=0.0, smooth_num=0.0, smooth_den=0.0)
+    k.update(criterion.fused_coefficients(logits.numel()))
+    sums, counts = fused_sums(logits, targets, focal_gamma=k['gamma'] if k['c_focal'] else None)
+    loss = _combine(sums, k['c_bce'], k['c_focal'], k['gamma'], k['c_jac'], k['smooth_num'], k['smooth_den'])
+    x, t = _prep(logits, targets)
+    if grad_out.dtype != torch.float32 or not grad_out.is_contiguous() or grad_out.numel() != x.numel():
+        raise ValueError("grad_out must be a contiguous float tensor with one element per logit")
+    s = float(loss_scale)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().snb_loss_grad(N.ptr(x), N.ptr(t), _TARGET_DT[t.dtype], x.numel(), N.ptr(sums), N.c_vp(0), 0,
+                                      k['c_bce'] * s, k['c_focal'] * s, k['gamma'], k['c_jac'] * s, k['smooth_num'],
+                                      k['smooth_den'], N.ptr(grad_out), N.stream_ptr()))
+    return loss, sums, counts

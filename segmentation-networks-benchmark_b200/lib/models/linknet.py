@@ -6,8 +6,11 @@ is rebuilt here with torchvision's module names so no torchvision import is need
 weights in this environment and, like every other model here, starts from random initialisation.
 
 Forward runs on the native engine in eval mode (BatchNorm / InPlaceABN folded into the convolutions) and in train mode
-(batch statistics, running statistics updated in place, Dropout2d p must be 0).  The backward pass through the
-convolutions (BASELINE configs[1]) is not built.  `InPlaceABN` holds the parameters of
+(batch statistics, running statistics updated in place, Dropout2d as a per-(image, channel) keep mask).  In train mode
+with grad enabled the forward is one autograd node whose backward runs the whole backward pass of BASELINE configs[1] on
+the tensor cores (snb_b200.train_engine.LinkNet34TrainPlan: tcgen05 input and weight gradients, BatchNorm / InPlaceABN
+backward) and hands every parameter its gradient; `train_step` fuses forward, loss and backward.  `InPlaceABN` holds the
+parameters of
 mapillary's in-place activated batch norm (lib/modules/abn/bn.py:47-103); in eval mode it is
 leaky_relu((x - mean) / sqrt(var + eps) * (|weight| + eps) + bias, 0.01) -- the `|weight| + eps` scale is that
 library's forward; the library is not vendored in the reference and has no pinned version (parity unpinned).
@@ -16,7 +19,8 @@ import torch
 from torch import nn
 
 from ... import _native as N
-from ...engine import LinkNet34Plan, LinkNet34TrainPlan
+from ...engine import LinkNet34Plan
+from ...train_engine import LinkNet34TrainPlan
 from ..modules.abn import InPlaceABN
 
 
@@ -63,18 +67,20 @@ class _TrainStep(torch.autograd.Function):
         plan = model.plan_train(x.shape[0], x.shape[2], x.shape[3])
         plan.load_nchw(x.detach().float())
         out = plan.run()
-        ctx.plan, ctx.model_params = plan, list(model.parameters())
+        # the plan's slabs ARE the saved activations: a later forward of the same shape overwrites them
+        ctx.plan, ctx.generation, ctx.model_params = plan, plan.generation, list(model.parameters())
         return out.unsqueeze(1).clone()
 
     @staticmethod
     def backward(ctx, dout):
+        plan = ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("LinkNet34: another train-mode forward of the same input shape ran before this backward; its "
+                               "activations replaced the ones this graph saved (run forward and backward in pairs)")
         with torch.cuda.device(dout.device):
-            pg = ctx.plan.backward(dout.contiguous())
-        grads = []
-        for p in ctx.model_params:
-            g = pg.get(p)
-            grads.append(None if g is None else g.reshape(p.shape).to(p.dtype))
-        return (None, None) + tuple(grads)
+            plan.backward(dout.contiguous())
+            pg = plan.grads_in(plan.grad_arena.clone())       # autograd may keep (or accumulate into) what it is handed
+        return (None, None) + tuple(pg.get(p) for p in ctx.model_params)
 
 
 class LinkNet34(nn.Module):
@@ -140,7 +146,8 @@ class LinkNet34(nn.Module):
         was replaced by a different tensor."""
         cache = self.__dict__.setdefault('_train_plans', {})
         ptrs = tuple(p.data_ptr() for p in self.parameters())
-        versions = tuple(p._version for p in self.parameters())
+        versions = tuple(p._version for p in self.parameters()) + tuple(
+            b._version for k, b in self.named_buffers() if not k.endswith('num_batches_tracked'))
         if self.__dict__.get('_train_ptrs') != ptrs:
             cache.clear()
             self.__dict__['_train_ptrs'] = ptrs
@@ -157,6 +164,32 @@ class LinkNet34(nn.Module):
             cache[key].refresh()
             self.__dict__['_train_versions'][key] = versions
         return cache[key]
+
+    def train_step(self, x, targets, criterion, loss_scale=None):
+        """One training step without the optimiser (torch_train.py:183-189: `outputs = model(x); loss = criterion(outputs, y);
+        (batch_size * loss).backward()`), fused: train-mode forward (one CUDA-graph replay), loss reduction and its gradient
+        (two launches, no autograd, no host synchronisation), backward (one CUDA-graph replay).  Every parameter's .grad is
+        set to its slice of the plan's gradient arena (valid until the next step of this shape).  `criterion` is one of
+        the fused losses of snb_b200.lib.losses; loss_scale defaults to the batch size as in the reference's loop.
+        Returns (loss, logits [N, 1, H, W]) -- device tensors, nothing is synchronised."""
+        from ..losses import fused_loss_and_grad
+
+        N.require_cuda()
+        if not self.training:
+            raise RuntimeError("train_step needs train() mode")
+        if not x.is_cuda or x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected a CUDA input of shape [N, 3, H, W]")
+        with torch.cuda.device(x.device), torch.no_grad():
+            self.__dict__.pop('_plan_stamp', None)
+            plan = self.plan_train(x.shape[0], x.shape[2], x.shape[3])
+            plan.load_nchw(x.detach().float())
+            logits = plan.run().unsqueeze(1)
+            loss, _, _ = fused_loss_and_grad(criterion, logits, targets, plan.dlogits,
+                                             float(x.shape[0]) if loss_scale is None else loss_scale)
+            grads = plan.backward(None)
+            for p in self.parameters():
+                p.grad = grads[p] if p.requires_grad else None
+        return loss, logits
 
     def forward(self, x):
         """eval(): folded BatchNorm / InPlaceABN (running statistics).  train(): batch statistics, running statistics

@@ -224,10 +224,9 @@ def test_linknet34_train_mode_forward(cuda, golden_dir):
     m.load_state_dict(sd, strict=True)
     m = m.cuda().train()
     x = torch.from_numpy(g["train_x"]).cuda()
-    with pytest.raises(NotImplementedError):
-        m(x)                                                           # Dropout2d(p=0.5) active: not built
     m.finaldrop1.p = 0.0
-    y = m(x).cpu()
+    with torch.no_grad():
+        y = m(x).cpu()
     ref = torch.from_numpy(g["train_logits"])
     assert y.shape == ref.shape == (4, 1, 64, 64)
     p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
@@ -294,23 +293,26 @@ def test_bn_train_nhwc_against_torch(cuda, c, abn, slope, res, after):
     assert (op.mean - mean).abs().max().item() < 1e-5 and (op.var - var).abs().max().item() < 1e-4
 
 
-def _linknet_step(sd, x, t, quant=None, linear=False):
+def _linknet_step(sd, x, t, quant=None, linear=False, keep=None):
     """torch autograd on the CPU through the restated train-mode forward and B * bce_jaccard (torch_train.py:186-189)."""
     leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
-    logits, _ = no.linknet34_forward_train(leaf, x, quant=quant, linear=linear)
+    logits, _ = no.linknet34_forward_train(leaf, x, quant=quant, linear=linear, keep=keep)
     (no.bce_jaccard(logits, t) * x.shape[0]).backward()
     return logits.detach(), {k: v.grad for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.grad is not None}
 
 
-def _device_step(sd, x, t, linear=False):
+def _device_step(sd, x, t, linear=False, keep=None):
     from snb_b200.lib import losses
     from snb_b200.lib.models import LinkNet34
 
     m = LinkNet34(pretrained=False)
     m.load_state_dict(sd)
     m = m.cuda().train()
-    m.finaldrop1.p = 0.0
     m._test_linear = linear
+    if keep is None:
+        m.finaldrop1.p = 0.0
+    else:           # the default Dropout2d(p=0.5) with an injected keep mask
+        m.plan_train(x.shape[0], x.shape[2], x.shape[3]).set_dropout_mask(keep.cuda())
     logits = m(x.cuda())
     assert logits.requires_grad
     (losses.BCEWithLogitsLossAndSmoothJaccard()(logits, t.cuda()) * x.shape[0]).backward()
@@ -358,6 +360,17 @@ def test_linknet34_training_step_gradients(cuda):
     # the stem sits behind the only gate left, the max-pool, whose arg-max flips under bf16 rounding (measured 8e-2)
     assert all(e < (0.15 if k.startswith("first") else 5e-2) for e, k in worst), worst[:6]
     assert len(live) >= 100 and max(dead.values()) < 0.1, dead
+    # (1b) gate-free with the reference's default Dropout2d(p=0.5) active (the same keep mask injected on both sides): half
+    # of decoder1's channels carry no signal and the rest is doubled, so the rounding noise weighs more further down
+    keep = torch.from_numpy(rs.rand(n, 64) > 0.5)
+    _, want = _linknet_step(sd, x, t, linear=True, keep=keep)
+    _, got = _device_step(sd, x, t, linear=True, keep=keep)
+    live, dead = _rel_errors(got, want)
+    worst = sorted(((e, k) for k, e in live.items()), reverse=True)
+    print("gate-free + dropout: largest rel-L2 gradient errors:", [(round(e, 4), k) for e, k in worst[:4]])
+    head = ("final", "decoder1")
+    assert all(e < (0.15 if k.startswith("first") else (5e-2 if k.startswith(head) else 8e-2)) for e, k in worst), worst[:6]
+    assert max(dead.values()) < 0.1, dead
     # (2) real network
     logits_ref, want = _linknet_step(sd, x, t)
     _, noise = _linknet_step(sd, x, t, quant=no.bf16_round)
@@ -409,3 +422,81 @@ def test_linknet34_sgd_steps_reduce_the_loss(cuda):
         m2.load_state_dict(m.state_dict())
         b = m2(x)
     assert (torch.sigmoid(a) - torch.sigmoid(b)).abs().max().item() < 1e-2
+
+
+def test_linknet34_train_mode_with_default_dropout(cuda, golden_dir):
+    """The reference's default LinkNet34 (Dropout2d(p=0.5) active, lib/models/linknet.py:57,83): with the keep mask torch
+    drew inside the reference module injected, the train-mode logits match the reference's; without injection a fresh
+    Bernoulli(0.5) mask per forward zeroes whole channels of decoder1's output and scales the others by 2."""
+    from snb_b200.lib.models import LinkNet34
+
+    g = np.load(os.path.join(golden_dir, "linknet34_dropout.npz"))
+    m = LinkNet34(pretrained=False)
+    m.load_state_dict(synth.linknet34_state_dict(seed=6), strict=True)
+    m = m.cuda().train()
+    assert m.finaldrop1.p == 0.5
+    x = torch.from_numpy(g["train_x"]).cuda()
+    plan = m.plan_train(4, 64, 64)
+    plan.set_dropout_mask(torch.from_numpy(g["keep"]).cuda())
+    with torch.no_grad():
+        y = m(x).cpu()
+    p_err = (torch.sigmoid(y) - torch.sigmoid(torch.from_numpy(g["train_logits"]))).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    fractions, outs = [], []
+    for _ in range(6):
+        with torch.no_grad():
+            outs.append(m(x).cpu())
+        sc = plan.drop_scale.cpu()
+        assert set(sc.unique().tolist()) <= {0.0, 2.0}
+        fractions.append((sc > 0).float().mean().item())
+    assert 0.35 < sum(fractions) / len(fractions) < 0.65 and len(set(fractions)) > 1
+    assert not torch.equal(outs[0], outs[1])
+    m.eval()                                   # eval mode: dropout off, deterministic
+    with torch.no_grad():
+        assert torch.equal(m(x), m(x))
+
+
+def test_linknet34_fused_train_step_and_stale_backward(cuda):
+    """model.train_step (forward graph + fused loss / loss gradient + backward graph, no autograd) produces the gradients
+    of the autograd path (criterion(model(x), t) * B).backward(), and a backward whose activations were overwritten by a
+    later forward of the same shape raises instead of returning wrong gradients."""
+    from snb_b200.lib import losses
+    from snb_b200.lib.models import LinkNet34
+
+    sd = synth.linknet34_state_dict(seed=6)
+    rs = np.random.RandomState(2)
+    x = torch.from_numpy(rs.standard_normal((4, 3, 64, 96)).astype(np.float32)).cuda()
+    t = torch.from_numpy((rs.rand(4, 1, 64, 96) > 0.5).astype(np.int64)).cuda()
+    crit = losses.BCEWithLogitsLossAndSmoothJaccard()
+    grads = []
+    for fused in (False, True, True):
+        m = LinkNet34(pretrained=False)
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        m.finaldrop1.p = 0.0
+        if fused:
+            loss, logits = m.train_step(x, t, crit)
+        else:
+            logits = m(x)
+            loss = crit(logits, t)
+            (loss * x.shape[0]).backward()
+        grads.append(({k: p.grad.clone() for k, p in m.named_parameters()}, float(loss), logits.detach().clone()))
+    (ga, la, ya), (gb, lb, yb), (gc, _, _) = grads
+    assert torch.equal(ya, yb) and la == pytest.approx(lb, rel=1e-6)
+    for k in ga:
+        # same kernels in both paths; only the order of the float atomics in the split-K weight gradients differs
+        assert (ga[k] - gb[k]).norm().item() <= 2e-3 * ga[k].norm().item() + 1e-7, k
+        assert (gc[k] - gb[k]).norm().item() <= 2e-3 * gb[k].norm().item() + 1e-7, k
+    # repeated fused steps (CUDA-graph replays) + an SGD update in between keep working
+    opt = torch.optim.SGD(m.parameters(), lr=0.01)
+    first = None
+    for i in range(6):
+        loss, _ = m.train_step(x, t, crit)
+        opt.step()
+        first = float(loss) if first is None else first
+    assert float(loss) < first
+    # stale backward
+    y1 = m(x)
+    _ = m(x)                                     # second forward of the same shape overwrites the saved activations
+    with pytest.raises(RuntimeError):
+        crit(y1, t).backward()

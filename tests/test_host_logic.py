@@ -336,3 +336,16 @@ def test_adjoint_weights_give_the_input_gradient():
         y.backward(dy)
         adj = wt.flip(2, 3).transpose(0, 1).contiguous()
         assert torch.allclose(F.conv2d(dy, adj, padding=k // 2), x.grad, atol=1e-4)
+
+
+def test_train_plan_host_logic_dry_run():
+    """The LinkNet34 training plan's host side (op lists, gradient-slab bookkeeping, index maps of the pack functions,
+    gather tables) built and walked on the CPU against a stub of the native library (tools/dry_run_train_plan.py)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "dry_run_train_plan.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "'WgradOp': 51" in r.stdout and "'ConvOp': 50" in r.stdout and "unpack segments 51" in r.stdout, r.stdout

@@ -254,3 +254,13 @@ def test_extra_losses(golden_dir, seed, shape):
             (y * upstream).sum().backward()
         want = g["seed%d_%s_grad" % (seed, tag)]
         assert np.abs(sample(x.grad.numpy().reshape(-1)) - want).max() <= 2e-6 * np.abs(want).max() + 1e-12, tag
+
+
+def test_linknet34_train_mode_with_dropout(golden_dir):
+    """Default Dropout2d(p=0.5) active: the restatement given the keep mask torch drew inside the reference module
+    reproduces the reference's train-mode logits (tests/golden/linknet34_dropout.npz)."""
+    g = np.load(os.path.join(golden_dir, "linknet34_dropout.npz"))
+    sd = synth.linknet34_state_dict(seed=6)
+    with torch.no_grad():
+        y, _ = no.linknet34_forward_train(sd, torch.from_numpy(g["train_x"]), keep=torch.from_numpy(g["keep"]))
+    assert np.abs(y.numpy() - g["train_logits"]).max() < 1e-5

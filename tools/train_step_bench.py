@@ -59,7 +59,12 @@ def step():
     return loss
 
 
-for name, fn in (("forward (train mode, batch statistics)", fwd), ("forward + loss + backward", step)):
+def fused():
+    return m.train_step(xd, td, crit)[0]
+
+
+for name, fn in (("forward (train mode, batch statistics)", fwd), ("forward + loss + backward (autograd)", step),
+                 ("forward + loss + backward (train_step)", fused)):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -71,3 +76,8 @@ for name, fn in (("forward (train mode, batch statistics)", fwd), ("forward + lo
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     print("LinkNet34 batch %d x %d^2 %-40s %8.2f ms/step  %8.1f images/s" % (args.batch, args.size, name, ms, args.batch / ms * 1e3))
+
+plan = m.plan_train(args.batch, args.size, args.size)
+flops = plan.flops + plan.bwd_flops
+print("plan: %d forward launches, %d backward launches, %.1f GFLOP forward, %.1f GFLOP backward (algorithmic)" % (
+    plan.launches, plan.bwd_launches, plan.flops / 1e9, plan.bwd_flops / 1e9))
