@@ -36,6 +36,20 @@ MODELS = {
 }
 
 
+def bench_config(n_gpus, tta=False):
+    """`config` of the JSON line: identical keys and values in the CUDA arm and the reference arm (the driver compares
+    them); everything specific to one arm goes into `run`."""
+    workload = "configs[2]: UNet16 tiled inference, 5000x5000x3 u8, tile 512 / step 384, pyramid merge"
+    if n_gpus > 1:
+        workload += "; configs[3]: one image per rank per step, NCCL all-reduce of IoU counts + gather of masks"
+    return {"workload": workload, "tiles_per_image": 169, "tta": bool(tta)}
+
+
+FLOP_PER_TILE_UNET16 = 319689850880            # SURVEY 8d: 25 convolutions + the 1x1 head of one 512 x 512 tile, no padding
+FLOP_PER_TILE_FCDENSENET67 = 41514292736       # SURVEY 8d: one 224 x 224 tile
+FLOP_PER_SAMPLE_LINKNET34 = 11.64e9            # SURVEY 8a: forward of one 256 x 256 sample (x3 with backward)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -198,8 +212,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2]: UNet16 tiled inference, 5000x5000x3 u8, tile 512 / step 384, pyramid merge",
-                       "tiles_per_image": 169, "tta": False},
+            "config": bench_config(args.gpus, args.tta),
+            "run": {"extrapolated": True, "net_tiles_timed_per_step": n_net, "tiles_per_image": len(tiles),
+                    "note": "ms_per_step is an EXTRAPOLATION: split and merge of one whole image timed once, the network timed "
+                            "on %d of 169 tiles per step and scaled x169/%d; a full image takes minutes on the host" % (n_net, n_net)},
             "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -207,6 +223,40 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
+def _fence(world):
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _timed(fn, steps, world, dev, after=None):
+    """K calls of fn bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, MAX over ranks."""
+    import torch.distributed as dist
+
+    _fence(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    if after is not None:
+        after()
+    e1.record()
+    _fence(world)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _mask_checksum(mask):
+    """position-weighted 64-bit checksum of a uint8 mask (a permutation or offsetting errors change it)"""
+    v = mask.reshape(-1).to(torch.int64)
+    w = (torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 65521) + 1
+    return (v * w).sum()
+
+
 def run_cuda(args):
     import torch.distributed as dist
 
@@ -232,13 +282,16 @@ def run_cuda(args):
     model = model.to(dev).eval()
     if args.precision != "bf16":
         model.set_precision(args.precision)
+    headline = args.model == "unet16" and (tile, step) == (TILE, STEP) and args.precision == "bf16" and not args.tta
     if args.shard == "tile":
-        run_tile_sharded(args, model, tile, step, default_batch, dev, rank, world, label, cls_name)
+        line = run_tile_sharded(args, model, tile, step, dev, rank, world, label, cls_name)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         return
     pred = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=args.batch or default_batch,
                               tta=args.tta, device=dev, use_graph=args.graph)
-    metric = METRIC if args.model == "unet16" and (tile, step) == (TILE, STEP) else (
-        "megapixels/sec tiled inference (%s, 5000x5000, %d/%d)" % (cls_name, tile, step))
+    metric = METRIC if headline else ("megapixels/sec tiled inference (%s, 5000x5000, %d/%d%s%s)" % (
+        cls_name, tile, step, ", D4 TTA" if args.tta else "", ", " + args.precision if args.precision != "bf16" else ""))
 
     # distinct synthetic images per rank (weak scaling: one image per rank per step)
     n_img = 2
@@ -246,20 +299,22 @@ def run_cuda(args):
     dev_imgs = [h.to(dev) for h in host_imgs]
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     gts = [(torch.rand((IMAGE_HW, IMAGE_HW, 1), device=dev, generator=g) > 0.5).to(torch.uint8) for _ in range(n_img)]
-    host_mask = torch.empty((IMAGE_HW, IMAGE_HW, 1), dtype=torch.uint8).pin_memory()
     host_counts = torch.empty(4, dtype=torch.int64).pin_memory()
-    gathered = [None]
+    counts_buf = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+    # the only exchange of the image-sharded job: all-reduce of int64[4] + gather of u8 masks, on a side stream with
+    # preallocated double buffers so that it overlaps the next image's convolutions
+    exchange = sdist.MaskExchange((IMAGE_HW, IMAGE_HW, 1), dev) if world > 1 else None
+    last_slot = [0]
 
-    def exchange(mask, counts):
-        if world > 1:
-            sdist.allreduce_counts(counts)                                    # NCCL all-reduce of int64[4]
-            gathered[0] = sdist.gather_masks(mask.view(1, IMAGE_HW, IMAGE_HW), world)   # NCCL gather of u8 masks
+    def finish_image(i, merged, mask):
+        counts = metrics.confusion_counts_from_probs(merged, gts[i % n_img], out=counts_buf[i & 1])
+        if exchange is not None:
+            last_slot[0] = exchange.submit(mask, counts)
         return counts
 
     def step_resident(i):
         merged, mask = pred.predict_device(dev_imgs[i % n_img])
-        counts = metrics.confusion_counts_from_probs(merged, gts[i % n_img])
-        return exchange(mask, counts)
+        return finish_image(i, merged, mask)
 
     streamer = sub.StreamingPredictor(pred)
 
@@ -267,33 +322,30 @@ def run_cuda(args):
         # H2D of this step's image from pinned memory and D2H of its mask both happen inside the timed region, on a
         # copy stream that overlaps the neighbouring images' compute (the public host-to-host API)
         streamer.submit(host_imgs[i % n_img], host_imgs[(i + 1) % n_img])
-        counts = exchange(pred.mask, metrics.confusion_counts_from_probs(pred.merged, gts[i % n_img]))
+        counts = finish_image(i, pred.merged, pred.mask)
+        if exchange is not None:
+            exchange.wait()
+            counts = exchange.result(last_slot[0])[0]
         host_counts.copy_(counts, non_blocking=True)
 
-    def fence():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        fence()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        fence()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
+    drain = exchange.wait if exchange is not None else None
     for i in range(args.warmup):
         step_resident(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_total = timed(step_resident, args.steps)          # the timed region: one CUDA-graph replay per image
+    ms_total = _timed(step_resident, args.steps, world, dev, after=drain)     # the timed region: one CUDA-graph replay per image
     clocks = sampler.summary()
+
+    # multi-rank integrity: what rank 0 gathered for rank r is byte-for-byte rank r's mask (position-weighted checksums)
+    gathered_ok = None
+    if world > 1:
+        exchange.wait()
+        mine = _mask_checksum(pred.mask).reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            g_masks = exchange.result(last_slot[0])[1]
+            gathered_ok = all(int(_mask_checksum(g_masks[r])) == int(sums[r]) for r in range(world))
 
     # Per-launch conv timing with CUDA events.  Events cannot be recorded between the nodes of a replayed graph, so
     # the same K steps are run once more eagerly, right here, with one event after every launch of every plan run.
@@ -312,7 +364,7 @@ def run_cuda(args):
         return plan.out
 
     plan.run, pred.use_graph = run_marked, False
-    ms_eager = timed(step_resident, args.steps)
+    ms_eager = _timed(step_resident, args.steps, world, dev, after=drain)
     plan.run, pred.use_graph = orig_run, args.graph
 
     conv_ms, conv_flops, conv_launches, other_ms = 0.0, 0.0, 0, 0.0
@@ -335,7 +387,7 @@ def run_cuda(args):
         if i == args.steps - 1:
             streamer.flush()                                                 # the last mask lands on the host inside the region
 
-    ms_e2e = timed(e2e_steps, args.steps)
+    ms_e2e = _timed(e2e_steps, args.steps, world, dev, after=drain)
 
     ms_step = ms_total / args.steps
     value = world * MPX_PER_IMAGE / (ms_step / 1e3)
@@ -343,100 +395,193 @@ def run_cuda(args):
     peak_tf, peak_bw, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     # DRAM bytes per conv launch from the committed ncu --set full capture of the same plan (profiles/), headline config only
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_conv_summary.json")
-    if args.model == "unet16" and pred.batch == 13 and os.path.exists(tpath):
-        with open(tpath) as fh:
-            traffic = float(json.load(fh)["mean_dram_bytes_per_launch"])
-    if rank != 0:
-        return
+    traffic, traffic_src = None, None
+    for name in ("r02_ncu_conv_summary.json", "r01_ncu_conv_summary.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if headline and pred.batch == 13 and os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic, traffic_src = float(json.load(fh)["mean_dram_bytes_per_launch"]), "profiles/" + name
+            break
     line = {
         "metric": metric, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
         "data": "synthetic",
-        "config": {"workload": "%s tiled inference, 5000x5000x3 u8, tile %d / step %d, pyramid merge" % (label, tile, step)
-                               + ("; configs[3]: one image per rank per step, NCCL all-reduce of IoU counts + gather of masks"
-                                  if world > 1 else ""),
-                   "tiles_per_image": pred.n_tiles, "tile_batch": pred.batch, "tta": bool(args.tta), "cuda_graph": bool(args.graph),
-                   "l2_policy": "no flush needed: per-step working set (activations of %d tiles/batch, GBs) >> 126 MB L2; "
-                                "%d images rotate" % (pred.batch, n_img),
-                   "flop_per_image": pred.flops_per_image},
+        "config": bench_config(world, args.tta) if headline else {
+            "workload": "%s tiled inference, 5000x5000x3 u8, tile %d / step %d, pyramid merge" % (label, tile, step),
+            "tiles_per_image": pred.n_tiles, "tta": bool(args.tta)},
+        "run": {"tile_batch": pred.batch, "cuda_graph": bool(args.graph),
+                "l2_policy": "no flush needed: per-step working set (activations of %d tiles/batch, GBs) >> 126 MB L2; "
+                             "%d images rotate" % (pred.batch, n_img),
+                "flop_per_image": pred.flops_per_image,
+                "flop_per_image_survey_8d": 169 * FLOP_PER_TILE_UNET16 if headline else None,
+                "exchange": None if world == 1 else "all-reduce int64[4] + gather u8 masks on a side stream (double-buffered)",
+                "gathered_masks_match_rank_masks": gathered_ok},
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": IMAGE_HW * IMAGE_HW * 3,
                 "d2h_bytes_per_step": IMAGE_HW * IMAGE_HW + 32},
         "gpu_launches": (pred.launches_per_image + 1) * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": traffic,
-                     "traffic_note": "mean dram__bytes_read+write per conv launch (23 halo-kernel launches of one 13-tile plan run, "
-                                     "ncu --set full, profiles/r01_ncu_conv_summary.json); algorithmic FLOPs per launch vary per layer",
-                     "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
+                     "traffic_note": "mean dram__bytes_read+write per conv launch of one 13-tile plan run (ncu --set full, %s); "
+                                     "algorithmic FLOPs per launch vary per layer" % traffic_src,
+                     "kernel": "conv_halo_kernel / conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
                      "peak_source": peak_src + " bf16_tflops_sustained",
                      "timing": "CUDA events after every launch in an eager re-run of the same K steps (the timed "
                                "region itself replays a CUDA graph); shares are of that eager pass",
                      "conv_share_of_step": conv_ms / ms_eager, "conv_ms_per_step": conv_ms / args.steps,
                      "eager_ms_per_step": ms_eager / args.steps,
-                     "pool_ms_per_step": other_ms / args.steps,
+                     "other_plan_ms_per_step": other_ms / args.steps,
                      "whole_step_tflops": pred.flops_per_image / (ms_step / 1e3) / 1e12},
     }
+    secondary = {}
+    if headline and not args.no_secondary:
+        # free the headline's buffers before the secondary workloads allocate theirs
+        del streamer, pred, plan, marks, dev_imgs, gts
+        model._plans = {}
+        torch.cuda.empty_cache()
+        if world > 1:
+            sargs = argparse.Namespace(**vars(args))
+            secondary["tile_sharded"] = run_tile_sharded(sargs, model, tile, step, dev, rank, world, label, cls_name, brief=True)
+        else:
+            secondary = run_secondary(args, dev, peak_tf)
+            line["roofline_hbm"] = run_hbm(peak_bw, dev)
+    if secondary:
+        line["secondary"] = secondary
+    if rank != 0:
+        return
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
 
 
-def run_tile_sharded(args, model, tile, step, default_batch, dev, rank, world, label, cls_name):
-    """--shard tile: ONE image per step split by crop range over all ranks (strong scaling of single-image latency);
-    NCCL all-gather of the float32 probability tiles, every rank merges, counts all-reduce is not needed."""
+def run_hbm(peak_bw, dev):
+    """HBM-bound kernels of the path at BASELINE sizes: algorithmic bytes / CUDA-event time / measured copy bandwidth."""
+    from snb_b200 import hbm_bench
+
+    try:
+        r = hbm_bench.measure(peak_bw, reps=5, device=dev)
+        r["_how"] = ("one call per timed iteration, CUDA events, 256 MB L2 flush between iterations, mean of 5; bytes are the "
+                     "algorithmic bytes of SURVEY 8d; frac is against the measured copy bandwidth (%.0f GB/s)" % peak_bw)
+        return r
+    except Exception as exc:                          # a secondary measurement must not take the headline line down
+        return {"error": repr(exc)}
+    finally:
+        torch.cuda.empty_cache()
+
+
+def run_secondary(args, dev, peak_tf):
+    """configs[4] (FCDenseNet67 tiled inference) and configs[1] (LinkNet34 forward / backward step) on this GPU."""
+    from snb_b200 import synth
+    from snb_b200 import inria_submit as sub
+    from snb_b200.lib import losses
+    from snb_b200.lib import models as M
+
+    out = {}
+    try:
+        m = M.FCDenseNet67(n_classes=1)
+        m.load_state_dict(synth.fcdensenet_state_dict(seed=0))
+        m = m.to(dev).eval()
+        pred = sub.TiledPredictor(m, (IMAGE_HW, IMAGE_HW, 3), 224, 112, batch_size=44, tta=False, device=dev)
+        img = torch.from_numpy(synth.image_u8(0, IMAGE_HW, IMAGE_HW)).to(dev)
+        steps = 2
+        for _ in range(2):
+            pred.predict_device(img)
+        ms = _timed(lambda i: pred.predict_device(img), steps, 1, dev) / steps
+        mpx = MPX_PER_IMAGE / (ms / 1e3)
+        roof = MPX_PER_IMAGE / (pred.n_tiles * FLOP_PER_TILE_FCDENSENET67 / (peak_tf * 1e12))
+        out["fcdensenet67_configs4"] = {"metric": "megapixels/sec tiled inference (FCDenseNet67, 5000x5000, 224/112, bf16)",
+                                        "value": mpx, "unit": "Mpx/s", "ms_per_image": ms, "tiles_per_image": pred.n_tiles,
+                                        "tile_batch": pred.batch, "steps": steps,
+                                        "roofline_mpx": roof, "frac": mpx / roof,
+                                        "note": "roofline = 1936 tiles x 41.51 GFLOP (SURVEY 8d) at the measured sustained bf16 peak"}
+        del pred, m, img
+    except Exception as exc:
+        out["fcdensenet67_configs4"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+    try:
+        batch, size = 8, 256
+        m = M.LinkNet34(pretrained=False)
+        m.load_state_dict(synth.linknet34_state_dict(seed=0))
+        m = m.to(dev).train()
+        rs = np.random.RandomState(0)
+        x = torch.from_numpy(rs.standard_normal((batch, 3, size, size)).astype(np.float32)).to(dev)
+        t = torch.from_numpy((rs.rand(batch, 1, size, size) > 0.5).astype(np.int64)).to(dev)
+        crit = losses.BCEWithLogitsLossAndSmoothJaccard()
+        for _ in range(3):
+            m.train_step(x, t, crit)
+        steps = 20
+        ms = _timed(lambda i: m.train_step(x, t, crit), steps, 1, dev) / steps
+        with torch.no_grad():
+            ms_fwd = _timed(lambda i: m(x), steps, 1, dev) / steps
+        plan = m.plan_train(batch, size, size)
+        flop = 3 * batch * FLOP_PER_SAMPLE_LINKNET34
+        out["linknet34_train_step_configs1"] = {
+            "metric": "LinkNet34 forward + bce_jaccard + backward, batch 8 x 3 x 256 x 256, bf16 (Dropout2d p = 0.5 active)",
+            "ms_per_step": ms, "images_per_s": batch / ms * 1e3, "forward_only_ms": ms_fwd, "steps": steps,
+            "gpu_launches_per_step": plan.launches + plan.bwd_launches + 2,
+            "algorithmic_tflops": flop / (ms / 1e3) / 1e12,
+            "note": "model.train_step: forward graph + fused loss + backward graph (tcgen05 dgrad / wgrad), no optimiser; "
+                    "algorithmic FLOPs = 3 x 8 x 11.64 GFLOP (SURVEY 8a); the step is launch- and BatchNorm-bound, not tensor-bound"}
+        del m, plan
+    except Exception as exc:
+        out["linknet34_train_step_configs1"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_tile_sharded(args, model, tile, step, dev, rank, world, label, cls_name, brief=False):
+    """ONE image per step split by crop range over all ranks (BASELINE configs[3] "sharded by tile", strong scaling of
+    single-image latency): seam tiles by NCCL send / recv, band merge per rank, all-gather of the uint8 mask bands and
+    all-reduce of the counts on a side stream that overlaps the next image.  Every rank's mask is compared BYTE FOR BYTE
+    with the single-GPU mask of the same image."""
     import torch.distributed as dist
 
     from snb_b200 import synth
     from snb_b200 import inria_submit as sub
     from snb_b200.lib import metrics
 
-    pred = sub.TileShardedPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=args.batch or default_batch,
-                                    tta=args.tta, device=dev, use_graph=args.graph)
+    pred = sub.TileShardedPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=args.batch or None, tta=args.tta,
+                                    device=dev, use_graph=args.graph, overlap=True)
     imgs = [torch.from_numpy(synth.image_u8(i, IMAGE_HW, IMAGE_HW)).to(dev) for i in range(2)]
     g = torch.Generator(device=dev).manual_seed(1000)
     gt = (torch.rand((IMAGE_HW, IMAGE_HW, 1), device=dev, generator=g) > 0.5).to(torch.uint8)
+    steps, warmup = args.steps, max(3, args.warmup)
 
     def step_fn(i):
-        merged, mask = pred.predict_device(imgs[i % 2])
-        return metrics.confusion_counts_from_probs(merged, gt)
+        pred.predict_device(imgs[i % 2], gt)
 
-    def fence():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
+    for i in range(warmup):
         step_fn(i)
-    fence()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        counts = step_fn(i)
-    e1.record()
-    fence()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    pred.wait()
+    ms = _timed(step_fn, steps, world, dev, after=pred.wait)
+    # byte equality with the single-GPU result of the last image, on every rank
+    last = (steps - 1) % 2
+    mask_sharded, counts_sharded = pred.local.mask.clone(), pred.counts.clone()
+    tiles_per_rank = [e - b for b, e in pred.ranges]
+    seam_bytes, tile_batch = pred.exchange_bytes, pred.local.batch
+    del pred
+    torch.cuda.empty_cache()
+    solo = sub.TiledPredictor(model, (IMAGE_HW, IMAGE_HW, 3), tile, step, batch_size=13, tta=args.tta, device=dev, use_graph=False)
+    merged, mask = solo.predict_device(imgs[last])
+    counts = metrics.confusion_counts_from_probs(merged, gt)
+    same = torch.tensor([1 if (torch.equal(mask, mask_sharded) and counts.tolist() == counts_sharded.tolist()) else 0], device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    # every rank must hold the same mask bytes
-    digest = pred.local.mask.to(torch.int64).sum().reshape(1)
-    lo, hi = digest.clone(), digest.clone()
-    if world > 1:
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        return
-    ms_step = float(ms.item()) / args.steps
-    print(json.dumps({
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    ms_step = ms / steps
+    line = {
         "metric": "megapixels/sec tiled inference, ONE image sharded by tile (%s, 5000x5000, %d/%d)" % (cls_name, tile, step),
-        "value": MPX_PER_IMAGE / (ms_step / 1e3), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "value": MPX_PER_IMAGE / (ms_step / 1e3), "unit": "Mpx/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "%s, one image per step split by crop range over %d ranks, NCCL all-gather of probability "
-                               "tiles, merge on every rank" % (label, world), "tiles_per_rank": pred.max_count,
-                   "masks_identical_across_ranks": bool(lo.item() == hi.item()), "counts": counts.tolist()},
-        "gpu_launches": (pred.local.launches_per_image + 2) * args.steps}), flush=True)
+        "config": {"workload": "%s, one image per step split by crop range over %d ranks; seam tiles by NCCL send/recv, band "
+                               "merge per rank, all-gather of u8 mask bands, all-reduce of counts" % (label, world),
+                   "tiles_per_image": 169, "tta": bool(args.tta)},
+        "run": {"tiles_per_rank": tiles_per_rank, "tile_batch": tile_batch, "seam_bytes_received_per_image_rank0": seam_bytes,
+                "exchange": "side stream, double-buffered tile store: overlaps the next image's convolutions"},
+        "masks_and_counts_byte_identical_to_single_gpu": bool(int(same) == 1), "counts": counts.tolist()}
+    del solo
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -455,6 +600,7 @@ def main():
     ap.add_argument("--step", type=int, default=0)
     ap.add_argument("--tta", action="store_true", help="D4 test-time augmentation (8 views per tile)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads / HBM-kernel block of the headline run")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -215,9 +215,7 @@ constexpr int kBnMaxCV = 256;   // <= 2048 channels
 template <bool PIVOT>
 __global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restrict__ in, int CV, int in_sv, int64_t pixels,
                                                             double* __restrict__ sums) {
-  __shared__ float sh[kBnMaxCV * 16];
-  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  __shared__ float sh[kBnMaxCV * 16];          // [pixel lane][channel][sum, sum of squares]: blockDim.x * 16 floats
   const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
   float s[8], q[8], pvt[8];
 #pragma unroll
@@ -243,14 +241,22 @@ __global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restr
         q[2 * e] += x.x * x.x; q[2 * e + 1] += x.y * x.y;
       }
     }
+  }
+  // fixed-order fold over the pixel lanes of the CTA (no shared-memory atomics: the same input gives the same statistics,
+  // so a train-mode forward is reproducible run to run), then one float64 atomic per channel and CTA
+  if (pl < ppb) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sh[(v * 8 + e) * 2], s[e]);
-      atomicAdd(&sh[(v * 8 + e) * 2 + 1], q[e]);
+      sh[pl * CV * 16 + (v * 8 + e) * 2] = s[e];
+      sh[pl * CV * 16 + (v * 8 + e) * 2 + 1] = q[e];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) atomicAdd(sums + i, (double)sh[i]);
+  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < ppb; ++k) t += sh[k * CV * 16 + i];
+    atomicAdd(sums + i, (double)t);
+  }
 }
 
 // mean / biased variance -> fused scale and shift of the normalisation; running statistics as nn.BatchNorm2d and
@@ -334,17 +340,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc_kernel(const uint4* __
                                                                  const float* __restrict__ mean, const float* __restrict__ var,
                                                                  float eps, float slope, int64_t pixels,
                                                                  double* __restrict__ sums) {
-  __shared__ float sh[kBnMaxCV * 16];
-  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  __shared__ float sh[kBnMaxCV * 16];          // [pixel lane][channel][sum dz, sum dz * xhat]: blockDim.x * 16 floats
   const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   if (pl < ppb) {
-    float sc[8], sf[8], mu[8], is[8], s[8], q[8];
+    float sc[8], sf[8], mu[8], is[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       sc[e] = __ldg(scale + v * 8 + e); sf[e] = __ldg(shift + v * 8 + e);
       mu[e] = __ldg(mean + v * 8 + e); is[e] = rsqrtf(__ldg(var + v * 8 + e) + eps);
-      s[e] = q[e] = 0.f;
     }
     for (int64_t pix = blockIdx.x * (int64_t)ppb + pl; pix < pixels; pix += (int64_t)gridDim.x * ppb) {
       const uint4 xu = __ldg(x + pix * x_sv + v), gu = __ldg(g + pix * g_sv + v);
@@ -363,14 +369,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc_kernel(const uint4* __
         q[e] += dz * (xv - mu[e]) * is[e];
       }
     }
+  }
+  // fixed-order fold over the pixel lanes of the CTA (no shared-memory atomics: the same input gives the same statistics,
+  // so a train-mode forward is reproducible run to run), then one float64 atomic per channel and CTA
+  if (pl < ppb) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sh[(v * 8 + e) * 2], s[e]);
-      atomicAdd(&sh[(v * 8 + e) * 2 + 1], q[e]);
+      sh[pl * CV * 16 + (v * 8 + e) * 2] = s[e];
+      sh[pl * CV * 16 + (v * 8 + e) * 2 + 1] = q[e];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) atomicAdd(sums + i, (double)sh[i]);
+  for (int i = threadIdx.x; i < CV * 16; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < ppb; ++k) t += sh[k * CV * 16 + i];
+    atomicAdd(sums + i, (double)t);
+  }
 }
 
 // dx = gamma' * invstd * (dz - mean(dz) - xhat * mean(dz * xhat)); optionally dz itself (the gradient of r_before)

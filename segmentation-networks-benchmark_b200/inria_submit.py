@@ -112,13 +112,20 @@ class TiledPredictor:
 
 
 class TileShardedPredictor:
-    """One image across all ranks (BASELINE configs[3], "sharded by tile"): rank r runs the contiguous crop range
-    dist.shard_range(n_tiles, r, world), the float32 probability tiles are all-gathered over NCCL (177 MB per image,
-    never partial float accumulators: SURVEY 8e), and every rank merges all crops in crop order, so the mask is
-    byte-identical to the single-GPU result.  Strong scaling of single-image latency."""
+    """One image across all ranks (BASELINE configs[3], "sharded by tile"; SURVEY 8e): rank r runs the contiguous crop range
+    dist.shard_range(n_tiles, r, world) and OWNS a band of image rows.  Only the seam tiles cross NVLink: a rank receives
+    the probability tiles of the crop rows that overlap its band and that a neighbour computed (NCCL grouped send / recv
+    straight between the ranks' tile buffers, ~1/8 of what an all-gather of all tiles would move), merges its band with
+    snb_merge_rows in crop order -- never partial float accumulators, so the bytes equal the single-GPU merge -- and the
+    uint8 mask bands are all-gathered (25 MB per image in total).  Exchange, band merge and gather run on a side stream
+    with double-buffered tiles, so they overlap the next image's convolutions.  Strong scaling of single-image latency.
 
-    def __init__(self, model, image_shape, patch_size, tile_step=None, batch_size=1, weight='pyramid', tta=True,
-                 normalize=None, device=None, use_graph=True):
+    predict_device(d_image, gt=None) -> (merged, mask[, counts]): `mask` is the full uint8 mask on every rank; `merged`
+    holds this rank's band of the float32 map (all of it with gather_probs=True); counts = all-reduced int64 [tp, fp, fn,
+    tn] against `gt` (uint8 [H, W, 1] on every rank) when given."""
+
+    def __init__(self, model, image_shape, patch_size, tile_step=None, batch_size=None, weight='pyramid', tta=True,
+                 normalize=None, device=None, use_graph=True, gather_probs=False, overlap=False):
         import torch.distributed as dist
 
         from . import dist as sdist
@@ -128,28 +135,85 @@ class TileShardedPredictor:
         probe = ImageSlicer(image_shape, patch_size, patch_size // 2 if tile_step is None else tile_step, weight=weight)
         n_tiles = len(probe.crops)
         self.ranges = [sdist.shard_range(n_tiles, r, self.world) for r in range(self.world)]
-        self.local = TiledPredictor(model, image_shape, patch_size, tile_step, batch_size, weight, tta, normalize, device,
-                                    use_graph, tile_range=self.ranges[self.rank], merge=False)
-        self.max_count = max(e - b for b, e in self.ranges)
+        b, e = self.ranges[self.rank]
+        batch = sdist.pick_tile_batch(e - b) if batch_size is None else batch_size
+        self.local = TiledPredictor(model, image_shape, patch_size, tile_step, batch, weight, tta, normalize, device, use_graph,
+                                    tile_range=(b, e), merge=False)
         p = self.local
-        row = p.probs[0].numel()
-        self.send = torch.zeros((self.max_count, row), dtype=torch.float32, device=p.device)
-        self.recv = torch.empty((self.world * self.max_count, row), dtype=torch.float32, device=p.device)
+        h = image_shape[0]
+        tiles_x = len({x for x, _, _, _ in probe.crops})
+        tiles_y = n_tiles // tiles_x
+        self.bands = [sdist.band_range(h, r, self.world) for r in range(self.world)]
+        self.needs = [sdist.tiles_covering_rows(rb, re, probe.margin_top, patch_size, p.tile_step, tiles_x, tiles_y)
+                      for rb, re in self.bands]
+        self.max_band = max(re - rb for rb, re in self.bands)
+        self.gather_probs = gather_probs
+        # overlap=True: predict_device returns while the exchange / merge / gather of this image still run on the side
+        # stream (call wait() before reading the results); False: results are ordered on the caller's stream
+        self.overlap = overlap
+        self.side = torch.cuda.Stream(device=p.device)
+        # double-buffered tile store for the side stream (the predictor's own buffer is baked into its CUDA graph)
+        self.stage = [torch.empty_like(p.probs) for _ in range(2)]
+        w = image_shape[1]
+        self.band_mask = torch.zeros((self.max_band, w, 1), dtype=torch.uint8, device=p.device)
+        self.all_masks = torch.empty((self.world, self.max_band, w, 1), dtype=torch.uint8, device=p.device)
+        self.band_f32 = torch.zeros((self.max_band, w, 1), dtype=torch.float32, device=p.device) if gather_probs else None
+        self.all_f32 = torch.empty((self.world, self.max_band, w, 1), dtype=torch.float32, device=p.device) if gather_probs else None
+        self.counts = torch.zeros(4, dtype=torch.int64, device=p.device)
+        self.computed = [torch.cuda.Event() for _ in range(2)]
+        self.merged_ev = [torch.cuda.Event() for _ in range(2)]
+        self.step = 0
+        self.exchange_bytes = sum(sdist.range_overlap(self.ranges[s], self.needs[self.rank])[1] for s in range(self.world)
+                                  if s != self.rank) * p.probs[0].numel() * 4
 
-    def predict_device(self, d_image):
+    def predict_device(self, d_image, gt=None):
         import torch.distributed as dist
 
+        from .lib import metrics
+
         p = self.local
-        p.predict_device(d_image)
-        if self.world > 1:
-            flat = p.probs.view(p.n_tiles, -1)
-            b, e = self.ranges[self.rank]
-            self.send[:e - b].copy_(flat[b:e])
-            dist.all_gather_into_tensor(self.recv, self.send)
-            for r, (rb, re) in enumerate(self.ranges):
-                if r != self.rank and re > rb:
-                    flat[rb:re].copy_(self.recv[r * self.max_count:r * self.max_count + (re - rb)])
-        return p.merge_probs()
+        slot = self.step & 1
+        self.step += 1
+        cur = torch.cuda.current_stream(p.device)
+        p.predict_device(d_image)                          # split + network for my crop range -> p.probs[b:e]
+        if self.step > 2:
+            cur.wait_event(self.merged_ev[slot])          # the merge that read this staging buffer two images ago is done
+        b, e = self.ranges[self.rank]
+        stage = self.stage[slot]
+        stage[b:e].copy_(p.probs[b:e], non_blocking=True)
+        self.computed[slot].record(cur)
+        rb, re = self.bands[self.rank]
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.computed[slot])
+            if self.world > 1:
+                from . import dist as sdist
+                sdist.exchange_seam_tiles(stage, self.ranges, self.needs, self.rank, self.world)
+            N.check(N.lib().snb_merge_rows(p.slicer.handle, N.ptr(stage), N.DT_F32, 1, p.views, N.ptr(p.weight),
+                                           N.ptr(p.merged), N.DT_F32, N.ptr(p.mask), 0.5, rb, re - rb, N.stream_ptr()))
+            self.merged_ev[slot].record(self.side)
+            if gt is not None:
+                metrics.confusion_counts_from_probs(p.merged[rb:re], gt[rb:re], out=self.counts)
+            if self.world > 1:
+                self.band_mask[:re - rb].copy_(p.mask[rb:re])
+                dist.all_gather_into_tensor(self.all_masks, self.band_mask)
+                for r, (b0, b1) in enumerate(self.bands):
+                    if r != self.rank:
+                        p.mask[b0:b1].copy_(self.all_masks[r, :b1 - b0])
+                if self.gather_probs:
+                    self.band_f32[:re - rb].copy_(p.merged[rb:re])
+                    dist.all_gather_into_tensor(self.all_f32, self.band_f32)
+                    for r, (b0, b1) in enumerate(self.bands):
+                        if r != self.rank:
+                            p.merged[b0:b1].copy_(self.all_f32[r, :b1 - b0])
+                if gt is not None:
+                    dist.all_reduce(self.counts, op=dist.ReduceOp.SUM)
+        if not self.overlap:
+            self.wait()
+        return (p.merged, p.mask) if gt is None else (p.merged, p.mask, self.counts)
+
+    def wait(self):
+        """make the current stream wait for the exchange / merge / gather of everything submitted"""
+        torch.cuda.current_stream(self.local.device).wait_stream(self.side)
 
 
 class StreamingPredictor:

@@ -349,3 +349,76 @@ def test_train_plan_host_logic_dry_run():
                        timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "'WgradOp': 51" in r.stdout and "'ConvOp': 50" in r.stdout and "unpack segments 51" in r.stdout, r.stdout
+
+
+def _seam_worker(rank, world, port, out):
+    """Tile-sharded mode on gloo: each rank 'computes' its crop range (oracle tiles), receives the seam tiles its row band
+    needs, merges its band with the oracle merge restricted to those rows; MaskExchange gathers / all-reduces on CPU."""
+    import torch.distributed as dist
+
+    from snb_b200 import dist as sdist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    h, w, T, S = 300, 260, 128, 96
+    s = to.SlicerOracle((h, w, 1), T, S, weight="pyramid")
+    rs = np.random.RandomState(7)
+    all_tiles = torch.from_numpy(rs.rand(len(s.crops), T, T, 1).astype(np.float32))     # what the network would produce
+    tiles_x = len({c[0] for c in s.crops})
+    tiles_y = len(s.crops) // tiles_x
+    owned = [sdist.shard_range(len(s.crops), r, world) for r in range(world)]
+    bands = [sdist.band_range(h, r, world) for r in range(world)]
+    needed = [sdist.tiles_covering_rows(b, e, s.margin_top, T, S, tiles_x, tiles_y) for b, e in bands]
+    mine = torch.full_like(all_tiles, float("nan"))
+    b, e = owned[rank]
+    mine[b:e] = all_tiles[b:e]
+    sdist.exchange_seam_tiles(mine, owned, needed, rank, world)
+    nb, ne = needed[rank]
+    assert torch.equal(mine[nb:ne], all_tiles[nb:ne])                    # every tile my band reads has arrived
+    rb, re = bands[rank]
+    # tiles outside `needed` never touch rows [rb, re): zero them (NaN would poison the oracle's full-image accumulate)
+    safe = torch.where(torch.isnan(mine), torch.zeros(()), mine)
+    band = torch.from_numpy(s.merge(list(safe.numpy()), dtype=np.float32)[rb:re])
+    mask = ((band > 0.5) * 255).to(torch.uint8)
+    ex = sdist.MaskExchange((bands[0][1] - bands[0][0], w, 1), torch.device("cpu"))
+    pad = torch.zeros((bands[0][1] - bands[0][0], w, 1), dtype=torch.uint8)
+    pad[:re - rb] = mask
+    counts = torch.tensor([int((mask > 0).sum()), 0, 0, int((mask == 0).sum())])
+    slot = ex.submit(pad, counts)
+    ex.wait()
+    total, gathered = ex.result(slot)
+    if rank == 0:
+        full = torch.cat([gathered[r][:bands[r][1] - bands[r][0]] for r in range(world)])
+        torch.save({"mask": full, "counts": total.clone(), "band0": band}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_tile_sharded_bands_equal_single_process(tmp_path):
+    """SURVEY 8e 'shard by tile': seam-tile exchange + per-rank band merge + mask gather reproduce the single-process
+    merge byte for byte (gloo, CPU tensors; the device path runs the same dist.py functions over NCCL)."""
+    import torch.multiprocessing as mp
+
+    from snb_b200 import dist as sdist
+
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    out = str(tmp_path / "seam.pt")
+    mp.spawn(_seam_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    h, w, T, S = 300, 260, 128, 96
+    s = to.SlicerOracle((h, w, 1), T, S, weight="pyramid")
+    tiles = np.random.RandomState(7).rand(len(s.crops), T, T, 1).astype(np.float32)
+    want = s.merge(list(tiles), dtype=np.float32)
+    assert np.array_equal(got["band0"].numpy(), want[:150])
+    assert np.array_equal(got["mask"].numpy(), ((want > 0.5) * 255).astype(np.uint8))
+    assert got["counts"].tolist() == [int((want > 0.5).sum()), 0, 0, int((want <= 0.5).sum())]
+    # helper properties
+    assert sdist.pick_tile_batch(169) == 13 and sdist.pick_tile_batch(22) == 22 and sdist.pick_tile_batch(85) == 17
+    assert sdist.range_overlap((0, 10), (7, 20)) == (7, 3) and sdist.range_overlap((0, 5), (7, 9))[1] == 0
+    for world in (1, 2, 3, 8):
+        rows = [sdist.band_range(5000, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 5000 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
