@@ -460,8 +460,9 @@ def run_hbm(peak_bw, dev):
 
     try:
         r = hbm_bench.measure(peak_bw, reps=5, device=dev)
-        r["_how"] = ("one call per timed iteration, CUDA events, 256 MB L2 flush between iterations, mean of 5; bytes are the "
-                     "algorithmic bytes of SURVEY 8d; frac is against the measured copy bandwidth (%.0f GB/s)" % peak_bw)
+        r["_how"] = ("CUDA events around 5 back-to-back calls; every call moves > 126 MB and the inputs rotate over 3-4 sets "
+                     "(> 2 x L2), so no call finds its inputs in L2; bytes are the algorithmic bytes of SURVEY 8d; frac is "
+                     "against the measured copy bandwidth (%.0f GB/s)" % peak_bw)
         return r
     except Exception as exc:                          # a secondary measurement must not take the headline line down
         return {"error": repr(exc)}

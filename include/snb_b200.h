@@ -88,8 +88,13 @@ SNB_API int snb_split_hwc(const snb_slicer* s, const void* d_src, int64_t channe
 #define SNB_LAYOUT_NCHW_F32 0
 #define SNB_LAYOUT_PATCH32 1
 #define SNB_LAYOUT_PATCH32_F32 2 /* same rows as PATCH32 but float rounded to TF32 (128 bytes per pixel): TF32 mode */
+#define SNB_LAYOUT_NHWC3_BF16 3  /* bf16 [n][T][T][3], packed (6 bytes per pixel): the input of SNB_CONV_FIRST_3X3, which
+                                    builds the first layer's operand rows in shared memory; T % 8 == 0, 3 channels */
 SNB_API int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int64_t channels, const float* d_lut,
                       int tta, int layout, void* d_dst, int64_t tile_begin, int64_t tile_count, void* stream);
+
+/* float [n][3][h][w] (the nn.Module.forward input) -> packed NHWC bf16 [n][h][w][3] (SNB_LAYOUT_NHWC3_BF16); w % 8 == 0 */
+SNB_API int snb_nchw_f32_to_nhwc3(const float* d_src, int64_t n, int64_t h, int64_t w, void* d_dst, void* stream);
 
 /* float [n][3][H][W] (the nn.Module.forward input) -> PATCH32 rows, same definition as above; out_f32 != 0 writes
  * the SNB_LAYOUT_PATCH32_F32 form */
@@ -128,6 +133,10 @@ SNB_API int snb_merge_rows(const snb_slicer* s, const void* d_tiles, int tile_dt
 #define SNB_CONVT_3X3_S2_FULL 5 /* ConvTranspose2d k3 s2 p0 uncropped: output (2h+1) x (2w+1) (lib/models/linknet.py:58) */
 #define SNB_CONV_2X2_ADJ 6   /* the adjoint tap set of SNB_CONV_2X2: 4 taps (dy,dx in {0,+1}), output h x w (valid: (h-1) x (w-1)):
                                input gradients of stride-2 convolutions / of Conv2d k2 p1 (torch_train.py:186-189)            */
+#define SNB_CONV_FIRST_3X3 7 /* the networks' first conv3x3 (Cin = 3, padding 1) from the packed 3-channel bf16 tile
+                               [n][h][w][3] (SNB_LAYOUT_NHWC3_BF16): the K = 32 operand rows are built in shared memory;
+                               cin = in_cstride = 3, cout 32 or 64, weight bf16 [1][cout][32] with k = (ky*3+kx)*3 + c,
+                               bias + optional ReLU, w % 8 == 0 (lib/models/unet16.py:71-73, zf_unet.py:60, tiramisu.py:118) */
 #define SNB_CONVT_3X3_S2 3  /* ConvTranspose2d k3 s2 p0 cropped to [0,2h) x [0,2w) (lib/models/tiramisu.py:62-90):
                                4 phases x 4 tap slots, unused slots carry zero weights       */
 

@@ -19,8 +19,8 @@ SNB_E_CUDA = -3
 SNB_E_UNSUPPORTED = -4
 
 DT_U8, DT_F32, DT_F64, DT_I64 = 0, 1, 2, 3
-LAYOUT_NCHW_F32, LAYOUT_PATCH32, LAYOUT_PATCH32_F32 = 0, 1, 2
-CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2, CONV_2X2, CONVT_3X3_S2_FULL, CONV_2X2_ADJ = 0, 1, 2, 3, 4, 5, 6
+LAYOUT_NCHW_F32, LAYOUT_PATCH32, LAYOUT_PATCH32_F32, LAYOUT_NHWC3_BF16 = 0, 1, 2, 3
+CONV_3X3, CONV_1X1, CONVT_4X4_S2, CONVT_3X3_S2, CONV_2X2, CONVT_3X3_S2_FULL, CONV_2X2_ADJ, CONV_FIRST_3X3 = 0, 1, 2, 3, 4, 5, 6, 7
 CONV_BF16, CONV_TF32 = 0, 1
 
 c_i64 = ctypes.c_int64
@@ -88,6 +88,7 @@ SIGNATURES = {
     "snb_slicer_crops": (c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "snb_split_hwc": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "snb_split_norm_u8": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp]),
+    "snb_nchw_f32_to_nhwc3": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "snb_nchw_f32_to_patch32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
     "snb_merge": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_float, c_vp]),
     "snb_merge_rows": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_float, c_i64, c_i64, c_vp]),

@@ -754,6 +754,212 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
   }
 }
 
+// ===================================================================================== first layer: conv3x3 over 3 channels
+// conv1_1 of every network (Cin = 3) as a K = 32 GEMM whose operand rows are BUILT IN SHARED MEMORY: the input is the
+// normalised tile as packed NHWC bf16 with 3 channels (6 bytes per pixel -- exactly the algorithmic size of SURVEY 8d, no
+// 64-byte im2col row per pixel in HBM).  Per 16 x 8 patch one TMA box brings the (16+2) x (8+2) x 3 neighbourhood (zero
+// filled outside the tile = the convolution's padding; widened to a 16-byte aligned start); four builder warps (one thread per pixel) assemble the 128 operand
+// rows k = tap * 3 + c (27 values + 5 zeros, 64 bytes, written with the 64-byte swizzle the MMA descriptor expects); the
+// MMA thread issues two K = 16 steps against the resident [Cout][32] weights; the epilogue is the common one.
+// TMA fetches 16-byte granules: the innermost start coordinate must be a multiple of 16 bytes, i.e. of 8 packed pixels
+// (48 bytes), so the box starts 8 pixels left of the patch and spans pixels x0 - 8 .. x0 + 18 (80 elements = 160 bytes)
+constexpr int kFirstRawW = 80;
+constexpr int kFirstRawLead = 8;                       // pixels between the box start and the patch origin
+constexpr int kFirstRawRows = 10;
+constexpr int kFirstRawStage = 1664;                   // 10 x 160 = 1600 bytes, 128-byte aligned stages
+constexpr int kFirstRawStages = 4, kFirstAStages = 3;
+constexpr int kFirstABytes = kBM * 64;                 // 128 rows x 32 bf16
+
+// Warp roles (384 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-3 = builders (two pixels per thread),
+// 4-7 and 8-11 = TWO epilogue groups that take alternate tiles (accumulator stage 0 / 1): with K = 32 the MMA of a tile lasts
+// ~100 cycles while its epilogue (bias, ReLU, bf16, swizzled staging, TMA store of 128 x Cout) lasts ~1000, so this layer
+// is bound by the epilogue and, beyond it, by the HBM write of its output.
+template <int BN>
+__global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN, 32, 2>;
+  constexpr uint32_t IDESC = make_idesc(kBM, BN, 1u);
+  constexpr int TW = 16, TH = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                                   // kFirstAStages x 8 KB operand rows
+  uint8_t* smem_b = smem_a + kFirstAStages * kFirstABytes;                  // BN x 64 B weights (resident)
+  uint8_t* smem_out = smem_b + Cfg::B_BYTES;                                // 2 groups x 2 x OUT_BYTES
+  uint8_t* smem_in = smem_out + 4 * Cfg::OUT_BYTES;                         // kFirstRawStages raw neighbourhoods
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_in + kFirstRawStages * kFirstRawStage);
+  uint64_t* raw_full = bars;                          // [4]
+  uint64_t* raw_empty = raw_full + kFirstRawStages;   // [4]
+  uint64_t* a_ready = raw_empty + kFirstRawStages;    // [3]
+  uint64_t* a_empty = a_ready + kFirstAStages;        // [3]
+  uint64_t* b_full = a_empty + kFirstAStages;         // [1]
+  uint64_t* tmem_full = b_full + 1;                   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;               // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+    tma_prefetch_desc(&p.map_d[0]);
+    for (int i = 0; i < kFirstRawStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 2); }
+    for (int i = 0; i < kFirstAStages; ++i) { mbar_init(&a_ready[i], 2); mbar_init(&a_empty[i], 1); }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc05_fence_before();
+  __syncthreads();
+  tc05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA: weights once, then raw neighbourhoods
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
+      tma_load_3d(&p.map_b, b_full, smem_b, 0, 0, 0);
+      uint32_t s = 0, par = 1;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile<TW, TH>(p, t);
+        mbar_wait(&raw_empty[s], par);
+        mbar_arrive_expect_tx(&raw_full[s], kFirstRawRows * kFirstRawW * 2);
+        tma_load_3d(&p.map_a, &raw_full[s], smem_in + s * kFirstRawStage, (tc.x0 - kFirstRawLead) * 3, tc.y0 - 1, tc.img);
+        if (++s == kFirstRawStages) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      mbar_wait(b_full, 0);
+      tc05_fence_after();
+      const uint64_t bdesc = make_kmajor_desc<64>(smem_u32(smem_b), 8 * 64);
+      uint32_t sa = 0, pa = 0, local_tile = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+        const uint32_t acc = local_tile & 1;
+        mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
+        mbar_wait(&a_ready[sa], pa);
+        tc05_fence_after();
+        const uint64_t adesc = make_kmajor_desc<64>(smem_u32(smem_a + sa * kFirstABytes), 8 * 64);
+        umma_bf16_ss(adesc, bdesc, tmem_base + acc * BN, IDESC, 0u);
+        umma_bf16_ss(adesc + 2, bdesc + 2, tmem_base + acc * BN, IDESC, 1u);
+        umma_commit(&a_empty[sa]);
+        umma_commit(&tmem_full[acc]);
+        if (++sa == kFirstAStages) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ builders: one thread = two pixels = two 64-byte rows
+    const int r0 = threadIdx.x - 64;
+    uint32_t s = 0, ps = 0, sa = 0, pa = 1;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&raw_full[s], ps);
+      const unsigned short* raw = reinterpret_cast<const unsigned short*>(smem_in + s * kFirstRawStage);
+      uint4 rows[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = r0 + h * 64;
+        const int px = r & 15, py = r >> 4;
+        unsigned short el[32];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const unsigned short* q = raw + (py + tap / 3) * kFirstRawW + (px + tap % 3 + kFirstRawLead - 1) * 3;
+          el[tap * 3 + 0] = q[0];
+          el[tap * 3 + 1] = q[1];
+          el[tap * 3 + 2] = q[2];
+        }
+#pragma unroll
+        for (int k = 27; k < 32; ++k) el[k] = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          rows[h][c] = make_uint4(el[c * 8 + 0] | ((uint32_t)el[c * 8 + 1] << 16), el[c * 8 + 2] | ((uint32_t)el[c * 8 + 3] << 16),
+                                  el[c * 8 + 4] | ((uint32_t)el[c * 8 + 5] << 16), el[c * 8 + 6] | ((uint32_t)el[c * 8 + 7] << 16));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[s]);       // the raw stage is in registers now
+      if (++s == kFirstRawStages) { s = 0; ps ^= 1; }
+      mbar_wait(&a_empty[sa], pa);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = r0 + h * 64;
+        const int sw = (r >> 1) & 3;                   // 64-byte swizzle: 16-byte chunk index ^= (row >> 1) & 3
+        uint8_t* row = smem_a + sa * kFirstABytes + r * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = rows[h][c];
+      }
+      fence_proxy_async_smem();                        // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[sa]);
+      if (++sa == kFirstAStages) { sa = 0; pa ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------------ two epilogue groups (128 threads each)
+    const int grp = (warp - 4) >> 2;                   // 0: warps 4-7 (even tiles), 1: warps 8-11 (odd tiles)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 128 - grp * 128;
+    uint8_t* my_out = smem_out + grp * 2 * Cfg::OUT_BYTES;
+    constexpr int CW = BN < 64 ? BN : 64;
+    constexpr int OUT_SWZ = CW * 2;
+    uint32_t local_tile = 0, n_store = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+      if ((local_tile & 1) != static_cast<uint32_t>(grp)) continue;
+      const TileCoord tc = decode_tile<TW, TH>(p, t);
+      const uint32_t acc = grp;
+      mbar_wait(&tmem_full[acc], (local_tile >> 1) & 1);
+      tc05_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      // bias, ReLU, bf16, swizzled staging, TMA store (the common epilogue with this group's own staging buffers and barrier)
+      static_assert(BN <= 64, "one store chunk per tile");
+      uint8_t* sout = my_out + (n_store & 1) * Cfg::OUT_BYTES;
+      if (epi_tid == 0) tma_store_wait_read<1>();
+      named_bar_sync(1 + grp, 128);
+#pragma unroll
+      for (int g = 0; g < CW / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + g * 32, v);
+        tmem_ld_wait();
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + g * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+          float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
+                        __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
+                        __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
+                        __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
+          const int chunk = g * 4 + j;
+          *reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+      }
+      tc05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);    // accumulator stage back to the MMA warp
+      fence_proxy_async_smem();
+      named_bar_sync(1 + grp, 128);
+      if (epi_tid == 0) {
+        tma_store_4d(&p.map_d[0], sout, 0, tc.x0, tc.y0, tc.img);
+        tma_store_commit();
+      }
+      ++n_store;
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // --------------------------------------------------------------------------------------------- host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -779,6 +985,7 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 0  ? CU_TENSOR_MAP_SWIZZLE_NONE
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -943,9 +1150,77 @@ struct snb_conv {
 
 using namespace snb;
 
+// conv1_1 from the packed 3-channel tile (SNB_CONV_FIRST_3X3): see conv_first_kernel
+static int create_first(const snb_conv_desc* d, snb_conv** out) {
+  if (d->dtype != SNB_CONV_BF16) return fail(SNB_E_UNSUPPORTED, "the 3-channel first-layer kernel is bf16 only");
+  if (d->cin != 3 || d->in_cstride != 3) return fail(SNB_E_INVALID, "first-layer input must be packed NHWC with 3 channels");
+  if (d->cout != 32 && d->cout != 64) return fail(SNB_E_UNSUPPORTED, "first-layer cout must be 32 or 64, got %lld", (long long)d->cout);
+  if (d->w % 8) return fail(SNB_E_INVALID, "first-layer width must be a multiple of 8 (16-byte image rows)");
+  if (d->valid || d->d_head_w || d->d_pool_out || d->out_upsample2x || d->d_pre_scale || d->d_residual || d->act_slope != 0.f)
+    return fail(SNB_E_INVALID, "the first-layer kernel takes bias + optional ReLU only");
+  if (!d->d_in || !d->d_weight || !d->d_bias || !d->d_out || d->out_cstride < d->cout || d->out_cstride % 8)
+    return fail(SNB_E_INVALID, "bad first-layer tensors");
+  if ((reinterpret_cast<uintptr_t>(d->d_in) & 15) || (reinterpret_cast<uintptr_t>(d->d_out) & 15) ||
+      (reinterpret_cast<uintptr_t>(d->d_weight) & 15) || (reinterpret_cast<uintptr_t>(d->d_bias) & 15))
+    return fail(SNB_E_INVALID, "tensor pointers must be 16-byte aligned");
+  const int sms = sm_count();
+  if (sms <= 0) return fail(SNB_E_CUDA, "no CUDA device");
+  snb_conv* c = new (std::nothrow) snb_conv();
+  if (!c) return fail(SNB_E_INVALID, "out of host memory");
+  c->cluster = 1;
+  c->threads = 384;
+  ConvParams& p = c->params;
+  std::memset(&p, 0, sizeof(p));
+  const int bn = (int)d->cout;
+  p.n_phases = 1; p.taps = 1; p.k_chunks = 1; p.n_tiles = 1;
+  p.tiles_x = static_cast<int32_t>((d->w + 15) / 16);
+  p.tiles_y = static_cast<int32_t>((d->h + 7) / 8);
+  p.n_img = static_cast<int32_t>(d->n);
+  const int64_t total = (int64_t)p.n_img * p.tiles_y * p.tiles_x;
+  if (total > INT32_MAX) { delete c; return fail(SNB_E_UNSUPPORTED, "too many tiles"); }
+  p.total_tiles = static_cast<int32_t>(total);
+  p.relu = d->relu;
+  p.bias = d->d_bias;
+  p.out_w = static_cast<int32_t>(d->w); p.out_h = static_cast<int32_t>(d->h);
+  p.in_w = p.out_w; p.in_h = p.out_h;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)d->w * 3, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[2] = {(uint64_t)d->w * 6, (uint64_t)d->h * d->w * 6};
+    uint32_t box[3] = {kFirstRawW, kFirstRawRows, 1};
+    rc = encode_map(&p.map_a, const_cast<void*>(d->d_in), 3, dims, str, box, 0, 2);
+    if (rc) { delete c; return rc; }
+  }
+  {
+    uint64_t dims[3] = {32, (uint64_t)d->cout, 1};
+    uint64_t str[2] = {64, (uint64_t)d->cout * 64};
+    uint32_t box[3] = {32, (uint32_t)bn, 1};
+    rc = encode_map(&p.map_b, const_cast<void*>(d->d_weight), 3, dims, str, box, 64, 2);
+    if (rc) { delete c; return rc; }
+  }
+  const int cw = bn < 64 ? bn : 64;
+  {
+    uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->out_cstride * 2, (uint64_t)d->w * d->out_cstride * 2, (uint64_t)d->h * d->w * d->out_cstride * 2};
+    uint32_t box[4] = {(uint32_t)cw, 16, 8, 1};
+    rc = encode_map(&p.map_d[0], d->d_out, 4, dims, str, box, cw * 2, 2);
+    if (rc) { delete c; return rc; }
+  }
+  c->fn = bn == 64 ? reinterpret_cast<const void*>(&conv_first_kernel<64>) : reinterpret_cast<const void*>(&conv_first_kernel<32>);
+  const int out_bytes = kBM * cw * 2;
+  c->smem = 1024 + kFirstAStages * kFirstABytes + bn * 64 + 4 * out_bytes + kFirstRawStages * kFirstRawStage + 1024;
+  cudaError_t e = cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  if (e != cudaSuccess) { delete c; return fail(SNB_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
+  c->grid = std::min<int>(p.total_tiles, sms);
+  c->flops = 2.0 * (double)d->n * d->h * d->w * 27.0 * (double)d->cout;
+  *out = c;
+  return SNB_OK;
+}
+
 extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (!d || !out) return fail(SNB_E_INVALID, "snb_conv_create: null argument");
   *out = nullptr;
+  if (d->kind == SNB_CONV_FIRST_3X3) return create_first(d, out);
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return fail(SNB_E_INVALID, "bad input shape");
   ConvTapGeom tgeo;
   if (int rc = conv_tap_geometry(d->kind, d->valid, d->h, d->w, &tgeo)) return rc;

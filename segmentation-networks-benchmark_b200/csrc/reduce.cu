@@ -76,9 +76,11 @@ __device__ __forceinline__ float bce_element(float x, float t, float& p_out) {
   const float p = __fdividef(pos ? 1.f : e, d);
   p_out = p;
   const float xm = fminf(x, 0.f);
-  if (t == 0.f) return __logf(1.f + p);
-  if (t == 1.f) return __logf(pos ? 2.f + e : fmaf(2.f, e, 1.f)) - xm;
-  return __logf(1.f + p) - t * (xm - __logf(d));
+  // branch-free for binary targets (a select, not a divergent branch: neighbouring lanes hold different targets)
+  const float arg = t == 1.f ? (pos ? 2.f + e : fmaf(2.f, e, 1.f)) : 1.f + p;
+  float b = __logf(arg) - t * xm;
+  if (t != 0.f && t != 1.f) b = __logf(1.f + p) - t * (xm - __logf(d));     // soft / non-binary targets: rare, whole warps skip it
+  return b;
 }
 
 // FocalLossBinary element (lib/losses.py:90-96): logpt = -bce, pt = exp(logpt), loss = (1 - pt)^gamma * bce
@@ -127,11 +129,11 @@ __device__ __forceinline__ bool publish_and_elect(ReduceWs* ws) {
 }
 
 // Deterministic sum of the first `n_slots` slots by a 256-thread block: thread j adds slots j, j + 256, ... in order, then a
-// fixed-shape tree over the 256 partials.  NF float sums + NC counts.
+// fixed-shape shuffle butterfly per warp and the 8 warp totals in warp order.  NF float sums + NC counts.
 template <int NF, int NC>
 __device__ __forceinline__ void sum_slots(const ReduceWs* ws, int n_slots, double (&f)[NF], unsigned long long (&c)[NC]) {
-  __shared__ double s_f[256];
-  __shared__ unsigned long long s_c[256];
+  __shared__ double s_f[8][NF];
+  __shared__ unsigned long long s_c[8][NC];
   double lf[NF];
   unsigned long long lc[NC];
 #pragma unroll
@@ -145,21 +147,33 @@ __device__ __forceinline__ void sum_slots(const ReduceWs* ws, int n_slots, doubl
 #pragma unroll
     for (int k = 0; k < NC; ++k) lc[k] += __ldcg(&sl->c[k]);
   }
+  // fixed-shape butterfly inside each warp (the same order every run), then the 8 warp totals in warp order
 #pragma unroll
-  for (int k = 0; k < (NF > NC ? NF : NC); ++k) {
-    __syncthreads();
-    if (k < NF) s_f[threadIdx.x] = lf[k < NF ? k : 0];
-    if (k < NC) s_c[threadIdx.x] = lc[k < NC ? k : 0];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
-        if (k < NF) s_f[threadIdx.x] += s_f[threadIdx.x + o];
-        if (k < NC) s_c[threadIdx.x] += s_c[threadIdx.x + o];
-      }
-      __syncthreads();
-    }
-    if (k < NF) f[k < NF ? k : 0] = s_f[0];
-    if (k < NC) c[k < NC ? k : 0] = s_c[0];
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NF; ++k) lf[k] += __shfl_xor_sync(0xffffffffu, lf[k], o);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) lc[k] += __shfl_xor_sync(0xffffffffu, lc[k], o);
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < NF; ++k) s_f[warp][k] = lf[k];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) s_c[warp][k] = lc[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NF; ++k) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_f[w][k];
+    f[k] = t;
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += s_c[w][k];
+    c[k] = t;
   }
 }
 

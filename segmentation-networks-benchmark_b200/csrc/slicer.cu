@@ -57,47 +57,93 @@ struct BorderPixel {
 };
 
 // ---------------------------------------------------------------------------------------------- split_hwc
-// blockIdx.y = (tile, tile row); threads walk the row's bytes, UNIT output bytes each (4 -> one 32-bit store).
-// Every output byte is gathered through the reflect-101 map, so the copy is bit-exact for any element size.
-constexpr int kSplitRows = 8;   // tile rows per block
+// One warp per tile row.  Almost every output byte of a row belongs to ONE contiguous run of source bytes (the pixels whose
+// source column lies inside the image), so the run is copied as aligned 16-byte stores fed by two aligned 16-byte loads and
+// a funnel shift (source and destination are misaligned by an arbitrary byte count: 3-byte pixels, odd margins); only the
+// reflected / constant border pixels at the two ends of a row and the sub-16-byte fringes of the run go through the
+// per-byte reflect-101 map.  Bit-exact for any element size.
+constexpr int kSplitRows = 8;   // tile rows (= warps) per block
 
-template <int UNIT>
 __global__ void __launch_bounds__(256) split_hwc_kernel(SlicerGeom g, const uint8_t* __restrict__ src, int pixel_bytes,
                                                         int border_mode, BorderPixel border, uint8_t* __restrict__ dst,
                                                         int64_t tile_begin, int64_t total_rows) {
   const int T = (int)g.tile;
   const int row_bytes = T * pixel_bytes;
-  for (int row = blockIdx.y * kSplitRows; row < (int)min((int64_t)(blockIdx.y + 1) * kSplitRows, total_rows); ++row) {
-  const int t = row / T, ty = row - t * T;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kSplitRows + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  const int64_t t = row / T;
+  const int ty = (int)(row - t * T);
   const int64_t tile = tile_begin + t;
   const int cy = (int)((tile / g.tiles_x) * g.step), cx = (int)((tile % g.tiles_x) * g.step);
   const int py = cy + ty - (int)g.margin_top;
-  const int H = (int)g.image_h, Wd = (int)g.image_w;
+  const int H = (int)g.image_h, Wd = (int)g.image_w, ml = (int)g.margin_left;
   const bool row_inside = py >= 0 && py < H;
   const int sy = (int)reflect101(py, H);
   const uint8_t* src_row = src + (int64_t)sy * Wd * pixel_bytes;
-  uint8_t* dst_row = dst + (int64_t)row * row_bytes;
-  for (int b0 = (blockIdx.x * blockDim.x + threadIdx.x) * UNIT; b0 < row_bytes; b0 += gridDim.x * blockDim.x * UNIT) {
-    uint8_t out[UNIT];
+  const uint8_t* src_end = src + (int64_t)H * Wd * pixel_bytes;
+  uint8_t* dst_row = dst + row * row_bytes;
+  // pixels tx in [x_lo, x_hi) read source column cx + tx - ml inside the image: one contiguous run of bytes
+  int x_lo = max(0, ml - cx), x_hi = min(T, Wd + ml - cx);
+  if (border_mode == 1 && !row_inside) x_hi = x_lo;          // the whole row is constant border
+  if (x_hi < x_lo) x_hi = x_lo;
+  const int b_lo = x_lo * pixel_bytes, b_hi = x_hi * pixel_bytes;
+  const uint8_t* s0 = src_row + (int64_t)(cx - ml) * pixel_bytes;   // source byte of destination byte b (inside the run) = s0[b]
+  const uintptr_t d0 = reinterpret_cast<uintptr_t>(dst_row);
+  int v_lo = (int)(((d0 + b_lo + 15) & ~uintptr_t(15)) - d0), v_hi = (int)(((d0 + b_hi) & ~uintptr_t(15)) - d0);
+  if (v_hi <= v_lo) v_lo = v_hi = 0;
+  // four 16-byte chunks per lane and trip: all loads are issued before the first store (bytes in flight, not
+  // instructions, are what a copy kernel needs)
+  for (int b0 = v_lo + lane * 16; b0 < v_hi; b0 += 4 * 32 * 16) {
+    uint4 o[4];
 #pragma unroll
-    for (int b = 0; b < UNIT; ++b) {
-      const int xb = b0 + b;
-      const int tx = xb / pixel_bytes;
-      const int pb = xb - tx * pixel_bytes;
-      const int px = cx + tx - (int)g.margin_left;
-      if (border_mode == 1 && !(row_inside && px >= 0 && px < Wd)) {
-        out[b] = border.bytes[pb];
-      } else {
-        out[b] = __ldg(src_row + (int)reflect101(px, Wd) * pixel_bytes + pb);
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + u * 32 * 16;
+      if (b >= v_hi) break;
+      const uint8_t* sp = s0 + b;
+      const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
+      const uint4* vp = reinterpret_cast<const uint4*>(sa & ~uintptr_t(15));
+      const uint32_t off = (uint32_t)(sa & 15);
+      if (off == 0) {
+        o[u] = __ldg(vp);
+      } else if (reinterpret_cast<const uint8_t*>(vp + 2) <= src_end) {
+        // two aligned 16-byte loads cover the 16 wanted bytes; pick the 5 words around them and funnel-shift
+        const uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1);
+        const uint32_t sh = (off & 3) * 8;
+        uint32_t w0, w1, w2, w3, w4;
+        switch (off >> 2) {
+          case 0: w0 = v0.x; w1 = v0.y; w2 = v0.z; w3 = v0.w; w4 = v1.x; break;
+          case 1: w0 = v0.y; w1 = v0.z; w2 = v0.w; w3 = v1.x; w4 = v1.y; break;
+          case 2: w0 = v0.z; w1 = v0.w; w2 = v1.x; w3 = v1.y; w4 = v1.z; break;
+          default: w0 = v0.w; w1 = v1.x; w2 = v1.y; w3 = v1.z; w4 = v1.w; break;
+        }
+        o[u] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                          __funnelshift_r(w3, w4, sh));
+      } else {                                                  // the second vector would cross the end of the image buffer
+        uint8_t by[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) by[k] = __ldg(sp + k);
+        o[u] = make_uint4(by[0] | (by[1] << 8) | (by[2] << 16) | ((uint32_t)by[3] << 24), by[4] | (by[5] << 8) | (by[6] << 16) | ((uint32_t)by[7] << 24),
+                          by[8] | (by[9] << 8) | (by[10] << 16) | ((uint32_t)by[11] << 24), by[12] | (by[13] << 8) | (by[14] << 16) | ((uint32_t)by[15] << 24));
       }
     }
-    if (UNIT == 4) {
-      *reinterpret_cast<uint32_t*>(dst_row + b0) =
-          (uint32_t)out[0] | ((uint32_t)out[1 % UNIT] << 8) | ((uint32_t)out[2 % UNIT] << 16) | ((uint32_t)out[3 % UNIT] << 24);
-    } else {
-      dst_row[b0] = out[0];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + u * 32 * 16;
+      if (b < v_hi) *reinterpret_cast<uint4*>(dst_row + b) = o[u];
     }
   }
+  // everything else byte by byte through the border map: [0, v_lo) and [v_hi, row_bytes)
+  const int n_head = v_lo, n_rest = n_head + (row_bytes - v_hi);
+  for (int i = lane; i < n_rest; i += 32) {
+    const int xb = i < n_head ? i : v_hi + (i - n_head);
+    const int tx = xb / pixel_bytes;
+    const int pb = xb - tx * pixel_bytes;
+    const int px = cx + tx - ml;
+    uint8_t v;
+    if (border_mode == 1 && !(row_inside && px >= 0 && px < Wd)) v = border.bytes[pb];
+    else v = __ldg(src_row + (int64_t)reflect101(px, Wd) * pixel_bytes + pb);
+    dst_row[xb] = v;
   }
 }
 
@@ -257,6 +303,137 @@ __global__ void __launch_bounds__(256) split_norm_patch32_kernel(SlicerGeom g, c
     dst[((t * T + y0 + y) * (int64_t)T + x) * 4 + qd] =
         make_uint4(e[0] | ((uint32_t)e[1] << 16), e[2] | ((uint32_t)e[3] << 16), e[4] | ((uint32_t)e[5] << 16),
                    e[6] | ((uint32_t)e[7] << 16));
+  }
+}
+
+// SNB_LAYOUT_NHWC3_BF16: the normalised tile as packed NHWC bf16 with 3 channels (6 bytes per pixel: exactly the algorithmic
+// output size of SURVEY 8d).  A block writes kNhwcRows rows of one tile; the D4 view map, the reflect-101 border and the
+// 64-bit index arithmetic are evaluated once per row / column (tables in shared memory), a thread converts 8 consecutive
+// pixels (24 bytes in, LUT already rounded to bf16) and writes 48 contiguous bytes as three 16-byte stores.
+constexpr int kNhwcRows = 32;
+
+__global__ void __launch_bounds__(256) split_norm_nhwc3_kernel(SlicerGeom g, const uint8_t* __restrict__ src,
+                                                               const float* __restrict__ lut, int tta,
+                                                               uint4* __restrict__ dst, int64_t tile_begin) {
+  extern __shared__ int s_tab[];                   // [kNhwcRows] row offsets, [T] column offsets
+  __shared__ unsigned short s_lut[3 * 256];
+  const int T = (int)g.tile;
+  const int strips = (T + kNhwcRows - 1) / kNhwcRows;
+  const int64_t t = blockIdx.x / strips;
+  const int y0 = (int)(blockIdx.x % strips) * kNhwcRows;
+  const int64_t tile = tile_begin + t;
+  const int64_t cy = (tile / g.tiles_x) * g.step, cx = (tile % g.tiles_x) * g.step;
+  // NormalizeImage is affine per channel, so bf16(fma(v, a_c, b_c)) normally reproduces the bf16-rounded LUT entry for all
+  // 256 levels; the block checks that exhaustively (768 comparisons) and only then takes the arithmetic path -- the
+  // shared-memory gather of 3 LUT entries per pixel (random banks) is what bounds the table path
+  float la[3], lb[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    lb[c] = __ldg(lut + c * 256);
+    la[c] = (__ldg(lut + c * 256 + 255) - lb[c]) * (1.f / 255.f);
+  }
+  int ok = 1;
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    const __nv_bfloat16 b = __float2bfloat16(lut[i]);
+    const unsigned short bits = *reinterpret_cast<const unsigned short*>(&b);
+    s_lut[i] = bits;
+    const int c = i >> 8;
+    const __nv_bfloat16 a = __float2bfloat16(fmaf((float)(i & 255), c == 0 ? la[0] : (c == 1 ? la[1] : la[2]),
+                                                  c == 0 ? lb[0] : (c == 1 ? lb[1] : lb[2])));
+    ok &= (*reinterpret_cast<const unsigned short*>(&a) == bits) ? 1 : 0;
+  }
+  const bool arith = __syncthreads_and(ok) != 0;
+  const uint8_t* src_end = src + g.image_h * g.image_w * 3;
+  int* s_row = s_tab;
+  int* s_col = s_tab + kNhwcRows;
+  const bool transposed = (tta & 1) != 0;
+  for (int i = threadIdx.x; i < kNhwcRows + T; i += blockDim.x) {
+    const bool is_row = i < kNhwcRows;
+    const int v = is_row ? y0 + i : i - kNhwcRows;
+    int off = 0;
+    if (v < T) {
+      int si, sj;
+      d4_src(tta, is_row ? v : 0, is_row ? 0 : v, T, si, sj);
+      if (is_row != transposed) off = (int)(reflect101(cy + si - g.margin_top, g.image_h) * g.image_w * 3);
+      else off = (int)(reflect101(cx + sj - g.margin_left, g.image_w) * 3);
+    }
+    if (is_row) s_row[i] = off; else s_col[i - kNhwcRows] = off;
+  }
+  __syncthreads();
+  const int groups = T / 8;                        // 8-pixel groups per row
+  const int rows = min(kNhwcRows, T - y0);
+  for (int i = threadIdx.x; i < rows * groups; i += blockDim.x) {
+    const int y = i / groups, x0 = (i - y * groups) * 8;
+    const int rp = s_row[y];
+    unsigned short e[24];
+    uint8_t lv[24];
+    const int c0 = s_col[x0];
+    const uint8_t* sp = src + rp + c0;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    if (s_col[x0 + 7] - c0 == 21 && reinterpret_cast<const uint8_t*>(wp + 7) <= src_end) {
+      // 8 consecutive source pixels (no reflection inside the group): 24 contiguous bytes through 7 aligned words
+      const uint32_t sh = (uint32_t)(sa & 3) * 8;
+      uint32_t w[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) w[k] = __ldg(wp + k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const uint32_t b4 = __funnelshift_r(w[k], w[k + 1], sh);
+        lv[4 * k + 0] = (uint8_t)(b4 & 255u); lv[4 * k + 1] = (uint8_t)((b4 >> 8) & 255u);
+        lv[4 * k + 2] = (uint8_t)((b4 >> 16) & 255u); lv[4 * k + 3] = (uint8_t)(b4 >> 24);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint8_t* px = src + rp + s_col[x0 + k];
+        lv[3 * k + 0] = __ldg(px); lv[3 * k + 1] = __ldg(px + 1); lv[3 * k + 2] = __ldg(px + 2);
+      }
+    }
+    if (arith) {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) {
+        const int c = k % 3;
+        const __nv_bfloat16 v = __float2bfloat16(fmaf((float)lv[k], la[c], lb[c]));
+        e[k] = *reinterpret_cast<const unsigned short*>(&v);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) e[k] = s_lut[(k % 3) * 256 + lv[k]];
+    }
+    uint4* o = dst + (((t * T + y0 + y) * (int64_t)T + x0) * 3) / 8;     // 8 pixels x 6 bytes = 48 bytes = 3 vectors
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      o[q] = make_uint4(e[8 * q + 0] | ((uint32_t)e[8 * q + 1] << 16), e[8 * q + 2] | ((uint32_t)e[8 * q + 3] << 16),
+                        e[8 * q + 4] | ((uint32_t)e[8 * q + 5] << 16), e[8 * q + 6] | ((uint32_t)e[8 * q + 7] << 16));
+  }
+}
+
+// float [n][3][h][w] -> packed NHWC bf16 [n][h][w][3] (the nn.Module.forward entry of the same first-layer kernel)
+__global__ void nchw_to_nhwc3_kernel(const float* __restrict__ src, int H, int W, uint4* __restrict__ dst, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t groups = W / 8;
+    const int x0 = (int)(i % groups) * 8;
+    int64_t r = i / groups;
+    const int y = (int)(r % H);
+    const int64_t n = r / H;
+    const float* p0 = src + ((n * 3) * (int64_t)H + y) * W + x0;
+    const int64_t plane = (int64_t)H * W;
+    unsigned short e[24];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p0 + c * plane)), b = __ldg(reinterpret_cast<const float4*>(p0 + c * plane) + 1);
+      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const __nv_bfloat16 v = __float2bfloat16(f[k]);
+        e[3 * k + c] = *reinterpret_cast<const unsigned short*>(&v);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      dst[i * 3 + q] = make_uint4(e[8 * q + 0] | ((uint32_t)e[8 * q + 1] << 16), e[8 * q + 2] | ((uint32_t)e[8 * q + 3] << 16),
+                                  e[8 * q + 4] | ((uint32_t)e[8 * q + 5] << 16), e[8 * q + 6] | ((uint32_t)e[8 * q + 7] << 16));
   }
 }
 
@@ -1030,22 +1207,12 @@ extern "C" int snb_split_hwc(const snb_slicer* s, const void* d_src, int64_t cha
   const int64_t row_bytes = s->g.tile * pixel_bytes;
   if (tile_count * s->g.tile > 65535LL * 32768 || row_bytes > INT32_MAX / 2 || s->g.image_w * pixel_bytes > INT32_MAX / 2)
     return fail(SNB_E_UNSUPPORTED, "split too large");
-  const bool words = row_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 3) == 0;
-  // gridDim.y is limited to 65535 rows per launch: split the tile range
-  const int64_t tiles_per_launch = std::max<int64_t>(1, 65535LL * kSplitRows / s->g.tile);
-  for (int64_t t0 = 0; t0 < tile_count; t0 += tiles_per_launch) {
-    const int64_t nt = std::min(tiles_per_launch, tile_count - t0);
-    uint8_t* dst = static_cast<uint8_t*>(d_dst) + t0 * s->g.tile * row_bytes;
-    const int unit = words ? 4 : 1;
-    const int64_t rows = nt * s->g.tile;
-    const dim3 grid((unsigned)std::min<int64_t>((row_bytes / unit + 255) / 256, 64), (unsigned)((rows + kSplitRows - 1) / kSplitRows));
-    if (words)
-      split_hwc_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(s->g, static_cast<const uint8_t*>(d_src), (int)pixel_bytes,
-                                                              border_mode, bp, dst, tile_begin + t0, rows);
-    else
-      split_hwc_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(s->g, static_cast<const uint8_t*>(d_src), (int)pixel_bytes,
-                                                              border_mode, bp, dst, tile_begin + t0, rows);
-  }
+  if (reinterpret_cast<uintptr_t>(d_src) & 3) return fail(SNB_E_INVALID, "the source image must be 4-byte aligned");
+  const int64_t rows = tile_count * s->g.tile;
+  const int64_t blocks = (rows + kSplitRows - 1) / kSplitRows;
+  if (blocks > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "split too large");
+  split_hwc_kernel<<<(unsigned)blocks, 32 * kSplitRows, 0, as_stream(stream)>>>(
+      s->g, static_cast<const uint8_t*>(d_src), (int)pixel_bytes, border_mode, bp, static_cast<uint8_t*>(d_dst), tile_begin, rows);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
@@ -1090,9 +1257,31 @@ extern "C" int snb_split_norm_u8(const snb_slicer* s, const uint8_t* d_src, int6
       else SNB_SPLIT_P32(1, false);
     }
 #undef SNB_SPLIT_P32
+  } else if (layout == SNB_LAYOUT_NHWC3_BF16) {
+    if (channels != 3) return fail(SNB_E_INVALID, "the packed 3-channel layout needs a 3-channel image");
+    if (T % 8) return fail(SNB_E_INVALID, "the packed 3-channel layout needs a tile size that is a multiple of 8");
+    if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(SNB_E_INVALID, "destination must be 16-byte aligned");
+    if (s->g.image_h * s->g.image_w * channels > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "image too large for 32-bit source offsets");
+    const int strips = (int)((T + kNhwcRows - 1) / kNhwcRows);
+    if (tile_count * strips > INT32_MAX) return fail(SNB_E_UNSUPPORTED, "too many strips");
+    const size_t smem = (size_t)(kNhwcRows + T) * sizeof(int);
+    if (smem > 48 * 1024) return fail(SNB_E_UNSUPPORTED, "tile size %lld too large", (long long)T);
+    split_norm_nhwc3_kernel<<<(unsigned)(tile_count * strips), 256, smem, as_stream(stream)>>>(
+        s->g, d_src, d_lut, tta, static_cast<uint4*>(d_dst), tile_begin);
   } else {
     return fail(SNB_E_INVALID, "unknown layout %d", layout);
   }
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_nchw_f32_to_nhwc3(const float* d_src, int64_t n, int64_t h, int64_t w, void* d_dst, void* stream) {
+  if (!d_src || !d_dst) return fail(SNB_E_INVALID, "snb_nchw_f32_to_nhwc3: null argument");
+  if (n <= 0 || h <= 0 || w <= 0 || w % 8) return fail(SNB_E_INVALID, "bad shape (w must be a multiple of 8)");
+  if ((reinterpret_cast<uintptr_t>(d_dst) & 15) || (reinterpret_cast<uintptr_t>(d_src) & 15))
+    return fail(SNB_E_INVALID, "pointers must be 16-byte aligned");
+  const int64_t total = n * h * (w / 8);
+  nchw_to_nhwc3_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_src, (int)h, (int)w, static_cast<uint4*>(d_dst), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

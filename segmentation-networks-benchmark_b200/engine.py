@@ -145,7 +145,10 @@ class ConvOp:
         if pool_dst is not None:
             d.d_pool_out = pool_dst.ptr
             d.pool_cstride = pool_dst.cstride
-        if weight.shape[1] != d.cout or weight.shape[2] != d.cin:
+        if kind == N.CONV_FIRST_3X3:
+            if weight.shape[1] != d.cout or weight.shape[2] != 32 or src.c != 3 or src.cstride != 3:
+                raise ValueError("the first-layer kernel takes a packed 3-channel tile and a [1][cout][32] weight")
+        elif weight.shape[1] != d.cout or weight.shape[2] != d.cin:
             raise ValueError("packed weight %s does not match cout=%d cin=%d" % (tuple(weight.shape), d.cout, d.cin))
         self.desc = (int(d.kind), int(d.h), int(d.w), int(d.cin), int(d.cout))
         self._h = ctypes.c_void_p()
@@ -237,6 +240,23 @@ class ScatterConvOp:
                 pass
 
 
+def first_layer(plan, S, dtype, n, h, w, dst, weight, bias, relu=True, cout_real=None):
+    """Input buffer + first conv3x3 (Cin = 3) of a plan.  bf16: the packed 3-channel tile (6 bytes per pixel) and the kernel
+    that builds its operand rows in shared memory (SNB_CONV_FIRST_3X3); TF32 mode (and widths that are not multiples of 8):
+    the PATCH32 rows in HBM and a K = 32 conv1x1 over them."""
+    cout = weight.shape[0]
+    real = (9 * weight.shape[1], cout if cout_real is None else cout_real)
+    if dtype == torch.bfloat16 and w % 8 == 0 and weight.shape[1] == 3 and cout in (32, 64) and os.environ.get("SNB_FIRST_PATCH32", "0") != "1":
+        plan.x_in3 = S(h, w, 3)
+        plan.x_patch = None
+        op = ConvOp(N.CONV_FIRST_3X3, plan.x_in3.view(), dst, pack_first_conv3x3(weight, dtype), bias, relu=relu)
+        op.flops *= real[1] / float(cout)
+        return op
+    plan.x_in3 = None
+    plan.x_patch = S(h, w, 32)
+    return ConvOp(N.CONV_1X1, plan.x_patch.view(), dst, pack_first_conv3x3(weight, dtype), bias, relu=relu, real=real)
+
+
 class PoolOp:
     def __init__(self, src, dst):
         self.keep = (src, dst)
@@ -280,8 +300,7 @@ class VGGUNetPlan:
             slabs.append(S(hh, ww, up_c[4 - s] + skip_c[s]))
         self.slabs = slabs
 
-        self.x_patch = S(h, w, 32)
-        cur = self.x_patch.view()
+        cur = None
         for s, stage in enumerate(enc):
             hh, ww = h >> s, w >> s
             for li, (wt, bs) in enumerate(stage):
@@ -292,7 +311,7 @@ class VGGUNetPlan:
                 pooled = S(hh // 2, ww // 2, cout).view() if last else None
                 fuse = pooled is not None and fuse_pool and not (s == 0 and li == 0)
                 if s == 0 and li == 0:
-                    self.ops.append(ConvOp(N.CONV_1X1, cur, dst, pack_first_conv3x3(wt, dtype), f32(bs), real=(9 * wt.shape[1], cout)))
+                    self.ops.append(first_layer(self, S, dtype, n, h, w, dst, wt, f32(bs)))
                 else:
                     self.ops.append(ConvOp(N.CONV_3X3, cur, dst, pack_conv3x3(wt, dtype), f32(bs),
                                            pool_dst=pooled if fuse else None))
@@ -320,11 +339,22 @@ class VGGUNetPlan:
         self.launches = sum(op.launches for op in self.ops)
 
     def load_nchw(self, x):
-        """float [n,3,h,w] CUDA tensor -> first-layer operand rows."""
+        """float [n,3,h,w] CUDA tensor -> the first layer's input (packed 3-channel bf16 tile, or PATCH32 operand rows)."""
         x = x.contiguous()
+        if self.x_in3 is not None:
+            N.check(N.lib().snb_nchw_f32_to_nhwc3(N.ptr(x), x.shape[0], x.shape[2], x.shape[3],
+                                                  N.c_vp(self.x_in3.t.data_ptr()), N.stream_ptr()))
+            return
         N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(x), x.shape[0], x.shape[1], x.shape[2], x.shape[3],
                                                 N.c_vp(self.x_patch.t.data_ptr()),
                                                 1 if self.x_patch.t.dtype == torch.float32 else 0, N.stream_ptr()))
+
+    def input_layout(self):
+        """(snb_split_norm_u8 layout, destination pointer) of the tiled predictor's fused split"""
+        if self.x_in3 is not None:
+            return N.LAYOUT_NHWC3_BF16, self.x_in3.t.data_ptr()
+        f32 = self.x_patch.t.dtype == torch.float32
+        return (N.LAYOUT_PATCH32_F32 if f32 else N.LAYOUT_PATCH32), self.x_patch.t.data_ptr()
 
     def run(self):
         """Enqueue the whole forward on the current stream; result lands in self.out [n,h,w] float32."""
@@ -371,13 +401,11 @@ class ZFUNetPlan:
         def conv(src, dst, layer, first=False, **kw):
             wt, bs = fold_bn(*layer)
             if first:
-                self.ops.append(ConvOp(N.CONV_1X1, src, dst, pack_first_conv3x3(wt, dtype), bs.contiguous(),
-                                       real=(9 * wt.shape[1], wt.shape[0]), **kw))
+                self.ops.append(first_layer(self, S, dtype, n, h, w, dst, wt, bs.contiguous()))
             else:
                 self.ops.append(ConvOp(N.CONV_3X3, src, dst, pack_conv3x3(wt, dtype), bs.contiguous(), **kw))
 
-        self.x_patch = S(h, w, 32)
-        cur = self.x_patch.view()
+        cur = None
         for l in range(5):                                             # encoder: double conv, skip into the slab, pool
             hh, ww = h >> l, w >> l
             l1, l2 = blocks[l]
@@ -408,6 +436,7 @@ class ZFUNetPlan:
         self.launches = sum(op.launches for op in self.ops)
 
     load_nchw = VGGUNetPlan.load_nchw
+    input_layout = VGGUNetPlan.input_layout
     run = VGGUNetPlan.run
 
 
@@ -556,13 +585,12 @@ class FCDenseNetPlan:
                                    real=(cin, wt.shape[0])))
 
         # ---- first conv: 3 -> 48 (no activation), stored 64 wide
-        self.x_patch = S(h, w, 32)
         wf, bf = spec['first']
         cf_pad = _pad32(c_first) if c_first % 64 == 0 else (c_first + 63) // 64 * 64
         wfp = torch.zeros((cf_pad, wf.shape[1], 3, 3), dtype=torch.float32, device=dev)
         wfp[:c_first] = wf.detach().float()
-        self.ops.append(ConvOp(N.CONV_1X1, self.x_patch.view(), slabs[0].view(0, cf_pad), pack_first_conv3x3(wfp),
-                               padded_bias(bf, cf_pad), relu=False, real=(9 * wf.shape[1], c_first)))
+        self.ops.append(first_layer(self, S, torch.bfloat16, n, h, w, slabs[0].view(0, cf_pad), wfp, padded_bias(bf, cf_pad),
+                                    relu=False, cout_real=c_first))
 
         # ---- down path
         ident = lambda k: torch.arange(k, device=dev)
@@ -623,6 +651,7 @@ class FCDenseNetPlan:
         self.launches = sum(op.launches for op in self.ops)
 
     load_nchw = VGGUNetPlan.load_nchw
+    input_layout = VGGUNetPlan.input_layout
     run = VGGUNetPlan.run
 
 

@@ -88,9 +88,8 @@ class TiledPredictor:
                 x_nchw = getattr(self.plan, "x_nchw", None)
                 if x_nchw is not None:      # plans that take normalised float NCHW tiles (LinkNet34's 7x7 stem)
                     layout, target = N.LAYOUT_NCHW_F32, x_nchw.data_ptr()
-                else:                       # first conv3x3 as a K=32 GEMM over PATCH32 rows
-                    layout = N.LAYOUT_PATCH32_F32 if self.plan.x_patch.t.dtype == torch.float32 else N.LAYOUT_PATCH32
-                    target = self.plan.x_patch.t.data_ptr()
+                else:                       # packed 3-channel bf16 tile (first-layer operand rows built on chip), or PATCH32
+                    layout, target = self.plan.input_layout()
                 N.check(lib.snb_split_norm_u8(self.slicer.handle, N.ptr(d_image), self.channels, N.ptr(self.lut), v,
                                               layout, N.c_vp(target), begin, count, st))
                 out = self.plan.run()
@@ -280,6 +279,96 @@ class StreamingPredictor:
         last = (self.count - 1) & 1
         self.downloaded[last].synchronize()
         return self.mask_host[last]
+
+
+class FileSubmitter:
+    """The loop of reference inria_submit.main (inria_submit.py:291-306) as a three-stage host pipeline around the device
+    pipeline: a pool of DECODE threads (`cv2.imread`, releases the GIL) reads images ahead into pinned
+    buffers, the StreamingPredictor overlaps H2D / compute / D2H of consecutive images, and a pool of WRITE threads encodes
+    the uint8 masks (`cv2.imwrite`) while the GPU is already on the next images.  With the network at ~50 ms per
+    5000 x 5000 image, TIFF decode (~100-300 ms per image on one core) is what bounds a directory run: `decoders` threads
+    hide it.  `read` / `write` are injectable (tests, other formats).  All images must share one shape."""
+
+    def __init__(self, predictor, decoders=4, writers=2, prefetch=None, read=None, write=None):
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .lib.common import read_rgb
+
+        self.predictor = predictor
+        self.streamer = StreamingPredictor(predictor)
+        self.read = read_rgb if read is None else read
+        self.write = write if write is not None else self._imwrite
+        self.decode_pool = ThreadPoolExecutor(max_workers=max(1, decoders), thread_name_prefix="snb-decode")
+        self.write_pool = ThreadPoolExecutor(max_workers=max(1, writers), thread_name_prefix="snb-write")
+        self.prefetch = max(2, decoders * 2 if prefetch is None else prefetch)
+        shape = tuple(predictor.image.shape)
+        self._free = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(self.prefetch + 2)]
+
+    @staticmethod
+    def _imwrite(path, mask):
+        import cv2
+
+        if not cv2.imwrite(path, mask):
+            raise IOError("cv2.imwrite failed for %s" % path)
+
+    def _decode(self, path, buf):
+        image = self.read(path)
+        if image is None:
+            raise FileNotFoundError(path)
+        if image.ndim == 2:
+            image = image[..., None]
+        if tuple(image.shape) != tuple(buf.shape):
+            raise ValueError("%s has shape %s, the predictor was built for %s" % (path, image.shape, tuple(buf.shape)))
+        buf.numpy()[...] = image                      # into pinned memory: the H2D copy is then asynchronous
+        return buf
+
+    def run(self, image_paths, out_dir, suffix='.tif'):
+        """Predict every file, write `<basename><suffix>` masks into out_dir; returns the list of output paths."""
+        import os
+        from collections import deque
+
+        os.makedirs(out_dir, exist_ok=True)
+        paths = list(image_paths)
+        outs = [os.path.join(out_dir, os.path.splitext(os.path.basename(p))[0] + suffix) for p in paths]
+        pending, writes, in_gpu = deque(), [], deque()
+        nxt = 0
+
+        def feed():
+            nonlocal nxt
+            while nxt < len(paths) and len(pending) < self.prefetch and self._free:
+                buf = self._free.pop()
+                pending.append((nxt, buf, self.decode_pool.submit(self._decode, paths[nxt], buf)))
+                nxt += 1
+
+        def retire(mask_host):
+            idx, buf = in_gpu.popleft()
+            mask = mask_host.numpy().copy()           # the streamer reuses its pinned mask buffers
+            writes.append(self.write_pool.submit(self.write, outs[idx], mask[..., 0] if mask.shape[-1] == 1 else mask))
+            self._free.append(buf)
+
+        feed()
+        while pending:
+            idx, buf, fut = pending.popleft()
+            fut.result()
+            nxt_buf = None
+            if pending:
+                pending[0][2].result()
+                nxt_buf = pending[0][1]
+            prev = self.streamer.submit(buf, nxt_buf)
+            in_gpu.append((idx, buf))
+            if prev is not None:
+                retire(prev)
+            feed()
+        last = self.streamer.flush()
+        while in_gpu:
+            retire(last)
+        for w in writes:
+            w.result()
+        return outs
+
+    def close(self):
+        self.decode_pool.shutdown(wait=True)
+        self.write_pool.shutdown(wait=True)
 
 
 def predict_tiled(image, model, test_transform, patch_size, batch_size, tile_step=None, tta=True, weight='pyramid'):

@@ -416,3 +416,27 @@ def test_scatter_conv3x3_cout16(cuda, conv_mode, n, h, w, cin, pre):
     check(nchw(dst.view(32, 16)), want)
     assert torch.all(dst.t[..., :32] == 7.0) and torch.all(dst.t[..., 48:] == 7.0)      # neighbours untouched
     assert op.flops == 2.0 * n * h * w * cin * 16 * 9
+
+
+@pytest.mark.parametrize("n,h,w,cout,relu", [(2, 64, 96, 64, True), (1, 13, 24, 64, False), (3, 40, 8, 32, True), (1, 512, 512, 64, True)])
+def test_first_layer_from_packed_3_channel_tile(cuda, n, h, w, cout, relu):
+    """SNB_CONV_FIRST_3X3: conv3x3 (Cin = 3, padding 1) whose K = 32 operand rows are built in shared memory from the packed
+    NHWC bf16 tile, against torch on the same bf16-rounded input and weights; ragged heights, one- and many-tile widths."""
+    g = torch.Generator(device="cuda").manual_seed(h + w)
+    x = torch.randn((n, 3, h, w), device="cuda", generator=g)
+    src = E.Slab(n, h, w, 3, "cuda")
+    N.check(N.lib().snb_nchw_f32_to_nhwc3(N.ptr(x.contiguous()), n, h, w, N.c_vp(src.t.data_ptr()), N.stream_ptr()))
+    assert torch.equal(src.t, x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    dst = E.Slab(n, h, w, cout + 32, "cuda")
+    dst.t.fill_(7.0)
+    wt = torch.randn((cout, 3, 3, 3), device="cuda", generator=g) * 0.3
+    bias = torch.randn(cout, device="cuda", generator=g)
+    op = E.ConvOp(N.CONV_FIRST_3X3, src.view(), dst.view(32, cout), E.pack_first_conv3x3(wt), bias, relu=relu)
+    op(N.stream_ptr())
+    torch.cuda.synchronize()
+    want = F.conv2d(bf(x), bf(wt), bias, padding=1)
+    if relu:
+        want = F.relu(want)
+    check(nchw(dst.view(32, cout)), want)
+    assert torch.all(dst.t[..., :32] == 7.0)
+    assert op.flops == 2.0 * n * h * w * 27 * cout

@@ -129,6 +129,18 @@ def test_split_norm_layouts(cuda, tta):
     rows2 = torch.empty_like(rows)
     N.check(N.lib().snb_nchw_f32_to_patch32(N.ptr(out), n, 3, T, T, N.ptr(rows2), 0, N.stream_ptr()))
     assert torch.equal(rows2, rows)
+    # packed 3-channel bf16 tiles (6 bytes per pixel: the first-layer kernel builds its operand rows on chip)
+    nhwc = torch.full((n, T, T, 3), float("nan"), dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().snb_split_norm_u8(s.handle, N.ptr(d_img), 3, N.ptr(lut), tta, N.LAYOUT_NHWC3_BF16, N.ptr(nhwc), 0, n,
+                                      N.stream_ptr()))
+    assert torch.equal(nhwc.cpu().float(), x.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    nhwc2 = torch.empty_like(nhwc)
+    N.check(N.lib().snb_nchw_f32_to_nhwc3(N.ptr(out), n, T, T, N.ptr(nhwc2), N.stream_ptr()))
+    assert torch.equal(nhwc2, nhwc)
+    part = torch.zeros((2, T, T, 3), dtype=torch.bfloat16, device="cuda")           # a tile sub-range
+    N.check(N.lib().snb_split_norm_u8(s.handle, N.ptr(d_img), 3, N.ptr(lut), tta, N.LAYOUT_NHWC3_BF16, N.ptr(part), n - 2, 2,
+                                      N.stream_ptr()))
+    assert torch.equal(part, nhwc[n - 2:])
 
 
 def test_full_size_roundtrip_properties(cuda):

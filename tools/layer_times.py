@@ -26,7 +26,7 @@ else:
     m.load_state_dict(synth.vgg_unet_state_dict(name, seed=0))
 m = m.cuda().eval()
 plan = m.plan(batch, T, T, sigmoid=True)
-plan.x_patch.t.normal_()
+(plan.x_in3 if getattr(plan, 'x_in3', None) is not None else plan.x_patch).t.normal_()
 reps = 5
 for _ in range(2):
     plan.run()

@@ -35,8 +35,8 @@ def timed(fn, reps=5):
 
 
 def split():
-    N.check(lib.snb_split_norm_u8(pred.slicer.handle, N.ptr(img), 3, N.ptr(pred.lut), 0, N.LAYOUT_PATCH32,
-                                  N.c_vp(pred.plan.x_patch.t.data_ptr()), 0, batch, st))
+    layout, target = pred.plan.input_layout()
+    N.check(lib.snb_split_norm_u8(pred.slicer.handle, N.ptr(img), 3, N.ptr(pred.lut), 0, layout, N.c_vp(target), 0, batch, st))
 
 
 def copy():
