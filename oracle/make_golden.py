@@ -398,6 +398,24 @@ def linknet34_dropout_vectors():
     np.savez_compressed(os.path.join(OUT, "linknet34_dropout.npz"), train_x=xt.numpy(), keep=keep.numpy(), train_logits=yt)
 
 
+def unet_vectors():
+    """UNet (lib/models/unet.py) and UNetABN (lib/models/unet_abn.py, InPlaceABN through the pure-torch shim of the
+    un-vendored backend: parity unpinned at that boundary) in eval mode -> tests/golden/unet.npz."""
+    from lib.models.unet import UNet
+    from lib.models.unet_abn import UNetABN
+
+    x = torch.from_numpy(np.random.RandomState(21).standard_normal((2, 3, 64, 96)).astype(np.float32))
+    out = dict(x=x.numpy())
+    for name, cls, abn in (("unet", UNet, False), ("unet_abn", UNetABN, True)):
+        m = cls()
+        res = m.load_state_dict(synth.unet_state_dict(seed=8, abn=abn), strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        m.eval()
+        with torch.no_grad():
+            out[name + "_logits"] = m(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "unet.npz"), **out)
+
+
 def inplace_abn_vectors():
     """lib.modules.abn.functions.InPlaceABN (the reference's own autograd glue: running-statistics update, saved tensors,
     eval-mode shortcut) driven through the pure-torch stand-in for the un-vendored backend: training and eval mode,
@@ -487,6 +505,7 @@ def main():
     predict_tiled_vector()
     loss_extra_vectors()
     linknet34_dropout_vectors()
+    unet_vectors()
     with open(os.path.join(OUT, "kats.json"), "w") as fh:
         json.dump(kats, fh, indent=1)
     for f in sorted(os.listdir(OUT)):

@@ -82,6 +82,34 @@ def zf_unet_forward(sd, x, quant=None, fold=False):
     return F.conv2d(x, sd['conv_final.weight'], sd['conv_final.bias'])
 
 
+def unet_forward(sd, x, abn=False, quant=None):
+    """UNet / UNetABN in eval mode (lib/models/unet.py:79-107, unet_abn.py:80-107): double_conv = (conv3x3 -> BatchNorm ->
+    ReLU) x 2, or (conv3x3 -> InPlaceABN [leaky 0.01]) x 2 with abn=True; MaxPool2d(2) down; nearest x2 upsampling +
+    torch.cat([skip, upsampled]) up; Dropout2d inactive; 1x1 output conv."""
+    q = quant if quant is not None else (lambda t: t)
+
+    def norm_act(t, prefix):
+        if abn:
+            return inplace_abn_eval(t, sd, prefix)
+        return F.relu(_bn_eval(t, sd, prefix))
+
+    def double_conv(t, prefix):
+        i2 = 2 if abn else 3
+        t = norm_act(F.conv2d(q(t), q(sd[prefix + '.0.weight']), sd[prefix + '.0.bias'], padding=1), prefix + '.1')
+        return norm_act(F.conv2d(q(t), q(sd[prefix + '.%d.weight' % i2]), sd[prefix + '.%d.bias' % i2], padding=1),
+                        prefix + '.%d' % (i2 + 1))
+
+    x1 = double_conv(x, 'inc.conv.conv')
+    xs = [x1]
+    for i in range(1, 5):
+        xs.append(double_conv(F.max_pool2d(q(xs[-1]), 2), 'down%d.mpconv.1.conv' % i))
+    t = xs[4]
+    for i, skip in zip(range(1, 5), (xs[3], xs[2], xs[1], xs[0])):
+        t = F.interpolate(q(t), scale_factor=2, mode='nearest')
+        t = double_conv(torch.cat([q(skip), t], dim=1), 'up%d.conv.conv' % i)
+    return F.conv2d(q(t), sd['outc.conv.weight'], sd['outc.conv.bias'])
+
+
 def _bn_relu_conv(x, sd, prefix, quant=None, padding=1):
     """DenseLayer / TransitionDown front: BatchNorm2d(eval) -> ReLU -> conv (lib/models/tiramisu.py:9-19,47-59)."""
     y = F.relu(F.batch_norm(x, sd[prefix + '.norm.running_mean'], sd[prefix + '.norm.running_var'],

@@ -31,56 +31,91 @@ __device__ __forceinline__ float load_target(const void* t, int64_t i) {
   return static_cast<const float*>(t)[i];
 }
 
+// byte / small integer -> float on the FMA pipe: 0x4B000000 | v is the float 2^23 + v (an I2F would go through the
+// 16-per-clock conversion unit, the pipe the exp / log / reciprocal of the loss already keep busy)
+__device__ __forceinline__ float small_uint_to_float(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
+
+// 4 targets of element group i4 as floats.  `big` is set when an int64 target is outside [0, 2^23) (then the exact
+// conversion is redone on the slow path)
 template <int DT>
-__device__ __forceinline__ void load_target4(const void* t, int64_t i4, float (&tv)[4]) {
+__device__ __forceinline__ void load_target4(const void* t, int64_t i4, float (&tv)[4], bool& big) {
   if (DT == SNB_DT_I64) {
     const longlong2* p = static_cast<const longlong2*>(t) + i4 * 2;
     const longlong2 a = __ldg(p), b = __ldg(p + 1);
-    tv[0] = (float)a.x; tv[1] = (float)a.y; tv[2] = (float)b.x; tv[3] = (float)b.y;
+    const long long v[4] = {a.x, a.y, b.x, b.y};
+    const unsigned long long any = (unsigned long long)(a.x | a.y | b.x | b.y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tv[k] = small_uint_to_float((uint32_t)v[k] & 0x7FFFFFu);
+    big = (any >> 23) != 0;
+    if (big) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tv[k] = (float)v[k];
+    }
   } else if (DT == SNB_DT_U8) {
-    const uchar4 a = __ldg(static_cast<const uchar4*>(t) + i4);
-    tv[0] = a.x; tv[1] = a.y; tv[2] = a.z; tv[3] = a.w;
+    const uint32_t w = __ldg(static_cast<const uint32_t*>(t) + i4);
+    tv[0] = small_uint_to_float(w & 255u); tv[1] = small_uint_to_float((w >> 8) & 255u);
+    tv[2] = small_uint_to_float((w >> 16) & 255u); tv[3] = small_uint_to_float(w >> 24);
   } else {
     const float4 a = __ldg(static_cast<const float4*>(t) + i4);
     tv[0] = a.x; tv[1] = a.y; tv[2] = a.z; tv[3] = a.w;
   }
 }
 
+template <int DT>
+__device__ __forceinline__ void load_target4(const void* t, int64_t i4, float (&tv)[4]) {
+  bool big;
+  load_target4<DT>(t, i4, tv, big);
+}
+
+// bce is accumulated as ln2 * sum log2(arg) - sum t * min(x, 0) (one multiply per block instead of one per element)
 struct LossAcc {
-  float bce, pt, p, t, focal;
+  float lg, lin, pt, p, t, focal;
   uint32_t n_pred, n_truth, n_tp;   // tp = n_tp, fp = n_pred - n_tp, fn = n_truth - n_tp, tn = n - n_pred - n_truth + n_tp
 };
 
+constexpr float kLn2 = 0.6931471805599453f, kLog2e = 1.4426950408889634f;
+
 // The integer decision must be exactly torch's `sigmoid(x) > 0.5` in float32.  For |x| > 1e-6 that is `x > 0`
 // (1 + exp(-x) rounds strictly below / above 2); only inside that sliver the rounded quotient decides, and there the
-// IEEE expression is evaluated (never taken on real data, warp-uniform skip otherwise).
-__device__ __forceinline__ bool sigmoid_gt_half(float x) {
-  if (fabsf(x) > 1e-6f) return x > 0.f;
-  return 1.f / (1.f + expf(-x)) > 0.5f;
-}
-
+// IEEE expression is evaluated.
 // One exponential serves everything: with e = exp(-|x|), d = 1 + e
 //   p = sigmoid(x)     = (x >= 0 ? 1 : e) / d
 //   z = logsigmoid(x)  = min(x, 0) - log(d)
 //   BCE-with-logits(z, t) = (1 - t) z - logsigmoid(z) = -t z + log(1 + exp(z)) = -t z + log(1 + p)     (z <= 0, exp(z) = p)
 // which is the reference's double squash (lib/losses.py:51-53).  With 1 + p = num / d, num = x >= 0 ? 2 + e : 1 + 2e:
 //   t == 0: bce = log(1 + p)                 t == 1: bce = log(num) - min(x, 0)
-// so a binary target costs ONE logarithm (3 SFU operations per element: ex2, rcp, lg2 -- with 5 bytes per element for
-// uint8 targets the SFU pipe, 16 results per clock per SM, is the next bound after HBM); any other target value takes
-// the general two-logarithm form.  The float sums use the SFU approximations (~2^-22 relative): they are
-// tolerance-checked (rel 5e-6; the reference itself sums in float32).
-__device__ __forceinline__ float bce_element(float x, float t, float& p_out) {
+// so a binary target costs ONE logarithm (3 SFU operations per element: ex2, rcp, lg2).  Everything unusual -- a target that
+// is not 0 or 1, a logit inside the |x| <= 1e-6 sliver -- is handled by ONE out-of-line fix-up per group of four elements
+// (never taken on real data), which keeps the main loop free of divergent regions.  The float sums use the SFU
+// approximations (~2^-22 relative): they are tolerance-checked (rel 5e-6; the reference itself sums in float32).
+// raw SFU instructions (the __expf / __log2f intrinsics wrap them in range checks and denormal rescaling: 5 and 4
+// instructions per call; here every argument is in range by construction: -|x| * log2(e) <= 0, log arguments in [1, 3])
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// the unusual element: general target value and / or a logit inside the |x| <= 1e-6 sliver (exact decision)
+__device__ __forceinline__ void loss_slow_element(float x, float t, float& lg, float& lin, bool& pred, bool& truth) {
+  truth = ((int)t & 0xff) != 0;                // target.byte() (metrics.py:33)
   const float e = __expf(-fabsf(x));
   const float d = 1.f + e;
-  const bool pos = x >= 0.f;
-  const float p = __fdividef(pos ? 1.f : e, d);
-  p_out = p;
-  const float xm = fminf(x, 0.f);
-  // branch-free for binary targets (a select, not a divergent branch: neighbouring lanes hold different targets)
-  const float arg = t == 1.f ? (pos ? 2.f + e : fmaf(2.f, e, 1.f)) : 1.f + p;
-  float b = __logf(arg) - t * xm;
-  if (t != 0.f && t != 1.f) b = __logf(1.f + p) - t * (xm - __logf(d));     // soft / non-binary targets: rare, whole warps skip it
-  return b;
+  const float p = __fdividef(x >= 0.f ? 1.f : e, d);
+  const float b = __logf(1.f + p) - t * (fminf(x, 0.f) - __logf(d));
+  lg = b * kLog2e;
+  lin = 0.f;
+  pred = fabsf(x) > 1e-6f ? x > 0.f : (1.f / (1.f + expf(-x)) > 0.5f);
 }
 
 // FocalLossBinary element (lib/losses.py:90-96): logpt = -bce, pt = exp(logpt), loss = (1 - pt)^gamma * bce
@@ -90,21 +125,48 @@ __device__ __forceinline__ float focal_element(float b, float gamma) {
   return w * b;
 }
 
-template <bool FOCAL>
-__device__ __forceinline__ float loss_accumulate(LossAcc& a, float x, float t, float gamma) {
-  float p;
-  const float b = bce_element(x, t, p);
-  a.bce += b;
-  a.pt += p * t;
-  a.p += p;
-  a.t += t;
-  if (FOCAL) a.focal += focal_element(b, gamma);
-  const bool pred = sigmoid_gt_half(x);     // metrics.py:31
-  const bool truth = ((int)t & 0xff) != 0;  // target.byte()
-  a.n_pred += pred;
-  a.n_truth += truth;
-  a.n_tp += pred && truth;
-  return b;
+// four elements; bout[k] = the per-element BCE when NEEDB
+template <bool FOCAL, bool NEEDB>
+__device__ __forceinline__ void loss_accumulate4(LossAcc& a, const float (&x)[4], const float (&t)[4], float gamma,
+                                                 float (&bout)[4]) {
+  float lg[4], lin[4], p[4];
+  bool pred[4], truth[4];
+  bool rare = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float e = ex2_approx(fabsf(x[k]) * -kLog2e);
+    const float r = rcp_approx(1.f + e);
+    const bool pos = x[k] >= 0.f;
+    p[k] = (pos ? 1.f : e) * r;
+    const float num = pos ? 2.f + e : fmaf(2.f, e, 1.f);
+    const bool one = t[k] == 1.f;
+    lg[k] = lg2_approx(one ? num : 1.f + p[k]);
+    lin[k] = t[k] * fminf(x[k], 0.f);
+    pred[k] = x[k] > 0.f;                       // metrics.py:31 outside the sliver
+    truth[k] = t[k] != 0.f;                     // target.byte() != 0 for a target that is 0 or 1
+    rare |= (fabsf(x[k]) <= 1e-6f) | (!one & (t[k] != 0.f));
+  }
+  if (rare) {                                   // one cold region per four elements
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((fabsf(x[k]) <= 1e-6f) | ((t[k] != 1.f) & (t[k] != 0.f))) loss_slow_element(x[k], t[k], lg[k], lin[k], pred[k], truth[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    a.lg += lg[k];
+    a.lin += lin[k];
+    a.pt = fmaf(p[k], t[k], a.pt);
+    a.p += p[k];
+    a.t += t[k];
+    if (FOCAL || NEEDB) {
+      const float b = fmaf(lg[k], kLn2, -lin[k]);
+      bout[k] = b;
+      if (FOCAL) a.focal += focal_element(b, gamma);
+    }
+    a.n_pred += pred[k];
+    a.n_truth += truth[k];
+    a.n_tp += pred[k] && truth[k];
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -185,30 +247,36 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
                                                           ReduceWs* __restrict__ ws, double* __restrict__ sums,
                                                           long long* __restrict__ counts) {
   LossAcc a{};
-  const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(logits) + i);
-    float tv[4];
+  const uint32_t n4 = (uint32_t)(n >> 2);                    // the host checks n < 2^33
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(logits) + i);
+    float tv[4], b[4];
     load_target4<DT>(targets, i, tv);
-    float4 b;
-    b.x = loss_accumulate<FOCAL>(a, x.x, tv[0], gamma);
-    b.y = loss_accumulate<FOCAL>(a, x.y, tv[1], gamma);
-    b.z = loss_accumulate<FOCAL>(a, x.z, tv[2], gamma);
-    b.w = loss_accumulate<FOCAL>(a, x.w, tv[3], gamma);
-    if (ELEM) reinterpret_cast<float4*>(elem)[i] = b;
+    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+    loss_accumulate4<FOCAL, ELEM>(a, x, tv, gamma, b);
+    if (ELEM) reinterpret_cast<float4*>(elem)[i] = make_float4(b[0], b[1], b[2], b[3]);
   }
-  // ragged tail (< 4 elements) handled by the first threads of block 0
+  // ragged tail (< 4 elements): the first threads of block 0, one element each, through the general (slow-path) formulas
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-    const int64_t i = (n4 << 2) + threadIdx.x;
-    const float b = loss_accumulate<FOCAL>(a, logits[i], load_target<DT>(targets, i), gamma);
+    const int64_t i = ((int64_t)n4 << 2) + threadIdx.x;
+    const float x = logits[i], t = load_target<DT>(targets, i);
+    float lg, lin;
+    bool pred, truth;
+    loss_slow_element(x, t, lg, lin, pred, truth);
+    const float e = __expf(-fabsf(x));
+    const float p = __fdividef(x >= 0.f ? 1.f : e, 1.f + e);
+    const float b = lg * kLn2;
+    a.lg += lg; a.lin += lin; a.pt = fmaf(p, t, a.pt); a.p += p; a.t += t;
+    if (FOCAL) a.focal += focal_element(b, gamma);
     if (ELEM) elem[i] = b;
+    a.n_pred += pred; a.n_truth += truth; a.n_tp += pred && truth;
   }
 
   __shared__ double s_f[8][5];
   __shared__ uint32_t s_i[8][3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float f0 = warp_sum(a.bce), f1 = warp_sum(a.pt), f2 = warp_sum(a.p), f3 = warp_sum(a.t);
+  const float f0 = fmaf(warp_sum(a.lg), kLn2, -warp_sum(a.lin)), f1 = warp_sum(a.pt), f2 = warp_sum(a.p), f3 = warp_sum(a.t);
   const float f4 = FOCAL ? warp_sum(a.focal) : 0.f;
   const uint32_t c0 = __reduce_add_sync(0xffffffffu, a.n_pred), c1 = __reduce_add_sync(0xffffffffu, a.n_truth);
   const uint32_t c2 = __reduce_add_sync(0xffffffffu, a.n_tp);
@@ -242,39 +310,58 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
   }
 }
 
+// truth bits (target.byte() != 0) of the four targets of element group i4, straight from the stored type
+template <int DT>
+__device__ __forceinline__ uint32_t load_truth4(const void* t, uint32_t i4) {
+  if (DT == SNB_DT_U8) {
+    const uint32_t w = __ldg(static_cast<const uint32_t*>(t) + i4);
+    return ((w & 0xffu) != 0) | (((w & 0xff00u) != 0) << 1) | (((w & 0xff0000u) != 0) << 2) | (((w >> 24) != 0) << 3);
+  } else if (DT == SNB_DT_I64) {
+    const longlong2* p = static_cast<const longlong2*>(t) + (size_t)i4 * 2;
+    const longlong2 a = __ldg(p), b = __ldg(p + 1);
+    return ((a.x & 0xff) != 0) | (((a.y & 0xff) != 0) << 1) | (((b.x & 0xff) != 0) << 2) | (((b.y & 0xff) != 0) << 3);
+  } else {
+    const float4 a = __ldg(static_cast<const float4*>(t) + i4);
+    return ((((int)a.x) & 0xff) != 0) | (((((int)a.y) & 0xff) != 0) << 1) | (((((int)a.z) & 0xff) != 0) << 2) |
+           (((((int)a.w) & 0xff) != 0) << 3);
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict__ probs, const void* __restrict__ targets,
                                                         int64_t n, float thr, ReduceWs* __restrict__ ws,
                                                         long long* __restrict__ counts) {
-  uint32_t c[4] = {0, 0, 0, 0};
-  auto add = [&](float p, float t) {
-    const bool pred = p > thr;
-    const bool truth = ((int)t & 0xff) != 0;
-    c[0] += pred && truth; c[1] += pred && !truth; c[2] += !pred && truth; c[3] += !pred && !truth;
+  // n_pred, n_truth, n_tp (tp / fp / fn / tn follow from them and n)
+  uint32_t n_pred = 0, n_truth = 0, n_tp = 0;
+  auto add4 = [&](const float4& x, uint32_t tb) {
+    const uint32_t pb = (x.x > thr) | ((x.y > thr) << 1) | ((x.z > thr) << 2) | ((x.w > thr) << 3);
+    n_pred += __popc(pb);
+    n_truth += __popc(tb);
+    n_tp += __popc(pb & tb);
   };
-  const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // two 16-byte probability loads in flight per thread and iteration (the counting itself is a handful of integer ops)
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (; i + stride < n4; i += 2 * stride) {
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(probs) + i);
-    const float4 x1 = __ldg(reinterpret_cast<const float4*>(probs) + i + stride);
-    float t0[4], t1[4];
-    load_target4<DT>(targets, i, t0);
-    load_target4<DT>(targets, i + stride, t1);
-    add(x0.x, t0[0]); add(x0.y, t0[1]); add(x0.z, t0[2]); add(x0.w, t0[3]);
-    add(x1.x, t1[0]); add(x1.y, t1[1]); add(x1.z, t1[2]); add(x1.w, t1[3]);
+  const uint32_t n4 = (uint32_t)(n >> 2);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // four 16-byte probability loads (and their targets) in flight per thread and trip
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 x[4];
+    uint32_t tb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x[u] = __ldg(reinterpret_cast<const float4*>(probs) + i + u * stride);
+      tb[u] = load_truth4<DT>(targets, i + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add4(x[u], tb[u]);
   }
-  if (i < n4) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(probs) + i);
-    float tv[4];
-    load_target4<DT>(targets, i, tv);
-    add(x.x, tv[0]); add(x.y, tv[1]); add(x.z, tv[2]); add(x.w, tv[3]);
-  }
+  for (; i < n4; i += stride) add4(__ldg(reinterpret_cast<const float4*>(probs) + i), load_truth4<DT>(targets, i));
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-    const int64_t j = (n4 << 2) + threadIdx.x;
-    add(probs[j], load_target<DT>(targets, j));
+    const int64_t j = ((int64_t)n4 << 2) + threadIdx.x;
+    const bool pred = probs[j] > thr;
+    const bool truth = ((int)load_target<DT>(targets, j) & 0xff) != 0;
+    n_pred += pred; n_truth += truth; n_tp += pred && truth;
   }
+  const uint32_t c[4] = {n_tp, n_pred - n_tp, n_truth - n_tp, 0};
   __shared__ uint32_t s_i[8][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -294,7 +381,8 @@ __global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict_
   sum_slots<0 + 1, 4>(ws, gridDim.x, f, tot);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) counts[k] = (long long)tot[k];
+    for (int k = 0; k < 3; ++k) counts[k] = (long long)tot[k];
+    counts[3] = (long long)n - (long long)(tot[0] + tot[1] + tot[2]);
     ws->ticket = 0;
   }
 }
@@ -452,6 +540,7 @@ extern "C" int snb_loss_iou_reduce(const float* d_logits, const void* d_targets,
   if (int rc = check_workspace(d_workspace)) return rc;
   if (int rc = check_targets(d_targets, target_dtype, n, true)) return rc;
   if (reinterpret_cast<uintptr_t>(d_logits) & 15) return fail(SNB_E_INVALID, "logits must be 16-byte aligned");
+  if (n >= (int64_t(1) << 33)) return fail(SNB_E_UNSUPPORTED, "more than 2^33 elements");
   if (d_elem_bce && (reinterpret_cast<uintptr_t>(d_elem_bce) & 15)) return fail(SNB_E_INVALID, "d_elem_bce must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (n == 0) {
@@ -515,6 +604,7 @@ extern "C" int snb_confusion_counts(const float* d_probs, const void* d_targets,
     SNB_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), st));
     return SNB_OK;
   }
+  if (n >= (int64_t(1) << 33)) return fail(SNB_E_UNSUPPORTED, "more than 2^33 elements");
   const int grid = reduce_grid((n + 3) / 4);
   ReduceWs* ws = static_cast<ReduceWs*>(d_workspace);
   long long* cnt = reinterpret_cast<long long*>(d_counts);

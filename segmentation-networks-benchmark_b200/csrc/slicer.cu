@@ -61,11 +61,14 @@ struct BorderPixel {
 // source column lies inside the image), so the run is copied as aligned 16-byte stores fed by two aligned 16-byte loads and
 // a funnel shift (source and destination are misaligned by an arbitrary byte count: 3-byte pixels, odd margins); only the
 // reflected / constant border pixels at the two ends of a row and the sub-16-byte fringes of the run go through the
-// per-byte reflect-101 map.  Bit-exact for any element size.
+// per-byte reflect-101 map.  Bit-exact for any element size.  (The border pixel is a __grid_constant__ parameter: indexed
+// dynamically it would otherwise be copied byte by byte into every thread's local memory, which ncu showed as 36 % of
+// all stall samples.)
 constexpr int kSplitRows = 8;   // tile rows (= warps) per block
 
 __global__ void __launch_bounds__(256) split_hwc_kernel(SlicerGeom g, const uint8_t* __restrict__ src, int pixel_bytes,
-                                                        int border_mode, BorderPixel border, uint8_t* __restrict__ dst,
+                                                        int border_mode, const __grid_constant__ BorderPixel border,
+                                                        uint8_t* __restrict__ dst,
                                                         int64_t tile_begin, int64_t total_rows) {
   const int T = (int)g.tile;
   const int row_bytes = T * pixel_bytes;

@@ -440,6 +440,92 @@ class ZFUNetPlan:
     run = VGGUNetPlan.run
 
 
+def fold_norm(conv_w, conv_b, norm):
+    """conv -> BatchNorm2d(eval) or InPlaceABN(eval) as one conv.  norm = (gamma, beta, mean, var, eps, abn); the ABN scale
+    is |gamma| + eps (mapillary's kernel)."""
+    gamma, beta, mean, var, eps, abn = norm
+    g = (gamma.detach().float().abs() + eps) if abn else gamma.detach().float()
+    scale = g / torch.sqrt(var.detach().float() + eps)
+    b0 = conv_b.detach().float() if conv_b is not None else torch.zeros_like(scale)
+    return conv_w.detach().float() * scale.view(-1, 1, 1, 1), (b0 - mean.detach().float()) * scale + beta.detach().float()
+
+
+class UNetPlan:
+    """UNet / UNetABN forward (lib/models/unet.py:79-107, unet_abn.py:80-107) in eval mode: BatchNorm / InPlaceABN folded
+    into the convolutions, MaxPool2d fused into the producing conv's epilogue, nn.Upsample(2, nearest) fused into the
+    producing conv's store (the tile is TMA-stored to its 2x2 replicated positions inside the consumer's concat slab,
+    torch.cat([skip, upsampled]) order), Dropout2d inactive, the 1x1 `outc` fused as head.
+
+    blocks: the 9 double_conv modules in forward order (inc, down1-4, up1-4), each ((w1, b1, norm1), (w2, b2, norm2));
+    final = (w, b) of outc; act_slope = 0 (ReLU) or 0.01 (InPlaceABN's leaky-ReLU)."""
+
+    def __init__(self, blocks, final, n, h, w, device, sigmoid, dtype=torch.bfloat16, act_slope=0.0):
+        self.dtype = dtype
+        if h % 16 or w % 16:
+            raise ValueError("height and width must be multiples of 16 (four 2x2 poolings)")
+        nf = blocks[0][0][0].shape[0]
+        if final[0].shape[0] != 1 or nf != 32:
+            raise NotImplementedError("fused head expects n_classes == 1 and n_filters == 32")
+        self.n, self.h, self.w, self.device = n, h, w, device
+        self.ops = []
+        S = lambda hh, ww, c: Slab(n, hh, ww, c, device, dtype)
+        ec = [blocks[i][1][0].shape[0] for i in range(5)]                    # nf, 2nf, 4nf, 8nf, 8nf
+        upc = [blocks[7][1][0].shape[0], blocks[6][1][0].shape[0], blocks[5][1][0].shape[0], ec[4]]   # into level 0..3
+        slabs = [S(h >> l, w >> l, ec[l] + upc[l]) for l in range(4)]       # [skip | upsampled deeper features]
+        self.slabs = slabs
+
+        def conv(src, dst, layer, first=False, **kw):
+            wt, bs = fold_norm(*layer)
+            if first:
+                self.ops.append(first_layer(self, S, dtype, n, h, w, dst, wt, bs.contiguous())
+                                if act_slope == 0.0 else self._first_leaky(S, dtype, n, h, w, dst, wt, bs.contiguous(), act_slope))
+            else:
+                self.ops.append(ConvOp(N.CONV_3X3, src, dst, pack_conv3x3(wt, dtype), bs.contiguous(), act_slope=act_slope, **kw))
+
+        cur = None
+        for l in range(5):                                                   # inc, down1..down4
+            hh, ww = h >> l, w >> l
+            l1, l2 = blocks[l]
+            mid = S(hh, ww, ec[l]).view()
+            conv(cur, mid, l1, first=(l == 0))
+            if l < 4:
+                pooled = S(hh // 2, ww // 2, ec[l]).view()
+                conv(mid, slabs[l].view(0, ec[l]), l2, pool_dst=pooled)
+                cur = pooled
+            else:                                                            # x5: upsampled straight into level 3's slab
+                conv(mid, slabs[3].view(ec[3], ec[4]), l2, upsample2x=True)
+        for i in range(3):                                                   # up1..up3 at levels 3, 2, 1
+            lvl = 3 - i
+            hh, ww = h >> lvl, w >> lvl
+            l1, l2 = blocks[5 + i]
+            c_out = l1[0].shape[0]
+            mid = S(hh, ww, c_out).view()
+            conv(slabs[lvl].view(), mid, l1)
+            conv(mid, slabs[lvl - 1].view(ec[lvl - 1], c_out), l2, upsample2x=True)
+        l1, l2 = blocks[8]                                                   # up4 + outc
+        mid = S(h, w, nf).view()
+        conv(slabs[0].view(), mid, l1)
+        self.out = torch.empty((n, h, w), dtype=torch.float32, device=device)
+        wt, bs = fold_norm(*l2)
+        head = (final[0].detach().reshape(32).float().contiguous(), float(final[1].detach().reshape(-1)[0]), sigmoid, self.out)
+        self.ops.append(ConvOp(N.CONV_3X3, mid, None, pack_conv3x3(wt, dtype), bs.contiguous(), head=head, act_slope=act_slope))
+        self.ops[-1].flops += 2.0 * n * h * w * 32
+        self.flops = sum(op.flops for op in self.ops)
+        self.launches = sum(op.launches for op in self.ops)
+
+    def _first_leaky(self, S, dtype, n, h, w, dst, wt, bias, slope):
+        """first conv with a leaky activation (UNetABN): the 3-channel first-layer kernel only knows ReLU, so the PATCH32
+        operand rows and the K = 32 conv1x1 (common epilogue with the activation slope) are used"""
+        self.x_in3 = None
+        self.x_patch = S(h, w, 32)
+        return ConvOp(N.CONV_1X1, self.x_patch.view(), dst, pack_first_conv3x3(wt, dtype), bias, act_slope=slope,
+                      real=(9 * wt.shape[1], wt.shape[0]))
+
+    load_nchw = VGGUNetPlan.load_nchw
+    input_layout = VGGUNetPlan.input_layout
+    run = VGGUNetPlan.run
+
+
 # ---------------------------------------------------------------------------------------------- FCDenseNet
 # out[2y+py] = sum in[y+dy] * W[ky] for ConvTranspose2d(k=3, s=2, p=0) cropped to [0, 2h): py=0 -> (dy=0, ky=0),
 # (dy=-1, ky=2); py=1 -> (dy=0, ky=1) and one unused slot (zero weights)

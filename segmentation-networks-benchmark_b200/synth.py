@@ -205,3 +205,36 @@ def logits_targets(seed, shape):
     logits = torch.from_numpy(rs.standard_normal(shape).astype(np.float32))
     targets = torch.from_numpy((rs.rand(*shape) > 0.5).astype(np.int64))
     return logits, targets
+
+
+def unet_state_dict(seed=0, abn=False, n_filters=32):
+    """He-initialised weights with the reference's UNet / UNetABN key names (lib/models/unet.py, unet_abn.py); norm buffers
+    randomised so that folding is exercised; ABN weights get mixed signs (the |weight| + eps scale)."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+    nf = n_filters
+
+    def double_conv(prefix, cin, cout):
+        i2 = 2 if abn else 3
+        for ci, c_in in ((0, cin), (i2, cout)):
+            sd['%s.%d.weight' % (prefix, ci)] = _he(rs, (cout, c_in, 3, 3), 9 * c_in, 0.9)
+            sd['%s.%d.bias' % (prefix, ci)] = _bias(rs, cout)
+            n = '%s.%d' % (prefix, ci + 1)
+            w = torch.from_numpy(rs.uniform(0.5, 1.5, cout).astype(np.float32))
+            if abn:
+                w = w * torch.from_numpy(np.where(rs.rand(cout) < 0.3, -1.0, 1.0).astype(np.float32))
+            sd[n + '.weight'] = w
+            sd[n + '.bias'] = torch.from_numpy((rs.standard_normal(cout) * 0.1).astype(np.float32))
+            sd[n + '.running_mean'] = torch.from_numpy((rs.standard_normal(cout) * 0.1).astype(np.float32))
+            sd[n + '.running_var'] = torch.from_numpy(rs.uniform(0.5, 1.5, cout).astype(np.float32))
+            if not abn:
+                sd[n + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.int64)
+
+    double_conv('inc.conv.conv', 3, nf)
+    for i, (a, b) in enumerate([(nf, 2 * nf), (2 * nf, 4 * nf), (4 * nf, 8 * nf), (8 * nf, 8 * nf)], 1):
+        double_conv('down%d.mpconv.1.conv' % i, a, b)
+    for i, (a, b) in enumerate([(16 * nf, 4 * nf), (8 * nf, 2 * nf), (4 * nf, nf), (2 * nf, nf)], 1):
+        double_conv('up%d.conv.conv' % i, a, b)
+    sd['outc.conv.weight'] = _he(rs, (1, nf, 1, 1), nf, 0.5)
+    sd['outc.conv.bias'] = _bias(rs, 1)
+    return sd

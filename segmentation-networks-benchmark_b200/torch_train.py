@@ -97,3 +97,38 @@ def validate(model, loss, dataloader, epoch: int, metrics=dict(), summary_writer
         for key, value in scores.items():
             summary_writer.add_scalar('val/epoch/' + key, value.avg, epoch)
     return losses, scores
+
+
+def get_loss(loss):
+    """torch_train.py:75-96: the registry strings of the binary losses."""
+    loss = str.lower(loss)
+    if loss == 'smooth_jaccard':
+        return L.SmoothJaccardLoss()
+    if loss == 'jaccard':
+        return L.JaccardLoss()
+    if loss == 'bce_jaccard':
+        return L.BCEWithLogitsLossAndSmoothJaccard()
+    if loss == 'focal':
+        return L.FocalLossBinary(size_average=False)
+    if loss == 'bce':
+        return L.BCEWithSigmoidLoss()
+    raise ValueError(loss)
+
+
+def get_model(model_name, patch_size=None, num_channels=3):
+    """torch_train.py:99-147 for the models built on the native engine; the ResNet101/152-based registry entries (gcn,
+    psp_net, duc, linknext, dilated_linknet34, squeezenet) need dilation / bilinear up-sampling kernels and are out of scope."""
+    from .lib import models as MM
+
+    model_name = str.lower(model_name)
+    if num_channels != 3:
+        raise NotImplementedError("the native first-layer kernels take 3-channel images")
+    table = {'unet': MM.UNet, 'unet_abn': MM.UNetABN, 'zf_unet': MM.ZF_UNET,
+             'unet11': lambda: MM.UNet11(pretrained=True), 'unet16': lambda: MM.UNet16(pretrained=True),
+             'linknet34': lambda: MM.LinkNet34(pretrained=True, num_channels=num_channels, num_classes=1),
+             'tiramisu67': lambda: MM.FCDenseNet67(n_classes=1)}
+    if model_name in table:
+        return table[model_name]()
+    if model_name in ('dilated_linknet34', 'linknext', 'gcn', 'gcn34', 'psp_net', 'duc', 'duc_dc', 'squeezenet'):
+        raise NotImplementedError("registry model %r is outside the hot-path scope (SURVEY 8f.4)" % model_name)
+    raise ValueError(model_name)

@@ -501,3 +501,36 @@ def test_linknet34_fused_train_step_and_stale_backward(cuda):
     _ = m(x)                                     # second forward of the same shape overwrites the saved activations
     with pytest.raises(RuntimeError):
         crit(y1, t).backward()
+
+
+@pytest.mark.parametrize("name,abn", [("unet", False), ("unet_abn", True)])
+def test_unet_against_reference_vectors(cuda, golden_dir, name, abn):
+    """Registry models 'unet' / 'unet_abn' (lib/models/unet.py, unet_abn.py; torch_train.py:103-107): same keys, eval
+    forward on the native engine (norm folded, pool / upsample / concat / head fused) against the reference's logits."""
+    from snb_b200.lib.models import UNet, UNetABN
+
+    g = np.load(os.path.join(golden_dir, "unet.npz"))
+    m = (UNetABN if abn else UNet)()
+    sd = synth.unet_state_dict(seed=8, abn=abn)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).cuda()).cpu()
+        y2 = m(torch.from_numpy(g["x"]).cuda()).cpu()
+    ref = torch.from_numpy(g[name + "_logits"])
+    assert y.shape == ref.shape and torch.equal(y, y2)
+    p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    assert p_err < BF16_PROB_TOL, p_err
+    with torch.no_grad():
+        q = no.unet_forward(sd, torch.from_numpy(g["x"]), abn=abn, quant=no.bf16_round)
+    assert (y - q).abs().max().item() < 0.03 * max(1.0, q.abs().max().item())
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.from_numpy(g["x"]).cuda())
+    # through the tiled predictor
+    from snb_b200 import inria_submit as sub
+    m.eval()
+    image = synth.image_u8(5, 100, 120)
+    merged, mask = sub.TiledPredictor(m, image.shape, 64, 32, batch_size=4, tta=False).predict_device(torch.from_numpy(image).cuda())
+    assert torch.isfinite(merged).all() and torch.equal(mask, ((merged > 0.5) * 255).to(torch.uint8))

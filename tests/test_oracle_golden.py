@@ -264,3 +264,14 @@ def test_linknet34_train_mode_with_dropout(golden_dir):
     with torch.no_grad():
         y, _ = no.linknet34_forward_train(sd, torch.from_numpy(g["train_x"]), keep=torch.from_numpy(g["keep"]))
     assert np.abs(y.numpy() - g["train_logits"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("name,abn", [("unet", False), ("unet_abn", True)])
+def test_unet_logits(golden_dir, name, abn):
+    """UNet / UNetABN restatement against the reference modules in eval mode (tests/golden/unet.npz)."""
+    g = np.load(os.path.join(golden_dir, "unet.npz"))
+    sd = synth.unet_state_dict(seed=8, abn=abn)
+    with torch.no_grad():
+        y = no.unet_forward(sd, torch.from_numpy(g["x"]), abn=abn).numpy()
+    assert y.shape == g[name + "_logits"].shape == (2, 1, 64, 96)
+    assert np.abs(y - g[name + "_logits"]).max() < 2e-5
