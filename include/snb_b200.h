@@ -319,7 +319,9 @@ SNB_API int snb_abn_backward(const float* d_z, const float* d_dz, int64_t n, int
  * momentum and the unbiased variance, then out = act(x * scale + shift [+ residual]) [+ residual];
  * abn != 0 uses gamma = |weight| + eps (the InPlaceABN backend); act_slope >= 0: leaky-ReLU with that slope (0 = ReLU),
  * act_slope < 0: no activation.  d_scale / d_shift / d_mean / d_var: float[channels] outputs (the fused normalisation and
- * the statistics, kept for the backward pass); d_workspace: double[2 * channels].  channels % 8 == 0, <= 2048. */
+ * the statistics, kept for the backward pass).  d_workspace: double[3 * channels + 2], zeroed ONCE by the caller and left
+ * zeroed by every call (the last block of the statistics kernel finalises and clears it: two launches per call, no
+ * memset); calls that may overlap need their own workspace.  channels % 8 == 0, <= 2048. */
 SNB_API int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t channels, int64_t in_cstride, const float* d_gamma,
                       const float* d_beta, int abn, float eps, float momentum, float* d_running_mean,
                       float* d_running_var, float act_slope, const void* d_residual, int64_t res_cstride,
@@ -330,20 +332,21 @@ SNB_API int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t channels
  * itself).  d_x = the raw convolution output the forward normalised, d_scale / d_shift / d_mean / d_var = what the forward
  * returned, d_res_before = the residual added before the activation (or NULL).  Outputs: d_dx (gradient of x, bf16 slab),
  * d_dres (gradient of r_before = dz, or NULL), d_dgamma / d_dbeta (float[channels]; dgamma carries sign(weight) when
- * abn != 0, as the InPlaceABN backend does), d_workspace double[2 * channels]. */
+ * abn != 0, as the InPlaceABN backend does), d_workspace double[3 * channels + 2] (zeroed once, left zeroed: see above). */
 SNB_API int snb_bn_backward_nhwc(const void* d_x, int64_t x_cstride, const void* d_dout, int64_t dout_cstride, int64_t pixels,
                          int64_t channels, const float* d_scale, const float* d_shift, const float* d_mean,
                          const float* d_var, const float* d_gamma, int abn, float eps, float act_slope,
                          const void* d_res_before, int64_t res_cstride, void* d_dx, int64_t dx_cstride, void* d_dres,
                          int64_t dres_cstride, float* d_dgamma, float* d_dbeta, double* d_workspace, void* stream);
-/* out[c] = sum over pixels of a bf16 slab (bias gradients); channels % 8 == 0; d_workspace double[2 * channels] */
+/* out[c] = sum over pixels of a bf16 slab (bias gradients); channels % 8 == 0; d_workspace double[3 * channels + 2]
+ * (zeroed once, left zeroed) */
 SNB_API int snb_channel_sum_nhwc(const void* d_in, int64_t pixels, int64_t channels, int64_t in_cstride, float* d_out,
                          double* d_workspace, void* stream);
 /* backward of nn.MaxPool2d(3, 2, 1) (lib/models/linknet.py:44): d_in = the forward input (arg-max recomputed, first
  * maximum wins as in PyTorch), d_dout = gradient of the pooled tensor, d_din = gradient of the input */
 SNB_API int snb_maxpool3x3s2_backward(const void* d_in, int64_t n, int64_t h, int64_t w, int64_t channels, int64_t in_cstride,
                               const void* d_dout, int64_t dout_cstride, void* d_din, int64_t din_cstride, void* stream);
-/* elementwise on bf16 slabs: mode 0 out = a + b (gradient fan-in); mode 1 out = a * (b > 0 ? 1 : slope) (gradient a through
+/* elementwise on bf16 slabs (channels % 8 == 0): mode 0 out = a + b (gradient fan-in); mode 1 out = a * (b > 0 ? 1 : slope) (gradient a through
  * a leaky-ReLU whose output is b) */
 SNB_API int snb_ew_nhwc(const void* d_a, int64_t a_cstride, const void* d_b, int64_t b_cstride, void* d_out, int64_t out_cstride,
                 int64_t pixels, int64_t channels, int mode, float slope, void* stream);

@@ -211,10 +211,74 @@ __global__ void abn_param_grads_kernel(const double* __restrict__ sums, const fl
 // float atomics across the pixel lanes of a CTA, then one float64 atomic per channel and CTA.
 constexpr int kBnMaxCV = 256;   // <= 2048 channels
 
+// What the LAST block of a statistics kernel does with the finished per-channel sums (one launch instead of memset +
+// reduce + finalize): the block that draws the last ticket reads the sums, writes the derived per-channel values, and puts
+// the workspace back to its "zero at rest" state.  Workspace = double[2 C] sums, then a 64-bit ticket word, then
+// float[2 C] reduced values for the backward apply kernel: double[3 C + 2] in total, zeroed ONCE by the caller.
+struct BnFinalize {
+  int mode;                  // 1: BatchNorm forward (scale / shift / statistics), 2: channel sums, 3: backward (means + dgamma / dbeta)
+  int C, abn;
+  double count;
+  float eps, momentum;
+  const __nv_bfloat16* pivot;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* scale;
+  float* shift;
+  float* mean_out;
+  float* var_out;
+  float* out0;               // mode 2: sums; mode 3: dgamma
+  float* out1;               // mode 3: dbeta
+};
+
+__device__ __forceinline__ void bn_last_block_finalize(double* __restrict__ sums, const BnFinalize& f) {
+  __shared__ unsigned int s_last;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * f.C);
+  float* red = reinterpret_cast<float*>(sums + 2 * f.C + 1);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
+    const double s0 = __ldcg(sums + 2 * c), s1 = __ldcg(sums + 2 * c + 1);
+    sums[2 * c] = 0.0;
+    sums[2 * c + 1] = 0.0;
+    if (f.mode == 1) {
+      // mean / biased variance -> fused scale and shift of the normalisation; running statistics as nn.BatchNorm2d and
+      // functions.py:84-85 update them (momentum, unbiased variance).  abn != 0: gamma = |weight| + eps (InPlaceABN backend)
+      const double ms = s0 / f.count;                              // mean of (x - pivot), pivot = pixel 0
+      double v = s1 / f.count - ms * ms;
+      v = v < 0.0 ? 0.0 : v;
+      const double m = ms + (double)__bfloat162float(f.pivot[c]);
+      const float g = f.gamma ? (f.abn ? fabsf(f.gamma[c]) + f.eps : f.gamma[c]) : 1.f;
+      const float sc = g * rsqrtf((float)v + f.eps);
+      f.scale[c] = sc;
+      f.shift[c] = (f.beta ? f.beta[c] : 0.f) - (float)m * sc;
+      if (f.mean_out) f.mean_out[c] = (float)m;
+      if (f.var_out) f.var_out[c] = (float)v;
+      if (f.running_mean) f.running_mean[c] = f.running_mean[c] * (1.f - f.momentum) + f.momentum * (float)m;
+      if (f.running_var && f.count > 1.0)
+        f.running_var[c] = f.running_var[c] * (1.f - f.momentum) + (float)(f.momentum * v * f.count / (f.count - 1.0));
+    } else if (f.mode == 2) {
+      f.out0[c] = (float)s0;
+    } else {
+      red[2 * c] = (float)(s0 / f.count);                          // mean dz, mean dz * xhat: read by the apply kernel
+      red[2 * c + 1] = (float)(s1 / f.count);
+      if (f.out0) f.out0[c] = (float)((f.abn && f.gamma && f.gamma[c] <= 0.f) ? -s1 : s1);
+      if (f.out1) f.out1[c] = (float)s0;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // PIVOT: accumulate (x - p), (x - p)^2 with p = the channel's value at pixel 0 (see abn_stats_kernel)
 template <bool PIVOT>
 __global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restrict__ in, int CV, int in_sv, int64_t pixels,
-                                                            double* __restrict__ sums) {
+                                                            double* __restrict__ sums, const BnFinalize fin) {
   __shared__ float sh[kBnMaxCV * 16];          // [pixel lane][channel][sum, sum of squares]: blockDim.x * 16 floats
   const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
   float s[8], q[8], pvt[8];
@@ -257,31 +321,7 @@ __global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const uint4* __restr
     for (int k = 0; k < ppb; ++k) t += sh[k * CV * 16 + i];
     atomicAdd(sums + i, (double)t);
   }
-}
-
-// mean / biased variance -> fused scale and shift of the normalisation; running statistics as nn.BatchNorm2d and
-// functions.py:84-85 update them (momentum, unbiased variance).  abn != 0: gamma = |weight| + eps (InPlaceABN backend)
-__global__ void bn_finalize_nhwc_kernel(const double* __restrict__ sums, const __nv_bfloat16* __restrict__ pivot, int C,
-                                        double count, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, int abn, float eps, float momentum,
-                                        float* __restrict__ running_mean, float* __restrict__ running_var,
-                                        float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                        float* __restrict__ var_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double ms = sums[2 * c] / count;                       // mean of (x - pivot), pivot = pixel 0
-  double v = sums[2 * c + 1] / count - ms * ms;
-  v = v < 0.0 ? 0.0 : v;
-  const double m = ms + (double)__bfloat162float(pivot[c]);
-  const float g = gamma ? (abn ? fabsf(gamma[c]) + eps : gamma[c]) : 1.f;
-  const float sc = g * rsqrtf((float)v + eps);
-  scale[c] = sc;
-  shift[c] = (beta ? beta[c] : 0.f) - (float)m * sc;
-  if (mean_out) mean_out[c] = (float)m;
-  if (var_out) var_out[c] = (float)v;
-  if (running_mean) running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * (float)m;
-  if (running_var && count > 1.0)
-    running_var[c] = running_var[c] * (1.f - momentum) + (float)(momentum * v * count / (count - 1.0));
+  bn_last_block_finalize(sums, fin);
 }
 
 // out = act(x * scale + shift (+ residual before the activation)) (+ residual after it); act: slope >= 0 -> leaky-ReLU
@@ -339,7 +379,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc_kernel(const uint4* __
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                                  const float* __restrict__ mean, const float* __restrict__ var,
                                                                  float eps, float slope, int64_t pixels,
-                                                                 double* __restrict__ sums) {
+                                                                 double* __restrict__ sums, const BnFinalize fin) {
   __shared__ float sh[kBnMaxCV * 16];          // [pixel lane][channel][sum dz, sum dz * xhat]: blockDim.x * 16 floats
   const int v = threadIdx.x % CV, pl = threadIdx.x / CV, ppb = blockDim.x / CV;
   float s[8], q[8];
@@ -385,6 +425,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc_kernel(const uint4* __
     for (int k = 0; k < ppb; ++k) t += sh[k * CV * 16 + i];
     atomicAdd(sums + i, (double)t);
   }
+  bn_last_block_finalize(sums, fin);
 }
 
 // dx = gamma' * invstd * (dz - mean(dz) - xhat * mean(dz * xhat)); optionally dz itself (the gradient of r_before)
@@ -393,8 +434,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc_kernel(const uint4* __r
                                                                 const uint4* __restrict__ rb, int rb_sv,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ var,
-                                                                float eps, float slope, const double* __restrict__ sums,
-                                                                double count, uint4* __restrict__ dx, int dx_sv,
+                                                                float eps, float slope, const float* __restrict__ red,
+                                                                uint4* __restrict__ dx, int dx_sv,
                                                                 uint4* __restrict__ dres, int dres_sv, int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
@@ -415,27 +456,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc_kernel(const uint4* __r
       float dz = __bfloat162float(ge[e]);
       if (slope >= 0.f && !(u > 0.f)) dz *= slope;
       const float xhat = (xv - __ldg(mean + c)) * is;
-      const float edz = (float)(sums[2 * c] / count), eydz = (float)(sums[2 * c + 1] / count);
+      const float edz = __ldg(red + 2 * c), eydz = __ldg(red + 2 * c + 1);
       od[e] = __float2bfloat16(sc * (dz - edz - xhat * eydz));      // scale = gamma' * invstd
       oz[e] = __float2bfloat16(dz);
     }
     dx[pix * dx_sv + cv] = *reinterpret_cast<uint4*>(od);
     if (dres) dres[pix * dres_sv + cv] = *reinterpret_cast<uint4*>(oz);
   }
-}
-
-__global__ void bn_bwd_params_nhwc_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, int abn, int C,
-                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (dgamma) dgamma[c] = (float)((abn && gamma && gamma[c] <= 0.f) ? -sums[2 * c + 1] : sums[2 * c + 1]);
-  if (dbeta) dbeta[c] = (float)sums[2 * c];
-}
-
-// per-channel sum of a bf16 slab (bias gradients): reuses the statistics kernel, keeps sum only
-__global__ void channel_sum_finalize_kernel(const double* __restrict__ sums, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) out[c] = (float)sums[2 * c];
 }
 
 static int abn_check(const void* x, int64_t n, int64_t c, int64_t hw, int act) {
@@ -536,12 +563,13 @@ extern "C" int snb_bn_train_nhwc(const void* d_in, int64_t pixels, int64_t chann
   const int ppb = threads / cv;
   const int64_t want = (pixels + ppb * 4 - 1) / (ppb * 4);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
-  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
-  bn_stats_nhwc_kernel<true><<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
-  bn_finalize_nhwc_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, static_cast<const __nv_bfloat16*>(d_in),
-                                                                            (int)channels, (double)pixels, d_gamma,
-                                                                            d_beta, abn, eps, momentum, d_running_mean,
-                                                                            d_running_var, d_scale, d_shift, d_mean, d_var);
+  // statistics + (last block) scale / shift / running statistics: one launch, the workspace returns to zero
+  BnFinalize fin{};
+  fin.mode = 1; fin.C = (int)channels; fin.abn = abn; fin.count = (double)pixels; fin.eps = eps; fin.momentum = momentum;
+  fin.pivot = static_cast<const __nv_bfloat16*>(d_in); fin.gamma = d_gamma; fin.beta = d_beta;
+  fin.running_mean = d_running_mean; fin.running_var = d_running_var; fin.scale = d_scale; fin.shift = d_shift;
+  fin.mean_out = d_mean; fin.var_out = d_var;
+  bn_stats_nhwc_kernel<true><<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace, fin);
   const int64_t total = pixels * cv;
   const int agrid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16));
   bn_apply_nhwc_kernel<<<agrid, 256, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), d_scale, d_shift,
@@ -580,22 +608,23 @@ extern "C" int snb_bn_backward_nhwc(const void* d_x, int64_t x_cstride, const vo
   cudaStream_t st = as_stream(stream);
   int threads, grid;
   const int cv = bn_launch_shape(pixels, channels, &threads, &grid);
-  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
+  // reduction + (last block) means for the apply kernel, dgamma / dbeta: one launch, the workspace sums return to zero
+  BnFinalize fin{};
+  fin.mode = 3; fin.C = (int)channels; fin.abn = abn; fin.count = (double)pixels; fin.gamma = d_gamma;
+  fin.out0 = d_dgamma; fin.out1 = d_dbeta;
   bn_bwd_reduce_nhwc_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_x), cv, (int)(x_cstride / 8),
                                                      static_cast<const uint4*>(d_dout), (int)(dout_cstride / 8),
                                                      static_cast<const uint4*>(d_res_before), (int)(res_cstride / 8), d_scale,
-                                                     d_shift, d_mean, d_var, eps, act_slope, pixels, d_workspace);
+                                                     d_shift, d_mean, d_var, eps, act_slope, pixels, d_workspace, fin);
   const int64_t total = pixels * cv;
   const int agrid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16));
   bn_bwd_apply_nhwc_kernel<<<agrid, 256, 0, st>>>(static_cast<const uint4*>(d_x), cv, (int)(x_cstride / 8),
                                                  static_cast<const uint4*>(d_dout), (int)(dout_cstride / 8),
                                                  static_cast<const uint4*>(d_res_before), (int)(res_cstride / 8), d_scale, d_shift,
-                                                 d_mean, d_var, eps, act_slope, d_workspace, (double)pixels,
+                                                 d_mean, d_var, eps, act_slope,
+                                                 reinterpret_cast<const float*>(d_workspace + 2 * channels + 1),
                                                  static_cast<uint4*>(d_dx), (int)(dx_cstride / 8), static_cast<uint4*>(d_dres),
                                                  (int)(dres_cstride / 8), total);
-  if (d_dgamma || d_dbeta)
-    bn_bwd_params_nhwc_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, d_gamma, abn, (int)channels,
-                                                                                d_dgamma, d_dbeta);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
@@ -609,9 +638,9 @@ extern "C" int snb_channel_sum_nhwc(const void* d_in, int64_t pixels, int64_t ch
   cudaStream_t st = as_stream(stream);
   int threads, grid;
   const int cv = bn_launch_shape(pixels, channels, &threads, &grid);
-  SNB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, sizeof(double) * 2 * channels, st));
-  bn_stats_nhwc_kernel<false><<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace);
-  channel_sum_finalize_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_workspace, (int)channels, d_out);
+  BnFinalize fin{};
+  fin.mode = 2; fin.C = (int)channels; fin.out0 = d_out;
+  bn_stats_nhwc_kernel<false><<<grid, threads, 0, st>>>(static_cast<const uint4*>(d_in), cv, (int)(in_cstride / 8), pixels, d_workspace, fin);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

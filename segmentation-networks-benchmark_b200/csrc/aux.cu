@@ -181,49 +181,77 @@ __global__ void stem7x7_rows_kernel(const float* __restrict__ src, int C, int H,
 // backward of nn.MaxPool2d(3, 2, 1) on NHWC bf16: gather formulation.  An input pixel receives the gradient of every
 // window whose arg-max it is; the arg-max is recomputed with the forward's scan order (rows, then columns, strict >), so
 // ties (frequent after a ReLU) go to the first maximum, as in PyTorch.
-__global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int in_cs,
-                                        const __nv_bfloat16* __restrict__ dout, int dout_cs, __nv_bfloat16* __restrict__ din,
-                                        int din_cs, int64_t total) {
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_kernel(const uint4* __restrict__ in, int H, int W, int CV, int in_sv,
+                                                               const uint4* __restrict__ dout, int dout_sv,
+                                                               uint4* __restrict__ din, int din_sv, int64_t total) {
+  // one thread = 8 channels of one input pixel
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i;
-    const int c = (int)(r % C); r /= C;
+    const int cv = (int)(r % CV); r /= CV;
     const int x = (int)(r % W); r /= W;
     const int y = (int)(r % H);
     const int64_t n = r / H;
-    float acc = 0.f;
-    for (int oy = max(0, y / 2); oy <= min(OH - 1, (y + 1) / 2); ++oy) {
-      for (int ox = max(0, x / 2); ox <= min(OW - 1, (x + 1) / 2); ++ox) {
-        // window rows 2oy-1 .. 2oy+1 (must contain y), cols 2ox-1 .. 2ox+1
-        if (y < 2 * oy - 1 || y > 2 * oy + 1 || x < 2 * ox - 1 || x > 2 * ox + 1) continue;
-        float best = -INFINITY;
-        int by = -1, bx = -1;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // windows containing (y, x): rows 2oy-1 .. 2oy+1, i.e. oy = y / 2 and, for odd y, (y + 1) / 2
+    for (int oy = y / 2; oy <= min(OH - 1, (y + 1) / 2); ++oy) {
+      for (int ox = x / 2; ox <= min(OW - 1, (x + 1) / 2); ++ox) {
+        float best[8];
+        bool mine[8];
+        bool first = true;
+#pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
           const int yy = 2 * oy + dy;
           if (yy < 0 || yy >= H) continue;
+#pragma unroll
           for (int dx = -1; dx <= 1; ++dx) {
             const int xx = 2 * ox + dx;
             if (xx < 0 || xx >= W) continue;
-            const float v = __bfloat162float(in[((n * H + yy) * W + xx) * in_cs + c]);
-            if (v > best || by < 0) { best = v; by = yy; bx = xx; }
+            const uint4 u = __ldg(in + ((n * H + yy) * W + xx) * in_sv + cv);
+            const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&u);
+            const bool here = yy == y && xx == x;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float v = __bfloat162float(ve[e]);
+              if (first || v > best[e]) { best[e] = v; mine[e] = here; }     // strict >: the first maximum wins (PyTorch)
+            }
+            first = false;
           }
         }
-        if (by == y && bx == x) acc += __bfloat162float(dout[((n * OH + oy) * OW + ox) * dout_cs + c]);
+        const uint4 g = __ldg(dout + ((n * OH + oy) * OW + ox) * dout_sv + cv);
+        const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += mine[e] ? __bfloat162float(ge[e]) : 0.f;
       }
     }
-    din[((n * H + y) * W + x) * din_cs + c] = __float2bfloat16(acc);
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+    din[((n * H + y) * W + x) * din_sv + cv] = *reinterpret_cast<const uint4*>(o);
   }
 }
 
 // elementwise helpers of the backward pass on bf16 slabs: mode 0: out = a + b;  mode 1: out = a * (b > 0 ? 1 : slope)
 // (the gradient through a leaky-ReLU whose OUTPUT is b)
-__global__ void ew_nhwc_kernel(const __nv_bfloat16* __restrict__ a, int a_cs, const __nv_bfloat16* __restrict__ b, int b_cs,
-                               __nv_bfloat16* __restrict__ out, int out_cs, int C, int mode, float slope, int64_t total) {
+__global__ void __launch_bounds__(256) ew_nhwc_kernel(const uint4* __restrict__ a, int a_sv, const uint4* __restrict__ b, int b_sv,
+                                                      uint4* __restrict__ out, int out_sv, int CV, int mode, float slope,
+                                                      int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int64_t pix = i / C;
-    const float av = __bfloat162float(a[pix * a_cs + c]), bv = __bfloat162float(b[pix * b_cs + c]);
-    out[pix * out_cs + c] = __float2bfloat16(mode == 0 ? av + bv : (bv > 0.f ? av : av * slope));
+    const int cv = (int)(i % CV);
+    const int64_t pix = i / CV;
+    const uint4 ua = __ldg(a + pix * a_sv + cv), ub = __ldg(b + pix * b_sv + cv);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ua);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 av = __bfloat1622float2(pa[e]), bv = __bfloat1622float2(pb[e]);
+      o[e] = mode == 0 ? __floats2bfloat162_rn(av.x + bv.x, av.y + bv.y)
+                       : __floats2bfloat162_rn(bv.x > 0.f ? av.x : av.x * slope, bv.y > 0.f ? av.y : av.y * slope);
+    }
+    out[pix * out_sv + cv] = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -425,10 +453,13 @@ extern "C" int snb_maxpool3x3s2_backward(const void* d_in, int64_t n, int64_t h,
   if (!d_in || !d_dout || !d_din) return fail(SNB_E_INVALID, "snb_maxpool3x3s2_backward: null argument");
   if (n <= 0 || h <= 0 || w <= 0 || channels <= 0 || in_cstride < channels || dout_cstride < channels || din_cstride < channels)
     return fail(SNB_E_INVALID, "bad shape");
-  const int64_t total = n * h * w * channels;
+  if (channels % 8 || in_cstride % 8 || dout_cstride % 8 || din_cstride % 8 || (reinterpret_cast<uintptr_t>(d_in) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_dout) & 15) || (reinterpret_cast<uintptr_t>(d_din) & 15))
+    return fail(SNB_E_INVALID, "channel counts / strides must be multiples of 8 and pointers 16-byte aligned");
+  const int64_t total = n * h * w * (channels / 8);
   maxpool3x3s2_bwd_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(d_in), (int)h, (int)w, (int)channels, (int)in_cstride,
-      static_cast<const __nv_bfloat16*>(d_dout), (int)dout_cstride, static_cast<__nv_bfloat16*>(d_din), (int)din_cstride, total);
+      static_cast<const uint4*>(d_in), (int)h, (int)w, (int)(channels / 8), (int)(in_cstride / 8),
+      static_cast<const uint4*>(d_dout), (int)(dout_cstride / 8), static_cast<uint4*>(d_din), (int)(din_cstride / 8), total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
@@ -438,11 +469,14 @@ extern "C" int snb_ew_nhwc(const void* d_a, int64_t a_cstride, const void* d_b, 
   if (!d_a || !d_b || !d_out) return fail(SNB_E_INVALID, "snb_ew_nhwc: null argument");
   if (pixels <= 0 || channels <= 0 || a_cstride < channels || b_cstride < channels || out_cstride < channels || mode < 0 || mode > 1)
     return fail(SNB_E_INVALID, "bad shape or mode");
-  const int64_t total = pixels * channels;
-  ew_nhwc_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(d_a), (int)a_cstride,
-                                                                 static_cast<const __nv_bfloat16*>(d_b), (int)b_cstride,
-                                                                 static_cast<__nv_bfloat16*>(d_out), (int)out_cstride,
-                                                                 (int)channels, mode, slope, total);
+  if (channels % 8 || a_cstride % 8 || b_cstride % 8 || out_cstride % 8 || (reinterpret_cast<uintptr_t>(d_a) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_b) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+    return fail(SNB_E_INVALID, "channel counts / strides must be multiples of 8 and pointers 16-byte aligned");
+  const int64_t total = pixels * (channels / 8);
+  ew_nhwc_kernel<<<aux_grid(total), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(d_a), (int)(a_cstride / 8),
+                                                                 static_cast<const uint4*>(d_b), (int)(b_cstride / 8),
+                                                                 static_cast<uint4*>(d_out), (int)(out_cstride / 8),
+                                                                 (int)(channels / 8), mode, slope, total);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -1023,12 +1023,12 @@ class BnTrainOp:
         self.shift = torch.empty(cpad, dtype=torch.float32, device=dev)
         self.mean = torch.empty(cpad, dtype=torch.float32, device=dev)     # kept for the backward pass
         self.var = torch.empty(cpad, dtype=torch.float32, device=dev)
-        self.work = torch.empty(2 * cpad, dtype=torch.float64, device=dev)
+        self.work = torch.zeros(3 * cpad + 2, dtype=torch.float64, device=dev)      # zero at rest (include/snb_b200.h)
         self.keep = (src, dst, residual, weight, bias, rmean, rvar)
         self.pixels = src.slab.n * src.slab.h * src.slab.w
         self._cfg = (cpad, abn, eps, momentum, slope, res_after_act)
         self.rebind()
-        self.flops, self.launches = 0.0, 4
+        self.flops, self.launches = 0.0, 2
 
     def rebind(self):
         """(re)build the argument list after self.gamma / self.beta were pointed at other tensors"""

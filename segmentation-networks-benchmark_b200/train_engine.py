@@ -78,7 +78,7 @@ class BnBwdOp:
     def __init__(self, raw, g_out, bnop, abn, eps, slope, res_before, draw, dres, dgamma, dbeta):
         cpad = raw.c
         self.keep = (raw, g_out, bnop, res_before, draw, dres, dgamma, dbeta)
-        self.work = torch.empty(2 * cpad, dtype=torch.float64, device=raw.slab.t.device)
+        self.work = torch.zeros(3 * cpad + 2, dtype=torch.float64, device=raw.slab.t.device)
         pixels = raw.slab.n * raw.slab.h * raw.slab.w
         self.args = (N.c_vp(raw.ptr), raw.cstride, N.c_vp(g_out.ptr), g_out.cstride, pixels, cpad, N.ptr(bnop.scale),
                      N.ptr(bnop.shift), N.ptr(bnop.mean), N.ptr(bnop.var), N.ptr(bnop.gamma), 1 if abn else 0, float(eps),
@@ -86,7 +86,7 @@ class BnBwdOp:
                      res_before.cstride if res_before is not None else 0, N.c_vp(draw.ptr), draw.cstride,
                      N.c_vp(dres.ptr if dres is not None else 0), dres.cstride if dres is not None else 0, N.ptr(dgamma),
                      N.ptr(dbeta), N.ptr(self.work))
-        self.flops, self.launches = 0.0, 4
+        self.flops, self.launches = 0.0, 2
 
     def __call__(self, stream):
         N.check(N.lib().snb_bn_backward_nhwc(*self.args, stream))
@@ -130,6 +130,7 @@ class LinkNet34TrainPlan:
         self.unpack = GatherTable(device, False)      # packed fp32 weight gradients -> parameter layouts
         self._pending_shortcut = None
         self._drop_is_ones = True
+        self._nbt = None
         self.generation = 0                           # bumped by every forward: a stale backward must not run
         self.use_graph = os.environ.get("SNB_TRAIN_GRAPH", "1") != "0"
         self._graphs = {}
@@ -338,7 +339,7 @@ class LinkNet34TrainPlan:
         def bias_grad(conv, gslab, channels):
             """channel sums of the output gradient -> the bias slot of the gradient arena"""
             cw = (channels + 7) // 8 * 8
-            work = torch.empty(2 * cw, dtype=torch.float64, device=dev)
+            work = torch.zeros(3 * cw + 2, dtype=torch.float64, device=dev)
             pixels = n * gslab.h * gslab.w
             ops.append(SimpleOp("snb_channel_sum_nhwc", (N.c_vp(gslab.t.data_ptr()), pixels, cw, gslab.c,
                                                          N.ptr(self.grad_slot[conv.bias]), N.ptr(work)), (gslab, work)))
@@ -505,8 +506,9 @@ class LinkNet34TrainPlan:
             self.drop_scale.fill_(1.0)
             self._drop_is_ones = True
         self._replay('fwd', self.ops)
-        for m in self.bn_modules:            # nn.BatchNorm2d bookkeeping (momentum is fixed, the counter only counts)
-            m.num_batches_tracked += 1
+        if self._nbt is None:                # nn.BatchNorm2d bookkeeping (momentum is fixed, the counter only counts)
+            self._nbt = [m.num_batches_tracked for m in self.bn_modules]
+        torch._foreach_add_(self._nbt, 1)    # one fused launch instead of one per module
         return self.out
 
     def backward(self, dlogits=None):

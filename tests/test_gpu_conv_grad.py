@@ -148,7 +148,7 @@ def test_bn_train_backward_nhwc(cuda, c, abn, slope, res, after):
     op(st)
     dx, dres = E.Slab(n, h, w, c, "cuda"), E.Slab(n, h, w, c, "cuda")
     dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
-    work = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    work = torch.zeros(3 * c + 2, dtype=torch.float64, device="cuda")
     rb = res and not after
     N.check(N.lib().snb_bn_backward_nhwc(
         N.c_vp(xs.t.data_ptr()), c, N.c_vp(gs.t.data_ptr()), c, n * h * w, c, N.ptr(op.scale), N.ptr(op.shift), N.ptr(op.mean),
@@ -183,6 +183,6 @@ def test_maxpool_backward_ew_and_channel_sum(cuda):
     N.check(N.lib().snb_ew_nhwc(N.c_vp(a.t.data_ptr()), c, N.c_vp(b.t.data_ptr()), c, N.c_vp(o.t.data_ptr()), c, px, c, 1, 0.01, st))
     assert torch.equal(o.t, torch.where(b.t.float() > 0, a.t.float(), a.t.float() * 0.01).to(torch.bfloat16))
     s = torch.empty(c, device="cuda")
-    work = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    work = torch.zeros(3 * c + 2, dtype=torch.float64, device="cuda")
     N.check(N.lib().snb_channel_sum_nhwc(N.c_vp(a.t.data_ptr()), px, c, c, N.ptr(s), N.ptr(work), st))
     assert (s - a.t.float().sum(dim=(0, 1, 2))).abs().max().item() < 1e-3

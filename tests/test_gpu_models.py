@@ -27,6 +27,7 @@ def test_logits_against_reference_vectors(cuda, golden_dir, arch, cls):
     assert y.shape == (2, 1, 64, 96) and y.dtype == torch.float32
     ref = torch.from_numpy(g[arch + "_logits"])
     p_err = (torch.sigmoid(y.cpu()) - torch.sigmoid(ref)).abs().max().item()
+    print("margin %s 2x64x96 bf16: max |p - reference| = %.3g (bar %.0e)" % (arch, p_err, BF16_PROB_TOL))
     assert p_err < BF16_PROB_TOL, p_err
     # against the oracle evaluated with bf16-rounded conv operands the agreement is much tighter
     sd = synth.vgg_unet_state_dict(arch, seed=1)
@@ -64,6 +65,7 @@ def test_zf_unet_against_reference_vectors(cuda, golden_dir):
     ref = torch.from_numpy(g["small_logits"])
     assert y.shape == ref.shape
     p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    print("margin zf_unet small bf16: max |p - reference| = %.3g (bar %.0e)" % (p_err, BF16_PROB_TOL))
     assert p_err < BF16_PROB_TOL, p_err
     sd = synth.zf_unet_state_dict(seed=4)
     with torch.no_grad():
@@ -118,6 +120,7 @@ def test_fcdensenet67_against_reference_vectors(cuda, golden_dir):
     p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
     assert p_err < BF16_PROB_TOL, p_err
     p_err224 = (torch.sigmoid(y224) - torch.sigmoid(torch.from_numpy(g["logits224"]))).abs().max().item()
+    print("margin fcdensenet67 bf16: max |p - reference| = %.3g (64x96), %.3g (224x224) (bar %.0e)" % (p_err, p_err224, BF16_PROB_TOL))
     assert p_err224 < BF16_PROB_TOL, p_err224
     sd = synth.fcdensenet_state_dict(seed=5)
     with torch.no_grad():
@@ -183,6 +186,8 @@ def test_precision_modes_on_default_init_weights(cuda, arch):
         with torch.no_grad():
             y = m(x.cuda()).cpu()
         errs[prec] = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    print("margin %s default-init weights: tf32 %.3g (bar %.0e), bf16 %.3g (bar %.0e)" % (
+        arch, errs["tf32"], FP32_PROB_TOL, errs["bf16"], BF16_PROB_TOL))
     assert errs["tf32"] < FP32_PROB_TOL, errs
     assert errs["bf16"] < BF16_PROB_TOL, errs
 
@@ -206,6 +211,7 @@ def test_linknet34_against_reference_vectors(cuda, golden_dir):
     p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
     assert p_err < BF16_PROB_TOL, p_err
     p_err256 = (torch.sigmoid(y256) - torch.sigmoid(torch.from_numpy(g["logits256"]))).abs().max().item()
+    print("margin linknet34 eval bf16: max |p - reference| = %.3g (64x96), %.3g (256x256) (bar %.0e)" % (p_err, p_err256, BF16_PROB_TOL))
     assert p_err256 < BF16_PROB_TOL, p_err256
     sd = synth.linknet34_state_dict(seed=6)
     with torch.no_grad():
@@ -521,6 +527,7 @@ def test_unet_against_reference_vectors(cuda, golden_dir, name, abn):
     ref = torch.from_numpy(g[name + "_logits"])
     assert y.shape == ref.shape and torch.equal(y, y2)
     p_err = (torch.sigmoid(y) - torch.sigmoid(ref)).abs().max().item()
+    print("margin %s 2x64x96 bf16: max |p - reference| = %.3g (bar %.0e)" % (name, p_err, BF16_PROB_TOL))
     assert p_err < BF16_PROB_TOL, p_err
     with torch.no_grad():
         q = no.unet_forward(sd, torch.from_numpy(g["x"]), abn=abn, quant=no.bf16_round)
