@@ -59,6 +59,8 @@ struct alignas(64) ConvParams {
   int32_t head_sigmoid;
   int32_t out_w, out_h;            // head output bounds
   int32_t a_stages, b_stages, bres;  // v2 pipeline shape
+  int32_t dual_mma;                  // two MMA-issuing warps: 1 = alternating tiles, 2 = phases 0-1 / 2-3 of every tile
+  int32_t epi_groups;                // 2 = warps 8-11 are a second epilogue group (kernels launched with 384 threads)
   int32_t pool;                      // also write the 2x2 max-pooled tile through map_p
   int32_t m_pairs;                   // CTA-pair kernels: spatial tiles per phase / 2
   int32_t up2x;                      // store every tile through all 4 map_d (nearest 2x upsample of the output)
@@ -172,10 +174,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // EXT = the ResNet / LinkNet extras (residual operand, leaky-ReLU slope); the VGG / UNet layers run the lean EXT = false
 // body: the high-resolution layers (K = 32..576 per 128 x 64 outputs) are bound by this epilogue, where the extra
 // selects and predicated adds cost 10-35 %.
-template <int BN, bool HEAD, int TW, int EB, bool EXT>
+// EG = 2: two epilogue groups of 4 warps take alternate tiles (group = TMEM stage); each group then owns ONE staging
+// buffer (index grp) and its own named barrier instead of double-buffering inside one group.
+template <int BN, bool HEAD, int TW, int EB, bool EXT, int EG = 1>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& tc, uint32_t t_addr,
                                               uint64_t* tmem_empty_bar, uint8_t* smem_out, uint32_t& n_store,
-                                              int row, int lane, int epi_tid, bool release = true) {
+                                              int row, int lane, int epi_tid, bool release = true, int grp = 0) {
   constexpr int CW = BN < 128 / EB ? BN : 128 / EB;
   constexpr int OUT_SWZ = CW * EB;
   constexpr int OUT_BYTES = kBM * OUT_SWZ;
@@ -222,11 +226,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
     const int64_t res_pix = ((static_cast<int64_t>(tc.img) * p.out_h + ry) * p.out_w + rx) * p.res_cstride;
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c, ++n_store) {
-      uint8_t* sout = smem_out + (n_store & 1) * OUT_BYTES;
-      uint8_t* spool = smem_out + 2 * OUT_BYTES + (n_store & 1) * POOL_BYTES;
-      // the TMA store issued two chunks ago must have finished reading this buffer
-      if (epi_tid == 0) tma_store_wait_read<1>();
-      named_bar_sync(1, 128);
+      const bool two = EG == 2 && p.epi_groups == 2;
+      const uint32_t buf = two ? static_cast<uint32_t>(grp) : (n_store & 1);
+      uint8_t* sout = smem_out + buf * OUT_BYTES;
+      uint8_t* spool = smem_out + 2 * OUT_BYTES + buf * POOL_BYTES;
+      // the TMA store that last read this buffer (two chunks ago; the group's previous chunk when EG = 2) must be done
+      if (epi_tid == 0) {
+        if (two) tma_store_wait_read<0>();
+        else tma_store_wait_read<1>();
+      }
+      named_bar_sync(1 + grp, 128);
 #pragma unroll
       for (int g = 0; g < CW / 32; ++g) {
         uint32_t v[32];
@@ -316,7 +325,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
         if (lane == 0) mbar_arrive(tmem_empty_bar);
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1 + grp, 128);
       if (epi_tid == 0) {
         if (p.up2x) {
 #pragma unroll
@@ -491,13 +500,20 @@ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
 // zero padding applies AFTER the pre-activation).  This is FCDenseNet's per-consumer BatchNorm+ReLU
 // (lib/models/tiramisu.py:12-13) fused into the operand path instead of a separate pass over the slab.
 template <int BN, int BK, bool HEAD, int TAPS, int NPH, int CL, int EB, bool PRE = false>
-__global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(PRE ? 512 : (CL == 1 && BN <= 64 ? 384 : 256), 1)
+conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  // narrow tiles are bound by the epilogue's dependent-instruction latency (one warp per scheduler): two epilogue groups
+  // (not the fused 1x1 head: its epilogue is a dot product per pixel, that layer is bound by the MMA pipe)
+  constexpr int EG = (!PRE && !HEAD && CL == 1 && BN <= 64) ? 2 : 1;
   static_assert(!PRE || (EB == 2 && NPH == 1 && CL == 1), "the fused pre-activation is built for bf16 conv3x3");
   static_assert(CL == 1 || (CL == 2 && NPH == 1 && !HEAD && BN >= 128), "CTA pairs are for the streamed-weight layers");
   using Cfg = ConvCfg<BN, BK, EB>;
   static_assert(NPH == 1 || (NPH == 4 && TAPS == 4 && !HEAD), "phase fusion is for ConvTranspose");
-  constexpr int TCOLS = Cfg::TMEM_COLS * NPH;
-  static_assert(TCOLS <= 512, "TMEM columns");
+  // accumulator stages: narrow tiles have a short main loop (M) next to a long epilogue (E); with two stages a tile costs
+  // (M + E) / 2 however many warps share the work, with four the issuers run ahead and it costs max(M, E / groups)
+  constexpr int NACC = (!PRE && !HEAD && CL == 1 && NPH * BN <= 128) ? 4 : 2;
+  constexpr int TCOLS = NACC * NPH * BN < 32 ? 32 : NACC * NPH * BN;
+  static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
   constexpr uint32_t IDESC = make_idesc(kBM, BN, EB == 2 ? 1u : 2u);
   constexpr int TW = 8, TH = 16;
   constexpr int SWZ = Cfg::SWZ;
@@ -515,9 +531,9 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
   uint64_t* a_empty = a_full + kMaxAStages;         // [kMaxAStages]
   uint64_t* b_full = a_empty + kMaxAStages;         // [kMaxBStages]  (b_full[0] doubles as the bres barrier)
   uint64_t* b_empty = b_full + kMaxBStages;         // [kMaxBStages]
-  uint64_t* tmem_full = b_empty + kMaxBStages;      // [2]
-  uint64_t* tmem_empty = tmem_full + 2;             // [2]
-  uint64_t* a_ready = tmem_empty + 2;               // [kMaxAStages] stage rewritten by the prologue warps (PRE)
+  uint64_t* tmem_full = b_empty + kMaxBStages;      // [4]
+  uint64_t* tmem_empty = tmem_full + 4;             // [4]
+  uint64_t* a_ready = tmem_empty + 4;               // [kMaxAStages] stage rewritten by the prologue warps (PRE)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + kMaxAStages);
   uint32_t* s_aoff = tmem_ptr + 4;                  // [kMaxPhases][TAPS] descriptor start offsets (>>4) per tap
 
@@ -534,15 +550,15 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kMaxAStages; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], p.dual_mma == 2 ? 2 : 1);   // phase-split issuers both read every activation stage
       mbar_init(&a_ready[i], 8);    // one arrival per prologue warp
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], CL);   // every CTA of the cluster must have consumed a multicast stage
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
+    for (int i = 0; i < NACC; ++i) {
+      mbar_init(&tmem_full[i], p.dual_mma == 2 ? 2 : 1);
       mbar_init(&tmem_empty[i], 4);
     }
     fence_barrier_init();
@@ -619,8 +635,14 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
+  } else if (warp == 1 || (warp == 2 && p.dual_mma)) {
+    // ------------------------------------------------------------------ MMA issuer (one thread per issuing warp)
+    // A narrow-N MMA retires in 40-48 cycles but costs the issuing thread ~60 (descriptor moves into uniform registers),
+    // so those layers were issue-bound (ncu: the issuing warp busy 85 % of the time, epilogue warps waiting).  With
+    // dual_mma = 1 a second warp issues too: warp 1 owns the even local tiles (TMEM stage 0), warp 2 the odd ones (stage 1);
+    // both walk the same in-order operand rings and skip the other warp's stages.  dual_mma = 2 (fused ConvTranspose
+    // phases): both warps work on EVERY tile, warp 1 on the accumulators of phases 0-1, warp 2 on phases 2-3; each still
+    // observes every weight-ring slot in order (a parity wait is only sound one phase ahead), the owner alone releases it.
     if (elect_one()) {
       constexpr uint32_t HI_A = desc_hi<SWZ>(kHaloW * SWZ);   // 8-row groups are one halo row (10 pixels) apart
       constexpr uint32_t HI_B = desc_hi<SWZ>(8 * SWZ);
@@ -628,6 +650,9 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
       const uint32_t b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
       const bool bres = p.bres != 0;
       const uint32_t a_stages = p.a_stages, b_stages = p.b_stages;
+      const bool dual = p.dual_mma == 1;
+      const bool by_phase = NPH == 4 && p.dual_mma == 2;
+      const uint32_t mine = warp == 1 ? 0u : 1u;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       uint32_t local_tile = 0;
       if (bres) {
@@ -635,13 +660,21 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
         tc05_fence_after();
       }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+        if (dual && (local_tile & 1) != mine) {
+          // the other issuer's tile: step over its ring slots.  The host makes a_stages a multiple of 2 * k_chunks in this
+          // mode, so a given slot only ever holds chunks of one tile parity: each barrier is waited on by ONE issuer, which
+          // sees every phase of it in order (a parity wait is unsound for a waiter that skipped a phase).
+          sa += p.k_chunks;
+          if (sa >= a_stages) { sa -= a_stages; pa ^= 1; }
+          continue;
+        }
         // phase is the slowest tile coordinate (and absent when the phases are fused)
         const int ph0 = NPH == 1 ? t / (p.total_tiles / p.n_phases) : 0;
         uint32_t aoff[NPH * TAPS];
 #pragma unroll
         for (int i = 0; i < NPH * TAPS; ++i) aoff[i] = s_aoff[ph0 * TAPS + i];
-        const uint32_t acc = local_tile & 1;
-        mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
+        const uint32_t acc = local_tile % NACC;
+        mbar_wait(&tmem_empty[acc], ((local_tile / NACC) & 1) ^ 1);
         tc05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (NPH * BN);
         uint32_t b_lo = b_lo0 + static_cast<uint32_t>(ph0 * p.k_chunks * TAPS) * B_BYTES16;
@@ -652,6 +685,15 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
 #pragma unroll
           for (int wt = 0; wt < NPH * TAPS; ++wt) {
             const int tap = wt % TAPS;
+            if (NPH == 4 && by_phase && static_cast<uint32_t>(wt / (2 * TAPS)) != mine) {   // the other issuer's phases
+              if (!bres) {
+                mbar_wait(&b_full[sb], pb);
+                if (++sb == b_stages) { sb = 0; pb ^= 1; }
+              } else {
+                b_lo += B_BYTES16;
+              }
+              continue;
+            }
             if (!bres) {
               mbar_wait(&b_full[sb], pb);
               tc05_fence_after();
@@ -717,17 +759,19 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
         if (++s == static_cast<uint32_t>(p.a_stages)) { s = 0; par ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ epilogue (128 threads)
-    const int q = warp & 3;
+  } else if (warp >= 4 && warp < 4 + 4 * EG) {
+    // ------------------------------------------------------------------ epilogue (EG groups of 128 threads)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int grp = (warp - 4) >> 2;        // EG = 2: group g takes the local tiles of parity g = TMEM stage g
     const int row = q * 32 + lane;
-    const int epi_tid = threadIdx.x - 128;
+    const int epi_tid = threadIdx.x - 128 - 128 * grp;
     uint32_t local_tile = 0;
     uint32_t n_store = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
+      const uint32_t acc = local_tile % NACC;
+      if (EG == 2 && (p.epi_groups == 2 ? (acc & 1) != static_cast<uint32_t>(grp) : grp != 0)) continue;
       TileCoord tc = decode(t);
-      const uint32_t acc = local_tile & 1;
-      const uint32_t acc_ph = (local_tile >> 1) & 1;
+      const uint32_t acc_ph = (local_tile / NACC) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * (NPH * BN) + (static_cast<uint32_t>(q * 32) << 16);
@@ -735,11 +779,11 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_halo_kernel(const __g
       for (int ph = 0; ph < NPH; ++ph) {
         if (NPH > 1) tc.ph = ph;
         if (p.ext)
-          epilogue_tile<BN, HEAD, TW, EB, true>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane,
-                                                epi_tid, ph == NPH - 1);
+          epilogue_tile<BN, HEAD, TW, EB, true, EG>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane,
+                                                    epi_tid, ph == NPH - 1, grp);
         else
-          epilogue_tile<BN, HEAD, TW, EB, false>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane,
-                                                 epi_tid, ph == NPH - 1);
+          epilogue_tile<BN, HEAD, TW, EB, false, EG>(p, tc, t_addr + ph * BN, &tmem_empty[acc], smem_out, n_store, row, lane,
+                                                     epi_tid, ph == NPH - 1, grp);
       }
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
@@ -1352,10 +1396,28 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     p.a_stages = a_stages;
     p.b_stages = b_stages;
     p.bres = bres ? 1 : 0;
+    {
+      // second MMA-issuing warp: narrow tiles (an N <= 64 MMA retires faster than one thread issues it); SNB_DUAL_MMA = 0 / 1
+      // forces it off / on for every halo layer (A/B runs)
+      // By tile (dual_mma = 1) only with resident weights and an activation ring of at least two tiles: a streamed weight
+      // ring holds a fraction of a tile, the two issuers would just take turns.
+      int dual = bn <= 64 ? 1 : 0;
+      if (const char* e = std::getenv("SNB_DUAL_MMA")) dual = std::atoi(e) != 0;
+      p.dual_mma = (dual && bres && a_stages >= 2 * p.k_chunks) ? 1 : 0;
+      if (p.dual_mma) {
+        a_stages -= a_stages % (2 * p.k_chunks);   // a ring slot then belongs to one issuer for good (see the skip in the kernel)
+        p.a_stages = a_stages;
+      }
+      if (dual && fuse_phases) p.dual_mma = 2;   // split by phase instead: no ring constraint, streamed weights included
+    }
     c->fn = p.taps == 9 ? kc.fn_halo9 : (fuse_phases ? kc.fn_halo4f : kc.fn_halo4);
     if (pre) {
       c->fn = kc.fn_pre9;
       c->threads = 512;
+    } else if (kc.bn <= 64) {
+      c->threads = 384;   // second epilogue group (warps 8-11); SNB_EPI_GROUPS = 1 leaves it idle (A/B runs)
+      p.epi_groups = 2;
+      if (const char* e = std::getenv("SNB_EPI_GROUPS")) p.epi_groups = std::atoi(e) == 1 ? 1 : 2;
     }
     // CTA pairs: streamed weights, an even number of spatial tiles per phase, and a pair kernel for this shape
     const int64_t m_tiles = (int64_t)d->n * ((grid_h + tile_h - 1) / tile_h) * ((grid_w + tile_w - 1) / tile_w);
@@ -1363,6 +1425,7 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     if (mode >= 4 && !bres && !fuse_phases && !pre && fn_pair && m_tiles % 2 == 0 && sms >= 2) {
       c->fn = fn_pair;
       c->cluster = 2;
+      p.dual_mma = 0;   // the multicast weight ring is consumed in lock step by the pair
       p.m_pairs = static_cast<int32_t>(m_tiles / 2);
     }
   }
