@@ -143,12 +143,13 @@ def lib():
     """The loaded library; raises ImportError (never falls back) when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SNB_B200_LIB", LIB_PATH)   # another build of the SAME ABI, for A/B timing (tools/build_rev.py)
+        if not os.path.exists(path):
             raise ImportError(
                 "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH
+                "(nvcc, sm_100a). There is no CPU fallback." % path
             )
-        handle = ctypes.CDLL(LIB_PATH)
+        handle = ctypes.CDLL(path)
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = restype

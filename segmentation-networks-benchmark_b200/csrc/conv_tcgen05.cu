@@ -61,6 +61,7 @@ struct alignas(64) ConvParams {
   int32_t a_stages, b_stages, bres;  // v2 pipeline shape
   int32_t dual_mma;                  // two MMA-issuing warps: 1 = alternating tiles, 2 = phases 0-1 / 2-3 of every tile
   int32_t epi_groups;                // 2 = warps 8-11 are a second epilogue group (kernels launched with 384 threads)
+  int32_t out_bufs;                  // 1 = single output staging buffer (the room goes to the weight ring); else 2
   int32_t pool;                      // also write the 2x2 max-pooled tile through map_p
   int32_t m_pairs;                   // CTA-pair kernels: spatial tiles per phase / 2
   int32_t up2x;                      // store every tile through all 4 map_d (nearest 2x upsample of the output)
@@ -141,6 +142,20 @@ __device__ __forceinline__ TileCoord decode_tile_pair(const ConvParams& p, int u
   c.y0 = (m % p.tiles_y) * TH;
   c.img = m / p.tiles_y;
   return c;
+}
+
+// bf16x2 pack with the ReLU folded into the conversion (negative -> +0): one instruction instead of two FMNMX + F2F
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// two fp32 adds in one instruction (sm_100 packed fp32 pipe)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
 }
 
 __device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
@@ -227,12 +242,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c, ++n_store) {
       const bool two = EG == 2 && p.epi_groups == 2;
-      const uint32_t buf = two ? static_cast<uint32_t>(grp) : (n_store & 1);
+      const bool single = !two && p.out_bufs == 1;
+      const uint32_t buf = two ? static_cast<uint32_t>(grp) : (single ? 0u : (n_store & 1));
       uint8_t* sout = smem_out + buf * OUT_BYTES;
-      uint8_t* spool = smem_out + 2 * OUT_BYTES + buf * POOL_BYTES;
-      // the TMA store that last read this buffer (two chunks ago; the group's previous chunk when EG = 2) must be done
+      uint8_t* spool = smem_out + (single ? 1 : 2) * OUT_BYTES + buf * POOL_BYTES;   // (only allocated when p.pool)
+      // the TMA store that last read this buffer (two chunks ago; the previous chunk with one buffer per group) must be done
       if (epi_tid == 0) {
-        if (two) tma_store_wait_read<0>();
+        if (two || single) tma_store_wait_read<0>();
         else tma_store_wait_read<1>();
       }
       named_bar_sync(1 + grp, 128);
@@ -245,10 +261,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // 4 x 16-byte chunks of 8 channels
           const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-          float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
-                        __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
-                        __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
-                        __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+          add2(f[0], f[1], b0.x, b0.y);
+          add2(f[2], f[3], b0.z, b0.w);
+          add2(f[4], f[5], b1.x, b1.y);
+          add2(f[6], f[7], b1.z, b1.w);
           if constexpr (EXT) {
             float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (p.residual != nullptr && res_ok) {
@@ -282,7 +301,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
               for (int e = 0; e < 8; ++e) f[e] += res[e];
             }
           } else {
-            if (p.relu) {
+            if (EB != 2 && p.relu) {   // bf16 storage folds the ReLU into the conversion below
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
@@ -292,14 +311,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
           if constexpr (EB == 2) {
             const int chunk = g * 4 + j;
             uint4* dst = reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4));
-            uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                  pack_bf16x2(f[6], f[7]));
-            *dst = pk;
-            if (p.pool) {
-              pk = bf16x8_max(pk, shfl_xor_u4(pk, 1));
-              pk = bf16x8_max(pk, shfl_xor_u4(pk, TW));
-              if (pool_keep) *reinterpret_cast<uint4*>(spool + prow * OUT_SWZ + ((chunk ^ swp) << 4)) = pk;
-            }
+            uint4 pk;
+            if (!EXT && p.relu)
+              pk = make_uint4(pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]), pack_bf16x2_relu(f[4], f[5]),
+                              pack_bf16x2_relu(f[6], f[7]));
+            else
+              pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+            *dst = pk;   // (the 2x2 max-pool of a bf16 tile is taken from this staging buffer after the barrier)
           } else {
             // fp32 storage: 8 channels = two 16-byte chunks; values are rounded to TF32 so that the next layer's
             // tensor-core read (which drops the low mantissa bits) sees exactly what is stored
@@ -334,8 +353,34 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
         } else {
           tma_store_4d(&p.map_d[tc.ph], sout, tc.nt * BN + c * CW, tc.x0, tc.y0, tc.img);
         }
-        if (p.pool) tma_store_4d(&p.map_p, spool, tc.nt * BN + c * CW, tc.x0 >> 1, tc.y0 >> 1, tc.img);
-        tma_store_commit();
+        if (EB != 2 && p.pool) tma_store_4d(&p.map_p, spool, tc.nt * BN + c * CW, tc.x0 >> 1, tc.y0 >> 1, tc.img);
+        if (!(EB == 2 && p.pool)) tma_store_commit();   // (with the staged pool below: one group per chunk, closed there)
+      }
+      if constexpr (EB == 2) {
+        if (p.pool) {
+          // fused MaxPool2d(2, 2) of a bf16 tile, from the staged rows: one (pooled pixel, 16-byte chunk) item per thread
+          // and pass = 4 LDS.128 + 12 HMNMX2 + 1 STS.128, against 8 shuffles + 8 HMNMX2 per chunk in registers
+          constexpr int NCH = OUT_SWZ / 16;
+#pragma unroll
+          for (int it = 0; it < NCH / 4; ++it) {
+            const int item = epi_tid + it * 128;
+            const int pr = item / NCH, ch = item % NCH;
+            const int r00 = (pr / (TW / 2)) * (2 * TW) + (pr % (TW / 2)) * 2;
+            auto at = [&](int r) {
+              const int swr = OUT_SWZ == 128 ? (r & 7) : ((r >> 1) & 3);
+              return *reinterpret_cast<const uint4*>(sout + r * OUT_SWZ + ((ch ^ swr) << 4));
+            };
+            const uint4 m = bf16x8_max(bf16x8_max(at(r00), at(r00 + 1)), bf16x8_max(at(r00 + TW), at(r00 + TW + 1)));
+            const int swq = OUT_SWZ == 128 ? (pr & 7) : ((pr >> 1) & 3);
+            *reinterpret_cast<uint4*>(spool + pr * OUT_SWZ + ((ch ^ swq) << 4)) = m;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (epi_tid == 0) {
+            tma_store_4d(&p.map_p, spool, tc.nt * BN + c * CW, tc.x0 >> 1, tc.y0 >> 1, tc.img);
+            tma_store_commit();
+          }
+        }
       }
     }
   }
@@ -479,6 +524,23 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
 // needs is therefore precomputed: tap -> descriptor offsets live in a shared-memory table, stage indices advance by
 // compare-and-wrap (no division), descriptors are built from 32-bit halves with immediate K offsets, and the tap
 // loop is fully unrolled (TAPS is a template parameter: 9 for conv3x3, 4 for one ConvTranspose phase).
+// -DSNB_CONV_PROFILE (tools/build_rev.py --profile; never in the shipped library): cycles the roles of conv_halo_kernel
+// spend waiting, summed over all CTAs.  [0] issuer: activation stage, [1] issuer: weight slot, [2] issuer: accumulator
+// stage, [3] issuer: whole loop, [4] epilogue warp 4: accumulator full, [5] epilogue warp 4: whole loop, [6] weight
+// producer: slot free, [7] tiles.
+#ifdef SNB_CONV_PROFILE
+__device__ unsigned long long g_conv_prof[8];
+#define SNB_PROF_DECL long long prof_t = 0; unsigned long long prof_c[4] = {0, 0, 0, 0}; (void)prof_t;
+#define SNB_PROF_T0 prof_t = clock64();
+#define SNB_PROF_ADD(i) prof_c[i] += static_cast<unsigned long long>(clock64() - prof_t);
+#define SNB_PROF_FLUSH(dst, i) atomicAdd(&g_conv_prof[dst], prof_c[i]);
+#else
+#define SNB_PROF_DECL
+#define SNB_PROF_T0
+#define SNB_PROF_ADD(i)
+#define SNB_PROF_FLUSH(dst, i)
+#endif
+
 __device__ __forceinline__ uint64_t desc_from_halves(uint32_t lo, uint32_t hi) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
@@ -526,7 +588,8 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.a_stages * Cfg::HALO_STAGE_BYTES;
   uint8_t* smem_out = smem_b + n_b_slots * Cfg::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + (HEAD ? 0 : 2 * Cfg::OUT_BYTES + 2 * Cfg::POOL_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      smem_out + (HEAD ? 0 : (p.out_bufs == 1 ? 1 : 2) * (Cfg::OUT_BYTES + (p.pool ? Cfg::POOL_BYTES : 0))));
   uint64_t* a_full = bars;                          // [kMaxAStages]
   uint64_t* a_empty = a_full + kMaxAStages;         // [kMaxAStages]
   uint64_t* b_full = a_empty + kMaxAStages;         // [kMaxBStages]  (b_full[0] doubles as the bres barrier)
@@ -615,13 +678,16 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
     if (!p.bres && elect_one()) {
       const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
       uint32_t s = 0, par = 1;
+      SNB_PROF_DECL
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode(t);
         const int n0 = tc.nt * BN, w0 = tc.ph * TAPS;   // tc.ph == 0 when the phases are fused
         for (int kc = 0; kc < p.k_chunks; ++kc) {
 #pragma unroll 1
           for (int wt = 0; wt < NPH * TAPS; ++wt) {
+            SNB_PROF_T0
             mbar_wait(&b_empty[s], par);
+            SNB_PROF_ADD(0)
             mbar_arrive_expect_tx(&b_full[s], Cfg::B_BYTES);
             if (CL == 1) {
               tma_load_3d(&p.map_b, &b_full[s], smem_b + s * Cfg::B_BYTES, kc * BK, n0, w0 + wt);
@@ -634,6 +700,7 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
           }
         }
       }
+      SNB_PROF_FLUSH(6, 0)
     }
   } else if (warp == 1 || (warp == 2 && p.dual_mma)) {
     // ------------------------------------------------------------------ MMA issuer (one thread per issuing warp)
@@ -659,6 +726,10 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
         mbar_wait(&b_full[0], 0);
         tc05_fence_after();
       }
+      SNB_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+      const long long prof_loop0 = clock64();
+#endif
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
         if (dual && (local_tile & 1) != mine) {
           // the other issuer's tile: step over its ring slots.  The host makes a_stages a multiple of 2 * k_chunks in this
@@ -674,12 +745,16 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
         for (int i = 0; i < NPH * TAPS; ++i) aoff[i] = s_aoff[ph0 * TAPS + i];
         const uint32_t acc = local_tile % NACC;
+        SNB_PROF_T0
         mbar_wait(&tmem_empty[acc], ((local_tile / NACC) & 1) ^ 1);
+        SNB_PROF_ADD(2)
         tc05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (NPH * BN);
         uint32_t b_lo = b_lo0 + static_cast<uint32_t>(ph0 * p.k_chunks * TAPS) * B_BYTES16;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
+          SNB_PROF_T0
           mbar_wait(PRE ? &a_ready[sa] : &a_full[sa], pa);
+          SNB_PROF_ADD(0)
           tc05_fence_after();
           const uint32_t a_lo = a_lo0 + sa * A_STAGE16;
 #pragma unroll
@@ -695,7 +770,9 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
               continue;
             }
             if (!bres) {
+              SNB_PROF_T0
               mbar_wait(&b_full[sb], pb);
+              SNB_PROF_ADD(1)
               tc05_fence_after();
               b_lo = b_lo0 + sb * B_BYTES16;
             }
@@ -716,6 +793,13 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
         }
         umma_commit(&tmem_full[acc]);
       }
+#ifdef SNB_CONV_PROFILE
+      if (mine == 0) {
+        prof_c[3] = static_cast<unsigned long long>(clock64() - prof_loop0);
+        SNB_PROF_FLUSH(0, 0) SNB_PROF_FLUSH(1, 1) SNB_PROF_FLUSH(2, 2) SNB_PROF_FLUSH(3, 3)
+        atomicAdd(&g_conv_prof[7], static_cast<unsigned long long>(local_tile));
+      }
+#endif
     }
   } else if (PRE && warp >= 8) {
     // ------------------------------------------------------------------ prologue: pre-activation of the A operand
@@ -767,12 +851,18 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
     const int epi_tid = threadIdx.x - 128 - 128 * grp;
     uint32_t local_tile = 0;
     uint32_t n_store = 0;
+    SNB_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+    const long long prof_loop0 = clock64();
+#endif
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
       const uint32_t acc = local_tile % NACC;
       if (EG == 2 && (p.epi_groups == 2 ? (acc & 1) != static_cast<uint32_t>(grp) : grp != 0)) continue;
       TileCoord tc = decode(t);
       const uint32_t acc_ph = (local_tile / NACC) & 1;
+      SNB_PROF_T0
       mbar_wait(&tmem_full[acc], acc_ph);
+      SNB_PROF_ADD(0)
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * (NPH * BN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
@@ -787,6 +877,12 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
       }
     }
     if (!HEAD && epi_tid == 0) tma_store_wait_all<0>();
+#ifdef SNB_CONV_PROFILE
+    if (warp == 4 && lane == 0) {
+      prof_c[1] = static_cast<unsigned long long>(clock64() - prof_loop0);
+      SNB_PROF_FLUSH(4, 0) SNB_PROF_FLUSH(5, 1)
+    }
+#endif
   }
 
   tc05_fence_before();
@@ -1364,11 +1460,21 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
   if (halo) {
     tile_w = 8;
     tile_h = 16;
-    const int fixed = 1024 /*align*/ + 1024 /*ctrl*/ + 2 * kc.out_bytes + 2 * kc.pool_bytes;
+    const int pool_bytes = pool ? kc.pool_bytes : 0;   // staging of the pooled tile only where a pool is fused
+    int fixed = 1024 /*align*/ + 1024 /*ctrl*/ + 2 * kc.out_bytes + 2 * pool_bytes;
     const int64_t w_slots = (int64_t)p.n_phases * p.taps * p.k_chunks;
     const int64_t w_bytes = w_slots * kc.b_bytes;
     int a_stages = std::min<int>(3, std::max<int>(2, p.k_chunks + 1));
     bool bres = mode >= 2 && p.n_tiles == 1 && fixed + 2 * kc.halo_stage_bytes + w_bytes <= kSmemBudget;
+    p.out_bufs = 2;
+    if (std::getenv("SNB_OUT_BUFS1_BRES") && !bres && mode >= 2 && p.n_tiles == 1 && kc.bn > 64 && !pre &&
+        fixed - kc.out_bytes - pool_bytes + 2 * kc.halo_stage_bytes + w_bytes <= kSmemBudget) {
+      // experiment: resident weights at the price of the second staging buffer.  Measured on conv 64 -> 128 before the pool
+      // staging became conditional: no gain, the single-buffered epilogue (3300 cycles per tile) becomes the bound.
+      bres = true;
+      p.out_bufs = 1;
+      fixed -= kc.out_bytes + pool_bytes;
+    }
     int b_stages = 0;
     if (bres) {
       while (a_stages > 2 && fixed + a_stages * kc.halo_stage_bytes + w_bytes > kSmemBudget) --a_stages;
@@ -1379,7 +1485,14 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       c->smem = fixed + a_stages * kc.halo_stage_bytes + (int)w_bytes;
     } else {
       a_stages = 2;
-      b_stages = (kSmemBudget - fixed - a_stages * kc.halo_stage_bytes) / kc.b_bytes;
+      // (SNB_OUT_BUFS = 1: one output staging buffer, the room goes to the weight ring -- measured 1 % SLOWER on the
+      // BN = 256 layers: their issuer waits on weight slots ~15 % of the time but runs ahead of the pipe, the pipe does not starve)
+      int nb = 2;
+      if (const char* e = std::getenv("SNB_OUT_BUFS")) nb = std::atoi(e) == 1 ? 1 : 2;
+      if (kc.bn <= 64 || pre) nb = 2;   // two epilogue groups own one buffer each
+      const int fixed_s = fixed - (2 - nb) * (kc.out_bytes + pool_bytes);
+      p.out_bufs = nb;
+      b_stages = (kSmemBudget - fixed_s - a_stages * kc.halo_stage_bytes) / kc.b_bytes;
       if (b_stages > kMaxBStages) b_stages = kMaxBStages;
       if (const char* e = std::getenv("SNB_B_STAGES")) {   // pipeline-depth experiments
         const int v = std::atoi(e);
@@ -1390,8 +1503,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
         return fail(SNB_E_UNSUPPORTED, "halo pipeline does not fit in shared memory");
       }
       // a third activation stage if there is room left
-      if (fixed + 3 * kc.halo_stage_bytes + b_stages * kc.b_bytes <= kSmemBudget) a_stages = 3;
-      c->smem = fixed + a_stages * kc.halo_stage_bytes + b_stages * kc.b_bytes;
+      if (fixed_s + 3 * kc.halo_stage_bytes + b_stages * kc.b_bytes <= kSmemBudget) a_stages = 3;
+      c->smem = fixed_s + a_stages * kc.halo_stage_bytes + b_stages * kc.b_bytes;
     }
     p.a_stages = a_stages;
     p.b_stages = b_stages;
@@ -1401,7 +1514,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
       // forces it off / on for every halo layer (A/B runs)
       // By tile (dual_mma = 1) only with resident weights and an activation ring of at least two tiles: a streamed weight
       // ring holds a fraction of a tile, the two issuers would just take turns.
-      int dual = bn <= 64 ? 1 : 0;
+      int dual = (bn <= 64 || bres) ? 1 : 0;
+      if (std::getenv("SNB_DUAL_NARROW_ONLY")) dual = bn <= 64 ? 1 : 0;
       if (const char* e = std::getenv("SNB_DUAL_MMA")) dual = std::atoi(e) != 0;
       p.dual_mma = (dual && bres && a_stages >= 2 * p.k_chunks) ? 1 : 0;
       if (p.dual_mma) {
@@ -1425,6 +1539,8 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
     if (mode >= 4 && !bres && !fuse_phases && !pre && fn_pair && m_tiles % 2 == 0 && sms >= 2) {
       c->fn = fn_pair;
       c->cluster = 2;
+      c->threads = 256;
+      p.epi_groups = 0;
       p.dual_mma = 0;   // the multicast weight ring is consumed in lock step by the pair
       p.m_pairs = static_cast<int32_t>(m_tiles / 2);
     }
@@ -1552,3 +1668,15 @@ extern "C" int snb_conv_launch(const snb_conv* c, void* stream) {
 extern "C" void snb_conv_destroy(snb_conv* c) { delete c; }
 
 extern "C" double snb_conv_flops(const snb_conv* c) { return c ? c->flops : 0.0; }
+
+#ifdef SNB_CONV_PROFILE
+// profiling builds only (tools/build_rev.py --profile): read (and clear) the wait-cycle counters of conv_halo_kernel
+extern "C" __attribute__((visibility("default"))) int snb_debug_conv_profile(unsigned long long* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, snb::g_conv_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(snb::g_conv_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif

@@ -75,15 +75,17 @@ def exchange_seam_tiles(tiles, owned, needed, rank, world):
             req.wait()
 
 
-def pick_tile_batch(n_tiles, preferred=13, lo=6, hi=24):
+def pick_tile_batch(n_tiles, preferred=85, lo=24, hi=96):
     """Tiles per network launch for a shard of n_tiles: the plan always runs whole batches, so the batch that wastes the
-    fewest padded tile slots wins (ties: closest to the preferred size)."""
+    fewest padded tile slots wins (ties: closest to the preferred size).  Large batches (measured on UNet16 at 512 x 512:
+    85 tiles per launch +3 % over 13): the low-resolution layers then fill many waves of 148 CTAs instead of 5.6."""
     if n_tiles <= hi:
         return max(1, n_tiles)
+    slack = max(1, n_tiles // 100)        # padded slots that are as good as none
     best = None
     for b in range(lo, hi + 1):
         waste = -(-n_tiles // b) * b - n_tiles
-        key = (waste, abs(b - preferred))
+        key = (max(0, waste - slack), abs(b - preferred), waste)
         if best is None or key < best[0]:
             best = (key, b)
     return best[1]

@@ -417,7 +417,7 @@ def test_world_size_2_tile_sharded_bands_equal_single_process(tmp_path):
     assert np.array_equal(got["mask"].numpy(), ((want > 0.5) * 255).astype(np.uint8))
     assert got["counts"].tolist() == [int((want > 0.5).sum()), 0, 0, int((want <= 0.5).sum())]
     # helper properties
-    assert sdist.pick_tile_batch(169) == 13 and sdist.pick_tile_batch(22) == 22 and sdist.pick_tile_batch(85) == 17
+    assert sdist.pick_tile_batch(169) == 85 and sdist.pick_tile_batch(22) == 22 and sdist.pick_tile_batch(85) == 85 and sdist.pick_tile_batch(338) == 85
     assert sdist.range_overlap((0, 10), (7, 20)) == (7, 3) and sdist.range_overlap((0, 5), (7, 9))[1] == 0
     for world in (1, 2, 3, 8):
         rows = [sdist.band_range(5000, r, world) for r in range(world)]

@@ -1,5 +1,5 @@
 """Summarise the `ncu --set full` capture of one UNet16 plan run (tools/layer_times.py 13) into profiles/rNN_ncu_conv_summary.{md,json}.
-Usage: ncu -i X.ncu-rep --page raw --csv > X.csv; python tools/ncu_conv_summary.py X.csv profiles/r02_ncu_conv_summary"""
+Usage: ncu -i X.ncu-rep --page raw --csv > X.csv; python tools/ncu_conv_summary.py X.csv profiles/r02_ncu_conv_summary [tiles]"""
 import csv
 import json
 import sys
@@ -17,6 +17,7 @@ SHAPES = [(512, 3, 64, 9), (512, 64, 64, 9), (256, 64, 128, 9), (256, 128, 128, 
           (128, 256, 256, 9), (64, 256, 512, 9), (64, 512, 512, 9), (64, 512, 512, 9), (32, 512, 512, 9), (32, 512, 512, 9),
           (32, 512, 512, 9), (16, 512, 512, 9), (32, 512, 256, 4), (32, 768, 512, 9), (64, 512, 256, 4), (64, 768, 512, 9),
           (128, 512, 256, 4), (128, 512, 256, 9), (256, 256, 64, 4), (256, 192, 128, 9), (512, 128, 32, 4), (512, 96, 32, 9)]
+TILES = int(sys.argv[3]) if len(sys.argv) > 3 else 13
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
 ix = {h: i for i, h in enumerate(hdr)}
@@ -34,7 +35,7 @@ for layer, (hw, ci, co, taps), r in zip(LAYERS, SHAPES, rows[2:]):
     scale = {"Mbyte": 1.0, "Gbyte": 1e3, "Kbyte": 1e-3, "byte": 1e-6}
     rd *= scale[rows[1][ix["dram__bytes_read.sum"]]]
     wr *= scale[rows[1][ix["dram__bytes_write.sum"]]]
-    gflop = 2.0 * 13 * hw * hw * ci * co * taps / 1e9
+    gflop = 2.0 * TILES * hw * hw * ci * co * taps / 1e9
     out.append({"layer": layer, "kernel": r[ix["Kernel Name"]].replace("void ", "").split("(")[0], "us": us,
                 "tflops": gflop / us * 1e3, "dram_read_MB": rd, "dram_write_MB": wr,
                 "tensor_pipe_active_pct": f(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
@@ -45,13 +46,13 @@ for layer, (hw, ci, co, taps), r in zip(LAYERS, SHAPES, rows[2:]):
 tot = sum(o["dram_read_MB"] + o["dram_write_MB"] for o in out)
 tus = sum(o["us"] for o in out)
 tfl = sum(o["tflops"] * o["us"] for o in out) / tus
-js = {"source": "ncu --set full --clock-control none, tools/layer_times.py 13 (UNet16, 13 tiles of 512x512, bf16), the %d conv launches of one "
-      "plan run" % len(out), "total_dram_bytes_per_plan_run": tot * 1e6, "conv_launches": len(out),
+js = {"source": "ncu --set full --clock-control none, tools/layer_times.py %d (UNet16, %d tiles of 512x512, bf16), the %d conv launches "
+      "of one plan run" % (TILES, TILES, len(out)), "tile_batch": TILES, "total_dram_bytes_per_plan_run": tot * 1e6, "conv_launches": len(out),
       "mean_dram_bytes_per_launch": tot * 1e6 / len(out), "total_us": tus, "tflops_over_plan_run": tfl, "launches": out}
 json.dump(js, open(sys.argv[2] + ".json", "w"), indent=1)
 with open(sys.argv[2] + ".md", "w") as fo:
-    fo.write("# ncu --set full, conv kernels of one UNet16 plan run (13 tiles of 512x512, bf16)\n\n")
-    fo.write("Command: `ncu --set full --clock-control none -k regex:\"conv_halo|conv_first|conv_igemm\" -s 48 -c 24 python tools/layer_times.py 13`"
+    fo.write("# ncu --set full, conv kernels of one UNet16 plan run (%d tiles of 512x512, bf16)\n\n" % TILES)
+    fo.write("Command: `ncu --set full --clock-control none -k regex:\"conv_halo|conv_first|conv_igemm\" -s 48 -c 24 python tools/layer_times.py %d`" % TILES +
              " (B200).\n`tensor pipe` = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active; clocks are what the power cap "
              "allowed during the replay; TFLOP/s = algorithmic FLOPs / ncu duration (cold caches, serialised).\n\n")
     fo.write("| layer | kernel | time us | TFLOP/s | DRAM read MB | DRAM write MB | tensor pipe % | SM GHz | regs |\n|---|---|---:|---:|---:|---:|---:|---:|---:|\n")
