@@ -910,12 +910,13 @@ constexpr int kFirstRawStage = 1664;                   // 10 x 160 = 1600 bytes,
 constexpr int kFirstRawStages = 4, kFirstAStages = 3;
 constexpr int kFirstABytes = kBM * 64;                 // 128 rows x 32 bf16
 
-// Warp roles (384 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-3 = builders (two pixels per thread),
-// 4-7 and 8-11 = TWO epilogue groups that take alternate tiles (accumulator stage 0 / 1): with K = 32 the MMA of a tile lasts
-// ~100 cycles while its epilogue (bias, ReLU, bf16, swizzled staging, TMA store of 128 x Cout) lasts ~1000, so this layer
-// is bound by the epilogue and, beyond it, by the HBM write of its output.
+// Warp roles (448 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-5 = builders (one pixel per thread),
+// 6-9 and 10-13 = TWO epilogue groups that take alternate tiles (accumulator stage 0 / 1): with K = 32 the MMA of a tile lasts
+// ~100 cycles while its epilogue (bias, ReLU, bf16, swizzled staging, TMA store of 128 x Cout) lasts ~1000.  Measured with
+// two builder warps (two pixels per thread): the issuer waited on the builders 998 of 1269 cycles per tile.
+constexpr int kFirstThreads = 448;
 template <int BN>
-__global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN, 32, 2>;
   constexpr uint32_t IDESC = make_idesc(kBM, BN, 1u);
   constexpr int TW = 16, TH = 8;
@@ -940,8 +941,8 @@ __global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constan
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_d[0]);
-    for (int i = 0; i < kFirstRawStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 2); }
-    for (int i = 0; i < kFirstAStages; ++i) { mbar_init(&a_ready[i], 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kFirstRawStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
+    for (int i = 0; i < kFirstAStages; ++i) { mbar_init(&a_ready[i], 4); mbar_init(&a_empty[i], 1); }
     mbar_init(b_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
@@ -976,10 +977,18 @@ __global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constan
       tc05_fence_after();
       const uint64_t bdesc = make_kmajor_desc<64>(smem_u32(smem_b), 8 * 64);
       uint32_t sa = 0, pa = 0, local_tile = 0;
+      SNB_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+      const long long prof_loop0 = clock64();
+#endif
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
         const uint32_t acc = local_tile & 1;
+        SNB_PROF_T0
         mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
+        SNB_PROF_ADD(2)
+        SNB_PROF_T0
         mbar_wait(&a_ready[sa], pa);
+        SNB_PROF_ADD(0)
         tc05_fence_after();
         const uint64_t adesc = make_kmajor_desc<64>(smem_u32(smem_a + sa * kFirstABytes), 8 * 64);
         umma_bf16_ss(adesc, bdesc, tmem_base + acc * BN, IDESC, 0u);
@@ -988,66 +997,81 @@ __global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constan
         umma_commit(&tmem_full[acc]);
         if (++sa == kFirstAStages) { sa = 0; pa ^= 1; }
       }
+#ifdef SNB_CONV_PROFILE
+      prof_c[3] = static_cast<unsigned long long>(clock64() - prof_loop0);
+      SNB_PROF_FLUSH(0, 0) SNB_PROF_FLUSH(2, 2) SNB_PROF_FLUSH(3, 3)
+      atomicAdd(&g_conv_prof[7], static_cast<unsigned long long>(local_tile));
+#endif
     }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------------ builders: one thread = two pixels = two 64-byte rows
-    const int r0 = threadIdx.x - 64;
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ builders: one thread = one pixel = one 64-byte row
+    const int r = threadIdx.x - 64;
+    const int px = r & 15, py = r >> 4;
     uint32_t s = 0, ps = 0, sa = 0, pa = 1;
+    SNB_PROF_DECL
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      SNB_PROF_T0
       mbar_wait(&raw_full[s], ps);
+      SNB_PROF_ADD(1)
       const unsigned short* raw = reinterpret_cast<const unsigned short*>(smem_in + s * kFirstRawStage);
-      uint4 rows[2][4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = r0 + h * 64;
-        const int px = r & 15, py = r >> 4;
+      uint4 rowv[4];
+      {
         unsigned short el[32];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const unsigned short* q = raw + (py + tap / 3) * kFirstRawW + (px + tap % 3 + kFirstRawLead - 1) * 3;
-          el[tap * 3 + 0] = q[0];
-          el[tap * 3 + 1] = q[1];
-          el[tap * 3 + 2] = q[2];
+        for (int dy = 0; dy < 3; ++dy) {
+          // k = tap * 3 + c = dy * 9 + (dx * 3 + c): the nine values of one neighbourhood row are contiguous in the raw box
+          const unsigned short* q = raw + (py + dy) * kFirstRawW + (px + kFirstRawLead - 1) * 3;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) el[dy * 9 + e] = q[e];
         }
 #pragma unroll
         for (int k = 27; k < 32; ++k) el[k] = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          rows[h][c] = make_uint4(el[c * 8 + 0] | ((uint32_t)el[c * 8 + 1] << 16), el[c * 8 + 2] | ((uint32_t)el[c * 8 + 3] << 16),
-                                  el[c * 8 + 4] | ((uint32_t)el[c * 8 + 5] << 16), el[c * 8 + 6] | ((uint32_t)el[c * 8 + 7] << 16));
+          rowv[c] = make_uint4(el[c * 8 + 0] | ((uint32_t)el[c * 8 + 1] << 16), el[c * 8 + 2] | ((uint32_t)el[c * 8 + 3] << 16),
+                               el[c * 8 + 4] | ((uint32_t)el[c * 8 + 5] << 16), el[c * 8 + 6] | ((uint32_t)el[c * 8 + 7] << 16));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[s]);       // the raw stage is in registers now
       if (++s == kFirstRawStages) { s = 0; ps ^= 1; }
+      SNB_PROF_T0
       mbar_wait(&a_empty[sa], pa);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = r0 + h * 64;
+      SNB_PROF_ADD(0)
+      {
         const int sw = (r >> 1) & 3;                   // 64-byte swizzle: 16-byte chunk index ^= (row >> 1) & 3
         uint8_t* row = smem_a + sa * kFirstABytes + r * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = rows[h][c];
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = rowv[c];
       }
       fence_proxy_async_smem();                        // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_ready[sa]);
       if (++sa == kFirstAStages) { sa = 0; pa ^= 1; }
     }
+#ifdef SNB_CONV_PROFILE
+    if (threadIdx.x == 64) { SNB_PROF_FLUSH(6, 0) SNB_PROF_FLUSH(1, 1) }   // builder: [6] operand stage free, [1] raw box landed
+#endif
   } else {
     // ------------------------------------------------------------------ two epilogue groups (128 threads each)
-    const int grp = (warp - 4) >> 2;                   // 0: warps 4-7 (even tiles), 1: warps 8-11 (odd tiles)
-    const int q = warp & 3;
+    const int grp = (warp - 6) >> 2;                   // 0: warps 6-9 (even tiles), 1: warps 10-13 (odd tiles)
+    const int q = warp & 3;                            // TMEM lane quarter (any four consecutive warps cover all four)
     const int row = q * 32 + lane;
-    const int epi_tid = threadIdx.x - 128 - grp * 128;
+    const int epi_tid = (warp - 6 - grp * 4) * 32 + lane;
     uint8_t* my_out = smem_out + grp * 2 * Cfg::OUT_BYTES;
     constexpr int CW = BN < 64 ? BN : 64;
     constexpr int OUT_SWZ = CW * 2;
     uint32_t local_tile = 0, n_store = 0;
+    SNB_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+    const long long prof_loop0 = clock64();
+#endif
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
       if ((local_tile & 1) != static_cast<uint32_t>(grp)) continue;
       const TileCoord tc = decode_tile<TW, TH>(p, t);
       const uint32_t acc = grp;
+      SNB_PROF_T0
       mbar_wait(&tmem_full[acc], (local_tile >> 1) & 1);
+      SNB_PROF_ADD(0)
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       // bias, ReLU, bf16, swizzled staging, TMA store (the common epilogue with this group's own staging buffers and barrier)
@@ -1064,18 +1088,22 @@ __global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-          float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
-                        __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
-                        __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
-                        __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
-          if (p.relu) {
+          float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-          }
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+          add2(f[0], f[1], b0.x, b0.y);
+          add2(f[2], f[3], b0.z, b0.w);
+          add2(f[4], f[5], b1.x, b1.y);
+          add2(f[6], f[7], b1.z, b1.w);
           const int sw = OUT_SWZ == 128 ? (row & 7) : ((row >> 1) & 3);
           const int chunk = g * 4 + j;
-          *reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          uint4 pk;
+          if (p.relu)
+            pk = make_uint4(pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]), pack_bf16x2_relu(f[4], f[5]),
+                            pack_bf16x2_relu(f[6], f[7]));
+          else
+            pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          *reinterpret_cast<uint4*>(sout + row * OUT_SWZ + ((chunk ^ sw) << 4)) = pk;
         }
       }
       tc05_fence_before();
@@ -1090,6 +1118,12 @@ __global__ void __launch_bounds__(384, 1) conv_first_kernel(const __grid_constan
       ++n_store;
     }
     if (epi_tid == 0) tma_store_wait_all<0>();
+#ifdef SNB_CONV_PROFILE
+    if (warp == 6 && lane == 0) {
+      prof_c[1] = static_cast<unsigned long long>(clock64() - prof_loop0);
+      SNB_PROF_FLUSH(4, 0) SNB_PROF_FLUSH(5, 1)
+    }
+#endif
   }
 
   tc05_fence_before();
@@ -1308,7 +1342,7 @@ static int create_first(const snb_conv_desc* d, snb_conv** out) {
   snb_conv* c = new (std::nothrow) snb_conv();
   if (!c) return fail(SNB_E_INVALID, "out of host memory");
   c->cluster = 1;
-  c->threads = 384;
+  c->threads = kFirstThreads;
   ConvParams& p = c->params;
   std::memset(&p, 0, sizeof(p));
   const int bn = (int)d->cout;

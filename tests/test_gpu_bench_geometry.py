@@ -116,6 +116,12 @@ def test_predict_tiled_512_384_against_oracle_pipeline(cuda):
     merged2, mask2 = pred.predict_device(torch.from_numpy(image).cuda())        # graph replay
     assert np.array_equal(merged2.cpu().numpy(), merged) and np.array_equal(mask2.cpu().numpy(), mask)
 
+    # the tile batching is not allowed to change a single bit (kernel selection depends on it: N tile, waves, issuers):
+    # 5 tiles per launch (3 launches, 3 padded slots) against all 12 in one launch
+    pred5 = sub.TiledPredictor(m, image.shape, 512, 384, batch_size=5, tta=False)
+    merged5, mask5 = pred5.predict_device(torch.from_numpy(image).cuda())
+    assert np.array_equal(merged5.cpu().numpy(), merged) and np.array_equal(mask5.cpu().numpy(), mask)
+
     x = to.normalize_image(image)
     s = to.SlicerOracle(x.shape, 512, 384, weight="pyramid")
     assert len(s.crops) == pred.n_tiles
