@@ -75,6 +75,22 @@ __device__ __forceinline__ uint32_t sc_pack_bf16x2(float lo, float hi) {
 }
 
 // smem: [a_stages x A_BYTES][B: b_stages (or all k_chunks when resident) x B_BYTES][P: 73,728 B][ctrl]
+// -DSNB_CONV_PROFILE (profiling builds only, tools/build_rev.py --profile): wait cycles of the roles, as in conv_tcgen05.cu.
+// [0] issuer: activation stage, [1] prologue warp 8: raw stage landed, [2] issuer: accumulator stage, [3] issuer loop,
+// [4] epilogue warp 4: accumulator full, [5] epilogue loop, [6] prologue loop, [7] tiles.
+#ifdef SNB_CONV_PROFILE
+__device__ unsigned long long g_scatter_prof[8];
+#define SC_PROF_DECL long long prof_t = 0; unsigned long long prof_c[4] = {0, 0, 0, 0}; (void)prof_t;
+#define SC_PROF_T0 prof_t = clock64();
+#define SC_PROF_ADD(i) prof_c[i] += static_cast<unsigned long long>(clock64() - prof_t);
+#define SC_PROF_FLUSH(dst, i) atomicAdd(&g_scatter_prof[dst], prof_c[i]);
+#else
+#define SC_PROF_DECL
+#define SC_PROF_T0
+#define SC_PROF_ADD(i)
+#define SC_PROF_FLUSH(dst, i)
+#endif
+
 template <int BK, bool PRE>
 __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const __grid_constant__ ScatterParams p) {
   constexpr int SWZ = BK * 2;
@@ -163,13 +179,21 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
         mbar_wait(&b_full[0], 0);
         tc05_fence_after();
       }
+      SC_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+      const long long prof_loop0 = clock64();
+#endif
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
         const uint32_t acc = local_tile & 1;
+        SC_PROF_T0
         mbar_wait(&tmem_empty[acc], ((local_tile >> 1) & 1) ^ 1);
+        SC_PROF_ADD(2)
         tc05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kScAcc;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
+          SC_PROF_T0
           mbar_wait(PRE ? &a_ready[sa] : &a_full[sa], pa);
+          SC_PROF_ADD(0)
           if (!bres) mbar_wait(&b_full[sb], pb);
           tc05_fence_after();
           const uint64_t adesc = make_kmajor_desc<SWZ>(smem_u32(smem_a + sa * A_BYTES), 8 * SWZ);
@@ -186,6 +210,11 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
         }
         umma_commit(&tmem_full[acc]);
       }
+#ifdef SNB_CONV_PROFILE
+      prof_c[3] = static_cast<unsigned long long>(clock64() - prof_loop0);
+      SC_PROF_FLUSH(0, 0) SC_PROF_FLUSH(2, 2) SC_PROF_FLUSH(3, 3)
+      atomicAdd(&g_scatter_prof[7], static_cast<unsigned long long>(local_tile));
+#endif
     }
   } else if (PRE && warp >= 8) {
     // ------------------------------------------------------------------ prologue: pre-activation of the A operand
@@ -195,13 +224,19 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
     const int jl = tt % CPR;                 // logical chunk = channels [8 jl, 8 jl + 8) of the K chunk
     const int r0 = tt / CPR;
     uint32_t s = 0, par = 0;
+    SC_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+    const long long prof_loop0 = clock64();
+#endif
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const ScTile tc = sc_decode(p, t);
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         const float4* sc4 = reinterpret_cast<const float4*>(p.pre_scale + kc * BK + jl * 8);
         const float4* sh4 = reinterpret_cast<const float4*>(p.pre_shift + kc * BK + jl * 8);
         const float4 s0 = __ldg(sc4), s1 = __ldg(sc4 + 1), b0 = __ldg(sh4), b1 = __ldg(sh4 + 1);
+        SC_PROF_T0
         mbar_wait(&a_full[s], par);
+        SC_PROF_ADD(1)
         uint8_t* base = smem_a + s * A_BYTES;
 #pragma unroll 2
         for (int r = r0; r < kScM; r += RSTEP) {
@@ -229,6 +264,12 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
         if (++s == static_cast<uint32_t>(p.a_stages)) { s = 0; par ^= 1; }
       }
     }
+#ifdef SNB_CONV_PROFILE
+    if (threadIdx.x == 256) {
+      prof_c[2] = static_cast<unsigned long long>(clock64() - prof_loop0);
+      SC_PROF_FLUSH(1, 1) SC_PROF_FLUSH(6, 2)
+    }
+#endif
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue (128 threads = 128 patch pixels)
     const int q = warp & 3;
@@ -242,10 +283,16 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
       bias[c] = b.x; bias[c + 1] = b.y; bias[c + 2] = b.z; bias[c + 3] = b.w;
     }
     uint32_t local_tile = 0;
+    SC_PROF_DECL
+#ifdef SNB_CONV_PROFILE
+    const long long prof_loop0 = clock64();
+#endif
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local_tile) {
       const ScTile tc = sc_decode(p, t);
       const uint32_t acc = local_tile & 1;
+      SC_PROF_T0
       mbar_wait(&tmem_full[acc], (local_tile >> 1) & 1);
+      SC_PROF_ADD(0)
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * kScAcc + (static_cast<uint32_t>(q * 32) << 16);
       // partial planes: P[tap][channel quad j][pixel] as float4 (fp32): consecutive pixels (= lanes) are 16 bytes
@@ -265,7 +312,9 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
       tc05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      SC_PROF_T0
       named_bar_sync(1, 128);
+      SC_PROF_ADD(2)
       const int ox = tc.x0 + px - 1, oy = tc.y0 + py - 1;
       if (interior && ox < p.w && oy < p.h) {
         float o[kScCout];
@@ -288,8 +337,16 @@ __global__ void __launch_bounds__(PRE ? 512 : 256, 1) conv_scatter_kernel(const 
         d4[1] = make_uint4(sc_pack_bf16x2(o[8], o[9]), sc_pack_bf16x2(o[10], o[11]), sc_pack_bf16x2(o[12], o[13]),
                            sc_pack_bf16x2(o[14], o[15]));
       }
+      SC_PROF_T0
       named_bar_sync(1, 128);   // the planes may be overwritten by the next tile
+      SC_PROF_ADD(2)
     }
+#ifdef SNB_CONV_PROFILE
+    if (warp == 4 && lane == 0) {
+      prof_c[1] = static_cast<unsigned long long>(clock64() - prof_loop0);
+      SC_PROF_FLUSH(4, 0) SC_PROF_FLUSH(5, 1)
+    }
+#endif
   }
 
   tc05_fence_before();
@@ -413,3 +470,14 @@ extern "C" int snb_conv_scatter_launch(const snb_conv_scatter* c, void* stream) 
 extern "C" void snb_conv_scatter_destroy(snb_conv_scatter* c) { delete c; }
 
 extern "C" double snb_conv_scatter_flops(const snb_conv_scatter* c) { return c ? c->flops : 0.0; }
+
+#ifdef SNB_CONV_PROFILE
+extern "C" __attribute__((visibility("default"))) int snb_debug_scatter_profile(unsigned long long* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, snb::g_scatter_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(snb::g_scatter_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif

@@ -398,9 +398,13 @@ __global__ void __launch_bounds__(256) pr_hist_kernel(const float* __restrict__ 
   extern __shared__ uint32_t sh[];            // [8 warps][2][n_thr+1] then thresholds
   const int bins = n_thr + 1;
   uint32_t* hist = sh;
-  float* s_thr = reinterpret_cast<float*>(sh + 8 * 2 * bins);
+  float* s_thr = reinterpret_cast<float*>(sh + 8 * 2 * bins) + 1;   // s_thr[-1] = -inf, s_thr[n_thr] = +inf (sentinels)
   for (int i = threadIdx.x; i < 8 * 2 * bins; i += blockDim.x) hist[i] = 0;
   for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr[i];
+  if (threadIdx.x == 0) {
+    s_thr[-1] = -INFINITY;
+    s_thr[n_thr] = INFINITY;
+  }
   __syncthreads();
   uint32_t* my = hist + (threadIdx.x >> 5) * 2 * bins;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -416,6 +420,20 @@ __global__ void __launch_bounds__(256) pr_hist_kernel(const float* __restrict__ 
     while (lo > 0 && !(p > s_thr[lo - 1])) --lo;
     return lo;
   };
+  // Fast path: the bin of sigmoid_f32(x) (the exact float the reference compares, expf + IEEE division, ~40 instructions)
+  // is decided from an SFU approximation pa (ex2.approx + rcp.approx, 4 instructions) whenever pa is farther than kEps from
+  // both neighbouring thresholds: |pa - sigmoid(x)| <= 1e-6 for |x| <= 20 (ex2.approx 2^-22 relative, its argument rounding
+  // |x| 2^-24 log2(e) p (1 - p), rcp.approx 1 ulp) and |sigmoid_f32(x) - sigmoid(x)| <= 4 ulp <= 2.4e-7, so both floats lie
+  // in the same open interval between two thresholds.  Everything else -- within kEps of a threshold (~5e-4 of uniform
+  // probabilities), |x| > 20, NaN -- takes the exact evaluation through ONE cold branch.  Same integers, 3x fewer instructions.
+  constexpr float kEps = 2e-6f;
+  auto bin_fast = [&](float x, int& lo) {
+    float e, pa;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pa) : "f"(1.f + e));
+    lo = min(n_thr, max(0, __float2int_rd((pa - t0) * gscale) + 1));
+    return fabsf(x) <= 20.f && pa - s_thr[lo - 1] > kEps && s_thr[lo] - pa > kEps;   // (NaN fails every comparison)
+  };
   const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(targets) & 15) == 0;
   if (vec) {
     for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += stride) {
@@ -426,7 +444,9 @@ __global__ void __launch_bounds__(256) pr_hist_kernel(const float* __restrict__ 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int truth = ((int)tv[e]) != 0;                         // astype(int32) then k*true with k=2
-        atomicAdd(&my[truth * bins + bin_of(sigmoid_f32(xs[e]))], 1u);
+        int lo;
+        if (!bin_fast(xs[e], lo)) lo = bin_of(sigmoid_f32(xs[e]));
+        atomicAdd(&my[truth * bins + lo], 1u);
       }
     }
   } else {
@@ -626,7 +646,7 @@ extern "C" int snb_pr_curve_update(const float* d_logits, const void* d_targets,
   if (n == 0) return SNB_OK;
   cudaStream_t st = as_stream(stream);
   const int bins = (int)n_thr + 1;
-  const size_t smem = (size_t)(8 * 2 * bins) * sizeof(uint32_t) + (size_t)n_thr * sizeof(float);
+  const size_t smem = (size_t)(8 * 2 * bins) * sizeof(uint32_t) + (size_t)(n_thr + 2) * sizeof(float);   // + two sentinels
   const int grid = reduce_grid(n);
   ReduceWs* ws = static_cast<ReduceWs*>(d_workspace);
 #define SNB_PR(DT)                                                                                         \

@@ -75,10 +75,13 @@ __global__ void __launch_bounds__(256) split_hwc_kernel(SlicerGeom g, const uint
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kSplitRows + (threadIdx.x >> 5);
   if (row >= total_rows) return;
-  const int64_t t = row / T;
-  const int ty = (int)(row - t * T);
-  const int64_t tile = tile_begin + t;
-  const int cy = (int)((tile / g.tiles_x) * g.step), cx = (int)((tile % g.tiles_x) * g.step);
+  // 32-bit unsigned divisions (the host checks the ranges): the emulated 64-bit ones were ~250 of the instructions a
+  // thread spends on its three 16-byte chunks
+  const uint32_t t = (uint32_t)row / (uint32_t)T;
+  const int ty = (int)((uint32_t)row - t * (uint32_t)T);
+  const uint32_t tile = (uint32_t)tile_begin + t;
+  const uint32_t tyi = tile / (uint32_t)g.tiles_x;
+  const int cy = (int)(tyi * (uint32_t)g.step), cx = (int)((tile - tyi * (uint32_t)g.tiles_x) * (uint32_t)g.step);
   const int py = cy + ty - (int)g.margin_top;
   const int H = (int)g.image_h, Wd = (int)g.image_w, ml = (int)g.margin_left;
   const bool row_inside = py >= 0 && py < H;
@@ -397,7 +400,10 @@ __global__ void __launch_bounds__(256) split_norm_nhwc3_kernel(SlicerGeom g, con
 #pragma unroll
       for (int k = 0; k < 24; ++k) {
         const int c = k % 3;
-        const __nv_bfloat16 v = __float2bfloat16(fmaf((float)lv[k], la[c], lb[c]));
+        // (float) level on the FMA pipe: 0x4B000000 | level is the float 2^23 + level (24 I2F per thread and trip were
+        // queueing on the 16-per-clock conversion unit)
+        const float fl = __uint_as_float(0x4B000000u | (uint32_t)lv[k]) - 8388608.f;
+        const __nv_bfloat16 v = __float2bfloat16(fmaf(fl, la[c], lb[c]));
         e[k] = *reinterpret_cast<const unsigned short*>(&v);
       }
     } else {

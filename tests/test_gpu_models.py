@@ -532,6 +532,14 @@ def test_unet_against_reference_vectors(cuda, golden_dir, name, abn):
     with torch.no_grad():
         q = no.unet_forward(sd, torch.from_numpy(g["x"]), abn=abn, quant=no.bf16_round)
     assert (y - q).abs().max().item() < 0.03 * max(1.0, q.abs().max().item())
+    # tf32 mode (fp32 storage, TF32 tensor-core products): an order of magnitude tighter than bf16 on these He-scaled weights
+    m.set_precision("tf32")
+    with torch.no_grad():
+        y32 = m(torch.from_numpy(g["x"]).cuda()).cpu()
+    p32 = (torch.sigmoid(y32) - torch.sigmoid(ref)).abs().max().item()
+    print("margin %s 2x64x96 tf32: max |p - reference| = %.3g" % (name, p32))
+    assert p32 < 2e-3, p32
+    m.set_precision("bf16")
     m.train()
     with pytest.raises(NotImplementedError):
         m(torch.from_numpy(g["x"]).cuda())

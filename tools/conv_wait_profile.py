@@ -17,27 +17,36 @@ from snb_b200.engine import ConvOp  # noqa: E402
 from snb_b200.lib import models as M  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 13
-m = M.UNet16()
-m.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=0))
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+name = sys.argv[3] if len(sys.argv) > 3 else "unet16"
+if name == "fcdensenet67":
+    m = M.FCDenseNet67(n_classes=1)
+    m.load_state_dict(synth.fcdensenet_state_dict(seed=0))
+else:
+    m = M.UNet16()
+    m.load_state_dict(synth.vgg_unet_state_dict("unet16", seed=0))
 m = m.cuda().eval()
-plan = m.plan(batch, 512, 512, sigmoid=True)
-plan.x_in3.t.normal_()
+plan = m.plan(batch, T, T, sigmoid=True)
+(plan.x_in3 if getattr(plan, 'x_in3', None) is not None else plan.x_patch).t.normal_()
 for _ in range(2):
     plan.run()
 torch.cuda.synchronize()
 lib = N.lib()
 prof = lib.snb_debug_conv_profile
 prof.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+prof_sc = lib.snb_debug_scatter_profile      # conv_scatter_kernel: "w:wgt" = prologue warp waiting for the raw stage, "prodB" = prologue loop
+prof_sc.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 buf = (ctypes.c_ulonglong * 8)()
 st = N.stream_ptr()
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 print("cycles per tile (one CTA's view; %d CTAs)" % sms)
 print("%-44s %7s | %8s %7s %7s %7s | %8s %7s | %7s" % ("layer", "tiles", "issuer", "w:act", "w:wgt", "w:acc", "epilogue", "w:full", "prodB"))
 for k, op in enumerate(plan.ops):
-    if not isinstance(op, ConvOp):
+    if not getattr(op, "flops", 0):
         continue
     torch.cuda.synchronize()
     prof(buf, 1)
+    prof_sc(buf, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     op(st)
@@ -45,8 +54,13 @@ for k, op in enumerate(plan.ops):
     torch.cuda.synchronize()
     prof(buf, 0)
     v = list(buf)
+    kind = "halo"
+    if v[7] == 0:
+        prof_sc(buf, 0)
+        v = list(buf)
+        kind = "scat"
     tiles = max(1, v[7])
-    d = op.desc
-    name = "%2d kind=%d %4dx%-4d %4d->%-4d %.3f ms" % (k, d[0], d[1], d[2], d[3], d[4], e0.elapsed_time(e1))
+    d = getattr(op, "desc", None)
+    name = ("%2d %s k=%d %4dx%-4d %4d->%-4d" % (k, kind, d[0], d[1], d[2], d[3], d[4]) if d is not None else "%2d %s %s" % (k, kind, type(op).__name__)) + " %.3f ms" % e0.elapsed_time(e1)
     print("%-44s %7d | %8.0f %7.0f %7.0f %7.0f | %8.0f %7.0f | %7.0f" % (
         name, v[7], v[3] / tiles, v[0] / tiles, v[1] / tiles, v[2] / tiles, v[5] / tiles, v[4] / tiles, v[6] / tiles))
