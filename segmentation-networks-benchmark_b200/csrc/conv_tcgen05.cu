@@ -1031,8 +1031,9 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
           rowv[c] = make_uint4(el[c * 8 + 0] | ((uint32_t)el[c * 8 + 1] << 16), el[c * 8 + 2] | ((uint32_t)el[c * 8 + 3] << 16),
                                el[c * 8 + 4] | ((uint32_t)el[c * 8 + 5] << 16), el[c * 8 + 6] | ((uint32_t)el[c * 8 + 7] << 16));
       }
+      fence_proxy_async_smem();                        // generic-proxy reads before the async-proxy refill of the stage
       __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[s]);       // the raw stage is in registers now
+      if (lane == 0) mbar_arrive(&raw_empty[s]);       // the raw stage is in registers now (rowv depends on every load)
       if (++s == kFirstRawStages) { s = 0; ps ^= 1; }
       SNB_PROF_T0
       mbar_wait(&a_empty[sa], pa);

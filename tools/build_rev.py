@@ -29,6 +29,9 @@ with tempfile.TemporaryDirectory() as tmp:
     flags = [f.replace(os.path.join(ROOT, "include"), os.path.join(tmp, "include")) for f in b.NVCC_FLAGS if f != "--use_fast_math=false"]
     if profile:
         flags.append("-DSNB_CONV_PROFILE")
+        flags += os.environ.get("SNB_EXTRA_NVCC_FLAGS", "").split()      # timing experiments (e.g. -DSNB_TS_EXP=1)
+        if os.environ.get("SNB_PROFILE_TAG"):
+            rev = "profile_" + os.environ["SNB_PROFILE_TAG"]
     objs, procs = [], []
     for src in sorted(f for f in os.listdir(csrc) if f.endswith(".cu")):
         obj = os.path.join(tmp, src[:-3] + ".o")

@@ -36,7 +36,7 @@ prof = lib.snb_debug_conv_profile
 prof.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 prof_sc = lib.snb_debug_scatter_profile      # conv_scatter_kernel: "w:wgt" = prologue warp waiting for the raw stage, "prodB" = prologue loop
 prof_sc.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 12)()
 st = N.stream_ptr()
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 print("cycles per tile (one CTA's view; %d CTAs)" % sms)
@@ -62,5 +62,6 @@ for k, op in enumerate(plan.ops):
     tiles = max(1, v[7])
     d = getattr(op, "desc", None)
     name = ("%2d %s k=%d %4dx%-4d %4d->%-4d" % (k, kind, d[0], d[1], d[2], d[3], d[4]) if d is not None else "%2d %s %s" % (k, kind, type(op).__name__)) + " %.3f ms" % e0.elapsed_time(e1)
-    print("%-44s %7d | %8.0f %7.0f %7.0f %7.0f | %8.0f %7.0f | %7.0f" % (
-        name, v[7], v[3] / tiles, v[0] / tiles, v[1] / tiles, v[2] / tiles, v[5] / tiles, v[4] / tiles, v[6] / tiles))
+    extra = "  | TS prologue: w:tmem %.0f  st+arrive %.0f" % (v[8] / tiles, v[9] / tiles) if kind == "scat" and v[9] else ""
+    print("%-44s %7d | %8.0f %7.0f %7.0f %7.0f | %8.0f %7.0f | %7.0f%s" % (
+        name, v[7], v[3] / tiles, v[0] / tiles, v[1] / tiles, v[2] / tiles, v[5] / tiles, v[4] / tiles, v[6] / tiles, extra))
