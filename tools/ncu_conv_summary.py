@@ -29,8 +29,8 @@ def f(r, name):
 
 out = []
 for layer, (hw, ci, co, taps), r in zip(LAYERS, SHAPES, rows[2:]):
-    us = f(r, "gpu__time_duration.sum")
-    us = us / 1e3 if rows[1][ix["gpu__time_duration.sum"]] in ("ns", "nsecond") else us
+    us = f(r, "gpu__time_duration.sum") * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3,
+                                           "s": 1e6}[rows[1][ix["gpu__time_duration.sum"]]]
     rd, wr = f(r, "dram__bytes_read.sum"), f(r, "dram__bytes_write.sum")
     scale = {"Mbyte": 1.0, "Gbyte": 1e3, "Kbyte": 1e-3, "byte": 1e-6}
     rd *= scale[rows[1][ix["dram__bytes_read.sum"]]]
