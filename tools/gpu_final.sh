@@ -20,7 +20,8 @@ timeout 600 python bench.py --precision tf32 --steps 3 --warmup 3 --no-cpu-basel
 timeout 300 python tools/hbm_kernels.py > gpurun_out/${R}_hbm_kernels.txt 2>&1; cut -c1-110 gpurun_out/${R}_hbm_kernels.txt
 (timeout 300 python tools/train_step_bench.py --batch 8 --steps 20; timeout 300 python tools/train_step_bench.py --batch 32 --steps 10) > gpurun_out/${R}_train_step.txt 2>&1; cat gpurun_out/${R}_train_step.txt
 SNB_B200_LIB=tools/ab/libsnb_b200_profile.so timeout 200 python tools/conv_wait_profile.py 13 > gpurun_out/${R}_conv_roles.txt 2>&1; tail -3 gpurun_out/${R}_conv_roles.txt
+SNB_B200_LIB=tools/ab/libsnb_b200_profile.so timeout 200 python tools/conv_wait_profile.py 44 224 fcdensenet67 > gpurun_out/${R}_fcd_roles.txt 2>&1; tail -2 gpurun_out/${R}_fcd_roles.txt | cut -c1-200
 # launch list of the bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 106 -c 530 --csv --log-file gpurun_out/${R}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/${R}_ncu_bench.log 2>&1; echo "ncu launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_halo|conv_first|conv_igemm" -s 48 -c 24 -f -o gpurun_out/${R}_conv85 python tools/layer_times.py 85 > gpurun_out/${R}_ncu_conv85.log 2>&1; echo "ncu conv rc=$?"
+timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg.per_second,launch__registers_per_thread --clock-control none -k regex:"conv_halo|conv_first|conv_igemm" -s 48 -c 24 -f -o gpurun_out/${R}_conv85m python tools/layer_times.py 85 > gpurun_out/${R}_ncu_conv85m.log 2>&1; echo "ncu conv metrics rc=$?"
 ls -la gpurun_out/${R}_* | head -40
