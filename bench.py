@@ -32,9 +32,10 @@ MODELS = {
     # 148 CTAs instead of 5.6 / 11.2 (measured: 13 -> 555, 57 -> 572, 85 -> 575, 169 -> 563 Mpx/s)
     "unet16": ("UNet16", lambda s: s.vgg_unet_state_dict("unet16", seed=0), 512, 384, 85, "configs[2]: UNet16"),
     "unet11": ("UNet11", lambda s: s.vgg_unet_state_dict("unet11", seed=0), 512, 384, 85, "UNet11 (TernausNet-VGG11)"),
-    "zf_unet": ("ZF_UNET", lambda s: s.zf_unet_state_dict(seed=0), 224, 112, 44, "ZF_UNET"),
-    "linknet34": ("LinkNet34", lambda s: s.linknet34_state_dict(seed=0), 512, 384, 85, "LinkNet34 (configs[1] model, eval forward)"),
-    "fcdensenet67": ("FCDenseNet67", lambda s: s.fcdensenet_state_dict(seed=0), 224, 112, 44, "configs[4]: FCDenseNet67"),
+    # 1936 tiles of 224 x 224: 11 launches of 176 (zf_unet: 44 -> 372, 176 -> 395 Mpx/s), 16 launches of 121 (fcdensenet67)
+    "zf_unet": ("ZF_UNET", lambda s: s.zf_unet_state_dict(seed=0), 224, 112, 176, "ZF_UNET"),
+    "linknet34": ("LinkNet34", lambda s: s.linknet34_state_dict(seed=0), 512, 384, 169, "LinkNet34 (configs[1] model, eval forward)"),
+    "fcdensenet67": ("FCDenseNet67", lambda s: s.fcdensenet_state_dict(seed=0), 224, 112, 121, "configs[4]: FCDenseNet67"),
 }
 
 
@@ -486,7 +487,7 @@ def run_secondary(args, dev, peak_tf):
         m = M.FCDenseNet67(n_classes=1)
         m.load_state_dict(synth.fcdensenet_state_dict(seed=0))
         m = m.to(dev).eval()
-        pred = sub.TiledPredictor(m, (IMAGE_HW, IMAGE_HW, 3), 224, 112, batch_size=44, tta=False, device=dev)
+        pred = sub.TiledPredictor(m, (IMAGE_HW, IMAGE_HW, 3), 224, 112, batch_size=MODELS["fcdensenet67"][4], tta=False, device=dev)
         img = torch.from_numpy(synth.image_u8(0, IMAGE_HW, IMAGE_HW)).to(dev)
         steps = 2
         for _ in range(2):

@@ -552,12 +552,7 @@ __global__ void __launch_bounds__(512, 1) conv_scatter_ts_kernel(const __grid_co
       const float4* sh4 = reinterpret_cast<const float4*>(s_pre + nc + kc * BK);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-#if defined(SNB_TS_EXP) && SNB_TS_EXP == 1   // timing experiment: no shared-memory reads for (scale, shift) -- results are wrong
-        const float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-        (void)sc4; (void)sh4;
-#else
         const float4 s0 = sc4[2 * j], s1 = sc4[2 * j + 1], b0 = sh4[2 * j], b1 = sh4[2 * j + 1];
-#endif
         const uint32_t w[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
         const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -603,7 +598,12 @@ __global__ void __launch_bounds__(512, 1) conv_scatter_ts_kernel(const __grid_co
     }
 #endif
   } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ epilogue: as in conv_scatter_kernel
+    // ------------------------------------------------------------------ epilogue: shifted sum of the nine partial planes
+    // out(q) = bias + sum_{dy,dx} P[dy,dx](q + 8 dy + dx).  The kernel above sends all nine fp32 planes through shared
+    // memory (73 KB written + read per tile, the largest shared-memory stream of the kernel).  Here the dx shifts are warp
+    // shuffles (a warp holds 4 patch rows of 8 pixels: the x neighbours of an interior pixel are lanes +-1) and only the
+    // two row sums S(-1), S(+1) that have to move by one patch ROW (8 lanes: across warps at the warp's first / last row)
+    // go through shared memory: 2 x 8 KB.
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int px = row % kScPW, py = row / kScPW;
@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(512, 1) conv_scatter_ts_kernel(const __grid_co
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
       bias[c] = b.x; bias[c + 1] = b.y; bias[c + 2] = b.z; bias[c + 3] = b.w;
     }
+    float4* p4 = reinterpret_cast<float4*>(smem_p);      // [2 planes][4 channel quads][128 pixels] of float4
     uint32_t local_tile = 0;
     SC_PROF_DECL
 #ifdef SNB_CONV_PROFILE
@@ -627,42 +628,43 @@ __global__ void __launch_bounds__(512, 1) conv_scatter_ts_kernel(const __grid_co
       SC_PROF_ADD(0)
       tc05_fence_after();
       const uint32_t t_addr = tmem_base + acc * kTsAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      float4* p4 = reinterpret_cast<float4*>(smem_p);
-#pragma unroll 3
-      for (int tap = 0; tap < 9; ++tap) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_addr + tap * kScCout, v);
-        tmem_ld_wait();
-#if defined(SNB_TS_EXP) && SNB_TS_EXP == 2   // timing experiment: no partial planes in shared memory -- results are wrong
-        if (tap == 20) p4[row] = make_float4(__uint_as_float(v[0]), 0.f, 0.f, 0.f);
-#else
+      float o[kScCout];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          p4[(tap * 4 + j) * kScM + row] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-#endif
+      for (int dy = 0; dy < 3; ++dy) {
+        uint32_t vl[16], vc[16], vr[16];
+        tmem_ld_32x16(t_addr + (dy * 3 + 0) * kScCout, vl);     // tap (dy, dx = -1): wanted from the pixel on the left
+        tmem_ld_32x16(t_addr + (dy * 3 + 1) * kScCout, vc);
+        tmem_ld_32x16(t_addr + (dy * 3 + 2) * kScCout, vr);     // tap (dy, dx = +1): from the pixel on the right
+        tmem_ld_wait();
+        float sdy[kScCout];
+#pragma unroll
+        for (int c = 0; c < kScCout; ++c) {
+          const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[c]), 1);
+          const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(vr[c]), 1);
+          sdy[c] = (l + __uint_as_float(vc[c])) + r;            // (garbage at px = 0 / 7: those pixels are not outputs)
+        }
+        if (dy == 1) {
+#pragma unroll
+          for (int c = 0; c < kScCout; ++c) o[c] = bias[c] + sdy[c];
+        } else {
+          // S(dy = -1) is wanted by the pixel one patch row BELOW, S(+1) by the one above: plane 0 / 1
+          float4* pl = p4 + (dy == 0 ? 0 : 4 * kScM);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pl[j * kScM + row] = make_float4(sdy[4 * j], sdy[4 * j + 1], sdy[4 * j + 2], sdy[4 * j + 3]);
+        }
       }
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
       tc05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       named_bar_sync(1, 128);
       const int ox = tc.x0 + px - 1, oy = tc.y0 + py - 1;
       if (interior && ox < p.w && oy < p.h) {
-        float o[kScCout];
 #pragma unroll
-        for (int c = 0; c < kScCout; ++c) o[c] = bias[c];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int src = row + (tap / 3 - 1) * kScPW + (tap % 3 - 1);
-#if defined(SNB_TS_EXP) && SNB_TS_EXP == 2
-          o[tap] += (float)src;
-#else
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 a = p4[(tap * 4 + j) * kScM + src];
-            o[4 * j] += a.x; o[4 * j + 1] += a.y; o[4 * j + 2] += a.z; o[4 * j + 3] += a.w;
-          }
-#endif
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = p4[j * kScM + row - kScPW];               // S(-1) of the pixel above
+          const float4 b = p4[(4 + j) * kScM + row + kScPW];         // S(+1) of the pixel below
+          o[4 * j] += a.x + b.x; o[4 * j + 1] += a.y + b.y; o[4 * j + 2] += a.z + b.z; o[4 * j + 3] += a.w + b.w;
         }
         __nv_bfloat16* dst = p.out + ((static_cast<int64_t>(tc.img) * p.h + oy) * p.w + ox) * p.out_cstride;
         uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -671,7 +673,7 @@ __global__ void __launch_bounds__(512, 1) conv_scatter_ts_kernel(const __grid_co
         d4[1] = make_uint4(sc_pack_bf16x2(o[8], o[9]), sc_pack_bf16x2(o[10], o[11]), sc_pack_bf16x2(o[12], o[13]),
                            sc_pack_bf16x2(o[14], o[15]));
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 128);   // the planes may be overwritten by the next tile
     }
 #ifdef SNB_CONV_PROFILE
     if (warp == 4 && lane == 0) {

@@ -2,8 +2,8 @@
 
 The unit tests run small shapes where `snb_conv_create` picks other kernels than at the benchmarked shapes
 (wave-aware N = 128 tiles on the 32x32 / 16x16 layers, resident weights, conv_halo_kernel<256,...>).  Here the plans are
-built exactly as bench.py builds them -- default SNB_CONV_MODE, UNet16 at 13 x 512 x 512, FCDenseNet67 / ZF_UNET at
-44 x 224 x 224 -- and checked against the CPU oracle (fp32, and with bf16-rounded conv operands) on a few tiles of the
+built exactly as bench.py builds them -- default SNB_CONV_MODE, UNet16 at 13 and 85 x 512 x 512, FCDenseNet67 / ZF_UNET at
+121 / 176 x 224 x 224 (and at 44, round 1's batch) -- and checked against the CPU oracle (fp32, and with bf16-rounded conv operands) on a few tiles of the
 batch, then through the whole tiled pipeline at 512 / 384 on an image small enough for the oracle.
 """
 import numpy as np
@@ -44,8 +44,9 @@ def _check_tiles(probs, x, picks, fwd, fwd_q):
     return worst_p, worst_l
 
 
-def test_unet16_plan_at_bench_geometry(cuda):
-    """UNet16, batch 13 of 512x512 tiles, default kernel selection (the plan bench.py replays)."""
+@pytest.mark.parametrize("nb", [13, 85])
+def test_unet16_plan_at_bench_geometry(cuda, nb):
+    """UNet16, 85 tiles of 512x512 per launch (the plan bench.py replays; 13 = round 1's), default kernel selection."""
     from snb_b200.lib.models import UNet16
 
     sd = synth.vgg_unet_state_dict("unet16", seed=0)           # bench.py's weights
@@ -53,15 +54,15 @@ def test_unet16_plan_at_bench_geometry(cuda):
     m.load_state_dict(sd)
     m = m.cuda().eval()
     g = torch.Generator(device="cuda").manual_seed(5)
-    x = torch.randn((13, 3, 512, 512), device="cuda", generator=g)
-    plan = m.plan(13, 512, 512, sigmoid=True)
+    x = torch.randn((nb, 3, 512, 512), device="cuda", generator=g)
+    plan = m.plan(nb, 512, 512, sigmoid=True)
     plan.load_nchw(x)
     probs = plan.run().clone()
     torch.cuda.synchronize()
-    assert probs.shape == (13, 512, 512) and torch.isfinite(probs).all()
-    p_err, l_err = _check_tiles(probs, x, (0, 6, 12), lambda t: no.unet_vgg_forward(sd, t, "unet16"),
+    assert probs.shape == (nb, 512, 512) and torch.isfinite(probs).all()
+    p_err, l_err = _check_tiles(probs, x, (0, nb // 2, nb - 1), lambda t: no.unet_vgg_forward(sd, t, "unet16"),
                                 lambda t: no.unet_vgg_forward(sd, t, "unet16", quant=no.bf16_round))
-    print("unet16 13x512x512: max |p - oracle| = %.3g, logits vs bf16 oracle %.3g" % (p_err, l_err))
+    print("unet16 %dx512x512: max |p - oracle| = %.3g, logits vs bf16 oracle %.3g" % (nb, p_err, l_err))
     assert p_err < BF16_PROB_TOL, p_err
     assert l_err < 0.02, l_err
     # the nn.Module path (logits, no sigmoid) at the same geometry agrees with the plan
@@ -70,9 +71,9 @@ def test_unet16_plan_at_bench_geometry(cuda):
     assert (torch.sigmoid(y[:, 0]) - probs[:2]).abs().max().item() < 2e-3
 
 
-@pytest.mark.parametrize("arch", ["fcdensenet67", "zf_unet"])
-def test_224_plans_at_bench_batch(cuda, arch):
-    """configs[4] (FCDenseNet67) and ZF_UNET at the tile batch bench.py uses for them: 44 x 224 x 224."""
+@pytest.mark.parametrize("arch,nb", [("fcdensenet67", 44), ("zf_unet", 44), ("fcdensenet67", 121), ("zf_unet", 176)])
+def test_224_plans_at_bench_batch(cuda, arch, nb):
+    """configs[4] (FCDenseNet67) and ZF_UNET at the tile batches bench.py uses for them (121 / 176 x 224 x 224; 44 in round 1)."""
     from snb_b200.lib.models import FCDenseNet67, ZF_UNET
 
     if arch == "fcdensenet67":
@@ -88,13 +89,13 @@ def test_224_plans_at_bench_batch(cuda, arch):
     m.load_state_dict(sd)
     m = m.cuda().eval()
     g = torch.Generator(device="cuda").manual_seed(7)
-    x = torch.randn((44, 3, 224, 224), device="cuda", generator=g)
-    plan = m.plan(44, 224, 224, sigmoid=True)
+    x = torch.randn((nb, 3, 224, 224), device="cuda", generator=g)
+    plan = m.plan(nb, 224, 224, sigmoid=True)
     plan.load_nchw(x)
     probs = plan.run().clone()
     torch.cuda.synchronize()
-    p_err, l_err = _check_tiles(probs, x, (0, 21, 43), fwd, fwd_q)
-    print("%s 44x224x224: max |p - oracle| = %.3g, logits vs bf16 oracle %.3g" % (arch, p_err, l_err))
+    p_err, l_err = _check_tiles(probs, x, (0, nb // 2, nb - 1), fwd, fwd_q)
+    print("%s %dx224x224: max |p - oracle| = %.3g, logits vs bf16 oracle %.3g" % (arch, nb, p_err, l_err))
     assert p_err < BF16_PROB_TOL, p_err
     assert l_err < 0.03, l_err
 
