@@ -427,9 +427,9 @@ def run_cuda(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": traffic,
-                     "traffic_note": "mean dram__bytes_read+write per conv launch of one 13-tile plan run (ncu --set full, %s); "
+                     "traffic_note": "mean dram__bytes_read+write per conv launch of one plan run at the same tiles per launch (ncu, %s); "
                                      "algorithmic FLOPs per launch vary per layer" % traffic_src,
-                     "kernel": "conv_halo_kernel / conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
+                     "kernel": "conv_halo_kernel / conv_first_kernel (tcgen05 implicit GEMM, all %d conv launches of the timed region)" % conv_launches,
                      "peak_source": peak_src + " bf16_tflops_sustained",
                      "timing": "CUDA events after every launch in an eager re-run of the same K steps (the timed "
                                "region itself replays a CUDA graph); shares are of that eager pass",
