@@ -708,8 +708,7 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
     // so those layers were issue-bound (ncu: the issuing warp busy 85 % of the time, epilogue warps waiting).  With
     // dual_mma = 1 a second warp issues too: warp 1 owns the even local tiles (TMEM stage 0), warp 2 the odd ones (stage 1);
     // both walk the same in-order operand rings and skip the other warp's stages.  dual_mma = 2 (fused ConvTranspose
-    // phases): both warps work on EVERY tile, warp 1 on the accumulators of phases 0-1, warp 2 on phases 2-3; each still
-    // observes every weight-ring slot in order (a parity wait is only sound one phase ahead), the owner alone releases it.
+    // phases, resident weights): both warps work on EVERY tile, warp 1 on the accumulators of phases 0-1, warp 2 on 2-3.
     if (elect_one()) {
       constexpr uint32_t HI_A = desc_hi<SWZ>(kHaloW * SWZ);   // 8-row groups are one halo row (10 pixels) apart
       constexpr uint32_t HI_B = desc_hi<SWZ>(8 * SWZ);
@@ -1557,7 +1556,11 @@ extern "C" int snb_conv_create(const snb_conv_desc* d, snb_conv** out) {
         a_stages -= a_stages % (2 * p.k_chunks);   // a ring slot then belongs to one issuer for good (see the skip in the kernel)
         p.a_stages = a_stages;
       }
-      if (dual && fuse_phases) p.dual_mma = 2;   // split by phase instead: no ring constraint, streamed weights included
+      // Fused ConvTranspose phases: split by phase pair instead (no constraint on the activation ring: both issuers consume
+      // every stage, its "free" barrier counts two arrivals).  Resident weights only: with a streamed weight ring the
+      // non-owner has to OBSERVE the owner's slots, and an observer that falls two fills behind misreads the barrier parity
+      // and waits for ever -- compute-sanitizer's timing produced exactly that hang (and the split gained nothing there).
+      if (dual && fuse_phases && bres) p.dual_mma = 2;
     }
     c->fn = p.taps == 9 ? kc.fn_halo9 : (fuse_phases ? kc.fn_halo4f : kc.fn_halo4);
     if (pre) {

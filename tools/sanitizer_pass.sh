@@ -16,4 +16,4 @@ run mem_wgrad memcheck 600 tests/test_gpu_wgrad.py tests/test_gpu_conv_grad.py -
 run mem_slicer_reduce memcheck 600 tests/test_gpu_slicer.py tests/test_gpu_reduce.py tests/test_gpu_abn.py -k "not full_size"
 run race_reduce racecheck 600 tests/test_gpu_reduce.py tests/test_gpu_abn.py -k "not full_size"
 run race_slicer racecheck 600 tests/test_gpu_slicer.py -k "not full_size"
-run mem_models memcheck 900 tests/test_gpu_models.py -k "logits_against_reference_vectors or linknet34_against_reference_vectors or zf_unet_against or fused_train_step"
+run mem_models memcheck 900 tests/test_gpu_models.py -k "logits_against_reference_vectors or linknet34_against_reference_vectors or zf_unet_against or fused_train_step or fcdensenet67_against"
