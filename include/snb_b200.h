@@ -194,6 +194,10 @@ SNB_API int snb_conv_launch(const snb_conv* c, void* stream);
 SNB_API void snb_conv_destroy(snb_conv* c);
 /* algorithmic FLOPs of one launch (2*MACs, padding excluded), for roofline bookkeeping */
 SNB_API double snb_conv_flops(const snb_conv* c);
+/* Redirect the fused-head output (float [n][h][w]) of a conv created with d_head_w != NULL: the tiled predictor lets the
+ * last layer write straight into its probability-tile buffer (the reference copies every batch, inria_submit.py:251-253).
+ * Takes effect at the next snb_conv_launch; a CUDA graph keeps the pointer that was set when the launch was captured. */
+SNB_API int snb_conv_set_head_out(snb_conv* c, float* d_head_out);
 
 /* Weight gradient of a convolution of the kinds above on the tensor cores (autograd of nn.Conv2d / nn.ConvTranspose2d,
  * torch_train.py:186-189): with X the forward input and dY the gradient of the forward output (both NHWC bf16 slabs),

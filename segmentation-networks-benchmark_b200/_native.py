@@ -96,6 +96,7 @@ SIGNATURES = {
     "snb_conv_launch": (c_int, [c_vp, c_vp]),
     "snb_conv_destroy": (None, [c_vp]),
     "snb_conv_flops": (ctypes.c_double, [c_vp]),
+    "snb_conv_set_head_out": (c_int, [c_vp, c_vp]),
     "snb_wgrad_create": (c_int, [ctypes.POINTER(WgradDesc), ctypes.POINTER(c_vp)]),
     "snb_wgrad_launch": (c_int, [c_vp, c_vp]),
     "snb_wgrad_destroy": (None, [c_vp]),

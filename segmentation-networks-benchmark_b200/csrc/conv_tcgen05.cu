@@ -1707,6 +1707,13 @@ extern "C" void snb_conv_destroy(snb_conv* c) { delete c; }
 
 extern "C" double snb_conv_flops(const snb_conv* c) { return c ? c->flops : 0.0; }
 
+extern "C" int snb_conv_set_head_out(snb_conv* c, float* d_head_out) {
+  if (!c || !d_head_out) return fail(SNB_E_INVALID, "snb_conv_set_head_out: null argument");
+  if (c->params.head_w == nullptr) return fail(SNB_E_INVALID, "snb_conv_set_head_out: this convolution has no fused head");
+  c->params.head_out = d_head_out;
+  return SNB_OK;
+}
+
 #ifdef SNB_CONV_PROFILE
 // profiling builds only (tools/build_rev.py --profile): read (and clear) the wait-cycle counters of conv_halo_kernel
 extern "C" __attribute__((visibility("default"))) int snb_debug_conv_profile(unsigned long long* out8, int reset) {

@@ -14,6 +14,14 @@ import torch
 from . import _native as N
 
 
+def head_op(plan):
+    """The op of an inference plan that writes plan.out (the conv with the fused 1x1 head), or None."""
+    for op in reversed(getattr(plan, "ops", [])):
+        if getattr(op, "has_head", False):
+            return op
+    return None
+
+
 # ------------------------------------------------------------------------------------------- precision
 PRECISIONS = {"bf16": torch.bfloat16, "tf32": torch.float32}
 
@@ -112,6 +120,7 @@ class ConvOp:
     def __init__(self, kind, src, dst, weight, bias, relu=True, head=None, pool_dst=None, upsample2x=False, pre=None,
                  act_slope=0.0, residual=None, res_after_act=False, valid=False, real=None):
         self.keep = (src, dst, weight, bias, head, pool_dst, pre, residual)
+        self.has_head = head is not None
         d = N.ConvDesc()
         d.kind = kind
         d.dtype = N.CONV_TF32 if src.slab.t.dtype == torch.float32 else N.CONV_BF16
@@ -161,6 +170,10 @@ class ConvOp:
 
     def __call__(self, stream):
         N.check(N.lib().snb_conv_launch(self._h, stream))
+
+    def set_head_out(self, ptr):
+        """Fused-head convs only: the float [n][h][w] output goes to `ptr` (a device address) from the next launch on."""
+        N.check(N.lib().snb_conv_set_head_out(self._h, N.c_vp(ptr)))
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import engine
 from .lib.augmentations import NormalizeImage, find_normalize
 from .lib.tiles import ImageSlicer
 
@@ -47,7 +48,10 @@ class TiledPredictor:
             self.plan = model.plan(self.batch, patch_size, patch_size, sigmoid=True)
             self.weight = self.slicer.weight_on_device(self.device)
             T = patch_size
-            self.probs = torch.empty((self.n_tiles, self.views, T, T, 1), dtype=torch.float32, device=self.device)
+            # (padded to whole network launches: the last layer writes its batch straight into this buffer)
+            n_alloc = max(self.n_tiles, self.tile_begin + -(-(self.tile_end - self.tile_begin) // self.batch) * self.batch)
+            self._probs_store = torch.empty((n_alloc, self.views, T, T, 1), dtype=torch.float32, device=self.device)
+            self.probs = self._probs_store[:self.n_tiles]
             h, w = image_shape[0], image_shape[1]
             self.merged = torch.empty((h, w, 1), dtype=torch.float32, device=self.device)
             self.mask = torch.empty((h, w, 1), dtype=torch.uint8, device=self.device)
@@ -82,8 +86,13 @@ class TiledPredictor:
 
     def _enqueue(self, d_image):
         lib, st = N.lib(), N.stream_ptr()
+        # Without TTA a batch of probability tiles is contiguous in self.probs: the fused head of the last layer writes it
+        # there directly (no copy kernel per batch).  A partial last batch may only do so when the tile slots it spills into
+        # are padding, i.e. this predictor owns the tail of the crop list.
+        head = engine.head_op(self.plan) if (self.views == 1 and hasattr(self, "_probs_store")) else None
         for begin in range(self.tile_begin, self.tile_end, self.batch):
             count = min(self.batch, self.tile_end - begin)
+            direct = head is not None and (count == self.batch or self.tile_end == self.n_tiles)
             for v in range(self.views):
                 x_nchw = getattr(self.plan, "x_nchw", None)
                 if x_nchw is not None:      # plans that take normalised float NCHW tiles (LinkNet34's 7x7 stem)
@@ -92,8 +101,14 @@ class TiledPredictor:
                     layout, target = self.plan.input_layout()
                 N.check(lib.snb_split_norm_u8(self.slicer.handle, N.ptr(d_image), self.channels, N.ptr(self.lut), v,
                                               layout, N.c_vp(target), begin, count, st))
-                out = self.plan.run()
-                self.probs[begin:begin + count, v, :, :, 0].copy_(out[:count])
+                if direct:
+                    head.set_head_out(self._probs_store[begin].data_ptr())
+                    self.plan.run()
+                else:
+                    out = self.plan.run()
+                    self.probs[begin:begin + count, v, :, :, 0].copy_(out[:count])
+        if head is not None:
+            head.set_head_out(self.plan.out.data_ptr())      # the plan is shared (model.plan cache): leave it as it was
         if self.do_merge:
             self.merge_probs()
         return self.merged, self.mask
