@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-end measurement pass on one B200: tests (with parity margins), smoke, headline bench (+ reference arm), secondary
-# workloads, HBM kernels, training step, conv role profile, ncu launch list of the bench command and one ncu --set full
-# capture of the conv kernels at the bench's tiles per launch.  Outputs under gpurun_out/r02_* (copy summaries to profiles/).
+# workloads, HBM kernels, training step, role profiles (UNet16 and FCDenseNet67; needs tools/build_rev.py --profile), ncu launch
+# list of the bench command and one ncu metrics pass over the conv kernels at the bench's tiles per launch.
+# Outputs under gpurun_out/r02_* (copy summaries to profiles/; tools/fill_docs.py fills the documents from them).
 R=r02
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/${R}_smi.txt 2>&1
